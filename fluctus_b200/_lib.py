@@ -1,0 +1,69 @@
+"""ctypes binding of libfluctus_b200.so (C ABI: include/fluctus_b200.h).  Fails loudly when the library is absent:
+there is no Python or CPU implementation of the path behind it."""
+import ctypes as C
+import os
+
+from .structs import QueueCounters, RenderParams, RenderStats64
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfluctus_b200.so")
+
+_P = C.c_void_p
+_SIGNATURES = {
+    # name: (restype, argtypes)
+    "flx_version": (C.c_char_p, []),
+    "flx_last_error": (C.c_char_p, [_P]),
+    "flx_create": (C.c_int, [C.c_int, C.c_uint32, C.POINTER(_P)]),
+    "flx_destroy": (None, [_P]),
+    "flx_upload_scene": (C.c_int, [_P, _P, C.c_uint32, _P, C.c_uint32, _P, C.c_uint32, _P, C.c_uint32, _P, C.c_uint32, _P, C.c_size_t]),
+    "flx_upload_envmap": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _P]),
+    "flx_resize": (C.c_int, [_P, C.c_uint32, C.c_uint32]),
+    "flx_update_params": (C.c_int, [_P, C.POINTER(RenderParams)]),
+    "flx_enqueue_reset": (C.c_int, [_P]),
+    "flx_enqueue_raygen": (C.c_int, [_P]),
+    "flx_enqueue_extrays": (C.c_int, [_P]),
+    "flx_enqueue_shadowrays": (C.c_int, [_P]),
+    "flx_enqueue_logic": (C.c_int, [_P, C.c_int]),
+    "flx_enqueue_materials": (C.c_int, [_P]),
+    "flx_enqueue_clear_queues": (C.c_int, [_P]),
+    "flx_enqueue_get_counters": (C.c_int, [_P, C.POINTER(QueueCounters)]),
+    "flx_finish": (C.c_int, [_P]),
+    "flx_update_pixel_index": (C.c_int, [_P, C.c_uint32, C.c_uint32]),
+    "flx_reset_pixel_index": (C.c_int, [_P]),
+    "flx_num_tasks": (C.c_uint32, [_P]),
+    "flx_render": (C.c_int, [_P, C.c_uint32]),
+    "flx_reset_stats": (C.c_int, [_P]),
+    "flx_get_stats": (C.c_int, [_P, C.POINTER(RenderStats64)]),
+    "flx_set_profiling": (C.c_int, [_P, C.c_int]),
+    "flx_get_kernel_ms": (C.c_int, [_P, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]),
+    "flx_read_pixels": (C.c_int, [_P, _P, C.c_size_t]),
+    "flx_read_tasks": (C.c_int, [_P, _P]),
+    "flx_write_tasks": (C.c_int, [_P, _P]),
+    "flx_read_queue": (C.c_int, [_P, C.c_int, _P, C.c_uint32]),
+    "flx_write_queue": (C.c_int, [_P, C.c_int, _P, C.c_uint32]),
+    "flx_write_counters": (C.c_int, [_P, C.POINTER(QueueCounters)]),
+    "flx_set_tile": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "flx_tile_pixels": (C.c_uint32, [_P]),
+    "flx_comm_unique_id": (C.c_int, [_P]),
+    "flx_comm_init": (C.c_int, [_P, _P, C.c_int, C.c_int]),
+    "flx_gather_pixels": (C.c_int, [_P, C.c_int, _P]),
+    "flx_comm_destroy": (C.c_int, [_P]),
+    "flx_device_bytes": (C.c_size_t, [_P]),
+}
+EXPORTS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(nvcc, sm_100a). fluctus_b200 has no fallback implementation." % LIB_PATH)
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError here = the library does not match include/fluctus_b200.h
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib

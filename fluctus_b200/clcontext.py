@@ -1,0 +1,207 @@
+"""CLContext -- host-side mirror of the reference's device context for the wavefront path.
+
+Same method names, argument meaning and error behaviour as the reference class (src/clcontext.hpp:26-211):
+methods enqueue work asynchronously on one in-order queue, `finishQueue` is the only synchronisation point, and
+failures raise (the reference throws std::runtime_error through clt::check, ext/CLT/src/utils.cpp:22-29).
+Everything is forwarded to the C ABI in include/fluctus_b200.h; nothing is computed here.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .structs import QUEUE_NAMES, QueueCounters, RenderParams, RenderStats64
+
+
+class FluctusError(RuntimeError):
+    pass
+
+
+KERNEL_IDS = {"reset": 0, "raygen": 1, "extrays": 2, "shadowrays": 3, "logic": 4, "materials": 5, "end_iteration": 6}
+
+
+class CLContext:
+    def __init__(self, num_tasks=1 << 20, device=0):  # wfBufferSize default 1<<20 (src/settings.cpp:20)
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        rc = self._lib.flx_create(int(device), int(num_tasks), C.byref(self._h))
+        if rc != 0:
+            msg = self._lib.flx_last_error(None)
+            self._h = C.c_void_p()
+            raise FluctusError("flx_create failed (%d): %s" % (rc, msg.decode() if msg else "?"))
+        self.NUM_TASKS = int(num_tasks)
+        self._keep = []
+
+    # ---- plumbing
+    def _check(self, rc, what):
+        if rc != 0:
+            msg = self._lib.flx_last_error(self._h)
+            raise FluctusError("%s failed (%d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.flx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @staticmethod
+    def _ptr(a):
+        return a.ctypes.data_as(C.c_void_p) if a is not None and a.size else None
+
+    # ---- setup (clcontext.hpp:62-79)
+    def uploadSceneData(self, scene):
+        """reference: CLContext::uploadSceneData(BVH*, Scene*) -- here the already-built arrays (fluctus_b200.SceneData)."""
+        self._check(self._lib.flx_upload_scene(self._h, self._ptr(scene.tris), len(scene.tris), self._ptr(scene.indices), len(scene.indices),
+                                               self._ptr(scene.nodes), len(scene.nodes), self._ptr(scene.materials), len(scene.materials),
+                                               self._ptr(scene.tex_desc), len(scene.tex_desc), self._ptr(scene.tex_data), scene.tex_data.nbytes),
+                    "uploadSceneData")
+
+    def createEnvMap(self, env):
+        self._check(self._lib.flx_upload_envmap(self._h, self._ptr(env.rgb), env.width, env.height, self._ptr(env.prob), self._ptr(env.alias),
+                                                self._ptr(env.pdf)), "createEnvMap")
+
+    def setupPixelStorage(self, width, height):
+        self._check(self._lib.flx_resize(self._h, int(width), int(height)), "setupPixelStorage")
+
+    def updateParams(self, params):
+        assert isinstance(params, RenderParams)
+        self._check(self._lib.flx_update_params(self._h, C.byref(params)), "updateParams")
+
+    def recompileKernels(self, setArgs=False):
+        """reference: clcontext.cpp:852-874. Specialisations are chosen from the params at launch; nothing to rebuild."""
+
+    # ---- the wavefront stages (clcontext.hpp:43-48). `params` is accepted and ignored, like in the reference,
+    # where the kernels read the device copy written by updateParams.
+    def enqueueWfResetKernel(self, params=None):
+        self._check(self._lib.flx_enqueue_reset(self._h), "enqueueWfResetKernel")
+
+    def enqueueWfRaygenKernel(self, params=None):
+        self._check(self._lib.flx_enqueue_raygen(self._h), "enqueueWfRaygenKernel")
+
+    def enqueueWfExtRayKernel(self, params=None):
+        self._check(self._lib.flx_enqueue_extrays(self._h), "enqueueWfExtRayKernel")
+
+    def enqueueWfShadowRayKernel(self, params=None):
+        self._check(self._lib.flx_enqueue_shadowrays(self._h), "enqueueWfShadowRayKernel")
+
+    def enqueueWfLogicKernel(self, params=None, firstIteration=False):
+        self._check(self._lib.flx_enqueue_logic(self._h, 1 if firstIteration else 0), "enqueueWfLogicKernel")
+
+    def enqueueWfMaterialKernels(self, params=None):
+        self._check(self._lib.flx_enqueue_materials(self._h), "enqueueWfMaterialKernels")
+
+    # ---- queue bookkeeping (clcontext.hpp:53-57, 71)
+    def enqueueClearWfQueues(self):
+        self._check(self._lib.flx_enqueue_clear_queues(self._h), "enqueueClearWfQueues")
+
+    def enqueueGetCounters(self, cnt):
+        """cnt: a QueueCounters instance; filled in when finishQueue returns (reference: non-blocking read, clcontext.cpp:668-671)."""
+        self._keep.append(cnt)
+        self._check(self._lib.flx_enqueue_get_counters(self._h, C.byref(cnt)), "enqueueGetCounters")
+
+    def finishQueue(self):
+        self._check(self._lib.flx_finish(self._h), "finishQueue")
+        self._keep.clear()
+
+    def updatePixelIndex(self, numPixels, numNewPaths):
+        self._check(self._lib.flx_update_pixel_index(self._h, int(numPixels), int(numNewPaths)), "updatePixelIndex")
+
+    def resetPixelIndex(self):
+        self._check(self._lib.flx_reset_pixel_index(self._h), "resetPixelIndex")
+
+    def getNumTasks(self):
+        return int(self._lib.flx_num_tasks(self._h))
+
+    # ---- fused loop + statistics (new; see fluctus_b200.h)
+    def render(self, iterations):
+        self._check(self._lib.flx_render(self._h, int(iterations)), "render")
+
+    def resetStats(self):
+        self._check(self._lib.flx_reset_stats(self._h), "resetStats")
+
+    def getStats(self):
+        s = RenderStats64()
+        self._check(self._lib.flx_get_stats(self._h, C.byref(s)), "getStats")
+        return s
+
+    def setProfiling(self, enabled):
+        self._check(self._lib.flx_set_profiling(self._h, 1 if enabled else 0), "setProfiling")
+
+    def checkTracingPerf(self):
+        """reference: clcontext.cpp:673-701 -- per-kernel device time; returns {name: (total_ms, launches)}."""
+        out = {}
+        for name, kid in KERNEL_IDS.items():
+            ms, n = C.c_float(), C.c_uint32()
+            self._check(self._lib.flx_get_kernel_ms(self._h, kid, C.byref(ms), C.byref(n)), "checkTracingPerf")
+            out[name] = (ms.value, n.value)
+        return out
+
+    # ---- read-back
+    def tilePixels(self):
+        return int(self._lib.flx_tile_pixels(self._h))
+
+    def readPixels(self):
+        n = self.tilePixels()
+        out = np.empty((n, 4), np.float32)
+        self._check(self._lib.flx_read_pixels(self._h, self._ptr(out), n), "readPixels")
+        return out
+
+    def readTasks(self):
+        out = np.empty((64, self.NUM_TASKS), np.uint32)
+        self._check(self._lib.flx_read_tasks(self._h, self._ptr(out)), "readTasks")
+        return out
+
+    def writeTasks(self, slots):
+        slots = np.ascontiguousarray(slots, np.uint32)
+        assert slots.shape == (64, self.NUM_TASKS)
+        self._check(self._lib.flx_write_tasks(self._h, self._ptr(slots)), "writeTasks")
+
+    def readQueue(self, name, n=None):
+        out = np.empty(self.NUM_TASKS if n is None else int(n), np.uint32)
+        self._check(self._lib.flx_read_queue(self._h, QUEUE_NAMES.index(name), self._ptr(out), len(out)), "readQueue")
+        return out
+
+    def writeQueue(self, name, entries):
+        entries = np.ascontiguousarray(entries, np.uint32)
+        self._check(self._lib.flx_write_queue(self._h, QUEUE_NAMES.index(name), self._ptr(entries), len(entries)), "writeQueue")
+
+    def writeCounters(self, cnt):
+        self._check(self._lib.flx_write_counters(self._h, C.byref(cnt)), "writeCounters")
+
+    def readCounters(self):
+        cnt = QueueCounters()
+        self.enqueueGetCounters(cnt)
+        self.finishQueue()
+        return cnt
+
+    def deviceBytes(self):
+        return int(self._lib.flx_device_bytes(self._h))
+
+    # ---- multi-GPU
+    def setTile(self, part, n_parts, stripe_rows=8):
+        self._check(self._lib.flx_set_tile(self._h, int(part), int(n_parts), int(stripe_rows)), "setTile")
+
+    def commUniqueId(self):
+        buf = (C.c_char * 128)()
+        rc = self._lib.flx_comm_unique_id(buf)
+        if rc != 0:
+            raise FluctusError("flx_comm_unique_id failed (%d): %s" % (rc, (self._lib.flx_last_error(None) or b"?").decode()))
+        return bytes(buf)
+
+    def commInit(self, unique_id, rank, nranks):
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._check(self._lib.flx_comm_init(self._h, buf, int(rank), int(nranks)), "commInit")
+
+    def gatherPixels(self, root=0, out=None):
+        self._check(self._lib.flx_gather_pixels(self._h, int(root), self._ptr(out) if out is not None else None), "gatherPixels")

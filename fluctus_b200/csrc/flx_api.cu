@@ -1,0 +1,1105 @@
+// flx_api.cu -- the C ABI of include/fluctus_b200.h: device memory, scene upload + BVH repack,
+// stage launches on one in-order stream, counters/stats/timing, tiling and the NCCL gather.
+// Mirrors the method set of the reference's CLContext (src/clcontext.hpp:26-211; implementation
+// src/clcontext.cpp) -- each function below names the method it stands in for.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "flx_kernels.cuh"
+
+static_assert(sizeof(flx_RenderParams) == 240, "RenderParams layout (geom.h:163-180)");
+static_assert(sizeof(flx_AreaLight) == 96 && sizeof(flx_Camera) == 80, "AreaLight/Camera layout");
+static_assert(sizeof(flx_Node) == 48 && sizeof(flx_Triangle) == 160 && sizeof(flx_Material) == 80, "scene layouts");
+static_assert(sizeof(flx_TexDescriptor) == 12 && sizeof(flx_QueueCounters) == 32, "descriptor/counter layouts");
+static_assert(offsetof(flx_RenderParams, camera) == 96 && offsetof(flx_RenderParams, width) == 184 && offsetof(flx_RenderParams, worldRadius) == 228, "RenderParams offsets");
+static_assert(offsetof(flx_Node, nPrims) == 40 && offsetof(flx_Triangle, matId) == 144 && offsetof(flx_Material, type) == 68, "field offsets");
+
+struct Id128 // ncclUniqueId is a 128-byte opaque struct passed by value
+{
+    char bytes[128];
+};
+
+namespace
+{
+thread_local std::string g_create_error;
+
+struct EventPair
+{
+    cudaEvent_t a, b;
+    int kernel;
+};
+
+// NCCL entry points resolved at run time (the process usually already holds torch's libnccl.so.2)
+struct NcclApi
+{
+    void *lib = nullptr;
+    int (*GetUniqueId)(void *) = nullptr;
+    int (*CommInitRank)(void **, int, Id128, int) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*Send)(const void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*Recv)(void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+} // namespace
+
+struct flx_ctx
+{
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    uint32_t numTasks = 0;
+    std::string error;
+
+    // path state
+    uint32_t *tasks = nullptr;
+    uint32_t *queues[8] = {};
+    flx_QueueCounters *counters = nullptr, *snapshot = nullptr;
+    flx_RenderStats64 *stats = nullptr;
+    uint32_t *currPixelIdx = nullptr;
+    unsigned long long *scanTiles = nullptr;
+    uint32_t *scanTicket = nullptr;
+    uint32_t numScanTiles = 0;
+    uint32_t hostPixelIdx = 0; // CLContext::pixelIdx (clcontext.hpp:164)
+
+    // pinned staging for asynchronous counter reads
+    flx_QueueCounters *pinnedCounters = nullptr;
+    std::vector<std::pair<int, flx_QueueCounters *>> pendingCounterReads; // (slot in pinned ring, host destination)
+    static const int kCounterRing = 64;
+    int counterRingPos = 0;
+
+    // scene
+    flx_Triangle *tris = nullptr;
+    flx_Material *materials = nullptr;
+    flx_TexDescriptor *texDesc = nullptr;
+    uint8_t *texData = nullptr;
+    float4 *tnodes = nullptr, *ttris = nullptr;
+    int rootRef = 0;
+    uint32_t nTris = 0, nTNodes = 0, nTTris = 0;
+    bool sceneReady = false;
+    size_t sceneBytes = 0;
+
+    // environment map
+    float *envRGBA = nullptr, *probTable = nullptr, *pdfTable = nullptr;
+    int32_t *aliasTable = nullptr;
+    int envW = 1, envH = 1;
+
+    // image
+    float *pixels = nullptr, *denoiserAlbedo = nullptr, *denoiserNormal = nullptr;
+    uint32_t width = 0, height = 0, tilePixels = 0;
+    uint32_t part = 0, nParts = 1, stripeRows = 1;
+    float *gatherBuf = nullptr, *fullImage = nullptr; // rank-major gather target and de-interleaved full image (root)
+    size_t gatherBufPixels = 0;
+
+    flx_RenderParams params;
+    bool paramsSet = false;
+    float tanHalfFov = 0.0f;
+
+    // timing
+    bool profiling = false;
+    std::vector<EventPair> pendingEvents, freeEvents;
+    double kernelMs[FLX_K_COUNT] = {};
+    uint32_t kernelLaunches[FLX_K_COUNT] = {};
+
+    // NCCL
+    NcclApi nccl;
+    void *comm = nullptr;
+    int rank = 0, nranks = 1;
+};
+
+namespace
+{
+int fail(flx_ctx *ctx, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx)
+        ctx->error = buf;
+    else
+        g_create_error = buf;
+    return code;
+}
+
+#define CU(call)                                                                                                       \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        cudaError_t e_ = (call);                                                                                       \
+        if (e_ != cudaSuccess)                                                                                         \
+            return fail(ctx, (int)e_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);     \
+    } while (0)
+
+#define REQUIRE(cond, msg)                                                                                             \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        if (!(cond))                                                                                                   \
+            return fail(ctx, FLX_E_INVALID, "%s", msg);                                                                \
+    } while (0)
+
+template <class T> void freeDev(T *&p)
+{
+    if (p)
+        cudaFree(p);
+    p = nullptr;
+}
+
+Frame makeFrame(const flx_ctx *c)
+{
+    Frame f;
+    f.tasks.base = c->tasks;
+    f.tasks.n = c->numTasks;
+    f.counters = c->counters;
+    for (int i = 0; i < 8; i++)
+        f.queues[i] = c->queues[i];
+    f.pixels = c->pixels;
+    f.denoiserAlbedo = c->denoiserAlbedo;
+    f.denoiserNormal = c->denoiserNormal;
+    f.currPixelIdx = c->currPixelIdx;
+    f.numTasks = c->numTasks;
+    f.tilePixels = c->tilePixels;
+    f.part = c->part;
+    f.nParts = c->nParts;
+    f.stripeRows = c->stripeRows;
+    f.tanHalfFov = c->tanHalfFov;
+    return f;
+}
+
+SceneView makeScene(const flx_ctx *c)
+{
+    SceneView s;
+    s.tris = c->tris;
+    s.materials = c->materials;
+    s.textures = c->texDesc;
+    s.texData = c->texData;
+    s.envRGBA = c->envRGBA;
+    s.envW = c->envW;
+    s.envH = c->envH;
+    s.probTable = c->probTable;
+    s.aliasTable = c->aliasTable;
+    s.pdfTable = c->pdfTable;
+    return s;
+}
+
+BvhView makeBvh(const flx_ctx *c)
+{
+    BvhView b;
+    b.nodes = c->tnodes;
+    b.tris = c->ttris;
+    b.rootRef = c->rootRef;
+    return b;
+}
+
+IterationState makeIter(const flx_ctx *c)
+{
+    IterationState it;
+    it.counters = c->counters;
+    it.snapshot = c->snapshot;
+    it.stats = c->stats;
+    it.currPixelIdx = c->currPixelIdx;
+    it.tilePixels = c->tilePixels;
+    return it;
+}
+
+uint32_t localRows(uint32_t height, uint32_t part, uint32_t nParts, uint32_t stripeRows)
+{
+    uint32_t rows = 0;
+    for (uint32_t s = part; s * stripeRows < height; s += nParts)
+        rows += std::min(stripeRows, height - s * stripeRows);
+    return rows;
+}
+
+// ---- timing helpers
+struct Timed
+{
+    flx_ctx *c;
+    int k;
+    EventPair ev;
+    bool on;
+    Timed(flx_ctx *ctx, int kernel) : c(ctx), k(kernel), on(ctx->profiling)
+    {
+        if (!on)
+            return;
+        if (!c->freeEvents.empty())
+        {
+            ev = c->freeEvents.back();
+            c->freeEvents.pop_back();
+        }
+        else
+        {
+            cudaEventCreate(&ev.a);
+            cudaEventCreate(&ev.b);
+        }
+        ev.kernel = k;
+        cudaEventRecord(ev.a, c->stream);
+    }
+    ~Timed()
+    {
+        c->kernelLaunches[k]++;
+        if (!on)
+            return;
+        cudaEventRecord(ev.b, c->stream);
+        c->pendingEvents.push_back(ev);
+    }
+};
+
+void drainEvents(flx_ctx *c)
+{
+    for (auto &e : c->pendingEvents)
+    {
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess)
+            c->kernelMs[e.kernel] += ms;
+        c->freeEvents.push_back(e);
+    }
+    c->pendingEvents.clear();
+}
+
+int checkReady(flx_ctx *ctx, bool needScene, bool needImage)
+{
+    if (!ctx)
+        return FLX_E_INVALID;
+    if (!ctx->paramsSet)
+        return fail(ctx, FLX_E_NOT_READY, "flx_update_params has not been called");
+    if (needImage && !ctx->pixels)
+        return fail(ctx, FLX_E_NOT_READY, "flx_resize has not been called");
+    if (needScene && !ctx->sceneReady)
+        return fail(ctx, FLX_E_NOT_READY, "flx_upload_scene has not been called");
+    return 0;
+}
+
+int launchCheck(flx_ctx *ctx, const char *what)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess)
+        return fail(ctx, (int)e, "launch of %s failed: %s", what, cudaGetErrorString(e));
+    return 0;
+}
+
+unsigned streamingGrid(uint32_t n) { return std::max(1u, std::min((n + FLX_BLOCK - 1) / FLX_BLOCK, 148u * 16u)); }
+
+// ---- BVH repack: reference Node[] (48 B, DFS, left = self + 1) + indices + Triangle[] (160 B)
+//      -> TNode[] (64 B, inner nodes only) + TTri[] (48 B per leaf reference). See flx_trace.cuh.
+struct Repacked
+{
+    std::vector<float4> nodes, tris;
+    int rootRef = 0;
+};
+
+int repackBvh(flx_ctx *ctx, const flx_Triangle *tris, uint32_t nTris, const uint32_t *indices, uint32_t nIndices, const flx_Node *nodes, uint32_t nNodes,
+              Repacked &out)
+{
+    std::vector<int> ref(nNodes, 0); // child reference of every reference node
+    // pass 1: number inner nodes in DFS order, lay out leaves' triangles in DFS order
+    uint32_t nInner = 0;
+    size_t nLeafTris = 0;
+    for (uint32_t i = 0; i < nNodes; i++)
+    {
+        if (nodes[i].nPrims == 0)
+        {
+            const uint32_t r = nodes[i].iStartOrRightChild;
+            if (i + 1 >= nNodes || r >= nNodes || r <= i + 1)
+                return fail(ctx, FLX_E_INVALID, "node %u: child links out of range (left %u, right %u, %u nodes)", i, i + 1, r, nNodes);
+            ref[i] = (int)nInner++;
+        }
+        else
+        {
+            const uint32_t s = nodes[i].iStartOrRightChild, n = nodes[i].nPrims;
+            if ((size_t)s + n > nIndices)
+                return fail(ctx, FLX_E_INVALID, "leaf %u: index range [%u,%u) exceeds %u indices", i, s, s + n, nIndices);
+            if (nLeafTris > 0x7ffffff0u)
+                return fail(ctx, FLX_E_INVALID, "too many leaf references");
+            ref[i] = ~(int)nLeafTris;
+            nLeafTris += n;
+        }
+    }
+    out.nodes.assign((size_t)nInner * 4, make_float4(0, 0, 0, 0));
+    out.tris.assign(nLeafTris * 3, make_float4(0, 0, 0, 0));
+    out.rootRef = ref[0];
+    for (uint32_t i = 0; i < nNodes; i++)
+    {
+        if (nodes[i].nPrims == 0)
+        {
+            const flx_Node &L = nodes[i + 1], &R = nodes[nodes[i].iStartOrRightChild];
+            float4 *q = &out.nodes[(size_t)ref[i] * 4];
+            q[0] = make_float4(L.bmin.x, L.bmin.y, L.bmin.z, L.bmax.x);
+            q[1] = make_float4(L.bmax.y, L.bmax.z, R.bmin.x, R.bmin.y);
+            q[2] = make_float4(R.bmin.z, R.bmax.x, R.bmax.y, R.bmax.z);
+            int4 links = make_int4(ref[i + 1], ref[nodes[i].iStartOrRightChild], 0, 0);
+            memcpy(&q[3], &links, sizeof links);
+        }
+        else
+        {
+            const uint32_t s = nodes[i].iStartOrRightChild, n = nodes[i].nPrims;
+            float4 *q = &out.tris[(size_t)(~ref[i]) * 3];
+            for (uint32_t k = 0; k < n; k++, q += 3)
+            {
+                const uint32_t ti = indices[s + k];
+                if (ti >= nTris || ti > 0x7fffffffu)
+                    return fail(ctx, FLX_E_INVALID, "leaf %u references triangle %u of %u", i, ti, nTris);
+                const flx_Triangle &T = tris[ti];
+                uint32_t tag = ti | (k + 1 == n ? 0x80000000u : 0u);
+                float tagf;
+                memcpy(&tagf, &tag, 4);
+                // the float differences below are the ones the reference forms per test (intersect.cl:66-67)
+                q[0] = make_float4(T.v0.p.x, T.v0.p.y, T.v0.p.z, tagf);
+                q[1] = make_float4(T.v1.p.x - T.v0.p.x, T.v1.p.y - T.v0.p.y, T.v1.p.z - T.v0.p.z, 0.0f);
+                q[2] = make_float4(T.v2.p.x - T.v0.p.x, T.v2.p.y - T.v0.p.y, T.v2.p.z - T.v0.p.z, 0.0f);
+            }
+        }
+    }
+    return 0;
+}
+
+template <class T> int uploadArray(flx_ctx *ctx, T *&dst, const T *src, size_t count, size_t minCount = 1)
+{
+    freeDev(dst);
+    const size_t bytes = std::max(count, minCount) * sizeof(T);
+    CU(cudaMalloc(&dst, bytes));
+    CU(cudaMemset(dst, 0, bytes));
+    if (count)
+        CU(cudaMemcpy(dst, src, count * sizeof(T), cudaMemcpyHostToDevice));
+    ctx->sceneBytes += bytes;
+    return 0;
+}
+
+int loadNccl(flx_ctx *ctx)
+{
+    NcclApi &n = ctx->nccl;
+    if (n.lib)
+        return 0;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *nm : names)
+    {
+        n.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (n.lib)
+            break;
+    }
+    if (!n.lib)
+        return fail(ctx, FLX_E_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+#define SYM(field, name)                                                                                              \
+    *(void **)(&n.field) = dlsym(n.lib, name);                                                                         \
+    if (!n.field)                                                                                                      \
+        return fail(ctx, FLX_E_NCCL, "libnccl lacks %s", name);
+    SYM(GetUniqueId, "ncclGetUniqueId")
+    SYM(CommInitRank, "ncclCommInitRank")
+    SYM(CommDestroy, "ncclCommDestroy")
+    SYM(AllGather, "ncclAllGather")
+    SYM(GroupStart, "ncclGroupStart")
+    SYM(GroupEnd, "ncclGroupEnd")
+    SYM(Send, "ncclSend")
+    SYM(Recv, "ncclRecv")
+    SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+    return 0;
+}
+
+// rank-major gathered tiles -> full image rows (inverse of local_pixel_to_xy)
+__global__ void k_deinterleave(const float4 *gathered, float4 *full, uint32_t width, uint32_t height, uint32_t nParts, uint32_t stripeRows, uint32_t maxTilePixels)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= width * height)
+        return;
+    const uint32_t x = i % width, y = i / width;
+    const uint32_t stripe = y / stripeRows, within = y % stripeRows;
+    const uint32_t part = stripe % nParts, localStripe = stripe / nParts;
+    const uint32_t ly = localStripe * stripeRows + within;
+    full[i] = gathered[(size_t)part * maxTilePixels + (size_t)ly * width + x];
+}
+} // namespace
+
+// ================================================================================================ C ABI
+extern "C"
+{
+const char *flx_version(void) { return "fluctus_b200 0.1 (sm_100a)"; }
+
+const char *flx_last_error(const flx_ctx *ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
+
+int flx_create(int device, uint32_t num_tasks, flx_ctx **out)
+{
+    flx_ctx *ctx = nullptr; // for the CU/REQUIRE macros: errors land in the thread-local create message
+    if (!out || num_tasks == 0)
+        return fail(nullptr, FLX_E_INVALID, "flx_create: bad arguments");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, FLX_E_NO_DEVICE, "no CUDA device: %s (this library has no CPU path)", cudaGetErrorString(e));
+    if (device < 0 || device >= count)
+        return fail(nullptr, FLX_E_INVALID, "device %d out of range (%d devices)", device, count);
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(nullptr, FLX_E_UNSUPPORTED_ARCH, "device %d is sm_%d%d; this library carries sm_100a code only", device, prop.major, prop.minor);
+    CU(cudaSetDevice(device));
+    flx_ctx *c = new flx_ctx();
+    c->device = device;
+    c->numTasks = num_tasks;
+    memset(&c->params, 0, sizeof c->params);
+    ctx = c;
+    auto bail = [&](int code) {
+        g_create_error = c->error;
+        flx_destroy(c);
+        return code;
+    };
+#define CUB(call)                                                                                                      \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        cudaError_t e_ = (call);                                                                                       \
+        if (e_ != cudaSuccess)                                                                                         \
+        {                                                                                                              \
+            fail(c, (int)e_, "%s failed: %s", #call, cudaGetErrorString(e_));                                          \
+            return bail((int)e_);                                                                                      \
+        }                                                                                                              \
+    } while (0)
+    CUB(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    const size_t taskBytes = (size_t)num_tasks * FLX_NUM_SLOTS * sizeof(uint32_t); // initMCBuffers, clcontext.cpp:116-141
+    CUB(cudaMalloc(&c->tasks, taskBytes));
+    CUB(cudaMemset(c->tasks, 0, taskBytes));
+    for (int i = 0; i < 8; i++)
+    {
+        CUB(cudaMalloc(&c->queues[i], (size_t)num_tasks * sizeof(uint32_t)));
+        CUB(cudaMemset(c->queues[i], 0, (size_t)num_tasks * sizeof(uint32_t)));
+    }
+    CUB(cudaMalloc(&c->counters, sizeof(flx_QueueCounters)));
+    CUB(cudaMemset(c->counters, 0, sizeof(flx_QueueCounters)));
+    CUB(cudaMalloc(&c->snapshot, sizeof(flx_QueueCounters)));
+    CUB(cudaMemset(c->snapshot, 0, sizeof(flx_QueueCounters)));
+    CUB(cudaMalloc(&c->stats, sizeof(flx_RenderStats64)));
+    CUB(cudaMemset(c->stats, 0, sizeof(flx_RenderStats64)));
+    CUB(cudaMalloc(&c->currPixelIdx, sizeof(uint32_t)));
+    CUB(cudaMemset(c->currPixelIdx, 0, sizeof(uint32_t)));
+    c->numScanTiles = (num_tasks + FLX_LOGIC_TILE - 1) / FLX_LOGIC_TILE;
+    CUB(cudaMalloc(&c->scanTiles, (size_t)c->numScanTiles * sizeof(unsigned long long)));
+    CUB(cudaMalloc(&c->scanTicket, sizeof(uint32_t)));
+    CUB(cudaMallocHost(&c->pinnedCounters, sizeof(flx_QueueCounters) * flx_ctx::kCounterRing));
+    // dummy 1x1 environment map (CLContext::setupScene, clcontext.cpp:513-519)
+    CUB(cudaMalloc(&c->envRGBA, 4 * sizeof(float)));
+    CUB(cudaMemset(c->envRGBA, 0, 4 * sizeof(float)));
+    CUB(cudaMalloc(&c->probTable, sizeof(float)));
+    CUB(cudaMalloc(&c->pdfTable, sizeof(float)));
+    CUB(cudaMalloc(&c->aliasTable, sizeof(int32_t)));
+    CUB(cudaMemset(c->probTable, 0, sizeof(float)));
+    CUB(cudaMemset(c->pdfTable, 0, sizeof(float)));
+    CUB(cudaMemset(c->aliasTable, 0, sizeof(int32_t)));
+    CUB(cudaStreamSynchronize(c->stream));
+#undef CUB
+    *out = c;
+    return 0;
+}
+
+void flx_destroy(flx_ctx *c)
+{
+    if (!c)
+        return;
+    cudaSetDevice(c->device);
+    if (c->stream)
+        cudaStreamSynchronize(c->stream);
+    flx_comm_destroy(c);
+    drainEvents(c);
+    for (auto &e : c->freeEvents)
+    {
+        cudaEventDestroy(e.a);
+        cudaEventDestroy(e.b);
+    }
+    freeDev(c->tasks);
+    for (int i = 0; i < 8; i++)
+        freeDev(c->queues[i]);
+    freeDev(c->counters);
+    freeDev(c->snapshot);
+    freeDev(c->stats);
+    freeDev(c->currPixelIdx);
+    freeDev(c->scanTiles);
+    freeDev(c->scanTicket);
+    if (c->pinnedCounters)
+        cudaFreeHost(c->pinnedCounters);
+    freeDev(c->tris);
+    freeDev(c->materials);
+    freeDev(c->texDesc);
+    freeDev(c->texData);
+    freeDev(c->tnodes);
+    freeDev(c->ttris);
+    freeDev(c->envRGBA);
+    freeDev(c->probTable);
+    freeDev(c->pdfTable);
+    freeDev(c->aliasTable);
+    freeDev(c->pixels);
+    freeDev(c->denoiserAlbedo);
+    freeDev(c->denoiserNormal);
+    freeDev(c->gatherBuf);
+    freeDev(c->fullImage);
+    if (c->stream)
+        cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+uint32_t flx_num_tasks(const flx_ctx *ctx) { return ctx ? ctx->numTasks : 0; }
+uint32_t flx_tile_pixels(const flx_ctx *ctx) { return ctx ? ctx->tilePixels : 0; }
+
+size_t flx_device_bytes(const flx_ctx *ctx)
+{
+    if (!ctx)
+        return 0;
+    return (size_t)ctx->numTasks * (FLX_NUM_SLOTS + 8) * 4 + ctx->sceneBytes + (size_t)ctx->tilePixels * 48;
+}
+
+int flx_upload_scene(flx_ctx *ctx, const flx_Triangle *tris, uint32_t n_tris, const uint32_t *indices, uint32_t n_indices, const flx_Node *nodes,
+                     uint32_t n_nodes, const flx_Material *materials, uint32_t n_materials, const flx_TexDescriptor *tex_desc, uint32_t n_tex,
+                     const uint8_t *tex_data, size_t tex_bytes)
+{
+    if (!ctx)
+        return FLX_E_INVALID;
+    REQUIRE(tris && indices && nodes && materials, "flx_upload_scene: null array");
+    REQUIRE(n_tris > 0 && n_indices > 0 && n_nodes > 0 && n_materials > 0, "flx_upload_scene: empty scene");
+    REQUIRE(n_tex == 0 || (tex_desc && tex_data), "flx_upload_scene: texture descriptors without data");
+    for (uint32_t i = 0; i < n_tris; i++)
+        if (tris[i].matId < 0 || (uint32_t)tris[i].matId >= n_materials)
+            return fail(ctx, FLX_E_INVALID, "triangle %u has material %d of %u", i, tris[i].matId, n_materials);
+    for (uint32_t i = 0; i < n_materials; i++)
+    {
+        const int maps[3] = {materials[i].map_Kd, materials[i].map_Ks, materials[i].map_N};
+        for (int m : maps)
+            if (m < -1 || m >= (int)n_tex)
+                return fail(ctx, FLX_E_INVALID, "material %u references texture %d of %u", i, m, n_tex);
+    }
+    for (uint32_t i = 0; i < n_tex; i++)
+        if ((size_t)tex_desc[i].offset + (size_t)tex_desc[i].width * tex_desc[i].height * 4 > tex_bytes || (tex_desc[i].offset & 3u) || tex_desc[i].width == 0 ||
+            tex_desc[i].height == 0)
+            return fail(ctx, FLX_E_INVALID, "texture %u: descriptor outside the %zu-byte blob", i, tex_bytes);
+    Repacked rp;
+    int rc = repackBvh(ctx, tris, n_tris, indices, n_indices, nodes, n_nodes, rp);
+    if (rc)
+        return rc;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->sceneReady = false;
+    ctx->sceneBytes = 0;
+    if ((rc = uploadArray(ctx, ctx->tris, tris, n_tris)))
+        return rc;
+    if ((rc = uploadArray(ctx, ctx->materials, materials, n_materials)))
+        return rc;
+    if ((rc = uploadArray(ctx, ctx->texDesc, tex_desc, n_tex)))
+        return rc;
+    if ((rc = uploadArray(ctx, ctx->texData, tex_data, tex_bytes, 4)))
+        return rc;
+    if ((rc = uploadArray(ctx, ctx->tnodes, rp.nodes.data(), rp.nodes.size(), 4)))
+        return rc;
+    if ((rc = uploadArray(ctx, ctx->ttris, rp.tris.data(), rp.tris.size(), 3)))
+        return rc;
+    ctx->rootRef = rp.rootRef;
+    ctx->nTris = n_tris;
+    ctx->nTNodes = (uint32_t)(rp.nodes.size() / 4);
+    ctx->nTTris = (uint32_t)(rp.tris.size() / 3);
+    ctx->sceneReady = true;
+    return 0;
+}
+
+int flx_upload_envmap(flx_ctx *ctx, const float *rgb, int32_t w, int32_t h, const float *prob, const int32_t *alias, const float *pdf)
+{
+    if (!ctx)
+        return FLX_E_INVALID;
+    REQUIRE(rgb && prob && alias && pdf && w > 0 && h > 0, "flx_upload_envmap: bad arguments");
+    const size_t n = (size_t)w * h;
+    for (size_t i = 0; i < n; i++)
+        if (alias[i] < 0 || (size_t)alias[i] >= n)
+            return fail(ctx, FLX_E_INVALID, "alias table entry %zu = %d out of range", i, alias[i]);
+    std::vector<float> rgba(n * 4); // RGB -> RGBA with alpha 1 (clcontext.cpp:472-487)
+    for (size_t i = 0; i < n; i++)
+    {
+        rgba[4 * i + 0] = rgb[3 * i + 0];
+        rgba[4 * i + 1] = rgb[3 * i + 1];
+        rgba[4 * i + 2] = rgb[3 * i + 2];
+        rgba[4 * i + 3] = 1.0f;
+    }
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    const size_t before = ctx->sceneBytes;
+    int rc;
+    if ((rc = uploadArray(ctx, ctx->envRGBA, rgba.data(), n * 4)))
+        return rc;
+    if ((rc = uploadArray(ctx, ctx->probTable, prob, n)))
+        return rc;
+    if ((rc = uploadArray(ctx, ctx->aliasTable, alias, n)))
+        return rc;
+    if ((rc = uploadArray(ctx, ctx->pdfTable, pdf, n)))
+        return rc;
+    (void)before;
+    ctx->envW = w;
+    ctx->envH = h;
+    return 0;
+}
+
+static int allocImage(flx_ctx *ctx)
+{
+    const uint32_t rows = localRows(ctx->height, ctx->part, ctx->nParts, ctx->stripeRows);
+    ctx->tilePixels = rows * ctx->width;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    freeDev(ctx->pixels);
+    freeDev(ctx->denoiserAlbedo);
+    freeDev(ctx->denoiserNormal);
+    if (ctx->tilePixels == 0)
+        return fail(ctx, FLX_E_INVALID, "tile %u of %u owns no rows of a %ux%u image", ctx->part, ctx->nParts, ctx->width, ctx->height);
+    const size_t bytes = (size_t)ctx->tilePixels * 4 * sizeof(float);
+    CU(cudaMalloc(&ctx->pixels, bytes));
+    CU(cudaMalloc(&ctx->denoiserAlbedo, bytes));
+    CU(cudaMalloc(&ctx->denoiserNormal, bytes));
+    CU(cudaMemset(ctx->pixels, 0, bytes));
+    CU(cudaMemset(ctx->denoiserAlbedo, 0, bytes));
+    CU(cudaMemset(ctx->denoiserNormal, 0, bytes));
+    return 0;
+}
+
+int flx_resize(flx_ctx *ctx, uint32_t width, uint32_t height)
+{
+    if (!ctx)
+        return FLX_E_INVALID;
+    REQUIRE(width > 0 && height > 0 && (uint64_t)width * height < 0x7fffffffull, "flx_resize: bad image size");
+    ctx->width = width;
+    ctx->height = height;
+    return allocImage(ctx);
+}
+
+int flx_set_tile(flx_ctx *ctx, uint32_t part, uint32_t n_parts, uint32_t stripe_rows)
+{
+    if (!ctx)
+        return FLX_E_INVALID;
+    REQUIRE(n_parts > 0 && part < n_parts && stripe_rows > 0, "flx_set_tile: bad arguments");
+    ctx->part = part;
+    ctx->nParts = n_parts;
+    ctx->stripeRows = stripe_rows;
+    if (ctx->width && ctx->height)
+        return allocImage(ctx);
+    return 0;
+}
+
+int flx_update_params(flx_ctx *ctx, const flx_RenderParams *p)
+{
+    if (!ctx)
+        return FLX_E_INVALID;
+    REQUIRE(p != nullptr, "flx_update_params: null params");
+    REQUIRE(p->width > 0 && p->height > 0, "flx_update_params: empty image");
+    if (ctx->pixels && (p->width != ctx->width || p->height != ctx->height))
+        return fail(ctx, FLX_E_INVALID, "params are %ux%u but pixel storage is %ux%u: call flx_resize first", p->width, p->height, ctx->width, ctx->height);
+    ctx->params = *p;
+    ctx->tanHalfFov = flx_tanf(0.5f * p->camera.fov * 3.14159265358979323846f / 180); // toRad, geom.h:22; wf_raygen.cl:50
+    ctx->paramsSet = true;
+    return 0;
+}
+
+int flx_enqueue_reset(flx_ctx *ctx)
+{
+    int rc = checkReady(ctx, false, true);
+    if (rc)
+        return rc;
+    CU(cudaSetDevice(ctx->device));
+    const uint32_t n = std::max(ctx->numTasks, ctx->tilePixels); // clcontext.cpp:767
+    Timed tm(ctx, FLX_K_RESET);
+    k_reset<<<(n + FLX_BLOCK - 1) / FLX_BLOCK, FLX_BLOCK, 0, ctx->stream>>>(makeFrame(ctx), ctx->params);
+    return launchCheck(ctx, "k_reset");
+}
+
+int flx_enqueue_raygen(flx_ctx *ctx)
+{
+    int rc = checkReady(ctx, false, true);
+    if (rc)
+        return rc;
+    CU(cudaSetDevice(ctx->device));
+    Timed tm(ctx, FLX_K_RAYGEN);
+    k_raygen<<<streamingGrid(ctx->numTasks), FLX_BLOCK, 0, ctx->stream>>>(makeFrame(ctx), ctx->params);
+    return launchCheck(ctx, "k_raygen");
+}
+
+int flx_enqueue_extrays(flx_ctx *ctx)
+{
+    int rc = checkReady(ctx, true, true);
+    if (rc)
+        return rc;
+    CU(cudaSetDevice(ctx->device));
+    Timed tm(ctx, FLX_K_EXTRAYS);
+    k_extrays<<<(ctx->numTasks + FLX_TRACE_BLOCK - 1) / FLX_TRACE_BLOCK, FLX_TRACE_BLOCK, 0, ctx->stream>>>(makeFrame(ctx), ctx->params, makeBvh(ctx), ctx->tris);
+    return launchCheck(ctx, "k_extrays");
+}
+
+int flx_enqueue_shadowrays(flx_ctx *ctx)
+{
+    int rc = checkReady(ctx, true, true);
+    if (rc)
+        return rc;
+    CU(cudaSetDevice(ctx->device));
+    Timed tm(ctx, FLX_K_SHADOWRAYS);
+    k_shadowrays<<<(ctx->numTasks + FLX_TRACE_BLOCK - 1) / FLX_TRACE_BLOCK, FLX_TRACE_BLOCK, 0, ctx->stream>>>(makeFrame(ctx), ctx->params, makeBvh(ctx));
+    return launchCheck(ctx, "k_shadowrays");
+}
+
+int flx_enqueue_logic(flx_ctx *ctx, int first_iteration)
+{
+    int rc = checkReady(ctx, true, true);
+    if (rc)
+        return rc;
+    CU(cudaSetDevice(ctx->device));
+    const uint32_t maxId = first_iteration ? std::min(ctx->tilePixels, ctx->numTasks) : ctx->numTasks; // wf_logic.cl:45
+    const uint32_t tiles = (maxId + FLX_LOGIC_TILE - 1) / FLX_LOGIC_TILE;
+    CU(cudaMemsetAsync(ctx->scanTiles, 0, (size_t)tiles * sizeof(unsigned long long), ctx->stream));
+    CU(cudaMemsetAsync(ctx->scanTicket, 0, sizeof(uint32_t), ctx->stream));
+    ScanState scan{ctx->scanTiles, ctx->scanTicket};
+    Timed tm(ctx, FLX_K_LOGIC);
+    if (ctx->params.wfSeparateQueues)
+        k_logic<true><<<tiles, FLX_BLOCK, 0, ctx->stream>>>(makeFrame(ctx), ctx->params, makeScene(ctx), scan, maxId);
+    else
+        k_logic<false><<<tiles, FLX_BLOCK, 0, ctx->stream>>>(makeFrame(ctx), ctx->params, makeScene(ctx), scan, maxId);
+    return launchCheck(ctx, "k_logic");
+}
+
+int flx_enqueue_materials(flx_ctx *ctx)
+{
+    int rc = checkReady(ctx, true, true);
+    if (rc)
+        return rc;
+    CU(cudaSetDevice(ctx->device));
+    const unsigned grid = streamingGrid(ctx->numTasks);
+    const Frame fr = makeFrame(ctx);
+    const SceneView sc = makeScene(ctx);
+    Timed tm(ctx, FLX_K_MATERIALS);
+    if (ctx->params.wfSeparateQueues) // clcontext.cpp:798-812
+    {
+        k_material<FLX_BXDF_DIFFUSE><<<grid, FLX_BLOCK, 0, ctx->stream>>>(fr, sc, Q_DIFFUSE);
+        k_material<FLX_BXDF_GLOSSY><<<grid, FLX_BLOCK, 0, ctx->stream>>>(fr, sc, Q_GLOSSY);
+        k_material<FLX_BXDF_GGX_ROUGH_REFLECTION><<<grid, FLX_BLOCK, 0, ctx->stream>>>(fr, sc, Q_GGXREFL);
+        k_material<FLX_BXDF_GGX_ROUGH_DIELECTRIC><<<grid, FLX_BLOCK, 0, ctx->stream>>>(fr, sc, Q_GGXREFR);
+        k_material<FLX_BXDF_IDEAL_REFLECTION | FLX_BXDF_IDEAL_DIELECTRIC><<<grid, FLX_BLOCK, 0, ctx->stream>>>(fr, sc, Q_DELTA);
+    }
+    else
+    {
+        constexpr int ALL = FLX_BXDF_DIFFUSE | FLX_BXDF_GLOSSY | FLX_BXDF_GGX_ROUGH_REFLECTION | FLX_BXDF_IDEAL_REFLECTION | FLX_BXDF_GGX_ROUGH_DIELECTRIC |
+                            FLX_BXDF_IDEAL_DIELECTRIC | FLX_BXDF_EMISSIVE;
+        k_material<ALL><<<grid, FLX_BLOCK, 0, ctx->stream>>>(fr, sc, Q_DIFFUSE);
+    }
+    return launchCheck(ctx, "k_material");
+}
+
+int flx_enqueue_clear_queues(flx_ctx *ctx)
+{
+    if (!ctx)
+        return FLX_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemsetAsync(ctx->counters, 0, sizeof(flx_QueueCounters), ctx->stream));
+    return 0;
+}
+
+int flx_enqueue_get_counters(flx_ctx *ctx, flx_QueueCounters *host_out)
+{
+    if (!ctx)
+        return FLX_E_INVALID;
+    REQUIRE(host_out != nullptr, "flx_enqueue_get_counters: null destination");
+    CU(cudaSetDevice(ctx->device));
+    if ((int)ctx->pendingCounterReads.size() >= flx_ctx::kCounterRing)
+    {
+        int rc = flx_finish(ctx);
+        if (rc)
+            return rc;
+    }
+    const int slot = ctx->counterRingPos;
+    ctx->counterRingPos = (ctx->counterRingPos + 1) % flx_ctx::kCounterRing;
+    CU(cudaMemcpyAsync(ctx->pinnedCounters + slot, ctx->counters, sizeof(flx_QueueCounters), cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->pendingCounterReads.push_back({slot, host_out});
+    return 0;
+}
+
+int flx_finish(flx_ctx *ctx)
+{
+    if (!ctx)
+        return FLX_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (auto &r : ctx->pendingCounterReads)
+        *r.second = ctx->pinnedCounters[r.first];
+    ctx->pendingCounterReads.clear();
+    drainEvents(ctx);
+    return 0;
+}
+
+int flx_update_pixel_index(flx_ctx *ctx, uint32_t num_pixels, uint32_t num_new_paths)
+{
+    if (!ctx)
+        return FLX_E_INVALID;
+    REQUIRE(num_pixels > 0, "flx_update_pixel_index: zero pixels");
+    CU(cudaSetDevice(ctx->device));
+    // the device copy is authoritative (flx_render advances it there); fetch, advance, write back
+    CU(cudaMemcpyAsync(&ctx->hostPixelIdx, ctx->currPixelIdx, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->hostPixelIdx = (ctx->hostPixelIdx + num_new_paths) % num_pixels; // clcontext.cpp:891-895
+    CU(cudaMemcpyAsync(ctx->currPixelIdx, &ctx->hostPixelIdx, sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int flx_reset_pixel_index(flx_ctx *ctx)
+{
+    if (!ctx)
+        return FLX_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    ctx->hostPixelIdx = 0;
+    CU(cudaMemsetAsync(ctx->currPixelIdx, 0, sizeof(uint32_t), ctx->stream));
+    return 0;
+}
+
+int flx_render(flx_ctx *ctx, uint32_t n_iterations)
+{
+    int rc = checkReady(ctx, true, true);
+    if (rc)
+        return rc;
+    CU(cudaSetDevice(ctx->device));
+    const IterationState it = makeIter(ctx);
+    for (uint32_t i = 0; i < n_iterations; i++) // tracer.cpp:433-439, 465
+    {
+        if ((rc = flx_enqueue_logic(ctx, 0)))
+            return rc;
+        if ((rc = flx_enqueue_raygen(ctx)))
+            return rc;
+        if ((rc = flx_enqueue_materials(ctx)))
+            return rc;
+        k_snapshot_counters<<<1, 32, 0, ctx->stream>>>(it);
+        if ((rc = flx_enqueue_extrays(ctx)))
+            return rc;
+        if ((rc = flx_enqueue_shadowrays(ctx)))
+            return rc;
+        {
+            Timed tm(ctx, FLX_K_END_ITERATION);
+            k_end_iteration<<<1, 32, 0, ctx->stream>>>(it);
+        }
+        if ((rc = launchCheck(ctx, "k_end_iteration")))
+            return rc;
+    }
+    return 0;
+}
+
+int flx_reset_stats(flx_ctx *ctx)
+{
+    if (!ctx)
+        return FLX_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    drainEvents(ctx);
+    CU(cudaMemsetAsync(ctx->stats, 0, sizeof(flx_RenderStats64), ctx->stream));
+    for (int k = 0; k < FLX_K_COUNT; k++)
+    {
+        ctx->kernelMs[k] = 0.0;
+        ctx->kernelLaunches[k] = 0;
+    }
+    return 0;
+}
+
+int flx_get_stats(flx_ctx *ctx, flx_RenderStats64 *out)
+{
+    if (!ctx)
+        return FLX_E_INVALID;
+    REQUIRE(out != nullptr, "flx_get_stats: null destination");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(out, ctx->stats, sizeof *out, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int flx_set_profiling(flx_ctx *ctx, int enabled)
+{
+    if (!ctx)
+        return FLX_E_INVALID;
+    ctx->profiling = enabled != 0;
+    return 0;
+}
+
+int flx_get_kernel_ms(flx_ctx *ctx, int kernel_id, float *total_ms, uint32_t *launches)
+{
+    if (!ctx)
+        return FLX_E_INVALID;
+    REQUIRE(kernel_id >= 0 && kernel_id < FLX_K_COUNT, "flx_get_kernel_ms: bad kernel id");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    drainEvents(ctx);
+    if (total_ms)
+        *total_ms = (float)ctx->kernelMs[kernel_id];
+    if (launches)
+        *launches = ctx->kernelLaunches[kernel_id];
+    return 0;
+}
+
+int flx_read_pixels(flx_ctx *ctx, float *rgba, size_t n_pixels)
+{
+    if (!ctx)
+        return FLX_E_INVALID;
+    REQUIRE(rgba != nullptr, "flx_read_pixels: null destination");
+    REQUIRE(ctx->pixels && n_pixels <= ctx->tilePixels, "flx_read_pixels: more pixels requested than the context owns");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(rgba, ctx->pixels, n_pixels * 4 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int flx_read_tasks(flx_ctx *ctx, uint32_t *slots_out)
+{
+    if (!ctx)
+        return FLX_E_INVALID;
+    REQUIRE(slots_out != nullptr, "flx_read_tasks: null destination");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(slots_out, ctx->tasks, (size_t)ctx->numTasks * FLX_NUM_SLOTS * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int flx_write_tasks(flx_ctx *ctx, const uint32_t *slots_in)
+{
+    if (!ctx)
+        return FLX_E_INVALID;
+    REQUIRE(slots_in != nullptr, "flx_write_tasks: null source");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(ctx->tasks, slots_in, (size_t)ctx->numTasks * FLX_NUM_SLOTS * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int flx_read_queue(flx_ctx *ctx, int queue_id, uint32_t *out, uint32_t max_entries)
+{
+    if (!ctx)
+        return FLX_E_INVALID;
+    REQUIRE(queue_id >= 0 && queue_id < 8 && out, "flx_read_queue: bad arguments");
+    CU(cudaSetDevice(ctx->device));
+    const uint32_t n = std::min(max_entries, ctx->numTasks);
+    CU(cudaMemcpyAsync(out, ctx->queues[queue_id], (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int flx_write_queue(flx_ctx *ctx, int queue_id, const uint32_t *entries, uint32_t n)
+{
+    if (!ctx)
+        return FLX_E_INVALID;
+    REQUIRE(queue_id >= 0 && queue_id < 8 && (entries || n == 0) && n <= ctx->numTasks, "flx_write_queue: bad arguments");
+    CU(cudaSetDevice(ctx->device));
+    if (n)
+        CU(cudaMemcpyAsync(ctx->queues[queue_id], entries, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int flx_write_counters(flx_ctx *ctx, const flx_QueueCounters *in)
+{
+    if (!ctx)
+        return FLX_E_INVALID;
+    REQUIRE(in != nullptr, "flx_write_counters: null source");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(ctx->counters, in, sizeof *in, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ---- NCCL gather of the per-tile radiance buffers: the only collective of the path
+int flx_comm_unique_id(void *out128)
+{
+    flx_ctx tmp;
+    flx_ctx *ctx = &tmp;
+    int rc = loadNccl(ctx);
+    if (rc)
+    {
+        g_create_error = tmp.error;
+        return rc;
+    }
+    int r = tmp.nccl.GetUniqueId(out128);
+    if (r != 0)
+    {
+        g_create_error = std::string("ncclGetUniqueId: ") + tmp.nccl.GetErrorString(r);
+        return FLX_E_NCCL;
+    }
+    return 0;
+}
+
+int flx_comm_init(flx_ctx *ctx, const void *unique_id128, int rank, int nranks)
+{
+    if (!ctx)
+        return FLX_E_INVALID;
+    REQUIRE(unique_id128 && nranks > 0 && rank >= 0 && rank < nranks, "flx_comm_init: bad arguments");
+    int rc = loadNccl(ctx);
+    if (rc)
+        return rc;
+    CU(cudaSetDevice(ctx->device));
+    Id128 id;
+    memcpy(&id, unique_id128, sizeof id);
+    int r = ctx->nccl.CommInitRank(&ctx->comm, nranks, id, rank);
+    if (r != 0)
+        return fail(ctx, FLX_E_NCCL, "ncclCommInitRank: %s", ctx->nccl.GetErrorString(r));
+    ctx->rank = rank;
+    ctx->nranks = nranks;
+    return 0;
+}
+
+int flx_comm_destroy(flx_ctx *ctx)
+{
+    if (!ctx)
+        return FLX_E_INVALID;
+    if (ctx->comm && ctx->nccl.CommDestroy)
+        ctx->nccl.CommDestroy(ctx->comm);
+    ctx->comm = nullptr;
+    return 0;
+}
+
+int flx_gather_pixels(flx_ctx *ctx, int root, float *full_rgba_host_or_null)
+{
+    int rc = checkReady(ctx, false, true);
+    if (rc)
+        return rc;
+    REQUIRE(ctx->comm != nullptr, "flx_gather_pixels: flx_comm_init has not been called");
+    REQUIRE(ctx->nranks == (int)ctx->nParts && ctx->rank == (int)ctx->part, "flx_gather_pixels: tile partition does not match the communicator");
+    REQUIRE(root >= 0 && root < ctx->nranks, "flx_gather_pixels: bad root");
+    CU(cudaSetDevice(ctx->device));
+    // every rank's tile has at most maxTile pixels; ragged tiles are sent at their own size
+    uint32_t maxTile = 0;
+    std::vector<uint32_t> tileOf(ctx->nranks);
+    for (int r = 0; r < ctx->nranks; r++)
+    {
+        tileOf[r] = localRows(ctx->height, r, ctx->nParts, ctx->stripeRows) * ctx->width;
+        maxTile = std::max(maxTile, tileOf[r]);
+    }
+    const size_t fullPixels = (size_t)ctx->width * ctx->height;
+    if (ctx->rank == root && ctx->gatherBufPixels < (size_t)maxTile * ctx->nranks)
+    {
+        freeDev(ctx->gatherBuf);
+        freeDev(ctx->fullImage);
+        CU(cudaMalloc(&ctx->gatherBuf, (size_t)maxTile * ctx->nranks * 16));
+        CU(cudaMalloc(&ctx->fullImage, fullPixels * 16));
+        ctx->gatherBufPixels = (size_t)maxTile * ctx->nranks;
+    }
+    const int ncclFloat = 7; // ncclFloat32
+    int r = ctx->nccl.GroupStart();
+    if (r == 0)
+        r = ctx->nccl.Send(ctx->pixels, (size_t)ctx->tilePixels * 4, ncclFloat, root, ctx->comm, ctx->stream);
+    if (r == 0 && ctx->rank == root)
+        for (int src = 0; src < ctx->nranks && r == 0; src++)
+            r = ctx->nccl.Recv(ctx->gatherBuf + (size_t)src * maxTile * 4, (size_t)tileOf[src] * 4, ncclFloat, src, ctx->comm, ctx->stream);
+    const int r2 = ctx->nccl.GroupEnd();
+    if (r != 0 || r2 != 0)
+        return fail(ctx, FLX_E_NCCL, "NCCL gather failed: %s", ctx->nccl.GetErrorString(r != 0 ? r : r2));
+    if (ctx->rank == root)
+    {
+        k_deinterleave<<<(unsigned)((fullPixels + 255) / 256), 256, 0, ctx->stream>>>(reinterpret_cast<const float4 *>(ctx->gatherBuf),
+                                                                                      reinterpret_cast<float4 *>(ctx->fullImage), ctx->width, ctx->height,
+                                                                                      ctx->nParts, ctx->stripeRows, maxTile);
+        if ((rc = launchCheck(ctx, "k_deinterleave")))
+            return rc;
+        if (full_rgba_host_or_null)
+        {
+            CU(cudaMemcpyAsync(full_rgba_host_or_null, ctx->fullImage, fullPixels * 16, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    return 0;
+}
+} // extern "C"

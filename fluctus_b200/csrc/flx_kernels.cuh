@@ -1,0 +1,614 @@
+// flx_kernels.cuh -- the stages of one wavefront iteration as CUDA kernels for sm_100a:
+//   k_reset        (reference: src/wf_reset.cl:5-66)
+//   k_raygen       (reference: src/wf_raygen.cl:4-97)
+//   k_extrays      (reference: src/wf_extrays.cl:5-36)
+//   k_shadowrays   (reference: src/wf_shadowrays.cl:6-37)
+//   k_logic        (reference: src/wf_logic.cl:14-314 and the three enqueue strategies 322-519)
+//   k_material<M>  (reference: src/wf_mat_*.cl, one instantiation per material queue)
+//   k_end_iteration (what the reference's host does between iterations: tracer.cpp:455-465,
+//                    clcontext.cpp:877-895)
+// Path state stays in the reference's GPUTaskState SoA (geom.h:199-236) so the stages can be
+// driven one by one through the C ABI exactly like the reference's enqueueWf*Kernel calls.
+#pragma once
+
+#include "flx_bsdf.cuh"
+#include "flx_trace.cuh"
+
+#define FLX_BLOCK 256       // streaming stages
+#define FLX_TRACE_BLOCK 128 // traversal stages
+#define FLX_LOGIC_TILE FLX_BLOCK
+
+// Everything a stage needs besides the scene; passed by value (lives in the constant bank).
+struct Frame
+{
+    Tasks tasks;
+    flx_QueueCounters *counters;
+    uint32_t *queues[8]; // order of flx_QueueCounters: raygen, extension, shadow, diffuse, glossy, ggxRefl, ggxRefr, delta
+    float *pixels;       // tilePixels x float4
+    float *denoiserAlbedo, *denoiserNormal;
+    uint32_t *currPixelIdx;
+    uint32_t numTasks;
+    // image / tile geometry (flx_set_tile): local pixel -> full-image pixel
+    uint32_t tilePixels; // pixels owned by this context (= width*height when untiled)
+    uint32_t part, nParts, stripeRows;
+    float tanHalfFov;    // tan(toRad(0.5f * fov)), evaluated once on the host with flx_tanf (wf_raygen.cl:50)
+};
+
+enum { Q_RAYGEN = 0, Q_EXT, Q_SHADOW, Q_DIFFUSE, Q_GLOSSY, Q_GGXREFL, Q_GGXREFR, Q_DELTA };
+
+FLX_DEV uint32_t *counter_ptr(flx_QueueCounters *c, int q) { return reinterpret_cast<uint32_t *>(c) + q; }
+
+FLX_DEV void write_empty_hit(const Tasks &t, uint32_t g) // EMPTY_HIT(FLT_MAX), geom.h:144 + utils.cl:202-211
+{
+    t.setv(FLX_S_P, g, v3(0.0f));
+    t.setv(FLX_S_N, g, v3(0.0f));
+    t.setf(FLX_S_UV, g, 0.0f);
+    t.setf(FLX_S_UV + 1, g, 0.0f);
+    t.setf(FLX_S_HIT_T, g, 3.402823466e+38f);
+    t.setu(FLX_S_HIT_I, g, (uint32_t)-1);
+    t.setu(FLX_S_AREA_LIGHT_HIT, g, 0u);
+    t.setu(FLX_S_MAT_ID, g, (uint32_t)-1);
+}
+
+FLX_DEV void reset_path_fields(const Tasks &t, uint32_t g, float worldRadius) // shared by reset and raygen
+{
+    t.setv(FLX_S_EI, g, v3(0.0f));
+    t.setv(FLX_S_T, g, v3(1.0f));
+    t.setu(FLX_S_PATH_LEN, g, 0u);
+    t.setu(FLX_S_LAST_SPECULAR, g, 1u);
+    t.setf(FLX_S_LAST_PDF_W, g, 1.0f);
+    t.setf(FLX_S_LAST_PDF_DIRECT, g, 0.0f);
+    t.setf(FLX_S_LAST_PDF_IMPLICIT, g, 0.0f);
+    t.setf(FLX_S_LAST_COS_TH, g, 0.0f);
+    t.setf(FLX_S_LAST_LIGHT_PICK, g, 1.0f);
+    t.setf(FLX_S_SHADOW_RAY_LEN, g, 2.0f * worldRadius);
+    t.setu(FLX_S_BACKFACE, g, 0u);
+    t.setu(FLX_S_SHADOW_BLOCKED, g, 1u);
+    t.setu(FLX_S_FIRST_DIFFUSE, g, 0u);
+    t.setv(FLX_S_LAST_EMISSION, g, v3(0.0f));
+    t.setv(FLX_S_LAST_BSDF, g, v3(0.0f));
+    write_empty_hit(t, g);
+}
+
+// ------------------------------------------------------------------------------------------------ reset
+__global__ void __launch_bounds__(FLX_BLOCK) k_reset(const __grid_constant__ Frame fr, const __grid_constant__ flx_RenderParams prm)
+{
+    const uint32_t gid = blockIdx.x * FLX_BLOCK + threadIdx.x;
+    if (gid < fr.tilePixels)
+    {
+        reinterpret_cast<float4 *>(fr.pixels)[gid] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        reinterpret_cast<float4 *>(fr.denoiserNormal)[gid] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        reinterpret_cast<float4 *>(fr.denoiserAlbedo)[gid] = make_float4(0.1f, 0.1f, 0.1f, 0.0f);
+    }
+    if (gid >= fr.numTasks)
+        return;
+    reset_path_fields(fr.tasks, gid, prm.worldRadius);
+    fr.tasks.setu(FLX_S_PIXEL_INDEX, gid, 0u);
+    fr.tasks.setu(FLX_S_SEED, gid, gid);
+    fr.queues[Q_RAYGEN][gid] = gid;
+    if (gid == 0)
+        fr.counters->raygenQueue = fr.numTasks;
+}
+
+// ------------------------------------------------------------------------------------------------ raygen
+// local pixel index -> (x, y) in the FULL image: rows are dealt to the parts in stripes of
+// stripeRows rows, stripe s -> part s % nParts. Untiled: identity.
+FLX_DEV void local_pixel_to_xy(const Frame &fr, uint32_t width, uint32_t local, uint32_t &x, uint32_t &y)
+{
+    x = local % width;
+    const uint32_t ly = local / width;
+    const uint32_t stripe = ly / fr.stripeRows, within = ly % fr.stripeRows;
+    y = (stripe * fr.nParts + fr.part) * fr.stripeRows + within;
+}
+
+__global__ void __launch_bounds__(FLX_BLOCK) k_raygen(const __grid_constant__ Frame fr, const __grid_constant__ flx_RenderParams prm)
+{
+    const uint32_t count = fr.counters->raygenQueue;
+    const uint32_t curr = *fr.currPixelIdx;
+    for (uint32_t gd = blockIdx.x * FLX_BLOCK + threadIdx.x; gd < count; gd += gridDim.x * FLX_BLOCK)
+    {
+        const uint32_t gid = fr.queues[Q_RAYGEN][gd];
+        const Tasks &t = fr.tasks;
+        uint32_t seed = t.u(FLX_S_SEED, gid);
+
+        const uint32_t pixelIdx = (curr + gd) % fr.tilePixels;
+        t.setu(FLX_S_PIXEL_INDEX, gid, pixelIdx);
+        uint32_t px, py;
+        local_pixel_to_xy(fr, prm.width, pixelIdx, px, py);
+        float x = (float)px, y = (float)py;
+        x += flx_rand(seed);
+        y += flx_rand(seed);
+        const float NDCx = x / (float)prm.width, NDCy = y / (float)prm.height;
+        float SCRx = 2.0f * NDCx - 1.0f, SCRy = 2.0f * NDCy - 1.0f;
+        SCRx *= (float)prm.width / (float)prm.height;
+        SCRx *= fr.tanHalfFov;
+        SCRy *= fr.tanHalfFov;
+
+        const V3 camPos = v3(prm.camera.pos), camRight = v3(prm.camera.right), camUp = v3(prm.camera.up), camDir = v3(prm.camera.dir);
+        V3 rayOrig = camPos;
+        const V3 target = ((rayOrig + camRight * SCRx) + camUp * SCRy) + camDir;
+        V3 rayDir = norm3(target - rayOrig);
+
+        // thin lens (wf_raygen.cl:59-63; disk sample utils.cl:75-80)
+        const V3 fp = camPos + rayDir * prm.camera.focalDist;
+        const float sqrt_r = sqrtf(flx_rand(seed));
+        const float th = FLX_2PI_F * flx_rand(seed);
+        const float rx = sqrt_r * flx_cosf(th), ry = sqrt_r * flx_sinf(th);
+        rayOrig = rayOrig + (prm.worldRadius * prm.camera.apertureSize) * (camRight * rx + camUp * ry);
+        rayDir = norm3(fp - rayOrig);
+
+        t.setv(FLX_S_ORIG, gid, rayOrig);
+        t.setv(FLX_S_DIR, gid, rayDir);
+        t.setu(FLX_S_SEED, gid, seed);
+        reset_path_fields(t, gid, prm.worldRadius);
+
+        const uint32_t slot = warp_push(counter_ptr(fr.counters, Q_EXT), true);
+        fr.queues[Q_EXT][slot] = gid;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ extension rays
+struct LocalStack
+{
+    int s[FLX_STACK_DEPTH];
+    FLX_DEV int &operator[](int i) { return s[i]; }
+};
+
+__global__ void __launch_bounds__(FLX_TRACE_BLOCK) k_extrays(const __grid_constant__ Frame fr, const __grid_constant__ flx_RenderParams prm, const BvhView bvh,
+                                                             const flx_Triangle *tris160)
+{
+    const uint32_t count = fr.counters->extensionQueue;
+    const uint32_t gd = blockIdx.x * FLX_TRACE_BLOCK + threadIdx.x;
+    if (gd >= count)
+        return;
+    const uint32_t gid = fr.queues[Q_EXT][gd];
+    const Tasks &t = fr.tasks;
+    const V3 o = t.v(FLX_S_ORIG, gid), d = t.v(FLX_S_DIR, gid);
+
+    float tbest = 3.402823466e+38f, ub = 0.0f, vb = 0.0f;
+    int tri = -1;
+    LocalStack stack;
+    trace_closest(bvh, o, d, tbest, ub, vb, tri, stack);
+
+    // hit record (bvh.cl:271-279): attributes of the winning triangle, fetched once
+    V3 P = v3(0.0f), N = v3(0.0f);
+    float tu = 0.0f, tv = 0.0f;
+    int matId = -1, lightHit = 0;
+    if (tri >= 0)
+    {
+        const float4 *q = reinterpret_cast<const float4 *>(tris160 + tri);
+        const float4 n0 = __ldg(q + 1), t0 = __ldg(q + 2), n1 = __ldg(q + 4), t1 = __ldg(q + 5), n2 = __ldg(q + 7), t2 = __ldg(q + 8);
+        matId = __float_as_int(__ldg(q + 9).x);
+        P = o + tbest * d;
+        N = norm3(bary3(ub, vb, v3(n0.x, n0.y, n0.z), v3(n1.x, n1.y, n1.z), v3(n2.x, n2.y, n2.z)));
+        const V3 uv = bary3(ub, vb, v3(t0.x, t0.y, t0.z), v3(t1.x, t1.y, t1.z), v3(t2.x, t2.y, t2.z));
+        tu = uv.x;
+        tv = uv.y;
+    }
+    if (prm.sampleImpl && prm.useAreaLight) // wf_extrays.cl:29, intersect.cl:124-155
+    {
+        if (light_quad(prm.areaLight, o, d, tbest))
+        {
+            lightHit = 1;
+            P = o + tbest * d;
+            N = v3(prm.areaLight.N);
+            tri = 0;
+            matId = 0;
+        }
+    }
+    t.setu(FLX_S_PATH_LEN, gid, t.u(FLX_S_PATH_LEN, gid) + 1u);
+    t.setv(FLX_S_P, gid, P);
+    t.setv(FLX_S_N, gid, N);
+    t.setf(FLX_S_UV, gid, tu);
+    t.setf(FLX_S_UV + 1, gid, tv);
+    t.setf(FLX_S_HIT_T, gid, tbest);
+    t.setu(FLX_S_HIT_I, gid, (uint32_t)tri);
+    t.setu(FLX_S_AREA_LIGHT_HIT, gid, (uint32_t)lightHit);
+    t.setu(FLX_S_MAT_ID, gid, (uint32_t)matId);
+}
+
+// ------------------------------------------------------------------------------------------------ shadow rays
+__global__ void __launch_bounds__(FLX_TRACE_BLOCK) k_shadowrays(const __grid_constant__ Frame fr, const __grid_constant__ flx_RenderParams prm, const BvhView bvh)
+{
+    const uint32_t count = fr.counters->shadowQueue;
+    const uint32_t gd = blockIdx.x * FLX_TRACE_BLOCK + threadIdx.x;
+    if (gd >= count)
+        return;
+    const uint32_t gid = fr.queues[Q_SHADOW][gd];
+    const Tasks &t = fr.tasks;
+    const V3 o = t.v(FLX_S_SHADOW_ORIG, gid), d = t.v(FLX_S_SHADOW_DIR, gid);
+    const float lenL = t.f(FLX_S_SHADOW_RAY_LEN, gid);
+    bool occluded = false;
+    if (prm.useAreaLight) // the light quad is tested first and blocks (wf_shadowrays.cl:29-31)
+    {
+        float tl = lenL;
+        occluded = light_quad(prm.areaLight, o, d, tl);
+    }
+    if (!occluded)
+    {
+        LocalStack stack;
+        occluded = trace_any(bvh, o, d, lenL, stack);
+    }
+    t.setu(FLX_S_SHADOW_BLOCKED, gid, occluded ? 1u : 0u);
+}
+
+// ------------------------------------------------------------------------------------------------ logic
+// Stable compaction state for the raygen queue: one 64-bit word per 256-path tile,
+// (status << 32 | value); status 0 = not ready, 1 = tile aggregate, 2 = inclusive prefix.
+struct ScanState
+{
+    unsigned long long *tiles;
+    uint32_t *ticket;
+};
+#define SCAN_AGG (1ull << 32)
+#define SCAN_PREFIX (2ull << 32)
+
+FLX_DEV unsigned long long ld_relaxed(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+FLX_DEV void st_relaxed(unsigned long long *p, unsigned long long v) { asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+
+FLX_DEV float luminance3(V3 v) { return (0.212671f * v.x + 0.715160f * v.y) + 0.072169f * v.z; } // utils.cl:237-240
+
+template <bool SEPARATE_QUEUES>
+__global__ void __launch_bounds__(FLX_BLOCK) k_logic(const __grid_constant__ Frame fr, const __grid_constant__ flx_RenderParams prm, const SceneView sc,
+                                                     const ScanState scan, const uint32_t maxId)
+{
+    __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_warpCount[FLX_BLOCK / 32];
+    __shared__ uint32_t s_base;
+    if (threadIdx.x == 0)
+        s_tile = atomicAdd(scan.ticket, 1u); // tiles are numbered in the order blocks start, so look-back never waits on an unscheduled block
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint32_t gid = tile * FLX_LOGIC_TILE + threadIdx.x;
+    const bool live = gid < maxId;
+    const Tasks &t = fr.tasks;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    // ---- phase 1: decide termination (wf_logic.cl:48-127) -------------------------------------------------
+    uint32_t seed = 0, len = 0;
+    V3 T = v3(0.0f), rayOrig = v3(0.0f), rayDir = v3(0.0f), Ei = v3(0.0f);
+    int hitI = -1, hitLight = 0;
+    bool terminate = false;
+    if (live)
+    {
+        seed = t.u(FLX_S_SEED, gid);
+        len = t.u(FLX_S_PATH_LEN, gid);
+        hitI = (int)t.u(FLX_S_HIT_I, gid);
+        hitLight = (int)t.u(FLX_S_AREA_LIGHT_HIT, gid);
+        rayOrig = t.v(FLX_S_ORIG, gid);
+        rayDir = t.v(FLX_S_DIR, gid);
+        T = t.v(FLX_S_T, gid);
+        Ei = t.v(FLX_S_EI, gid);
+        terminate = (len >= prm.maxBounces + 1u);
+        if (terminate && prm.useRoulette)
+        {
+            const float contProb = fminf(fmaxf(luminance3(T), 0.01f), 0.5f);
+            terminate = (flx_rand(seed) > contProb);
+            T = T / contProb;
+            t.setv(FLX_S_T, gid, T);
+        }
+        const float lastPdfW = t.f(FLX_S_LAST_PDF_W, gid);
+        if (is_zero3(T) || lastPdfW == 0.0f)
+            terminate = true;
+
+        if (hitI < 0 && !terminate) // escaped: implicit environment sample
+        {
+            float weight = 1.0f;
+            const bool lastSpecular = t.u(FLX_S_LAST_SPECULAR, gid) != 0u;
+            V3 bg = v3(0.0f);
+            if (prm.useEnvMap && (len == 1u || prm.sampleImpl))
+                bg = env_eval_dir(sc, rayDir) * prm.envMapStrength;
+            if (prm.sampleImpl && prm.sampleExpl && prm.useEnvMap && len > 1u && !lastSpecular)
+            {
+                const float lightPickProb = t.f(FLX_S_LAST_LIGHT_PICK, gid);
+                const float directPdfW = env_pdf(sc, rayDir);
+                weight = (lastPdfW * lightPickProb) / (lastPdfW * lightPickProb + directPdfW);
+            }
+            Ei = Ei + (weight * T) * bg;
+            t.setv(FLX_S_EI, gid, Ei);
+            terminate = true;
+        }
+        else if (hitLight && !terminate) // implicit area-light sample
+        {
+            float misWeight = 1.0f;
+            const bool lastSpecular = t.u(FLX_S_LAST_SPECULAR, gid) != 0u;
+            if (prm.sampleExpl && len > 1u && !lastSpecular)
+            {
+                const V3 hP = t.v(FLX_S_P, gid), hN = t.v(FLX_S_N, gid);
+                const float directPdfA = 1.0f / (4.0f * prm.areaLight.size.x * prm.areaLight.size.y);
+                const float dist = len3(hP - rayOrig);
+                const float cosine = dot3(norm3(-rayDir), hN);
+                const float directPdfW = directPdfA * (dist * dist) / fabsf(cosine); // pdfAtoW, utils.cl:197-200
+                const float lightPickProb = t.f(FLX_S_LAST_LIGHT_PICK, gid);
+                misWeight = lastPdfW / (lastPdfW + directPdfW * lightPickProb);
+            }
+            Ei = Ei + (T * misWeight) * v3(prm.areaLight.E);
+            t.setv(FLX_S_EI, gid, Ei);
+            terminate = true;
+        }
+    }
+
+    // publish this tile's count of terminated paths as early as possible
+    const unsigned termMask = __ballot_sync(0xffffffffu, live && terminate);
+    if (lane == 0)
+        s_warpCount[warp] = __popc(termMask);
+    __syncthreads();
+    uint32_t tileCount = 0, warpBase = 0;
+#pragma unroll
+    for (int w = 0; w < FLX_BLOCK / 32; w++)
+    {
+        if (w == warp)
+            warpBase = tileCount;
+        tileCount += s_warpCount[w];
+    }
+    if (threadIdx.x == 0)
+        st_relaxed(scan.tiles + tile, (tile == 0 ? SCAN_PREFIX : SCAN_AGG) | tileCount);
+
+    // ---- phase 2: previous vertex's light sample, splat, next-event estimation (wf_logic.cl:129-303) -------
+    if (live)
+    {
+        if (t.u(FLX_S_SHADOW_BLOCKED, gid) == 0u)
+        {
+            const V3 emission = t.v(FLX_S_LAST_EMISSION, gid), bsdf = t.v(FLX_S_LAST_BSDF, gid), lastT = t.v(FLX_S_LAST_T, gid);
+            const float cosTh = t.f(FLX_S_LAST_COS_TH, gid), directPdfW = t.f(FLX_S_LAST_PDF_DIRECT, gid);
+            const float bsdfPdfW = t.f(FLX_S_LAST_PDF_IMPLICIT, gid), lightPickProb = t.f(FLX_S_LAST_LIGHT_PICK, gid);
+            float weight = 1.0f;
+            if (prm.sampleImpl)
+                weight = (directPdfW * lightPickProb) / (directPdfW * lightPickProb + bsdfPdfW);
+            const V3 contrib = ((((bsdf * lastT) * emission) * weight) * cosTh) / (lightPickProb * directPdfW);
+            Ei = Ei + contrib;
+            t.setv(FLX_S_EI, gid, Ei);
+        }
+        if (terminate)
+        {
+            if (len > 0u)
+            {
+                const uint32_t pix = t.u(FLX_S_PIXEL_INDEX, gid);
+                atomicAdd(reinterpret_cast<float4 *>(fr.pixels) + pix, make_float4(Ei.x, Ei.y, Ei.z, 1.0f)); // one 128-bit reduction
+            }
+            t.setu(FLX_S_SEED, gid, seed);
+        }
+    }
+
+    bool toMaterial = false;
+    int matType = 0;
+    if (live && !terminate)
+    {
+        Surface s;
+        s.P = t.v(FLX_S_P, gid);
+        s.N = t.v(FLX_S_N, gid);
+        s.u = t.f(FLX_S_UV, gid);
+        s.v = t.f(FLX_S_UV + 1, gid);
+        s.tri = hitI;
+        const Mat mat = load_material(sc.materials, (int)t.u(FLX_S_MAT_ID, gid));
+        V3 N = shading_normal(s, mat, sc);
+        const bool backface = dot3(N, rayDir) > 0.0f;
+        if (backface)
+            N = N * -1.0f;
+        const V3 orig = s.P - 1e-3f * rayDir;
+        t.setv(FLX_S_N, gid, N);
+        t.setu(FLX_S_BACKFACE, gid, backface ? 1u : 0u);
+
+        const bool singular = (mat.type & (FLX_BXDF_IDEAL_REFLECTION | FLX_BXDF_IDEAL_DIELECTRIC)) != 0;
+        bool pushShadow = false;
+        if (prm.sampleExpl && !singular)
+        {
+            const uint32_t nLights = prm.useEnvMap + prm.useAreaLight;
+            const float envMapProb = (float)prm.useEnvMap / (float)(nLights > 1u ? nLights : 1u);
+            const bool useEnv = flx_rand(seed) < envMapProb;
+            const bool useArea = !useEnv && prm.useAreaLight;
+            if (useEnv && prm.useEnvMap)
+            {
+                V3 L;
+                float directPdfW = 0.0f;
+                env_sample_alias(sc, flx_rand(seed), L, directPdfW);
+                const float lenL = 2.0f * prm.worldRadius;
+                L = norm3(L);
+                const float cosTh = fmaxf(0.0f, dot3(L, N));
+                const V3 Li = env_eval_dir(sc, L) * prm.envMapStrength;
+                t.setv(FLX_S_SHADOW_ORIG, gid, orig);
+                t.setv(FLX_S_SHADOW_DIR, gid, L);
+                t.setf(FLX_S_SHADOW_RAY_LEN, gid, lenL);
+                t.setf(FLX_S_LAST_PDF_DIRECT, gid, directPdfW);
+                t.setf(FLX_S_LAST_COS_TH, gid, cosTh);
+                t.setf(FLX_S_LAST_LIGHT_PICK, gid, envMapProb);
+                t.setv(FLX_S_LAST_EMISSION, gid, Li);
+                pushShadow = true;
+            }
+            if (useArea)
+            {
+                const float lightPickProb = 1.0f - envMapProb;
+                const flx_AreaLight &A = prm.areaLight;
+                const float directPdfA = 1.0f / (4.0f * A.size.x * A.size.y); // sampleAreaLight, utils.cl:226-234
+                V3 posL = v3(A.pos);
+                const float r1 = 2.0f * flx_rand(seed) - 1.0f;
+                const float r2 = 2.0f * flx_rand(seed) - 1.0f;
+                posL = posL + (r1 * A.size.x) * v3(A.right);
+                posL = posL + (r2 * A.size.y) * v3(A.up);
+                V3 L = posL - orig;
+                const float lenL = len3(L) * 0.995f;
+                L = norm3(L);
+                const float cosLight = fmaxf(dot3(v3(A.N), -L), 0.0f);
+                if (cosLight > 0.0f)
+                {
+                    const float directPdfW = directPdfA * (lenL * lenL) / fabsf(cosLight);
+                    const float cosTh = fmaxf(0.0f, dot3(L, N));
+                    t.setv(FLX_S_SHADOW_ORIG, gid, orig);
+                    t.setv(FLX_S_SHADOW_DIR, gid, L);
+                    t.setf(FLX_S_SHADOW_RAY_LEN, gid, lenL);
+                    t.setf(FLX_S_LAST_PDF_DIRECT, gid, directPdfW);
+                    t.setf(FLX_S_LAST_COS_TH, gid, cosTh);
+                    t.setf(FLX_S_LAST_LIGHT_PICK, gid, lightPickProb);
+                    t.setv(FLX_S_LAST_EMISSION, gid, v3(A.E));
+                    pushShadow = true;
+                }
+                else
+                    t.setu(FLX_S_SHADOW_BLOCKED, gid, 1u);
+            }
+        }
+        t.setu(FLX_S_SEED, gid, seed);
+        toMaterial = true;
+        matType = mat.type;
+
+        const uint32_t slot = warp_push(counter_ptr(fr.counters, Q_SHADOW), pushShadow);
+        if (pushShadow)
+            fr.queues[Q_SHADOW][slot] = gid;
+    }
+
+    // ---- material queues: one warp-aggregated atomic per queue per warp (wf_logic.cl:459-519 intent) --------
+    if (!SEPARATE_QUEUES)
+    {
+        const uint32_t slot = warp_push(counter_ptr(fr.counters, Q_DIFFUSE), toMaterial);
+        if (toMaterial)
+            fr.queues[Q_DIFFUSE][slot] = gid;
+    }
+    else
+    {
+        int q = -1;
+        if (toMaterial)
+        {
+            if (matType == FLX_BXDF_DIFFUSE) q = Q_DIFFUSE;
+            else if (matType == FLX_BXDF_GLOSSY) q = Q_GLOSSY;
+            else if (matType == FLX_BXDF_GGX_ROUGH_REFLECTION) q = Q_GGXREFL;
+            else if (matType == FLX_BXDF_GGX_ROUGH_DIELECTRIC) q = Q_GGXREFR;
+            else if (matType == FLX_BXDF_IDEAL_REFLECTION || matType == FLX_BXDF_IDEAL_DIELECTRIC) q = Q_DELTA;
+            // any other type is dropped, as in the reference (wf_logic.cl:362-364)
+        }
+#pragma unroll
+        for (int qq = Q_DIFFUSE; qq <= Q_DELTA; qq++)
+        {
+            const uint32_t slot = warp_push(counter_ptr(fr.counters, qq), q == qq);
+            if (q == qq)
+                fr.queues[qq][slot] = gid;
+        }
+    }
+
+    // ---- raygen queue in ascending path order: decoupled look-back over the tile words ----------------------
+    if (warp == 0 && tile > 0)
+    {
+        uint32_t running = 0;
+        int look = (int)tile - 1 - lane;
+        while (true)
+        {
+            unsigned long long st = SCAN_PREFIX; // tiles before tile 0 contribute an empty inclusive prefix
+            if (look >= 0)
+            {
+                st = ld_relaxed(scan.tiles + look);
+                while ((st >> 32) == 0ull)
+                    st = ld_relaxed(scan.tiles + look);
+            }
+            const unsigned isPrefix = __ballot_sync(0xffffffffu, (st >> 32) == 2ull);
+            const int firstP = isPrefix ? (__ffs(isPrefix) - 1) : 31;
+            uint32_t v = (lane <= firstP) ? (uint32_t)(st & 0xffffffffull) : 0u;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+                v += __shfl_xor_sync(0xffffffffu, v, o);
+            running += v;
+            if (isPrefix)
+                break;
+            look -= 32;
+        }
+        if (lane == 0)
+        {
+            s_base = running;
+            st_relaxed(scan.tiles + tile, SCAN_PREFIX | (unsigned long long)(running + tileCount));
+        }
+    }
+    else if (threadIdx.x == 0 && tile == 0)
+        s_base = 0;
+    __syncthreads();
+    if (live && terminate)
+    {
+        const uint32_t rank = s_base + warpBase + __popc(termMask & ((1u << lane) - 1u));
+        fr.queues[Q_RAYGEN][fr.counters->raygenQueue * 0u + rank] = gid;
+    }
+    // the last tile knows the total
+    if (threadIdx.x == 0 && (tile + 1u) * FLX_LOGIC_TILE >= maxId && tile * FLX_LOGIC_TILE < maxId)
+        atomicAdd(counter_ptr(fr.counters, Q_RAYGEN), s_base + tileCount);
+}
+
+// ------------------------------------------------------------------------------------------------ materials
+template <int MASK>
+__global__ void __launch_bounds__(FLX_BLOCK) k_material(const __grid_constant__ Frame fr, const SceneView sc, const int queue)
+{
+    const uint32_t count = *counter_ptr(fr.counters, queue);
+    const Tasks &t = fr.tasks;
+    for (uint32_t gd = blockIdx.x * FLX_BLOCK + threadIdx.x; gd < count; gd += gridDim.x * FLX_BLOCK)
+    {
+        const uint32_t gid = fr.queues[queue][gd];
+        uint32_t seed = t.u(FLX_S_SEED, gid);
+        Surface s;
+        s.P = t.v(FLX_S_P, gid);
+        s.N = t.v(FLX_S_N, gid);
+        s.u = t.f(FLX_S_UV, gid);
+        s.v = t.f(FLX_S_UV + 1, gid);
+        s.tri = (int)t.u(FLX_S_HIT_I, gid);
+        const Mat mat = load_material(sc.materials, (int)t.u(FLX_S_MAT_ID, gid));
+        const bool backface = t.u(FLX_S_BACKFACE, gid) != 0u;
+        const V3 dirIn = t.v(FLX_S_DIR, gid); // points toward the surface
+        const V3 L = t.v(FLX_S_SHADOW_DIR, gid);
+
+        // BSDF value and pdf toward the pending light sample (wf_mat_*.cl:33-36)
+        const V3 bsdfNEE = bxdf_eval<MASK>(s, mat, backface, sc, dirIn, L);
+        const float bsdfPdfW = fmaxf(0.0f, bxdf_pdf<MASK>(s, mat, backface, sc, dirIn, L));
+        t.setv(FLX_S_LAST_BSDF, gid, bsdfNEE);
+        t.setf(FLX_S_LAST_PDF_IMPLICIT, gid, bsdfPdfW);
+
+        // continuation (wf_mat_*.cl:38-62)
+        float pdfW = 0.0f;
+        V3 newDir = v3(0.0f);
+        const V3 bsdf = bxdf_sample<MASK>(s, mat, backface, sc, dirIn, newDir, pdfW, seed);
+        const float costh = dot3(s.N, norm3(newDir));
+        const V3 oldT = t.v(FLX_S_T, gid);
+        V3 newT = v3(0.0f);
+        if (!(pdfW == 0.0f || is_zero3(bsdf)))
+            newT = ((oldT * bsdf) * costh) / pdfW;
+        const V3 orig = s.P + 1e-4f * newDir;
+        t.setv(FLX_S_LAST_T, gid, oldT);
+        t.setv(FLX_S_T, gid, newT);
+        t.setv(FLX_S_ORIG, gid, orig);
+        t.setv(FLX_S_DIR, gid, newDir);
+        t.setf(FLX_S_LAST_PDF_W, gid, pdfW);
+        t.setu(FLX_S_SEED, gid, seed);
+        t.setu(FLX_S_LAST_SPECULAR, gid, (mat.type & (FLX_BXDF_IDEAL_REFLECTION | FLX_BXDF_IDEAL_DIELECTRIC)) != 0 ? 1u : 0u);
+
+        const uint32_t slot = warp_push(counter_ptr(fr.counters, Q_EXT), true);
+        fr.queues[Q_EXT][slot] = gid;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ between iterations
+struct IterationState
+{
+    flx_QueueCounters *counters;
+    flx_QueueCounters *snapshot; // counters as they were after the material stage (enqueueGetCounters point)
+    flx_RenderStats64 *stats;
+    uint32_t *currPixelIdx;
+    uint32_t tilePixels;
+};
+// single thread: snapshot = counters (tracer.cpp:436)
+__global__ void k_snapshot_counters(const IterationState it)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0)
+        *it.snapshot = *it.counters;
+}
+// single thread: stats += snapshot (tracer.cpp:455-462), pixelIdx advance (clcontext.cpp:891-895), clear (877-883)
+__global__ void k_end_iteration(const IterationState it)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0)
+        return;
+    const flx_QueueCounters c = *it.snapshot;
+    it.stats->extensionRays += c.extensionQueue;
+    it.stats->shadowRays += c.shadowQueue;
+    it.stats->primaryRays += c.raygenQueue;
+    it.stats->samples += c.raygenQueue;
+    it.stats->iterations += 1;
+    *it.currPixelIdx = (uint32_t)(((uint64_t)*it.currPixelIdx + c.raygenQueue) % it.tilePixels);
+    flx_QueueCounters z = {0, 0, 0, 0, 0, 0, 0, 0};
+    *it.counters = z;
+}

@@ -1,0 +1,61 @@
+"""Tracer -- the part of the reference's Tracer that drives the wavefront path, headless.
+
+Replays, call for call, the order in which the reference drives CLContext:
+  * start()     = the `iteration == 0` prologue of Tracer::update       (reference: src/tracer.cpp:236-240)
+  * iterate()   = one steady-state iteration of Tracer::runBenchmark    (reference: src/tracer.cpp:433-439, 447, 455-465)
+  * render(n)   = n such iterations without host round trips (flx_render)
+It works with any object that has CLContext's method set -- the CUDA context (fluctus_b200.CLContext) and the oracle
+contexts in oracle/ alike -- which is how the parity tests run the same loop on both.
+"""
+from .structs import QueueCounters
+
+
+class Tracer:
+    def __init__(self, clctx, params):
+        self.clctx = clctx
+        self.params = params
+        self.iteration = 0
+        self.stats = dict(primaryRays=0, extensionRays=0, shadowRays=0, samples=0)
+
+    def start(self):
+        c, p = self.clctx, self.params
+        c.updateParams(p)
+        c.resetPixelIndex()
+        c.enqueueWfResetKernel(p)   # puts all paths in the raygen queue
+        c.enqueueWfRaygenKernel(p)
+        c.enqueueWfExtRayKernel(p)
+        c.enqueueClearWfQueues()
+        c.finishQueue()
+        self.iteration = 0
+
+    def iterate(self):
+        c, p = self.clctx, self.params
+        cnt = QueueCounters()
+        c.enqueueWfLogicKernel(p, False)
+        c.enqueueWfRaygenKernel(p)
+        c.enqueueWfMaterialKernels(p)
+        c.enqueueGetCounters(cnt)   # the following kernels do not grow the queues
+        c.enqueueWfExtRayKernel(p)
+        c.enqueueWfShadowRayKernel(p)
+        c.enqueueClearWfQueues()
+        c.finishQueue()
+        self.stats["extensionRays"] += cnt.extensionQueue
+        self.stats["shadowRays"] += cnt.shadowQueue
+        self.stats["primaryRays"] += cnt.raygenQueue
+        self.stats["samples"] += cnt.raygenQueue
+        c.updatePixelIndex(self._num_pixels(), cnt.raygenQueue)
+        self.iteration += 1
+        return cnt
+
+    def _num_pixels(self):
+        tp = getattr(self.clctx, "tilePixels", None)
+        return tp() if tp else self.params.width * self.params.height
+
+    def render(self, iterations):
+        """Fused loop (device-side bookkeeping); falls back to iterate() for contexts without it (the oracles)."""
+        if hasattr(self.clctx, "render"):
+            self.clctx.render(iterations)
+            self.iteration += iterations
+        else:
+            for _ in range(iterations):
+                self.iterate()

@@ -1,0 +1,174 @@
+/*
+ * fluctus_b200.h -- C ABI of the B200-native wavefront path-tracing hot path.
+ *
+ * Drop-in boundary: the reference has no FFI; its boundary for this path is the C++ class
+ * CLContext (reference: src/clcontext.hpp:26-211) as driven by Tracer::update()
+ * (src/tracer.cpp:222-266) and Tracer::runBenchmark() (src/tracer.cpp:431-470), plus the
+ * per-kernel argument contracts of src/kernel_impl.hpp.  Every entry point below names the
+ * CLContext method it replaces.  All structs are byte-for-byte the reference's device layouts
+ * (src/geom.h), so a caller can hand over the very arrays it used to write into cl::Buffers.
+ *
+ * Conventions
+ *   - every function returns 0 on success, else a non-zero code (cudaError_t, or FLX_E_*);
+ *     flx_last_error(ctx) returns the message.  Nothing ever calls exit()  (the reference
+ *     throws std::runtime_error through clt::check, ext/CLT/src/utils.cpp:22-29; the C++
+ *     wrapper include/fluctus_b200/clcontext.hpp rethrows to keep that behaviour).
+ *   - the library owns all device memory; host pointers are borrowed for the duration of the
+ *     call (uploads are blocking, like the reference's CL_TRUE writes), except the output of
+ *     flx_enqueue_get_counters which is valid after the next flx_finish (reference: CL_FALSE
+ *     read, src/clcontext.cpp:668-671).
+ *   - one context = one GPU = one in-order CUDA stream (reference: one cl::CommandQueue);
+ *     a context is not thread-safe; any number of contexts may live in one process.
+ *   - there is no CPU fallback: flx_create fails when no sm_100 device is usable.
+ */
+#ifndef FLUCTUS_B200_H
+#define FLUCTUS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- layouts (reference: src/geom.h; sizes checked by static_assert in the library and by tests) */
+typedef struct { float x, y, z, w; } flx_float3;  /* OpenCL float3 / FireRays::float3: 16 bytes */
+typedef struct { float x, y; } flx_float2;
+
+typedef struct { flx_float3 right, up, N, pos, E; flx_float2 size; float _pad[2]; } flx_AreaLight;      /* geom.h:104-111, 96 B */
+typedef struct { flx_float3 pos, dir, up, right; float fov, apertureSize, focalDist, _pad; } flx_Camera; /* geom.h:146-155, 80 B */
+typedef struct { float exposure; uint32_t tmOperator; } flx_PostProcessParams;                            /* geom.h:157-161 */
+typedef struct {                                                                                          /* geom.h:163-180, 240 B */
+    flx_AreaLight areaLight;
+    flx_Camera camera;
+    flx_PostProcessParams ppParams;
+    uint32_t width, height, n_tris, useEnvMap, useAreaLight;
+    float envMapStrength;
+    uint32_t maxBounces, sampleImpl, sampleExpl, useRoulette, wfSeparateQueues;
+    float worldRadius;
+    uint32_t _pad[2];
+} flx_RenderParams;
+
+typedef struct { flx_float3 bmin, bmax; int32_t parent; uint32_t iStartOrRightChild; uint8_t nPrims; uint8_t _pad[7]; } flx_Node;  /* geom.h:71-80, bvhnode.hpp:50-59, 48 B */
+typedef struct { flx_float3 p, n, t; } flx_Vertex;                                                        /* geom.h:82-87 */
+typedef struct { flx_Vertex v0, v1, v2; int32_t matId; int32_t _pad[3]; } flx_Triangle;                    /* geom.h:89-95, triangle.hpp:18-49, 160 B */
+typedef struct { flx_float3 Kd, Ks, Ke; float Ns, Ni; int32_t map_Kd, map_Ks, map_N, type; int32_t _pad[2]; } flx_Material; /* geom.h:113-124, 80 B */
+typedef struct { uint32_t offset, width, height; } flx_TexDescriptor;                                     /* geom.h:126-131, 12 B */
+typedef struct { uint32_t raygenQueue, extensionQueue, shadowQueue, diffuseQueue, glossyQueue, ggxReflQueue, ggxRefrQueue, deltaQueue; } flx_QueueCounters; /* geom.h:240-252 */
+typedef struct { uint32_t primaryRays, extensionRays, shadowRays, samples; } flx_RenderStats;             /* geom.h:254-260 */
+typedef struct { uint64_t primaryRays, extensionRays, shadowRays, samples, iterations; } flx_RenderStats64; /* same counters, 64-bit (new) */
+typedef struct { float primary, extension, shadow, samples, total; } flx_PerfNumbers;                     /* clcontext.hpp:12-19 */
+
+/* BSDF type bits, reference src/bxdf_types.h:4-11 */
+#define FLX_BXDF_DIFFUSE (1 << 1)
+#define FLX_BXDF_GLOSSY (1 << 2)
+#define FLX_BXDF_GGX_ROUGH_REFLECTION (1 << 3)
+#define FLX_BXDF_IDEAL_REFLECTION (1 << 4)
+#define FLX_BXDF_GGX_ROUGH_DIELECTRIC (1 << 5)
+#define FLX_BXDF_IDEAL_DIELECTRIC (1 << 6)
+#define FLX_BXDF_EMISSIVE (1 << 7)
+
+/* GPUTaskState is a structure of arrays: 64 four-byte slots, slot s of path g lives at
+ * ((uint32_t*)tasks)[s * num_tasks + g]  (geom.h:37-49, 199-236).  Slot numbers: */
+enum {
+    FLX_S_ORIG = 0, FLX_S_DIR = 4, FLX_S_SHADOW_ORIG = 8, FLX_S_SHADOW_DIR = 12, FLX_S_T = 16, FLX_S_EI = 20,
+    FLX_S_LAST_BSDF = 24, FLX_S_LAST_EMISSION = 28, FLX_S_LAST_T = 32, FLX_S_P = 36, FLX_S_N = 40, FLX_S_UV = 44,
+    FLX_S_PHASE = 46, FLX_S_LAST_PDF_W = 47, FLX_S_PATH_LEN = 48, FLX_S_SEED = 49, FLX_S_LAST_SPECULAR = 50,
+    FLX_S_SHADOW_BLOCKED = 51, FLX_S_BACKFACE = 52, FLX_S_PIXEL_INDEX = 53, FLX_S_FIRST_DIFFUSE = 54,
+    FLX_S_LAST_PDF_DIRECT = 55, FLX_S_LAST_PDF_IMPLICIT = 56, FLX_S_LAST_COS_TH = 57, FLX_S_LAST_LIGHT_PICK = 58,
+    FLX_S_SHADOW_RAY_LEN = 59, FLX_S_HIT_T = 60, FLX_S_HIT_I = 61, FLX_S_AREA_LIGHT_HIT = 62, FLX_S_MAT_ID = 63,
+    FLX_NUM_SLOTS = 64
+};
+
+enum { FLX_OK = 0, FLX_E_INVALID = 10001, FLX_E_NO_DEVICE = 10002, FLX_E_NOT_READY = 10003, FLX_E_NCCL = 10004, FLX_E_UNSUPPORTED_ARCH = 10005 };
+
+/* kernel ids for flx_get_kernel_ms (reference instrument: CLContext::checkTracingPerf, clcontext.cpp:673-701) */
+enum { FLX_K_RESET = 0, FLX_K_RAYGEN, FLX_K_EXTRAYS, FLX_K_SHADOWRAYS, FLX_K_LOGIC, FLX_K_MATERIALS, FLX_K_END_ITERATION, FLX_K_COUNT };
+
+typedef struct flx_ctx flx_ctx;
+
+/* CLContext::CLContext + setup (clcontext.hpp:32,62; clcontext.cpp:18-69,116-141): pick the device, allocate the
+ * path-state SoA for num_tasks paths (256 B each), 8 index queues, counters, pixel index, params. */
+int flx_create(int device, uint32_t num_tasks, flx_ctx **out);
+void flx_destroy(flx_ctx *ctx);
+const char *flx_last_error(const flx_ctx *ctx); /* ctx may be NULL: message of the last failed flx_create */
+const char *flx_version(void);
+
+/* CLContext::uploadSceneData + packTextures (clcontext.hpp:76; clcontext.cpp:522-611). Blocking; copies.
+ * nodes: reference Node[] in DFS order, left child = self+1 (bvhnode.hpp:50-59); indices: u32 triangle refs. */
+int flx_upload_scene(flx_ctx *ctx, const flx_Triangle *tris, uint32_t n_tris, const uint32_t *indices, uint32_t n_indices,
+                     const flx_Node *nodes, uint32_t n_nodes, const flx_Material *materials, uint32_t n_materials,
+                     const flx_TexDescriptor *tex_desc, uint32_t n_tex, const uint8_t *tex_data, size_t tex_bytes);
+
+/* CLContext::createEnvMap (clcontext.hpp:79; clcontext.cpp:467-511): rgb is w*h*3 floats; tables are w*h entries. */
+int flx_upload_envmap(flx_ctx *ctx, const float *rgb, int32_t w, int32_t h, const float *prob, const int32_t *alias, const float *pdf);
+
+/* CLContext::setupPixelStorage (clcontext.hpp:77; clcontext.cpp:326-384) without the GL PBOs: (re)allocate W*H float4. */
+int flx_resize(flx_ctx *ctx, uint32_t width, uint32_t height);
+
+/* CLContext::updateParams (clcontext.hpp:75; clcontext.cpp:703-707); also plays the role of recompileKernels
+ * (clcontext.cpp:852-874): kernel specialisations are picked from the params at launch time. */
+int flx_update_params(flx_ctx *ctx, const flx_RenderParams *params);
+
+/* CLContext::enqueueWf*Kernel (clcontext.hpp:43-48; clcontext.cpp:765-848). Asynchronous, in order. */
+int flx_enqueue_reset(flx_ctx *ctx);
+int flx_enqueue_raygen(flx_ctx *ctx);
+int flx_enqueue_extrays(flx_ctx *ctx);
+int flx_enqueue_shadowrays(flx_ctx *ctx);
+int flx_enqueue_logic(flx_ctx *ctx, int first_iteration);
+int flx_enqueue_materials(flx_ctx *ctx); /* 5 per-type kernels or the single-queue kernel, by params.wfSeparateQueues */
+
+/* CLContext::enqueueClearWfQueues / enqueueGetCounters / finishQueue / updatePixelIndex / resetPixelIndex /
+ * getNumTasks (clcontext.hpp:53-57,71; clcontext.cpp:668-671, 877-906). */
+int flx_enqueue_clear_queues(flx_ctx *ctx);
+int flx_enqueue_get_counters(flx_ctx *ctx, flx_QueueCounters *host_out);
+int flx_finish(flx_ctx *ctx);
+int flx_update_pixel_index(flx_ctx *ctx, uint32_t num_pixels, uint32_t num_new_paths);
+int flx_reset_pixel_index(flx_ctx *ctx);
+uint32_t flx_num_tasks(const flx_ctx *ctx);
+
+/* The steady-state loop of Tracer::runBenchmark (tracer.cpp:431-470) replayed n_iterations times with no host
+ * round trip: logic, raygen, materials, [counter snapshot], extrays, shadowrays, then a one-thread kernel that does
+ * what the host does between iterations (stats += counters, pixelIdx = (pixelIdx + cnt.raygen) % numPixels
+ * [clcontext.cpp:891-895], counters = 0).  Results are identical to driving the single calls above. */
+int flx_render(flx_ctx *ctx, uint32_t n_iterations);
+
+/* CLContext::resetStats/getStats/updateRenderPerf/getRenderPerf (clcontext.hpp:66-70; clcontext.cpp:634-666).
+ * Totals are accumulated on the device by flx_render (64-bit) and are read here (synchronises). */
+int flx_reset_stats(flx_ctx *ctx);
+int flx_get_stats(flx_ctx *ctx, flx_RenderStats64 *out);
+
+/* CLContext::checkTracingPerf (clcontext.hpp:73; clcontext.cpp:673-701): accumulated CUDA-event time and launch
+ * count of one kernel since the last flx_reset_stats. Timing is off by default (flx_set_profiling). */
+int flx_set_profiling(flx_ctx *ctx, int enabled);
+int flx_get_kernel_ms(flx_ctx *ctx, int kernel_id, float *total_ms, uint32_t *launches);
+
+/* Raw read-back, replaces CLContext::saveImage (clcontext.hpp:78; clcontext.cpp:386-465). Synchronises. */
+int flx_read_pixels(flx_ctx *ctx, float *rgba, size_t n_pixels);
+/* Test/diagnostic access to the path state and queues (no reference equivalent; the reference's debugger did this). */
+int flx_read_tasks(flx_ctx *ctx, uint32_t *slots_out /* 64*num_tasks */);
+int flx_write_tasks(flx_ctx *ctx, const uint32_t *slots_in);
+int flx_read_queue(flx_ctx *ctx, int queue_id /* 0..7 = order of flx_QueueCounters */, uint32_t *out, uint32_t max_entries);
+int flx_write_queue(flx_ctx *ctx, int queue_id, const uint32_t *entries, uint32_t n);
+int flx_write_counters(flx_ctx *ctx, const flx_QueueCounters *in);
+
+/* ---- image-space sharding across GPUs (new). A context renders the rows {y : (y / stripe_rows) % n_parts
+ * == part} of a full_width x full_height image; its local pixel buffer holds only those rows, top to bottom.
+ * flx_set_tile must be followed by flx_update_params (width/height there are the FULL image). */
+int flx_set_tile(flx_ctx *ctx, uint32_t part, uint32_t n_parts, uint32_t stripe_rows);
+uint32_t flx_tile_pixels(const flx_ctx *ctx);
+
+/* One NCCL collective per frame: gather every rank's tile into the full image on `root` (de-interleaved on the GPU).
+ * NCCL is resolved at run time (dlopen of libnccl.so.2, i.e. the copy torch.distributed already loaded). */
+int flx_comm_unique_id(void *out128);
+int flx_comm_init(flx_ctx *ctx, const void *unique_id128, int rank, int nranks);
+int flx_gather_pixels(flx_ctx *ctx, int root, float *full_rgba_host_or_null);
+int flx_comm_destroy(flx_ctx *ctx);
+
+/* End-to-end convenience used by bench.py's e2e leg: host scene in, host image out, all copies included. */
+size_t flx_device_bytes(const flx_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLUCTUS_B200_H */

@@ -1,0 +1,213 @@
+"""oracle_host.py -- TEST INFRASTRUCTURE. CPU contexts with CLContext's method set, for parity checks only.
+
+Two oracles share this driver (only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+leg may import this module; the product package never does):
+
+  RefContext   runs the REFERENCE'S OWN kernel sources compiled for the host (oracle/_ref/libfluctus_ref.so, built by
+               oracle/build_ref.py from /root/reference/src/wf_*.cl).  Serial = deterministic ground truth; `parallel=True`
+               = the OpenMP build used as the CPU baseline.
+  PortContext  runs the plain-C restatement in oracle/wf_oracle.c (oracle/liboracle.so).
+
+Both keep every buffer the reference keeps in cl::Buffers (src/clcontext.hpp:167-210) as numpy arrays and enqueue
+"kernels" by looping the NDRange the reference launches (src/clcontext.cpp:765-848).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_LIB = os.path.join(HERE, "_ref", "libfluctus_ref.so")
+PORT_LIB = os.path.join(HERE, "liboracle.so")
+
+
+class RefBufs(C.Structure):  # oracle/ref_shim/ref_abi.h
+    _fields_ = [("tasks", C.c_void_p), ("pixels", C.c_void_p), ("denoiserAlbedo", C.c_void_p), ("denoiserNormal", C.c_void_p),
+                ("queueLens", C.c_void_p), ("raygenQueue", C.c_void_p), ("extensionQueue", C.c_void_p), ("shadowQueue", C.c_void_p),
+                ("diffuseQueue", C.c_void_p), ("glossyQueue", C.c_void_p), ("ggxReflQueue", C.c_void_p), ("ggxRefrQueue", C.c_void_p),
+                ("deltaQueue", C.c_void_p), ("tris", C.c_void_p), ("nodes", C.c_void_p), ("indices", C.c_void_p), ("envRGBA", C.c_void_p),
+                ("envW", C.c_int32), ("envH", C.c_int32), ("probTable", C.c_void_p), ("aliasTable", C.c_void_p), ("pdfTable", C.c_void_p),
+                ("materials", C.c_void_p), ("texData", C.c_void_p), ("textures", C.c_void_p), ("params", C.c_void_p),
+                ("currPixelIdx", C.c_void_p), ("numTasks", C.c_uint32), ("firstIteration", C.c_uint32)]
+
+
+QUEUE_FIELDS = ("raygenQueue", "extensionQueue", "shadowQueue", "diffuseQueue", "glossyQueue", "ggxReflQueue", "ggxRefrQueue", "deltaQueue")
+QUEUE_NAMES = ("raygen", "extension", "shadow", "diffuse", "glossy", "ggxRefl", "ggxRefr", "delta")
+
+
+def ref_available():
+    return os.path.exists(REF_LIB)
+
+
+def port_available():
+    return os.path.exists(PORT_LIB)
+
+
+class _CpuContext:
+    """Shared implementation; subclasses pick the library and symbol prefix."""
+
+    LIB = None
+    PREFIX = None
+
+    def __init__(self, num_tasks, parallel=False):
+        if not os.path.exists(self.LIB):
+            raise FileNotFoundError(self.LIB)
+        self.lib = C.CDLL(self.LIB)
+        self.prefix = self.PREFIX + ("par_" if parallel else "")
+        self.NUM_TASKS = int(num_tasks)
+        n = self.NUM_TASKS
+        self.tasks = np.zeros((64, n), np.uint32)
+        self.queues = {q: np.zeros(n, np.uint32) for q in QUEUE_FIELDS}
+        self.counters = np.zeros(8, np.uint32)
+        self.currPixelIdx = np.zeros(1, np.uint32)
+        self.pixelIdx = 0
+        self.params_buf = np.zeros(240, np.uint8)
+        self.env_rgba = np.zeros(4, np.float32)
+        self.env_w = self.env_h = 1
+        self.prob = np.zeros(1, np.float32)
+        self.alias = np.zeros(1, np.int32)
+        self.pdf = np.zeros(1, np.float32)
+        self.scene = None
+        self.pixels = self.albedo = self.normal = None
+        self._pending = []
+        self._separate = False
+        self.width = self.height = 0
+
+    # ---- setup
+    def uploadSceneData(self, scene):
+        self.scene = scene
+        self.tex_desc = scene.tex_desc if len(scene.tex_desc) else np.zeros(12, np.uint8)
+        self.tex_data = scene.tex_data if len(scene.tex_data) else np.zeros(4, np.uint8)
+
+    def createEnvMap(self, env):
+        n = env.width * env.height
+        rgba = np.ones((n, 4), np.float32)
+        rgba[:, :3] = env.rgb.reshape(n, 3)
+        self.env_rgba, self.env_w, self.env_h = np.ascontiguousarray(rgba), env.width, env.height
+        self.prob, self.alias, self.pdf = env.prob, env.alias, env.pdf
+
+    def setupPixelStorage(self, width, height):
+        self.width, self.height = int(width), int(height)
+        self.pixels = np.zeros((self.width * self.height, 4), np.float32)
+        self.albedo = np.zeros_like(self.pixels)
+        self.normal = np.zeros_like(self.pixels)
+
+    def updateParams(self, params):
+        C.memmove(self.params_buf.ctypes.data, C.byref(params), 240)
+        self._separate = bool(params.wfSeparateQueues)
+
+    def recompileKernels(self, setArgs=False):
+        pass
+
+    def _bufs(self, first=0):
+        b = RefBufs()
+        p = lambda a: a.ctypes.data
+        b.tasks, b.pixels, b.denoiserAlbedo, b.denoiserNormal = p(self.tasks), p(self.pixels), p(self.albedo), p(self.normal)
+        b.queueLens = p(self.counters)
+        for q in QUEUE_FIELDS:
+            setattr(b, q, p(self.queues[q]))
+        s = self.scene
+        b.tris, b.nodes, b.indices, b.materials = p(s.tris), p(s.nodes), p(s.indices), p(s.materials)
+        b.texData, b.textures = p(self.tex_data), p(self.tex_desc)
+        b.envRGBA, b.envW, b.envH = p(self.env_rgba), self.env_w, self.env_h
+        b.probTable, b.aliasTable, b.pdfTable = p(self.prob), p(self.alias), p(self.pdf)
+        b.params, b.currPixelIdx = p(self.params_buf), p(self.currPixelIdx)
+        b.numTasks, b.firstIteration = self.NUM_TASKS, first
+        return b
+
+    def _run(self, name, n, first=0):
+        fn = getattr(self.lib, self.prefix + name)
+        fn.argtypes = [C.POINTER(RefBufs), C.c_size_t, C.c_size_t]
+        fn.restype = None
+        b = self._bufs(first)
+        fn(C.byref(b), 0, int(n))
+
+    # ---- stages: NDRange sizes of src/clcontext.cpp:765-848
+    def enqueueWfResetKernel(self, params=None):
+        self._run("reset", max(self.NUM_TASKS, self.width * self.height))
+
+    def enqueueWfRaygenKernel(self, params=None):
+        self._run("raygen", self.NUM_TASKS)
+
+    def enqueueWfExtRayKernel(self, params=None):
+        self._run("ext", self.NUM_TASKS)
+
+    def enqueueWfShadowRayKernel(self, params=None):
+        self._run("shadow", self.NUM_TASKS)
+
+    def enqueueWfLogicKernel(self, params=None, firstIteration=False):
+        n = ((self.NUM_TASKS - 1) // 32 + 1) * 32
+        self._run("logic_separate" if self._separate else "logic_single", n, 1 if firstIteration else 0)
+
+    def enqueueWfMaterialKernels(self, params=None):
+        if self._separate:
+            for k in ("mat_diffuse", "mat_glossy", "mat_ggx_refl", "mat_ggx_refr", "mat_delta"):
+                self._run(k, self.NUM_TASKS)
+        else:
+            self._run("mat_all", self.NUM_TASKS)
+
+    # ---- bookkeeping
+    def enqueueClearWfQueues(self):
+        self.counters[:] = 0
+
+    def enqueueGetCounters(self, cnt):
+        for i, (name, _) in enumerate(cnt._fields_):
+            setattr(cnt, name, int(self.counters[i]))
+
+    def finishQueue(self):
+        pass
+
+    def updatePixelIndex(self, numPixels, numNewPaths):
+        self.pixelIdx = (self.pixelIdx + int(numNewPaths)) % int(numPixels)
+        self.currPixelIdx[0] = self.pixelIdx
+
+    def resetPixelIndex(self):
+        self.pixelIdx = 0
+        self.currPixelIdx[0] = 0
+
+    def getNumTasks(self):
+        return self.NUM_TASKS
+
+    # ---- read-back, same names as fluctus_b200.CLContext
+    def tilePixels(self):
+        return self.width * self.height
+
+    def readPixels(self):
+        return self.pixels.copy()
+
+    def readTasks(self):
+        return self.tasks.copy()
+
+    def writeTasks(self, slots):
+        self.tasks[...] = slots
+
+    def readQueue(self, name, n=None):
+        q = self.queues[QUEUE_FIELDS[QUEUE_NAMES.index(name)]]
+        return q.copy() if n is None else q[:n].copy()
+
+    def writeQueue(self, name, entries):
+        q = self.queues[QUEUE_FIELDS[QUEUE_NAMES.index(name)]]
+        q[:len(entries)] = entries
+
+    def writeCounters(self, cnt):
+        for i, (name, _) in enumerate(cnt._fields_):
+            self.counters[i] = getattr(cnt, name)
+
+    def readCounters(self):
+        from fluctus_b200.structs import QueueCounters
+        cnt = QueueCounters()
+        self.enqueueGetCounters(cnt)
+        return cnt
+
+    def close(self):
+        pass
+
+
+class RefContext(_CpuContext):
+    LIB = REF_LIB
+    PREFIX = "ref_"
+
+
+class PortContext(_CpuContext):
+    LIB = PORT_LIB
+    PREFIX = "port_"

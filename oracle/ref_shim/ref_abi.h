@@ -1,0 +1,32 @@
+/* ref_abi.h -- TEST INFRASTRUCTURE (oracle). Plain-C argument block handed to the host-compiled
+ * reference kernels in oracle/_ref/libfluctus_ref.so.  Field names follow the kernel argument
+ * names the reference binds in src/kernel_impl.hpp:18-48, 90-139, 246-285. */
+#ifndef REF_ABI_H
+#define REF_ABI_H
+#include <stdint.h>
+typedef struct
+{
+    void *tasks;            /* GPUTaskState SoA, numTasks*256 B */
+    float *pixels;          /* W*H float4 */
+    float *denoiserAlbedo;
+    float *denoiserNormal;
+    void *queueLens;        /* QueueCounters, 8 x u32 */
+    uint32_t *raygenQueue, *extensionQueue, *shadowQueue;
+    uint32_t *diffuseQueue, *glossyQueue, *ggxReflQueue, *ggxRefrQueue, *deltaQueue;
+    void *tris;             /* Triangle[ ] 160 B */
+    void *nodes;            /* GPUNode[ ] 48 B */
+    uint32_t *indices;
+    const float *envRGBA;   /* RGBA32F env map (or 1x1 dummy) */
+    int32_t envW, envH;
+    float *probTable;
+    int32_t *aliasTable;
+    float *pdfTable;
+    void *materials;        /* Material[ ] 80 B */
+    uint8_t *texData;
+    void *textures;         /* TexDescriptor[ ] 12 B */
+    void *params;           /* RenderParams 240 B */
+    uint32_t *currPixelIdx;
+    uint32_t numTasks;
+    uint32_t firstIteration;
+} RefBufs;
+#endif

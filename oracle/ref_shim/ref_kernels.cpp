@@ -1,0 +1,114 @@
+// ref_kernels.cpp -- TEST INFRASTRUCTURE (oracle).
+// One translation unit per reference kernel file: build_ref.py compiles this file once per
+// kernel with -DREF_TU_<name> and an include path that holds the "(float3)(" -> "float3("
+// transformed copy of /root/reference/src/*.cl (made in a temporary directory at build time;
+// no reference source is stored in this repository).  The kernel body is the reference's own.
+// Each exported function runs the NDRange [begin, end) one work-item at a time; with
+// -DSHIM_PARALLEL the loop is an OpenMP parallel-for (CPU baseline), otherwise it is serial
+// and therefore deterministic (parity oracle).
+#include "cl_shim.hpp"
+#include "ref_abi.h"
+
+namespace
+{
+#if defined(REF_TU_RESET)
+#include "wf_reset.cl"
+#elif defined(REF_TU_RAYGEN)
+#include "wf_raygen.cl"
+#elif defined(REF_TU_EXT)
+#include "wf_extrays.cl"
+#elif defined(REF_TU_SHADOW)
+#include "wf_shadowrays.cl"
+#elif defined(REF_TU_LOGIC_SINGLE) || defined(REF_TU_LOGIC_SEPARATE)
+#include "wf_logic.cl"
+#elif defined(REF_TU_MAT_ALL)
+#include "wf_mat_all.cl"
+#elif defined(REF_TU_MAT_DIFFUSE)
+#include "wf_mat_diffuse.cl"
+#elif defined(REF_TU_MAT_GLOSSY)
+#include "wf_mat_glossy.cl"
+#elif defined(REF_TU_MAT_GGX_REFL)
+#include "wf_mat_ggx_reflection.cl"
+#elif defined(REF_TU_MAT_GGX_REFR)
+#include "wf_mat_ggx_refraction.cl"
+#elif defined(REF_TU_MAT_DELTA)
+#include "wf_mat_delta.cl"
+#else
+#error "no REF_TU_* selected"
+#endif
+} // namespace
+
+#ifdef SHIM_PARALLEL
+#define REF_LOOP _Pragma("omp parallel for schedule(dynamic, 4096)") for (long long g = (long long)begin; g < (long long)end; ++g)
+#define REF_NAME(n) ref_par_##n
+#else
+#define REF_LOOP for (long long g = (long long)begin; g < (long long)end; ++g)
+#define REF_NAME(n) ref_##n
+#endif
+
+#define T(b) ((GPUTaskState *)(b)->tasks)
+#define QL(b) ((QueueCounters *)(b)->queueLens)
+#define P(b) ((RenderParams *)(b)->params)
+#define MATARGS(b, q) T(b), QL(b), (b)->q, (b)->extensionQueue, (Material *)(b)->materials, (b)->texData, (TexDescriptor *)(b)->textures, P(b), (b)->numTasks
+
+extern "C"
+{
+#if defined(REF_TU_RESET)
+    void REF_NAME(reset)(const RefBufs *b, size_t begin, size_t end)
+    {
+        REF_LOOP { g_shim_gid = (size_t)g; reset(T(b), b->pixels, b->denoiserAlbedo, b->denoiserNormal, QL(b), b->raygenQueue, P(b), b->numTasks); }
+    }
+#ifndef SHIM_PARALLEL
+    // layout facts the rest of the repo relies on, checked by tests
+    void ref_layout(uint32_t out[8])
+    {
+        out[0] = sizeof(GPUTaskState); out[1] = sizeof(GPUNode); out[2] = sizeof(Triangle); out[3] = sizeof(Material);
+        out[4] = sizeof(RenderParams); out[5] = sizeof(QueueCounters); out[6] = sizeof(TexDescriptor); out[7] = sizeof(Hit);
+    }
+#endif
+#elif defined(REF_TU_RAYGEN)
+    void REF_NAME(raygen)(const RefBufs *b, size_t begin, size_t end)
+    {
+        REF_LOOP { g_shim_gid = (size_t)g; genRays(T(b), P(b), QL(b), b->raygenQueue, b->extensionQueue, b->currPixelIdx, b->numTasks); }
+    }
+#elif defined(REF_TU_EXT)
+    void REF_NAME(ext)(const RefBufs *b, size_t begin, size_t end)
+    {
+        REF_LOOP { g_shim_gid = (size_t)g; traceExtension(T(b), QL(b), b->extensionQueue, (Triangle *)b->tris, (GPUNode *)b->nodes, b->indices, P(b), b->numTasks); }
+    }
+#elif defined(REF_TU_SHADOW)
+    void REF_NAME(shadow)(const RefBufs *b, size_t begin, size_t end)
+    {
+        REF_LOOP { g_shim_gid = (size_t)g; traceShadow(T(b), QL(b), b->shadowQueue, (Triangle *)b->tris, (GPUNode *)b->nodes, b->indices, P(b), b->numTasks); }
+    }
+#elif defined(REF_TU_LOGIC_SINGLE) || defined(REF_TU_LOGIC_SEPARATE)
+#if defined(REF_TU_LOGIC_SINGLE)
+    void REF_NAME(logic_single)(const RefBufs *b, size_t begin, size_t end)
+#else
+    void REF_NAME(logic_separate)(const RefBufs *b, size_t begin, size_t end)
+#endif
+    {
+        const shim_image img = {b->envW, b->envH, b->envRGBA};
+        REF_LOOP
+        {
+            g_shim_gid = (size_t)g;
+            logic(T(b), b->pixels, b->denoiserNormal, b->denoiserAlbedo, QL(b), b->extensionQueue, b->shadowQueue, b->raygenQueue,
+                  b->diffuseQueue, b->glossyQueue, b->ggxReflQueue, b->ggxRefrQueue, b->deltaQueue, (Triangle *)b->tris,
+                  (GPUNode *)b->nodes, b->indices, &img, b->probTable, b->aliasTable, b->pdfTable, (Material *)b->materials,
+                  b->texData, (TexDescriptor *)b->textures, P(b), b->numTasks, b->firstIteration);
+        }
+    }
+#elif defined(REF_TU_MAT_ALL)
+    void REF_NAME(mat_all)(const RefBufs *b, size_t begin, size_t end) { REF_LOOP { g_shim_gid = (size_t)g; wavefrontAllMaterials(MATARGS(b, diffuseQueue)); } }
+#elif defined(REF_TU_MAT_DIFFUSE)
+    void REF_NAME(mat_diffuse)(const RefBufs *b, size_t begin, size_t end) { REF_LOOP { g_shim_gid = (size_t)g; wavefrontDiffuse(MATARGS(b, diffuseQueue)); } }
+#elif defined(REF_TU_MAT_GLOSSY)
+    void REF_NAME(mat_glossy)(const RefBufs *b, size_t begin, size_t end) { REF_LOOP { g_shim_gid = (size_t)g; wavefrontGlossy(MATARGS(b, glossyQueue)); } }
+#elif defined(REF_TU_MAT_GGX_REFL)
+    void REF_NAME(mat_ggx_refl)(const RefBufs *b, size_t begin, size_t end) { REF_LOOP { g_shim_gid = (size_t)g; wavefrontGGXReflection(MATARGS(b, ggxReflQueue)); } }
+#elif defined(REF_TU_MAT_GGX_REFR)
+    void REF_NAME(mat_ggx_refr)(const RefBufs *b, size_t begin, size_t end) { REF_LOOP { g_shim_gid = (size_t)g; wavefrontGGXRefraction(MATARGS(b, ggxRefrQueue)); } }
+#elif defined(REF_TU_MAT_DELTA)
+    void REF_NAME(mat_delta)(const RefBufs *b, size_t begin, size_t end) { REF_LOOP { g_shim_gid = (size_t)g; wavefrontDelta(MATARGS(b, deltaQueue)); } }
+#endif
+}

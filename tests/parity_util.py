@@ -1,0 +1,94 @@
+"""Shared helpers of the parity tests: drive two contexts through the same loop and compare their state."""
+import numpy as np
+
+from fluctus_b200 import SLOT, Tracer
+
+USED_SLOTS = [s for s in range(SLOT.COUNT) if s not in SLOT.UNUSED]
+
+
+def slot_name(s):
+    base = max(k for k in SLOT.NAMES if k <= s)
+    return "%s[%d]" % (SLOT.NAMES[base], s - base)
+
+
+def compare_tasks(a, b, what, n_live=None, exact=True):
+    """a, b: (64, N) uint32 path-state dumps. Bit-exact on every slot the wavefront path writes, except lastPdfW of
+    paths whose throughput is zero: the reference leaves pdfW unset there (src/glossy.cl:58-59 returns before writing it,
+    src/wf_mat_*.cl:39 declares it uninitialised), so its value is whatever was on the stack."""
+    n = a.shape[1] if n_live is None else n_live
+    bad = []
+    for s in USED_SLOTS:
+        x, y = a[s, :n], b[s, :n]
+        neq = x != y
+        if s == SLOT.LAST_PDF_W:
+            t_zero = (a[SLOT.T, :n].view(np.float32) == 0) & (a[SLOT.T + 1, :n].view(np.float32) == 0) & (a[SLOT.T + 2, :n].view(np.float32) == 0)
+            neq &= ~t_zero
+        # NaN payloads: compare as floats too (NaN == NaN for our purposes when both are NaN)
+        if neq.any():
+            xf, yf = x.view(np.float32), y.view(np.float32)
+            both_nan = np.isnan(xf) & np.isnan(yf)
+            neq &= ~both_nan
+        if neq.any():
+            idx = np.flatnonzero(neq)
+            bad.append("%s: %d/%d differ, first path %d: %r vs %r (0x%08x vs 0x%08x)" % (
+                slot_name(s), len(idx), n, idx[0], x.view(np.float32)[idx[0]], y.view(np.float32)[idx[0]], x[idx[0]], y[idx[0]]))
+    assert not bad, "%s: path state differs\n  " % what + "\n  ".join(bad)
+
+
+def compare_counters(ca, cb, what):
+    da, db = ca.as_dict(), cb.as_dict()
+    assert da == db, "%s: queue counters differ: %r vs %r" % (what, da, db)
+
+
+def compare_queues(ctx_a, ctx_b, cnt, what):
+    d = cnt.as_dict()
+    for q in ("raygen", "extension", "shadow", "diffuse", "glossy", "ggxRefl", "ggxRefr", "delta"):
+        n = d[q + "Queue"]
+        qa, qb = ctx_a.readQueue(q, n), ctx_b.readQueue(q, n)
+        if q == "raygen":  # order decides the pixel each regenerated path gets (wf_raygen.cl:25)
+            assert np.array_equal(qa, qb), "%s: raygen queue order differs" % what
+        else:
+            assert np.array_equal(np.sort(qa), np.sort(qb)), "%s: %s queue holds different paths" % (what, q)
+
+
+def compare_pixels(pa, pb, what, rtol=1e-4, exact_rgb=False):
+    """pa, pb: (P, 4) accumulators. Alpha (sample count) must match exactly; RGB within rtol of the oracle
+    (|a-b| <= rtol * max(|b|, 1e-3)) -- bit-exact when at most one path per pixel terminates per iteration."""
+    assert np.array_equal(pa[:, 3], pb[:, 3]), "%s: per-pixel sample counts differ (%d pixels)" % (what, int((pa[:, 3] != pb[:, 3]).sum()))
+    if exact_rgb:
+        neq = (pa[:, :3].view(np.uint32) != pb[:, :3].view(np.uint32)) & ~(np.isnan(pa[:, :3]) & np.isnan(pb[:, :3]))
+        assert not neq.any(), "%s: %d pixel channels not bit-identical" % (what, int(neq.sum()))
+        return 0.0
+    err = np.abs(pa[:, :3].astype(np.float64) - pb[:, :3]) / np.maximum(np.abs(pb[:, :3]).astype(np.float64), 1e-3)
+    worst = float(np.nanmax(err)) if err.size else 0.0
+    assert worst <= rtol, "%s: max relative radiance error %.3g > %.1g (%d channels over)" % (what, worst, rtol, int((err > rtol).sum()))
+    return worst
+
+
+def setup_context(ctx, scene, params, env=None):
+    ctx.uploadSceneData(scene)
+    if env is not None:
+        ctx.createEnvMap(env)
+    ctx.setupPixelStorage(params.width, params.height)
+    ctx.updateParams(params)
+    return Tracer(ctx, params)
+
+
+def run_lockstep(gpu, cpu, scene, params, iterations, env=None, check_every=1, exact_rgb=None):
+    """Run the reference's loop on both contexts, comparing complete state after the prologue and after iterations."""
+    tg, tc = setup_context(gpu, scene, params, env), setup_context(cpu, scene, params, env)
+    tg.start()
+    tc.start()
+    compare_tasks(gpu.readTasks(), cpu.readTasks(), "after reset+raygen+extrays")
+    n_pix = params.width * params.height
+    if exact_rgb is None:
+        exact_rgb = gpu.NUM_TASKS <= n_pix
+    for it in range(iterations):
+        cg, cc = tg.iterate(), tc.iterate()
+        what = "iteration %d" % it
+        compare_counters(cg, cc, what)
+        if it % check_every == 0 or it == iterations - 1:
+            compare_queues(gpu, cpu, cc, what)
+            compare_tasks(gpu.readTasks(), cpu.readTasks(), what)
+            compare_pixels(gpu.readPixels(), cpu.readPixels(), what, exact_rgb=exact_rgb)
+    return tg, tc
