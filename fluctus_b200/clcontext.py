@@ -169,11 +169,15 @@ class CLContext:
 
     def readQueue(self, name, n=None):
         out = np.empty(self.NUM_TASKS if n is None else int(n), np.uint32)
+        if out.size == 0:
+            return out
         self._check(self._lib.flx_read_queue(self._h, QUEUE_NAMES.index(name), self._ptr(out), len(out)), "readQueue")
         return out
 
     def writeQueue(self, name, entries):
         entries = np.ascontiguousarray(entries, np.uint32)
+        if entries.size == 0:
+            return
         self._check(self._lib.flx_write_queue(self._h, QUEUE_NAMES.index(name), self._ptr(entries), len(entries)), "writeQueue")
 
     def writeCounters(self, cnt):

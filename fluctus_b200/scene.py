@@ -256,7 +256,7 @@ def build_bvh(tris, max_leaf=4):
     return np.array(nodes, NODE_DTYPE), np.array(order, np.uint32)
 
 
-def make_test_scene(seed=0, n_blobs=6, detail=6, materials="diffuse", textured=False):
+def make_room_scene(seed=0, n_blobs=6, detail=6, materials="diffuse", textured=False):
     """A closed room (so every path keeps bouncing) with a ceiling light gap and a few tessellated spheres.
     materials: "diffuse" (all Lambert) or "mixed" (one sphere per BSDF type of bxdf_types.h:4-11)."""
     rng = np.random.default_rng(seed)
@@ -318,7 +318,7 @@ def make_test_scene(seed=0, n_blobs=6, detail=6, materials="diffuse", textured=F
     return SceneData(tris, indices, nodes, np.array(mats, MATERIAL_DTYPE), tex_desc, tex_data, name="room_%s" % materials)
 
 
-def test_scene_params(scene, width, height, max_bounces=4, separate_queues=False, use_env_map=False, use_area_light=True, **kw):
+def room_params(scene, width, height, max_bounces=4, separate_queues=False, use_env_map=False, use_area_light=True, **kw):
     cam = look_at((0.0, 1.0, 0.95), (0.0, 0.9, -0.2), fov=70.0)
     light = dict(pos=(0.0, 1.98, 0.0), N=(0.0, -1.0, 0.0), right=(1.0, 0.0, 0.0), up=(0.0, 0.0, 1.0), size=(0.3, 0.3), E=(60.0, 60.0, 60.0))
     return make_params(width, height, cam, scene.world_radius, n_tris=len(scene.tris), light=light if use_area_light else False, max_bounces=max_bounces,

@@ -80,9 +80,11 @@ def run_lockstep(gpu, cpu, scene, params, iterations, env=None, check_every=1, e
     tg.start()
     tc.start()
     compare_tasks(gpu.readTasks(), cpu.readTasks(), "after reset+raygen+extrays")
-    n_pix = params.width * params.height
+    # Two paths that hold the same pixel (the pixel counter wraps around the image while older paths are still in
+    # flight, wf_raygen.cl:25) may terminate in the same iteration; the order of their float atomics is free, so RGB is
+    # compared to 1e-5 relative (far inside the 1e-4 of the north star) unless the caller knows better.
     if exact_rgb is None:
-        exact_rgb = gpu.NUM_TASKS <= n_pix
+        exact_rgb = False
     for it in range(iterations):
         cg, cc = tg.iterate(), tc.iterate()
         what = "iteration %d" % it
@@ -90,5 +92,5 @@ def run_lockstep(gpu, cpu, scene, params, iterations, env=None, check_every=1, e
         if it % check_every == 0 or it == iterations - 1:
             compare_queues(gpu, cpu, cc, what)
             compare_tasks(gpu.readTasks(), cpu.readTasks(), what)
-            compare_pixels(gpu.readPixels(), cpu.readPixels(), what, exact_rgb=exact_rgb)
+            compare_pixels(gpu.readPixels(), cpu.readPixels(), what, rtol=1e-5, exact_rgb=exact_rgb)
     return tg, tc

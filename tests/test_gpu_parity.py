@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from fluctus_b200 import CLContext, EnvMapData, SceneData
-from fluctus_b200.scene import make_test_scene, test_scene_params
+from fluctus_b200.scene import make_room_scene, room_params
 
 from conftest import scene_blob
 from parity_util import run_lockstep
@@ -32,25 +32,25 @@ def synthetic_env(w=32, h=16, seed=3):
 
 @pytest.mark.parametrize("separate", [False, True])
 def test_room_diffuse_area_light(separate):
-    scene = make_test_scene(materials="diffuse")
+    scene = make_room_scene(materials="diffuse")
     W, H, N = 96, 64, 4096
-    params = test_scene_params(scene, W, H, max_bounces=4, separate_queues=separate)
+    params = room_params(scene, W, H, max_bounces=4, separate_queues=separate)
     with CLContext(N) as gpu:
         run_lockstep(gpu, oracle_ctx(N), scene, params, iterations=16)
 
 
 @pytest.mark.parametrize("separate", [False, True])
 def test_room_all_bsdfs_textures_normal_map(separate):
-    scene = make_test_scene(materials="mixed", textured=True, n_blobs=8)
+    scene = make_room_scene(materials="mixed", textured=True, n_blobs=8)
     W, H, N = 96, 64, 6144
-    params = test_scene_params(scene, W, H, max_bounces=6, separate_queues=separate)
+    params = room_params(scene, W, H, max_bounces=6, separate_queues=separate)
     with CLContext(N) as gpu:
         run_lockstep(gpu, oracle_ctx(N), scene, params, iterations=20)
 
 
 @pytest.mark.parametrize("area", [False, True])
 def test_room_env_map_mis(area):
-    scene = make_test_scene(materials="mixed", textured=True)
+    scene = make_room_scene(materials="mixed", textured=True)
     # open the room: drop the ceiling and front wall so paths escape to the environment
     keep = np.ones(len(scene.tris), bool)
     keep[2:4] = False
@@ -60,24 +60,24 @@ def test_room_env_map_mis(area):
     nodes, indices = build_bvh(tris)
     scene = SceneData(tris, indices, nodes, scene.materials, scene.tex_desc, scene.tex_data)
     W, H, N = 80, 48, 80 * 48
-    params = test_scene_params(scene, W, H, max_bounces=5, separate_queues=True, use_env_map=True, use_area_light=area, env_map_strength=2.0)
+    params = room_params(scene, W, H, max_bounces=5, separate_queues=True, use_env_map=True, use_area_light=area, env_map_strength=2.0)
     with CLContext(N) as gpu:
         run_lockstep(gpu, oracle_ctx(N), scene, params, iterations=16, env=synthetic_env())
 
 
 @pytest.mark.parametrize("impl,expl", [(True, False), (False, True)])
 def test_room_sampling_modes(impl, expl):
-    scene = make_test_scene(materials="mixed")
+    scene = make_room_scene(materials="mixed")
     W, H, N = 64, 48, 64 * 48
-    params = test_scene_params(scene, W, H, max_bounces=4, sample_impl=impl, sample_expl=expl)
+    params = room_params(scene, W, H, max_bounces=4, sample_impl=impl, sample_expl=expl)
     with CLContext(N) as gpu:
         run_lockstep(gpu, oracle_ctx(N), scene, params, iterations=10)
 
 
 def test_room_russian_roulette_more_paths_than_pixels():
-    scene = make_test_scene(materials="mixed")
+    scene = make_room_scene(materials="mixed")
     W, H, N = 48, 32, 4096  # N > W*H: several paths per pixel in flight, splat order free -> tolerance on RGB
-    params = test_scene_params(scene, W, H, max_bounces=3, use_roulette=True)
+    params = room_params(scene, W, H, max_bounces=3, use_roulette=True)
     with CLContext(N) as gpu:
         run_lockstep(gpu, oracle_ctx(N), scene, params, iterations=12)
 
