@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py -- Mrays/s (extension + shadow) of the wavefront path on the Conference scene at 1920x1080 (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one wavefront iteration (logic -> raygen -> materials -> extension rays -> shadow rays) over the
+NUM_TASKS paths in flight on each GPU.  Prints ONE JSON line on rank 0.  For N > 1 it expects to run under
+`python -m torch.distributed.run --nproc-per-node N` (it re-launches itself that way when started bare).
+
+  value      whole-job Mrays/s with scene and path state resident in HBM, device time (CUDA events on the library's
+             stream), max over ranks
+  e2e        the same metric through the reference-facing per-stage API (fluctus_b200.CLContext driven like
+             Tracer::runBenchmark) starting from HOST buffers: scene upload, per-iteration counter read-back,
+             final image read-back inside the timed region
+  roofline   wf_extrays traversal kernel: algorithmic bytes / measured kernel time vs measured HBM peak
+  cpu_baseline  the reference's own kernels compiled for the host (oracle/_ref, OpenMP) on a bounded sample
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "Mrays/sec (extension+shadow) at 1920x1080, Conference scene"
+UNIT = "Mrays/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scene", default="conference")
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--tasks", type=int, default=1 << 21, help="paths in flight per GPU (NUM_TASKS)")
+    ap.add_argument("--bounces", type=int, default=8)
+    ap.add_argument("--gather-every", type=int, default=16, help="N>1: NCCL gather of the tile radiance every this many iterations")
+    ap.add_argument("--stripe-rows", type=int, default=8)
+    ap.add_argument("--cpu-tasks", type=int, default=1 << 16, help="paths in flight of the CPU sample")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def load_scene(name):
+    from fluctus_b200 import SceneData
+    path = os.path.join(ROOT, "oracle", "_ref", "scenes", name + ".bin")
+    if not os.path.exists(path):
+        raise SystemExit("scene blob %s is missing: run `python oracle/make_scenes.py` where /root/reference exists" % path)
+    return SceneData.load_blob(path)
+
+
+def scene_params(scene, args):
+    from bench_configs import params_for
+    return params_for(args.scene, scene, args.width, args.height, args.bounces)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    FIELDS = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def a_ext_bytes(c):  # bytes the reference's algorithm and layout touch per extension ray
+    r = max(c["rays"], 1)
+    V, B, T, U = c["nodes"] / r, c["boxes"] / r, c["tris"] / r, c["updates"] / r
+    return 84 + 48 * V + 32 * B + 52 * T + 104 * U, dict(V=round(V, 3), B=round(B, 3), T=round(T, 3), U=round(U, 3))
+
+
+def a_shadow_bytes(c):
+    r = max(c["rays"], 1)
+    V, B, T = c["nodes"] / r, c["boxes"] / r, c["tris"] / r
+    return 36 + 48 * V + 32 * B + 52 * T, dict(V=round(V, 3), B=round(B, 3), T=round(T, 3))
+
+
+# ---------------------------------------------------------------------------------------------------------- CPU arm
+def run_cpu(args, scene, params, steps, warmup, seconds=None):
+    """The reference's own wavefront kernels, host-compiled (oracle/_ref, OpenMP over the NDRange, float atomics on) --
+    or the C restatement when _ref was not built -- on a bounded sample: same scene, camera, image and loop, fewer paths
+    in flight (cpu_tasks) so a step takes a fraction of a second."""
+    from fluctus_b200 import Tracer
+    from oracle.oracle_host import PortContext, RefContext, ref_available
+    kind = "reference" if ref_available() else "port"
+    ctx = (RefContext if kind == "reference" else PortContext)(args.cpu_tasks, parallel=True)
+    ctx.uploadSceneData(scene)
+    ctx.setupPixelStorage(params.width, params.height)
+    tr = Tracer(ctx, params)
+    tr.start()
+    for _ in range(warmup):
+        tr.iterate()
+    r0 = tr.stats["extensionRays"] + tr.stats["shadowRays"]
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        tr.iterate()
+        done += 1
+        if seconds is not None and time.perf_counter() - t0 > seconds:
+            break
+    dt = time.perf_counter() - t0
+    rays = tr.stats["extensionRays"] + tr.stats["shadowRays"] - r0
+    cores = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
+    return dict(value=rays / dt / 1e6, unit=UNIT, cores=cores, kind=kind, steps=done, seconds=dt,
+                sample="%s %dx%d, %d bounces, %d paths in flight, %d wavefront iterations after %d warm-up; %s kernels, g++ -O3 -march=native, OpenMP %d threads"
+                       % (args.scene, params.width, params.height, params.maxBounces, args.cpu_tasks, done, warmup,
+                          "reference OpenCL (host-compiled)" if kind == "reference" else "C restatement", cores))
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    scene = load_scene(args.scene)
+    params = scene_params(scene, args)
+    res = run_cpu(args, scene, params, args.steps, max(args.warmup, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": res["steps"], "warmup": args.warmup,
+            "ms_per_step": res["seconds"] * 1e3 / max(res["steps"], 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "reference asset (conference.obj) through the reference's loader and SBVH builder; no GPU",
+            "config": workload_config(args, params, cpu=True),
+            "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, params, cpu=False):
+    return {"workload": "%s %dx%d, %d bounces, MIS (sampleImpl+sampleExpl), area light, single material queue" % (args.scene, params.width, params.height, params.maxBounces),
+            "num_tasks_per_gpu": args.cpu_tasks if cpu else args.tasks,
+            "l2_policy": "inputs larger than L2: path state %d MiB per GPU is streamed every stage" % ((args.cpu_tasks if cpu else args.tasks) * 256 >> 20)}
+
+
+# ---------------------------------------------------------------------------------------------------------- GPU arm
+def main_ours(args):
+    import numpy as np
+    import torch
+    from fluctus_b200 import CLContext, QueueCounters, Tracer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus > 1 and world == 1:  # started bare: launch one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus), "--master-addr", "127.0.0.1",
+               "--master-port", str(29500 + os.getpid() % 1000)] + sys.argv
+        raise SystemExit(subprocess.call(cmd))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    scene = load_scene(args.scene)
+    params = scene_params(scene, args)
+    ctx = CLContext(args.tasks, device=local)
+    if world > 1:
+        ctx.setTile(rank, world, args.stripe_rows)
+    # ---- e2e leg first (it starts from host buffers): upload, K iterations through the per-stage API, image read-back
+    e2e = None
+    if not args.no_e2e:
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ctx.uploadSceneData(scene)
+        ctx.setupPixelStorage(params.width, params.height)
+        tr = Tracer(ctx, params)
+        tr.start()
+        for _ in range(args.warmup + args.steps):
+            tr.iterate()
+        img = ctx.readPixels()
+        dt = time.perf_counter() - t0
+        rays = tr.stats["extensionRays"] + tr.stats["shadowRays"]
+        tot = torch.tensor([float(rays), dt], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            r = tot[:1].clone(); dist.all_reduce(r); t = tot[1:].clone(); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            rays, dt = float(r.item()), float(t.item())
+        n_it = args.warmup + args.steps
+        e2e = {"value": rays / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(scene.nbytes() / n_it + 240 / n_it + 36),
+               "d2h_bytes_per_step": int(img.nbytes / n_it + 32), "iterations": n_it, "seconds": dt,
+               "what": "host scene arrays -> uploadSceneData, Tracer.start, per-stage enqueue calls with counter read-back and finishQueue every iteration (tracer.cpp:431-470), readPixels; wall clock, max over ranks"}
+    else:
+        ctx.uploadSceneData(scene)
+        ctx.setupPixelStorage(params.width, params.height)
+
+    # ---- device-resident leg
+    tr = Tracer(ctx, params)
+    tr.start()
+    if world > 1:
+        uid = [ctx.commUniqueId() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.commInit(uid[0], rank, world)
+    ctx.render(max(args.warmup, 3))
+    if world > 1:
+        ctx.gatherPixels(0)
+    ctx.finishQueue()
+    ctx.resetStats()
+    ctx.setProfiling(True)
+    sampler = ClockSampler(local)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    ctx.timerBegin()
+    done, gathers = 0, 0
+    while done < args.steps:
+        n = min(args.gather_every, args.steps - done) if world > 1 else args.steps - done
+        ctx.render(n)
+        done += n
+        if world > 1:
+            ctx.gatherPixels(0)
+            gathers += 1
+    ms = ctx.timerEnd()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    clocks = sampler.stop()
+    st = ctx.getStats()
+    rays = int(st.extensionRays + st.shadowRays)
+    perf = ctx.checkTracingPerf()
+    launches = sum(n for _, n in perf.values()) + args.steps  # + one counter-snapshot kernel per iteration
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+        r = torch.tensor([float(rays), float(launches)], dtype=torch.float64, device="cuda"); dist.all_reduce(r)
+        rays, launches = int(r[0].item()), int(r[1].item())
+    ctx.setProfiling(False)
+
+    # ---- roofline of the dominant kernel (rank 0's launches): algorithmic bytes per ray from an instrumented pass
+    ctx.setCounting(True)
+    ctx.render(8)
+    counts = ctx.getTraceCounts()
+    ctx.setCounting(False)
+    a_ext, per_ext = a_ext_bytes(counts["ext"])
+    a_sh, per_sh = a_shadow_bytes(counts["shadow"])
+    ext_ms, ext_n = perf["extrays"]
+    sh_ms, sh_n = perf["shadowrays"]
+    ext_rays_per_launch = st.extensionRays / max(st.iterations, 1)
+    sh_rays_per_launch = st.shadowRays / max(st.iterations, 1)
+    peak, peak_src = measured_peaks()
+    achieved = a_ext * ext_rays_per_launch / (ext_ms / max(ext_n, 1) * 1e-3) / 1e9 if ext_ms > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "extrays_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    kernel_share = {k: round(v[0] / ms, 4) for k, v in perf.items() if v[1]}
+    roofline = {"kernel": "k_extrays (wf_extrays SBVH closest-hit traversal)", "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_ray": round(a_ext, 1), "per_ray": per_ext, "rays_per_launch": int(ext_rays_per_launch),
+                "avg_launch_ms": round(ext_ms / max(ext_n, 1), 4), "mrays_per_s": round(ext_rays_per_launch / (ext_ms / max(ext_n, 1)) / 1e3, 1) if ext_ms else None,
+                "frac_of_nominal_8TBs": round(achieved / 8000.0, 4),
+                "shadow": {"algorithmic_bytes_per_ray": round(a_sh, 1), "per_ray": per_sh, "avg_launch_ms": round(sh_ms / max(sh_n, 1), 4),
+                           "achieved": round(a_sh * sh_rays_per_launch / (sh_ms / max(sh_n, 1) * 1e-3) / 1e9, 1) if sh_ms else None,
+                           "mrays_per_s": round(sh_rays_per_launch / (sh_ms / max(sh_n, 1)) / 1e3, 1) if sh_ms else None},
+                "kernel_share_of_step": kernel_share}
+
+    if rank != 0:
+        ctx.close()
+        if dist is not None:
+            dist.barrier(); dist.destroy_process_group()
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        res = run_cpu(args, scene, params, steps=10 ** 6, warmup=2, seconds=args.cpu_seconds)
+        cpu = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    cfg = workload_config(args, params)
+    cfg.update({"parallelism": "image stripes x%d, full scene replica per GPU, NCCL gather every %d iterations" % (world, args.gather_every) if world > 1 else "single GPU",
+                "timing": "CUDA events on the library stream around %d iterations (flx_timer_begin/end), max over ranks" % args.steps})
+    line = {"metric": METRIC, "value": rays / (ms * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "reference asset conference.obj (282,655 triangles) through the reference's own loader and SBVH builder; synthetic camera/light of SURVEY 8d; seeds = path index",
+            "config": cfg, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+    ctx.close()
+    if dist is not None:
+        dist.barrier(); dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        main_reference(a)
+    else:
+        main_ours(a)

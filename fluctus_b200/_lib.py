@@ -32,6 +32,11 @@ _SIGNATURES = {
     "flx_reset_pixel_index": (C.c_int, [_P]),
     "flx_num_tasks": (C.c_uint32, [_P]),
     "flx_render": (C.c_int, [_P, C.c_uint32]),
+    "flx_render_timed": (C.c_int, [_P, C.c_uint32, C.POINTER(C.c_float)]),
+    "flx_timer_begin": (C.c_int, [_P]),
+    "flx_timer_end": (C.c_int, [_P, C.POINTER(C.c_float)]),
+    "flx_set_counting": (C.c_int, [_P, C.c_int]),
+    "flx_get_trace_counts": (C.c_int, [_P, _P, _P]),
     "flx_reset_stats": (C.c_int, [_P]),
     "flx_get_stats": (C.c_int, [_P, C.POINTER(RenderStats64)]),
     "flx_set_profiling": (C.c_int, [_P, C.c_int]),

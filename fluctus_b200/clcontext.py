@@ -127,6 +127,31 @@ class CLContext:
     def render(self, iterations):
         self._check(self._lib.flx_render(self._h, int(iterations)), "render")
 
+    def renderTimed(self, iterations):
+        """flx_render bracketed by CUDA events on the context's stream; returns device milliseconds."""
+        ms = C.c_float()
+        self._check(self._lib.flx_render_timed(self._h, int(iterations), C.byref(ms)), "renderTimed")
+        return ms.value
+
+    def timerBegin(self):
+        self._check(self._lib.flx_timer_begin(self._h), "timerBegin")
+
+    def timerEnd(self):
+        ms = C.c_float()
+        self._check(self._lib.flx_timer_end(self._h, C.byref(ms)), "timerEnd")
+        return ms.value
+
+    def setCounting(self, enabled):
+        self._check(self._lib.flx_set_counting(self._h, 1 if enabled else 0), "setCounting")
+
+    def getTraceCounts(self):
+        """{'ext': {...}, 'shadow': {...}} totals of nodes/boxes/tris/updates/rays since setCounting(True)."""
+        a = (C.c_uint64 * 5)()
+        b = (C.c_uint64 * 5)()
+        self._check(self._lib.flx_get_trace_counts(self._h, a, b), "getTraceCounts")
+        keys = ("nodes", "boxes", "tris", "updates", "rays")
+        return {"ext": dict(zip(keys, map(int, a))), "shadow": dict(zip(keys, map(int, b)))}
+
     def resetStats(self):
         self._check(self._lib.flx_reset_stats(self._h), "resetStats")
 

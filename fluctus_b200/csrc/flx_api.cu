@@ -103,7 +103,12 @@ struct flx_ctx
     bool paramsSet = false;
     float tanHalfFov = 0.0f;
 
+    // traversal work counters (flx_set_counting): [0..4] extension V,B,T,U,rays  [5..9] shadow V,B,T,U,rays
+    unsigned long long *traceCounts = nullptr;
+    bool counting = false;
+
     // timing
+    cudaEvent_t evStart = nullptr, evStop = nullptr;
     bool profiling = false;
     std::vector<EventPair> pendingEvents, freeEvents;
     double kernelMs[FLX_K_COUNT] = {};
@@ -482,6 +487,10 @@ int flx_create(int device, uint32_t num_tasks, flx_ctx **out)
     CUB(cudaMalloc(&c->scanTiles, (size_t)c->numScanTiles * sizeof(unsigned long long)));
     CUB(cudaMalloc(&c->scanTicket, sizeof(uint32_t)));
     CUB(cudaMallocHost(&c->pinnedCounters, sizeof(flx_QueueCounters) * flx_ctx::kCounterRing));
+    CUB(cudaMalloc(&c->traceCounts, 10 * sizeof(unsigned long long)));
+    CUB(cudaMemset(c->traceCounts, 0, 10 * sizeof(unsigned long long)));
+    CUB(cudaEventCreate(&c->evStart));
+    CUB(cudaEventCreate(&c->evStop));
     // dummy 1x1 environment map (CLContext::setupScene, clcontext.cpp:513-519)
     CUB(cudaMalloc(&c->envRGBA, 4 * sizeof(float)));
     CUB(cudaMemset(c->envRGBA, 0, 4 * sizeof(float)));
@@ -520,6 +529,11 @@ void flx_destroy(flx_ctx *c)
     freeDev(c->currPixelIdx);
     freeDev(c->scanTiles);
     freeDev(c->scanTicket);
+    freeDev(c->traceCounts);
+    if (c->evStart)
+        cudaEventDestroy(c->evStart);
+    if (c->evStop)
+        cudaEventDestroy(c->evStop);
     if (c->pinnedCounters)
         cudaFreeHost(c->pinnedCounters);
     freeDev(c->tris);
@@ -726,7 +740,11 @@ int flx_enqueue_extrays(flx_ctx *ctx)
         return rc;
     CU(cudaSetDevice(ctx->device));
     Timed tm(ctx, FLX_K_EXTRAYS);
-    k_extrays<<<(ctx->numTasks + FLX_TRACE_BLOCK - 1) / FLX_TRACE_BLOCK, FLX_TRACE_BLOCK, 0, ctx->stream>>>(makeFrame(ctx), ctx->params, makeBvh(ctx), ctx->tris);
+    const unsigned grid = (ctx->numTasks + FLX_TRACE_BLOCK - 1) / FLX_TRACE_BLOCK;
+    if (ctx->counting)
+        k_extrays<RayCount><<<grid, FLX_TRACE_BLOCK, 0, ctx->stream>>>(makeFrame(ctx), ctx->params, makeBvh(ctx), ctx->tris, ctx->traceCounts);
+    else
+        k_extrays<NoCount><<<grid, FLX_TRACE_BLOCK, 0, ctx->stream>>>(makeFrame(ctx), ctx->params, makeBvh(ctx), ctx->tris, nullptr);
     return launchCheck(ctx, "k_extrays");
 }
 
@@ -737,7 +755,11 @@ int flx_enqueue_shadowrays(flx_ctx *ctx)
         return rc;
     CU(cudaSetDevice(ctx->device));
     Timed tm(ctx, FLX_K_SHADOWRAYS);
-    k_shadowrays<<<(ctx->numTasks + FLX_TRACE_BLOCK - 1) / FLX_TRACE_BLOCK, FLX_TRACE_BLOCK, 0, ctx->stream>>>(makeFrame(ctx), ctx->params, makeBvh(ctx));
+    const unsigned grid = (ctx->numTasks + FLX_TRACE_BLOCK - 1) / FLX_TRACE_BLOCK;
+    if (ctx->counting)
+        k_shadowrays<RayCount><<<grid, FLX_TRACE_BLOCK, 0, ctx->stream>>>(makeFrame(ctx), ctx->params, makeBvh(ctx), ctx->traceCounts + 5);
+    else
+        k_shadowrays<NoCount><<<grid, FLX_TRACE_BLOCK, 0, ctx->stream>>>(makeFrame(ctx), ctx->params, makeBvh(ctx), nullptr);
     return launchCheck(ctx, "k_shadowrays");
 }
 
@@ -879,6 +901,79 @@ int flx_render(flx_ctx *ctx, uint32_t n_iterations)
         }
         if ((rc = launchCheck(ctx, "k_end_iteration")))
             return rc;
+    }
+    return 0;
+}
+
+int flx_render_timed(flx_ctx *ctx, uint32_t n_iterations, float *elapsed_ms)
+{
+    if (!ctx)
+        return FLX_E_INVALID;
+    REQUIRE(elapsed_ms != nullptr, "flx_render_timed: null destination");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaEventRecord(ctx->evStart, ctx->stream));
+    int rc = flx_render(ctx, n_iterations);
+    if (rc)
+        return rc;
+    CU(cudaEventRecord(ctx->evStop, ctx->stream));
+    CU(cudaEventSynchronize(ctx->evStop));
+    CU(cudaEventElapsedTime(elapsed_ms, ctx->evStart, ctx->evStop));
+    drainEvents(ctx);
+    return 0;
+}
+
+int flx_timer_begin(flx_ctx *ctx)
+{
+    if (!ctx)
+        return FLX_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaEventRecord(ctx->evStart, ctx->stream));
+    return 0;
+}
+
+int flx_timer_end(flx_ctx *ctx, float *elapsed_ms)
+{
+    if (!ctx)
+        return FLX_E_INVALID;
+    REQUIRE(elapsed_ms != nullptr, "flx_timer_end: null destination");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaEventRecord(ctx->evStop, ctx->stream));
+    CU(cudaEventSynchronize(ctx->evStop));
+    CU(cudaEventElapsedTime(elapsed_ms, ctx->evStart, ctx->evStop));
+    drainEvents(ctx);
+    return 0;
+}
+
+int flx_set_counting(flx_ctx *ctx, int enabled)
+{
+    if (!ctx)
+        return FLX_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    ctx->counting = enabled != 0;
+    if (ctx->counting)
+        CU(cudaMemsetAsync(ctx->traceCounts, 0, 10 * sizeof(unsigned long long), ctx->stream));
+    return 0;
+}
+
+int flx_get_trace_counts(flx_ctx *ctx, flx_TraceCounts *ext, flx_TraceCounts *shadow)
+{
+    if (!ctx)
+        return FLX_E_INVALID;
+    REQUIRE(ext && shadow, "flx_get_trace_counts: null destination");
+    CU(cudaSetDevice(ctx->device));
+    unsigned long long h[10];
+    CU(cudaMemcpyAsync(h, ctx->traceCounts, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    flx_TraceCounts *o[2] = {ext, shadow};
+    for (int k = 0; k < 2; k++)
+    {
+        o[k]->nodes = h[5 * k + 0];
+        o[k]->boxes = h[5 * k + 1];
+        o[k]->tris = h[5 * k + 2];
+        o[k]->updates = h[5 * k + 3];
+        o[k]->rays = h[5 * k + 4];
     }
     return 0;
 }

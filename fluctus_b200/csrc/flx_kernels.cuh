@@ -154,8 +154,25 @@ struct LocalStack
     FLX_DEV int &operator[](int i) { return s[i]; }
 };
 
+// warp-reduce the per-ray work counters and add them to the context totals (instrumented launches only)
+FLX_DEV void flush_counts(const RayCount &c, unsigned long long *totals, bool traced)
+{
+    unsigned v[5] = {c.V, c.B, c.T, c.U, traced ? 1u : 0u};
+    const unsigned active = __activemask();
+#pragma unroll
+    for (int k = 0; k < 5; k++)
+    {
+        unsigned x = v[k];
+        x = __reduce_add_sync(active, x);
+        if ((threadIdx.x & 31) == (__ffs(active) - 1))
+            atomicAdd(totals + k, (unsigned long long)x);
+    }
+}
+FLX_DEV void flush_counts(const NoCount &, unsigned long long *, bool) {}
+
+template <class COUNT>
 __global__ void __launch_bounds__(FLX_TRACE_BLOCK) k_extrays(const __grid_constant__ Frame fr, const __grid_constant__ flx_RenderParams prm, const BvhView bvh,
-                                                             const flx_Triangle *tris160)
+                                                             const flx_Triangle *tris160, unsigned long long *countTotals)
 {
     const uint32_t count = fr.counters->extensionQueue;
     const uint32_t gd = blockIdx.x * FLX_TRACE_BLOCK + threadIdx.x;
@@ -168,7 +185,9 @@ __global__ void __launch_bounds__(FLX_TRACE_BLOCK) k_extrays(const __grid_consta
     float tbest = 3.402823466e+38f, ub = 0.0f, vb = 0.0f;
     int tri = -1;
     LocalStack stack;
-    trace_closest(bvh, o, d, tbest, ub, vb, tri, stack);
+    COUNT cnt;
+    trace_closest(bvh, o, d, tbest, ub, vb, tri, stack, cnt);
+    flush_counts(cnt, countTotals, true);
 
     // hit record (bvh.cl:271-279): attributes of the winning triangle, fetched once
     V3 P = v3(0.0f), N = v3(0.0f);
@@ -208,7 +227,9 @@ __global__ void __launch_bounds__(FLX_TRACE_BLOCK) k_extrays(const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------------ shadow rays
-__global__ void __launch_bounds__(FLX_TRACE_BLOCK) k_shadowrays(const __grid_constant__ Frame fr, const __grid_constant__ flx_RenderParams prm, const BvhView bvh)
+template <class COUNT>
+__global__ void __launch_bounds__(FLX_TRACE_BLOCK) k_shadowrays(const __grid_constant__ Frame fr, const __grid_constant__ flx_RenderParams prm, const BvhView bvh,
+                                                                unsigned long long *countTotals)
 {
     const uint32_t count = fr.counters->shadowQueue;
     const uint32_t gd = blockIdx.x * FLX_TRACE_BLOCK + threadIdx.x;
@@ -224,11 +245,13 @@ __global__ void __launch_bounds__(FLX_TRACE_BLOCK) k_shadowrays(const __grid_con
         float tl = lenL;
         occluded = light_quad(prm.areaLight, o, d, tl);
     }
+    COUNT cnt;
     if (!occluded)
     {
         LocalStack stack;
-        occluded = trace_any(bvh, o, d, lenL, stack);
+        occluded = trace_any(bvh, o, d, lenL, stack, cnt);
     }
+    flush_counts(cnt, countTotals, true);
     t.setu(FLX_S_SHADOW_BLOCKED, gid, occluded ? 1u : 0u);
 }
 

@@ -30,6 +30,25 @@
 
 #define FLX_STACK_DEPTH 64 // reference: uint stack[64] (bvh.cl:240); builders cap depth at 64 (bvh.hpp:71)
 
+// Per-ray work counters in the reference's terms: V = nodes popped (inner or leaf, bvh.cl:251/329),
+// B = child boxes tested (bvh.cl:283-284), T = triangles tested (bvh.cl:260), U = closest-hit updates (bvh.cl:271-279).
+// They feed the algorithmic-bytes numerator of the roofline; NoCount compiles to nothing.
+struct NoCount
+{
+    FLX_DEV void inner() {}
+    FLX_DEV void leaf() {}
+    FLX_DEV void tri() {}
+    FLX_DEV void update() {}
+};
+struct RayCount
+{
+    unsigned V = 0, B = 0, T = 0, U = 0;
+    FLX_DEV void inner() { V++; B += 2; }
+    FLX_DEV void leaf() { V++; }
+    FLX_DEV void tri() { T++; }
+    FLX_DEV void update() { U++; }
+};
+
 struct BvhView
 {
     const float4 *nodes; // TNode as 4 x float4
@@ -76,7 +95,7 @@ FLX_DEV bool tri_test(V3 v0, V3 s1, V3 s2, V3 o, V3 d, float &t, float &u, float
 
 // Closest hit. On return tbest/ubest/vbest/tribest describe the hit (tribest = -1: none).
 // STACK is any int-indexable object (local array or strided shared-memory view).
-template <class STACK> FLX_DEV void trace_closest(const BvhView &bvh, V3 o, V3 d, float &tbest, float &ubest, float &vbest, int &tribest, STACK &stack)
+template <class STACK, class COUNT> FLX_DEV void trace_closest(const BvhView &bvh, V3 o, V3 d, float &tbest, float &ubest, float &vbest, int &tribest, STACK &stack, COUNT &cnt)
 {
     const V3 idir = v3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z); // native_recip pinned to IEEE 1/x
     int sp = 0;
@@ -85,6 +104,7 @@ template <class STACK> FLX_DEV void trace_closest(const BvhView &bvh, V3 o, V3 d
     {
         if (cur >= 0)
         {
+            cnt.inner();
             const float4 *n = bvh.nodes + 4 * (size_t)cur;
             const float4 q0 = __ldg(n), q1 = __ldg(n + 1), q2 = __ldg(n + 2);
             const int4 q3 = __ldg(reinterpret_cast<const int4 *>(n + 3));
@@ -119,12 +139,14 @@ template <class STACK> FLX_DEV void trace_closest(const BvhView &bvh, V3 o, V3 d
             // leaf: best of the leaf first, then strict "<" against the ray's best (bvh.cl:255-279)
             float tmin = 3.402823466e+38f, umin = 0.0f, vmin = 0.0f;
             int imin = -1;
+            cnt.leaf();
             const float4 *p = bvh.tris + 3 * (size_t)(~cur);
             while (true)
             {
                 const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
                 const int tag = __float_as_int(a.w);
                 float t, u, v;
+                cnt.tri();
                 if (tri_test(v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), o, d, t, u, v))
                 {
                     if (t > 0.0f && t < tmin)
@@ -141,6 +163,7 @@ template <class STACK> FLX_DEV void trace_closest(const BvhView &bvh, V3 o, V3 d
             }
             if (imin != -1 && tmin < tbest)
             {
+                cnt.update();
                 tribest = imin;
                 tbest = tmin;
                 ubest = umin;
@@ -155,7 +178,7 @@ template <class STACK> FLX_DEV void trace_closest(const BvhView &bvh, V3 o, V3 d
 
 // Any hit with 0 < t < maxDist (reference: bvh_occluded, src/bvh.cl:312-373). The answer does not
 // depend on the visiting order; near-first is kept because it finds occluders soonest.
-template <class STACK> FLX_DEV bool trace_any(const BvhView &bvh, V3 o, V3 d, float maxDist, STACK &stack)
+template <class STACK, class COUNT> FLX_DEV bool trace_any(const BvhView &bvh, V3 o, V3 d, float maxDist, STACK &stack, COUNT &cnt)
 {
     const V3 idir = v3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
     int sp = 0;
@@ -164,6 +187,7 @@ template <class STACK> FLX_DEV bool trace_any(const BvhView &bvh, V3 o, V3 d, fl
     {
         if (cur >= 0)
         {
+            cnt.inner();
             const float4 *n = bvh.nodes + 4 * (size_t)cur;
             const float4 q0 = __ldg(n), q1 = __ldg(n + 1), q2 = __ldg(n + 2);
             const int4 q3 = __ldg(reinterpret_cast<const int4 *>(n + 3));
@@ -195,11 +219,13 @@ template <class STACK> FLX_DEV bool trace_any(const BvhView &bvh, V3 o, V3 d, fl
         }
         else
         {
+            cnt.leaf();
             const float4 *p = bvh.tris + 3 * (size_t)(~cur);
             while (true)
             {
                 const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
                 float t, u, v;
+                cnt.tri();
                 if (tri_test(v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), o, d, t, u, v) && t > 0.0f && t < maxDist)
                     return true;
                 if (__float_as_int(a.w) < 0)

@@ -58,6 +58,10 @@ typedef struct { uint32_t raygenQueue, extensionQueue, shadowQueue, diffuseQueue
 typedef struct { uint32_t primaryRays, extensionRays, shadowRays, samples; } flx_RenderStats;             /* geom.h:254-260 */
 typedef struct { uint64_t primaryRays, extensionRays, shadowRays, samples, iterations; } flx_RenderStats64; /* same counters, 64-bit (new) */
 typedef struct { float primary, extension, shadow, samples, total; } flx_PerfNumbers;                     /* clcontext.hpp:12-19 */
+/* traversal work in the reference's terms, summed over rays (new; numerator of the roofline):
+ * nodes popped (bvh.cl:251/329), child boxes tested (bvh.cl:283-284), triangles tested (bvh.cl:260),
+ * closest-hit updates (bvh.cl:271-279), rays traced */
+typedef struct { uint64_t nodes, boxes, tris, updates, rays; } flx_TraceCounts;
 
 /* BSDF type bits, reference src/bxdf_types.h:4-11 */
 #define FLX_BXDF_DIFFUSE (1 << 1)
@@ -132,6 +136,17 @@ uint32_t flx_num_tasks(const flx_ctx *ctx);
  * what the host does between iterations (stats += counters, pixelIdx = (pixelIdx + cnt.raygen) % numPixels
  * [clcontext.cpp:891-895], counters = 0).  Results are identical to driving the single calls above. */
 int flx_render(flx_ctx *ctx, uint32_t n_iterations);
+
+/* flx_render bracketed by CUDA events on the context's stream; elapsed_ms is device time (synchronises). */
+int flx_render_timed(flx_ctx *ctx, uint32_t n_iterations, float *elapsed_ms);
+/* a CUDA-event pair on the context's stream around any sequence of calls (begin synchronises first, end waits) */
+int flx_timer_begin(flx_ctx *ctx);
+int flx_timer_end(flx_ctx *ctx, float *elapsed_ms);
+
+/* Instrumented traversal: while enabled, flx_enqueue_extrays / flx_enqueue_shadowrays also count the work the
+ * reference's algorithm does per ray (results are unchanged). Used outside timed regions only. */
+int flx_set_counting(flx_ctx *ctx, int enabled);
+int flx_get_trace_counts(flx_ctx *ctx, flx_TraceCounts *ext, flx_TraceCounts *shadow);
 
 /* CLContext::resetStats/getStats/updateRenderPerf/getRenderPerf (clcontext.hpp:66-70; clcontext.cpp:634-666).
  * Totals are accumulated on the device by flx_render (64-bit) and are read here (synchronises). */

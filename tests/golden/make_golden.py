@@ -1,0 +1,85 @@
+#!/usr/bin/env python
+"""make_golden.py -- generates the committed golden vectors by running the REFERENCE'S OWN wavefront kernels, compiled
+for the host (oracle/_ref/libfluctus_ref.so, built by oracle/build_ref.py from /root/reference/src/wf_*.cl), serially.
+
+Each fixture holds the complete path state (64 x N uint32 slots) after the prologue and after K iterations, the
+radiance accumulator and the ray counts.  Inputs are regenerated deterministically by build_case(); only the
+reference-derived teapot scene (reference asset assets/teapot.ply through the reference's PLY import and SBVH builder)
+is stored inside its fixture, because neither exists on the GPU box or in a fresh clone.
+
+    python tests/golden/make_golden.py          # needs /root/reference (or FLX_REFERENCE_DIR)
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+CASES = ("room_mixed_separate", "room_env_mis", "teapot_c1")
+
+
+def build_case(name, blob_loader=None):
+    """-> (scene, params, env or None, num_tasks, iterations)"""
+    from fluctus_b200 import EnvMapData, SceneData, make_params
+    from fluctus_b200.scene import build_bvh, make_room_scene, room_params
+    if name == "room_mixed_separate":
+        scene = make_room_scene(materials="mixed", textured=True, n_blobs=8)
+        return scene, room_params(scene, 48, 32, max_bounces=6, separate_queues=True), None, 2048, 12
+    if name == "room_env_mis":
+        scene = make_room_scene(materials="mixed", textured=True)
+        keep = np.ones(len(scene.tris), bool)
+        keep[2:4] = False
+        keep[6:8] = False
+        tris = scene.tris[keep]
+        nodes, indices = build_bvh(tris)
+        scene = SceneData(tris, indices, nodes, scene.materials, scene.tex_desc, scene.tex_data)
+        rng = np.random.default_rng(3)
+        rgb = rng.uniform(0.0, 0.4, size=(16, 32, 3)).astype(np.float32)
+        rgb[3:5, 5:8] += 25.0
+        env = EnvMapData.from_rgb(rgb)
+        return scene, room_params(scene, 40, 24, max_bounces=5, separate_queues=False, use_env_map=True, use_area_light=True, env_map_strength=2.0), env, 960, 12
+    if name == "teapot_c1":  # BASELINE config C1 at 64x64: teapot.ply, 2 bounces, default camera and light (tracer.cpp:760-797)
+        fix = os.path.join(HERE, "teapot_c1.npz")
+        if os.path.exists(fix):
+            z = np.load(fix)
+            from fluctus_b200.structs import MATERIAL_DTYPE, NODE_DTYPE, TRIANGLE_DTYPE
+            scene = SceneData(z["scene_tris"].view(TRIANGLE_DTYPE).reshape(-1), z["scene_indices"], z["scene_nodes"].view(NODE_DTYPE).reshape(-1),
+                              z["scene_materials"].view(MATERIAL_DTYPE).reshape(-1), name="teapot")
+        else:
+            scene = SceneData.load_blob(blob_loader("teapot") if blob_loader else os.path.join(ROOT, "oracle", "_ref", "scenes", "teapot.bin"))
+        cam = dict(pos=(0, 1, 3.5), dir=(0, 0, -1), right=(1, 0, 0), up=(0, 1, 0), fov=60.0)
+        return scene, make_params(64, 64, cam, scene.world_radius, len(scene.tris), max_bounces=2), None, 4096, 16
+    raise KeyError(name)
+
+
+def main():
+    from oracle import build_ref, make_scenes
+    from oracle.oracle_host import RefContext
+    from parity_util import setup_context
+    build_ref.build()
+    make_scenes.build(["teapot"])
+    for name in CASES:
+        fix = os.path.join(HERE, name + ".npz")
+        if name == "teapot_c1" and os.path.exists(fix):
+            os.remove(fix)  # rebuild the scene from the reference asset, not from the old fixture
+        scene, params, env, n, iters = build_case(name)
+        ctx = RefContext(n)
+        tr = setup_context(ctx, scene, params, env)
+        tr.start()
+        out = dict(tasks_start=ctx.readTasks())
+        for _ in range(iters):
+            tr.iterate()
+        out.update(tasks_end=ctx.readTasks(), pixels=ctx.readPixels(), stats=np.array([tr.stats[k] for k in ("primaryRays", "extensionRays", "shadowRays")], np.int64))
+        if name == "teapot_c1":
+            out.update(scene_tris=scene.tris.view(np.uint8), scene_indices=scene.indices, scene_nodes=scene.nodes.view(np.uint8), scene_materials=scene.materials.view(np.uint8))
+        np.savez_compressed(fix, **out)
+        print(name, os.path.getsize(fix), "bytes;", dict(zip(("primary", "extension", "shadow"), out["stats"])))
+
+
+if __name__ == "__main__":
+    main()
