@@ -35,7 +35,7 @@ UNIT = "Mrays/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=500)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scene", default="conference")
@@ -76,44 +76,63 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks and throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-
-    FIELDS = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md): NVML polled every 5 ms from a
+    thread (nvidia-smi -lms cannot start fast enough for a sub-second region); falls back to one nvidia-smi query."""
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.stop_flag, self.thread = index, [], False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(index)
+        except Exception:
+            self.nv = None
+
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((sm, reasons))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+        if self.nv:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
 
     def stop(self):
-        if self.proc:
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=2)
-            except Exception:
-                self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-            except Exception:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=1)
+        if not self.nv or not self.rows:
+            return self._smi_once()
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "hw_power_brake_slowdown": 0x80}
+        seen = set()
+        for _, r in self.rows:
+            for n, bit in names.items():
+                if r & bit:
+                    seen.add(n)
+        try:
+            mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+        except Exception:
+            mx = None
+        return {"sm_mhz": statistics.median(s for s, _ in self.rows), "sm_max_mhz": mx, "reasons": sorted(seen), "samples": len(self.rows)}
+
+    def _smi_once(self):
+        try:
+            out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits"],
+                                 capture_output=True, text=True, timeout=10).stdout.split(",")
+            return {"sm_mhz": float(out[0]), "sm_max_mhz": float(out[1]), "reasons": [], "samples": 1, "note": "single nvidia-smi query after the timed region"}
+        except Exception:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
 def a_ext_bytes(c):  # SURVEY 8(d): bytes the reference's algorithm and layout touch per extension ray
@@ -188,24 +207,21 @@ def main_ours(args):
     import torch
     from fluctus_b200 import CLContext, QueueCounters, Tracer
 
+    from fluctus_b200 import dist as fd
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.gpus > 1 and world == 1:  # started bare: launch one rank per GPU
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus), "--master-addr", "127.0.0.1",
                "--master-port", str(29500 + os.getpid() % 1000)] + sys.argv
         raise SystemExit(subprocess.call(cmd))
+    rank, world, local = fd.init("nccl")
     dist = None
     if world > 1:
         import torch.distributed as dist
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     scene = load_scene(args.scene)
     params = scene_params(scene, args)
     ctx = CLContext(args.tasks, device=local)
-    if world > 1:
-        ctx.setTile(rank, world, args.stripe_rows)
+    fd.setup_context(ctx, rank, world, args.stripe_rows)
     # ---- e2e leg first (it starts from host buffers): upload, K iterations through the per-stage API, image read-back
     e2e = None
     if not args.no_e2e:
@@ -222,10 +238,7 @@ def main_ours(args):
         img = ctx.readPixels()
         dt = time.perf_counter() - t0
         rays = tr.stats["extensionRays"] + tr.stats["shadowRays"]
-        tot = torch.tensor([float(rays), dt], dtype=torch.float64, device="cuda")
-        if dist is not None:
-            r = tot[:1].clone(); dist.all_reduce(r); t = tot[1:].clone(); dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            rays, dt = float(r.item()), float(t.item())
+        rays, dt = fd.reduce_scalars([float(rays)])[0], fd.reduce_scalars([dt], "max")[0]
         n_it = args.warmup + args.steps
         e2e = {"value": rays / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(scene.nbytes() / n_it + 240 / n_it + 36),
                "d2h_bytes_per_step": int(img.nbytes / n_it + 32), "iterations": n_it, "seconds": dt,
@@ -237,10 +250,6 @@ def main_ours(args):
     # ---- device-resident leg
     tr = Tracer(ctx, params)
     tr.start()
-    if world > 1:
-        uid = [ctx.commUniqueId() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        ctx.commInit(uid[0], rank, world)
     ctx.render(max(args.warmup, 3))
     if world > 1:
         ctx.gatherPixels(0)
@@ -270,10 +279,8 @@ def main_ours(args):
     rays = int(st.extensionRays + st.shadowRays)
     perf = ctx.checkTracingPerf()
     launches = sum(n for _, n in perf.values()) + args.steps  # + one counter-snapshot kernel per iteration
-    if dist is not None:
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
-        r = torch.tensor([float(rays), float(launches)], dtype=torch.float64, device="cuda"); dist.all_reduce(r)
-        rays, launches = int(r[0].item()), int(r[1].item())
+    ms = fd.reduce_scalars([ms], "max")[0]
+    rays, launches = (int(v) for v in fd.reduce_scalars([float(rays), float(launches)]))
     ctx.setProfiling(False)
 
     # ---- roofline of the dominant kernel (rank 0's launches): algorithmic bytes per ray from an instrumented pass
