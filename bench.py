@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--tune", default="", help="k=v,... forwarded to CLContext.setTuning (experiments)")
     return ap.parse_args()
 
 
@@ -222,6 +223,8 @@ def main_ours(args):
     params = scene_params(scene, args)
     ctx = CLContext(args.tasks, device=local)
     fd.setup_context(ctx, rank, world, args.stripe_rows)
+    if args.tune:
+        ctx.setTuning(**{k: int(v) for k, v in (kv.split("=") for kv in args.tune.split(","))})
     # ---- e2e leg first (it starts from host buffers): upload, K iterations through the per-stage API, image read-back
     e2e = None
     if not args.no_e2e:

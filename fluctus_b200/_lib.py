@@ -35,6 +35,7 @@ _SIGNATURES = {
     "flx_render_timed": (C.c_int, [_P, C.c_uint32, C.POINTER(C.c_float)]),
     "flx_timer_begin": (C.c_int, [_P]),
     "flx_timer_end": (C.c_int, [_P, C.POINTER(C.c_float)]),
+    "flx_set_tuning": (C.c_int, [_P, C.c_int, C.c_int]),
     "flx_set_counting": (C.c_int, [_P, C.c_int]),
     "flx_get_trace_counts": (C.c_int, [_P, _P, _P]),
     "flx_reset_stats": (C.c_int, [_P]),

@@ -141,6 +141,12 @@ class CLContext:
         self._check(self._lib.flx_timer_end(self._h, C.byref(ms)), "timerEnd")
         return ms.value
 
+    TUNING = {"trace_variant": 0, "fetch_threshold": 1, "trace_blocks_per_sm": 2, "top_nodes": 3, "inner_min": 4}
+
+    def setTuning(self, **kv):
+        for k, v in kv.items():
+            self._check(self._lib.flx_set_tuning(self._h, self.TUNING[k], int(v)), "setTuning(%s)" % k)
+
     def setCounting(self, enabled):
         self._check(self._lib.flx_set_counting(self._h, 1 if enabled else 0), "setCounting")
 

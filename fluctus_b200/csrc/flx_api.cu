@@ -9,10 +9,12 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <queue>
 #include <string>
 #include <vector>
 
 #include "flx_kernels.cuh"
+#include "flx_trace_persistent.cuh"
 
 static_assert(sizeof(flx_RenderParams) == 240, "RenderParams layout (geom.h:163-180)");
 static_assert(sizeof(flx_AreaLight) == 96 && sizeof(flx_Camera) == 80, "AreaLight/Camera layout");
@@ -83,7 +85,7 @@ struct flx_ctx
     uint8_t *texData = nullptr;
     float4 *tnodes = nullptr, *ttris = nullptr;
     int rootRef = 0;
-    uint32_t nTris = 0, nTNodes = 0, nTTris = 0;
+    uint32_t nTris = 0, nTNodes = 0, nTTris = 0, treeletNodes = 0;
     bool sceneReady = false;
     size_t sceneBytes = 0;
 
@@ -106,6 +108,16 @@ struct flx_ctx
     // traversal work counters (flx_set_counting): [0..4] extension V,B,T,U,rays  [5..9] shadow V,B,T,U,rays
     unsigned long long *traceCounts = nullptr;
     bool counting = false;
+
+    // tuning knobs (flx_set_tuning)
+    int traceVariant = 1;     // 0: one ray per thread, 1: persistent threads + dynamic fetch, 2: 1 + top-of-tree treelet in shared memory
+    int topNodes = 2047;      // variant 2: treelet nodes staged per CTA (64 B each)
+    int fetchThreshold = 16;  // refill when fewer lanes than this still hold a ray
+    int innerMin = 8;         // leave the inner-node phase when fewer lanes than this are still at inner nodes
+    int traceBlocksPerSM = 0; // 0: occupancy calculator
+    int numSMs = 148;
+    int maxDynSmem = 48 * 1024;
+    uint32_t *fetchCounters = nullptr; // [0] extension, [1] shadow
 
     // timing
     cudaEvent_t evStart = nullptr, evStop = nullptr;
@@ -298,13 +310,14 @@ struct Repacked
 {
     std::vector<float4> nodes, tris;
     int rootRef = 0;
+    uint32_t treeletNodes = 0;
 };
 
 int repackBvh(flx_ctx *ctx, const flx_Triangle *tris, uint32_t nTris, const uint32_t *indices, uint32_t nIndices, const flx_Node *nodes, uint32_t nNodes,
               Repacked &out)
 {
     std::vector<int> ref(nNodes, 0); // child reference of every reference node
-    // pass 1: number inner nodes in DFS order, lay out leaves' triangles in DFS order
+    // pass 1: validate, lay out the leaves' triangles in DFS order
     uint32_t nInner = 0;
     size_t nLeafTris = 0;
     for (uint32_t i = 0; i < nNodes; i++)
@@ -314,7 +327,7 @@ int repackBvh(flx_ctx *ctx, const flx_Triangle *tris, uint32_t nTris, const uint
             const uint32_t r = nodes[i].iStartOrRightChild;
             if (i + 1 >= nNodes || r >= nNodes || r <= i + 1)
                 return fail(ctx, FLX_E_INVALID, "node %u: child links out of range (left %u, right %u, %u nodes)", i, i + 1, r, nNodes);
-            ref[i] = (int)nInner++;
+            nInner++;
         }
         else
         {
@@ -327,8 +340,39 @@ int repackBvh(flx_ctx *ctx, const flx_Triangle *tris, uint32_t nTris, const uint
             nLeafTris += n;
         }
     }
+    // pass 2: number the inner nodes -- first a treelet grown from the root by always taking the pending node with the
+    // largest box area (the nodes a random ray is most likely to visit; any prefix of this order is a connected
+    // top-of-tree, which is what the TOP traversal variant stages in shared memory), then everything else in DFS order.
+    const uint32_t kTreeletMax = 4096;
+    std::vector<char> placed(nNodes, 0);
+    uint32_t next = 0;
+    if (nodes[0].nPrims == 0)
+    {
+        auto area = [&](uint32_t i) {
+            const float dx = nodes[i].bmax.x - nodes[i].bmin.x, dy = nodes[i].bmax.y - nodes[i].bmin.y, dz = nodes[i].bmax.z - nodes[i].bmin.z;
+            return dx * dy + dx * dz + dy * dz;
+        };
+        typedef std::pair<float, uint32_t> Item; // (area, ~index): larger area first, lower index first on ties
+        std::priority_queue<Item> pq;
+        pq.push(Item(area(0), ~0u));
+        while (!pq.empty() && next < kTreeletMax)
+        {
+            const uint32_t i = ~pq.top().second;
+            pq.pop();
+            ref[i] = (int)next++;
+            placed[i] = 1;
+            const uint32_t kids[2] = {i + 1, nodes[i].iStartOrRightChild};
+            for (uint32_t c : kids)
+                if (nodes[c].nPrims == 0)
+                    pq.push(Item(area(c), ~c));
+        }
+    }
+    out.treeletNodes = next;
+    for (uint32_t i = 0; i < nNodes; i++)
+        if (nodes[i].nPrims == 0 && !placed[i])
+            ref[i] = (int)next++;
     out.nodes.assign((size_t)nInner * 4, make_float4(0, 0, 0, 0));
-    out.tris.assign(nLeafTris * 3, make_float4(0, 0, 0, 0));
+    out.tris.assign(nLeafTris * 4, make_float4(0, 0, 0, 0));
     out.rootRef = ref[0];
     for (uint32_t i = 0; i < nNodes; i++)
     {
@@ -345,8 +389,8 @@ int repackBvh(flx_ctx *ctx, const flx_Triangle *tris, uint32_t nTris, const uint
         else
         {
             const uint32_t s = nodes[i].iStartOrRightChild, n = nodes[i].nPrims;
-            float4 *q = &out.tris[(size_t)(~ref[i]) * 3];
-            for (uint32_t k = 0; k < n; k++, q += 3)
+            float4 *q = &out.tris[(size_t)(~ref[i]) * 4];
+            for (uint32_t k = 0; k < n; k++, q += 4)
             {
                 const uint32_t ti = indices[s + k];
                 if (ti >= nTris || ti > 0x7fffffffu)
@@ -422,6 +466,42 @@ __global__ void k_deinterleave(const float4 *gathered, float4 *full, uint32_t wi
 }
 } // namespace
 
+template <bool ANYHIT, class COUNT> static int launchPersistentT(flx_ctx *ctx, uint32_t *fetch, unsigned long long *counts)
+{
+    const Frame fr = makeFrame(ctx);
+    const BvhView bvh = makeBvh(ctx);
+    if (ctx->traceVariant == 2)
+    {
+        constexpr int BLOCK = 1024; // one persistent CTA per SM owns the staged treelet
+        auto kern = k_trace_persistent<ANYHIT, COUNT, BLOCK, true>;
+        const int top = (int)std::min<uint32_t>({(uint32_t)ctx->topNodes, ctx->treeletNodes, ctx->nTNodes, (uint32_t)((ctx->maxDynSmem - 1024) / 64)});
+        const size_t smem = (size_t)top * 64;
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<ctx->numSMs, BLOCK, smem, ctx->stream>>>(fr, ctx->params, bvh, ctx->tris, fetch, ctx->fetchThreshold, ctx->innerMin, top, counts);
+    }
+    else
+    {
+        auto kern = k_trace_persistent<ANYHIT, COUNT, FLX_TRACE_BLOCK, false>;
+        int perSM = ctx->traceBlocksPerSM;
+        if (perSM <= 0)
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, FLX_TRACE_BLOCK, 0));
+        const unsigned grid = (unsigned)std::max(1, perSM) * (unsigned)ctx->numSMs;
+        kern<<<grid, FLX_TRACE_BLOCK, 0, ctx->stream>>>(fr, ctx->params, bvh, ctx->tris, fetch, ctx->fetchThreshold, ctx->innerMin, 0, counts);
+    }
+    return 0;
+}
+
+template <bool ANYHIT> static int launchPersistent(flx_ctx *ctx)
+{
+    uint32_t *fetch = ctx->fetchCounters + (ANYHIT ? 1 : 0);
+    CU(cudaMemsetAsync(fetch, 0, sizeof(uint32_t), ctx->stream));
+    Timed tm(ctx, ANYHIT ? FLX_K_SHADOWRAYS : FLX_K_EXTRAYS);
+    int rc = ctx->counting ? launchPersistentT<ANYHIT, RayCount>(ctx, fetch, ctx->traceCounts + (ANYHIT ? 5 : 0)) : launchPersistentT<ANYHIT, NoCount>(ctx, fetch, nullptr);
+    if (rc)
+        return rc;
+    return launchCheck(ctx, ANYHIT ? "k_trace_persistent<shadow>" : "k_trace_persistent<extension>");
+}
+
 // ================================================================================================ C ABI
 extern "C"
 {
@@ -487,6 +567,9 @@ int flx_create(int device, uint32_t num_tasks, flx_ctx **out)
     CUB(cudaMalloc(&c->scanTiles, (size_t)c->numScanTiles * sizeof(unsigned long long)));
     CUB(cudaMalloc(&c->scanTicket, sizeof(uint32_t)));
     CUB(cudaMallocHost(&c->pinnedCounters, sizeof(flx_QueueCounters) * flx_ctx::kCounterRing));
+    c->numSMs = prop.multiProcessorCount;
+    c->maxDynSmem = (int)prop.sharedMemPerBlockOptin;
+    CUB(cudaMalloc(&c->fetchCounters, 2 * sizeof(uint32_t)));
     CUB(cudaMalloc(&c->traceCounts, 10 * sizeof(unsigned long long)));
     CUB(cudaMemset(c->traceCounts, 0, 10 * sizeof(unsigned long long)));
     CUB(cudaEventCreate(&c->evStart));
@@ -530,6 +613,7 @@ void flx_destroy(flx_ctx *c)
     freeDev(c->scanTiles);
     freeDev(c->scanTicket);
     freeDev(c->traceCounts);
+    freeDev(c->fetchCounters);
     if (c->evStart)
         cudaEventDestroy(c->evStart);
     if (c->evStop)
@@ -607,12 +691,13 @@ int flx_upload_scene(flx_ctx *ctx, const flx_Triangle *tris, uint32_t n_tris, co
         return rc;
     if ((rc = uploadArray(ctx, ctx->tnodes, rp.nodes.data(), rp.nodes.size(), 4)))
         return rc;
-    if ((rc = uploadArray(ctx, ctx->ttris, rp.tris.data(), rp.tris.size(), 3)))
+    if ((rc = uploadArray(ctx, ctx->ttris, rp.tris.data(), rp.tris.size(), 4)))
         return rc;
     ctx->rootRef = rp.rootRef;
     ctx->nTris = n_tris;
     ctx->nTNodes = (uint32_t)(rp.nodes.size() / 4);
-    ctx->nTTris = (uint32_t)(rp.tris.size() / 3);
+    ctx->nTTris = (uint32_t)(rp.tris.size() / 4);
+    ctx->treeletNodes = rp.treeletNodes;
     ctx->sceneReady = true;
     return 0;
 }
@@ -739,6 +824,8 @@ int flx_enqueue_extrays(flx_ctx *ctx)
     if (rc)
         return rc;
     CU(cudaSetDevice(ctx->device));
+    if (ctx->traceVariant >= 1)
+        return launchPersistent<false>(ctx);
     Timed tm(ctx, FLX_K_EXTRAYS);
     const unsigned grid = (ctx->numTasks + FLX_TRACE_BLOCK - 1) / FLX_TRACE_BLOCK;
     if (ctx->counting)
@@ -754,6 +841,8 @@ int flx_enqueue_shadowrays(flx_ctx *ctx)
     if (rc)
         return rc;
     CU(cudaSetDevice(ctx->device));
+    if (ctx->traceVariant >= 1)
+        return launchPersistent<true>(ctx);
     Timed tm(ctx, FLX_K_SHADOWRAYS);
     const unsigned grid = (ctx->numTasks + FLX_TRACE_BLOCK - 1) / FLX_TRACE_BLOCK;
     if (ctx->counting)
@@ -944,6 +1033,36 @@ int flx_timer_end(flx_ctx *ctx, float *elapsed_ms)
     CU(cudaEventElapsedTime(elapsed_ms, ctx->evStart, ctx->evStop));
     drainEvents(ctx);
     return 0;
+}
+
+int flx_set_tuning(flx_ctx *ctx, int key, int value)
+{
+    if (!ctx)
+        return FLX_E_INVALID;
+    switch (key)
+    {
+    case FLX_TUNE_TRACE_VARIANT:
+        REQUIRE(value >= 0 && value <= 2, "flx_set_tuning: trace variant must be 0, 1 or 2");
+        ctx->traceVariant = value;
+        return 0;
+    case FLX_TUNE_FETCH_THRESHOLD:
+        REQUIRE(value >= 1 && value <= 32, "flx_set_tuning: fetch threshold must be in 1..32");
+        ctx->fetchThreshold = value;
+        return 0;
+    case FLX_TUNE_INNER_MIN:
+        REQUIRE(value >= 1 && value <= 32, "flx_set_tuning: inner-phase minimum must be in 1..32");
+        ctx->innerMin = value;
+        return 0;
+    case FLX_TUNE_TOP_NODES:
+        REQUIRE(value >= 0 && value <= 4096, "flx_set_tuning: top nodes must be in 0..4096");
+        ctx->topNodes = value;
+        return 0;
+    case FLX_TUNE_TRACE_BLOCKS_PER_SM:
+        REQUIRE(value >= 0 && value <= 32, "flx_set_tuning: blocks per SM must be in 0..32");
+        ctx->traceBlocksPerSM = value;
+        return 0;
+    }
+    return fail(ctx, FLX_E_INVALID, "flx_set_tuning: unknown key %d", key);
 }
 
 int flx_set_counting(flx_ctx *ctx, int enabled)

@@ -155,9 +155,9 @@ struct LocalStack
 };
 
 // warp-reduce the per-ray work counters and add them to the context totals (instrumented launches only)
-FLX_DEV void flush_counts(const RayCount &c, unsigned long long *totals, bool traced)
+FLX_DEV void flush_counts(const RayCount &c, unsigned long long *totals, unsigned rays)
 {
-    unsigned v[5] = {c.V, c.B, c.T, c.U, traced ? 1u : 0u};
+    unsigned v[5] = {c.V, c.B, c.T, c.U, rays};
     const unsigned active = __activemask();
 #pragma unroll
     for (int k = 0; k < 5; k++)
@@ -168,7 +168,7 @@ FLX_DEV void flush_counts(const RayCount &c, unsigned long long *totals, bool tr
             atomicAdd(totals + k, (unsigned long long)x);
     }
 }
-FLX_DEV void flush_counts(const NoCount &, unsigned long long *, bool) {}
+FLX_DEV void flush_counts(const NoCount &, unsigned long long *, unsigned) {}
 
 template <class COUNT>
 __global__ void __launch_bounds__(FLX_TRACE_BLOCK) k_extrays(const __grid_constant__ Frame fr, const __grid_constant__ flx_RenderParams prm, const BvhView bvh,
@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(FLX_TRACE_BLOCK) k_extrays(const __grid_consta
     LocalStack stack;
     COUNT cnt;
     trace_closest(bvh, o, d, tbest, ub, vb, tri, stack, cnt);
-    flush_counts(cnt, countTotals, true);
+    flush_counts(cnt, countTotals, 1u);
 
     // hit record (bvh.cl:271-279): attributes of the winning triangle, fetched once
     V3 P = v3(0.0f), N = v3(0.0f);
@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(FLX_TRACE_BLOCK) k_shadowrays(const __grid_con
         LocalStack stack;
         occluded = trace_any(bvh, o, d, lenL, stack, cnt);
     }
-    flush_counts(cnt, countTotals, true);
+    flush_counts(cnt, countTotals, 1u);
     t.setu(FLX_S_SHADOW_BLOCKED, gid, occluded ? 1u : 0u);
 }
 

@@ -12,10 +12,12 @@
 //       q0 = (Lmin.x, Lmin.y, Lmin.z, Lmax.x)   q1 = (Lmax.y, Lmax.z, Rmin.x, Rmin.y)
 //       q2 = (Rmin.z, Rmax.x, Rmax.y, Rmax.z)   q3 = (leftRef, rightRef, -, -)  as int
 //     a child reference >= 0 is a TNode index; < 0 is ~(first TTri of a leaf).
-//   TTri, 48 B, one per leaf REFERENCE (duplicated SBVH references stay duplicated, so a leaf
+//     Node ORDER: a treelet of the nodes with the largest box areas, grown greedily from the root, comes first (it is
+//     what the TOP traversal variant stages in shared memory), the remaining nodes follow in DFS order.
+//   TTri, 64 B (two 256-bit loads), one per leaf REFERENCE (duplicated SBVH references stay duplicated, so a leaf
 //   is one contiguous run):
 //       q0 = (v0.x, v0.y, v0.z, bits(triangle index | last-in-leaf << 31))
-//       q1 = (v1 - v0, 0)   q2 = (v2 - v0, 0)
+//       q1 = (v1 - v0, 0)   q2 = (v2 - v0, 0)   q3 = unused
 //     the edges are the exact float differences the reference computes per test
 //     (intersect.cl:66-67), hoisted to build time: same bits, six fewer subtractions per test.
 //
@@ -52,7 +54,7 @@ struct RayCount
 struct BvhView
 {
     const float4 *nodes; // TNode as 4 x float4
-    const float4 *tris;  // TTri as 3 x float4
+    const float4 *tris;  // TTri as 4 x float4
     int rootRef;
 };
 
@@ -140,7 +142,7 @@ template <class STACK, class COUNT> FLX_DEV void trace_closest(const BvhView &bv
             float tmin = 3.402823466e+38f, umin = 0.0f, vmin = 0.0f;
             int imin = -1;
             cnt.leaf();
-            const float4 *p = bvh.tris + 3 * (size_t)(~cur);
+            const float4 *p = bvh.tris + 4 * (size_t)(~cur);
             while (true)
             {
                 const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
@@ -159,7 +161,7 @@ template <class STACK, class COUNT> FLX_DEV void trace_closest(const BvhView &bv
                 }
                 if (tag < 0)
                     break;
-                p += 3;
+                p += 4;
             }
             if (imin != -1 && tmin < tbest)
             {
@@ -220,7 +222,7 @@ template <class STACK, class COUNT> FLX_DEV bool trace_any(const BvhView &bvh, V
         else
         {
             cnt.leaf();
-            const float4 *p = bvh.tris + 3 * (size_t)(~cur);
+            const float4 *p = bvh.tris + 4 * (size_t)(~cur);
             while (true)
             {
                 const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
@@ -230,7 +232,7 @@ template <class STACK, class COUNT> FLX_DEV bool trace_any(const BvhView &bvh, V
                     return true;
                 if (__float_as_int(a.w) < 0)
                     break;
-                p += 3;
+                p += 4;
             }
         }
         if (sp == 0)

@@ -1,0 +1,304 @@
+// flx_trace_persistent.cuh -- the production traversal kernels: persistent threads with dynamic ray fetch.
+//
+// Why: with one ray per thread (k_extrays/k_shadowrays in flx_kernels.cuh, kept as the simple variant) ncu shows 5.9 of
+// 32 lanes active per issued instruction on Conference (profiles/r1_v1_extrays_raw.csv): incoherent rays differ widely in
+// traversal length, so a warp is held by its longest ray.  Here a warp owns 32 ray SLOTS instead: whenever fewer than
+// `threshold` lanes still hold a ray, the idle lanes take new rays from the queue with one warp-aggregated atomic
+// (persistent-threads scheme after Aila & Laine 2009), and the traversal itself is organised "while-while": all lanes
+// walk inner nodes until each has reached a leaf (or finished), then all intersect their leaves.
+//
+// Exactness: per ray the visiting order, box test and triangle test are those of flx_trace.cuh (i.e. the reference's),
+// so results stay bit-identical; only WHICH lane traces a ray and WHEN changes.  No speculative traversal for closest
+// hits: testing boxes against a stale hit distance can admit a leaf the reference culls, and on axis-aligned geometry a
+// coplanar triangle there can win a tie the reference never sees.
+//
+// Memory path (what the ncu capture of the first persistent version showed: the L1TEX tag stage, one wavefront per
+// lane per load instruction for divergent 16-byte loads, was the limiter at ~1.1 wavefronts/clk/SM):
+//   * nodes and triangles are fetched with 256-bit loads (LDG.E.256, new on sm_100): 2 wavefronts per record, not 4 / 3;
+//   * TOP variant: the hottest part of the tree -- a treelet grown from the root by always expanding the node with the
+//     largest box area, which repack_bvh lays out FIRST in the node array -- is staged once per CTA into shared memory
+//     by the bulk-copy engine (cp.async.bulk + mbarrier, SASS UBLKCP) and read with LDS.128.  On Conference a 2047-node
+//     treelet (128 KB) serves 92 % of all inner-node visits (measured with the instrumented oracle).  One persistent
+//     CTA per SM owns the staged treelet.
+#pragma once
+
+#include "flx_kernels.cuh"
+
+struct F8
+{
+    float v[8];
+};
+FLX_DEV F8 ldg256(const void *p) // 32-byte aligned, read-only path
+{
+    F8 r;
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+                 : "l"(p));
+    return r;
+}
+FLX_DEV uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// Stage `bytes` (multiple of 16) from global to shared memory with the bulk-copy engine; all threads of the CTA call this.
+FLX_DEV void stage_bulk(void *dstShared, const void *srcGlobal, uint32_t bytes, unsigned long long *mbar)
+{
+    const uint32_t bar = smem_addr(mbar);
+    if (threadIdx.x == 0)
+    {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && bytes > 0)
+    {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        const uint32_t chunk = 32768u;
+        for (uint32_t off = 0; off < bytes; off += chunk)
+        {
+            const uint32_t n = min(chunk, bytes - off);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dstShared) + off),
+                         "l"(reinterpret_cast<const char *>(srcGlobal) + off), "r"(n), "r"(bar)
+                         : "memory");
+        }
+    }
+    if (bytes > 0)
+    {
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(bar) : "memory");
+    }
+}
+
+template <bool ANYHIT, class COUNT, int BLOCK, bool TOP>
+__global__ void __launch_bounds__(BLOCK, TOP ? 1 : (ANYHIT ? 10 : 8)) k_trace_persistent(const __grid_constant__ Frame fr, const __grid_constant__ flx_RenderParams prm,
+                                                                         const BvhView bvh, const flx_Triangle *tris160, uint32_t *fetchCounter,
+                                                                         const int threshold, const int innerMin, const int topCount, unsigned long long *countTotals)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ __align__(128) unsigned char dynSmem[];
+    __shared__ unsigned long long stageBar;
+    const float4 *topNodes = reinterpret_cast<const float4 *>(dynSmem);
+    if (TOP)
+        stage_bulk(dynSmem, bvh.nodes, (uint32_t)topCount * 64u, &stageBar);
+    const int lane = threadIdx.x & 31;
+    const unsigned lanesBelow = (1u << lane) - 1u;
+    const uint32_t *queue = fr.queues[ANYHIT ? Q_SHADOW : Q_EXT];
+    const uint32_t count = *counter_ptr(fr.counters, ANYHIT ? Q_SHADOW : Q_EXT);
+    const Tasks &t = fr.tasks;
+    const bool lightTest = ANYHIT ? (prm.useAreaLight != 0) : (prm.sampleImpl && prm.useAreaLight);
+
+    bool active = false, pending = false, exhausted = false; // pending: ray finished, result not yet written
+    uint32_t gid = 0;
+    V3 o = v3(0.0f), d = v3(0.0f), idir = v3(0.0f);
+    float tbest = 0.0f, ub = 0.0f, vb = 0.0f;
+    int tri = -1, cur = 0, sp = 0;
+    bool occluded = false;
+    int stack[FLX_STACK_DEPTH];
+    COUNT cnt;
+    unsigned raysDone = 0;
+
+    while (true)
+    {
+        // ---- write back finished rays (all lanes that finished since the last round do this together)
+        if (pending)
+        {
+            pending = false;
+            raysDone++;
+            if (ANYHIT)
+                t.setu(FLX_S_SHADOW_BLOCKED, gid, occluded ? 1u : 0u);
+            else
+            {
+                V3 P = v3(0.0f), N = v3(0.0f);
+                float tu = 0.0f, tv = 0.0f;
+                int matId = -1, lightHit = 0;
+                if (tri >= 0)
+                {
+                    const float4 *q = reinterpret_cast<const float4 *>(tris160 + tri);
+                    const float4 n0 = __ldg(q + 1), t0 = __ldg(q + 2), n1 = __ldg(q + 4), t1 = __ldg(q + 5), n2 = __ldg(q + 7), t2 = __ldg(q + 8);
+                    matId = __float_as_int(__ldg(q + 9).x);
+                    P = o + tbest * d;
+                    N = norm3(bary3(ub, vb, v3(n0.x, n0.y, n0.z), v3(n1.x, n1.y, n1.z), v3(n2.x, n2.y, n2.z)));
+                    const V3 uv = bary3(ub, vb, v3(t0.x, t0.y, t0.z), v3(t1.x, t1.y, t1.z), v3(t2.x, t2.y, t2.z));
+                    tu = uv.x;
+                    tv = uv.y;
+                }
+                if (lightTest && light_quad(prm.areaLight, o, d, tbest)) // wf_extrays.cl:29
+                {
+                    lightHit = 1;
+                    P = o + tbest * d;
+                    N = v3(prm.areaLight.N);
+                    tri = 0;
+                    matId = 0;
+                }
+                t.setu(FLX_S_PATH_LEN, gid, t.u(FLX_S_PATH_LEN, gid) + 1u);
+                t.setv(FLX_S_P, gid, P);
+                t.setv(FLX_S_N, gid, N);
+                t.setf(FLX_S_UV, gid, tu);
+                t.setf(FLX_S_UV + 1, gid, tv);
+                t.setf(FLX_S_HIT_T, gid, tbest);
+                t.setu(FLX_S_HIT_I, gid, (uint32_t)tri);
+                t.setu(FLX_S_AREA_LIGHT_HIT, gid, (uint32_t)lightHit);
+                t.setu(FLX_S_MAT_ID, gid, (uint32_t)matId);
+            }
+        }
+
+        // ---- idle lanes take the next rays of the queue: one atomic per warp
+        const bool need = !active && !exhausted;
+        const unsigned needMask = __ballot_sync(FULL, need);
+        if (needMask)
+        {
+            uint32_t base = 0;
+            const int leader = __ffs(needMask) - 1;
+            if (lane == leader)
+                base = atomicAdd(fetchCounter, (uint32_t)__popc(needMask));
+            base = __shfl_sync(FULL, base, leader);
+            if (need)
+            {
+                const uint32_t idx = base + (uint32_t)__popc(needMask & lanesBelow);
+                if (idx < count)
+                {
+                    gid = queue[idx];
+                    o = t.v(ANYHIT ? FLX_S_SHADOW_ORIG : FLX_S_ORIG, gid);
+                    d = t.v(ANYHIT ? FLX_S_SHADOW_DIR : FLX_S_DIR, gid);
+                    idir = v3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+                    tbest = ANYHIT ? t.f(FLX_S_SHADOW_RAY_LEN, gid) : 3.402823466e+38f;
+                    ub = vb = 0.0f;
+                    tri = -1;
+                    occluded = false;
+                    cur = bvh.rootRef;
+                    sp = 0;
+                    active = true;
+                    if (ANYHIT && lightTest) // the light quad is tested first and blocks (wf_shadowrays.cl:29-31)
+                    {
+                        float tl = tbest;
+                        if (light_quad(prm.areaLight, o, d, tl))
+                        {
+                            occluded = true;
+                            active = false;
+                            pending = true;
+                        }
+                    }
+                }
+                else
+                    exhausted = true;
+            }
+        }
+        if (__ballot_sync(FULL, active || pending) == 0u)
+            break; // queue drained and every lane idle
+        const bool drain = __any_sync(FULL, exhausted); // nothing left to fetch: run the remaining rays to the end
+
+        // ---- traverse until too few lanes hold a ray
+        while (true)
+        {
+            // (1) inner nodes: every lane that is at an inner node steps, until fewer than innerMin lanes still are
+            //     (innerMin = 1: until every lane has reached a leaf or finished its ray)
+            while (true)
+            {
+                const bool atInner = active && cur >= 0;
+                const unsigned innerMask = __ballot_sync(FULL, atInner);
+                if (innerMask == 0u)
+                    break;
+                if (__popc(innerMask) < innerMin && __ballot_sync(FULL, active && cur < 0) != 0u)
+                    break; // few stragglers and some lane has a leaf to intersect: switch phase (never with nothing to do)
+                if (!atInner)
+                    continue;
+                cnt.inner();
+                float4 q0, q1, q2;
+                int4 q3;
+                if (TOP && cur < topCount)
+                {
+                    const float4 *n = topNodes + 4 * cur;
+                    q0 = n[0];
+                    q1 = n[1];
+                    q2 = n[2];
+                    q3 = *reinterpret_cast<const int4 *>(n + 3);
+                }
+                else
+                {
+                    const float4 *n = bvh.nodes + 4 * (size_t)cur;
+                    const F8 h0 = ldg256(n), h1 = ldg256(n + 2);
+                    q0 = make_float4(h0.v[0], h0.v[1], h0.v[2], h0.v[3]);
+                    q1 = make_float4(h0.v[4], h0.v[5], h0.v[6], h0.v[7]);
+                    q2 = make_float4(h1.v[0], h1.v[1], h1.v[2], h1.v[3]);
+                    q3 = make_int4(__float_as_int(h1.v[4]), __float_as_int(h1.v[5]), 0, 0);
+                }
+                float ln, rn;
+                const bool lh = box_test(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, o, idir, tbest, ln);
+                const bool rh = box_test(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, o, idir, tbest, rn);
+                if (lh && rh)
+                {
+                    const bool swap = rn < ln; // right child closer -> first (bvh.cl:292); ties keep left first
+                    stack[sp++] = swap ? q3.x : q3.y;
+                    cur = swap ? q3.y : q3.x;
+                }
+                else if (lh)
+                    cur = q3.x;
+                else if (rh)
+                    cur = q3.y;
+                else if (sp > 0)
+                    cur = stack[--sp];
+                else
+                {
+                    active = false;
+                    pending = true;
+                }
+            }
+            // (2) one leaf
+            if (active && cur < 0)
+            {
+                cnt.leaf();
+                const float4 *p = bvh.tris + 4 * (size_t)(~cur);
+                float tmin = 3.402823466e+38f, umin = 0.0f, vmin = 0.0f;
+                int imin = -1;
+                while (true)
+                {
+                    const F8 h0 = ldg256(p), h1 = ldg256(p + 2);
+                    const int tag = __float_as_int(h0.v[3]);
+                    float tt, uu, vv;
+                    cnt.tri();
+                    if (tri_test(v3(h0.v[0], h0.v[1], h0.v[2]), v3(h0.v[4], h0.v[5], h0.v[6]), v3(h1.v[0], h1.v[1], h1.v[2]), o, d, tt, uu, vv))
+                    {
+                        if (ANYHIT)
+                        {
+                            if (tt > 0.0f && tt < tbest)
+                            {
+                                occluded = true;
+                                break;
+                            }
+                        }
+                        else if (tt > 0.0f && tt < tmin)
+                        {
+                            imin = tag & 0x7fffffff;
+                            tmin = tt;
+                            umin = uu;
+                            vmin = vv;
+                        }
+                    }
+                    if (tag < 0)
+                        break;
+                    p += 4;
+                }
+                if (!ANYHIT && imin != -1 && tmin < tbest)
+                {
+                    cnt.update();
+                    tri = imin;
+                    tbest = tmin;
+                    ub = umin;
+                    vb = vmin;
+                }
+                if ((ANYHIT && occluded) || sp == 0)
+                {
+                    active = false;
+                    pending = true;
+                }
+                else
+                    cur = stack[--sp];
+            }
+            const unsigned still = __ballot_sync(FULL, active);
+            if (still == 0u)
+                break;
+            if (!drain && __popc(still) < threshold)
+                break;
+        }
+    }
+    flush_counts(cnt, countTotals, raysDone);
+}

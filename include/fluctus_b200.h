@@ -143,6 +143,15 @@ int flx_render_timed(flx_ctx *ctx, uint32_t n_iterations, float *elapsed_ms);
 int flx_timer_begin(flx_ctx *ctx);
 int flx_timer_end(flx_ctx *ctx, float *elapsed_ms);
 
+/* Tuning knobs; results never depend on them (tests/test_gpu_parity.py runs the parity suite over the variants). */
+enum { FLX_TUNE_TRACE_VARIANT = 0,      /* 0: one ray per thread; 1 (default): persistent threads with dynamic ray fetch; 2: 1 + the top-of-tree
+                                           treelet staged in shared memory by the bulk-copy engine, one CTA per SM */
+       FLX_TUNE_FETCH_THRESHOLD = 1,    /* persistent variant: refill a warp when fewer lanes than this hold a ray (default 16) */
+       FLX_TUNE_TRACE_BLOCKS_PER_SM = 2,/* variant 1: resident CTAs per SM, 0 = occupancy calculator */
+       FLX_TUNE_TOP_NODES = 3,          /* variant 2: treelet nodes (64 B each) staged per CTA, default 2047 */
+       FLX_TUNE_INNER_MIN = 4           /* leave the inner-node phase when fewer lanes than this are still at inner nodes (default 8) */ };
+int flx_set_tuning(flx_ctx *ctx, int key, int value);
+
 /* Instrumented traversal: while enabled, flx_enqueue_extrays / flx_enqueue_shadowrays also count the work the
  * reference's algorithm does per ray (results are unchanged). Used outside timed regions only. */
 int flx_set_counting(flx_ctx *ctx, int enabled);

@@ -235,7 +235,7 @@ FLX_HD float flx_powf(float x, float y)
     if (x != x || y != y)
         return x + y;
     if (x < 0.0f)
-        return x / 0.0f * 0.0f; /* NaN */
+        return (float)flx__bits2d(0x7ff8000000000000LL); /* NaN */
     if (x == 0.0f)
         return (y > 0.0f) ? 0.0f : ((y == 0.0f) ? 1.0f : 1.0f / 0.0f);
     if (x > 3.4028234663852886e38f)

@@ -190,6 +190,7 @@ void NAME(raygen)(const RefBufs *b, size_t begin, size_t end)
 typedef struct { unsigned long long V, B, T, U, rays; } WorkCount; /* SURVEY 8d terms; read with port_work_counts */
 static WorkCount g_ext_work, g_shadow_work;
 static int g_count_work = 0;
+static uint32_t *g_visit_hist = 0; /* optional: per-node pop counts of the extension traversal (layout studies) */
 
 static int intersect_aabb(v3 o, v3 d, const Node *box, float *tminRet, float tMaxPrev, WorkCount *wc)
 {
@@ -235,6 +236,9 @@ static void bvh_intersect(v3 o, v3 d, Hit *hit, const Triangle *tris, const Node
         const uint32_t ni = stack[sp--];
         const Node *n = &nodes[ni];
         if (wc) wc->V++;
+#ifndef PORT_PARALLEL
+        if (g_visit_hist) g_visit_hist[ni]++;
+#endif
         if (n->nPrims != 0)
         {
             float tmin = FLT_MAX, umin = 0.0f, vmin = 0.0f; int imin = -1;
@@ -365,6 +369,7 @@ void NAME(shadow)(const RefBufs *b, size_t begin, size_t end)                   
 }
 
 #ifndef PORT_PARALLEL
+void port_visit_hist(uint32_t *hist) { g_visit_hist = hist; }
 void port_count_work(int enable) { g_count_work = enable; memset(&g_ext_work, 0, sizeof g_ext_work); memset(&g_shadow_work, 0, sizeof g_shadow_work); }
 void port_work_counts(unsigned long long ext[5], unsigned long long shadow[5])
 {
