@@ -191,3 +191,49 @@ def test_multi_gpu_tiles_and_nccl_gather():
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                         "--master-port", "29731", os.path.join(root, "tests", "multi_gpu_check.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "MULTI_GPU_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+def test_cpp_wrapper_headless_driver_matches_golden(tmp_path):
+    """The C++ host side (include/fluctus_b200/clcontext.hpp, examples/flx_headless.cpp: the reference's benchmark loop with
+    its call sites unchanged) reproduces the teapot golden vector produced by the reference kernels."""
+    import json, os, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "examples", "flx_headless")
+    if not os.path.exists(exe):
+        pytest.skip("examples/flx_headless not built (python __graft_entry__.py)")
+    z = np.load(os.path.join(root, "tests", "golden", "teapot_c1.npz"))
+    out = tmp_path / "pix.rgba"
+    r = subprocess.run([exe, scene_blob("teapot"), "64", "64", "4096", "2", "16", str(out)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    res = json.loads(r.stdout.strip().splitlines()[-1])
+    assert [res["primary"], res["extension"], res["shadow"]] == list(z["stats"])
+    pix = np.fromfile(out, np.float32).reshape(-1, 4)
+    from parity_util import compare_pixels
+    compare_pixels(pix, z["pixels"], "C++ driver vs golden", rtol=1e-5)
+
+
+def test_luxball_c4_small():
+    """BASELINE config C4 (luxball, ideal dielectric, 16 bounces, separate material queues) at 96x54."""
+    scene = SceneData.load_blob(scene_blob("luxball"))
+    from bench_configs import luxball_params
+    W, H = 96, 54
+    params = luxball_params(scene, W, H)
+    with CLContext(W * H) as gpu:
+        run_lockstep(gpu, oracle_ctx(W * H), scene, params, iterations=20, check_every=4)
+
+
+def test_country_kitchen_c3_small():
+    """BASELINE config C3 (country kitchen: glossy / GGX / mirror / dielectric materials, 17 textures + a bump map,
+    night.hdr environment map with alias-method IBL, MIS, separate queues) at 96x54."""
+    scene = SceneData.load_blob(scene_blob("country_kitchen"))
+    import os
+    from conftest import SCENES_DIR
+    envp = os.path.join(SCENES_DIR, "night.env.bin")
+    if not os.path.exists(envp):
+        pytest.skip("env map blob missing")
+    env = EnvMapData.load_blob(envp)
+    from bench_configs import kitchen_params
+    W, H = 96, 54
+    params = kitchen_params(scene, W, H)
+    with CLContext(W * H) as gpu:
+        run_lockstep(gpu, oracle_ctx(W * H), scene, params, iterations=12, env=env, check_every=4)
