@@ -58,6 +58,10 @@ struct flx_ctx
 {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;   // flx_render runs the shadow-ray kernel here so its start overlaps the extension kernel's tail
+    cudaStream_t cur = nullptr;       // stream the next traversal launch goes to (== stream except inside flx_render)
+    cudaEvent_t evFork = nullptr, evJoin = nullptr;
+    int overlapTrace = 1;
     uint32_t numTasks = 0;
     std::string error;
 
@@ -81,6 +85,7 @@ struct flx_ctx
     // scene
     flx_Triangle *tris = nullptr;
     flx_Material *materials = nullptr;
+    float4 *kdGamma = nullptr;
     flx_TexDescriptor *texDesc = nullptr;
     uint8_t *texData = nullptr;
     float4 *tnodes = nullptr, *ttris = nullptr;
@@ -113,6 +118,8 @@ struct flx_ctx
     int traceVariant = 1;     // 0: one ray per thread, 1: persistent threads + dynamic fetch, 2: 1 + top-of-tree treelet in shared memory
     int topNodes = 2047;      // variant 2: treelet nodes staged per CTA (64 B each)
     int fetchThreshold = 16;  // refill when fewer lanes than this still hold a ray
+    int fetchChunk = 32;     // queue entries a warp reserves per atomic
+    int logicMinBlocks = 3;   // resident 256-thread CTAs per SM the logic kernel is compiled for (register budget)
     int innerMin = 8;         // leave the inner-node phase when fewer lanes than this are still at inner nodes
     int traceBlocksPerSM = 0; // 0: occupancy calculator
     int numSMs = 148;
@@ -198,6 +205,7 @@ SceneView makeScene(const flx_ctx *c)
     s.materials = c->materials;
     s.textures = c->texDesc;
     s.texData = c->texData;
+    s.kdGamma = c->kdGamma;
     s.envRGBA = c->envRGBA;
     s.envW = c->envW;
     s.envH = c->envH;
@@ -257,14 +265,14 @@ struct Timed
             cudaEventCreate(&ev.b);
         }
         ev.kernel = k;
-        cudaEventRecord(ev.a, c->stream);
+        cudaEventRecord(ev.a, c->cur);
     }
     ~Timed()
     {
         c->kernelLaunches[k]++;
         if (!on)
             return;
-        cudaEventRecord(ev.b, c->stream);
+        cudaEventRecord(ev.b, c->cur);
         c->pendingEvents.push_back(ev);
     }
 };
@@ -477,7 +485,7 @@ template <bool ANYHIT, class COUNT> static int launchPersistentT(flx_ctx *ctx, u
         const int top = (int)std::min<uint32_t>({(uint32_t)ctx->topNodes, ctx->treeletNodes, ctx->nTNodes, (uint32_t)((ctx->maxDynSmem - 1024) / 64)});
         const size_t smem = (size_t)top * 64;
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<ctx->numSMs, BLOCK, smem, ctx->stream>>>(fr, ctx->params, bvh, ctx->tris, fetch, ctx->fetchThreshold, ctx->innerMin, top, counts);
+        kern<<<ctx->numSMs, BLOCK, smem, ctx->cur>>>(fr, ctx->params, bvh, ctx->tris, fetch, ctx->fetchThreshold, ctx->innerMin, ctx->fetchChunk, top, counts);
     }
     else
     {
@@ -486,7 +494,7 @@ template <bool ANYHIT, class COUNT> static int launchPersistentT(flx_ctx *ctx, u
         if (perSM <= 0)
             CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, FLX_TRACE_BLOCK, 0));
         const unsigned grid = (unsigned)std::max(1, perSM) * (unsigned)ctx->numSMs;
-        kern<<<grid, FLX_TRACE_BLOCK, 0, ctx->stream>>>(fr, ctx->params, bvh, ctx->tris, fetch, ctx->fetchThreshold, ctx->innerMin, 0, counts);
+        kern<<<grid, FLX_TRACE_BLOCK, 0, ctx->cur>>>(fr, ctx->params, bvh, ctx->tris, fetch, ctx->fetchThreshold, ctx->innerMin, ctx->fetchChunk, 0, counts);
     }
     return 0;
 }
@@ -494,7 +502,7 @@ template <bool ANYHIT, class COUNT> static int launchPersistentT(flx_ctx *ctx, u
 template <bool ANYHIT> static int launchPersistent(flx_ctx *ctx)
 {
     uint32_t *fetch = ctx->fetchCounters + (ANYHIT ? 1 : 0);
-    CU(cudaMemsetAsync(fetch, 0, sizeof(uint32_t), ctx->stream));
+    CU(cudaMemsetAsync(fetch, 0, sizeof(uint32_t), ctx->cur));
     Timed tm(ctx, ANYHIT ? FLX_K_SHADOWRAYS : FLX_K_EXTRAYS);
     int rc = ctx->counting ? launchPersistentT<ANYHIT, RayCount>(ctx, fetch, ctx->traceCounts + (ANYHIT ? 5 : 0)) : launchPersistentT<ANYHIT, NoCount>(ctx, fetch, nullptr);
     if (rc)
@@ -547,6 +555,10 @@ int flx_create(int device, uint32_t num_tasks, flx_ctx **out)
         }                                                                                                              \
     } while (0)
     CUB(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUB(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    c->cur = c->stream;
+    CUB(cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming));
+    CUB(cudaEventCreateWithFlags(&c->evJoin, cudaEventDisableTiming));
     const size_t taskBytes = (size_t)num_tasks * FLX_NUM_SLOTS * sizeof(uint32_t); // initMCBuffers, clcontext.cpp:116-141
     CUB(cudaMalloc(&c->tasks, taskBytes));
     CUB(cudaMemset(c->tasks, 0, taskBytes));
@@ -622,6 +634,7 @@ void flx_destroy(flx_ctx *c)
         cudaFreeHost(c->pinnedCounters);
     freeDev(c->tris);
     freeDev(c->materials);
+    freeDev(c->kdGamma);
     freeDev(c->texDesc);
     freeDev(c->texData);
     freeDev(c->tnodes);
@@ -635,6 +648,12 @@ void flx_destroy(flx_ctx *c)
     freeDev(c->denoiserNormal);
     freeDev(c->gatherBuf);
     freeDev(c->fullImage);
+    if (c->evFork)
+        cudaEventDestroy(c->evFork);
+    if (c->evJoin)
+        cudaEventDestroy(c->evJoin);
+    if (c->stream2)
+        cudaStreamDestroy(c->stream2);
     if (c->stream)
         cudaStreamDestroy(c->stream);
     delete c;
@@ -684,6 +703,11 @@ int flx_upload_scene(flx_ctx *ctx, const flx_Triangle *tris, uint32_t n_tris, co
     if ((rc = uploadArray(ctx, ctx->tris, tris, n_tris)))
         return rc;
     if ((rc = uploadArray(ctx, ctx->materials, materials, n_materials)))
+        return rc;
+    std::vector<float4> kdGamma(n_materials);
+    for (uint32_t i = 0; i < n_materials; i++) // matGetAlbedo of an untextured material (utils.cl:136-141), hoisted out of the kernels
+        kdGamma[i] = make_float4(flx_powf(materials[i].Kd.x, 2.2f), flx_powf(materials[i].Kd.y, 2.2f), flx_powf(materials[i].Kd.z, 2.2f), 0.0f);
+    if ((rc = uploadArray(ctx, ctx->kdGamma, kdGamma.data(), n_materials)))
         return rc;
     if ((rc = uploadArray(ctx, ctx->texDesc, tex_desc, n_tex)))
         return rc;
@@ -829,9 +853,9 @@ int flx_enqueue_extrays(flx_ctx *ctx)
     Timed tm(ctx, FLX_K_EXTRAYS);
     const unsigned grid = (ctx->numTasks + FLX_TRACE_BLOCK - 1) / FLX_TRACE_BLOCK;
     if (ctx->counting)
-        k_extrays<RayCount><<<grid, FLX_TRACE_BLOCK, 0, ctx->stream>>>(makeFrame(ctx), ctx->params, makeBvh(ctx), ctx->tris, ctx->traceCounts);
+        k_extrays<RayCount><<<grid, FLX_TRACE_BLOCK, 0, ctx->cur>>>(makeFrame(ctx), ctx->params, makeBvh(ctx), ctx->tris, ctx->traceCounts);
     else
-        k_extrays<NoCount><<<grid, FLX_TRACE_BLOCK, 0, ctx->stream>>>(makeFrame(ctx), ctx->params, makeBvh(ctx), ctx->tris, nullptr);
+        k_extrays<NoCount><<<grid, FLX_TRACE_BLOCK, 0, ctx->cur>>>(makeFrame(ctx), ctx->params, makeBvh(ctx), ctx->tris, nullptr);
     return launchCheck(ctx, "k_extrays");
 }
 
@@ -846,9 +870,9 @@ int flx_enqueue_shadowrays(flx_ctx *ctx)
     Timed tm(ctx, FLX_K_SHADOWRAYS);
     const unsigned grid = (ctx->numTasks + FLX_TRACE_BLOCK - 1) / FLX_TRACE_BLOCK;
     if (ctx->counting)
-        k_shadowrays<RayCount><<<grid, FLX_TRACE_BLOCK, 0, ctx->stream>>>(makeFrame(ctx), ctx->params, makeBvh(ctx), ctx->traceCounts + 5);
+        k_shadowrays<RayCount><<<grid, FLX_TRACE_BLOCK, 0, ctx->cur>>>(makeFrame(ctx), ctx->params, makeBvh(ctx), ctx->traceCounts + 5);
     else
-        k_shadowrays<NoCount><<<grid, FLX_TRACE_BLOCK, 0, ctx->stream>>>(makeFrame(ctx), ctx->params, makeBvh(ctx), nullptr);
+        k_shadowrays<NoCount><<<grid, FLX_TRACE_BLOCK, 0, ctx->cur>>>(makeFrame(ctx), ctx->params, makeBvh(ctx), nullptr);
     return launchCheck(ctx, "k_shadowrays");
 }
 
@@ -864,10 +888,17 @@ int flx_enqueue_logic(flx_ctx *ctx, int first_iteration)
     CU(cudaMemsetAsync(ctx->scanTicket, 0, sizeof(uint32_t), ctx->stream));
     ScanState scan{ctx->scanTiles, ctx->scanTicket};
     Timed tm(ctx, FLX_K_LOGIC);
-    if (ctx->params.wfSeparateQueues)
-        k_logic<true><<<tiles, FLX_BLOCK, 0, ctx->stream>>>(makeFrame(ctx), ctx->params, makeScene(ctx), scan, maxId);
-    else
-        k_logic<false><<<tiles, FLX_BLOCK, 0, ctx->stream>>>(makeFrame(ctx), ctx->params, makeScene(ctx), scan, maxId);
+    const Frame fr = makeFrame(ctx);
+    const SceneView sc = makeScene(ctx);
+    const bool sep = ctx->params.wfSeparateQueues != 0;
+#define LOGIC(SEP, MB) k_logic<SEP, MB><<<tiles, FLX_BLOCK, 0, ctx->stream>>>(fr, ctx->params, sc, scan, maxId)
+    switch (ctx->logicMinBlocks)
+    {
+    case 2: if (sep) LOGIC(true, 2); else LOGIC(false, 2); break;
+    case 4: if (sep) LOGIC(true, 4); else LOGIC(false, 4); break;
+    default: if (sep) LOGIC(true, 3); else LOGIC(false, 3); break;
+    }
+#undef LOGIC
     return launchCheck(ctx, "k_logic");
 }
 
@@ -980,10 +1011,29 @@ int flx_render(flx_ctx *ctx, uint32_t n_iterations)
         if ((rc = flx_enqueue_materials(ctx)))
             return rc;
         k_snapshot_counters<<<1, 32, 0, ctx->stream>>>(it);
-        if ((rc = flx_enqueue_extrays(ctx)))
-            return rc;
-        if ((rc = flx_enqueue_shadowrays(ctx)))
-            return rc;
+        if (ctx->overlapTrace)
+        {
+            // the two traversal stages are independent (disjoint inputs and outputs): fork the shadow rays onto a second
+            // stream so their CTAs fill the SMs the extension kernel's tail leaves idle, join before the bookkeeping
+            CU(cudaEventRecord(ctx->evFork, ctx->stream));
+            CU(cudaStreamWaitEvent(ctx->stream2, ctx->evFork, 0));
+            if ((rc = flx_enqueue_extrays(ctx)))
+                return rc;
+            ctx->cur = ctx->stream2;
+            rc = flx_enqueue_shadowrays(ctx);
+            ctx->cur = ctx->stream;
+            if (rc)
+                return rc;
+            CU(cudaEventRecord(ctx->evJoin, ctx->stream2));
+            CU(cudaStreamWaitEvent(ctx->stream, ctx->evJoin, 0));
+        }
+        else
+        {
+            if ((rc = flx_enqueue_extrays(ctx)))
+                return rc;
+            if ((rc = flx_enqueue_shadowrays(ctx)))
+                return rc;
+        }
         {
             Timed tm(ctx, FLX_K_END_ITERATION);
             k_end_iteration<<<1, 32, 0, ctx->stream>>>(it);
@@ -1052,6 +1102,17 @@ int flx_set_tuning(flx_ctx *ctx, int key, int value)
     case FLX_TUNE_INNER_MIN:
         REQUIRE(value >= 1 && value <= 32, "flx_set_tuning: inner-phase minimum must be in 1..32");
         ctx->innerMin = value;
+        return 0;
+    case FLX_TUNE_OVERLAP_TRACE:
+        ctx->overlapTrace = value != 0;
+        return 0;
+    case FLX_TUNE_FETCH_CHUNK:
+        REQUIRE(value >= 32 && value <= 4096, "flx_set_tuning: fetch chunk must be in 32..4096");
+        ctx->fetchChunk = value;
+        return 0;
+    case FLX_TUNE_LOGIC_MIN_BLOCKS:
+        REQUIRE(value == 2 || value == 3 || value == 4, "flx_set_tuning: logic min blocks must be 2, 3 or 4");
+        ctx->logicMinBlocks = value;
         return 0;
     case FLX_TUNE_TOP_NODES:
         REQUIRE(value >= 0 && value <= 4096, "flx_set_tuning: top nodes must be in 0..4096");

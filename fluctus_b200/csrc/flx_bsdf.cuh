@@ -14,6 +14,7 @@ struct SceneView
     const flx_Material *materials;
     const flx_TexDescriptor *textures;
     const uint8_t *texData;
+    const float4 *kdGamma; // per material: pow(Kd, 2.2) evaluated once at upload with the same flx_powf (bit-identical)
     // environment map (RGBA32F) + alias-method tables
     const float *envRGBA;
     int envW, envH;
@@ -31,12 +32,12 @@ struct Surface // the hit record as the BSDF code sees it (reference: Hit, src/g
 
 struct Mat // reference: Material, src/geom.h:113-124
 {
-    V3 Kd, Ks;
+    V3 Kd, Ks, KdGamma;
     float Ns, Ni;
     int map_Kd, map_Ks, map_N, type;
 };
 
-FLX_DEV Mat load_material(const flx_Material *materials, int id)
+FLX_DEV Mat load_material(const flx_Material *materials, int id, const float4 *kdGamma)
 {
     // 80-byte records, 16-byte aligned: five 128-bit loads
     const float4 *p = reinterpret_cast<const float4 *>(materials + id);
@@ -44,6 +45,8 @@ FLX_DEV Mat load_material(const flx_Material *materials, int id)
     Mat m;
     m.Kd = v3(a.x, a.y, a.z);
     m.Ks = v3(b.x, b.y, b.z);
+    const float4 g = __ldg(kdGamma + id);
+    m.KdGamma = v3(g.x, g.y, g.z);
     m.Ns = d.x;
     m.Ni = d.y;
     m.map_Kd = __float_as_int(d.z);
@@ -155,7 +158,12 @@ FLX_DEV float fresnel_dielectric(float cosI, float etaI, float etaT)
 }
 
 // ---- Lambert (reference: src/diffuse.cl:9-26)
-FLX_DEV V3 diffuse_value(const Surface &s, const Mat &m, const SceneView &sc) { return mat_albedo(m.Kd, s.u, s.v, m.map_Kd, sc) * FLX_INV_PI_F; }
+FLX_DEV V3 diffuse_value(const Surface &s, const Mat &m, const SceneView &sc)
+{
+    // untextured: the gamma-expanded albedo is a per-material constant (utils.cl:136-141 evaluates pow per call)
+    const V3 kd = (m.map_Kd == -1) ? m.KdGamma : mat_albedo(m.Kd, s.u, s.v, m.map_Kd, sc);
+    return kd * FLX_INV_PI_F;
+}
 FLX_DEV float diffuse_pdf(const Surface &s, V3 dirOut) { return dot3(s.N, dirOut) * FLX_INV_PI_F; }
 FLX_DEV V3 diffuse_sample(const Surface &s, const Mat &m, const SceneView &sc, V3 &dirOut, float &pdfW, uint32_t &seed)
 {

@@ -105,9 +105,18 @@ __global__ void __launch_bounds__(FLX_BLOCK) k_raygen(const __grid_constant__ Fr
 {
     const uint32_t count = fr.counters->raygenQueue;
     const uint32_t curr = *fr.currPixelIdx;
-    for (uint32_t gd = blockIdx.x * FLX_BLOCK + threadIdx.x; gd < count; gd += gridDim.x * FLX_BLOCK)
+    __shared__ uint32_t s_extBase;
+    for (uint32_t base = blockIdx.x * FLX_BLOCK; base < count; base += gridDim.x * FLX_BLOCK)
     {
-        const uint32_t gid = fr.queues[Q_RAYGEN][gd];
+        // every path of this chunk goes to the extension queue: one atomic per CTA reserves the slots up front
+        if (threadIdx.x == 0)
+            s_extBase = atomicAdd(counter_ptr(fr.counters, Q_EXT), min((uint32_t)FLX_BLOCK, count - base));
+        const uint32_t gd = base + threadIdx.x;
+        const bool valid = gd < count;
+        uint32_t gid = 0;
+        if (valid)
+        {
+        gid = fr.queues[Q_RAYGEN][gd];
         const Tasks &t = fr.tasks;
         uint32_t seed = t.u(FLX_S_SEED, gid);
 
@@ -142,8 +151,11 @@ __global__ void __launch_bounds__(FLX_BLOCK) k_raygen(const __grid_constant__ Fr
         t.setu(FLX_S_SEED, gid, seed);
         reset_path_fields(t, gid, prm.worldRadius);
 
-        const uint32_t slot = warp_push(counter_ptr(fr.counters, Q_EXT), true);
-        fr.queues[Q_EXT][slot] = gid;
+        }
+        __syncthreads();
+        if (valid)
+            fr.queues[Q_EXT][s_extBase + threadIdx.x] = gid;
+        __syncthreads();
     }
 }
 
@@ -276,8 +288,8 @@ FLX_DEV void st_relaxed(unsigned long long *p, unsigned long long v) { asm volat
 
 FLX_DEV float luminance3(V3 v) { return (0.212671f * v.x + 0.715160f * v.y) + 0.072169f * v.z; } // utils.cl:237-240
 
-template <bool SEPARATE_QUEUES>
-__global__ void __launch_bounds__(FLX_BLOCK) k_logic(const __grid_constant__ Frame fr, const __grid_constant__ flx_RenderParams prm, const SceneView sc,
+template <bool SEPARATE_QUEUES, int MIN_BLOCKS>
+__global__ void __launch_bounds__(FLX_BLOCK, MIN_BLOCKS) k_logic(const __grid_constant__ Frame fr, const __grid_constant__ flx_RenderParams prm, const SceneView sc,
                                                      const ScanState scan, const uint32_t maxId)
 {
     __shared__ uint32_t s_tile;
@@ -292,10 +304,15 @@ __global__ void __launch_bounds__(FLX_BLOCK) k_logic(const __grid_constant__ Fra
     const Tasks &t = fr.tasks;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-    // ---- phase 1: decide termination (wf_logic.cl:48-127) -------------------------------------------------
-    uint32_t seed = 0, len = 0;
+    // ---- all loads up front: one DRAM round trip instead of a chain of dependent ones (this stage is latency-bound:
+    //      ncu showed 17 warps stalled on the long scoreboard per issued instruction at 36 % occupancy).  Fields that only
+    //      some paths need (the pending light sample, the hit record) are fetched for all: ~10 % more bytes, 3 fewer trips.
+    uint32_t seed = 0, len = 0, pixIdx = 0;
     V3 T = v3(0.0f), rayOrig = v3(0.0f), rayDir = v3(0.0f), Ei = v3(0.0f);
-    int hitI = -1, hitLight = 0;
+    V3 hP = v3(0.0f), hN = v3(0.0f), neeEmission = v3(0.0f), neeBsdf = v3(0.0f), neeT = v3(0.0f);
+    float hU = 0.0f, hV = 0.0f, lastPdfW = 0.0f, lastLightPick = 0.0f, neeCosTh = 0.0f, neePdfDirect = 0.0f, neePdfImplicit = 0.0f;
+    int hitI = -1, hitLight = 0, matId = 0;
+    bool lastSpecular = false, blocked = true;
     bool terminate = false;
     if (live)
     {
@@ -303,10 +320,31 @@ __global__ void __launch_bounds__(FLX_BLOCK) k_logic(const __grid_constant__ Fra
         len = t.u(FLX_S_PATH_LEN, gid);
         hitI = (int)t.u(FLX_S_HIT_I, gid);
         hitLight = (int)t.u(FLX_S_AREA_LIGHT_HIT, gid);
+        matId = (int)t.u(FLX_S_MAT_ID, gid);
         rayOrig = t.v(FLX_S_ORIG, gid);
         rayDir = t.v(FLX_S_DIR, gid);
         T = t.v(FLX_S_T, gid);
         Ei = t.v(FLX_S_EI, gid);
+        lastPdfW = t.f(FLX_S_LAST_PDF_W, gid);
+        lastSpecular = t.u(FLX_S_LAST_SPECULAR, gid) != 0u;
+        lastLightPick = t.f(FLX_S_LAST_LIGHT_PICK, gid);
+        blocked = t.u(FLX_S_SHADOW_BLOCKED, gid) != 0u;
+        pixIdx = t.u(FLX_S_PIXEL_INDEX, gid);
+        hP = t.v(FLX_S_P, gid);
+        hN = t.v(FLX_S_N, gid);
+        hU = t.f(FLX_S_UV, gid);
+        hV = t.f(FLX_S_UV + 1, gid);
+        neeEmission = t.v(FLX_S_LAST_EMISSION, gid);
+        neeBsdf = t.v(FLX_S_LAST_BSDF, gid);
+        neeT = t.v(FLX_S_LAST_T, gid);
+        neeCosTh = t.f(FLX_S_LAST_COS_TH, gid);
+        neePdfDirect = t.f(FLX_S_LAST_PDF_DIRECT, gid);
+        neePdfImplicit = t.f(FLX_S_LAST_PDF_IMPLICIT, gid);
+    }
+
+    // ---- phase 1: decide termination (wf_logic.cl:48-127) -------------------------------------------------
+    if (live)
+    {
         terminate = (len >= prm.maxBounces + 1u);
         if (terminate && prm.useRoulette)
         {
@@ -315,43 +353,35 @@ __global__ void __launch_bounds__(FLX_BLOCK) k_logic(const __grid_constant__ Fra
             T = T / contProb;
             t.setv(FLX_S_T, gid, T);
         }
-        const float lastPdfW = t.f(FLX_S_LAST_PDF_W, gid);
         if (is_zero3(T) || lastPdfW == 0.0f)
             terminate = true;
 
         if (hitI < 0 && !terminate) // escaped: implicit environment sample
         {
             float weight = 1.0f;
-            const bool lastSpecular = t.u(FLX_S_LAST_SPECULAR, gid) != 0u;
             V3 bg = v3(0.0f);
             if (prm.useEnvMap && (len == 1u || prm.sampleImpl))
                 bg = env_eval_dir(sc, rayDir) * prm.envMapStrength;
             if (prm.sampleImpl && prm.sampleExpl && prm.useEnvMap && len > 1u && !lastSpecular)
             {
-                const float lightPickProb = t.f(FLX_S_LAST_LIGHT_PICK, gid);
                 const float directPdfW = env_pdf(sc, rayDir);
-                weight = (lastPdfW * lightPickProb) / (lastPdfW * lightPickProb + directPdfW);
+                weight = (lastPdfW * lastLightPick) / (lastPdfW * lastLightPick + directPdfW);
             }
             Ei = Ei + (weight * T) * bg;
-            t.setv(FLX_S_EI, gid, Ei);
             terminate = true;
         }
         else if (hitLight && !terminate) // implicit area-light sample
         {
             float misWeight = 1.0f;
-            const bool lastSpecular = t.u(FLX_S_LAST_SPECULAR, gid) != 0u;
             if (prm.sampleExpl && len > 1u && !lastSpecular)
             {
-                const V3 hP = t.v(FLX_S_P, gid), hN = t.v(FLX_S_N, gid);
                 const float directPdfA = 1.0f / (4.0f * prm.areaLight.size.x * prm.areaLight.size.y);
                 const float dist = len3(hP - rayOrig);
                 const float cosine = dot3(norm3(-rayDir), hN);
                 const float directPdfW = directPdfA * (dist * dist) / fabsf(cosine); // pdfAtoW, utils.cl:197-200
-                const float lightPickProb = t.f(FLX_S_LAST_LIGHT_PICK, gid);
-                misWeight = lastPdfW / (lastPdfW + directPdfW * lightPickProb);
+                misWeight = lastPdfW / (lastPdfW + directPdfW * lastLightPick);
             }
             Ei = Ei + (T * misWeight) * v3(prm.areaLight.E);
-            t.setv(FLX_S_EI, gid, Ei);
             terminate = true;
         }
     }
@@ -375,40 +405,39 @@ __global__ void __launch_bounds__(FLX_BLOCK) k_logic(const __grid_constant__ Fra
     // ---- phase 2: previous vertex's light sample, splat, next-event estimation (wf_logic.cl:129-303) -------
     if (live)
     {
-        if (t.u(FLX_S_SHADOW_BLOCKED, gid) == 0u)
+        bool eiDirty = terminate && (hitI < 0 || hitLight); // Ei was updated above only on the implicit-hit branches
+        // (a terminated path whose Ei did not change keeps its stored value; writing the same bits back is harmless, so
+        //  the flag only saves stores)
+        if (!blocked)
         {
-            const V3 emission = t.v(FLX_S_LAST_EMISSION, gid), bsdf = t.v(FLX_S_LAST_BSDF, gid), lastT = t.v(FLX_S_LAST_T, gid);
-            const float cosTh = t.f(FLX_S_LAST_COS_TH, gid), directPdfW = t.f(FLX_S_LAST_PDF_DIRECT, gid);
-            const float bsdfPdfW = t.f(FLX_S_LAST_PDF_IMPLICIT, gid), lightPickProb = t.f(FLX_S_LAST_LIGHT_PICK, gid);
             float weight = 1.0f;
             if (prm.sampleImpl)
-                weight = (directPdfW * lightPickProb) / (directPdfW * lightPickProb + bsdfPdfW);
-            const V3 contrib = ((((bsdf * lastT) * emission) * weight) * cosTh) / (lightPickProb * directPdfW);
+                weight = (neePdfDirect * lastLightPick) / (neePdfDirect * lastLightPick + neePdfImplicit);
+            const V3 contrib = ((((neeBsdf * neeT) * neeEmission) * weight) * neeCosTh) / (lastLightPick * neePdfDirect);
             Ei = Ei + contrib;
-            t.setv(FLX_S_EI, gid, Ei);
+            eiDirty = true;
         }
+        if (eiDirty)
+            t.setv(FLX_S_EI, gid, Ei);
         if (terminate)
         {
             if (len > 0u)
-            {
-                const uint32_t pix = t.u(FLX_S_PIXEL_INDEX, gid);
-                atomicAdd(reinterpret_cast<float4 *>(fr.pixels) + pix, make_float4(Ei.x, Ei.y, Ei.z, 1.0f)); // one 128-bit reduction
-            }
+                atomicAdd(reinterpret_cast<float4 *>(fr.pixels) + pixIdx, make_float4(Ei.x, Ei.y, Ei.z, 1.0f)); // one 128-bit reduction
             t.setu(FLX_S_SEED, gid, seed);
         }
     }
 
-    bool toMaterial = false;
+    bool toMaterial = false, pushShadow = false;
     int matType = 0;
     if (live && !terminate)
     {
         Surface s;
-        s.P = t.v(FLX_S_P, gid);
-        s.N = t.v(FLX_S_N, gid);
-        s.u = t.f(FLX_S_UV, gid);
-        s.v = t.f(FLX_S_UV + 1, gid);
+        s.P = hP;
+        s.N = hN;
+        s.u = hU;
+        s.v = hV;
         s.tri = hitI;
-        const Mat mat = load_material(sc.materials, (int)t.u(FLX_S_MAT_ID, gid));
+        const Mat mat = load_material(sc.materials, matId, sc.kdGamma);
         V3 N = shading_normal(s, mat, sc);
         const bool backface = dot3(N, rayDir) > 0.0f;
         if (backface)
@@ -418,7 +447,6 @@ __global__ void __launch_bounds__(FLX_BLOCK) k_logic(const __grid_constant__ Fra
         t.setu(FLX_S_BACKFACE, gid, backface ? 1u : 0u);
 
         const bool singular = (mat.type & (FLX_BXDF_IDEAL_REFLECTION | FLX_BXDF_IDEAL_DIELECTRIC)) != 0;
-        bool pushShadow = false;
         if (prm.sampleExpl && !singular)
         {
             const uint32_t nLights = prm.useEnvMap + prm.useAreaLight;
@@ -478,36 +506,65 @@ __global__ void __launch_bounds__(FLX_BLOCK) k_logic(const __grid_constant__ Fra
         toMaterial = true;
         matType = mat.type;
 
-        const uint32_t slot = warp_push(counter_ptr(fr.counters, Q_SHADOW), pushShadow);
-        if (pushShadow)
-            fr.queues[Q_SHADOW][slot] = gid;
     }
 
-    // ---- material queues: one warp-aggregated atomic per queue per warp (wf_logic.cl:459-519 intent) --------
-    if (!SEPARATE_QUEUES)
+    // ---- shadow + material queues: ONE atomic per queue per 256-path tile.  All paths of a tile hammer the same
+    //      counter word, and same-address atomics serialise in the L2 slice that owns it; aggregating over the CTA
+    //      (ballot -> per-warp counts in shared memory -> one atomicAdd by one thread per queue) cuts them 8x versus the
+    //      per-warp aggregation the reference's NVIDIA path does (wf_logic.cl:459-519, ptx_asm.cl:83-111).
     {
-        const uint32_t slot = warp_push(counter_ptr(fr.counters, Q_DIFFUSE), toMaterial);
-        if (toMaterial)
-            fr.queues[Q_DIFFUSE][slot] = gid;
-    }
-    else
-    {
-        int q = -1;
+        constexpr int NQ = SEPARATE_QUEUES ? 6 : 2; // slot 0: shadow, slots 1..: material queues
+        constexpr int NW = FLX_BLOCK / 32;
+        __shared__ uint32_t s_cnt[6][NW];
+        __shared__ uint32_t s_qbase[6];
+        int q = -1; // material queue slot of this path (1-based), -1: none
         if (toMaterial)
         {
-            if (matType == FLX_BXDF_DIFFUSE) q = Q_DIFFUSE;
-            else if (matType == FLX_BXDF_GLOSSY) q = Q_GLOSSY;
-            else if (matType == FLX_BXDF_GGX_ROUGH_REFLECTION) q = Q_GGXREFL;
-            else if (matType == FLX_BXDF_GGX_ROUGH_DIELECTRIC) q = Q_GGXREFR;
-            else if (matType == FLX_BXDF_IDEAL_REFLECTION || matType == FLX_BXDF_IDEAL_DIELECTRIC) q = Q_DELTA;
+            if (!SEPARATE_QUEUES) q = 1;
+            else if (matType == FLX_BXDF_DIFFUSE) q = 1;
+            else if (matType == FLX_BXDF_GLOSSY) q = 2;
+            else if (matType == FLX_BXDF_GGX_ROUGH_REFLECTION) q = 3;
+            else if (matType == FLX_BXDF_GGX_ROUGH_DIELECTRIC) q = 4;
+            else if (matType == FLX_BXDF_IDEAL_REFLECTION || matType == FLX_BXDF_IDEAL_DIELECTRIC) q = 5;
             // any other type is dropped, as in the reference (wf_logic.cl:362-364)
         }
+        unsigned myMask = 0u, shadowMask = __ballot_sync(0xffffffffu, pushShadow);
+        if (lane == 0)
+            s_cnt[0][warp] = __popc(shadowMask);
 #pragma unroll
-        for (int qq = Q_DIFFUSE; qq <= Q_DELTA; qq++)
+        for (int k = 1; k < NQ; k++)
         {
-            const uint32_t slot = warp_push(counter_ptr(fr.counters, qq), q == qq);
-            if (q == qq)
-                fr.queues[qq][slot] = gid;
+            const unsigned m = __ballot_sync(0xffffffffu, q == k);
+            if (lane == 0)
+                s_cnt[k][warp] = __popc(m);
+            if (q == k)
+                myMask = m;
+        }
+        __syncthreads();
+        if (threadIdx.x < NQ)
+        {
+            uint32_t total = 0;
+#pragma unroll
+            for (int w = 0; w < NW; w++)
+                total += s_cnt[threadIdx.x][w];
+            const int queueId = threadIdx.x == 0 ? Q_SHADOW : Q_DIFFUSE + (int)threadIdx.x - 1;
+            s_qbase[threadIdx.x] = total ? atomicAdd(counter_ptr(fr.counters, queueId), total) : 0u;
+        }
+        __syncthreads();
+        const unsigned below = (1u << lane) - 1u;
+        if (pushShadow)
+        {
+            uint32_t slot = s_qbase[0] + __popc(shadowMask & below);
+            for (int w = 0; w < warp; w++)
+                slot += s_cnt[0][w];
+            fr.queues[Q_SHADOW][slot] = gid;
+        }
+        if (q > 0)
+        {
+            uint32_t slot = s_qbase[q] + __popc(myMask & below);
+            for (int w = 0; w < warp; w++)
+                slot += s_cnt[q][w];
+            fr.queues[Q_DIFFUSE + q - 1][slot] = gid;
         }
     }
 
@@ -561,9 +618,17 @@ __global__ void __launch_bounds__(FLX_BLOCK) k_material(const __grid_constant__ 
 {
     const uint32_t count = *counter_ptr(fr.counters, queue);
     const Tasks &t = fr.tasks;
-    for (uint32_t gd = blockIdx.x * FLX_BLOCK + threadIdx.x; gd < count; gd += gridDim.x * FLX_BLOCK)
+    __shared__ uint32_t s_extBase;
+    for (uint32_t base = blockIdx.x * FLX_BLOCK; base < count; base += gridDim.x * FLX_BLOCK)
     {
-        const uint32_t gid = fr.queues[queue][gd];
+        if (threadIdx.x == 0) // one atomic per CTA reserves this chunk's extension-queue slots
+            s_extBase = atomicAdd(counter_ptr(fr.counters, Q_EXT), min((uint32_t)FLX_BLOCK, count - base));
+        const uint32_t gd = base + threadIdx.x;
+        const bool valid = gd < count;
+        uint32_t gid = 0;
+        if (valid)
+        {
+        gid = fr.queues[queue][gd];
         uint32_t seed = t.u(FLX_S_SEED, gid);
         Surface s;
         s.P = t.v(FLX_S_P, gid);
@@ -571,10 +636,11 @@ __global__ void __launch_bounds__(FLX_BLOCK) k_material(const __grid_constant__ 
         s.u = t.f(FLX_S_UV, gid);
         s.v = t.f(FLX_S_UV + 1, gid);
         s.tri = (int)t.u(FLX_S_HIT_I, gid);
-        const Mat mat = load_material(sc.materials, (int)t.u(FLX_S_MAT_ID, gid));
+        const Mat mat = load_material(sc.materials, (int)t.u(FLX_S_MAT_ID, gid), sc.kdGamma);
         const bool backface = t.u(FLX_S_BACKFACE, gid) != 0u;
         const V3 dirIn = t.v(FLX_S_DIR, gid); // points toward the surface
         const V3 L = t.v(FLX_S_SHADOW_DIR, gid);
+        const V3 oldT = t.v(FLX_S_T, gid);
 
         // BSDF value and pdf toward the pending light sample (wf_mat_*.cl:33-36)
         const V3 bsdfNEE = bxdf_eval<MASK>(s, mat, backface, sc, dirIn, L);
@@ -587,7 +653,6 @@ __global__ void __launch_bounds__(FLX_BLOCK) k_material(const __grid_constant__ 
         V3 newDir = v3(0.0f);
         const V3 bsdf = bxdf_sample<MASK>(s, mat, backface, sc, dirIn, newDir, pdfW, seed);
         const float costh = dot3(s.N, norm3(newDir));
-        const V3 oldT = t.v(FLX_S_T, gid);
         V3 newT = v3(0.0f);
         if (!(pdfW == 0.0f || is_zero3(bsdf)))
             newT = ((oldT * bsdf) * costh) / pdfW;
@@ -600,8 +665,11 @@ __global__ void __launch_bounds__(FLX_BLOCK) k_material(const __grid_constant__ 
         t.setu(FLX_S_SEED, gid, seed);
         t.setu(FLX_S_LAST_SPECULAR, gid, (mat.type & (FLX_BXDF_IDEAL_REFLECTION | FLX_BXDF_IDEAL_DIELECTRIC)) != 0 ? 1u : 0u);
 
-        const uint32_t slot = warp_push(counter_ptr(fr.counters, Q_EXT), true);
-        fr.queues[Q_EXT][slot] = gid;
+        }
+        __syncthreads();
+        if (valid)
+            fr.queues[Q_EXT][s_extBase + threadIdx.x] = gid;
+        __syncthreads();
     }
 }
 

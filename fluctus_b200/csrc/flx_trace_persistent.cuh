@@ -71,7 +71,7 @@ FLX_DEV void stage_bulk(void *dstShared, const void *srcGlobal, uint32_t bytes, 
 template <bool ANYHIT, class COUNT, int BLOCK, bool TOP>
 __global__ void __launch_bounds__(BLOCK, TOP ? 1 : (ANYHIT ? 10 : 8)) k_trace_persistent(const __grid_constant__ Frame fr, const __grid_constant__ flx_RenderParams prm,
                                                                          const BvhView bvh, const flx_Triangle *tris160, uint32_t *fetchCounter,
-                                                                         const int threshold, const int innerMin, const int topCount, unsigned long long *countTotals)
+                                                                         const int threshold, const int innerMin, const int fetchChunk, const int topCount, unsigned long long *countTotals)
 {
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(128) unsigned char dynSmem[];
@@ -95,6 +95,7 @@ __global__ void __launch_bounds__(BLOCK, TOP ? 1 : (ANYHIT ? 10 : 8)) k_trace_pe
     int stack[FLX_STACK_DEPTH];
     COUNT cnt;
     unsigned raysDone = 0;
+    uint32_t chunkNext = 0, chunkEnd = 0, chunkSize = (uint32_t)fetchChunk; // warp-uniform
 
     while (true)
     {
@@ -141,19 +142,37 @@ __global__ void __launch_bounds__(BLOCK, TOP ? 1 : (ANYHIT ? 10 : 8)) k_trace_pe
             }
         }
 
-        // ---- idle lanes take the next rays of the queue: one atomic per warp
+        // ---- idle lanes take the next rays of the queue.  A warp reserves the queue in chunks (one atomic per chunk, not
+        //      per refill: every warp of the grid hits the same counter word and same-address atomics serialise in L2)
+        //      and hands the chunk out locally; chunks shrink to 32 near the end of the queue to keep the tail balanced.
         const bool need = !active && !exhausted;
         const unsigned needMask = __ballot_sync(FULL, need);
         if (needMask)
         {
-            uint32_t base = 0;
-            const int leader = __ffs(needMask) - 1;
-            if (lane == leader)
-                base = atomicAdd(fetchCounter, (uint32_t)__popc(needMask));
-            base = __shfl_sync(FULL, base, leader);
+            const uint32_t needCount = (uint32_t)__popc(needMask);
+            const uint32_t avail = chunkEnd - chunkNext; // warp-uniform
+            uint32_t base = chunkNext, fresh = 0;
+            if (avail < needCount)
+            {
+                if (lane == 0)
+                    fresh = atomicAdd(fetchCounter, chunkSize);
+                fresh = __shfl_sync(FULL, fresh, 0);
+            }
+            const uint32_t rank = (uint32_t)__popc(needMask & lanesBelow);
+            uint32_t idx = base + rank;
+            if (avail < needCount)
+            {
+                if (rank >= avail)
+                    idx = fresh + (rank - avail);
+                chunkNext = fresh + (needCount - avail);
+                chunkEnd = fresh + chunkSize;
+                if (fresh + chunkSize > count - count / 4u)
+                    chunkSize = 32u;
+            }
+            else
+                chunkNext += needCount;
             if (need)
             {
-                const uint32_t idx = base + (uint32_t)__popc(needMask & lanesBelow);
                 if (idx < count)
                 {
                     gid = queue[idx];

@@ -149,6 +149,9 @@ enum { FLX_TUNE_TRACE_VARIANT = 0,      /* 0: one ray per thread; 1 (default): p
        FLX_TUNE_FETCH_THRESHOLD = 1,    /* persistent variant: refill a warp when fewer lanes than this hold a ray (default 16) */
        FLX_TUNE_TRACE_BLOCKS_PER_SM = 2,/* variant 1: resident CTAs per SM, 0 = occupancy calculator */
        FLX_TUNE_TOP_NODES = 3,          /* variant 2: treelet nodes (64 B each) staged per CTA, default 2047 */
+       FLX_TUNE_LOGIC_MIN_BLOCKS = 5,   /* register budget of the logic kernel: compiled for 2, 3 (default) or 4 resident CTAs per SM */
+       FLX_TUNE_FETCH_CHUNK = 6,        /* persistent variants: queue entries a warp reserves per atomic (default 32) */
+       FLX_TUNE_OVERLAP_TRACE = 7,      /* flx_render: run the shadow-ray kernel on a second stream, overlapping the extension kernel's tail (default 1) */
        FLX_TUNE_INNER_MIN = 4           /* leave the inner-node phase when fewer lanes than this are still at inner nodes (default 8) */ };
 int flx_set_tuning(flx_ctx *ctx, int key, int value);
 
