@@ -315,7 +315,10 @@ def main_ours(args):
                 "shadow": {"algorithmic_bytes_per_ray": round(a_sh, 1), "per_ray": per_sh, "avg_launch_ms": round(sh_ms / max(sh_n, 1), 4),
                            "achieved": round(a_sh * sh_rays_per_launch / (sh_ms / max(sh_n, 1) * 1e-3) / 1e9, 1) if sh_ms else None,
                            "mrays_per_s": round(sh_rays_per_launch / (sh_ms / max(sh_n, 1)) / 1e3, 1) if sh_ms else None},
-                "kernel_share_of_step": kernel_share}
+                "kernel_share_of_step": kernel_share,
+                "note": "numerator = bytes the REFERENCE's layout moves per ray (SURVEY 8d: 48-B nodes, 160-B triangles), counted on this run's rays; the repacked "
+                        "BVH is L2-resident, so the kernel is issue/L1-bound and frac can exceed 1 (DESIGN.md 4.1). The shadow kernel runs on a second stream and "
+                        "overlaps the extension kernel's tail, so per-kernel elapsed times overlap and their shares sum to more than 1."}
 
     if rank != 0:
         ctx.close()

@@ -118,6 +118,7 @@ struct flx_ctx
     int traceVariant = 1;     // 0: one ray per thread, 1: persistent threads + dynamic fetch, 2: 1 + top-of-tree treelet in shared memory
     int topNodes = 2047;      // variant 2: treelet nodes staged per CTA (64 B each)
     int fetchThreshold = 16;  // refill when fewer lanes than this still hold a ray
+    int extMinBlocks = 9, shadowMinBlocks = 10; // variant 1: resident 128-thread CTAs per SM the kernels are compiled for
     int fetchChunk = 32;     // queue entries a warp reserves per atomic
     int logicMinBlocks = 3;   // resident 256-thread CTAs per SM the logic kernel is compiled for (register budget)
     int innerMin = 8;         // leave the inner-node phase when fewer lanes than this are still at inner nodes
@@ -474,29 +475,38 @@ __global__ void k_deinterleave(const float4 *gathered, float4 *full, uint32_t wi
 }
 } // namespace
 
+template <bool ANYHIT, class COUNT, int MINB> static int launchPersistentV1(flx_ctx *ctx, uint32_t *fetch, unsigned long long *counts)
+{
+    auto kern = k_trace_persistent<ANYHIT, COUNT, FLX_TRACE_BLOCK, false, MINB>;
+    int perSM = ctx->traceBlocksPerSM;
+    if (perSM <= 0)
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, FLX_TRACE_BLOCK, 0));
+    const unsigned grid = (unsigned)std::max(1, perSM) * (unsigned)ctx->numSMs;
+    kern<<<grid, FLX_TRACE_BLOCK, 0, ctx->cur>>>(makeFrame(ctx), ctx->params, makeBvh(ctx), ctx->tris, fetch, ctx->fetchThreshold, ctx->innerMin, ctx->fetchChunk, 0, counts);
+    return 0;
+}
+
 template <bool ANYHIT, class COUNT> static int launchPersistentT(flx_ctx *ctx, uint32_t *fetch, unsigned long long *counts)
 {
-    const Frame fr = makeFrame(ctx);
-    const BvhView bvh = makeBvh(ctx);
     if (ctx->traceVariant == 2)
     {
         constexpr int BLOCK = 1024; // one persistent CTA per SM owns the staged treelet
-        auto kern = k_trace_persistent<ANYHIT, COUNT, BLOCK, true>;
+        auto kern = k_trace_persistent<ANYHIT, COUNT, BLOCK, true, 1>;
         const int top = (int)std::min<uint32_t>({(uint32_t)ctx->topNodes, ctx->treeletNodes, ctx->nTNodes, (uint32_t)((ctx->maxDynSmem - 1024) / 64)});
         const size_t smem = (size_t)top * 64;
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<ctx->numSMs, BLOCK, smem, ctx->cur>>>(fr, ctx->params, bvh, ctx->tris, fetch, ctx->fetchThreshold, ctx->innerMin, ctx->fetchChunk, top, counts);
+        kern<<<ctx->numSMs, BLOCK, smem, ctx->cur>>>(makeFrame(ctx), ctx->params, makeBvh(ctx), ctx->tris, fetch, ctx->fetchThreshold, ctx->innerMin, ctx->fetchChunk, top, counts);
+        return 0;
     }
-    else
+    // register budget: the kernel is compiled for MINB resident 128-thread CTAs per SM
+    const int mb = ANYHIT ? ctx->shadowMinBlocks : ctx->extMinBlocks;
+    switch (mb)
     {
-        auto kern = k_trace_persistent<ANYHIT, COUNT, FLX_TRACE_BLOCK, false>;
-        int perSM = ctx->traceBlocksPerSM;
-        if (perSM <= 0)
-            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, FLX_TRACE_BLOCK, 0));
-        const unsigned grid = (unsigned)std::max(1, perSM) * (unsigned)ctx->numSMs;
-        kern<<<grid, FLX_TRACE_BLOCK, 0, ctx->cur>>>(fr, ctx->params, bvh, ctx->tris, fetch, ctx->fetchThreshold, ctx->innerMin, ctx->fetchChunk, 0, counts);
+    case 8: return launchPersistentV1<ANYHIT, COUNT, 8>(ctx, fetch, counts);
+    case 9: return launchPersistentV1<ANYHIT, COUNT, 9>(ctx, fetch, counts);
+    case 12: return launchPersistentV1<ANYHIT, COUNT, 12>(ctx, fetch, counts);
+    default: return launchPersistentV1<ANYHIT, COUNT, 10>(ctx, fetch, counts);
     }
-    return 0;
 }
 
 template <bool ANYHIT> static int launchPersistent(flx_ctx *ctx)
@@ -1102,6 +1112,11 @@ int flx_set_tuning(flx_ctx *ctx, int key, int value)
     case FLX_TUNE_INNER_MIN:
         REQUIRE(value >= 1 && value <= 32, "flx_set_tuning: inner-phase minimum must be in 1..32");
         ctx->innerMin = value;
+        return 0;
+    case FLX_TUNE_EXT_MIN_BLOCKS:
+    case FLX_TUNE_SHADOW_MIN_BLOCKS:
+        REQUIRE(value == 8 || value == 9 || value == 10 || value == 12, "flx_set_tuning: trace min blocks must be 8, 9, 10 or 12");
+        (key == FLX_TUNE_EXT_MIN_BLOCKS ? ctx->extMinBlocks : ctx->shadowMinBlocks) = value;
         return 0;
     case FLX_TUNE_OVERLAP_TRACE:
         ctx->overlapTrace = value != 0;

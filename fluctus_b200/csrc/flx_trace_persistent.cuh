@@ -68,8 +68,8 @@ FLX_DEV void stage_bulk(void *dstShared, const void *srcGlobal, uint32_t bytes, 
     }
 }
 
-template <bool ANYHIT, class COUNT, int BLOCK, bool TOP>
-__global__ void __launch_bounds__(BLOCK, TOP ? 1 : (ANYHIT ? 10 : 8)) k_trace_persistent(const __grid_constant__ Frame fr, const __grid_constant__ flx_RenderParams prm,
+template <bool ANYHIT, class COUNT, int BLOCK, bool TOP, int MIN_BLOCKS>
+__global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_trace_persistent(const __grid_constant__ Frame fr, const __grid_constant__ flx_RenderParams prm,
                                                                          const BvhView bvh, const flx_Triangle *tris160, uint32_t *fetchCounter,
                                                                          const int threshold, const int innerMin, const int fetchChunk, const int topCount, unsigned long long *countTotals)
 {

@@ -26,6 +26,8 @@ def main():
     ap.add_argument("--logic-blocks", default="3")
     ap.add_argument("--chunks", default="32")
     ap.add_argument("--overlaps", default="1")
+    ap.add_argument("--ext-blocks", default="8")
+    ap.add_argument("--shadow-blocks", default="10")
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
     from fluctus_b200 import CLContext, EnvMapData, SceneData, Tracer
@@ -48,8 +50,9 @@ def main():
             combos += [(v, th, 0, top, im) for th, top, im in itertools.product(map(int, a.thresholds.split(",")), map(int, a.tops.split(",")), map(int, a.inner_mins.split(",")))]
     combos = [c + (lb, ch) for c in combos for lb in map(int, a.logic_blocks.split(",")) for ch in map(int, a.chunks.split(","))]
     combos = [c + (ov,) for c in combos for ov in map(int, a.overlaps.split(","))]
-    for v, th, b, top, im, lb, ch, ov in combos:
-        ctx.setTuning(trace_variant=v, logic_min_blocks=lb, fetch_chunk=ch, overlap_trace=ov)
+    combos = [c + (eb, sb) for c in combos for eb in map(int, a.ext_blocks.split(",")) for sb in map(int, a.shadow_blocks.split(","))]
+    for v, th, b, top, im, lb, ch, ov, eb, sb in combos:
+        ctx.setTuning(trace_variant=v, logic_min_blocks=lb, fetch_chunk=ch, overlap_trace=ov, ext_min_blocks=eb, shadow_min_blocks=sb)
         if v:
             ctx.setTuning(fetch_threshold=th, trace_blocks_per_sm=b, top_nodes=top, inner_min=im)
         tr = Tracer(ctx, params)
@@ -62,7 +65,7 @@ def main():
         ctx.setProfiling(False)
         st = ctx.getStats()
         perf = ctx.checkTracingPerf()
-        row = dict(variant=v, threshold=th, blocks_per_sm=b, top_nodes=top, inner_min=im, logic_blocks=lb, fetch_chunk=ch, overlap=ov, ms_per_iter=ms / a.iters, mrays=(st.extensionRays + st.shadowRays) / ms / 1e3,
+        row = dict(variant=v, threshold=th, blocks_per_sm=b, top_nodes=top, inner_min=im, logic_blocks=lb, fetch_chunk=ch, overlap=ov, ext_blocks=eb, shadow_blocks=sb, ms_per_iter=ms / a.iters, mrays=(st.extensionRays + st.shadowRays) / ms / 1e3,
                    ext_ms=perf["extrays"][0] / a.iters, shadow_ms=perf["shadowrays"][0] / a.iters, logic_ms=perf["logic"][0] / a.iters,
                    mat_ms=perf["materials"][0] / a.iters, raygen_ms=perf["raygen"][0] / a.iters,
                    ext_mrays=st.extensionRays / perf["extrays"][0] / 1e3, shadow_mrays=st.shadowRays / perf["shadowrays"][0] / 1e3)
