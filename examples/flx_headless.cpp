@@ -135,6 +135,7 @@ int main(int argc, char **argv)
             clctx.enqueueWfExtRayKernel(params);
             clctx.enqueueWfShadowRayKernel(params);
             clctx.enqueueClearWfQueues();
+            clctx.enqueuePostprocessKernel(params);
             clctx.finishQueue();
             ext += cnt.extensionQueue;
             shadow += cnt.shadowQueue;

@@ -25,6 +25,8 @@ _SIGNATURES = {
     "flx_enqueue_shadowrays": (C.c_int, [_P]),
     "flx_enqueue_logic": (C.c_int, [_P, C.c_int]),
     "flx_enqueue_materials": (C.c_int, [_P]),
+    "flx_enqueue_postprocess": (C.c_int, [_P]),
+    "flx_read_preview": (C.c_int, [_P, _P, C.c_size_t]),
     "flx_enqueue_clear_queues": (C.c_int, [_P]),
     "flx_enqueue_get_counters": (C.c_int, [_P, C.POINTER(QueueCounters)]),
     "flx_finish": (C.c_int, [_P]),

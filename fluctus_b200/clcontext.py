@@ -17,7 +17,7 @@ class FluctusError(RuntimeError):
     pass
 
 
-KERNEL_IDS = {"reset": 0, "raygen": 1, "extrays": 2, "shadowrays": 3, "logic": 4, "materials": 5, "end_iteration": 6}
+KERNEL_IDS = {"reset": 0, "raygen": 1, "extrays": 2, "shadowrays": 3, "logic": 4, "materials": 5, "end_iteration": 6, "postprocess": 7}
 
 
 class CLContext:
@@ -101,6 +101,16 @@ class CLContext:
     def enqueueWfMaterialKernels(self, params=None):
         self._check(self._lib.flx_enqueue_materials(self._h), "enqueueWfMaterialKernels")
 
+    def enqueuePostprocessKernel(self, params=None):
+        """reference: clcontext.hpp:41 -- normalise / exposure / tone map / gamma into the preview buffer."""
+        self._check(self._lib.flx_enqueue_postprocess(self._h), "enqueuePostprocessKernel")
+
+    def readPreview(self):
+        n = self.tilePixels()
+        out = np.empty((n, 4), np.float32)
+        self._check(self._lib.flx_read_preview(self._h, self._ptr(out), n), "readPreview")
+        return out
+
     # ---- queue bookkeeping (clcontext.hpp:53-57, 71)
     def enqueueClearWfQueues(self):
         self._check(self._lib.flx_enqueue_clear_queues(self._h), "enqueueClearWfQueues")
@@ -141,7 +151,7 @@ class CLContext:
         self._check(self._lib.flx_timer_end(self._h, C.byref(ms)), "timerEnd")
         return ms.value
 
-    TUNING = {"trace_variant": 0, "fetch_threshold": 1, "trace_blocks_per_sm": 2, "top_nodes": 3, "inner_min": 4, "logic_min_blocks": 5, "fetch_chunk": 6, "overlap_trace": 7, "ext_min_blocks": 8, "shadow_min_blocks": 9}
+    TUNING = {"trace_variant": 0, "fetch_threshold": 1, "trace_blocks_per_sm": 2, "top_nodes": 3, "inner_min": 4, "logic_min_blocks": 5, "fetch_chunk": 6, "overlap_trace": 7, "postprocess_in_loop": 10, "ext_min_blocks": 8, "shadow_min_blocks": 9}
 
     def setTuning(self, **kv):
         for k, v in kv.items():

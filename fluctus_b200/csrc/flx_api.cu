@@ -62,6 +62,7 @@ struct flx_ctx
     cudaStream_t cur = nullptr;       // stream the next traversal launch goes to (== stream except inside flx_render)
     cudaEvent_t evFork = nullptr, evJoin = nullptr;
     int overlapTrace = 1;
+    int postprocessInLoop = 1;        // flx_render runs the display pass every iteration, like the reference's loop (tracer.cpp:447)
     uint32_t numTasks = 0;
     std::string error;
 
@@ -100,7 +101,7 @@ struct flx_ctx
     int envW = 1, envH = 1;
 
     // image
-    float *pixels = nullptr, *denoiserAlbedo = nullptr, *denoiserNormal = nullptr;
+    float *pixels = nullptr, *denoiserAlbedo = nullptr, *denoiserNormal = nullptr, *preview = nullptr;
     uint32_t width = 0, height = 0, tilePixels = 0;
     uint32_t part = 0, nParts = 1, stripeRows = 1;
     float *gatherBuf = nullptr, *fullImage = nullptr; // rank-major gather target and de-interleaved full image (root)
@@ -656,6 +657,7 @@ void flx_destroy(flx_ctx *c)
     freeDev(c->pixels);
     freeDev(c->denoiserAlbedo);
     freeDev(c->denoiserNormal);
+    freeDev(c->preview);
     freeDev(c->gatherBuf);
     freeDev(c->fullImage);
     if (c->evFork)
@@ -780,12 +782,15 @@ static int allocImage(flx_ctx *ctx)
     freeDev(ctx->pixels);
     freeDev(ctx->denoiserAlbedo);
     freeDev(ctx->denoiserNormal);
+    freeDev(ctx->preview);
     if (ctx->tilePixels == 0)
         return fail(ctx, FLX_E_INVALID, "tile %u of %u owns no rows of a %ux%u image", ctx->part, ctx->nParts, ctx->width, ctx->height);
     const size_t bytes = (size_t)ctx->tilePixels * 4 * sizeof(float);
     CU(cudaMalloc(&ctx->pixels, bytes));
     CU(cudaMalloc(&ctx->denoiserAlbedo, bytes));
     CU(cudaMalloc(&ctx->denoiserNormal, bytes));
+    CU(cudaMalloc(&ctx->preview, bytes));
+    CU(cudaMemset(ctx->preview, 0, bytes));
     CU(cudaMemset(ctx->pixels, 0, bytes));
     CU(cudaMemset(ctx->denoiserAlbedo, 0, bytes));
     CU(cudaMemset(ctx->denoiserNormal, 0, bytes));
@@ -939,6 +944,30 @@ int flx_enqueue_materials(flx_ctx *ctx)
     return launchCheck(ctx, "k_material");
 }
 
+int flx_enqueue_postprocess(flx_ctx *ctx)
+{
+    int rc = checkReady(ctx, false, true);
+    if (rc)
+        return rc;
+    CU(cudaSetDevice(ctx->device));
+    Timed tm(ctx, FLX_K_POSTPROCESS);
+    k_postprocess<<<streamingGrid(ctx->tilePixels), FLX_BLOCK, 0, ctx->stream>>>(reinterpret_cast<const float4 *>(ctx->pixels), reinterpret_cast<float4 *>(ctx->preview),
+                                                                               ctx->tilePixels, ctx->params.ppParams.exposure, ctx->params.ppParams.tmOperator);
+    return launchCheck(ctx, "k_postprocess");
+}
+
+int flx_read_preview(flx_ctx *ctx, float *rgba, size_t n_pixels)
+{
+    if (!ctx)
+        return FLX_E_INVALID;
+    REQUIRE(rgba != nullptr, "flx_read_preview: null destination");
+    REQUIRE(ctx->preview && n_pixels <= ctx->tilePixels, "flx_read_preview: more pixels requested than the context owns");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(rgba, ctx->preview, n_pixels * 4 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
 int flx_enqueue_clear_queues(flx_ctx *ctx)
 {
     if (!ctx)
@@ -1050,6 +1079,8 @@ int flx_render(flx_ctx *ctx, uint32_t n_iterations)
         }
         if ((rc = launchCheck(ctx, "k_end_iteration")))
             return rc;
+        if (ctx->postprocessInLoop && (rc = flx_enqueue_postprocess(ctx))) // tracer.cpp:447
+            return rc;
     }
     return 0;
 }
@@ -1117,6 +1148,9 @@ int flx_set_tuning(flx_ctx *ctx, int key, int value)
     case FLX_TUNE_SHADOW_MIN_BLOCKS:
         REQUIRE(value == 8 || value == 9 || value == 10 || value == 12, "flx_set_tuning: trace min blocks must be 8, 9, 10 or 12");
         (key == FLX_TUNE_EXT_MIN_BLOCKS ? ctx->extMinBlocks : ctx->shadowMinBlocks) = value;
+        return 0;
+    case FLX_TUNE_POSTPROCESS_IN_LOOP:
+        ctx->postprocessInLoop = value != 0;
         return 0;
     case FLX_TUNE_OVERLAP_TRACE:
         ctx->overlapTrace = value != 0;

@@ -673,6 +673,46 @@ __global__ void __launch_bounds__(FLX_BLOCK) k_material(const __grid_constant__ 
     }
 }
 
+// ------------------------------------------------------------------------------------------------ post-process
+// The display pass the reference runs at the end of every loop iteration (src/mk_postprocess.cl:7-55 with
+// src/tonemap.cl:3-26; enqueued at src/tracer.cpp:302 and :447): normalise by the sample count, exposure, Reinhard or
+// Uncharted-2 tone map, gamma 1/2.2.  Pure streaming: 16 B in, 16 B out per pixel.
+FLX_DEV float uc2_curve(float x)
+{
+    const float A = 0.22, B = 0.30, C = 0.10, D = 0.20, E = 0.01, F = 0.30; // double literals rounded to float, as in the reference
+    return (x * (A * x + C * B) + D * E) / (x * (A * x + B) + D * F) - E / F;
+}
+__global__ void __launch_bounds__(FLX_BLOCK) k_postprocess(const float4 *__restrict__ pixels, float4 *__restrict__ preview, uint32_t nPixels, float exposure,
+                                                           uint32_t tmOperator)
+{
+    const float W = 11.2, exposureBias = 2.0;
+    const float white = uc2_curve(W);
+    for (uint32_t i = blockIdx.x * FLX_BLOCK + threadIdx.x; i < nPixels; i += gridDim.x * FLX_BLOCK)
+    {
+        float4 c = pixels[i];
+        if (c.w > 0.0f)
+        {
+            const float w = c.w;
+            c = make_float4(c.x / w, c.y / w, c.z / w, c.w / w);
+        }
+        float r = c.x * exposure, g = c.y * exposure, b = c.z * exposure;
+        if (tmOperator == 1u)
+        {
+            r = r / (1.0f + r);
+            g = g / (1.0f + g);
+            b = b / (1.0f + b);
+        }
+        if (tmOperator == 2u)
+        {
+            r = uc2_curve(exposureBias * r) / white;
+            g = uc2_curve(exposureBias * g) / white;
+            b = uc2_curve(exposureBias * b) / white;
+        }
+        const float ig = 1.0f / 2.2f;
+        preview[i] = make_float4(flx_powf(r, ig), flx_powf(g, ig), flx_powf(b, ig), c.w);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ between iterations
 struct IterationState
 {

@@ -2,7 +2,7 @@
 
 Replays, call for call, the order in which the reference drives CLContext:
   * start()     = the `iteration == 0` prologue of Tracer::update       (reference: src/tracer.cpp:236-240)
-  * iterate()   = one steady-state iteration of Tracer::runBenchmark    (reference: src/tracer.cpp:433-439, 447, 455-465)
+  * iterate()   = one steady-state iteration of Tracer::runBenchmark    (reference: src/tracer.cpp:433-439, 447 [post-process], 455-465)
   * render(n)   = n such iterations without host round trips (flx_render)
 It works with any object that has CLContext's method set -- the CUDA context (fluctus_b200.CLContext) and the oracle
 contexts in oracle/ alike -- which is how the parity tests run the same loop on both.
@@ -38,6 +38,7 @@ class Tracer:
         c.enqueueWfExtRayKernel(p)
         c.enqueueWfShadowRayKernel(p)
         c.enqueueClearWfQueues()
+        c.enqueuePostprocessKernel(p)  # src/tracer.cpp:302, 447: the display pass is part of every loop iteration
         c.finishQueue()
         self.stats["extensionRays"] += cnt.extensionQueue
         self.stats["shadowRays"] += cnt.shadowQueue

@@ -87,7 +87,7 @@ enum {
 enum { FLX_OK = 0, FLX_E_INVALID = 10001, FLX_E_NO_DEVICE = 10002, FLX_E_NOT_READY = 10003, FLX_E_NCCL = 10004, FLX_E_UNSUPPORTED_ARCH = 10005 };
 
 /* kernel ids for flx_get_kernel_ms (reference instrument: CLContext::checkTracingPerf, clcontext.cpp:673-701) */
-enum { FLX_K_RESET = 0, FLX_K_RAYGEN, FLX_K_EXTRAYS, FLX_K_SHADOWRAYS, FLX_K_LOGIC, FLX_K_MATERIALS, FLX_K_END_ITERATION, FLX_K_COUNT };
+enum { FLX_K_RESET = 0, FLX_K_RAYGEN, FLX_K_EXTRAYS, FLX_K_SHADOWRAYS, FLX_K_LOGIC, FLX_K_MATERIALS, FLX_K_END_ITERATION, FLX_K_POSTPROCESS, FLX_K_COUNT };
 
 typedef struct flx_ctx flx_ctx;
 
@@ -122,6 +122,12 @@ int flx_enqueue_shadowrays(flx_ctx *ctx);
 int flx_enqueue_logic(flx_ctx *ctx, int first_iteration);
 int flx_enqueue_materials(flx_ctx *ctx); /* 5 per-type kernels or the single-queue kernel, by params.wfSeparateQueues */
 
+/* CLContext::enqueuePostprocessKernel (clcontext.hpp:41; clcontext.cpp:752-763; kernel src/mk_postprocess.cl:7-55): the display
+ * pass of every loop iteration -- divide by the sample count, exposure, tone map (params.ppParams), gamma -- into a float4
+ * preview buffer (a GL PBO in the reference; here read back with flx_read_preview). */
+int flx_enqueue_postprocess(flx_ctx *ctx);
+int flx_read_preview(flx_ctx *ctx, float *rgba, size_t n_pixels);
+
 /* CLContext::enqueueClearWfQueues / enqueueGetCounters / finishQueue / updatePixelIndex / resetPixelIndex /
  * getNumTasks (clcontext.hpp:53-57,71; clcontext.cpp:668-671, 877-906). */
 int flx_enqueue_clear_queues(flx_ctx *ctx);
@@ -153,6 +159,7 @@ enum { FLX_TUNE_TRACE_VARIANT = 0,      /* 0: one ray per thread; 1 (default): p
        FLX_TUNE_FETCH_CHUNK = 6,        /* persistent variants: queue entries a warp reserves per atomic (default 32) */
        FLX_TUNE_EXT_MIN_BLOCKS = 8,     /* variant 1 register budget: extension kernel compiled for 8, 9 (default), 10 or 12 CTAs of 128 per SM */
        FLX_TUNE_SHADOW_MIN_BLOCKS = 9,  /* same for the shadow kernel (default 10) */
+       FLX_TUNE_POSTPROCESS_IN_LOOP = 10, /* flx_render: run the display pass every iteration like the reference's loop (default 1) */
        FLX_TUNE_OVERLAP_TRACE = 7,      /* flx_render: run the shadow-ray kernel on a second stream, overlapping the extension kernel's tail (default 1) */
        FLX_TUNE_INNER_MIN = 4           /* leave the inner-node phase when fewer lanes than this are still at inner nodes (default 8) */ };
 int flx_set_tuning(flx_ctx *ctx, int key, int value);

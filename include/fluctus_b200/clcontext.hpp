@@ -89,6 +89,14 @@ class CLContext
     void enqueueWfLogicKernel(const RenderParams &, const bool firstIteration) { verify(flx_enqueue_logic(ctx, firstIteration ? 1 : 0), "enqueueWfLogicKernel"); }
     void enqueueWfMaterialKernels(const RenderParams &) { verify(flx_enqueue_materials(ctx), "enqueueWfMaterialKernels"); }
 
+    void enqueuePostprocessKernel(const RenderParams &) { verify(flx_enqueue_postprocess(ctx), "enqueuePostprocessKernel"); } // clcontext.hpp:41
+    std::vector<float> readPreview()
+    {
+        std::vector<float> rgba((size_t)flx_tile_pixels(ctx) * 4);
+        verify(flx_read_preview(ctx, rgba.data(), rgba.size() / 4), "readPreview");
+        return rgba;
+    }
+
     // ---- queue bookkeeping (clcontext.hpp:53-57, 71)
     void enqueueClearWfQueues() { verify(flx_enqueue_clear_queues(ctx), "enqueueClearWfQueues"); }
     void enqueueGetCounters(QueueCounters *cnt) { verify(flx_enqueue_get_counters(ctx, cnt), "enqueueGetCounters"); }

@@ -45,6 +45,7 @@ KERNEL_TUS = {
     "mat_ggx_refl": ("REF_TU_MAT_GGX_REFL", []),
     "mat_ggx_refr": ("REF_TU_MAT_GGX_REFR", []),
     "mat_delta": ("REF_TU_MAT_DELTA", []),
+    "postprocess": ("REF_TU_POSTPROCESS", []),  # src/mk_postprocess.cl + src/tonemap.cl (the display pass of the render loop, tracer.cpp:302,447)
 }
 
 VEC_LITERAL = re.compile(r"\((v?float[234]|int2)\)\(")

@@ -28,7 +28,7 @@ class RefBufs(C.Structure):  # oracle/ref_shim/ref_abi.h
                 ("deltaQueue", C.c_void_p), ("tris", C.c_void_p), ("nodes", C.c_void_p), ("indices", C.c_void_p), ("envRGBA", C.c_void_p),
                 ("envW", C.c_int32), ("envH", C.c_int32), ("probTable", C.c_void_p), ("aliasTable", C.c_void_p), ("pdfTable", C.c_void_p),
                 ("materials", C.c_void_p), ("texData", C.c_void_p), ("textures", C.c_void_p), ("params", C.c_void_p),
-                ("currPixelIdx", C.c_void_p), ("numTasks", C.c_uint32), ("firstIteration", C.c_uint32)]
+                ("currPixelIdx", C.c_void_p), ("numTasks", C.c_uint32), ("firstIteration", C.c_uint32), ("pixelsPreview", C.c_void_p)]
 
 
 QUEUE_FIELDS = ("raygenQueue", "extensionQueue", "shadowQueue", "diffuseQueue", "glossyQueue", "ggxReflQueue", "ggxRefrQueue", "deltaQueue")
@@ -91,6 +91,7 @@ class _CpuContext:
         self.pixels = np.zeros((self.width * self.height, 4), np.float32)
         self.albedo = np.zeros_like(self.pixels)
         self.normal = np.zeros_like(self.pixels)
+        self.preview = np.zeros_like(self.pixels)
 
     def updateParams(self, params):
         C.memmove(self.params_buf.ctypes.data, C.byref(params), 240)
@@ -113,6 +114,7 @@ class _CpuContext:
         b.probTable, b.aliasTable, b.pdfTable = p(self.prob), p(self.alias), p(self.pdf)
         b.params, b.currPixelIdx = p(self.params_buf), p(self.currPixelIdx)
         b.numTasks, b.firstIteration = self.NUM_TASKS, first
+        b.pixelsPreview = p(self.preview)
         return b
 
     def _run(self, name, n, first=0):
@@ -145,6 +147,12 @@ class _CpuContext:
                 self._run(k, self.NUM_TASKS)
         else:
             self._run("mat_all", self.NUM_TASKS)
+
+    def enqueuePostprocessKernel(self, params=None):
+        self._run("postprocess", self.width * self.height)  # NDRange(width*height), src/clcontext.cpp:758
+
+    def readPreview(self):
+        return self.preview.copy()
 
     # ---- bookkeeping
     def enqueueClearWfQueues(self):

@@ -52,6 +52,7 @@ struct xyz_proxy
     float x, y, z;
     inline operator float3() const;
     inline xyz_proxy &operator=(const float3 &v);
+    xyz_proxy &operator*=(float s) { x *= s; y *= s; z *= s; return *this; }
 };
 
 struct alignas(16) float3
@@ -121,6 +122,7 @@ inline float3 operator-(float s, const float3 &a) { return float3(s - a.x, s - a
 inline float3 operator-(const float3 &a) { return float3(-a.x, -a.y, -a.z); }
 inline float4 operator+(const float4 &a, const float4 &b) { return float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 inline float4 operator*(const float4 &a, float s) { return float4(a.x * s, a.y * s, a.z * s, a.w * s); }
+inline float4 operator/(const float4 &a, float s) { return float4(a.x / s, a.y / s, a.z / s, a.w / s); }
 inline float2 operator*(const float2 &a, float s) { return float2(a.x * s, a.y * s); }
 inline float2 operator*(float s, const float2 &a) { return float2(s * a.x, s * a.y); }
 inline float2 operator+(const float2 &a, const float2 &b) { return float2(a.x + b.x, a.y + b.y); }

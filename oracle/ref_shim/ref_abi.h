@@ -28,5 +28,6 @@ typedef struct
     uint32_t *currPixelIdx;
     uint32_t numTasks;
     uint32_t firstIteration;
+    float *pixelsPreview;   /* W*H float4, output of the post-process kernel (GL PBO in the reference) */
 } RefBufs;
 #endif

@@ -33,6 +33,8 @@ namespace
 #include "wf_mat_ggx_refraction.cl"
 #elif defined(REF_TU_MAT_DELTA)
 #include "wf_mat_delta.cl"
+#elif defined(REF_TU_POSTPROCESS)
+#include "mk_postprocess.cl"
 #else
 #error "no REF_TU_* selected"
 #endif
@@ -108,6 +110,11 @@ extern "C"
     void REF_NAME(mat_ggx_refl)(const RefBufs *b, size_t begin, size_t end) { REF_LOOP { g_shim_gid = (size_t)g; wavefrontGGXReflection(MATARGS(b, ggxReflQueue)); } }
 #elif defined(REF_TU_MAT_GGX_REFR)
     void REF_NAME(mat_ggx_refr)(const RefBufs *b, size_t begin, size_t end) { REF_LOOP { g_shim_gid = (size_t)g; wavefrontGGXRefraction(MATARGS(b, ggxRefrQueue)); } }
+#elif defined(REF_TU_POSTPROCESS)
+    void REF_NAME(postprocess)(const RefBufs *b, size_t begin, size_t end)
+    {
+        REF_LOOP { g_shim_gid = (size_t)g; process(b->pixels, b->denoiserAlbedo, b->denoiserNormal, b->pixelsPreview, b->denoiserAlbedo, b->denoiserNormal, P(b), b->numTasks); }
+    }
 #elif defined(REF_TU_MAT_DELTA)
     void REF_NAME(mat_delta)(const RefBufs *b, size_t begin, size_t end) { REF_LOOP { g_shim_gid = (size_t)g; wavefrontDelta(MATARGS(b, deltaQueue)); } }
 #endif

@@ -906,6 +906,37 @@ void NAME(mat_ggx_refl)(const RefBufs *b, size_t begin, size_t end) { material_k
 void NAME(mat_ggx_refr)(const RefBufs *b, size_t begin, size_t end) { material_kernel(b, begin, end, b->ggxRefrQueue, &QL(b)->ggxRefr, BXDF_GGX_REFR); }
 void NAME(mat_delta)(const RefBufs *b, size_t begin, size_t end) { material_kernel(b, begin, end, b->deltaQueue, &QL(b)->delta, BXDF_IDEAL_REFL | BXDF_IDEAL_DIEL); }
 
+/* ================================================================ post-process (mk_postprocess.cl:7-55, tonemap.cl:3-26) */
+static v3 uc2_tonemap_func(v3 x)
+{
+    const float A = 0.22, B = 0.30, C = 0.10, D = 0.20, E = 0.01, Fq = 0.30; /* double literals rounded to float, as in the reference */
+    const v3 num = V(x.x * (A * x.x + C * B) + D * E, x.y * (A * x.y + C * B) + D * E, x.z * (A * x.z + C * B) + D * E);
+    const v3 den = V(x.x * (A * x.x + B) + D * Fq, x.y * (A * x.y + B) + D * Fq, x.z * (A * x.z + B) + D * Fq);
+    return V(num.x / den.x - E / Fq, num.y / den.y - E / Fq, num.z / den.z - E / Fq);
+}
+void NAME(postprocess)(const RefBufs *b, size_t begin, size_t end)
+{
+    const RenderParams *p = (const RenderParams *)b->params;
+    const uint32_t limit = p->width * p->height;
+    LOOP
+    {
+        const size_t gid = (size_t)g_;
+        if (gid >= limit) continue;
+        float c[4] = {b->pixels[4 * gid], b->pixels[4 * gid + 1], b->pixels[4 * gid + 2], b->pixels[4 * gid + 3]};
+        if (c[3] > 0.0) { const float w = c[3]; c[0] /= w; c[1] /= w; c[2] /= w; c[3] /= w; }
+        v3 col = V(c[0] * p->exposure, c[1] * p->exposure, c[2] * p->exposure);
+        if (p->tmOperator == 1) col = V(col.x / (1.0f + col.x), col.y / (1.0f + col.y), col.z / (1.0f + col.z));
+        if (p->tmOperator == 2)
+        {
+            const float W = 11.2, exposureBias = 2.0;
+            const v3 a = uc2_tonemap_func(lscl(exposureBias, col)), w = uc2_tonemap_func(V(W, W, W));
+            col = V(a.x / w.x, a.y / w.y, a.z / w.z);
+        }
+        col = V(flx_powf(col.x, 1.0f / 2.2f), flx_powf(col.y, 1.0f / 2.2f), flx_powf(col.z, 1.0f / 2.2f));
+        b->pixelsPreview[4 * gid] = col.x; b->pixelsPreview[4 * gid + 1] = col.y; b->pixelsPreview[4 * gid + 2] = col.z; b->pixelsPreview[4 * gid + 3] = c[3];
+    }
+}
+
 #ifndef PORT_PARALLEL
 /* vector entry points for tests/test_math.py */
 void port_math(int fn, const float *a, const float *bb, float *out, int n)

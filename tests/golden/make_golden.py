@@ -3,7 +3,7 @@
 for the host (oracle/_ref/libfluctus_ref.so, built by oracle/build_ref.py from /root/reference/src/wf_*.cl), serially.
 
 Each fixture holds the complete path state (64 x N uint32 slots) after the prologue and after K iterations, the
-radiance accumulator and the ray counts.  Inputs are regenerated deterministically by build_case(); only the
+radiance accumulator, the post-processed preview (mk_postprocess.cl) and the ray counts.  Inputs are regenerated deterministically by build_case(); only the
 reference-derived teapot scene (reference asset assets/teapot.ply through the reference's PLY import and SBVH builder)
 is stored inside its fixture, because neither exists on the GPU box or in a fresh clone.
 
@@ -74,7 +74,7 @@ def main():
         out = dict(tasks_start=ctx.readTasks())
         for _ in range(iters):
             tr.iterate()
-        out.update(tasks_end=ctx.readTasks(), pixels=ctx.readPixels(), stats=np.array([tr.stats[k] for k in ("primaryRays", "extensionRays", "shadowRays")], np.int64))
+        out.update(tasks_end=ctx.readTasks(), pixels=ctx.readPixels(), preview=ctx.readPreview(), stats=np.array([tr.stats[k] for k in ("primaryRays", "extensionRays", "shadowRays")], np.int64))
         if name == "teapot_c1":
             out.update(scene_tris=scene.tris.view(np.uint8), scene_indices=scene.indices, scene_nodes=scene.nodes.view(np.uint8), scene_materials=scene.materials.view(np.uint8))
         np.savez_compressed(fix, **out)

@@ -92,5 +92,10 @@ def run_lockstep(gpu, cpu, scene, params, iterations, env=None, check_every=1, e
         if it % check_every == 0 or it == iterations - 1:
             compare_queues(gpu, cpu, cc, what)
             compare_tasks(gpu.readTasks(), cpu.readTasks(), what)
-            compare_pixels(gpu.readPixels(), cpu.readPixels(), what, rtol=1e-5, exact_rgb=exact_rgb)
+            pg, pc = gpu.readPixels(), cpu.readPixels()
+            compare_pixels(pg, pc, what, rtol=1e-5, exact_rgb=exact_rgb)
+            if hasattr(gpu, "readPreview") and hasattr(cpu, "readPreview"):  # display pass (mk_postprocess.cl), run by iterate()
+                vg, vc = gpu.readPreview(), cpu.readPreview()
+                same_in = np.array_equal(pg.view(np.uint32), pc.view(np.uint32))
+                compare_pixels(vg, vc, what + " (post-processed preview)", rtol=1e-5, exact_rgb=same_in)
     return tg, tc

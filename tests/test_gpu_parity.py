@@ -154,6 +154,7 @@ def test_gpu_matches_golden(name):
             tr.iterate()
         compare_tasks(gpu.readTasks(), z["tasks_end"], "%s after %d iterations" % (name, iters))
         compare_pixels(gpu.readPixels(), z["pixels"], name, rtol=1e-5)
+        compare_pixels(gpu.readPreview(), z["preview"], name + " preview", rtol=1e-5)
         assert [tr.stats[k] for k in ("primaryRays", "extensionRays", "shadowRays")] == list(z["stats"])
 
 

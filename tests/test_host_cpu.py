@@ -166,4 +166,4 @@ def test_tracer_replays_reference_call_order():
     calls.clear()
     t.iterate()
     assert calls == ["enqueueWfLogicKernel", "enqueueWfRaygenKernel", "enqueueWfMaterialKernels", "enqueueGetCounters", "enqueueWfExtRayKernel",
-                     "enqueueWfShadowRayKernel", "enqueueClearWfQueues", "finishQueue", "updatePixelIndex"]
+                     "enqueueWfShadowRayKernel", "enqueueClearWfQueues", "enqueuePostprocessKernel", "finishQueue", "updatePixelIndex"]

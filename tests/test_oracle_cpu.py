@@ -116,4 +116,5 @@ def test_port_matches_golden(name):
         tr.iterate()
     compare_tasks(ctx.readTasks(), z["tasks_end"], "%s after %d iterations" % (name, iters))
     compare_pixels(ctx.readPixels(), z["pixels"], name, exact_rgb=True)
+    compare_pixels(ctx.readPreview(), z["preview"], name + " preview", exact_rgb=True)
     assert [tr.stats[k] for k in ("primaryRays", "extensionRays", "shadowRays")] == list(z["stats"])
