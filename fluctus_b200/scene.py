@@ -128,7 +128,15 @@ class EnvMapData:
         h, w = rgb.shape[:2]
         n = w * h
         f32 = np.float32
-        sin_th = np.array([math.sin(float(f32(np.pi)) * float(f32(v + 0.5)) / float(f32(h))) for v in range(h)]).astype(np.float32)
+        # float sinTh = std::sin(PI * float(v + 0.5f) / float(height)): float32 argument, sinf
+        arg = (f32(np.pi) * (np.arange(h, dtype=np.float32) + f32(0.5))).astype(np.float32) / f32(h)
+        try:  # the C library's sinf, which is what std::sin(float) calls in the reference (not always correctly rounded)
+            import ctypes
+            libm = ctypes.CDLL("libm.so.6")
+            libm.sinf.restype, libm.sinf.argtypes = ctypes.c_float, [ctypes.c_float]
+            sin_th = np.array([libm.sinf(float(a)) for a in arg], np.float32)
+        except OSError:
+            sin_th = np.sin(arg.astype(np.float64)).astype(np.float32)
         lum = (f32(0.212671) * rgb[..., 0] + f32(0.715160) * rgb[..., 1]).astype(np.float32) + f32(0.072169) * rgb[..., 2]
         scal = (lum.astype(np.float32) * sin_th[:, None]).astype(np.float32).reshape(-1)
         I = f32(0.0)

@@ -167,3 +167,15 @@ def test_tracer_replays_reference_call_order():
     t.iterate()
     assert calls == ["enqueueWfLogicKernel", "enqueueWfRaygenKernel", "enqueueWfMaterialKernels", "enqueueGetCounters", "enqueueWfExtRayKernel",
                      "enqueueWfShadowRayKernel", "enqueueClearWfQueues", "enqueuePostprocessKernel", "finishQueue", "updatePixelIndex"]
+
+
+def test_env_tables_reproduce_reference_builder_bit_for_bit():
+    """EnvMapData.from_rgb (mirror of EnvironmentMap::computeProbabilities, src/envmap.cpp:31-114) against the tables the
+    reference's own envmap.cpp produced for assets/env_maps/night.hdr (oracle/_ref/scenes/night.env.bin)."""
+    from conftest import SCENES_DIR
+    p = os.path.join(SCENES_DIR, "night.env.bin")
+    if not os.path.exists(p):
+        pytest.skip("env map blob not built (needs /root/reference)")
+    ref = fx.EnvMapData.load_blob(p)
+    mine = fx.EnvMapData.from_rgb(ref.rgb)
+    assert np.array_equal(mine.pdf, ref.pdf) and np.array_equal(mine.prob, ref.prob) and np.array_equal(mine.alias, ref.alias)
