@@ -175,7 +175,7 @@ def run_cpu(args, scene, params, steps, warmup, seconds=None):
     rays = tr.stats["extensionRays"] + tr.stats["shadowRays"] - r0
     cores = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
     return dict(value=rays / dt / 1e6, unit=UNIT, cores=cores, kind=kind, steps=done, seconds=dt,
-                sample="%s %dx%d, %d bounces, %d paths in flight, %d wavefront iterations after %d warm-up; %s kernels, g++ -O3 -march=native, OpenMP %d threads"
+                sample="%s %dx%d, %d bounces, %d paths in flight, %d wavefront iterations after %d warm-up; %s kernels, g++ -O3 -march=x86-64-v3, OpenMP %d threads"
                        % (args.scene, params.width, params.height, params.maxBounces, args.cpu_tasks, done, warmup,
                           "reference OpenCL (host-compiled)" if kind == "reference" else "C restatement", cores))
 

@@ -20,7 +20,7 @@ def build(force=False):
         common = ["gcc", "-std=gnu11", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-Wall", "-Wno-unused-function", "-Wno-unused-variable",
                   "-I", INC, "-I", HERE, "-c", SRC]
         objs = [os.path.join(tmp, "serial.o"), os.path.join(tmp, "par.o")]
-        cmds = [common + ["-O2", "-o", objs[0]], common + ["-O3", "-march=native", "-fopenmp", "-DPORT_PARALLEL", "-o", objs[1]]]
+        cmds = [common + ["-O2", "-o", objs[0]], common + ["-O3", "-march=x86-64-v3", "-fopenmp", "-DPORT_PARALLEL", "-o", objs[1]]]
         for c in cmds + [["gcc", "-shared", "-fopenmp", "-o", OUT] + objs + ["-lm"]]:
             r = subprocess.run(c, capture_output=True, text=True)
             if r.returncode != 0:

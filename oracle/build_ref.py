@@ -109,7 +109,7 @@ def build(force=False):
                 cmd = common + ["-D" + tu] + ["-D" + d for d in defs]
                 if par:
                     # the reference builds with -DFLT_FLOAT_ATOMICS (clcontext.cpp:145); needed once work-items run concurrently
-                    cmd += ["-DSHIM_PARALLEL", "-DFLT_FLOAT_ATOMICS", "-fopenmp", "-O3", "-march=native"]
+                    cmd += ["-DSHIM_PARALLEL", "-DFLT_FLOAT_ATOMICS", "-fopenmp", "-O3", "-march=x86-64-v3"]
                 cmd += ["-c", os.path.join(SHIM, "ref_kernels.cpp"), "-o", obj]
                 jobs.append(cmd)
                 objs.append(obj)
