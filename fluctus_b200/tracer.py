@@ -48,6 +48,47 @@ class Tracer:
         self.iteration += 1
         return cnt
 
+    def update(self):
+        """One call of the interactive loop, Tracer::update() wavefront branch (src/tracer.cpp:222-266, 301-308, 333-340):
+        on `iteration == 0` the accumulation restarts with a preview -- maxBounces clamped to 2, the prologue, then THREE
+        logic/raygen/material/trace rounds with `firstIteration` set, and only the LAST round's counters advance the
+        pixel index -- otherwise one normal round."""
+        c, p = self.clctx, self.params
+        cnt = QueueCounters()
+        n_rounds = 1
+        max_bounces = p.maxBounces
+        first = self.iteration == 0
+        if first:
+            p.maxBounces = min(2, max_bounces)
+            c.updateParams(p)
+            n_rounds = 3
+            c.resetPixelIndex()
+            c.enqueueWfResetKernel(p)
+            c.enqueueWfRaygenKernel(p)
+            c.enqueueWfExtRayKernel(p)
+            c.enqueueClearWfQueues()
+        for _ in range(n_rounds):
+            cnt = QueueCounters()
+            c.enqueueWfLogicKernel(p, first)
+            c.enqueueWfRaygenKernel(p)
+            c.enqueueWfMaterialKernels(p)
+            c.enqueueGetCounters(cnt)
+            c.enqueueWfExtRayKernel(p)
+            c.enqueueWfShadowRayKernel(p)
+            c.enqueueClearWfQueues()
+        if first:
+            p.maxBounces = max_bounces
+            c.updateParams(p)
+        c.enqueuePostprocessKernel(p)
+        c.finishQueue()
+        c.updatePixelIndex(self._num_pixels(), cnt.raygenQueue)
+        self.stats["extensionRays"] += cnt.extensionQueue
+        self.stats["shadowRays"] += cnt.shadowQueue
+        self.stats["primaryRays"] += cnt.raygenQueue
+        self.stats["samples"] += cnt.raygenQueue if self.iteration > 0 else 0
+        self.iteration += 1
+        return cnt
+
     def _num_pixels(self):
         tp = getattr(self.clctx, "tilePixels", None)
         return tp() if tp else self.params.width * self.params.height

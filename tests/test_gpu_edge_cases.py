@@ -1,0 +1,177 @@
+"""GPU edge cases and size-independent properties: ragged sizes, degenerate scenes, the interactive first-iteration path,
+API misuse, and -- at the BASELINE.json full size, where the serial oracle is too slow -- invariants of the loop and
+bit-equality between the three traversal kernels."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from fluctus_b200 import CLContext, FluctusError, QueueCounters, SceneData, SLOT, Tracer, make_params, look_at
+from fluctus_b200.scene import build_bvh, make_room_scene, room_params, _tri, _material
+from fluctus_b200.structs import MATERIAL_DTYPE, TRIANGLE_DTYPE
+
+from conftest import scene_blob
+from parity_util import compare_counters, compare_pixels, compare_tasks, run_lockstep, setup_context
+
+pytestmark = pytest.mark.gpu
+
+
+def oracle_ctx(n):
+    from oracle.oracle_host import PortContext, RefContext, port_available, ref_available
+    if ref_available():
+        return RefContext(n)
+    if port_available():
+        return PortContext(n)
+    pytest.skip("no oracle library built")
+
+
+@pytest.mark.parametrize("n_tasks", [1, 31, 33, 1237])
+def test_ragged_task_counts(n_tasks):
+    """NUM_TASKS that is not a multiple of the warp, the logic tile or the trace block; more pixels than paths."""
+    scene = make_room_scene(materials="mixed")
+    params = room_params(scene, 37, 23, max_bounces=3, separate_queues=True)
+    with CLContext(n_tasks) as gpu:
+        run_lockstep(gpu, oracle_ctx(n_tasks), scene, params, iterations=10)
+
+
+def test_more_paths_than_pixels_and_one_pixel_image():
+    scene = make_room_scene(materials="diffuse")
+    for w, h, n in ((1, 1, 64), (5, 3, 600)):
+        params = room_params(scene, w, h, max_bounces=2)
+        with CLContext(n) as gpu:
+            run_lockstep(gpu, oracle_ctx(n), scene, params, iterations=6)
+
+
+def test_scene_whose_root_is_a_leaf():
+    """Two triangles, one leaf, no inner node: the traversal starts at a leaf reference."""
+    tris = np.array([_tri((-1, 0, -1), (1, 0, -1), (1, 0, 1), 0), _tri((-1, 0, -1), (1, 0, 1), (-1, 0, 1), 0)], TRIANGLE_DTYPE)
+    nodes, indices = build_bvh(tris, max_leaf=4)
+    assert len(nodes) == 1 and nodes[0]["nPrims"] == 2
+    scene = SceneData(tris, indices, nodes, np.array([_material()], MATERIAL_DTYPE))
+    cam = look_at((0.0, 1.5, 0.5), (0.0, 0.0, 0.0), fov=70.0)
+    light = dict(pos=(0.0, 2.0, 0.0), N=(0.0, -1.0, 0.0), right=(1.0, 0.0, 0.0), up=(0.0, 0.0, 1.0), size=(0.5, 0.5), E=(30.0, 30.0, 30.0))
+    params = make_params(24, 16, cam, scene.world_radius, 2, light=light, max_bounces=3)
+    with CLContext(24 * 16) as gpu:
+        run_lockstep(gpu, oracle_ctx(24 * 16), scene, params, iterations=6)
+
+
+@pytest.mark.parametrize("n_tasks", [700, 4000])
+def test_interactive_first_iteration_path(n_tasks):
+    """Tracer::update() with iteration == 0 (src/tracer.cpp:228-240): preview bounce clamp, three rounds with
+    firstIteration = true (logic limited to min(W*H, N) paths, wf_logic.cl:45), pixel index advanced once."""
+    scene = make_room_scene(materials="mixed")
+    W, H = 48, 32  # 1536 pixels: one case with N < W*H, one with N > W*H
+    params_g, params_c = room_params(scene, W, H, max_bounces=5), room_params(scene, W, H, max_bounces=5)
+    cpu = oracle_ctx(n_tasks)
+    with CLContext(n_tasks) as gpu:
+        tg, tc = setup_context(gpu, scene, params_g), setup_context(cpu, scene, params_c)
+        for it in range(5):
+            cg, cc = tg.update(), tc.update()
+            compare_counters(cg, cc, "update %d" % it)
+            compare_tasks(gpu.readTasks(), cpu.readTasks(), "update %d" % it)
+            compare_pixels(gpu.readPixels(), cpu.readPixels(), "update %d" % it, rtol=1e-5)
+        assert tg.stats == tc.stats
+
+
+def test_api_misuse_raises_like_the_reference():
+    scene = make_room_scene(materials="diffuse")
+    params = room_params(scene, 16, 16)
+    with CLContext(256) as gpu:
+        with pytest.raises(FluctusError, match="update_params|flx_update_params"):
+            gpu.enqueueWfLogicKernel(params, False)  # nothing set up yet
+        gpu.updateParams(params)
+        with pytest.raises(FluctusError, match="resize"):
+            gpu.enqueueWfResetKernel(params)
+        gpu.setupPixelStorage(16, 16)
+        with pytest.raises(FluctusError, match="upload_scene"):
+            gpu.enqueueWfExtRayKernel(params)
+        bad = SceneData(scene.tris, scene.indices, scene.nodes, scene.materials)
+        bad.nodes["link"][0] = 10 ** 6  # child link out of range
+        with pytest.raises(FluctusError, match="child links"):
+            gpu.uploadSceneData(bad)
+        bad = SceneData(scene.tris, scene.indices, scene.nodes, scene.materials)
+        bad.tris["matId"][3] = 99
+        with pytest.raises(FluctusError, match="material"):
+            gpu.uploadSceneData(bad)
+        bad = SceneData(scene.tris, scene.indices, scene.nodes, scene.materials)
+        bad.indices[5] = 10 ** 6
+        with pytest.raises(FluctusError, match="references triangle"):
+            gpu.uploadSceneData(bad)
+        gpu.uploadSceneData(scene)
+        p2 = params.copy()
+        p2.width = 32
+        with pytest.raises(FluctusError, match="flx_resize"):
+            gpu.updateParams(p2)
+        # and it still works after all those errors
+        tr = Tracer(gpu, params)
+        tr.start()
+        for _ in range(8):
+            tr.iterate()
+        assert gpu.readPixels()[:, 3].sum() > 0
+
+
+def _full_size_conference():
+    scene = SceneData.load_blob(scene_blob("conference"))
+    from bench_configs import conference_params
+    return scene, conference_params(scene, 1920, 1080)
+
+
+def test_full_size_invariants_and_kernel_variants_agree():
+    """BASELINE metric configuration (conference 1920x1080, 8 bounces, N = 2^21) -- too big for the serial oracle, so:
+    (1) the three traversal kernels (one ray per thread / persistent / persistent + smem treelet) must leave bit-identical
+        path state and counters,
+    (2) every iteration the extension queue is a permutation of all paths and queue lengths are consistent,
+    (3) every terminated path with at least one segment splats exactly once: sum of pixel weights == regenerated paths,
+    (4) radiance is finite and non-negative."""
+    scene, params = _full_size_conference()
+    N, iters = 1 << 21, 12
+    states, pixels, counters = [], [], []
+    for variant in (0, 1, 2):
+        with CLContext(N) as gpu:
+            gpu.setTuning(trace_variant=variant)
+            tr = setup_context(gpu, scene, params)
+            tr.start()
+            regenerated = 0
+            cs = []
+            for it in range(iters):
+                cnt = tr.iterate()
+                cs.append(cnt.as_dict())
+                regenerated += cnt.raygenQueue
+                assert cnt.extensionQueue == N, "every live path is extended every iteration (SURVEY 3B)"
+                assert cnt.diffuseQueue + cnt.raygenQueue == N and cnt.shadowQueue <= cnt.diffuseQueue
+                if variant == 1 and it in (0, iters - 1):
+                    q = gpu.readQueue("extension", N)
+                    assert np.array_equal(np.sort(q), np.arange(N, dtype=np.uint32)), "extension queue is not a permutation"
+                    rq = gpu.readQueue("raygen", cnt.raygenQueue)
+                    assert (np.diff(rq.astype(np.int64)) > 0).all(), "raygen queue is not in ascending path order"
+            pix = gpu.readPixels()
+            # the paths regenerated in the LAST iteration have not terminated yet; all earlier ones that terminated have splatted
+            assert np.isfinite(pix).all() and (pix >= 0).all()
+            alive = gpu.readTasks()
+            assert pix[:, 3].sum() == regenerated, "sum of sample weights must equal the number of terminated (= regenerated) paths"
+            states.append(alive)
+            pixels.append(pix)
+            counters.append(cs)
+    assert counters[0] == counters[1] == counters[2]
+    for k in (1, 2):
+        compare_tasks(states[0], states[k], "trace variant 0 vs %d at full size" % k)
+        compare_pixels(pixels[0], pixels[k], "trace variant 0 vs %d at full size" % k, rtol=1e-5)
+
+
+def test_full_size_is_deterministic_and_matches_fused_loop():
+    """Two runs (one per-stage with host round trips, one fused flx_render with the shadow/extension overlap) at full size
+    give the same path state bit for bit: no race decides anything that matters."""
+    scene, params = _full_size_conference()
+    N, iters = 1 << 21, 10
+    with CLContext(N) as a, CLContext(N) as b:
+        ta, tb = setup_context(a, scene, params), setup_context(b, scene, params)
+        ta.start(); tb.start()
+        for _ in range(iters):
+            ta.iterate()
+        b.resetStats()
+        tb.render(iters)
+        compare_tasks(a.readTasks(), b.readTasks(), "per-stage vs fused at full size")
+        compare_pixels(a.readPixels(), b.readPixels(), "per-stage vs fused at full size", rtol=1e-5)
+        st = b.getStats()
+        assert (st.extensionRays, st.shadowRays, st.primaryRays) == (ta.stats["extensionRays"], ta.stats["shadowRays"], ta.stats["primaryRays"])
