@@ -120,6 +120,8 @@ struct flx_ctx
     int topNodes = 2047;      // variant 2: treelet nodes staged per CTA (64 B each)
     int fetchThreshold = 16;  // refill when fewer lanes than this still hold a ray
     int extMinBlocks = 9, shadowMinBlocks = 10; // variant 1: resident 128-thread CTAs per SM the kernels are compiled for
+    int maxL1 = 0;
+    int smemStack = 0;        // variant 1: first 24 stack levels in shared memory ([level][thread], conflict-free)
     int fetchChunk = 32;     // queue entries a warp reserves per atomic
     int logicMinBlocks = 3;   // resident 256-thread CTAs per SM the logic kernel is compiled for (register budget)
     int innerMin = 8;         // leave the inner-node phase when fewer lanes than this are still at inner nodes
@@ -476,14 +478,19 @@ __global__ void k_deinterleave(const float4 *gathered, float4 *full, uint32_t wi
 }
 } // namespace
 
-template <bool ANYHIT, class COUNT, int MINB> static int launchPersistentV1(flx_ctx *ctx, uint32_t *fetch, unsigned long long *counts)
+template <bool ANYHIT, class COUNT, int MINB, int SDEPTH> static int launchPersistentV1(flx_ctx *ctx, uint32_t *fetch, unsigned long long *counts)
 {
-    auto kern = k_trace_persistent<ANYHIT, COUNT, FLX_TRACE_BLOCK, false, MINB>;
+    auto kern = k_trace_persistent<ANYHIT, COUNT, FLX_TRACE_BLOCK, false, MINB, SDEPTH>;
+    const size_t smem = (size_t)SDEPTH * FLX_TRACE_BLOCK * sizeof(int);
+    if (smem > 48 * 1024)
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (SDEPTH == 0 && ctx->maxL1) // the L1 is what this kernel lives on: ask for the largest L1 carve-out
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1));
     int perSM = ctx->traceBlocksPerSM;
     if (perSM <= 0)
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, FLX_TRACE_BLOCK, 0));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, FLX_TRACE_BLOCK, smem));
     const unsigned grid = (unsigned)std::max(1, perSM) * (unsigned)ctx->numSMs;
-    kern<<<grid, FLX_TRACE_BLOCK, 0, ctx->cur>>>(makeFrame(ctx), ctx->params, makeBvh(ctx), ctx->tris, fetch, ctx->fetchThreshold, ctx->innerMin, ctx->fetchChunk, 0, counts);
+    kern<<<grid, FLX_TRACE_BLOCK, smem, ctx->cur>>>(makeFrame(ctx), ctx->params, makeBvh(ctx), ctx->tris, fetch, ctx->fetchThreshold, ctx->innerMin, ctx->fetchChunk, 0, counts);
     return 0;
 }
 
@@ -492,21 +499,29 @@ template <bool ANYHIT, class COUNT> static int launchPersistentT(flx_ctx *ctx, u
     if (ctx->traceVariant == 2)
     {
         constexpr int BLOCK = 1024; // one persistent CTA per SM owns the staged treelet
-        auto kern = k_trace_persistent<ANYHIT, COUNT, BLOCK, true, 1>;
+        auto kern = k_trace_persistent<ANYHIT, COUNT, BLOCK, true, 1, 0>;
         const int top = (int)std::min<uint32_t>({(uint32_t)ctx->topNodes, ctx->treeletNodes, ctx->nTNodes, (uint32_t)((ctx->maxDynSmem - 1024) / 64)});
         const size_t smem = (size_t)top * 64;
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<ctx->numSMs, BLOCK, smem, ctx->cur>>>(makeFrame(ctx), ctx->params, makeBvh(ctx), ctx->tris, fetch, ctx->fetchThreshold, ctx->innerMin, ctx->fetchChunk, top, counts);
         return 0;
     }
-    // register budget: the kernel is compiled for MINB resident 128-thread CTAs per SM
+    // register budget: the kernel is compiled for MINB resident 128-thread CTAs per SM; stack: local or 24 levels in shared memory
     const int mb = ANYHIT ? ctx->shadowMinBlocks : ctx->extMinBlocks;
+    if (ctx->smemStack)
+    {
+        switch (mb)
+        {
+        case 8: return launchPersistentV1<ANYHIT, COUNT, 8, 24>(ctx, fetch, counts);
+        case 9: return launchPersistentV1<ANYHIT, COUNT, 9, 24>(ctx, fetch, counts);
+        default: return launchPersistentV1<ANYHIT, COUNT, 10, 24>(ctx, fetch, counts);
+        }
+    }
     switch (mb)
     {
-    case 8: return launchPersistentV1<ANYHIT, COUNT, 8>(ctx, fetch, counts);
-    case 9: return launchPersistentV1<ANYHIT, COUNT, 9>(ctx, fetch, counts);
-    case 12: return launchPersistentV1<ANYHIT, COUNT, 12>(ctx, fetch, counts);
-    default: return launchPersistentV1<ANYHIT, COUNT, 10>(ctx, fetch, counts);
+    case 8: return launchPersistentV1<ANYHIT, COUNT, 8, 0>(ctx, fetch, counts);
+    case 9: return launchPersistentV1<ANYHIT, COUNT, 9, 0>(ctx, fetch, counts);
+    default: return launchPersistentV1<ANYHIT, COUNT, 10, 0>(ctx, fetch, counts);
     }
 }
 
@@ -1146,8 +1161,14 @@ int flx_set_tuning(flx_ctx *ctx, int key, int value)
         return 0;
     case FLX_TUNE_EXT_MIN_BLOCKS:
     case FLX_TUNE_SHADOW_MIN_BLOCKS:
-        REQUIRE(value == 8 || value == 9 || value == 10 || value == 12, "flx_set_tuning: trace min blocks must be 8, 9, 10 or 12");
+        REQUIRE(value == 8 || value == 9 || value == 10, "flx_set_tuning: trace min blocks must be 8, 9 or 10");
         (key == FLX_TUNE_EXT_MIN_BLOCKS ? ctx->extMinBlocks : ctx->shadowMinBlocks) = value;
+        return 0;
+    case FLX_TUNE_MAX_L1:
+        ctx->maxL1 = value != 0;
+        return 0;
+    case FLX_TUNE_SMEM_STACK:
+        ctx->smemStack = value != 0;
         return 0;
     case FLX_TUNE_POSTPROCESS_IN_LOOP:
         ctx->postprocessInLoop = value != 0;

@@ -57,6 +57,18 @@ struct Tasks
     FLX_DEV void setf(int slot, uint32_t g, float v) const { base[(size_t)slot * n + g] = __float_as_uint(v); }
     FLX_DEV void setu(int slot, uint32_t g, uint32_t v) const { base[(size_t)slot * n + g] = v; }
     FLX_DEV V3 v(int slot, uint32_t g) const { return V3{f(slot, g), f(slot + 1, g), f(slot + 2, g)}; }
+    // streaming flavours (ld/st.global.cs: evict-first): for state touched once by a kernel whose L1 is busy caching the BVH
+    FLX_DEV float f_cs(int slot, uint32_t g) const { return __uint_as_float(__ldcs(base + (size_t)slot * n + g)); }
+    FLX_DEV uint32_t u_cs(int slot, uint32_t g) const { return __ldcs(base + (size_t)slot * n + g); }
+    FLX_DEV V3 v_cs(int slot, uint32_t g) const { return V3{f_cs(slot, g), f_cs(slot + 1, g), f_cs(slot + 2, g)}; }
+    FLX_DEV void setf_cs(int slot, uint32_t g, float v) const { __stcs(base + (size_t)slot * n + g, __float_as_uint(v)); }
+    FLX_DEV void setu_cs(int slot, uint32_t g, uint32_t v) const { __stcs(base + (size_t)slot * n + g, v); }
+    FLX_DEV void setv_cs(int slot, uint32_t g, V3 a) const
+    {
+        setf_cs(slot, g, a.x);
+        setf_cs(slot + 1, g, a.y);
+        setf_cs(slot + 2, g, a.z);
+    }
     FLX_DEV void setv(int slot, uint32_t g, V3 a) const
     {
         setf(slot, g, a.x);

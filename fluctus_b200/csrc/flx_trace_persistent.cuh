@@ -68,7 +68,7 @@ FLX_DEV void stage_bulk(void *dstShared, const void *srcGlobal, uint32_t bytes, 
     }
 }
 
-template <bool ANYHIT, class COUNT, int BLOCK, bool TOP, int MIN_BLOCKS>
+template <bool ANYHIT, class COUNT, int BLOCK, bool TOP, int MIN_BLOCKS, int SDEPTH>
 __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_trace_persistent(const __grid_constant__ Frame fr, const __grid_constant__ flx_RenderParams prm,
                                                                          const BvhView bvh, const flx_Triangle *tris160, uint32_t *fetchCounter,
                                                                          const int threshold, const int innerMin, const int fetchChunk, const int topCount, unsigned long long *countTotals)
@@ -92,7 +92,28 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_trace_persistent(const __
     float tbest = 0.0f, ub = 0.0f, vb = 0.0f;
     int tri = -1, cur = 0, sp = 0;
     bool occluded = false;
-    int stack[FLX_STACK_DEPTH];
+    // Traversal stack: the first SDEPTH levels live in shared memory, laid out [level][thread] so that every lane always
+    // hits its own bank whatever its depth (a push/pop is ONE wavefront); deeper levels -- beyond any tree the reference's
+    // builders make for the shipped scenes -- spill to local memory.  With SDEPTH = 0 the whole stack is local memory, where
+    // a push/pop by lanes at different depths touches up to 32 lines of L1, i.e. costs as much as a divergent node fetch.
+    static_assert(!(TOP && SDEPTH > 0), "the treelet and the stack do not share dynamic shared memory");
+    int lstack[FLX_STACK_DEPTH - SDEPTH];
+    int *const sstack = reinterpret_cast<int *>(dynSmem) + threadIdx.x;
+#define FLX_PUSH(v)                                                                                                                                            \
+    do                                                                                                                                                         \
+    {                                                                                                                                                          \
+        if (SDEPTH == 0 || sp >= SDEPTH)                                                                                                                       \
+            lstack[sp - SDEPTH] = (v);                                                                                                                         \
+        else                                                                                                                                                   \
+            sstack[sp * BLOCK] = (v);                                                                                                                          \
+        sp++;                                                                                                                                                  \
+    } while (0)
+#define FLX_POP(dst)                                                                                                                                           \
+    do                                                                                                                                                         \
+    {                                                                                                                                                          \
+        --sp;                                                                                                                                                  \
+        (dst) = (SDEPTH == 0 || sp >= SDEPTH) ? lstack[sp - SDEPTH] : sstack[sp * BLOCK];                                                                      \
+    } while (0)
     COUNT cnt;
     unsigned raysDone = 0;
     uint32_t chunkNext = 0, chunkEnd = 0, chunkSize = (uint32_t)fetchChunk; // warp-uniform
@@ -105,7 +126,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_trace_persistent(const __
             pending = false;
             raysDone++;
             if (ANYHIT)
-                t.setu(FLX_S_SHADOW_BLOCKED, gid, occluded ? 1u : 0u);
+                t.setu_cs(FLX_S_SHADOW_BLOCKED, gid, occluded ? 1u : 0u);
             else
             {
                 V3 P = v3(0.0f), N = v3(0.0f);
@@ -114,8 +135,8 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_trace_persistent(const __
                 if (tri >= 0)
                 {
                     const float4 *q = reinterpret_cast<const float4 *>(tris160 + tri);
-                    const float4 n0 = __ldg(q + 1), t0 = __ldg(q + 2), n1 = __ldg(q + 4), t1 = __ldg(q + 5), n2 = __ldg(q + 7), t2 = __ldg(q + 8);
-                    matId = __float_as_int(__ldg(q + 9).x);
+                    const float4 n0 = __ldcs(q + 1), t0 = __ldcs(q + 2), n1 = __ldcs(q + 4), t1 = __ldcs(q + 5), n2 = __ldcs(q + 7), t2 = __ldcs(q + 8);
+                    matId = __float_as_int(__ldcs(q + 9).x);
                     P = o + tbest * d;
                     N = norm3(bary3(ub, vb, v3(n0.x, n0.y, n0.z), v3(n1.x, n1.y, n1.z), v3(n2.x, n2.y, n2.z)));
                     const V3 uv = bary3(ub, vb, v3(t0.x, t0.y, t0.z), v3(t1.x, t1.y, t1.z), v3(t2.x, t2.y, t2.z));
@@ -130,15 +151,15 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_trace_persistent(const __
                     tri = 0;
                     matId = 0;
                 }
-                t.setu(FLX_S_PATH_LEN, gid, t.u(FLX_S_PATH_LEN, gid) + 1u);
-                t.setv(FLX_S_P, gid, P);
-                t.setv(FLX_S_N, gid, N);
-                t.setf(FLX_S_UV, gid, tu);
-                t.setf(FLX_S_UV + 1, gid, tv);
-                t.setf(FLX_S_HIT_T, gid, tbest);
-                t.setu(FLX_S_HIT_I, gid, (uint32_t)tri);
-                t.setu(FLX_S_AREA_LIGHT_HIT, gid, (uint32_t)lightHit);
-                t.setu(FLX_S_MAT_ID, gid, (uint32_t)matId);
+                t.setu_cs(FLX_S_PATH_LEN, gid, t.u_cs(FLX_S_PATH_LEN, gid) + 1u);
+                t.setv_cs(FLX_S_P, gid, P);
+                t.setv_cs(FLX_S_N, gid, N);
+                t.setf_cs(FLX_S_UV, gid, tu);
+                t.setf_cs(FLX_S_UV + 1, gid, tv);
+                t.setf_cs(FLX_S_HIT_T, gid, tbest);
+                t.setu_cs(FLX_S_HIT_I, gid, (uint32_t)tri);
+                t.setu_cs(FLX_S_AREA_LIGHT_HIT, gid, (uint32_t)lightHit);
+                t.setu_cs(FLX_S_MAT_ID, gid, (uint32_t)matId);
             }
         }
 
@@ -175,11 +196,11 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_trace_persistent(const __
             {
                 if (idx < count)
                 {
-                    gid = queue[idx];
-                    o = t.v(ANYHIT ? FLX_S_SHADOW_ORIG : FLX_S_ORIG, gid);
-                    d = t.v(ANYHIT ? FLX_S_SHADOW_DIR : FLX_S_DIR, gid);
+                    gid = __ldcs(queue + idx);
+                    o = t.v_cs(ANYHIT ? FLX_S_SHADOW_ORIG : FLX_S_ORIG, gid);
+                    d = t.v_cs(ANYHIT ? FLX_S_SHADOW_DIR : FLX_S_DIR, gid);
                     idir = v3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-                    tbest = ANYHIT ? t.f(FLX_S_SHADOW_RAY_LEN, gid) : 3.402823466e+38f;
+                    tbest = ANYHIT ? t.f_cs(FLX_S_SHADOW_RAY_LEN, gid) : 3.402823466e+38f;
                     ub = vb = 0.0f;
                     tri = -1;
                     occluded = false;
@@ -246,7 +267,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_trace_persistent(const __
                 if (lh && rh)
                 {
                     const bool swap = rn < ln; // right child closer -> first (bvh.cl:292); ties keep left first
-                    stack[sp++] = swap ? q3.x : q3.y;
+                    FLX_PUSH(swap ? q3.x : q3.y);
                     cur = swap ? q3.y : q3.x;
                 }
                 else if (lh)
@@ -254,7 +275,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_trace_persistent(const __
                 else if (rh)
                     cur = q3.y;
                 else if (sp > 0)
-                    cur = stack[--sp];
+                    FLX_POP(cur);
                 else
                 {
                     active = false;
@@ -310,7 +331,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_trace_persistent(const __
                     pending = true;
                 }
                 else
-                    cur = stack[--sp];
+                    FLX_POP(cur);
             }
             const unsigned still = __ballot_sync(FULL, active);
             if (still == 0u)
@@ -320,4 +341,6 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_trace_persistent(const __
         }
     }
     flush_counts(cnt, countTotals, raysDone);
+#undef FLX_PUSH
+#undef FLX_POP
 }

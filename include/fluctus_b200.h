@@ -157,9 +157,11 @@ enum { FLX_TUNE_TRACE_VARIANT = 0,      /* 0: one ray per thread; 1 (default): p
        FLX_TUNE_TOP_NODES = 3,          /* variant 2: treelet nodes (64 B each) staged per CTA, default 2047 */
        FLX_TUNE_LOGIC_MIN_BLOCKS = 5,   /* register budget of the logic kernel: compiled for 2, 3 (default) or 4 resident CTAs per SM */
        FLX_TUNE_FETCH_CHUNK = 6,        /* persistent variants: queue entries a warp reserves per atomic (default 32) */
-       FLX_TUNE_EXT_MIN_BLOCKS = 8,     /* variant 1 register budget: extension kernel compiled for 8, 9 (default), 10 or 12 CTAs of 128 per SM */
+       FLX_TUNE_EXT_MIN_BLOCKS = 8,     /* variant 1 register budget: extension kernel compiled for 8, 9 (default) or 10 CTAs of 128 per SM */
        FLX_TUNE_SHADOW_MIN_BLOCKS = 9,  /* same for the shadow kernel (default 10) */
        FLX_TUNE_POSTPROCESS_IN_LOOP = 10, /* flx_render: run the display pass every iteration like the reference's loop (default 1) */
+       FLX_TUNE_SMEM_STACK = 11,        /* variant 1: keep the first 24 traversal-stack levels in shared memory (default 0: measured slower, L1 shrinks) */
+       FLX_TUNE_MAX_L1 = 12,            /* variant 1: request the maximum L1 carve-out for the traversal kernels (default 0: measured 4 % slower) */
        FLX_TUNE_OVERLAP_TRACE = 7,      /* flx_render: run the shadow-ray kernel on a second stream, overlapping the extension kernel's tail (default 1) */
        FLX_TUNE_INNER_MIN = 4           /* leave the inner-node phase when fewer lanes than this are still at inner nodes (default 8) */ };
 int flx_set_tuning(flx_ctx *ctx, int key, int value);

@@ -28,6 +28,8 @@ def main():
     ap.add_argument("--overlaps", default="1")
     ap.add_argument("--ext-blocks", default="8")
     ap.add_argument("--shadow-blocks", default="10")
+    ap.add_argument("--smem-stacks", default="0")
+    ap.add_argument("--max-l1", default="1")
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
     from fluctus_b200 import CLContext, EnvMapData, SceneData, Tracer
@@ -51,8 +53,9 @@ def main():
     combos = [c + (lb, ch) for c in combos for lb in map(int, a.logic_blocks.split(",")) for ch in map(int, a.chunks.split(","))]
     combos = [c + (ov,) for c in combos for ov in map(int, a.overlaps.split(","))]
     combos = [c + (eb, sb) for c in combos for eb in map(int, a.ext_blocks.split(",")) for sb in map(int, a.shadow_blocks.split(","))]
-    for v, th, b, top, im, lb, ch, ov, eb, sb in combos:
-        ctx.setTuning(trace_variant=v, logic_min_blocks=lb, fetch_chunk=ch, overlap_trace=ov, ext_min_blocks=eb, shadow_min_blocks=sb)
+    combos = [c + (ss, ml) for c in combos for ss in map(int, a.smem_stacks.split(",")) for ml in map(int, a.max_l1.split(","))]
+    for v, th, b, top, im, lb, ch, ov, eb, sb, ss, ml in combos:
+        ctx.setTuning(trace_variant=v, logic_min_blocks=lb, fetch_chunk=ch, overlap_trace=ov, ext_min_blocks=eb, shadow_min_blocks=sb, smem_stack=ss, max_l1=ml)
         if v:
             ctx.setTuning(fetch_threshold=th, trace_blocks_per_sm=b, top_nodes=top, inner_min=im)
         tr = Tracer(ctx, params)
@@ -65,7 +68,7 @@ def main():
         ctx.setProfiling(False)
         st = ctx.getStats()
         perf = ctx.checkTracingPerf()
-        row = dict(variant=v, threshold=th, blocks_per_sm=b, top_nodes=top, inner_min=im, logic_blocks=lb, fetch_chunk=ch, overlap=ov, ext_blocks=eb, shadow_blocks=sb, ms_per_iter=ms / a.iters, mrays=(st.extensionRays + st.shadowRays) / ms / 1e3,
+        row = dict(variant=v, threshold=th, blocks_per_sm=b, top_nodes=top, inner_min=im, logic_blocks=lb, fetch_chunk=ch, overlap=ov, ext_blocks=eb, shadow_blocks=sb, smem_stack=ss, max_l1=ml, ms_per_iter=ms / a.iters, mrays=(st.extensionRays + st.shadowRays) / ms / 1e3,
                    ext_ms=perf["extrays"][0] / a.iters, shadow_ms=perf["shadowrays"][0] / a.iters, logic_ms=perf["logic"][0] / a.iters,
                    mat_ms=perf["materials"][0] / a.iters, raygen_ms=perf["raygen"][0] / a.iters,
                    ext_mrays=st.extensionRays / perf["extrays"][0] / 1e3, shadow_mrays=st.shadowRays / perf["shadowrays"][0] / 1e3)
