@@ -1,0 +1,44 @@
+#!/usr/bin/env python
+"""Small end-to-end run for compute-sanitizer (memcheck / racecheck / initcheck): every kernel, both queue modes, env map,
+tiling with one part.  Usage on the GPU box:  compute-sanitizer --tool memcheck python tools/sanitize.py"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from fluctus_b200 import CLContext, EnvMapData, Tracer  # noqa: E402
+from fluctus_b200.scene import make_room_scene, room_params  # noqa: E402
+
+
+def main():
+    scene = make_room_scene(materials="mixed", textured=True)
+    rng = np.random.default_rng(3)
+    env = EnvMapData.from_rgb(rng.uniform(0.0, 0.4, size=(16, 32, 3)).astype(np.float32))
+    for variant in (0, 1, 2):
+        for separate in (False, True):
+            params = room_params(scene, 40, 24, max_bounces=4, separate_queues=separate, use_env_map=True, env_map_strength=1.5)
+            with CLContext(1500) as ctx:
+                ctx.setTuning(trace_variant=variant)
+                ctx.uploadSceneData(scene)
+                ctx.createEnvMap(env)
+                ctx.setupPixelStorage(40, 24)
+                ctx.setTile(0, 1, 4)
+                tr = Tracer(ctx, params)
+                tr.start()
+                for _ in range(3):
+                    tr.iterate()
+                ctx.render(3)
+                ctx.setCounting(True)
+                ctx.render(1)
+                ctx.setCounting(False)
+                tr.update()
+                pix = ctx.readPixels()
+                assert np.isfinite(pix).all()
+    print("SANITIZE_RUN_OK")
+
+
+if __name__ == "__main__":
+    main()
