@@ -32,11 +32,13 @@ int main(int argc, char **argv)
 {
     if (argc < 7)
     {
-        std::fprintf(stderr, "usage: %s scene.bin width height numTasks maxBounces iterations [out.rgba]\n", argv[0]);
+        std::fprintf(stderr, "usage: %s scene.bin width height numTasks maxBounces iterations|spp=N [out.rgba]\n"
+                             "  iterations: wavefront loop (Tracer::runBenchmark);  spp=N: final frame with the microkernel integrator (Tracer::renderSingle)\n", argv[0]);
         return 2;
     }
     const std::string path = argv[1];
-    const uint32_t W = std::atoi(argv[2]), H = std::atoi(argv[3]), N = std::atoi(argv[4]), bounces = std::atoi(argv[5]), iters = std::atoi(argv[6]);
+    const bool single = std::strncmp(argv[6], "spp=", 4) == 0;
+    const uint32_t W = std::atoi(argv[2]), H = std::atoi(argv[3]), N = std::atoi(argv[4]), bounces = std::atoi(argv[5]), iters = std::atoi(single ? argv[6] + 4 : argv[6]);
     std::ifstream in(path, std::ios::binary);
     if (!in)
     {
@@ -114,6 +116,43 @@ int main(int argc, char **argv)
         clctx.uploadSceneData(s);
         clctx.setupPixelStorage(W, H);
         clctx.updateParams(params);
+
+        if (single) // Tracer::renderSingle (src/tracer.cpp:95-169): exactly `iters` samples in every pixel, microkernel integrator
+        {
+            clctx.enqueueResetKernel(params);
+            const auto t0 = std::chrono::steady_clock::now();
+            for (uint32_t sample = 0; sample < iters; sample++)
+            {
+                clctx.enqueueRayGenKernel(params);
+                for (uint32_t bounce = 0; bounce < params.maxBounces + 1; bounce++)
+                {
+                    clctx.enqueueNextVertexKernel(params);
+                    clctx.enqueueBsdfSampleKernel(params);
+                }
+                clctx.enqueueSplatKernel(params);
+                clctx.enqueuePostprocessKernel(params);
+                clctx.finishQueue();
+            }
+            const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            flx_RenderStats64 st;
+            if (flx_get_stats(clctx.handle(), &st) != 0)
+                throw std::runtime_error(flx_last_error(clctx.handle()));
+            std::vector<float> pix = clctx.readPixels();
+            double sum[4] = {0, 0, 0, 0};
+            for (size_t i = 0; i < pix.size(); i += 4)
+                for (int c = 0; c < 4; c++)
+                    sum[c] += pix[i + c];
+            std::printf("{\"integrator\": \"microkernel\", \"spp\": %u, \"primary\": %llu, \"extension\": %llu, \"shadow\": %llu, \"seconds\": %.6f, \"mrays_per_s\": %.2f, \"samples\": %.0f, "
+                        "\"mean_rgb\": [%.6f, %.6f, %.6f]}\n",
+                        iters, (unsigned long long)st.primaryRays, (unsigned long long)st.extensionRays, (unsigned long long)st.shadowRays, dt,
+                        (st.primaryRays + st.extensionRays + st.shadowRays) / dt / 1e6, sum[3], sum[0] / sum[3], sum[1] / sum[3], sum[2] / sum[3]);
+            if (argc > 7)
+            {
+                std::ofstream out(argv[7], std::ios::binary);
+                out.write(reinterpret_cast<const char *>(pix.data()), pix.size() * sizeof(float));
+            }
+            return 0;
+        }
 
         // iteration == 0 prologue (src/tracer.cpp:236-240)
         clctx.resetPixelIndex();

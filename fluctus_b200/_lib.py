@@ -26,6 +26,13 @@ _SIGNATURES = {
     "flx_enqueue_logic": (C.c_int, [_P, C.c_int]),
     "flx_enqueue_materials": (C.c_int, [_P]),
     "flx_enqueue_postprocess": (C.c_int, [_P]),
+    "flx_enqueue_mk_reset": (C.c_int, [_P]),
+    "flx_enqueue_mk_raygen": (C.c_int, [_P]),
+    "flx_enqueue_mk_next_vertex": (C.c_int, [_P]),
+    "flx_enqueue_mk_sample_bsdf": (C.c_int, [_P]),
+    "flx_enqueue_mk_splat": (C.c_int, [_P]),
+    "flx_enqueue_mk_splat_preview": (C.c_int, [_P]),
+    "flx_render_single": (C.c_int, [_P, C.c_uint32]),
     "flx_read_preview": (C.c_int, [_P, _P, C.c_size_t]),
     "flx_enqueue_clear_queues": (C.c_int, [_P]),
     "flx_enqueue_get_counters": (C.c_int, [_P, C.POINTER(QueueCounters)]),

@@ -17,7 +17,8 @@ class FluctusError(RuntimeError):
     pass
 
 
-KERNEL_IDS = {"reset": 0, "raygen": 1, "extrays": 2, "shadowrays": 3, "logic": 4, "materials": 5, "end_iteration": 6, "postprocess": 7}
+KERNEL_IDS = {"reset": 0, "raygen": 1, "extrays": 2, "shadowrays": 3, "logic": 4, "materials": 5, "end_iteration": 6, "postprocess": 7,
+              "mk_reset": 8, "mk_raygen": 9, "mk_next_vertex": 10, "mk_sample_bsdf": 11, "mk_splat": 12}
 
 
 class CLContext:
@@ -100,6 +101,29 @@ class CLContext:
 
     def enqueueWfMaterialKernels(self, params=None):
         self._check(self._lib.flx_enqueue_materials(self._h), "enqueueWfMaterialKernels")
+
+    # ---- the microkernel integrator (clcontext.hpp:35-40; clcontext.cpp:709-750): one path per pixel, a phase per path
+    def enqueueResetKernel(self, params=None):
+        self._check(self._lib.flx_enqueue_mk_reset(self._h), "enqueueResetKernel")
+
+    def enqueueRayGenKernel(self, params=None):
+        self._check(self._lib.flx_enqueue_mk_raygen(self._h), "enqueueRayGenKernel")
+
+    def enqueueNextVertexKernel(self, params=None):
+        self._check(self._lib.flx_enqueue_mk_next_vertex(self._h), "enqueueNextVertexKernel")
+
+    def enqueueBsdfSampleKernel(self, params=None):
+        self._check(self._lib.flx_enqueue_mk_sample_bsdf(self._h), "enqueueBsdfSampleKernel")
+
+    def enqueueSplatKernel(self, params=None):
+        self._check(self._lib.flx_enqueue_mk_splat(self._h), "enqueueSplatKernel")
+
+    def enqueueSplatPreviewKernel(self, params=None):
+        self._check(self._lib.flx_enqueue_mk_splat_preview(self._h), "enqueueSplatPreviewKernel")
+
+    def renderSingleLoop(self, spp):
+        """The sample loop of Tracer::renderSingle (src/tracer.cpp:124-150) spp times without host round trips (flx_render_single)."""
+        self._check(self._lib.flx_render_single(self._h, int(spp)), "renderSingleLoop")
 
     def enqueuePostprocessKernel(self, params=None):
         """reference: clcontext.hpp:41 -- normalise / exposure / tone map / gamma into the preview buffer."""

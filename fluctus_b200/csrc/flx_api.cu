@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "flx_kernels.cuh"
+#include "flx_mk.cuh"
 #include "flx_trace_persistent.cuh"
 
 static_assert(sizeof(flx_RenderParams) == 240, "RenderParams layout (geom.h:163-180)");
@@ -128,7 +129,12 @@ struct flx_ctx
     int traceBlocksPerSM = 0; // 0: occupancy calculator
     int numSMs = 148;
     int maxDynSmem = 48 * 1024;
-    uint32_t *fetchCounters = nullptr; // [0] extension, [1] shadow
+    uint32_t *fetchCounters = nullptr; // [0] extension, [1] shadow, [2] microkernel nextVertex, [3] microkernel light samples
+
+    // microkernel integrator (flx_mk.cuh), allocated on first use
+    uint32_t *mkScratch = nullptr;  // MK_X_SLOTS x numTasks
+    uint32_t *mkRayQueue = nullptr; // 2 x numTasks candidate shadow rays
+    uint32_t *mkRayCount = nullptr;
 
     // timing
     cudaEvent_t evStart = nullptr, evStop = nullptr;
@@ -490,7 +496,7 @@ template <bool ANYHIT, class COUNT, int MINB, int SDEPTH> static int launchPersi
     if (perSM <= 0)
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, FLX_TRACE_BLOCK, smem));
     const unsigned grid = (unsigned)std::max(1, perSM) * (unsigned)ctx->numSMs;
-    kern<<<grid, FLX_TRACE_BLOCK, smem, ctx->cur>>>(makeFrame(ctx), ctx->params, makeBvh(ctx), ctx->tris, fetch, ctx->fetchThreshold, ctx->innerMin, ctx->fetchChunk, 0, counts);
+    kern<<<grid, FLX_TRACE_BLOCK, smem, ctx->cur>>>(makeFrame(ctx), ctx->params, makeBvh(ctx), ctx->tris, fetch, ctx->fetchThreshold, ctx->innerMin, ctx->fetchChunk, 0, counts, MkView{});
     return 0;
 }
 
@@ -503,7 +509,7 @@ template <bool ANYHIT, class COUNT> static int launchPersistentT(flx_ctx *ctx, u
         const int top = (int)std::min<uint32_t>({(uint32_t)ctx->topNodes, ctx->treeletNodes, ctx->nTNodes, (uint32_t)((ctx->maxDynSmem - 1024) / 64)});
         const size_t smem = (size_t)top * 64;
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<ctx->numSMs, BLOCK, smem, ctx->cur>>>(makeFrame(ctx), ctx->params, makeBvh(ctx), ctx->tris, fetch, ctx->fetchThreshold, ctx->innerMin, ctx->fetchChunk, top, counts);
+        kern<<<ctx->numSMs, BLOCK, smem, ctx->cur>>>(makeFrame(ctx), ctx->params, makeBvh(ctx), ctx->tris, fetch, ctx->fetchThreshold, ctx->innerMin, ctx->fetchChunk, top, counts, MkView{});
         return 0;
     }
     // register budget: the kernel is compiled for MINB resident 128-thread CTAs per SM; stack: local or 24 levels in shared memory
@@ -534,6 +540,50 @@ template <bool ANYHIT> static int launchPersistent(flx_ctx *ctx)
     if (rc)
         return rc;
     return launchCheck(ctx, ANYHIT ? "k_trace_persistent<shadow>" : "k_trace_persistent<extension>");
+}
+
+// ---- microkernel integrator plumbing
+static int ensureMk(flx_ctx *ctx)
+{
+    if (ctx->mkScratch)
+        return 0;
+    CU(cudaMalloc(&ctx->mkScratch, (size_t)ctx->numTasks * MK_X_SLOTS * sizeof(uint32_t)));
+    CU(cudaMalloc(&ctx->mkRayQueue, (size_t)ctx->numTasks * 2 * sizeof(uint32_t)));
+    CU(cudaMalloc(&ctx->mkRayCount, sizeof(uint32_t)));
+    CU(cudaMemsetAsync(ctx->mkScratch, 0, (size_t)ctx->numTasks * MK_X_SLOTS * sizeof(uint32_t), ctx->stream));
+    CU(cudaMemsetAsync(ctx->mkRayCount, 0, sizeof(uint32_t), ctx->stream));
+    return 0;
+}
+
+static MkView makeMk(const flx_ctx *c)
+{
+    MkView m;
+    m.scratch.base = c->mkScratch;
+    m.scratch.n = c->numTasks;
+    m.rayQueue = c->mkRayQueue;
+    m.rayCount = c->mkRayCount;
+    m.limit = std::min(c->tilePixels, c->numTasks); // min(width * height, numTasks), e.g. mk_raygen.cl:9
+    m.stats = c->stats;
+    return m;
+}
+
+static unsigned mkGrid(uint32_t n) { return std::max(1u, (n + FLX_BLOCK - 1) / FLX_BLOCK); }
+
+// one launch of the persistent traversal kernel in a microkernel mode (closest hit over the paths in phase
+// MK_RT_NEXT_VERTEX, or any hit over the light-sample ray list)
+template <bool ANYHIT> static int launchMkTrace(flx_ctx *ctx, const MkView &mk)
+{
+    constexpr int MODE = ANYHIT ? TRACE_MK_NEE : TRACE_MK_NEXT;
+    constexpr int MINB = ANYHIT ? 10 : 9;
+    uint32_t *fetch = ctx->fetchCounters + (ANYHIT ? 3 : 2);
+    CU(cudaMemsetAsync(fetch, 0, sizeof(uint32_t), ctx->stream));
+    auto kern = k_trace_persistent<ANYHIT, NoCount, FLX_TRACE_BLOCK, false, MINB, 0, MODE>;
+    int perSM = ctx->traceBlocksPerSM;
+    if (perSM <= 0)
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, FLX_TRACE_BLOCK, 0));
+    const unsigned grid = (unsigned)std::max(1, perSM) * (unsigned)ctx->numSMs;
+    kern<<<grid, FLX_TRACE_BLOCK, 0, ctx->stream>>>(makeFrame(ctx), ctx->params, makeBvh(ctx), ctx->tris, fetch, ctx->fetchThreshold, ctx->innerMin, ctx->fetchChunk, 0, nullptr, mk);
+    return launchCheck(ctx, ANYHIT ? "k_trace_persistent<mk light samples>" : "k_trace_persistent<mk nextVertex>");
 }
 
 // ================================================================================================ C ABI
@@ -607,7 +657,7 @@ int flx_create(int device, uint32_t num_tasks, flx_ctx **out)
     CUB(cudaMallocHost(&c->pinnedCounters, sizeof(flx_QueueCounters) * flx_ctx::kCounterRing));
     c->numSMs = prop.multiProcessorCount;
     c->maxDynSmem = (int)prop.sharedMemPerBlockOptin;
-    CUB(cudaMalloc(&c->fetchCounters, 2 * sizeof(uint32_t)));
+    CUB(cudaMalloc(&c->fetchCounters, 4 * sizeof(uint32_t)));
     CUB(cudaMalloc(&c->traceCounts, 10 * sizeof(unsigned long long)));
     CUB(cudaMemset(c->traceCounts, 0, 10 * sizeof(unsigned long long)));
     CUB(cudaEventCreate(&c->evStart));
@@ -652,6 +702,9 @@ void flx_destroy(flx_ctx *c)
     freeDev(c->scanTicket);
     freeDev(c->traceCounts);
     freeDev(c->fetchCounters);
+    freeDev(c->mkScratch);
+    freeDev(c->mkRayQueue);
+    freeDev(c->mkRayCount);
     if (c->evStart)
         cudaEventDestroy(c->evStart);
     if (c->evStop)
@@ -957,6 +1010,117 @@ int flx_enqueue_materials(flx_ctx *ctx)
         k_material<ALL><<<grid, FLX_BLOCK, 0, ctx->stream>>>(fr, sc, Q_DIFFUSE);
     }
     return launchCheck(ctx, "k_material");
+}
+
+// ---- microkernel integrator (CLContext::enqueueResetKernel ... enqueueSplatPreviewKernel, clcontext.cpp:709-750)
+int flx_enqueue_mk_reset(flx_ctx *ctx)
+{
+    int rc = checkReady(ctx, false, true);
+    if (rc || (rc = ensureMk(ctx)))
+        return rc;
+    CU(cudaSetDevice(ctx->device));
+    const MkView mk = makeMk(ctx);
+    Timed tm(ctx, FLX_K_MK_RESET);
+    k_mk_reset<<<mkGrid(mk.limit), FLX_BLOCK, 0, ctx->stream>>>(makeFrame(ctx), mk.limit);
+    return launchCheck(ctx, "k_mk_reset");
+}
+
+int flx_enqueue_mk_raygen(flx_ctx *ctx)
+{
+    int rc = checkReady(ctx, false, true);
+    if (rc || (rc = ensureMk(ctx)))
+        return rc;
+    CU(cudaSetDevice(ctx->device));
+    const MkView mk = makeMk(ctx);
+    Timed tm(ctx, FLX_K_MK_RAYGEN);
+    k_mk_raygen<<<mkGrid(mk.limit), FLX_BLOCK, 0, ctx->stream>>>(makeFrame(ctx), ctx->params, mk.limit);
+    return launchCheck(ctx, "k_mk_raygen");
+}
+
+int flx_enqueue_mk_next_vertex(flx_ctx *ctx)
+{
+    int rc = checkReady(ctx, true, true);
+    if (rc || (rc = ensureMk(ctx)))
+        return rc;
+    CU(cudaSetDevice(ctx->device));
+    const MkView mk = makeMk(ctx);
+    Timed tm(ctx, FLX_K_MK_NEXT_VERTEX);
+    if ((rc = launchMkTrace<false>(ctx, mk)))
+        return rc;
+    k_mk_next_vertex_logic<<<mkGrid(mk.limit), FLX_BLOCK, 0, ctx->stream>>>(makeFrame(ctx), ctx->params, makeScene(ctx), mk);
+    return launchCheck(ctx, "k_mk_next_vertex_logic");
+}
+
+int flx_enqueue_mk_sample_bsdf(flx_ctx *ctx)
+{
+    int rc = checkReady(ctx, true, true);
+    if (rc || (rc = ensureMk(ctx)))
+        return rc;
+    CU(cudaSetDevice(ctx->device));
+    const MkView mk = makeMk(ctx);
+    const Frame fr = makeFrame(ctx);
+    const SceneView sc = makeScene(ctx);
+    Timed tm(ctx, FLX_K_MK_SAMPLE_BSDF);
+    const bool nee = ctx->params.sampleExpl && (ctx->params.useEnvMap || ctx->params.useAreaLight);
+    if (nee)
+    {
+        CU(cudaMemsetAsync(ctx->mkRayCount, 0, sizeof(uint32_t), ctx->stream));
+        k_mk_nee_prepare<<<mkGrid(mk.limit), FLX_BLOCK, 0, ctx->stream>>>(fr, ctx->params, sc, mk);
+        if ((rc = launchCheck(ctx, "k_mk_nee_prepare")) || (rc = launchMkTrace<true>(ctx, mk)))
+            return rc;
+    }
+    else // no light samples: the shading kernel continues from the stored seed
+        k_mk_copy_seed<<<mkGrid(mk.limit), FLX_BLOCK, 0, ctx->stream>>>(fr, mk);
+    k_mk_shade<<<mkGrid(mk.limit), FLX_BLOCK, 0, ctx->stream>>>(fr, ctx->params, sc, mk);
+    return launchCheck(ctx, "k_mk_shade");
+}
+
+int flx_enqueue_mk_splat(flx_ctx *ctx)
+{
+    int rc = checkReady(ctx, false, true);
+    if (rc || (rc = ensureMk(ctx)))
+        return rc;
+    CU(cudaSetDevice(ctx->device));
+    const MkView mk = makeMk(ctx);
+    Timed tm(ctx, FLX_K_MK_SPLAT);
+    k_mk_splat<<<mkGrid(mk.limit), FLX_BLOCK, 0, ctx->stream>>>(makeFrame(ctx), mk);
+    return launchCheck(ctx, "k_mk_splat");
+}
+
+int flx_enqueue_mk_splat_preview(flx_ctx *ctx)
+{
+    int rc = checkReady(ctx, false, true);
+    if (rc || (rc = ensureMk(ctx)))
+        return rc;
+    CU(cudaSetDevice(ctx->device));
+    const MkView mk = makeMk(ctx);
+    Timed tm(ctx, FLX_K_MK_SPLAT);
+    k_mk_splat_preview<<<mkGrid(mk.limit), FLX_BLOCK, 0, ctx->stream>>>(makeFrame(ctx), mk.limit);
+    return launchCheck(ctx, "k_mk_splat_preview");
+}
+
+// Tracer::renderSingle's loop (tracer.cpp:124-150), spp times, no host round trips: camera rays, (maxBounces + 1) x
+// (nextVertex, sampleBsdf), splat, display pass.
+int flx_render_single(flx_ctx *ctx, uint32_t spp)
+{
+    int rc = checkReady(ctx, true, true);
+    if (rc)
+        return rc;
+    for (uint32_t s = 0; s < spp; s++)
+    {
+        if ((rc = flx_enqueue_mk_raygen(ctx)))
+            return rc;
+        for (uint32_t bounce = 0; bounce < ctx->params.maxBounces + 1u; bounce++)
+        {
+            if ((rc = flx_enqueue_mk_next_vertex(ctx)) || (rc = flx_enqueue_mk_sample_bsdf(ctx)))
+                return rc;
+        }
+        if ((rc = flx_enqueue_mk_splat(ctx)))
+            return rc;
+        if (ctx->postprocessInLoop && (rc = flx_enqueue_postprocess(ctx)))
+            return rc;
+    }
+    return 0;
 }
 
 int flx_enqueue_postprocess(flx_ctx *ctx)

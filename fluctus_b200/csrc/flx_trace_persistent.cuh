@@ -23,6 +23,7 @@
 #pragma once
 
 #include "flx_kernels.cuh"
+#include "flx_mk.cuh"
 
 struct F8
 {
@@ -68,11 +69,21 @@ FLX_DEV void stage_bulk(void *dstShared, const void *srcGlobal, uint32_t bytes, 
     }
 }
 
-template <bool ANYHIT, class COUNT, int BLOCK, bool TOP, int MIN_BLOCKS, int SDEPTH>
+// MODE selects where the rays come from and where the result goes:
+//   TRACE_WF       the wavefront stages: extension / shadow queue of path indices, rays and results in the path state;
+//   TRACE_MK_NEXT  microkernel nextVertex (src/mk_next_vertex.cl:22-40): no queue -- every path g < limit whose phase is
+//                  MK_RT_NEXT_VERTEX is traced; a lane that draws a path in another phase simply asks again;
+//   TRACE_MK_NEE   microkernel next-event rays (src/mk_sample_bsdf.cl:87-91, 120-121): the ray list and the rays live in the
+//                  MkView scratch (flx_mk.cuh), two candidate rays per path, entry = 2 * path + which.
+enum { TRACE_WF = 0, TRACE_MK_NEXT = 1, TRACE_MK_NEE = 2 };
+
+template <bool ANYHIT, class COUNT, int BLOCK, bool TOP, int MIN_BLOCKS, int SDEPTH, int MODE = TRACE_WF>
 __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_trace_persistent(const __grid_constant__ Frame fr, const __grid_constant__ flx_RenderParams prm,
                                                                          const BvhView bvh, const flx_Triangle *tris160, uint32_t *fetchCounter,
-                                                                         const int threshold, const int innerMin, const int fetchChunk, const int topCount, unsigned long long *countTotals)
+                                                                         const int threshold, const int innerMin, const int fetchChunk, const int topCount, unsigned long long *countTotals,
+                                                                         const MkView mk)
 {
+    static_assert(MODE == TRACE_WF || (MODE == TRACE_MK_NEXT && !ANYHIT) || (MODE == TRACE_MK_NEE && ANYHIT), "microkernel modes: closest hit for nextVertex, any hit for the light samples");
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(128) unsigned char dynSmem[];
     __shared__ unsigned long long stageBar;
@@ -81,8 +92,8 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_trace_persistent(const __
         stage_bulk(dynSmem, bvh.nodes, (uint32_t)topCount * 64u, &stageBar);
     const int lane = threadIdx.x & 31;
     const unsigned lanesBelow = (1u << lane) - 1u;
-    const uint32_t *queue = fr.queues[ANYHIT ? Q_SHADOW : Q_EXT];
-    const uint32_t count = *counter_ptr(fr.counters, ANYHIT ? Q_SHADOW : Q_EXT);
+    const uint32_t *queue = MODE == TRACE_MK_NEE ? mk.rayQueue : fr.queues[ANYHIT ? Q_SHADOW : Q_EXT];
+    const uint32_t count = MODE == TRACE_MK_NEXT ? mk.limit : (MODE == TRACE_MK_NEE ? *mk.rayCount : *counter_ptr(fr.counters, ANYHIT ? Q_SHADOW : Q_EXT));
     const Tasks &t = fr.tasks;
     const bool lightTest = ANYHIT ? (prm.useAreaLight != 0) : (prm.sampleImpl && prm.useAreaLight);
 
@@ -125,7 +136,9 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_trace_persistent(const __
         {
             pending = false;
             raysDone++;
-            if (ANYHIT)
+            if (ANYHIT && MODE == TRACE_MK_NEE)
+                mk.scratch.setu_cs(MK_X_BLOCKED0 + (int)(gid & 1u), gid >> 1, occluded ? 1u : 0u);
+            else if (ANYHIT)
                 t.setu_cs(FLX_S_SHADOW_BLOCKED, gid, occluded ? 1u : 0u);
             else
             {
@@ -194,20 +207,35 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_trace_persistent(const __
                 chunkNext += needCount;
             if (need)
             {
-                if (idx < count)
+                if (idx < count && (MODE != TRACE_MK_NEXT || t.u_cs(FLX_S_PHASE, idx) == (uint32_t)MK_RT_NEXT_VERTEX))
                 {
-                    gid = __ldcs(queue + idx);
-                    o = t.v_cs(ANYHIT ? FLX_S_SHADOW_ORIG : FLX_S_ORIG, gid);
-                    d = t.v_cs(ANYHIT ? FLX_S_SHADOW_DIR : FLX_S_DIR, gid);
+                    bool quadFirst = ANYHIT && lightTest; // the light quad is tested first and blocks (wf_shadowrays.cl:29-31)
+                    if (MODE == TRACE_MK_NEE)
+                    {
+                        gid = __ldcs(queue + idx); // 2 * path + which
+                        const uint32_t path = gid >> 1, which = gid & 1u;
+                        o = mk.scratch.v_cs(MK_X_ORIG, path);
+                        d = mk.scratch.v_cs(which ? MK_X_DIR1 : MK_X_DIR0, path);
+                        // env-map sample: 2 * worldRadius, light quad blocks (mk_sample_bsdf.cl:82-90); area-light sample: its own
+                        // length, no quad test (mk_sample_bsdf.cl:114-120)
+                        tbest = which ? mk.scratch.f_cs(MK_X_LEN1, path) : 2.0f * prm.worldRadius;
+                        quadFirst = lightTest && which == 0u;
+                    }
+                    else
+                    {
+                        gid = MODE == TRACE_MK_NEXT ? idx : __ldcs(queue + idx);
+                        o = t.v_cs(ANYHIT ? FLX_S_SHADOW_ORIG : FLX_S_ORIG, gid);
+                        d = t.v_cs(ANYHIT ? FLX_S_SHADOW_DIR : FLX_S_DIR, gid);
+                        tbest = ANYHIT ? t.f_cs(FLX_S_SHADOW_RAY_LEN, gid) : 3.402823466e+38f;
+                    }
                     idir = v3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-                    tbest = ANYHIT ? t.f_cs(FLX_S_SHADOW_RAY_LEN, gid) : 3.402823466e+38f;
                     ub = vb = 0.0f;
                     tri = -1;
                     occluded = false;
                     cur = bvh.rootRef;
                     sp = 0;
                     active = true;
-                    if (ANYHIT && lightTest) // the light quad is tested first and blocks (wf_shadowrays.cl:29-31)
+                    if (quadFirst)
                     {
                         float tl = tbest;
                         if (light_quad(prm.areaLight, o, d, tl))
@@ -218,13 +246,13 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_trace_persistent(const __
                         }
                     }
                 }
-                else
+                else if (idx >= count)
                     exhausted = true;
             }
         }
-        if (__ballot_sync(FULL, active || pending) == 0u)
-            break; // queue drained and every lane idle
         const bool drain = __any_sync(FULL, exhausted); // nothing left to fetch: run the remaining rays to the end
+        if (__ballot_sync(FULL, active || pending) == 0u && (MODE != TRACE_MK_NEXT || drain))
+            break; // queue drained and every lane idle (TRACE_MK_NEXT: a round may draw only paths in other phases)
 
         // ---- traverse until too few lanes hold a ray
         while (true)

@@ -4,6 +4,8 @@ Replays, call for call, the order in which the reference drives CLContext:
   * start()     = the `iteration == 0` prologue of Tracer::update       (reference: src/tracer.cpp:236-240)
   * iterate()   = one steady-state iteration of Tracer::runBenchmark    (reference: src/tracer.cpp:433-439, 447 [post-process], 455-465)
   * render(n)   = n such iterations without host round trips (flx_render)
+  * renderSingle(spp) / updateMicrokernel() = the same two loops with the reference's other integrator, the microkernel
+                  path tracer                                            (reference: src/tracer.cpp:95-169, 267-299)
 It works with any object that has CLContext's method set -- the CUDA context (fluctus_b200.CLContext) and the oracle
 contexts in oracle/ alike -- which is how the parity tests run the same loop on both.
 """
@@ -88,6 +90,53 @@ class Tracer:
         self.stats["samples"] += cnt.raygenQueue if self.iteration > 0 else 0
         self.iteration += 1
         return cnt
+
+    # ---- the microkernel integrator (the reference's default, `useWavefront = false`)
+    def renderSingle(self, spp, fused=False):
+        """Tracer::renderSingle (src/tracer.cpp:95-169): a final frame with exactly `spp` samples in every pixel -- which only
+        the microkernel integrator guarantees, so the reference switches to it here (tracer.cpp:99-101) and turns Russian
+        roulette off.  Per sample: camera rays, (maxBounces + 1) x (nextVertex, sampleBsdf), splat, display pass, finish.
+        `fused=True` runs the same loop inside the library without the per-sample finishQueue (flx_render_single)."""
+        c, p = self.clctx, self.params
+        if p.useRoulette:
+            p.useRoulette = 0
+        c.updateParams(p)
+        c.enqueueResetKernel(p)
+        if fused and hasattr(c, "renderSingleLoop"):
+            c.renderSingleLoop(spp)
+            c.finishQueue()
+            return
+        for _ in range(spp):
+            c.enqueueRayGenKernel(p)
+            for _bounce in range(p.maxBounces + 1):
+                c.enqueueNextVertexKernel(p)
+                c.enqueueBsdfSampleKernel(p)
+            c.enqueueSplatKernel(p)
+            c.enqueuePostprocessKernel(p)
+            c.finishQueue()
+
+    def updateMicrokernel(self):
+        """One call of the interactive loop with the microkernel integrator, Tracer::update() `else` branch
+        (src/tracer.cpp:267-299): the first call after a change resets and shows a two-segment preview, later calls add
+        one path segment per call."""
+        c, p = self.clctx, self.params
+        if self.iteration == 0:
+            c.updateParams(p)
+            c.enqueueResetKernel(p)
+            c.enqueueRayGenKernel(p)
+            c.enqueueNextVertexKernel(p)
+            c.enqueueBsdfSampleKernel(p)
+            c.enqueueNextVertexKernel(p)
+            c.enqueueBsdfSampleKernel(p)
+            c.enqueueSplatPreviewKernel(p)
+        else:
+            c.enqueueRayGenKernel(p)
+            c.enqueueNextVertexKernel(p)
+            c.enqueueBsdfSampleKernel(p)
+            c.enqueueSplatKernel(p)
+        c.enqueuePostprocessKernel(p)
+        c.finishQueue()
+        self.iteration += 1
 
     def _num_pixels(self):
         tp = getattr(self.clctx, "tilePixels", None)

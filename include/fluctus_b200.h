@@ -87,7 +87,8 @@ enum {
 enum { FLX_OK = 0, FLX_E_INVALID = 10001, FLX_E_NO_DEVICE = 10002, FLX_E_NOT_READY = 10003, FLX_E_NCCL = 10004, FLX_E_UNSUPPORTED_ARCH = 10005 };
 
 /* kernel ids for flx_get_kernel_ms (reference instrument: CLContext::checkTracingPerf, clcontext.cpp:673-701) */
-enum { FLX_K_RESET = 0, FLX_K_RAYGEN, FLX_K_EXTRAYS, FLX_K_SHADOWRAYS, FLX_K_LOGIC, FLX_K_MATERIALS, FLX_K_END_ITERATION, FLX_K_POSTPROCESS, FLX_K_COUNT };
+enum { FLX_K_RESET = 0, FLX_K_RAYGEN, FLX_K_EXTRAYS, FLX_K_SHADOWRAYS, FLX_K_LOGIC, FLX_K_MATERIALS, FLX_K_END_ITERATION, FLX_K_POSTPROCESS,
+       FLX_K_MK_RESET, FLX_K_MK_RAYGEN, FLX_K_MK_NEXT_VERTEX, FLX_K_MK_SAMPLE_BSDF, FLX_K_MK_SPLAT, FLX_K_COUNT };
 
 typedef struct flx_ctx flx_ctx;
 
@@ -127,6 +128,23 @@ int flx_enqueue_materials(flx_ctx *ctx); /* 5 per-type kernels or the single-que
  * preview buffer (a GL PBO in the reference; here read back with flx_read_preview). */
 int flx_enqueue_postprocess(flx_ctx *ctx);
 int flx_read_preview(flx_ctx *ctx, float *rgba, size_t n_pixels);
+
+/* The reference's other integrator, the "microkernel" path tracer (one path per pixel, a phase word per path): the one
+ * Tracer::renderSingle uses for final frames with an exact sample count per pixel (src/tracer.cpp:95-169) and the
+ * non-wavefront branch of Tracer::update (src/tracer.cpp:267-299).  CLContext::enqueueResetKernel / enqueueRayGenKernel /
+ * enqueueNextVertexKernel / enqueueBsdfSampleKernel / enqueueSplatKernel / enqueueSplatPreviewKernel (clcontext.hpp:34-40;
+ * clcontext.cpp:709-750; kernels src/mk_reset.cl, mk_raygen.cl, mk_next_vertex.cl, mk_sample_bsdf.cl, mk_splat.cl,
+ * mk_splat_preview.cl).  Paths 0 .. min(width*height, num_tasks)-1 take part, path g renders pixel g; ray and sample counts
+ * accumulate in the 64-bit stats (reference: atomics on RenderStats).  The path state after every call is the reference's. */
+int flx_enqueue_mk_reset(flx_ctx *ctx);
+int flx_enqueue_mk_raygen(flx_ctx *ctx);
+int flx_enqueue_mk_next_vertex(flx_ctx *ctx);
+int flx_enqueue_mk_sample_bsdf(flx_ctx *ctx);
+int flx_enqueue_mk_splat(flx_ctx *ctx);
+int flx_enqueue_mk_splat_preview(flx_ctx *ctx);
+/* The sample loop of Tracer::renderSingle (src/tracer.cpp:124-150) spp times without host round trips: camera rays,
+ * (maxBounces + 1) x (nextVertex, sampleBsdf), splat, display pass.  Call flx_enqueue_mk_reset first, like the reference. */
+int flx_render_single(flx_ctx *ctx, uint32_t spp);
 
 /* CLContext::enqueueClearWfQueues / enqueueGetCounters / finishQueue / updatePixelIndex / resetPixelIndex /
  * getNumTasks (clcontext.hpp:53-57,71; clcontext.cpp:668-671, 877-906). */

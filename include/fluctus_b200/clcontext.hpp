@@ -89,6 +89,15 @@ class CLContext
     void enqueueWfLogicKernel(const RenderParams &, const bool firstIteration) { verify(flx_enqueue_logic(ctx, firstIteration ? 1 : 0), "enqueueWfLogicKernel"); }
     void enqueueWfMaterialKernels(const RenderParams &) { verify(flx_enqueue_materials(ctx), "enqueueWfMaterialKernels"); }
 
+    // ---- microkernel integrator (clcontext.hpp:35-40; the one Tracer::renderSingle uses, tracer.cpp:95-169)
+    void enqueueResetKernel(const RenderParams &) { verify(flx_enqueue_mk_reset(ctx), "enqueueResetKernel"); }
+    void enqueueRayGenKernel(const RenderParams &) { verify(flx_enqueue_mk_raygen(ctx), "enqueueRayGenKernel"); }
+    void enqueueNextVertexKernel(const RenderParams &) { verify(flx_enqueue_mk_next_vertex(ctx), "enqueueNextVertexKernel"); }
+    void enqueueBsdfSampleKernel(const RenderParams &) { verify(flx_enqueue_mk_sample_bsdf(ctx), "enqueueBsdfSampleKernel"); }
+    void enqueueSplatKernel(const RenderParams &) { verify(flx_enqueue_mk_splat(ctx), "enqueueSplatKernel"); }
+    void enqueueSplatPreviewKernel(const RenderParams &) { verify(flx_enqueue_mk_splat_preview(ctx), "enqueueSplatPreviewKernel"); }
+    void renderSingleLoop(unsigned spp) { verify(flx_render_single(ctx, spp), "renderSingleLoop"); } // new: tracer.cpp:124-150 without host round trips
+
     void enqueuePostprocessKernel(const RenderParams &) { verify(flx_enqueue_postprocess(ctx), "enqueuePostprocessKernel"); } // clcontext.hpp:41
     std::vector<float> readPreview()
     {

@@ -46,6 +46,15 @@ KERNEL_TUS = {
     "mat_ggx_refr": ("REF_TU_MAT_GGX_REFR", []),
     "mat_delta": ("REF_TU_MAT_DELTA", []),
     "postprocess": ("REF_TU_POSTPROCESS", []),  # src/mk_postprocess.cl + src/tonemap.cl (the display pass of the render loop, tracer.cpp:302,447)
+    # the microkernel integrator (src/mk_*.cl; clcontext.cpp:709-750).  sampleBsdf gets every BXDF_USE_* the scene could
+    # need (src/kernel_impl.hpp:376-387; each is also selected by material->type at run time)
+    "mk_reset": ("REF_TU_MK_RESET", []),
+    "mk_raygen": ("REF_TU_MK_RAYGEN", []),
+    "mk_next_vertex": ("REF_TU_MK_NEXT_VERTEX", []),
+    "mk_sample_bsdf": ("REF_TU_MK_SAMPLE_BSDF", ["BXDF_USE_DIFFUSE", "BXDF_USE_GLOSSY", "BXDF_USE_GGX_ROUGH_REFLECTION", "BXDF_USE_IDEAL_REFLECTION",
+                                                 "BXDF_USE_GGX_ROUGH_DIELECTRIC", "BXDF_USE_IDEAL_DIELECTRIC", "BXDF_USE_EMISSIVE"]),
+    "mk_splat": ("REF_TU_MK_SPLAT", []),
+    "mk_splat_preview": ("REF_TU_MK_SPLAT_PREVIEW", []),
 }
 
 VEC_LITERAL = re.compile(r"\((v?float[234]|int2)\)\(")

@@ -28,7 +28,8 @@ class RefBufs(C.Structure):  # oracle/ref_shim/ref_abi.h
                 ("deltaQueue", C.c_void_p), ("tris", C.c_void_p), ("nodes", C.c_void_p), ("indices", C.c_void_p), ("envRGBA", C.c_void_p),
                 ("envW", C.c_int32), ("envH", C.c_int32), ("probTable", C.c_void_p), ("aliasTable", C.c_void_p), ("pdfTable", C.c_void_p),
                 ("materials", C.c_void_p), ("texData", C.c_void_p), ("textures", C.c_void_p), ("params", C.c_void_p),
-                ("currPixelIdx", C.c_void_p), ("numTasks", C.c_uint32), ("firstIteration", C.c_uint32), ("pixelsPreview", C.c_void_p)]
+                ("currPixelIdx", C.c_void_p), ("numTasks", C.c_uint32), ("firstIteration", C.c_uint32), ("pixelsPreview", C.c_void_p),
+                ("stats", C.c_void_p)]
 
 
 QUEUE_FIELDS = ("raygenQueue", "extensionQueue", "shadowQueue", "diffuseQueue", "glossyQueue", "ggxReflQueue", "ggxRefrQueue", "deltaQueue")
@@ -60,6 +61,7 @@ class _CpuContext:
         self.queues = {q: np.zeros(n, np.uint32) for q in QUEUE_FIELDS}
         self.counters = np.zeros(8, np.uint32)
         self.currPixelIdx = np.zeros(1, np.uint32)
+        self.render_stats = np.zeros(4, np.uint32)  # RenderStats {primaryRays, extensionRays, shadowRays, samples}, geom.h:254-260
         self.pixelIdx = 0
         self.params_buf = np.zeros(240, np.uint8)
         self.env_rgba = np.zeros(4, np.float32)
@@ -115,6 +117,7 @@ class _CpuContext:
         b.params, b.currPixelIdx = p(self.params_buf), p(self.currPixelIdx)
         b.numTasks, b.firstIteration = self.NUM_TASKS, first
         b.pixelsPreview = p(self.preview)
+        b.stats = p(self.render_stats)
         return b
 
     def _run(self, name, n, first=0):
@@ -147,6 +150,34 @@ class _CpuContext:
                 self._run(k, self.NUM_TASKS)
         else:
             self._run("mat_all", self.NUM_TASKS)
+
+    # ---- microkernel integrator: NDRange sizes of src/clcontext.cpp:709-750
+    def enqueueResetKernel(self, params=None):
+        self._run("mk_reset", self.width * self.height)
+
+    def enqueueRayGenKernel(self, params=None):
+        self._run("mk_raygen", self.NUM_TASKS)
+
+    def enqueueNextVertexKernel(self, params=None):
+        self._run("mk_next_vertex", self.NUM_TASKS)
+
+    def enqueueBsdfSampleKernel(self, params=None):
+        self._run("mk_sample_bsdf", self.NUM_TASKS)
+
+    def enqueueSplatKernel(self, params=None):
+        self._run("mk_splat", self.width * self.height)
+
+    def enqueueSplatPreviewKernel(self, params=None):
+        self._run("mk_splat_preview", self.width * self.height)
+
+    def resetStats(self):
+        self.render_stats[:] = 0
+
+    def getStats(self):
+        from fluctus_b200.structs import RenderStats64
+        s = RenderStats64()
+        s.primaryRays, s.extensionRays, s.shadowRays, s.samples = (int(v) for v in self.render_stats)
+        return s
 
     def enqueuePostprocessKernel(self, params=None):
         self._run("postprocess", self.width * self.height)  # NDRange(width*height), src/clcontext.cpp:758

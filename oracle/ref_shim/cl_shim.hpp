@@ -121,6 +121,7 @@ inline float3 operator-(const float3 &a, float s) { return float3(a.x - s, a.y -
 inline float3 operator-(float s, const float3 &a) { return float3(s - a.x, s - a.y, s - a.z); }
 inline float3 operator-(const float3 &a) { return float3(-a.x, -a.y, -a.z); }
 inline float4 operator+(const float4 &a, const float4 &b) { return float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+inline float4 &operator+=(float4 &a, const float4 &b) { a = a + b; return a; } // mk_splat.cl:22
 inline float4 operator*(const float4 &a, float s) { return float4(a.x * s, a.y * s, a.z * s, a.w * s); }
 inline float4 operator/(const float4 &a, float s) { return float4(a.x / s, a.y / s, a.z / s, a.w / s); }
 inline float2 operator*(const float2 &a, float s) { return float2(a.x * s, a.y * s); }
@@ -186,7 +187,8 @@ inline void vstore4(const float4 &v, size_t off, float *p)
 
 // ---------------------------------------------------------------- work-item ids, atomics
 static thread_local size_t g_shim_gid = 0;
-inline size_t get_global_id(int) { return g_shim_gid; }
+static thread_local size_t g_shim_gid1 = 0; // second NDRange dimension: only the microkernel reset/splat kernels are launched 2-D (clcontext.cpp:712,742,748)
+inline size_t get_global_id(int dim) { return dim == 1 ? g_shim_gid1 : g_shim_gid; }
 inline size_t get_local_id(int) { return g_shim_gid % 32; }
 
 #ifdef SHIM_PARALLEL

@@ -29,5 +29,6 @@ typedef struct
     uint32_t numTasks;
     uint32_t firstIteration;
     float *pixelsPreview;   /* W*H float4, output of the post-process kernel (GL PBO in the reference) */
+    uint32_t *stats;        /* RenderStats {primaryRays, extensionRays, shadowRays, samples} (geom.h:254-260), microkernel integrator */
 } RefBufs;
 #endif

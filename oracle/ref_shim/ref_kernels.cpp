@@ -35,6 +35,18 @@ namespace
 #include "wf_mat_delta.cl"
 #elif defined(REF_TU_POSTPROCESS)
 #include "mk_postprocess.cl"
+#elif defined(REF_TU_MK_RESET)
+#include "mk_reset.cl"
+#elif defined(REF_TU_MK_RAYGEN)
+#include "mk_raygen.cl"
+#elif defined(REF_TU_MK_NEXT_VERTEX)
+#include "mk_next_vertex.cl"
+#elif defined(REF_TU_MK_SAMPLE_BSDF)
+#include "mk_sample_bsdf.cl"
+#elif defined(REF_TU_MK_SPLAT)
+#include "mk_splat.cl"
+#elif defined(REF_TU_MK_SPLAT_PREVIEW)
+#include "mk_splat_preview.cl"
 #else
 #error "no REF_TU_* selected"
 #endif
@@ -52,6 +64,12 @@ namespace
 #define QL(b) ((QueueCounters *)(b)->queueLens)
 #define P(b) ((RenderParams *)(b)->params)
 #define MATARGS(b, q) T(b), QL(b), (b)->q, (b)->extensionQueue, (Material *)(b)->materials, (b)->texData, (TexDescriptor *)(b)->textures, P(b), (b)->numTasks
+
+// microkernel integrator (src/mk_*.cl).  reset / splat / splatPreview are launched as a 2-D NDRange(width, height)
+// (clcontext.cpp:712,742,748): work-item g of the flattened range is (g % width, g / width); the others are 1-D.
+#define REF_2D(g) g_shim_gid = (size_t)(g) % P(b)->width; g_shim_gid1 = (size_t)(g) / P(b)->width
+#define REF_1D(g) g_shim_gid = (size_t)(g); g_shim_gid1 = 0
+#define ST(b) ((RenderStats *)(b)->stats)
 
 extern "C"
 {
@@ -115,6 +133,39 @@ extern "C"
     {
         REF_LOOP { g_shim_gid = (size_t)g; process(b->pixels, b->denoiserAlbedo, b->denoiserNormal, b->pixelsPreview, b->denoiserAlbedo, b->denoiserNormal, P(b), b->numTasks); }
     }
+#elif defined(REF_TU_MK_RESET)
+    void REF_NAME(mk_reset)(const RefBufs *b, size_t begin, size_t end)
+    {
+        REF_LOOP { REF_2D(g); reset(T(b), b->pixels, b->denoiserAlbedo, b->denoiserNormal, P(b), b->numTasks); }
+    }
+#elif defined(REF_TU_MK_RAYGEN)
+    void REF_NAME(mk_raygen)(const RefBufs *b, size_t begin, size_t end) { REF_LOOP { REF_1D(g); genCameraRays(T(b), P(b), b->numTasks); } }
+#elif defined(REF_TU_MK_NEXT_VERTEX)
+    void REF_NAME(mk_next_vertex)(const RefBufs *b, size_t begin, size_t end)
+    {
+        const shim_image img = {b->envW, b->envH, b->envRGBA};
+        REF_LOOP
+        {
+            REF_1D(g);
+            nextVertex(T(b), (Material *)b->materials, b->texData, (TexDescriptor *)b->textures, b->denoiserNormal, (Triangle *)b->tris, (GPUNode *)b->nodes,
+                       b->indices, P(b), ST(b), &img, b->pdfTable, b->numTasks);
+        }
+    }
+#elif defined(REF_TU_MK_SAMPLE_BSDF)
+    void REF_NAME(mk_sample_bsdf)(const RefBufs *b, size_t begin, size_t end)
+    {
+        const shim_image img = {b->envW, b->envH, b->envRGBA};
+        REF_LOOP
+        {
+            REF_1D(g);
+            sampleBsdf(T(b), b->denoiserAlbedo, (Material *)b->materials, b->texData, (TexDescriptor *)b->textures, &img, b->probTable, b->aliasTable,
+                       b->pdfTable, (Triangle *)b->tris, (GPUNode *)b->nodes, b->indices, P(b), ST(b), b->numTasks);
+        }
+    }
+#elif defined(REF_TU_MK_SPLAT)
+    void REF_NAME(mk_splat)(const RefBufs *b, size_t begin, size_t end) { REF_LOOP { REF_2D(g); splat(T(b), b->pixels, P(b), ST(b), b->numTasks); } }
+#elif defined(REF_TU_MK_SPLAT_PREVIEW)
+    void REF_NAME(mk_splat_preview)(const RefBufs *b, size_t begin, size_t end) { REF_LOOP { REF_2D(g); splatPreview(T(b), b->pixels, P(b), b->numTasks); } }
 #elif defined(REF_TU_MAT_DELTA)
     void REF_NAME(mat_delta)(const RefBufs *b, size_t begin, size_t end) { REF_LOOP { g_shim_gid = (size_t)g; wavefrontDelta(MATARGS(b, deltaQueue)); } }
 #endif

@@ -10,6 +10,7 @@
  *     port_raygen    src/wf_raygen.cl:4-97         port_mat_*     src/wf_mat_*.cl + src/bxdf_partial.cl:19-153
  *     port_ext       src/wf_extrays.cl:5-36 + src/bvh.cl:234-310 + src/intersect.cl:41-155
  *     port_shadow    src/wf_shadowrays.cl:6-37 + src/bvh.cl:312-373
+ *     port_mk_*      the microkernel integrator, src/mk_reset.cl, mk_raygen.cl, mk_next_vertex.cl, mk_sample_bsdf.cl, mk_splat.cl, mk_splat_preview.cl
  * Built-ins that OpenCL leaves implementation-defined are pinned exactly as in oracle/ref_shim/cl_shim.hpp
  * (include/flx_math.h for sin/cos/tan/atan2/acos/pow; IEEE 1/x, sqrt; dot = (xx'+yy')+zz'; normalize(0) = 0).
  *
@@ -905,6 +906,234 @@ void NAME(mat_glossy)(const RefBufs *b, size_t begin, size_t end) { material_ker
 void NAME(mat_ggx_refl)(const RefBufs *b, size_t begin, size_t end) { material_kernel(b, begin, end, b->ggxReflQueue, &QL(b)->ggxRefl, BXDF_GGX_REFL); }
 void NAME(mat_ggx_refr)(const RefBufs *b, size_t begin, size_t end) { material_kernel(b, begin, end, b->ggxRefrQueue, &QL(b)->ggxRefr, BXDF_GGX_REFR); }
 void NAME(mat_delta)(const RefBufs *b, size_t begin, size_t end) { material_kernel(b, begin, end, b->deltaQueue, &QL(b)->delta, BXDF_IDEAL_REFL | BXDF_IDEAL_DIEL); }
+
+/* ================================================================ microkernel integrator (src/mk_*.cl)
+ * The reference's other integrator: one path per pixel, a phase word per path (geom.h:184-193).  Launch shapes as in
+ * clcontext.cpp:709-750: reset / splat / splatPreview over width*height, the rest over numTasks; all clamp to
+ * limit = min(width * height, numTasks).  The 2-D kernels compute gid = x + y * width, i.e. the flattened index. */
+enum { MK_RT_NEXT_VERTEX = 0, MK_SAMPLE_BSDF = 1, MK_SPLAT_SAMPLE = 4, MK_GENERATE_CAMERA_RAY = 5 };
+#define S_PHASE 46
+static inline uint32_t mk_limit(const RefBufs *b) { const RenderParams *p = (const RenderParams *)b->params; const uint32_t n = p->width * p->height; return n < b->numTasks ? n : b->numTasks; }
+
+void NAME(mk_reset)(const RefBufs *b, size_t begin, size_t end)                                         /* mk_reset.cl:4-43 */
+{
+    Tasks t = tasks_of(b); const uint32_t limit = mk_limit(b);
+    LOOP
+    {
+        const uint32_t gid = (uint32_t)g_;
+        if (gid >= limit) continue;
+        for (int c = 0; c < 4; c++) { b->pixels[4 * (size_t)gid + c] = 0.0f; b->denoiserNormal[4 * (size_t)gid + c] = 0.0f; }
+        b->denoiserAlbedo[4 * (size_t)gid + 0] = 0.1f; b->denoiserAlbedo[4 * (size_t)gid + 1] = 0.1f; b->denoiserAlbedo[4 * (size_t)gid + 2] = 0.1f; b->denoiserAlbedo[4 * (size_t)gid + 3] = 0.0f;
+        wu(t, S_PHASE, gid, MK_GENERATE_CAMERA_RAY);
+        wv(t, S_EI, gid, V1(0.0f)); wv(t, S_T, gid, V1(1.0f)); wu(t, S_LEN, gid, 0); wu(t, S_LSPEC, gid, 1); wf(t, S_LPDFW, gid, 1.0f);
+        wu(t, S_FIRSTDIFF, gid, 0); wu(t, S_SEED, gid, gid);
+    }
+}
+
+void NAME(mk_raygen)(const RefBufs *b, size_t begin, size_t end)                                        /* mk_raygen.cl:5-63 */
+{
+    const RenderParams *p = (const RenderParams *)b->params; Tasks t = tasks_of(b); const uint32_t limit = mk_limit(b);
+    LOOP
+    {
+        const uint32_t gid = (uint32_t)g_;
+        if (gid >= limit) continue;
+        if (ru(t, S_PHASE, gid) != MK_GENERATE_CAMERA_RAY) continue;
+        uint32_t seed = ru(t, S_SEED, gid);
+        float x = (float)(gid % p->width), y = (float)(gid / p->width);
+        x += rnd(&seed); y += rnd(&seed);
+        const float NDCx = x / p->width, NDCy = y / p->height;
+        float SCRx = 2.0f * NDCx - 1.0f, SCRy = 2.0f * NDCy - 1.0f;
+        SCRx *= (float)p->width / p->height;
+        const float scale = flx_tanf(0.5f * p->camera.fov * 3.14159265358979323846f / 180);
+        SCRx *= scale; SCRy *= scale;
+        v3 rayOrig = F(p->camera.pos);
+        const v3 target = add(add(add(rayOrig, scl(F(p->camera.right), SCRx)), scl(F(p->camera.up), SCRy)), F(p->camera.dir));
+        v3 rayDir = normalize(sub(target, rayOrig));
+        const v3 fp = add(F(p->camera.pos), scl(rayDir, p->camera.focalDist));
+        const float sqrt_r = sqrtf(rnd(&seed)); const float th = FLX_2PI_F * rnd(&seed);
+        const float rx = sqrt_r * flx_cosf(th), ry = sqrt_r * flx_sinf(th);
+        rayOrig = add(rayOrig, lscl(p->worldRadius * p->camera.apertureSize, add(scl(F(p->camera.right), rx), scl(F(p->camera.up), ry))));
+        rayDir = normalize(sub(fp, rayOrig));
+        wv(t, S_ORIG, gid, rayOrig); wv(t, S_DIR, gid, rayDir);
+        wu(t, S_SEED, gid, seed); wu(t, S_PHASE, gid, MK_RT_NEXT_VERTEX);
+    }
+}
+
+void NAME(mk_next_vertex)(const RefBufs *b, size_t begin, size_t end)                                   /* mk_next_vertex.cl:7-123 */
+{
+    const RenderParams *p = (const RenderParams *)b->params; Tasks t = tasks_of(b); const Scene sc = scene_of(b); const uint32_t limit = mk_limit(b);
+    LOOP
+    {
+        const uint32_t gid = (uint32_t)g_;
+        if (gid >= limit) continue;
+        if (ru(t, S_PHASE, gid) != MK_RT_NEXT_VERTEX) continue;
+        const v3 o = rv(t, S_ORIG, gid), d = rv(t, S_DIR, gid);
+        Hit hit = empty_hit(FLT_MAX);
+        bvh_intersect(o, d, &hit, (const Triangle *)b->tris, (const Node *)b->nodes, b->indices, 0);
+        if (p->sampleImpl && p->useAreaLight) intersect_light(&hit, o, d, p);
+        write_hit(t, gid, &hit);
+        uint32_t len = ru(t, S_LEN, gid);
+        atomic_inc(len == 0 ? &b->stats[0] : &b->stats[1]);                                               /* primaryRays : extensionRays */
+        len += 1; wu(t, S_LEN, gid, len);
+        if (hit.i < 0)                                                                                  /* implicit environment sample */
+        {
+            v3 bg = V1(0.0f);
+            if (p->useEnvMap && (len == 1 || p->sampleImpl)) bg = scl(eval_env_dir(&sc, d), p->envMapStrength);
+            float weight = 1.0f;
+            const int lastSpecular = ru(t, S_LSPEC, gid) != 0;
+            if (p->sampleImpl && p->sampleExpl && p->useEnvMap && len > 1 && !lastSpecular)
+            {
+                const float lightPickProb = 1.0f;
+                const float directPdfW = env_map_pdf(&sc, d), actualPdfW = rf(t, S_LPDFW, gid);
+                weight = (actualPdfW * lightPickProb) / (actualPdfW * lightPickProb + directPdfW);
+            }
+            wv(t, S_EI, gid, add(rv(t, S_EI, gid), mul(lscl(weight, rv(t, S_T, gid)), bg)));
+            wu(t, S_PHASE, gid, MK_SPLAT_SAMPLE);
+        }
+        else if (hit.areaLightHit)                                                                      /* implicit area-light sample */
+        {
+            float misWeight = 1.0f;
+            const int lastSpecular = ru(t, S_LSPEC, gid) != 0;
+            if (p->sampleExpl && len > 1 && !lastSpecular)
+            {
+                const float directPdfA = 1.0f / (4.0f * p->areaLight.sizex * p->areaLight.sizey);
+                const float directPdfW = pdf_a_to_w(directPdfA, length(sub(hit.P, o)), dot(normalize(neg(d)), hit.N));
+                const float lightPickProb = 1.0f, lastPdfW = rf(t, S_LPDFW, gid);
+                misWeight = lastPdfW / (lastPdfW + directPdfW * lightPickProb);
+            }
+            wv(t, S_EI, gid, add(rv(t, S_EI, gid), mul(scl(rv(t, S_T, gid), misWeight), F(p->areaLight.E))));
+            wu(t, S_PHASE, gid, MK_SPLAT_SAMPLE);
+        }
+        else
+            wu(t, S_PHASE, gid, MK_SAMPLE_BSDF);
+    }
+}
+
+void NAME(mk_sample_bsdf)(const RefBufs *b, size_t begin, size_t end)                                   /* mk_sample_bsdf.cl:11-197 */
+{
+    const RenderParams *p = (const RenderParams *)b->params; Tasks t = tasks_of(b); const Scene sc = scene_of(b); const uint32_t limit = mk_limit(b);
+    const Triangle *tris = (const Triangle *)b->tris; const Node *nodes = (const Node *)b->nodes;
+    LOOP
+    {
+        const uint32_t gid = (uint32_t)g_;
+        if (gid >= limit) continue;
+        uint32_t seed = ru(t, S_SEED, gid);
+        if (ru(t, S_PHASE, gid) != MK_SAMPLE_BSDF) continue;
+        const v3 rayDir = rv(t, S_DIR, gid);
+        Hit hit = read_hit(t, gid);
+        const Material mat = sc.materials[hit.matId];
+        hit.N = tangent_space_normal(&hit, &mat, &sc);
+        const int backface = dot(hit.N, rayDir) > 0.0f;
+        if (backface) hit.N = scl(hit.N, -1.0f);
+        v3 orig = sub(hit.P, lscl(1e-3f, rayDir));
+        if (p->sampleExpl && !IS_SINGULAR(mat.type))                                                    /* next-event estimation */
+        {
+            const float lightPickProb = 1.0f;
+            if (p->useEnvMap)
+            {
+                v3 L; float directPdfW = 0.0f;
+                sample_env_alias(&sc, rnd(&seed), &L, &directPdfW);
+                const float lenL = 2.0f * p->worldRadius;
+                L = normalize(L);
+                Hit hitL = empty_hit(lenL);
+                if (p->useAreaLight) intersect_light(&hitL, orig, L, p);
+                const int occluded = (hitL.i > -1) || bvh_occluded(orig, L, lenL, tris, nodes, b->indices, 0);
+                atomic_inc(&b->stats[2]);
+                if (!occluded && directPdfW != 0.0f)
+                {
+                    const v3 brdf = bxdf_eval(&hit, &mat, backface, &sc, rayDir, L, 0xfe);
+                    const float cosTh = fmaxf(0.0f, dot(L, hit.N));
+                    const float bsdfPdfW = fmaxf(0.0f, bxdf_pdf(&hit, &mat, backface, &sc, rayDir, L, 0xfe));
+                    float weight = 1.0f;
+                    if (p->sampleImpl) weight = (directPdfW * lightPickProb) / (directPdfW * lightPickProb + bsdfPdfW);
+                    const v3 T = rv(t, S_T, gid);
+                    const v3 envMapLi = scl(eval_env_dir(&sc, L), p->envMapStrength);
+                    const v3 contrib = divs(scl(scl(mul(mul(brdf, T), envMapLi), weight), cosTh), lightPickProb * directPdfW);
+                    wv(t, S_EI, gid, add(rv(t, S_EI, gid), contrib));
+                }
+            }
+            if (p->useAreaLight)
+            {
+                const AreaLight *A = &p->areaLight;
+                const float directPdfA = 1.0f / (4.0f * A->sizex * A->sizey);                           /* sampleAreaLight, utils.cl:226-234 */
+                v3 posL = F(A->pos);
+                const float r1 = 2.0f * rnd(&seed) - 1.0f, r2 = 2.0f * rnd(&seed) - 1.0f;
+                posL = add(posL, lscl(r1 * A->sizex, F(A->right)));
+                posL = add(posL, lscl(r2 * A->sizey, F(A->up)));
+                v3 L = sub(posL, orig);
+                const float lenL = length(L);
+                L = normalize(L);
+                const int occluded = bvh_occluded(orig, L, lenL, tris, nodes, b->indices, 0);
+                atomic_inc(&b->stats[2]);
+                const float cosLight = fmaxf(dot(F(A->N), neg(L)), 0.0f);
+                if (!occluded && cosLight > 0.0f)
+                {
+                    const v3 brdf = bxdf_eval(&hit, &mat, backface, &sc, rayDir, L, 0xfe);
+                    const float cosTh = fmaxf(0.0f, dot(L, hit.N));
+                    const float directPdfW = pdf_a_to_w(directPdfA, lenL, cosLight);
+                    const float bsdfPdfW = fmaxf(0.0f, bxdf_pdf(&hit, &mat, backface, &sc, rayDir, L, 0xfe));
+                    float weight = 1.0f;
+                    if (p->sampleImpl) weight = (directPdfW * lightPickProb) / (directPdfW * lightPickProb + bsdfPdfW);
+                    const v3 T = rv(t, S_T, gid);
+                    const v3 contrib = divs(scl(scl(mul(mul(brdf, T), F(A->E)), weight), cosTh), lightPickProb * directPdfW);
+                    wv(t, S_EI, gid, add(rv(t, S_EI, gid), contrib));
+                }
+            }
+        }
+        float contProb = 1.0f;                                                                          /* Russian roulette */
+        const uint32_t len = ru(t, S_LEN, gid);
+        int terminate = (len - 1 >= p->maxBounces);
+        if (terminate && p->useRoulette)
+        {
+            contProb = clampf(luminance(rv(t, S_T, gid)), 0.01f, 0.5f);
+            terminate = (rnd(&seed) > contProb);
+        }
+        float pdfW = 0.0f; v3 newDir = V1(0.0f);   /* the reference leaves both uninitialised; zero is this repo's pinned choice */
+        const v3 bsdf = bxdf_sample(&hit, &mat, backface, &sc, rayDir, &newDir, &pdfW, &seed, 0xfe);
+        const float costh = dot(hit.N, normalize(newDir));
+        pdfW *= contProb;
+        if (pdfW == 0.0f || is_zero(bsdf)) terminate = 1;
+        const v3 newT = divs(scl(mul(rv(t, S_T, gid), bsdf), costh), pdfW);
+        orig = add(hit.P, lscl(1e-4f, newDir));
+        wv(t, S_T, gid, newT); wv(t, S_ORIG, gid, orig); wv(t, S_DIR, gid, newDir); wf(t, S_LPDFW, gid, pdfW); wu(t, S_SEED, gid, seed);
+        wu(t, S_LSPEC, gid, IS_SINGULAR(mat.type) ? 1u : 0u);
+        wu(t, S_PHASE, gid, terminate ? MK_SPLAT_SAMPLE : MK_RT_NEXT_VERTEX);
+    }
+}
+
+void NAME(mk_splat)(const RefBufs *b, size_t begin, size_t end)                                         /* mk_splat.cl:5-41 */
+{
+    Tasks t = tasks_of(b); const uint32_t limit = mk_limit(b);
+    LOOP
+    {
+        const uint32_t gid = (uint32_t)g_;
+        if (gid >= limit) continue;
+        if (ru(t, S_PHASE, gid) != MK_SPLAT_SAMPLE) continue;
+        const v3 Ei = rv(t, S_EI, gid);
+        float color[4] = {Ei.x, Ei.y, Ei.z, 1.0f};
+        float *px = b->pixels + 4 * (size_t)gid;
+        if (px[3] > 0.0f) for (int c = 0; c < 4; c++) color[c] += px[c];
+        for (int c = 0; c < 4; c++) px[c] = color[c];
+        atomic_inc(&b->stats[3]);
+        wv(t, S_EI, gid, V1(0.0f)); wv(t, S_T, gid, V1(1.0f)); wu(t, S_LEN, gid, 0); wu(t, S_FIRSTDIFF, gid, 0);
+        wu(t, S_PHASE, gid, MK_GENERATE_CAMERA_RAY);
+    }
+}
+
+void NAME(mk_splat_preview)(const RefBufs *b, size_t begin, size_t end)                                 /* mk_splat_preview.cl:5-25 */
+{
+    Tasks t = tasks_of(b); const uint32_t limit = mk_limit(b);
+    LOOP
+    {
+        const uint32_t gid = (uint32_t)g_;
+        if (gid >= limit) continue;
+        const v3 Ei = rv(t, S_EI, gid);
+        float *px = b->pixels + 4 * (size_t)gid;
+        px[0] = Ei.x; px[1] = Ei.y; px[2] = Ei.z; px[3] = 0.0f;
+        wv(t, S_EI, gid, V1(0.0f)); wv(t, S_T, gid, V1(1.0f)); wu(t, S_LEN, gid, 0);
+        wu(t, S_PHASE, gid, MK_GENERATE_CAMERA_RAY);
+    }
+}
 
 /* ================================================================ post-process (mk_postprocess.cl:7-55, tonemap.cl:3-26) */
 static v3 uc2_tonemap_func(v3 x)

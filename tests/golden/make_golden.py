@@ -21,6 +21,36 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
         sys.path.insert(0, p)
 
 CASES = ("room_mixed_separate", "room_env_mis", "teapot_c1")
+# the microkernel integrator (src/mk_*.cl) through Tracer::renderSingle's loop: (case, scene/params of which wavefront case, spp)
+MK_CASES = {"mk_room_env_mis": ("room_env_mis", 3), "mk_room_mixed": ("room_mixed_separate", 3)}
+
+
+def run_mk_case(ctx, name, blob_loader=None):
+    """Runs Tracer::renderSingle (src/tracer.cpp:112-150) on `ctx` and returns what the fixture stores: the path state after
+    the first sample's first nextVertex + sampleBsdf, the state after the last splat, accumulator, preview, statistics."""
+    from fluctus_b200 import Tracer
+    from parity_util import mk_stats, setup_context
+    base, spp = MK_CASES[name]
+    scene, params, env, n, _ = build_case(base, blob_loader)
+    tr = setup_context(ctx, scene, params, env)
+    ctx.resetStats()
+    ctx.updateParams(params)
+    ctx.enqueueResetKernel(params)
+    out = {}
+    for s in range(spp):
+        ctx.enqueueRayGenKernel(params)
+        for bounce in range(params.maxBounces + 1):
+            ctx.enqueueNextVertexKernel(params)
+            ctx.enqueueBsdfSampleKernel(params)
+            if s == 0 and bounce == 0:
+                ctx.finishQueue()
+                out["tasks_first_bounce"] = ctx.readTasks()
+        ctx.enqueueSplatKernel(params)
+        ctx.enqueuePostprocessKernel(params)
+        ctx.finishQueue()
+    out.update(tasks_end=ctx.readTasks(), pixels=ctx.readPixels(), preview=ctx.readPreview(), stats=np.array(mk_stats(ctx), np.int64),
+               n_live=np.array([min(params.width * params.height, n)]))
+    return out
 
 
 def build_case(name, blob_loader=None):
@@ -79,6 +109,12 @@ def main():
             out.update(scene_tris=scene.tris.view(np.uint8), scene_indices=scene.indices, scene_nodes=scene.nodes.view(np.uint8), scene_materials=scene.materials.view(np.uint8))
         np.savez_compressed(fix, **out)
         print(name, os.path.getsize(fix), "bytes;", dict(zip(("primary", "extension", "shadow"), out["stats"])))
+    for name, (base, spp) in MK_CASES.items():
+        n = build_case(base)[3]
+        out = run_mk_case(RefContext(n), name)
+        fix = os.path.join(HERE, name + ".npz")
+        np.savez_compressed(fix, **out)
+        print(name, os.path.getsize(fix), "bytes;", dict(zip(("primary", "extension", "shadow", "samples"), out["stats"])))
 
 
 if __name__ == "__main__":

@@ -99,3 +99,86 @@ def run_lockstep(gpu, cpu, scene, params, iterations, env=None, check_every=1, e
                 same_in = np.array_equal(pg.view(np.uint32), pc.view(np.uint32))
                 compare_pixels(vg, vc, what + " (post-processed preview)", rtol=1e-5, exact_rgb=same_in)
     return tg, tc
+
+
+# ---------------------------------------------------------------------------------------------- microkernel integrator
+def compare_mk_tasks(a, b, what, n_live):
+    """a (ours), b (reference kernels): (64, N) path-state dumps of the microkernel integrator; bit-exact on every slot,
+    phase word included, for the first n_live = min(W*H, N) paths.  Two masks, both for values the reference leaves
+    UNINITIALISED: when a BSDF sampler rejects its direction without writing pdfW (src/glossy.cl:58-59; declared without
+    initialiser at src/mk_sample_bsdf.cl:160) the path terminates, but the garbage still lands in lastPdfW and, through
+    T * bsdf * costh / pdfW with bsdf = 0, in T (0, -0 or NaN).  This repo pins pdfW = 0 there, so lastPdfW is skipped where
+    ours is exactly 0 and T where ours is all zero/NaN.  Nothing reads either before it is overwritten."""
+    n = n_live
+    bad = []
+    ta = a[SLOT.T:SLOT.T + 3, :n].view(np.float32)
+    t_tainted = (np.isnan(ta) | (ta == 0)).all(axis=0)
+    for s in USED_SLOTS + [SLOT.PHASE]:
+        x, y = a[s, :n], b[s, :n]
+        neq = x != y
+        if s == SLOT.LAST_PDF_W:
+            neq &= ~(x.view(np.float32) == 0)
+        if SLOT.T <= s < SLOT.T + 3:
+            neq &= ~t_tainted
+        if neq.any():
+            xf, yf = x.view(np.float32), y.view(np.float32)
+            neq &= ~(np.isnan(xf) & np.isnan(yf))
+        if neq.any():
+            idx = np.flatnonzero(neq)
+            nm = "phase" if s == SLOT.PHASE else slot_name(s)
+            bad.append("%s: %d/%d differ, first path %d: %r vs %r (0x%08x vs 0x%08x)" % (
+                nm, len(idx), n, idx[0], x.view(np.float32)[idx[0]], y.view(np.float32)[idx[0]], x[idx[0]], y[idx[0]]))
+    assert not bad, "%s: microkernel path state differs\n  " % what + "\n  ".join(bad)
+
+
+def mk_stats(ctx):
+    s = ctx.getStats()
+    return (int(s.primaryRays) & 0xffffffff, int(s.extensionRays) & 0xffffffff, int(s.shadowRays) & 0xffffffff, int(s.samples) & 0xffffffff)
+
+
+def run_mk_lockstep(gpu, cpu, scene, params, spp, env=None, check_every=1, interactive=False):
+    """Drive two contexts through the reference's microkernel loop -- Tracer::renderSingle (src/tracer.cpp:112-150), or with
+    interactive=True the preview + progressive calls of Tracer::update (src/tracer.cpp:267-299) -- kernel by kernel,
+    comparing the complete path state after every enqueue and the accumulator after every splat."""
+    tg, tc = setup_context(gpu, scene, params, env), setup_context(cpu, scene, params, env)
+    n_live = min(params.width * params.height, gpu.getNumTasks())
+    for c in (gpu, cpu):
+        c.resetStats()
+    step = [0]
+
+    def both(method, what):
+        for c in (gpu, cpu):
+            getattr(c, method)(params)
+            c.finishQueue()
+        step[0] += 1
+        if step[0] % check_every == 0 or method.startswith("enqueueSplat"):
+            compare_mk_tasks(gpu.readTasks(), cpu.readTasks(), what, n_live)
+
+    def splat(method, what):
+        both(method, what)
+        pg, pc = gpu.readPixels(), cpu.readPixels()
+        compare_pixels(pg, pc, what, exact_rgb=True)  # path g owns pixel g: no atomics, so bit-exact
+        both("enqueuePostprocessKernel", what + " display pass")
+        compare_pixels(gpu.readPreview(), cpu.readPreview(), what + " (post-processed preview)", exact_rgb=True)
+
+    both("enqueueResetKernel", "after mk reset")
+    if interactive:
+        both("enqueueRayGenKernel", "preview raygen")
+        for seg in range(2):
+            both("enqueueNextVertexKernel", "preview nextVertex %d" % seg)
+            both("enqueueBsdfSampleKernel", "preview sampleBsdf %d" % seg)
+        splat("enqueueSplatPreviewKernel", "preview splat")
+        for it in range(spp):
+            both("enqueueRayGenKernel", "update %d raygen" % it)
+            both("enqueueNextVertexKernel", "update %d nextVertex" % it)
+            both("enqueueBsdfSampleKernel", "update %d sampleBsdf" % it)
+            splat("enqueueSplatKernel", "update %d splat" % it)
+    else:
+        for s in range(spp):
+            both("enqueueRayGenKernel", "sample %d raygen" % s)
+            for bounce in range(params.maxBounces + 1):
+                both("enqueueNextVertexKernel", "sample %d bounce %d nextVertex" % (s, bounce))
+                both("enqueueBsdfSampleKernel", "sample %d bounce %d sampleBsdf" % (s, bounce))
+            splat("enqueueSplatKernel", "sample %d splat" % s)
+    assert mk_stats(gpu) == mk_stats(cpu), "ray/sample statistics differ: %r vs %r" % (mk_stats(gpu), mk_stats(cpu))
+    return tg, tc

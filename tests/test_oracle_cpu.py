@@ -10,7 +10,7 @@ from fluctus_b200 import EnvMapData, SceneData, Tracer, make_params
 from fluctus_b200.scene import build_bvh, make_room_scene, room_params
 
 from conftest import scene_blob
-from parity_util import run_lockstep, setup_context, compare_tasks, compare_pixels
+from parity_util import run_lockstep, run_mk_lockstep, setup_context, compare_tasks, compare_mk_tasks, compare_pixels
 
 from oracle.oracle_host import PortContext, RefContext, port_available, ref_available
 
@@ -118,3 +118,62 @@ def test_port_matches_golden(name):
     compare_pixels(ctx.readPixels(), z["pixels"], name, exact_rgb=True)
     compare_pixels(ctx.readPreview(), z["preview"], name + " preview", exact_rgb=True)
     assert [tr.stats[k] for k in ("primaryRays", "extensionRays", "shadowRays")] == list(z["stats"])
+
+
+# ---------------------------------------------------------------------------------------------- microkernel integrator (src/mk_*.cl)
+@needs_ref
+@needs_port
+def test_port_mk_matches_reference_kernels_all_bsdfs():
+    scene = make_room_scene(materials="mixed", textured=True, n_blobs=8)
+    W, H = 48, 32
+    params = room_params(scene, W, H, max_bounces=5)
+    run_mk_lockstep(PortContext(W * H), RefContext(W * H), scene, params, spp=4)
+
+
+@needs_ref
+@needs_port
+@pytest.mark.parametrize("area", [False, True])
+def test_port_mk_matches_reference_kernels_env_map(area):
+    scene = open_room()
+    W, H = 40, 24
+    params = room_params(scene, W, H, max_bounces=4, use_env_map=True, use_area_light=area, env_map_strength=2.0)
+    run_mk_lockstep(PortContext(W * H), RefContext(W * H), scene, params, spp=3, env=synthetic_env())
+
+
+@needs_ref
+@needs_port
+def test_port_mk_matches_reference_kernels_interactive_roulette_sampling_modes_and_short_task_buffer():
+    """Tracer::update's preview + progressive calls (src/tracer.cpp:267-299); NUM_TASKS < width*height renders only the first
+    NUM_TASKS pixels (limit = min(width*height, numTasks), e.g. src/mk_raygen.cl:9)."""
+    scene = make_room_scene(materials="mixed")
+    for impl, expl, rr, n in ((True, False, False, 1200), (False, True, False, 700), (True, True, True, 1000)):
+        params = room_params(scene, 40, 30, max_bounces=3, sample_impl=impl, sample_expl=expl, use_roulette=rr)
+        run_mk_lockstep(PortContext(n), RefContext(n), scene, params, spp=6, interactive=True)
+
+
+@needs_ref
+@needs_port
+def test_port_mk_matches_reference_kernels_conference():
+    scene = SceneData.load_blob(scene_blob("conference"))
+    from bench_configs import conference_params
+    params = conference_params(scene, 64, 36)
+    params.maxBounces = 4
+    run_mk_lockstep(PortContext(64 * 36), RefContext(64 * 36), scene, params, spp=2, check_every=2)
+
+
+@needs_port
+@pytest.mark.parametrize("name", ["mk_room_env_mis", "mk_room_mixed"])
+def test_port_mk_matches_golden(name):
+    """Golden vectors written by the reference's own mk_*.cl kernels compiled for the host (tests/golden/make_golden.py)."""
+    from golden.make_golden import MK_CASES, build_case, run_mk_case
+    path = os.path.join(GOLDEN, name + ".npz")
+    if not os.path.exists(path):
+        pytest.fail("golden fixture %s is missing" % path)
+    z = np.load(path)
+    out = run_mk_case(PortContext(build_case(MK_CASES[name][0], scene_blob)[3]), name, scene_blob)
+    n_live = int(z["n_live"][0])
+    compare_mk_tasks(out["tasks_first_bounce"], z["tasks_first_bounce"], name + " after the first bounce", n_live)
+    compare_mk_tasks(out["tasks_end"], z["tasks_end"], name + " at the end", n_live)
+    compare_pixels(out["pixels"], z["pixels"], name, exact_rgb=True)
+    compare_pixels(out["preview"], z["preview"], name + " preview", exact_rgb=True)
+    assert list(out["stats"]) == list(z["stats"])

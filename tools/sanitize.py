@@ -37,6 +37,14 @@ def main():
                 tr.update()
                 pix = ctx.readPixels()
                 assert np.isfinite(pix).all()
+                # the microkernel integrator on the same context: renderSingle call by call and fused, then the interactive loop
+                tr.renderSingle(2)
+                tr.renderSingle(2, fused=True)
+                tr.iteration = 0
+                tr.updateMicrokernel()
+                tr.updateMicrokernel()
+                pix = ctx.readPixels()
+                assert np.isfinite(pix).all()
     print("SANITIZE_RUN_OK")
 
 
