@@ -13,6 +13,7 @@
 #include <string>
 #include <vector>
 
+#include "flx_bvh_build.cuh"
 #include "flx_kernels.cuh"
 #include "flx_mk.cuh"
 #include "flx_trace_persistent.cuh"
@@ -804,6 +805,120 @@ int flx_upload_scene(flx_ctx *ctx, const flx_Triangle *tris, uint32_t n_tris, co
     ctx->treeletNodes = rp.treeletNodes;
     ctx->sceneReady = true;
     return 0;
+}
+
+// ---- GPU hierarchy builder (flx_bvh_build.cuh): stands in for `new SBVH(&tris, mode)` / BVH::m_nodes + m_indices
+// (src/scene.cpp:574-590, src/sbvh.cpp:4-73) when build time matters more than tree quality
+int flx_build_bvh(flx_ctx *ctx, const flx_Triangle *tris, uint32_t n_tris, uint32_t max_leaf, flx_Node *nodes_out, uint32_t nodes_capacity, uint32_t *n_nodes_out,
+                  uint32_t *indices_out, float *build_ms)
+{
+    if (!ctx)
+        return FLX_E_INVALID;
+    REQUIRE(tris && nodes_out && n_nodes_out && indices_out, "flx_build_bvh: null array");
+    REQUIRE(n_tris > 0 && n_tris < 0x40000000u, "flx_build_bvh: triangle count out of range");
+    REQUIRE(max_leaf >= 1 && max_leaf <= 255, "flx_build_bvh: max_leaf must be in 1..255 (nPrims is a byte, src/bvhnode.hpp:58)");
+    CU(cudaSetDevice(ctx->device));
+    const uint32_t n = n_tris, total = 2u * n - 1u;
+    BvhBuild b;
+    memset(&b, 0, sizeof b);
+    b.n = n;
+    b.maxLeaf = max_leaf;
+    flx_Triangle *dTris = nullptr;
+    void *sortTemp = nullptr;
+    size_t sortBytes = 0;
+    std::vector<void *> owned;
+    auto release = [&]() {
+        for (void *p : owned)
+            cudaFree(p);
+    };
+#define BALLOC(ptr, count)                                                                                                                                      \
+    do                                                                                                                                                         \
+    {                                                                                                                                                          \
+        void *p_ = nullptr;                                                                                                                                    \
+        cudaError_t e_ = cudaMalloc(&p_, std::max<size_t>((size_t)(count) * sizeof(*(ptr)), 16));                                                              \
+        if (e_ != cudaSuccess)                                                                                                                                 \
+        {                                                                                                                                                      \
+            release();                                                                                                                                         \
+            return fail(ctx, (int)e_, "flx_build_bvh: cudaMalloc failed: %s", cudaGetErrorString(e_));                                                         \
+        }                                                                                                                                                      \
+        owned.push_back(p_);                                                                                                                                   \
+        (ptr) = reinterpret_cast<decltype(ptr)>(p_);                                                                                                           \
+    } while (0)
+    BALLOC(dTris, n);
+    BALLOC(b.keys, n);
+    BALLOC(b.keysSorted, n);
+    BALLOC(b.bmin, total);
+    BALLOC(b.bmax, total);
+    BALLOC(b.primMin, n);
+    BALLOC(b.primMax, n);
+    BALLOC(b.parent, total);
+    BALLOC(b.children, n);
+    BALLOC(b.range, n);
+    BALLOC(b.cost, total);
+    BALLOC(b.size, total);
+    BALLOC(b.collapsed, total); // indexed by node id in k_bvh_emit; leaves are never collapsed
+    BALLOC(b.visits, n);
+    BALLOC(b.sceneBounds, 6);
+    BALLOC(b.nodesOut, total);
+    BALLOC(b.indicesOut, n);
+    b.tris = dTris;
+    cub::DeviceRadixSort::SortKeys(nullptr, sortBytes, b.keys, b.keysSorted, (int)n, 0, 62, ctx->stream);
+    {
+        unsigned char *t = nullptr;
+        BALLOC(t, sortBytes);
+        sortTemp = t;
+    }
+#undef BALLOC
+    cudaStream_t st = ctx->stream;
+    int rc = 0;
+    auto cu = [&](cudaError_t e, const char *what) {
+        if (e != cudaSuccess && rc == 0)
+            rc = fail(ctx, (int)e, "flx_build_bvh: %s failed: %s", what, cudaGetErrorString(e));
+    };
+    cu(cudaMemcpyAsync(dTris, tris, (size_t)n * sizeof(flx_Triangle), cudaMemcpyHostToDevice, st), "triangle upload");
+    cu(cudaStreamSynchronize(st), "triangle upload");
+    cu(cudaEventRecord(ctx->evStart, st), "event");
+    const uint32_t boundsInit[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
+    cu(cudaMemcpyAsync(b.sceneBounds, boundsInit, sizeof boundsInit, cudaMemcpyHostToDevice, st), "bounds init");
+    cu(cudaMemsetAsync(b.parent, 0xff, (size_t)total * sizeof(int), st), "memset");
+    cu(cudaMemsetAsync(b.visits, 0, (size_t)n * sizeof(uint32_t), st), "memset");
+    cu(cudaMemsetAsync(b.collapsed, 0, (size_t)total * sizeof(uint32_t), st), "memset");
+    const unsigned gridN = (n + FLX_BVH_BLOCK - 1) / FLX_BVH_BLOCK, gridT = (total + FLX_BVH_BLOCK - 1) / FLX_BVH_BLOCK;
+    if (rc == 0)
+    {
+        k_bvh_prims<<<gridN, FLX_BVH_BLOCK, 0, st>>>(b);
+        k_bvh_morton<<<gridN, FLX_BVH_BLOCK, 0, st>>>(b);
+        cu(cub::DeviceRadixSort::SortKeys(sortTemp, sortBytes, b.keys, b.keysSorted, (int)n, 0, 62, st), "radix sort");
+        if (n > 1)
+            k_bvh_hierarchy<<<gridN, FLX_BVH_BLOCK, 0, st>>>(b);
+        k_bvh_fit<<<gridN, FLX_BVH_BLOCK, 0, st>>>(b);
+        k_bvh_emit<<<gridT, FLX_BVH_BLOCK, 0, st>>>(b);
+        cu(cudaGetLastError(), "kernel launch");
+        cu(cudaEventRecord(ctx->evStop, st), "event");
+    }
+    uint32_t nNodes = 0;
+    if (rc == 0)
+    {
+        cu(cudaMemcpyAsync(&nNodes, b.size, sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "size read-back");
+        cu(cudaStreamSynchronize(st), "build");
+    }
+    if (rc == 0 && nNodes > nodes_capacity)
+        rc = fail(ctx, FLX_E_INVALID, "flx_build_bvh: %u nodes do not fit the caller's %u", nNodes, nodes_capacity);
+    if (rc == 0)
+    {
+        cu(cudaMemcpyAsync(nodes_out, b.nodesOut, (size_t)nNodes * sizeof(flx_Node), cudaMemcpyDeviceToHost, st), "node read-back");
+        cu(cudaMemcpyAsync(indices_out, b.indicesOut, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "index read-back");
+        cu(cudaStreamSynchronize(st), "read-back");
+        *n_nodes_out = nNodes;
+        if (build_ms)
+        {
+            float ms = 0.0f;
+            cu(cudaEventElapsedTime(&ms, ctx->evStart, ctx->evStop), "event");
+            *build_ms = ms;
+        }
+    }
+    release();
+    return rc;
 }
 
 int flx_upload_envmap(flx_ctx *ctx, const float *rgb, int32_t w, int32_t h, const float *prob, const int32_t *alias, const float *pdf)

@@ -1,0 +1,284 @@
+// flx_bvh_build.cuh -- GPU construction of the acceleration structure the traversal stages consume.
+//
+// The reference builds its hierarchy on the CPU (src/bvh.cpp:205-407 full-sweep SAH, src/sbvh.cpp:4-449 SBVH; seconds per
+// scene) and hands CLContext::uploadSceneData two arrays: `Node[]` (48 B, depth-first order, left child = self + 1,
+// rightChild / iStart union, parent, nPrims; src/bvhnode.hpp:50-59, flattened by src/sbvh.cpp:52-73) and the u32 index list.
+// This builder produces THE SAME FORMAT in a few milliseconds, entirely on the device, so it can stand in for `new SBVH(...)`
+// wherever build time matters more than tree quality (interactive edits, first frame):
+//
+//   1. k_bvh_prims      per-triangle box + centroid, scene centroid bounds (block reduction + ordered-int atomics)
+//   2. k_bvh_morton     64-bit keys: 30-bit Morton code of the box centre << 32 | triangle index  (unique => no tie handling)
+//   3. radix sort       cub::DeviceRadixSort::SortKeys, bits 0..62 (library call: a plain sort, not a path kernel)
+//   4. k_bvh_hierarchy  binary radix tree over the sorted keys, one thread per internal node (Karras 2012)
+//   5. k_bvh_fit        bottom-up, second arriver proceeds: boxes, subtree SAH cost with the reference's constants
+//                       (costBox = costTri = 1, src/bvh.hpp:72-73; leaf = area * n, inner = 2 * area + children,
+//                       src/sbvh.cpp:115,129), collapse to a leaf when n <= maxLeaf and the leaf is not dearer
+//                       (the reference's rule, src/sbvh.cpp:133), and the size of every surviving subtree
+//   6. k_bvh_emit       every surviving node computes its depth-first index by walking to the root
+//                       (left child: +1, right child: +1 + size(left sibling)) and writes its 48-byte record;
+//                       leaves of a radix tree cover contiguous key ranges, so the index list IS the sorted key list.
+//
+// Everything is deterministic (unique keys, fixed association order, no float atomics), so the CPU restatement in
+// oracle/bvh_oracle.c reproduces the node and index arrays bit for bit.
+#pragma once
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include "flx_device.cuh"
+
+#define FLX_BVH_BLOCK 256
+
+struct BvhBuild
+{
+    const flx_Triangle *tris;
+    uint32_t n;
+    uint32_t maxLeaf;
+    unsigned long long *keys, *keysSorted;
+    float4 *bmin, *bmax;   // node boxes; node ids: internal i -> i (0 .. n-2), leaf j (sorted position) -> n-1+j
+    float4 *primMin, *primMax; // per triangle, by triangle index
+    int *parent;           // per node id
+    int2 *children;        // per internal node: node ids
+    uint2 *range;          // per internal node: first, last sorted position
+    float *cost;           // per node id: SAH cost of the subtree as finally built
+    uint32_t *size;        // per node id: nodes of the surviving subtree (1 for leaves and collapsed nodes)
+    uint32_t *collapsed;   // per internal node
+    uint32_t *visits;      // per internal node: arrival counter of the bottom-up pass
+    uint32_t *sceneBounds; // 6 ordered ints: centroid min xyz, max xyz
+    flx_Node *nodesOut;
+    uint32_t *indicesOut;
+};
+
+FLX_DEV uint32_t float_to_ordered(float f)
+{
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+FLX_DEV float ordered_to_float(uint32_t o) { return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o); }
+FLX_DEV float half_area(float4 lo, float4 hi)
+{
+    const float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
+    return (dx * dy + dy * dz) + dz * dx;
+}
+
+__global__ void __launch_bounds__(FLX_BVH_BLOCK) k_bvh_prims(const BvhBuild b)
+{
+    __shared__ float s_red[6][FLX_BVH_BLOCK / 32];
+    const uint32_t i = blockIdx.x * FLX_BVH_BLOCK + threadIdx.x;
+    float c[6] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
+    if (i < b.n)
+    {
+        const float4 *q = reinterpret_cast<const float4 *>(b.tris + i);
+        const float4 p0 = __ldg(q), p1 = __ldg(q + 3), p2 = __ldg(q + 6);
+        const float4 lo = make_float4(fminf(fminf(p0.x, p1.x), p2.x), fminf(fminf(p0.y, p1.y), p2.y), fminf(fminf(p0.z, p1.z), p2.z), 0.0f);
+        const float4 hi = make_float4(fmaxf(fmaxf(p0.x, p1.x), p2.x), fmaxf(fmaxf(p0.y, p1.y), p2.y), fmaxf(fmaxf(p0.z, p1.z), p2.z), 0.0f);
+        b.primMin[i] = lo;
+        b.primMax[i] = hi;
+        c[0] = c[3] = (lo.x + hi.x) * 0.5f;
+        c[1] = c[4] = (lo.y + hi.y) * 0.5f;
+        c[2] = c[5] = (lo.z + hi.z) * 0.5f;
+    }
+#pragma unroll
+    for (int k = 0; k < 6; k++)
+    {
+        float v = c[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+        {
+            const float w = __shfl_xor_sync(0xffffffffu, v, o);
+            v = k < 3 ? fminf(v, w) : fmaxf(v, w);
+        }
+        if ((threadIdx.x & 31) == 0)
+            s_red[k][threadIdx.x >> 5] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 6)
+    {
+        const int k = threadIdx.x;
+        float v = s_red[k][0];
+        for (int w = 1; w < FLX_BVH_BLOCK / 32; w++)
+            v = k < 3 ? fminf(v, s_red[k][w]) : fmaxf(v, s_red[k][w]);
+        if (k < 3)
+            atomicMin(b.sceneBounds + k, float_to_ordered(v));
+        else
+            atomicMax(b.sceneBounds + k, float_to_ordered(v));
+    }
+}
+
+FLX_DEV uint32_t spread10(uint32_t v) // 10 bits -> every third bit
+{
+    v = (v | (v << 16)) & 0x030000ffu;
+    v = (v | (v << 8)) & 0x0300f00fu;
+    v = (v | (v << 4)) & 0x030c30c3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+FLX_DEV uint32_t quantize10(float c, float lo, float hi)
+{
+    const float ext = hi - lo;
+    if (!(ext > 0.0f))
+        return 0u;
+    const float q = ((c - lo) / ext) * 1024.0f;
+    return (uint32_t)fminf(fmaxf(q, 0.0f), 1023.0f);
+}
+
+__global__ void __launch_bounds__(FLX_BVH_BLOCK) k_bvh_morton(const BvhBuild b)
+{
+    const uint32_t i = blockIdx.x * FLX_BVH_BLOCK + threadIdx.x;
+    if (i >= b.n)
+        return;
+    const float lox = ordered_to_float(b.sceneBounds[0]), loy = ordered_to_float(b.sceneBounds[1]), loz = ordered_to_float(b.sceneBounds[2]);
+    const float hix = ordered_to_float(b.sceneBounds[3]), hiy = ordered_to_float(b.sceneBounds[4]), hiz = ordered_to_float(b.sceneBounds[5]);
+    const float4 lo = b.primMin[i], hi = b.primMax[i];
+    const uint32_t x = quantize10((lo.x + hi.x) * 0.5f, lox, hix), y = quantize10((lo.y + hi.y) * 0.5f, loy, hiy), z = quantize10((lo.z + hi.z) * 0.5f, loz, hiz);
+    const uint32_t m = (spread10(x) << 2) | (spread10(y) << 1) | spread10(z);
+    b.keys[i] = ((unsigned long long)m << 32) | (unsigned long long)i;
+}
+
+// length of the common prefix of keys i and j, -1 when j is outside the array (Karras 2012, section 4; keys are unique)
+FLX_DEV int key_delta(const unsigned long long *keys, int n, int i, int j)
+{
+    if (j < 0 || j >= n)
+        return -1;
+    return __clzll((long long)(keys[i] ^ keys[j]));
+}
+
+__global__ void __launch_bounds__(FLX_BVH_BLOCK) k_bvh_hierarchy(const BvhBuild b)
+{
+    const int n = (int)b.n;
+    const int i = (int)(blockIdx.x * FLX_BVH_BLOCK + threadIdx.x);
+    if (i >= n - 1)
+        return;
+    const unsigned long long *k = b.keysSorted;
+    const int d = key_delta(k, n, i, i + 1) - key_delta(k, n, i, i - 1) > 0 ? 1 : -1;
+    const int dmin = key_delta(k, n, i, i - d);
+    int lmax = 2;
+    while (key_delta(k, n, i, i + lmax * d) > dmin)
+        lmax <<= 1;
+    int l = 0;
+    for (int t = lmax >> 1; t >= 1; t >>= 1)
+        if (key_delta(k, n, i, i + (l + t) * d) > dmin)
+            l += t;
+    const int j = i + l * d;
+    const int dnode = key_delta(k, n, i, j);
+    int s = 0;
+    for (int t = (l + 1) >> 1;; t = (t + 1) >> 1) // ceil(l / 2), ceil(l / 4), ... , 1
+    {
+        if (key_delta(k, n, i, i + (s + t) * d) > dnode)
+            s += t;
+        if (t == 1)
+            break;
+    }
+    const int gamma = i + s * d + min(d, 0);
+    const int first = min(i, j), last = max(i, j);
+    const int left = (first == gamma) ? (n - 1 + gamma) : gamma;
+    const int right = (last == gamma + 1) ? (n - 1 + gamma + 1) : (gamma + 1);
+    b.children[i] = make_int2(left, right);
+    b.range[i] = make_uint2((uint32_t)first, (uint32_t)last);
+    b.parent[left] = i;
+    b.parent[right] = i;
+    if (i == 0)
+        b.parent[0] = -1;
+}
+
+__global__ void __launch_bounds__(FLX_BVH_BLOCK) k_bvh_fit(const BvhBuild b)
+{
+    const uint32_t j = blockIdx.x * FLX_BVH_BLOCK + threadIdx.x;
+    if (j >= b.n)
+        return;
+    const uint32_t tri = (uint32_t)(b.keysSorted[j] & 0xffffffffull);
+    b.indicesOut[j] = tri;
+    int node = (int)(b.n - 1 + j);
+    {
+        const float4 lo = b.primMin[tri], hi = b.primMax[tri];
+        b.bmin[node] = lo;
+        b.bmax[node] = hi;
+        b.cost[node] = half_area(lo, hi) * 1.0f;
+        b.size[node] = 1u;
+    }
+    if (b.n == 1)
+        return;
+    while (true)
+    {
+        __threadfence();
+        const int p = b.parent[node];
+        if (p < 0)
+            break;
+        if (atomicAdd(b.visits + p, 1u) == 0u)
+            break; // the sibling's thread will do the parent
+        __threadfence();
+        const int2 ch = b.children[p];
+        const volatile float4 *vmin = b.bmin, *vmax = b.bmax;
+        const float4 lmin = make_float4(vmin[ch.x].x, vmin[ch.x].y, vmin[ch.x].z, 0.0f), lmax = make_float4(vmax[ch.x].x, vmax[ch.x].y, vmax[ch.x].z, 0.0f);
+        const float4 rmin = make_float4(vmin[ch.y].x, vmin[ch.y].y, vmin[ch.y].z, 0.0f), rmax = make_float4(vmax[ch.y].x, vmax[ch.y].y, vmax[ch.y].z, 0.0f);
+        const float4 lo = make_float4(fminf(lmin.x, rmin.x), fminf(lmin.y, rmin.y), fminf(lmin.z, rmin.z), 0.0f);
+        const float4 hi = make_float4(fmaxf(lmax.x, rmax.x), fmaxf(lmax.y, rmax.y), fmaxf(lmax.z, rmax.z), 0.0f);
+        const float area = half_area(lo, hi);
+        const uint2 r = b.range[p];
+        const uint32_t count = r.y - r.x + 1u;
+        const volatile float *vcost = b.cost;
+        const volatile uint32_t *vsize = b.size;
+        const float leafCost = area * (float)count;                        // parentArea * refs * costTri, sbvh.cpp:129
+        const float innerCost = (area * 2.0f + vcost[ch.x]) + vcost[ch.y]; // nodeSAH + children, sbvh.cpp:115,204
+        const bool collapse = count <= b.maxLeaf && leafCost <= innerCost;
+        b.bmin[p] = lo;
+        b.bmax[p] = hi;
+        b.cost[p] = collapse ? leafCost : innerCost;
+        b.size[p] = collapse ? 1u : 1u + vsize[ch.x] + vsize[ch.y];
+        b.collapsed[p] = collapse ? 1u : 0u;
+        node = p;
+    }
+}
+
+__global__ void __launch_bounds__(FLX_BVH_BLOCK) k_bvh_emit(const BvhBuild b)
+{
+    const uint32_t id = blockIdx.x * FLX_BVH_BLOCK + threadIdx.x;
+    const uint32_t total = 2u * b.n - 1u;
+    if (id >= total)
+        return;
+    const bool isLeafNode = id >= b.n - 1u;
+    // depth-first index: climb to the root; a collapsed ancestor means this node does not exist in the output
+    uint32_t dfs = 0, parentDfsDelta = 0;
+    bool first = true;
+    int node = (int)id;
+    while (true)
+    {
+        const int p = b.parent[node];
+        if (p < 0)
+            break;
+        if (b.collapsed[p])
+            return;
+        const int2 ch = b.children[p];
+        const uint32_t step = (ch.x == node) ? 1u : 1u + b.size[ch.x];
+        if (first)
+        {
+            parentDfsDelta = step;
+            first = false;
+        }
+        dfs += step;
+        node = p;
+    }
+    flx_Node out;
+    const float4 lo = b.bmin[id], hi = b.bmax[id];
+    out.bmin.x = lo.x; out.bmin.y = lo.y; out.bmin.z = lo.z; out.bmin.w = 0.0f;
+    out.bmax.x = hi.x; out.bmax.y = hi.y; out.bmax.z = hi.z; out.bmax.w = 0.0f;
+    out.parent = first ? -1 : (int)(dfs - parentDfsDelta);
+    for (int k = 0; k < 7; k++)
+        out._pad[k] = 0;
+    if (isLeafNode)
+    {
+        out.iStartOrRightChild = id - (b.n - 1u);
+        out.nPrims = 1;
+    }
+    else if (b.collapsed[id])
+    {
+        const uint2 r = b.range[id];
+        out.iStartOrRightChild = r.x;
+        out.nPrims = (uint8_t)(r.y - r.x + 1u);
+    }
+    else
+    {
+        out.iStartOrRightChild = dfs + 1u + b.size[b.children[id].x];
+        out.nPrims = 0;
+    }
+    b.nodesOut[dfs] = out;
+}

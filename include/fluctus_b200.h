@@ -105,6 +105,17 @@ int flx_upload_scene(flx_ctx *ctx, const flx_Triangle *tris, uint32_t n_tris, co
                      const flx_Node *nodes, uint32_t n_nodes, const flx_Material *materials, uint32_t n_materials,
                      const flx_TexDescriptor *tex_desc, uint32_t n_tex, const uint8_t *tex_data, size_t tex_bytes);
 
+/* GPU hierarchy builder (new).  Stands in for the reference's CPU builders -- `new SBVH(&tris, mode)` /
+ * `new BVH(...)` in Scene's initHierarchy (src/scene.cpp:574-590; src/sbvh.cpp:4-449, src/bvh.cpp:205-407) -- and returns THE
+ * SAME two arrays they produce (BVH::m_nodes, m_indices): Node[] in depth-first order with left child = self + 1
+ * (src/bvhnode.hpp:50-59, src/sbvh.cpp:52-73) and the u32 triangle index list, ready for flx_upload_scene.  LBVH (Morton
+ * order + binary radix tree) with a bottom-up SAH collapse into leaves of at most max_leaf triangles (reference MaxLeafElems
+ * = 8, src/bvh.hpp:70); no spatial splits, so every triangle is referenced exactly once (n_indices = n_tris).  Milliseconds
+ * instead of seconds; the tree is of lower quality than the reference's SBVH (DESIGN.md 4.5 has the measured trade-off).
+ * nodes_out must hold nodes_capacity >= 2 * n_tris - 1 records in the worst case; build_ms (may be NULL) = device time. */
+int flx_build_bvh(flx_ctx *ctx, const flx_Triangle *tris, uint32_t n_tris, uint32_t max_leaf, flx_Node *nodes_out, uint32_t nodes_capacity,
+                  uint32_t *n_nodes_out, uint32_t *indices_out /* n_tris */, float *build_ms);
+
 /* CLContext::createEnvMap (clcontext.hpp:79; clcontext.cpp:467-511): rgb is w*h*3 floats; tables are w*h entries. */
 int flx_upload_envmap(flx_ctx *ctx, const float *rgb, int32_t w, int32_t h, const float *prob, const int32_t *alias, const float *pdf);
 

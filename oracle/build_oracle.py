@@ -9,18 +9,20 @@ import tempfile
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(HERE, "liboracle.so")
 SRC = os.path.join(HERE, "wf_oracle.c")
+BVH_SRC = os.path.join(HERE, "bvh_oracle.c")  # CPU restatement of the GPU hierarchy builder
 INC = os.path.join(os.path.dirname(HERE), "include")
 
 
 def build(force=False):
-    deps = [SRC, os.path.join(INC, "flx_math.h"), os.path.join(HERE, "ref_shim", "ref_abi.h"), __file__]
+    deps = [SRC, BVH_SRC, os.path.join(INC, "flx_math.h"), os.path.join(HERE, "ref_shim", "ref_abi.h"), __file__]
     if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= max(os.path.getmtime(d) for d in deps):
         return OUT
     with tempfile.TemporaryDirectory() as tmp:
         common = ["gcc", "-std=gnu11", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-Wall", "-Wno-unused-function", "-Wno-unused-variable",
                   "-I", INC, "-I", HERE, "-c", SRC]
-        objs = [os.path.join(tmp, "serial.o"), os.path.join(tmp, "par.o")]
-        cmds = [common + ["-O2", "-o", objs[0]], common + ["-O3", "-march=x86-64-v3", "-fopenmp", "-DPORT_PARALLEL", "-o", objs[1]]]
+        objs = [os.path.join(tmp, "serial.o"), os.path.join(tmp, "par.o"), os.path.join(tmp, "bvh.o")]
+        cmds = [common + ["-O2", "-o", objs[0]], common + ["-O3", "-march=x86-64-v3", "-fopenmp", "-DPORT_PARALLEL", "-o", objs[1]],
+                common[:-1] + [BVH_SRC, "-O2", "-o", objs[2]]]
         for c in cmds + [["gcc", "-shared", "-fopenmp", "-o", OUT] + objs + ["-lm"]]:
             r = subprocess.run(c, capture_output=True, text=True)
             if r.returncode != 0:

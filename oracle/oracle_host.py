@@ -250,3 +250,19 @@ class RefContext(_CpuContext):
 class PortContext(_CpuContext):
     LIB = PORT_LIB
     PREFIX = "port_"
+
+
+def build_lbvh(tris, max_leaf=8):
+    """CPU restatement (oracle/bvh_oracle.c) of the GPU hierarchy builder flx_build_bvh -> (nodes, indices) in the
+    reference's Node[] / index-list format."""
+    from fluctus_b200.structs import NODE_DTYPE
+    lib = C.CDLL(PORT_LIB)
+    n = len(tris)
+    nodes = np.zeros(max(2 * n - 1, 1), NODE_DTYPE)
+    indices = np.zeros(n, np.uint32)
+    n_nodes = C.c_uint32()
+    lib.port_build_lbvh.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p]
+    rc = lib.port_build_lbvh(tris.ctypes.data, n, int(max_leaf), nodes.ctypes.data, C.byref(n_nodes), indices.ctypes.data)
+    if rc != 0:
+        raise RuntimeError("port_build_lbvh failed (%d)" % rc)
+    return nodes[:n_nodes.value].copy(), indices

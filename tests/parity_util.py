@@ -182,3 +182,43 @@ def run_mk_lockstep(gpu, cpu, scene, params, spp, env=None, check_every=1, inter
             splat("enqueueSplatKernel", "sample %d splat" % s)
     assert mk_stats(gpu) == mk_stats(cpu), "ray/sample statistics differ: %r vs %r" % (mk_stats(gpu), mk_stats(cpu))
     return tg, tc
+
+
+# ---------------------------------------------------------------------------------------------- hierarchy checks
+def validate_bvh(nodes, indices, tris, max_leaf=8, unique_refs=True):
+    """Structural contract of the reference's flattened hierarchy (src/bvhnode.hpp:50-59, src/sbvh.cpp:52-73) that the traversal
+    relies on: depth-first order with left child = self + 1, rightChild inside the array, parent links, every node box
+    containing its children / triangles, leaves of 1..max_leaf references, and (for builders without spatial splits) every
+    triangle referenced exactly once.  Returns (depth, number of leaves, SAH cost normalised by the root area)."""
+    n = len(nodes)
+    link, nprims, parent = nodes["link"].astype(np.int64), nodes["nPrims"].astype(np.int64), nodes["parent"].astype(np.int64)
+    bmin, bmax = nodes["bmin"][:, :3], nodes["bmax"][:, :3]
+    inner = np.flatnonzero(nprims == 0)
+    leaves = np.flatnonzero(nprims > 0)
+    assert len(inner) + 1 == len(leaves), "a full binary tree has one more leaf than inner nodes"
+    left, right = inner + 1, link[inner]
+    assert (right > left).all() and (right < n).all(), "rightChild out of range"
+    assert parent[0] == -1 and (parent[left] == inner).all() and (parent[right] == inner).all(), "parent links"
+    for ch in (left, right):
+        assert (bmin[ch] >= bmin[inner]).all() and (bmax[ch] <= bmax[inner]).all(), "child box not inside its parent's"
+    assert (nprims[leaves] <= max_leaf).all()
+    assert (link[leaves] + nprims[leaves] <= len(indices)).all()
+    starts = link[leaves]
+    order = np.argsort(starts)
+    assert (starts[order][1:] == (starts[order] + nprims[leaves][order])[:-1]).all() and starts[order][0] == 0, "leaf ranges must tile the index list"
+    assert starts[order][-1] + nprims[leaves][order][-1] == len(indices)
+    if unique_refs:
+        assert len(indices) == len(tris) and np.array_equal(np.sort(indices), np.arange(len(tris), dtype=indices.dtype)), "every triangle exactly once"
+    # triangles inside their leaf's box (not for spatial-split builders: an SBVH reference is clipped to its leaf, src/sbvh.cpp:268-330)
+    if unique_refs:
+        leaf_of_ref = np.repeat(leaves[order], nprims[leaves][order])
+        P = np.stack([tris["v0"]["p"][:, :3], tris["v1"]["p"][:, :3], tris["v2"]["p"][:, :3]], axis=1)[indices]  # (refs, 3 vertices, xyz)
+        assert (P.min(axis=1) >= bmin[leaf_of_ref]).all() and (P.max(axis=1) <= bmax[leaf_of_ref]).all(), "triangle outside its leaf box"
+    # depth (iteratively, parents precede children in DFS order) and SAH cost with the reference's constants
+    depth = np.zeros(n, np.int64)
+    for i in range(1, n):
+        depth[i] = depth[parent[i]] + 1
+    d = (bmax - bmin).astype(np.float64)
+    area = d[:, 0] * d[:, 1] + d[:, 1] * d[:, 2] + d[:, 2] * d[:, 0]
+    sah = (2.0 * area[inner].sum() + (area[leaves] * nprims[leaves]).sum()) / max(area[0], 1e-300)
+    return int(depth.max()), len(leaves), float(sah)

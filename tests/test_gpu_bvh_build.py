@@ -1,0 +1,80 @@
+"""GPU tests of the hierarchy builder flx_build_bvh: node and index arrays bit-identical to the CPU
+restatement (oracle/bvh_oracle.c) on procedural, reference-asset and degenerate inputs; and the wavefront path rendering
+through the built tree stays in bit-for-bit lockstep with the oracle rendering through the same tree."""
+import numpy as np
+import pytest
+
+from fluctus_b200 import CLContext, SceneData
+from fluctus_b200.scene import make_room_scene, room_params
+
+from conftest import scene_blob
+from parity_util import run_lockstep, validate_bvh
+from test_bvh_build_cpu import teapot_scene, tri_soup
+from test_gpu_parity import oracle_ctx
+
+pytestmark = pytest.mark.gpu
+
+
+def same_tree(gpu_nodes, gpu_idx, cpu_nodes, cpu_idx, what):
+    assert np.array_equal(gpu_idx, cpu_idx), "%s: index lists differ" % what
+    assert len(gpu_nodes) == len(cpu_nodes), "%s: %d vs %d nodes" % (what, len(gpu_nodes), len(cpu_nodes))
+    a, b = gpu_nodes.view(np.uint8).reshape(len(gpu_nodes), 48), cpu_nodes.view(np.uint8).reshape(len(cpu_nodes), 48)
+    bad = np.flatnonzero((a != b).any(axis=1))
+    assert len(bad) == 0, "%s: %d nodes differ, first %d: %r vs %r" % (what, len(bad), bad[0], gpu_nodes[bad[0]], cpu_nodes[bad[0]])
+
+
+def build_both(tris, max_leaf=8):
+    from oracle.oracle_host import build_lbvh
+    with CLContext(1024) as gpu:
+        nodes, idx, ms = gpu.buildBVH(tris, max_leaf)
+    cn, ci = build_lbvh(tris, max_leaf)
+    return nodes, idx, cn, ci, ms
+
+
+@pytest.mark.parametrize("max_leaf", [1, 8])
+def test_builder_matches_the_cpu_restatement(max_leaf):
+    for name, scene in (("room", make_room_scene(materials="mixed", n_blobs=8)), ("teapot", teapot_scene())):
+        nodes, idx, cn, ci, _ = build_both(scene.tris, max_leaf)
+        same_tree(nodes, idx, cn, ci, "%s max_leaf=%d" % (name, max_leaf))
+        validate_bvh(nodes, idx, scene.tris, max_leaf)
+
+
+def test_builder_edge_cases():
+    rng = np.random.default_rng(5)
+    cases = {"one": rng.uniform(-1, 1, (1, 3, 3)), "two": rng.uniform(-1, 1, (2, 3, 3)), "identical": np.repeat(rng.uniform(-1, 1, (1, 3, 3)), 37, axis=0),
+             "ragged": rng.uniform(-1, 1, (1001, 3, 3)) * 1e-3 + rng.uniform(-50, 50, (1001, 1, 3))}
+    flat = rng.uniform(-1, 1, (200, 3, 3))
+    flat[:, :, 2] = 0.25
+    cases["flat"] = flat
+    for name, pts in cases.items():
+        tris = tri_soup(pts.astype(np.float32))
+        nodes, idx, cn, ci, _ = build_both(tris, 4)
+        same_tree(nodes, idx, cn, ci, name)
+
+
+@pytest.mark.parametrize("name", ["conference", "country_kitchen"])
+def test_builder_matches_on_reference_assets(name):
+    scene = SceneData.load_blob(scene_blob(name))
+    nodes, idx, cn, ci, ms = build_both(scene.tris)
+    same_tree(nodes, idx, cn, ci, name)
+    assert ms < 50.0, "build took %.2f ms" % ms  # the reference's SBVH build takes seconds
+
+
+def test_wavefront_through_the_built_tree_is_in_lockstep_with_the_oracle():
+    room = make_room_scene(materials="mixed", textured=True, n_blobs=8)
+    W, H, N = 96, 64, 6144
+    params = room_params(room, W, H, max_bounces=6, separate_queues=True)
+    with CLContext(N) as gpu:
+        nodes, idx, _ = gpu.buildBVH(room.tris)
+        scene = SceneData(room.tris, idx, nodes, room.materials, room.tex_desc, room.tex_data)
+        run_lockstep(gpu, oracle_ctx(N), scene, params, iterations=12)
+
+
+def test_builder_rejects_bad_arguments():
+    from fluctus_b200.clcontext import FluctusError
+    tris = tri_soup(np.zeros((3, 3, 3), np.float32))
+    with CLContext(64) as gpu:
+        with pytest.raises(FluctusError):
+            gpu.buildBVH(tris, max_leaf=0)
+        with pytest.raises(FluctusError):
+            gpu.buildBVH(tris, max_leaf=256)
