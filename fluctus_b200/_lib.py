@@ -65,6 +65,24 @@ _SIGNATURES = {
     "flx_gather_pixels": (C.c_int, [_P, C.c_int, _P]),
     "flx_comm_destroy": (C.c_int, [_P]),
     "flx_device_bytes": (C.c_size_t, [_P]),
+    "flx_io_last_error": (C.c_char_p, []),
+    "flx_scene_load": (C.c_int, [C.c_char_p, C.POINTER(_P)]),
+    "flx_scene_free": (None, [_P]),
+    "flx_scene_num_triangles": (C.c_uint32, [_P]),
+    "flx_scene_num_materials": (C.c_uint32, [_P]),
+    "flx_scene_num_textures": (C.c_uint32, [_P]),
+    "flx_scene_triangles": (_P, [_P]),
+    "flx_scene_materials": (_P, [_P]),
+    "flx_scene_texture_name": (C.c_char_p, [_P, C.c_uint32]),
+    "flx_envmap_load": (C.c_int, [C.c_char_p, C.POINTER(_P)]),
+    "flx_envmap_from_rgb": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(_P)]),
+    "flx_envmap_free": (None, [_P]),
+    "flx_envmap_width": (C.c_int32, [_P]),
+    "flx_envmap_height": (C.c_int32, [_P]),
+    "flx_envmap_rgb": (_P, [_P]),
+    "flx_envmap_prob": (_P, [_P]),
+    "flx_envmap_alias": (_P, [_P]),
+    "flx_envmap_pdf": (_P, [_P]),
 }
 EXPORTS = tuple(_SIGNATURES)
 

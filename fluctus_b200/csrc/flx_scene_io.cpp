@@ -1,0 +1,871 @@
+// flx_scene_io.cpp -- host-side scene input for the C ABI: Wavefront OBJ + MTL, ASCII PLY and Radiance
+// RGBE environment maps into the arrays flx_upload_scene / flx_upload_envmap take, so a caller can go from files to a render
+// without the reference's loaders.  Plain host C++, no device code.
+//
+// What is produced follows the reference (and is checked byte for byte against the reference's own loader code in tests/):
+//   * OBJ/MTL: the reference loads through its vendored tinyobjloader 1.0.x (include/tiny_obj_loader.h) and converts in
+//     Scene::loadObjWithMaterials (src/scene.cpp:191-301): triangle-fan triangulation in file order, matId = material + 1
+//     (0 = the built-in default material, src/scene.cpp:13-26), face normal when any vertex lacks one, t = (u, v, 0), the
+//     custom MTL key `shader` -> BSDF type (src/scene.cpp:171-189), textures numbered in first-use order
+//     (src/scene.cpp:304-321).  Number parsing follows the loader's own decimal reader (tiny_obj_loader.h:463-586: digits
+//     accumulated in a double, fraction digits scaled by a table / pow(10, -k), exponent through pow(5, e) and ldexp, then
+//     rounded to float) -- NOT strtod, whose results differ in the last bit.
+//   * PLY: Scene::loadPlyModel (src/scene.cpp:422-553): ASCII, element/property header, x y z [nx ny nz], faces of 3 or 4.
+//   * RGBE: src/rgbe/rgbe.cpp:135-194 (header), 286-416 (run-length scanlines), 95-107 (rgbe -> float); importance tables:
+//     EnvironmentMap::computeProbabilities, src/envmap.cpp:31-114 (luminance * sin(theta), pdf with mean 1, Vose's alias
+//     method on two LIFO stacks).
+// Image decoding (textures) is not done here: the reference uses DevIL, which is not available; callers decode the named
+// files themselves and pass RGBA8 to flx_upload_scene.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "fluctus_b200.h"
+
+namespace
+{
+thread_local std::string g_io_error;
+
+// ---- numbers the way the reference's OBJ loader reads them (tiny_obj_loader.h:463-586)
+bool is_digit(char c) { return c >= '0' && c <= '9'; }
+
+bool read_decimal(const char *s, const char *end, double *out)
+{
+    if (s >= end)
+        return false;
+    double mant = 0.0;
+    int exp10 = 0;
+    bool neg = false, expNeg = false;
+    const char *p = s;
+    if (*p == '+' || *p == '-')
+    {
+        neg = (*p == '-');
+        p++;
+    }
+    else if (!is_digit(*p))
+        return false;
+    int nread = 0;
+    while (p != end && is_digit(*p))
+    {
+        mant *= 10;
+        mant += (int)(*p - '0');
+        p++;
+        nread++;
+    }
+    if (nread == 0)
+        return false;
+    bool haveExp = false;
+    if (p != end)
+    {
+        if (*p == '.')
+        {
+            static const double lut[] = {1.0, 0.1, 0.01, 0.001, 0.0001, 0.00001, 0.000001, 0.0000001};
+            p++;
+            int k = 1;
+            while (p != end && is_digit(*p))
+            {
+                mant += (int)(*p - '0') * (k < 8 ? lut[k] : std::pow(10.0, -k));
+                k++;
+                p++;
+            }
+            haveExp = (p != end) && (*p == 'e' || *p == 'E');
+        }
+        else
+            haveExp = (*p == 'e' || *p == 'E');
+    }
+    if (haveExp)
+    {
+        p++;
+        if (p != end && (*p == '+' || *p == '-'))
+        {
+            expNeg = (*p == '-');
+            p++;
+        }
+        else if (!(p != end && is_digit(*p))) // the loader reads *p even at the end: a NUL or blank, i.e. "not a digit"
+            return false;
+        int digits = 0;
+        while (p != end && is_digit(*p))
+        {
+            exp10 = exp10 * 10 + (int)(*p - '0');
+            p++;
+            digits++;
+        }
+        if (expNeg)
+            exp10 = -exp10;
+        if (digits == 0)
+            return false;
+    }
+    *out = (neg ? -1 : 1) * (exp10 ? std::ldexp(mant * std::pow(5.0, exp10), exp10) : mant);
+    return true;
+}
+
+float read_float(const char *&tok, double dflt = 0.0)
+{
+    tok += std::strspn(tok, " \t");
+    const char *end = tok + std::strcspn(tok, " \t\r");
+    double v = dflt;
+    read_decimal(tok, end, &v);
+    tok = end;
+    return (float)v;
+}
+
+bool is_space(char c) { return c == ' ' || c == '\t'; }
+bool is_eol(char c) { return c == '\r' || c == '\n' || c == '\0'; }
+
+// getline that accepts \n, \r\n and \r (tiny_obj_loader.h safeGetline)
+bool next_line(std::istream &in, std::string &line)
+{
+    line.clear();
+    if (in.peek() == EOF)
+        return false;
+    std::streambuf *sb = in.rdbuf();
+    for (;;)
+    {
+        const int c = sb->sbumpc();
+        if (c == '\n')
+            return true;
+        if (c == '\r')
+        {
+            if (sb->sgetc() == '\n')
+                sb->sbumpc();
+            return true;
+        }
+        if (c == EOF)
+        {
+            if (line.empty())
+                in.setstate(std::ios::eofbit);
+            return true;
+        }
+        line += (char)c;
+    }
+}
+
+struct Corner
+{
+    int v, vt, vn;
+};
+int fix_index(int idx, int n) { return idx > 0 ? idx - 1 : (idx == 0 ? 0 : n + idx); } // 1-based, negative = relative
+
+Corner read_corner(const char *&tok, int nv, int nvn, int nvt) // i, i/j, i//k, i/j/k
+{
+    Corner c{-1, -1, -1};
+    c.v = fix_index(std::atoi(tok), nv);
+    tok += std::strcspn(tok, "/ \t\r");
+    if (*tok != '/')
+        return c;
+    tok++;
+    if (*tok == '/')
+    {
+        tok++;
+        c.vn = fix_index(std::atoi(tok), nvn);
+        tok += std::strcspn(tok, "/ \t\r");
+        return c;
+    }
+    c.vt = fix_index(std::atoi(tok), nvt);
+    tok += std::strcspn(tok, "/ \t\r");
+    if (*tok != '/')
+        return c;
+    tok++;
+    c.vn = fix_index(std::atoi(tok), nvn);
+    tok += std::strcspn(tok, "/ \t\r");
+    return c;
+}
+
+struct MtlEntry
+{
+    std::string name, mapKd, mapKs, mapBump;
+    float Kd[3] = {0, 0, 0}, Ks[3] = {0, 0, 0}, Ke[3] = {0, 0, 0};
+    float Ns = 1.0f, Ni = 1.0f; // tiny_obj_loader.h:860-861
+    std::map<std::string, std::string> other;
+};
+
+std::string first_word(const char *tok) // sscanf("%s")
+{
+    tok += std::strspn(tok, " \t\r\n\v\f");
+    return std::string(tok, std::strcspn(tok, " \t\r\n\v\f"));
+}
+
+// texture statement: options (-bm, -o, ...) are skipped with their arguments, the last bare word is the file name
+// (tiny_obj_loader.h:746-840)
+std::string texture_name(const char *tok)
+{
+    std::string name;
+    while (!is_eol(*tok))
+    {
+        auto opt = [&](const char *o) {
+            const size_t n = std::strlen(o);
+            return std::strncmp(tok, o, n) == 0 && is_space(tok[n]);
+        };
+        auto skip_words = [&](int count) {
+            for (int i = 0; i < count; i++)
+            {
+                tok += std::strspn(tok, " \t");
+                tok += std::strcspn(tok, " \t\r");
+            }
+        };
+        if (opt("-blendu") || opt("-blendv")) { tok += 8; skip_words(1); }
+        else if (opt("-clamp") || opt("-boost")) { tok += 7; skip_words(1); }
+        else if (opt("-bm")) { tok += 4; skip_words(1); }
+        else if (opt("-o") || opt("-s") || opt("-t")) { tok += 3; skip_words(3); }
+        else if (opt("-type")) { tok += 5; skip_words(1); }
+        else if (opt("-imfchan")) { tok += 9; skip_words(1); }
+        else if (opt("-mm")) { tok += 4; skip_words(2); }
+        else
+        {
+            tok += std::strspn(tok, " \t");
+            const size_t len = std::strcspn(tok, " \t\r");
+            name.assign(tok, len);
+            tok += len;
+            tok += std::strspn(tok, " \t");
+        }
+    }
+    return name;
+}
+
+void read_mtl(std::istream &in, std::vector<MtlEntry> &mats, std::map<std::string, int> &byName) // tiny_obj_loader.h:954-1318
+{
+    MtlEntry cur;
+    std::string line;
+    while (next_line(in, line))
+    {
+        if (!line.empty())
+            line = line.substr(0, line.find_last_not_of(" \t") + 1);
+        if (line.empty())
+            continue;
+        const char *tok = line.c_str();
+        tok += std::strspn(tok, " \t");
+        if (*tok == '\0' || *tok == '#')
+            continue;
+        auto key = [&](const char *k) {
+            const size_t n = std::strlen(k);
+            return std::strncmp(tok, k, n) == 0 && is_space(tok[n]);
+        };
+        if (key("newmtl"))
+        {
+            if (!cur.name.empty())
+            {
+                byName.insert(std::make_pair(cur.name, (int)mats.size())); // first definition of a name wins
+                mats.push_back(cur);
+            }
+            cur = MtlEntry();
+            cur.name = first_word(tok + 7);
+            continue;
+        }
+        auto rgb = [&](float *dst) {
+            tok += 2;
+            dst[0] = read_float(tok);
+            dst[1] = read_float(tok);
+            dst[2] = read_float(tok);
+        };
+        if (key("Kd")) { rgb(cur.Kd); continue; }
+        if (key("Ks")) { rgb(cur.Ks); continue; }
+        if (key("Ke")) { rgb(cur.Ke); continue; }
+        if (key("Ni")) { tok += 2; cur.Ni = read_float(tok); continue; }
+        if (key("Ns")) { tok += 2; cur.Ns = read_float(tok); continue; }
+        if (key("map_Kd")) { const std::string n = texture_name(tok + 7); if (!n.empty()) cur.mapKd = n; continue; }
+        if (key("map_Ks")) { const std::string n = texture_name(tok + 7); if (!n.empty()) cur.mapKs = n; continue; }
+        if (key("map_bump")) { const std::string n = texture_name(tok + 9); if (!n.empty()) cur.mapBump = n; continue; }
+        if (key("bump")) { const std::string n = texture_name(tok + 5); if (!n.empty()) cur.mapBump = n; continue; }
+        // statements the loader knows but the reference never reads
+        static const char *ignored[] = {"Ka", "Kt", "Tf", "illum", "d", "Tr", "Pr", "Pm", "Ps", "Pc", "Pcr", "aniso", "anisor", "map_Ka", "map_Ns", "map_d", "disp",
+                                        "map_Pr", "map_Pm", "map_Ps", "map_Ke", "norm"};
+        bool known = false;
+        for (const char *k : ignored)
+            if (key(k))
+                known = true;
+        if (known)
+            continue;
+        // anything else is kept as key -> rest of the line; the reference reads "shader" from here
+        const char *sp = std::strchr(tok, ' ');
+        if (!sp)
+            sp = std::strchr(tok, '\t');
+        if (sp)
+            cur.other.insert(std::make_pair(std::string(tok, sp - tok), std::string(sp + 1)));
+    }
+    byName.insert(std::make_pair(cur.name, (int)mats.size()));
+    mats.push_back(cur);
+}
+
+int shader_type(const std::string &t) // src/scene.cpp:171-189
+{
+    if (t == "diffuse") return FLX_BXDF_DIFFUSE;
+    if (t == "glossy") return FLX_BXDF_GLOSSY;
+    if (t == "rough_reflection") return FLX_BXDF_GGX_ROUGH_REFLECTION;
+    if (t == "ideal_reflection") return FLX_BXDF_IDEAL_REFLECTION;
+    if (t == "rough_dielectric") return FLX_BXDF_GGX_ROUGH_DIELECTRIC;
+    if (t == "ideal_dielectric") return FLX_BXDF_IDEAL_DIELECTRIC;
+    if (t == "emissive") return FLX_BXDF_EMISSIVE;
+    return FLX_BXDF_DIFFUSE;
+}
+
+flx_float3 f3(float x, float y, float z) { return flx_float3{x, y, z, 0.0f}; }
+flx_float3 sub3(flx_float3 a, flx_float3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
+flx_float3 cross3(flx_float3 a, flx_float3 b) { return f3(a.y * b.z - b.y * a.z, b.x * a.z - a.x * b.z, a.x * b.y - a.y * b.x); } // include/math/float3.hpp:121
+flx_float3 normalize3(flx_float3 v)                                                                                                // include/math/float3.hpp:41,45
+{
+    const float inv = 1.f / std::sqrt(v.x * v.x + v.y * v.y + v.z * v.z);
+    return f3(v.x * inv, v.y * inv, v.z * inv);
+}
+} // namespace
+
+struct flx_scene
+{
+    std::vector<flx_Triangle> tris;
+    std::vector<flx_Material> mats;
+    std::vector<std::string> texNames;
+};
+
+struct flx_envmap
+{
+    int w = 0, h = 0;
+    std::vector<float> rgb, prob, pdf;
+    std::vector<int32_t> alias;
+};
+
+namespace
+{
+int tex_index(flx_scene &s, std::string name)
+{
+    if (name.empty())
+        return -1;
+    for (char &c : name)
+        if (c == '\\')
+            c = '/';
+    for (size_t i = 0; i < s.texNames.size(); i++)
+        if (s.texNames[i] == name)
+            return (int)i;
+    s.texNames.push_back(name);
+    return (int)s.texNames.size() - 1;
+}
+
+void push_default_material(flx_scene &s) // src/scene.cpp:13-26
+{
+    flx_Material m;
+    std::memset(&m, 0, sizeof m);
+    m.Kd = f3(0.64f, 0.64f, 0.64f);
+    m.Ni = 1.8f;
+    m.Ns = 700.0f;
+    m.map_Kd = m.map_Ks = m.map_N = -1;
+    m.type = FLX_BXDF_DIFFUSE;
+    s.mats.push_back(m);
+}
+
+flx_Triangle make_triangle(const flx_Vertex v[3], int matId)
+{
+    flx_Triangle t;
+    std::memset(&t, 0, sizeof t);
+    t.v0 = v[0];
+    t.v1 = v[1];
+    t.v2 = v[2];
+    t.matId = matId;
+    return t;
+}
+
+bool load_obj(const std::string &path, flx_scene &s)
+{
+    std::ifstream in(path.c_str());
+    if (!in)
+    {
+        g_io_error = "cannot open " + path;
+        return false;
+    }
+    size_t slash = path.find_last_of("\\");
+    if (slash == std::string::npos)
+        slash = path.find_last_of("/");
+    const std::string folder = path.substr(0, slash + 1);
+
+    std::vector<float> v, vn, vt;
+    std::vector<MtlEntry> mtl;
+    std::map<std::string, int> mtlByName;
+    int material = -1;
+    struct Face
+    {
+        Corner c[3];
+        int material;
+    };
+    std::vector<Face> faces; // fan-triangulated, file order (shape boundaries do not reorder anything)
+    std::string line;
+    std::vector<Corner> poly;
+    while (next_line(in, line))
+    {
+        if (line.empty())
+            continue;
+        const char *tok = line.c_str();
+        tok += std::strspn(tok, " \t");
+        if (*tok == '\0' || *tok == '#')
+            continue;
+        if (tok[0] == 'v' && is_space(tok[1]))
+        {
+            tok += 2;
+            for (int k = 0; k < 3; k++)
+                v.push_back(read_float(tok));
+            continue;
+        }
+        if (tok[0] == 'v' && tok[1] == 'n' && is_space(tok[2]))
+        {
+            tok += 3;
+            for (int k = 0; k < 3; k++)
+                vn.push_back(read_float(tok));
+            continue;
+        }
+        if (tok[0] == 'v' && tok[1] == 't' && is_space(tok[2]))
+        {
+            tok += 3;
+            for (int k = 0; k < 2; k++)
+                vt.push_back(read_float(tok));
+            continue;
+        }
+        if (tok[0] == 'f' && is_space(tok[1]))
+        {
+            tok += 2;
+            tok += std::strspn(tok, " \t");
+            poly.clear();
+            while (!is_eol(*tok))
+            {
+                poly.push_back(read_corner(tok, (int)(v.size() / 3), (int)(vn.size() / 3), (int)(vt.size() / 2)));
+                tok += std::strspn(tok, " \t\r");
+            }
+            for (size_t k = 2; k < poly.size(); k++) // tiny_obj_loader.h:897-920
+                faces.push_back(Face{{poly[0], poly[k - 1], poly[k]}, material});
+            continue;
+        }
+        if (std::strncmp(tok, "usemtl", 6) == 0 && is_space(tok[6]))
+        {
+            const std::string name = first_word(tok + 7);
+            const auto it = mtlByName.find(name);
+            material = it != mtlByName.end() ? it->second : -1;
+            continue;
+        }
+        if (std::strncmp(tok, "mtllib", 6) == 0 && is_space(tok[6]))
+        {
+            std::stringstream names(std::string(tok + 7));
+            std::string one;
+            while (std::getline(names, one, ' ')) // the first file that opens is used (tiny_obj_loader.h:1561-1576)
+            {
+                std::ifstream mf((folder + one).c_str());
+                if (!mf)
+                    continue;
+                read_mtl(mf, mtl, mtlByName);
+                break;
+            }
+            continue;
+        }
+        // g, o, s, t and unknown statements do not affect the triangle list
+    }
+    const bool hasNormals = !vn.empty(), hasTex = !vt.empty();
+    const int nv = (int)(v.size() / 3), nvn = (int)(vn.size() / 3), nvt = (int)(vt.size() / 2);
+    s.tris.reserve(faces.size());
+    for (const Face &f : faces) // src/scene.cpp:229-283
+    {
+        flx_Vertex V[3];
+        bool allNormals = true;
+        for (int k = 0; k < 3; k++)
+        {
+            const Corner &c = f.c[k];
+            if (c.v < 0 || c.v >= nv || c.vn >= nvn || c.vt >= nvt)
+            {
+                g_io_error = path + ": face index out of range";
+                return false;
+            }
+            V[k].p = f3(v[3 * c.v], v[3 * c.v + 1], v[3 * c.v + 2]);
+            if (c.vn < 0 || !hasNormals)
+            {
+                allNormals = false;
+                V[k].n = f3(0, 0, 0);
+            }
+            else
+                V[k].n = f3(vn[3 * c.vn], vn[3 * c.vn + 1], vn[3 * c.vn + 2]);
+            V[k].t = (c.vt > -1 && hasTex) ? f3(vt[2 * c.vt], vt[2 * c.vt + 1], 0.0f) : f3(0, 0, 0);
+        }
+        if (!allNormals)
+            V[0].n = V[1].n = V[2].n = normalize3(cross3(sub3(V[1].p, V[0].p), sub3(V[2].p, V[0].p)));
+        s.tris.push_back(make_triangle(V, f.material + 1));
+    }
+    for (MtlEntry &m : mtl) // src/scene.cpp:286-301
+    {
+        flx_Material o;
+        std::memset(&o, 0, sizeof o);
+        o.Kd = f3(m.Kd[0], m.Kd[1], m.Kd[2]);
+        o.Ks = f3(m.Ks[0], m.Ks[1], m.Ks[2]);
+        o.Ke = f3(m.Ke[0], m.Ke[1], m.Ke[2]);
+        o.Ns = m.Ns;
+        o.Ni = m.Ni;
+        o.map_Kd = tex_index(s, m.mapKd);
+        o.map_Ks = tex_index(s, m.mapKs);
+        o.map_N = tex_index(s, m.mapBump); // map_bump is treated as a normal map
+        o.type = shader_type(m.other["shader"]);
+        s.mats.push_back(o);
+    }
+    return true;
+}
+
+bool load_ply(const std::string &path, flx_scene &s) // src/scene.cpp:422-553, 815-861
+{
+    std::ifstream in(path.c_str());
+    if (!in)
+    {
+        g_io_error = "cannot open " + path;
+        return false;
+    }
+    struct Element
+    {
+        std::string name;
+        int lines;
+        std::vector<std::string> props;
+    };
+    std::vector<Element> elements;
+    std::string line, type = "none";
+    int count = 0;
+    std::vector<std::string> props;
+    while (std::getline(in, line))
+    {
+        std::istringstream iss(line);
+        std::string tok;
+        iss >> tok;
+        if (tok == "element")
+        {
+            elements.push_back(Element{type, count, props});
+            props.clear();
+            iss >> type >> count;
+        }
+        else if (tok == "property")
+        {
+            std::string t, n;
+            iss >> t >> n;
+            props.push_back(n);
+        }
+        else if (tok == "end_header")
+        {
+            elements.push_back(Element{type, count, props});
+            break;
+        }
+    }
+    std::vector<flx_float3> P, N;
+    std::vector<unsigned> F;
+    for (const Element &e : elements)
+        for (int i = 0; i < e.lines; i++)
+        {
+            std::getline(in, line);
+            std::istringstream iss(line);
+            if (e.name == "vertex")
+            {
+                std::map<std::string, float> m;
+                std::string word;
+                for (const std::string &name : e.props)
+                {
+                    iss >> word;
+                    m[name] = (float)std::atof(word.c_str());
+                }
+                P.push_back(f3(m["x"], m["y"], m["z"]));
+                if (m.find("nx") != m.end())
+                    N.push_back(f3(m["nx"], m["ny"], m["nz"]));
+            }
+            else if (e.name == "face")
+            {
+                int n = 0;
+                iss >> n;
+                unsigned a = 0, b = 0, c = 0, d = 0;
+                if (n == 3)
+                {
+                    iss >> a >> b >> c;
+                    F.insert(F.end(), {a, b, c});
+                }
+                else if (n == 4)
+                {
+                    iss >> a >> b >> c >> d;
+                    F.insert(F.end(), {a, b, c, c, d, a});
+                }
+                else
+                {
+                    g_io_error = path + ": only faces of 3 or 4 vertices are supported";
+                    return false;
+                }
+            }
+        }
+    for (size_t f = 0; f + 2 < F.size(); f += 3)
+    {
+        flx_Vertex V[3];
+        std::memset(V, 0, sizeof V);
+        for (int k = 0; k < 3; k++)
+        {
+            if (F[f + k] >= P.size())
+            {
+                g_io_error = path + ": face index out of range";
+                return false;
+            }
+            V[k].p = P[F[f + k]];
+        }
+        if (N.empty())
+            V[0].n = V[1].n = V[2].n = normalize3(cross3(sub3(V[1].p, V[0].p), sub3(V[2].p, V[0].p)));
+        else
+            for (int k = 0; k < 3; k++)
+                V[k].n = N[F[f + k]];
+        s.tris.push_back(make_triangle(V, 0));
+    }
+    return true;
+}
+
+// ---- Radiance RGBE (src/rgbe/rgbe.cpp)
+bool read_rgbe(const std::string &path, flx_envmap &e)
+{
+    FILE *fp = std::fopen(path.c_str(), "rb");
+    if (!fp)
+    {
+        g_io_error = "cannot open " + path;
+        return false;
+    }
+    auto bail = [&](const char *why) {
+        g_io_error = path + ": " + why;
+        std::fclose(fp);
+        return false;
+    };
+    char buf[128];
+    if (!std::fgets(buf, sizeof buf, fp))
+        return bail("empty file");
+    // header lines up to the blank line, then the resolution line (rgbe.cpp:165-193)
+    for (;;)
+    {
+        if (buf[0] == 0 || buf[0] == '\n')
+            return bail("no FORMAT specifier found");
+        if (!std::fgets(buf, sizeof buf, fp))
+            return bail("truncated header");
+        if (buf[0] == '\n')
+            break;
+    }
+    if (!std::fgets(buf, sizeof buf, fp) || std::sscanf(buf, "-Y %d +X %d", &e.h, &e.w) < 2 || e.w <= 0 || e.h <= 0)
+        return bail("missing image size specifier");
+    const int w = e.w, h = e.h;
+    e.rgb.assign((size_t)w * h * 3, 0.0f);
+    auto to_float = [](const unsigned char p[4], float *out) { // rgbe.cpp:95-107
+        if (p[3])
+        {
+            const float f = (float)std::ldexp(1.0, (int)p[3] - (128 + 8));
+            out[0] = p[0] * f;
+            out[1] = p[1] * f;
+            out[2] = p[2] * f;
+        }
+        else
+            out[0] = out[1] = out[2] = 0.0f;
+    };
+    float *data = e.rgb.data();
+    std::vector<unsigned char> scan((size_t)w * 4);
+    auto read_flat = [&](size_t pixels) {
+        unsigned char px[4];
+        for (size_t i = 0; i < pixels; i++, data += 3)
+        {
+            if (std::fread(px, 4, 1, fp) < 1)
+                return false;
+            to_float(px, data);
+        }
+        return true;
+    };
+    if (w < 8 || w > 0x7fff)
+    {
+        if (!read_flat((size_t)w * h))
+            return bail("truncated pixel data");
+        std::fclose(fp);
+        return true;
+    }
+    for (int y = 0; y < h; y++)
+    {
+        unsigned char head[4];
+        if (std::fread(head, 4, 1, fp) < 1)
+            return bail("truncated pixel data");
+        if (head[0] != 2 || head[1] != 2 || (head[2] & 0x80))
+        {
+            // not run-length encoded: this pixel, then everything else flat (rgbe.cpp:317-324)
+            to_float(head, data);
+            data += 3;
+            if (!read_flat((size_t)w * (h - y) - 1))
+                return bail("truncated pixel data");
+            break;
+        }
+        if ((((int)head[2]) << 8 | head[3]) != w)
+            return bail("wrong scanline width");
+        for (int ch = 0; ch < 4; ch++) // each channel separately (rgbe.cpp:331-360)
+        {
+            unsigned char *dst = scan.data() + (size_t)ch * w, *end = dst + w;
+            while (dst < end)
+            {
+                unsigned char two[2];
+                if (std::fread(two, 2, 1, fp) < 1)
+                    return bail("truncated pixel data");
+                if (two[0] > 128)
+                {
+                    int run = two[0] - 128;
+                    if (run == 0 || run > end - dst)
+                        return bail("bad scanline data");
+                    while (run-- > 0)
+                        *dst++ = two[1];
+                }
+                else
+                {
+                    int lit = two[0];
+                    if (lit == 0 || lit > end - dst)
+                        return bail("bad scanline data");
+                    *dst++ = two[1];
+                    if (--lit > 0)
+                    {
+                        if (std::fread(dst, (size_t)lit, 1, fp) < 1)
+                            return bail("truncated pixel data");
+                        dst += lit;
+                    }
+                }
+            }
+        }
+        for (int x = 0; x < w; x++, data += 3)
+        {
+            const unsigned char px[4] = {scan[x], scan[(size_t)w + x], scan[2 * (size_t)w + x], scan[3 * (size_t)w + x]};
+            to_float(px, data);
+        }
+    }
+    std::fclose(fp);
+    return true;
+}
+
+void importance_tables(flx_envmap &e) // src/envmap.cpp:31-114
+{
+    const int w = e.w, h = e.h, n = w * h;
+    std::vector<float> scal((size_t)n);
+    for (int v = 0; v < h; v++)
+    {
+        const float sinTh = std::sin(3.14159265358979323846f * float(v + 0.5f) / float(h));
+        for (int u = 0; u < w; u++)
+        {
+            const float *p = &e.rgb[3 * ((size_t)v * w + u)];
+            const float lum = 0.212671f * p[0] + 0.715160f * p[1] + 0.072169f * p[2];
+            scal[(size_t)v * w + u] = lum * sinTh;
+        }
+    }
+    e.pdf.assign((size_t)n, 0.0f);
+    e.prob.assign((size_t)n, 0.0f);
+    e.alias.assign((size_t)n, 0);
+    float I = 0.0f;
+    for (int i = 1; i < n + 1; i++)
+        I += scal[i - 1] / (w * h);
+    if (I == 0)
+        for (int i = 0; i < n; i++)
+            e.pdf[i] = 1.0f / float(n);
+    else
+        for (int i = 0; i < n; i++)
+            e.pdf[i] = scal[i] / I;
+    // Vose's alias method; both work lists are LIFO, which fixes which of the valid tables comes out
+    std::vector<std::pair<float, int>> small, large;
+    for (int i = 0; i < n; i++)
+        (e.pdf[i] < 1.0f ? small : large).push_back(std::make_pair(e.pdf[i], i));
+    while (!small.empty() && !large.empty())
+    {
+        const std::pair<float, int> l = small.back(), g = large.back();
+        small.pop_back();
+        large.pop_back();
+        e.prob[l.second] = l.first;
+        e.alias[l.second] = g.second;
+        const float pg = (g.first + l.first) - 1.0f;
+        (pg < 1.0f ? small : large).push_back(std::make_pair(pg, g.second));
+    }
+    for (auto &g : large)
+        e.prob[g.second] = 1.0f;
+    for (auto &l : small)
+        e.prob[l.second] = 1.0f;
+}
+
+bool ends_with(const std::string &s, const char *suffix)
+{
+    const size_t n = std::strlen(suffix);
+    return s.size() >= n && s.compare(s.size() - n, n, suffix) == 0;
+}
+} // namespace
+
+extern "C"
+{
+const char *flx_io_last_error(void) { return g_io_error.c_str(); }
+
+int flx_scene_load(const char *path, flx_scene **out)
+{
+    if (!path || !out)
+    {
+        g_io_error = "flx_scene_load: null argument";
+        return FLX_E_INVALID;
+    }
+    *out = nullptr;
+    flx_scene *s = new flx_scene();
+    push_default_material(*s);
+    const std::string p(path);
+    bool ok = false;
+    if (ends_with(p, "obj")) // Scene::loadModel dispatches on the file-name ending (src/scene.cpp:52-92)
+        ok = load_obj(p, *s);
+    else if (ends_with(p, "ply"))
+        ok = load_ply(p, *s);
+    else
+        g_io_error = p + ": unsupported model format (obj and ply are)";
+    if (ok && s->tris.empty())
+    {
+        g_io_error = p + ": no triangles";
+        ok = false;
+    }
+    if (!ok)
+    {
+        delete s;
+        return FLX_E_INVALID;
+    }
+    *out = s;
+    return 0;
+}
+
+void flx_scene_free(flx_scene *s) { delete s; }
+uint32_t flx_scene_num_triangles(const flx_scene *s) { return s ? (uint32_t)s->tris.size() : 0; }
+uint32_t flx_scene_num_materials(const flx_scene *s) { return s ? (uint32_t)s->mats.size() : 0; }
+uint32_t flx_scene_num_textures(const flx_scene *s) { return s ? (uint32_t)s->texNames.size() : 0; }
+const flx_Triangle *flx_scene_triangles(const flx_scene *s) { return s ? s->tris.data() : nullptr; }
+const flx_Material *flx_scene_materials(const flx_scene *s) { return s ? s->mats.data() : nullptr; }
+const char *flx_scene_texture_name(const flx_scene *s, uint32_t i) { return (s && i < s->texNames.size()) ? s->texNames[i].c_str() : nullptr; }
+
+int flx_envmap_load(const char *path, flx_envmap **out)
+{
+    if (!path || !out)
+    {
+        g_io_error = "flx_envmap_load: null argument";
+        return FLX_E_INVALID;
+    }
+    *out = nullptr;
+    flx_envmap *e = new flx_envmap();
+    if (!read_rgbe(path, *e))
+    {
+        delete e;
+        return FLX_E_INVALID;
+    }
+    importance_tables(*e);
+    *out = e;
+    return 0;
+}
+
+int flx_envmap_from_rgb(const float *rgb, int32_t w, int32_t h, flx_envmap **out)
+{
+    if (!rgb || !out || w <= 0 || h <= 0)
+    {
+        g_io_error = "flx_envmap_from_rgb: bad arguments";
+        return FLX_E_INVALID;
+    }
+    flx_envmap *e = new flx_envmap();
+    e->w = w;
+    e->h = h;
+    e->rgb.assign(rgb, rgb + (size_t)w * h * 3);
+    importance_tables(*e);
+    *out = e;
+    return 0;
+}
+
+void flx_envmap_free(flx_envmap *e) { delete e; }
+int32_t flx_envmap_width(const flx_envmap *e) { return e ? e->w : 0; }
+int32_t flx_envmap_height(const flx_envmap *e) { return e ? e->h : 0; }
+const float *flx_envmap_rgb(const flx_envmap *e) { return e ? e->rgb.data() : nullptr; }
+const float *flx_envmap_prob(const flx_envmap *e) { return e ? e->prob.data() : nullptr; }
+const int32_t *flx_envmap_alias(const flx_envmap *e) { return e ? e->alias.data() : nullptr; }
+const float *flx_envmap_pdf(const flx_envmap *e) { return e ? e->pdf.data() : nullptr; }
+}

@@ -1,0 +1,71 @@
+"""File input through the C ABI (flx_scene_load / flx_envmap_load, include/fluctus_b200.h): OBJ + MTL, ASCII PLY and
+Radiance RGBE in, the arrays uploadSceneData / createEnvMap take out -- the reference's Scene::loadModel and
+EnvironmentMap (src/scene.cpp:52-92, src/envmap.cpp:9-114) without the reference.  Nothing is parsed in Python."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .scene import EnvMapData
+from .structs import MATERIAL_DTYPE, TRIANGLE_DTYPE
+
+
+class LoadedModel:
+    """Triangles (file order), materials (0 = the reference's default material) and texture names (first-use order,
+    relative to the model's folder); the hierarchy is built separately (CLContext.buildBVH, or any builder that emits
+    the reference's Node[] format)."""
+
+    def __init__(self, tris, materials, texture_names):
+        self.tris, self.materials, self.texture_names = tris, materials, texture_names
+
+
+def _io_error(lib, what):
+    msg = lib.flx_io_last_error()
+    from .clcontext import FluctusError
+    return FluctusError("%s failed: %s" % (what, msg.decode() if msg else "?"))
+
+
+def load_model(path):
+    lib = _lib.load()
+    h = C.c_void_p()
+    if lib.flx_scene_load(str(path).encode(), C.byref(h)) != 0:
+        raise _io_error(lib, "flx_scene_load(%s)" % path)
+    try:
+        nt, nm, nx = lib.flx_scene_num_triangles(h), lib.flx_scene_num_materials(h), lib.flx_scene_num_textures(h)
+        tris = np.frombuffer(C.string_at(lib.flx_scene_triangles(h), nt * 160), TRIANGLE_DTYPE).copy()
+        mats = np.frombuffer(C.string_at(lib.flx_scene_materials(h), nm * 80), MATERIAL_DTYPE).copy()
+        names = [lib.flx_scene_texture_name(h, i).decode() for i in range(nx)]
+    finally:
+        lib.flx_scene_free(h)
+    return LoadedModel(tris, mats, names)
+
+
+def _env_out(lib, h):
+    try:
+        w, hh = lib.flx_envmap_width(h), lib.flx_envmap_height(h)
+        n = w * hh
+        rgb = np.frombuffer(C.string_at(lib.flx_envmap_rgb(h), n * 12), np.float32).reshape(hh, w, 3).copy()
+        prob = np.frombuffer(C.string_at(lib.flx_envmap_prob(h), n * 4), np.float32).copy()
+        alias = np.frombuffer(C.string_at(lib.flx_envmap_alias(h), n * 4), np.int32).copy()
+        pdf = np.frombuffer(C.string_at(lib.flx_envmap_pdf(h), n * 4), np.float32).copy()
+    finally:
+        lib.flx_envmap_free(h)
+    return EnvMapData(rgb, prob, alias, pdf)
+
+
+def load_envmap(path):
+    lib = _lib.load()
+    h = C.c_void_p()
+    if lib.flx_envmap_load(str(path).encode(), C.byref(h)) != 0:
+        raise _io_error(lib, "flx_envmap_load(%s)" % path)
+    return _env_out(lib, h)
+
+
+def envmap_from_rgb(rgb):
+    lib = _lib.load()
+    rgb = np.ascontiguousarray(rgb, np.float32)
+    hh, w = rgb.shape[:2]
+    h = C.c_void_p()
+    if lib.flx_envmap_from_rgb(rgb.ctypes.data_as(C.c_void_p), w, hh, C.byref(h)) != 0:
+        raise _io_error(lib, "flx_envmap_from_rgb")
+    return _env_out(lib, h)

@@ -232,6 +232,32 @@ int flx_comm_init(flx_ctx *ctx, const void *unique_id128, int rank, int nranks);
 int flx_gather_pixels(flx_ctx *ctx, int root, float *full_rgba_host_or_null);
 int flx_comm_destroy(flx_ctx *ctx);
 
+/* ---- scene input (host code, no device work).  The reference's Scene::loadModel for OBJ + MTL and ASCII PLY
+ * (src/scene.cpp:52-92, 191-301, 422-553 with its vendored tinyobjloader 1.0.x) and its EnvironmentMap (src/envmap.cpp:9-114
+ * with src/rgbe/rgbe.cpp), producing exactly the arrays flx_upload_scene / flx_upload_envmap take: triangles in file order,
+ * material 0 = the reference's default material, texture NAMES in first-use order (decoding images is left to the caller;
+ * the reference uses DevIL), RGB float image + alias-method tables.  Errors: non-zero return, message in flx_io_last_error(). */
+typedef struct flx_scene flx_scene;
+typedef struct flx_envmap flx_envmap;
+const char *flx_io_last_error(void);
+int flx_scene_load(const char *path /* .obj or .ply */, flx_scene **out);
+void flx_scene_free(flx_scene *scene);
+uint32_t flx_scene_num_triangles(const flx_scene *scene);
+uint32_t flx_scene_num_materials(const flx_scene *scene);
+uint32_t flx_scene_num_textures(const flx_scene *scene);
+const flx_Triangle *flx_scene_triangles(const flx_scene *scene);
+const flx_Material *flx_scene_materials(const flx_scene *scene);
+const char *flx_scene_texture_name(const flx_scene *scene, uint32_t index); /* relative to the model's folder */
+int flx_envmap_load(const char *path /* Radiance .hdr */, flx_envmap **out);
+int flx_envmap_from_rgb(const float *rgb, int32_t w, int32_t h, flx_envmap **out); /* tables only (EnvironmentMap::computeProbabilities) */
+void flx_envmap_free(flx_envmap *env);
+int32_t flx_envmap_width(const flx_envmap *env);
+int32_t flx_envmap_height(const flx_envmap *env);
+const float *flx_envmap_rgb(const flx_envmap *env);
+const float *flx_envmap_prob(const flx_envmap *env);
+const int32_t *flx_envmap_alias(const flx_envmap *env);
+const float *flx_envmap_pdf(const flx_envmap *env);
+
 /* End-to-end convenience used by bench.py's e2e leg: host scene in, host image out, all copies included. */
 size_t flx_device_bytes(const flx_ctx *ctx);
 

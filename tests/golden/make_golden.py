@@ -87,6 +87,48 @@ def build_case(name, blob_loader=None):
     raise KeyError(name)
 
 
+IO_FIXTURES = (("obj", "tricky.obj"), ("ply", "tricky.ply"), ("ply", "plain.ply"), ("env", "small_rle.hdr"))
+
+
+def make_io_expected():
+    """Runs the REFERENCE'S loader code (oracle/_ref/scene_tool: its vendored tinyobjloader + the scene.cpp conversion, its
+    PLY reader, its RGBE reader and importance tables) on the small input files under tests/golden/io/ and stores what it
+    produced; tests/test_scene_io_cpu.py holds flx_scene_load / flx_envmap_load to these bytes."""
+    import struct
+    import subprocess
+    import tempfile
+    from fluctus_b200.structs import MATERIAL_DTYPE, TRIANGLE_DTYPE
+    tool = os.path.join(ROOT, "oracle", "_ref", "scene_tool")
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        for mode, name in IO_FIXTURES:
+            blob = os.path.join(tmp, name + ".bin")
+            subprocess.run([tool, mode, os.path.join(HERE, "io", name), blob], check=True, capture_output=True)
+            buf = open(blob, "rb").read()
+            key = name.replace(".", "_")
+            if mode == "env":
+                magic, w, h = struct.unpack_from("<3I", buf, 0)
+                n, off = w * h, 12
+                out[key + "_size"] = np.array([w, h])
+                out[key + "_rgb"] = np.frombuffer(buf, np.float32, n * 3, off).copy(); off += n * 12
+                out[key + "_prob"] = np.frombuffer(buf, np.float32, n, off).copy(); off += n * 4
+                out[key + "_alias"] = np.frombuffer(buf, np.int32, n, off).copy(); off += n * 4
+                out[key + "_pdf"] = np.frombuffer(buf, np.float32, n, off).copy()
+                continue
+            magic, nt, ni, nn, nm, ntex = struct.unpack_from("<6I", buf, 0)
+            off = 24
+            out[key + "_tris"] = np.frombuffer(buf, np.uint8, nt * 160, off).copy(); off += nt * 160 + ni * 4 + nn * 48
+            out[key + "_materials"] = np.frombuffer(buf, np.uint8, nm * 80, off).copy(); off += nm * 80
+            names = []
+            for _ in range(ntex):
+                (ln,) = struct.unpack_from("<I", buf, off); off += 4
+                names.append(buf[off:off + ln].decode()); off += ln
+            out[key + "_textures"] = np.array(names, dtype="U128")
+    fix = os.path.join(HERE, "io", "expected.npz")
+    np.savez_compressed(fix, **out)
+    print("io fixtures:", os.path.getsize(fix), "bytes")
+
+
 def main():
     from oracle import build_ref, make_scenes
     from oracle.oracle_host import RefContext
@@ -109,6 +151,7 @@ def main():
             out.update(scene_tris=scene.tris.view(np.uint8), scene_indices=scene.indices, scene_nodes=scene.nodes.view(np.uint8), scene_materials=scene.materials.view(np.uint8))
         np.savez_compressed(fix, **out)
         print(name, os.path.getsize(fix), "bytes;", dict(zip(("primary", "extension", "shadow"), out["stats"])))
+    make_io_expected()
     for name, (base, spp) in MK_CASES.items():
         n = build_case(base)[3]
         out = run_mk_case(RefContext(n), name)

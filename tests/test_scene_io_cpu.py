@@ -1,0 +1,96 @@
+"""Scene input through the C ABI (flx_scene_load / flx_envmap_load) against the reference's own loader code
+(oracle/_ref/scene_tool = its vendored tinyobjloader + the scene.cpp conversion, its PLY reader, its RGBE reader and
+importance tables): byte-identical triangles, materials, texture names and tables -- on small committed inputs that poke
+at the loader's corners (always), and on the reference's assets (where /root/reference and the blobs exist).
+Host code only: runs without a GPU."""
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from fluctus_b200 import EnvMapData, FluctusError
+from fluctus_b200.scene_io import envmap_from_rgb, load_envmap, load_model
+from fluctus_b200.structs import MATERIAL_DTYPE, TRIANGLE_DTYPE
+
+from conftest import scene_blob
+
+IO = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "io")
+EXPECTED = np.load(os.path.join(IO, "expected.npz"))
+REF_ASSETS = os.path.join(os.environ.get("FLX_REFERENCE_DIR", "/root/reference"), "assets")
+
+
+def same_tables(env, prob, alias, pdf, what):
+    assert np.array_equal(env.prob.view(np.uint32), prob.view(np.uint32)), what + ": prob table"
+    assert np.array_equal(env.pdf.view(np.uint32), pdf.view(np.uint32)), what + ": pdf table"
+    live = prob < 1.0  # the reference never writes alias[i] where prob[i] = 1 (src/envmap.cpp:101-113): uninitialised memory there
+    assert np.array_equal(env.alias[live], alias[live]), what + ": alias table"
+
+
+@pytest.mark.parametrize("name", ["tricky.obj", "tricky.ply", "plain.ply"])
+def test_models_match_the_reference_loader_on_committed_inputs(name):
+    """tricky.obj: CRLF line ends, a missing first mtllib file, quads and a pentagon (fan triangulation), negative indices,
+    v / v/t / v//n / v/t/n corners (face normals when a normal is missing), numbers with exponents / leading '+' / '.5'
+    (which the loader reads as 0) / more digits than a float holds, an unknown usemtl (-> default material), a material
+    defined twice (first wins), texture statements with options and backslashes, the `shader` key with trailing blanks and
+    with a tab.  tricky.ply: normals and a quad.  plain.ply: no normals (face normals)."""
+    key = name.replace(".", "_")
+    m = load_model(os.path.join(IO, name))
+    assert m.tris.tobytes() == EXPECTED[key + "_tris"].tobytes()
+    assert m.materials.tobytes() == EXPECTED[key + "_materials"].tobytes()
+    assert m.texture_names == [str(s) for s in EXPECTED[key + "_textures"]]
+
+
+def test_rle_hdr_and_importance_tables_match_the_reference_reader():
+    env = load_envmap(os.path.join(IO, "small_rle.hdr"))
+    w, h = EXPECTED["small_rle_hdr_size"]
+    assert (env.width, env.height) == (w, h)
+    assert np.array_equal(env.rgb.reshape(-1).view(np.uint32), EXPECTED["small_rle_hdr_rgb"].view(np.uint32))
+    same_tables(env, EXPECTED["small_rle_hdr_prob"], EXPECTED["small_rle_hdr_alias"], EXPECTED["small_rle_hdr_pdf"], "small_rle.hdr")
+    # the Python mirror used by the tests for synthetic maps and the C++ tables agree too
+    py = EnvMapData.from_rgb(env.rgb)
+    same_tables(envmap_from_rgb(env.rgb), py.prob, py.alias, py.pdf, "from_rgb")
+    black = envmap_from_rgb(np.zeros((4, 8, 3), np.float32))  # I == 0: uniform pdf (src/envmap.cpp:62-63)
+    assert np.all(black.pdf == np.float32(1.0) / np.float32(32))
+
+
+def test_loader_errors_are_reported_not_fatal():
+    """the reference prints and calls waitExit() (src/scene.cpp:210-214, src/envmap.cpp:13-17); the library returns an error"""
+    with pytest.raises(FluctusError):
+        load_model(os.path.join(IO, "does_not_exist.obj"))
+    with pytest.raises(FluctusError):
+        load_model(os.path.join(IO, "small_rle.hdr"))  # unsupported ending
+    with pytest.raises(FluctusError):
+        load_envmap(os.path.join(IO, "tricky.obj"))  # not a Radiance file
+
+
+@pytest.mark.parametrize("name,rel", [("teapot", "teapot.ply"), ("conference", "conference/conference.obj"), ("luxball", "luxball/luxball.obj"),
+                                      ("country_kitchen", "country_kitchen/Country-Kitchen.obj")])
+def test_reference_assets_match_the_reference_loader(name, rel):
+    path = os.path.join(REF_ASSETS, rel)
+    if not os.path.exists(path):
+        pytest.skip("reference assets not present")
+    buf = open(scene_blob(name), "rb").read()
+    magic, nt, ni, nn, nm, ntex = struct.unpack_from("<6I", buf, 0)
+    off = 24
+    tris = buf[off:off + nt * 160]; off += nt * 160 + ni * 4 + nn * 48
+    mats = buf[off:off + nm * 80]; off += nm * 80
+    names = []
+    for _ in range(ntex):
+        (ln,) = struct.unpack_from("<I", buf, off); off += 4
+        names.append(buf[off:off + ln].decode()); off += ln
+    m = load_model(path)
+    assert len(m.tris) == nt and m.tris.tobytes() == tris
+    assert m.materials.tobytes() == mats
+    assert m.texture_names == names
+
+
+def test_reference_env_map_matches_the_reference_reader():
+    path = os.path.join(REF_ASSETS, "env_maps", "night.hdr")
+    blob = os.path.join(os.path.dirname(scene_blob("teapot")), "night.env.bin")
+    if not os.path.exists(path) or not os.path.exists(blob):
+        pytest.skip("reference assets not present")
+    ref = EnvMapData.load_blob(blob)
+    env = load_envmap(path)
+    assert np.array_equal(env.rgb.view(np.uint32), ref.rgb.view(np.uint32))
+    same_tables(env, ref.prob, ref.alias, ref.pdf, "night.hdr")
