@@ -45,6 +45,19 @@ def main():
                 tr.updateMicrokernel()
                 pix = ctx.readPixels()
                 assert np.isfinite(pix).all()
+    # the hierarchy builder, incl. the one- and two-triangle cases and a scene rendered through its tree
+    with CLContext(1500) as ctx:
+        for n in (1, 2, len(scene.tris)):
+            nodes, idx, _ = ctx.buildBVH(scene.tris[:n], 8 if n > 2 else 1)
+        from fluctus_b200 import SceneData
+        built = SceneData(scene.tris, idx, nodes, scene.materials, scene.tex_desc, scene.tex_data)
+        params = room_params(built, 40, 24, max_bounces=3)
+        ctx.uploadSceneData(built)
+        ctx.setupPixelStorage(40, 24)
+        tr = Tracer(ctx, params)
+        tr.start()
+        ctx.render(3)
+        assert np.isfinite(ctx.readPixels()).all()
     print("SANITIZE_RUN_OK")
 
 
