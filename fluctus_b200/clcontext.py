@@ -234,6 +234,11 @@ class CLContext:
         self._check(self._lib.flx_read_pixels(self._h, self._ptr(out), n), "readPixels")
         return out
 
+    def saveImage(self, filename, params=None):
+        """reference: CLContext::saveImage (clcontext.cpp:386-465) -- '*.hdr': linear radiance as Radiance RGBE, otherwise the
+        post-processed preview as 8-bit PNG."""
+        self._check(self._lib.flx_save_image(self._h, str(filename).encode()), "saveImage")
+
     def readTasks(self):
         out = np.empty((64, self.NUM_TASKS), np.uint32)
         self._check(self._lib.flx_read_tasks(self._h, self._ptr(out)), "readTasks")

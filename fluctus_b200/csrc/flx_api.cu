@@ -1569,6 +1569,25 @@ int flx_read_pixels(flx_ctx *ctx, float *rgba, size_t n_pixels)
     return 0;
 }
 
+// CLContext::saveImage (clcontext.hpp:78; clcontext.cpp:386-465): *.hdr from the accumulator, anything else from the preview
+int flx_save_image(flx_ctx *ctx, const char *filename)
+{
+    int rc = checkReady(ctx, false, true);
+    if (rc)
+        return rc;
+    REQUIRE(filename != nullptr, "flx_save_image: null file name");
+    REQUIRE(ctx->nParts == 1, "flx_save_image: this context renders a tile; gather the full image first (flx_gather_pixels)");
+    const std::string name(filename);
+    const bool hdr = name.size() >= 4 && (name.compare(name.size() - 4, 4, ".hdr") == 0 || name.compare(name.size() - 4, 4, ".HDR") == 0);
+    std::vector<float> host((size_t)ctx->tilePixels * 4);
+    rc = hdr ? flx_read_pixels(ctx, host.data(), ctx->tilePixels) : flx_read_preview(ctx, host.data(), ctx->tilePixels);
+    if (rc)
+        return rc;
+    if (flx_write_image(filename, host.data(), ctx->width, ctx->height) != 0)
+        return fail(ctx, FLX_E_INVALID, "flx_save_image: %s", flx_io_last_error());
+    return 0;
+}
+
 int flx_read_tasks(flx_ctx *ctx, uint32_t *slots_out)
 {
     if (!ctx)

@@ -16,6 +16,7 @@
 //     method on two LIFO stacks).
 // Image decoding (textures) is not done here: the reference uses DevIL, which is not available; callers decode the named
 // files themselves and pass RGBA8 to flx_upload_scene.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -775,6 +776,142 @@ void importance_tables(flx_envmap &e) // src/envmap.cpp:31-114
         e.prob[l.second] = 1.0f;
 }
 
+// ---- image output (CLContext::saveImage, src/clcontext.cpp:386-465, writes through DevIL; here two small writers)
+uint32_t crc32_of(const unsigned char *p, size_t n, uint32_t crc)
+{
+    static uint32_t table[256];
+    static bool ready = false;
+    if (!ready)
+    {
+        for (uint32_t i = 0; i < 256; i++)
+        {
+            uint32_t c = i;
+            for (int k = 0; k < 8; k++)
+                c = (c & 1u) ? 0xedb88320u ^ (c >> 1) : c >> 1;
+            table[i] = c;
+        }
+        ready = true;
+    }
+    crc = ~crc;
+    for (size_t i = 0; i < n; i++)
+        crc = table[(crc ^ p[i]) & 0xffu] ^ (crc >> 8);
+    return ~crc;
+}
+
+void put_be32(std::vector<unsigned char> &v, uint32_t x)
+{
+    for (int s = 24; s >= 0; s -= 8)
+        v.push_back((unsigned char)(x >> s));
+}
+
+bool write_chunk(FILE *fp, const char type[4], const std::vector<unsigned char> &body)
+{
+    std::vector<unsigned char> head;
+    put_be32(head, (uint32_t)body.size());
+    std::vector<unsigned char> typed(type, type + 4);
+    typed.insert(typed.end(), body.begin(), body.end());
+    std::vector<unsigned char> tail;
+    put_be32(tail, crc32_of(typed.data(), typed.size(), 0));
+    return std::fwrite(head.data(), 1, 4, fp) == 4 && std::fwrite(typed.data(), 1, typed.size(), fp) == typed.size() && std::fwrite(tail.data(), 1, 4, fp) == 4;
+}
+
+// 8-bit RGB PNG; rows[0] is the BOTTOM row of the image (the renderer's y axis points up; the reference sets DevIL's origin
+// to lower-left, src/main.cpp:69-71).  The zlib stream uses stored (uncompressed) deflate blocks: no dependency, valid PNG.
+bool write_png(const std::string &path, const unsigned char *rgb, uint32_t w, uint32_t h)
+{
+    FILE *fp = std::fopen(path.c_str(), "wb");
+    if (!fp)
+    {
+        g_io_error = "cannot create " + path;
+        return false;
+    }
+    static const unsigned char sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    bool ok = std::fwrite(sig, 1, 8, fp) == 8;
+    std::vector<unsigned char> ihdr;
+    put_be32(ihdr, w);
+    put_be32(ihdr, h);
+    const unsigned char fmt[5] = {8, 2, 0, 0, 0}; // 8 bits, truecolour, deflate, adaptive filtering (all rows filter 0), no interlace
+    ihdr.insert(ihdr.end(), fmt, fmt + 5);
+    ok = ok && write_chunk(fp, "IHDR", ihdr);
+    std::vector<unsigned char> raw;
+    raw.reserve((size_t)h * (3 * (size_t)w + 1));
+    for (uint32_t y = 0; y < h; y++)
+    {
+        raw.push_back(0);
+        const unsigned char *row = rgb + (size_t)(h - 1 - y) * w * 3;
+        raw.insert(raw.end(), row, row + (size_t)w * 3);
+    }
+    std::vector<unsigned char> z;
+    z.push_back(0x78);
+    z.push_back(0x01);
+    uint32_t a = 1, b = 0; // Adler-32
+    for (size_t off = 0; off < raw.size() || off == 0; off += 65535)
+    {
+        const size_t n = std::min<size_t>(65535, raw.size() - off);
+        z.push_back(off + n >= raw.size() ? 1 : 0);
+        z.push_back((unsigned char)(n & 0xff));
+        z.push_back((unsigned char)(n >> 8));
+        z.push_back((unsigned char)(~n & 0xff));
+        z.push_back((unsigned char)((~n >> 8) & 0xff));
+        z.insert(z.end(), raw.begin() + off, raw.begin() + off + n);
+        for (size_t i = 0; i < n; i++)
+        {
+            a = (a + raw[off + i]) % 65521u;
+            b = (b + a) % 65521u;
+        }
+        if (raw.empty())
+            break;
+    }
+    put_be32(z, (b << 16) | a);
+    ok = ok && write_chunk(fp, "IDAT", z) && write_chunk(fp, "IEND", std::vector<unsigned char>());
+    ok = (std::fclose(fp) == 0) && ok;
+    if (!ok)
+        g_io_error = "write error on " + path;
+    return ok;
+}
+
+// Radiance RGBE, flat (not run-length encoded) scanlines, top row first; rows[0] of the input is the bottom row
+bool write_hdr(const std::string &path, const float *rgb, uint32_t w, uint32_t h)
+{
+    FILE *fp = std::fopen(path.c_str(), "wb");
+    if (!fp)
+    {
+        g_io_error = "cannot create " + path;
+        return false;
+    }
+    bool ok = std::fprintf(fp, "#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n-Y %u +X %u\n", h, w) > 0;
+    std::vector<unsigned char> row((size_t)w * 4);
+    for (uint32_t y = 0; y < h && ok; y++)
+    {
+        const float *src = rgb + (size_t)(h - 1 - y) * w * 3;
+        for (uint32_t x = 0; x < w; x++)
+        {
+            const float r = src[3 * x], g = src[3 * x + 1], bl = src[3 * x + 2];
+            float v = r > g ? r : g;
+            if (bl > v)
+                v = bl;
+            unsigned char *o = &row[4 * (size_t)x];
+            if (!(v >= 1e-32f)) // also catches NaN
+                o[0] = o[1] = o[2] = o[3] = 0;
+            else
+            {
+                int e;
+                const float m = (float)(std::frexp(v, &e) * 256.0 / v);
+                auto q = [&](float c) { const float t = c * m; return (unsigned char)(t <= 0.0f ? 0 : (t >= 255.0f ? 255 : (int)t)); };
+                o[0] = q(r);
+                o[1] = q(g);
+                o[2] = q(bl);
+                o[3] = (unsigned char)(e + 128);
+            }
+        }
+        ok = std::fwrite(row.data(), 1, row.size(), fp) == row.size();
+    }
+    ok = (std::fclose(fp) == 0) && ok;
+    if (!ok)
+        g_io_error = "write error on " + path;
+    return ok;
+}
+
 bool ends_with(const std::string &s, const char *suffix)
 {
     const size_t n = std::strlen(suffix);
@@ -859,6 +996,33 @@ int flx_envmap_from_rgb(const float *rgb, int32_t w, int32_t h, flx_envmap **out
     importance_tables(*e);
     *out = e;
     return 0;
+}
+
+// CLContext::saveImage's two conversions (src/clcontext.cpp:407-451) on host buffers of n_pixels RGBA floats, row 0 = bottom row:
+// *.hdr / *.HDR: the raw accumulator divided by its sample count, linear and unclamped, as Radiance RGBE;
+// anything else: the post-processed preview (already tone-mapped and gamma-corrected) as 8-bit PNG, byte = (uchar)(255 * clamp01(c)).
+int flx_write_image(const char *path, const float *rgba, uint32_t width, uint32_t height)
+{
+    if (!path || !rgba || width == 0 || height == 0)
+    {
+        g_io_error = "flx_write_image: bad arguments";
+        return FLX_E_INVALID;
+    }
+    const std::string p(path);
+    const size_t n = (size_t)width * height;
+    if (ends_with(p, ".hdr") || ends_with(p, ".HDR"))
+    {
+        std::vector<float> rgb(n * 3);
+        for (size_t i = 0; i < n; i++)
+            for (int c = 0; c < 3; c++)
+                rgb[3 * i + c] = rgba[4 * i + c] / rgba[4 * i + 3];
+        return write_hdr(p, rgb.data(), width, height) ? 0 : FLX_E_INVALID;
+    }
+    std::vector<unsigned char> bytes(n * 3);
+    for (size_t i = 0; i < n; i++)
+        for (int c = 0; c < 3; c++)
+            bytes[3 * i + c] = (unsigned char)(255 * std::max(0.0f, std::min(1.0f, rgba[4 * i + c])));
+    return write_png(p, bytes.data(), width, height) ? 0 : FLX_E_INVALID;
 }
 
 void flx_envmap_free(flx_envmap *e) { delete e; }

@@ -69,3 +69,13 @@ def envmap_from_rgb(rgb):
     if lib.flx_envmap_from_rgb(rgb.ctypes.data_as(C.c_void_p), w, hh, C.byref(h)) != 0:
         raise _io_error(lib, "flx_envmap_from_rgb")
     return _env_out(lib, h)
+
+
+def write_image(path, rgba, width, height):
+    """CLContext::saveImage's conversions on a host RGBA float buffer (row 0 = bottom row): '*.hdr' -> RGBE of rgb / a,
+    anything else -> 8-bit PNG of clamp01(rgb) (flx_write_image)."""
+    lib = _lib.load()
+    rgba = np.ascontiguousarray(rgba, np.float32)
+    assert rgba.size == width * height * 4
+    if lib.flx_write_image(str(path).encode(), rgba.ctypes.data_as(C.c_void_p), int(width), int(height)) != 0:
+        raise _io_error(lib, "flx_write_image(%s)" % path)

@@ -212,6 +212,13 @@ int flx_get_kernel_ms(flx_ctx *ctx, int kernel_id, float *total_ms, uint32_t *la
 
 /* Raw read-back, replaces CLContext::saveImage (clcontext.hpp:78; clcontext.cpp:386-465). Synchronises. */
 int flx_read_pixels(flx_ctx *ctx, float *rgba, size_t n_pixels);
+/* CLContext::saveImage itself (clcontext.cpp:386-465): "*.hdr" = accumulator / sample count, linear, as Radiance RGBE; any
+ * other name = the post-processed preview (run flx_enqueue_postprocess first) as 8-bit PNG, byte = (uchar)(255 * clamp01(c)).
+ * Row 0 of the buffers is the bottom image row (the reference sets DevIL's origin to lower-left, src/main.cpp:69-71); files
+ * are written top row first.  flx_write_image does the same conversions on a caller's RGBA float buffer (host code). */
+int flx_save_image(flx_ctx *ctx, const char *filename);
+int flx_write_image(const char *path, const float *rgba, uint32_t width, uint32_t height);
+
 /* Test/diagnostic access to the path state and queues (no reference equivalent; the reference's debugger did this). */
 int flx_read_tasks(flx_ctx *ctx, uint32_t *slots_out /* 64*num_tasks */);
 int flx_write_tasks(flx_ctx *ctx, const uint32_t *slots_in);

@@ -89,6 +89,8 @@ class CLContext
     void enqueueWfLogicKernel(const RenderParams &, const bool firstIteration) { verify(flx_enqueue_logic(ctx, firstIteration ? 1 : 0), "enqueueWfLogicKernel"); }
     void enqueueWfMaterialKernels(const RenderParams &) { verify(flx_enqueue_materials(ctx), "enqueueWfMaterialKernels"); }
 
+    void saveImage(const std::string &filename, const RenderParams &) { verify(flx_save_image(ctx, filename.c_str()), "saveImage"); } // clcontext.hpp:78
+
     // ---- microkernel integrator (clcontext.hpp:35-40; the one Tracer::renderSingle uses, tracer.cpp:95-169)
     void enqueueResetKernel(const RenderParams &) { verify(flx_enqueue_mk_reset(ctx), "enqueueResetKernel"); }
     void enqueueRayGenKernel(const RenderParams &) { verify(flx_enqueue_mk_raygen(ctx), "enqueueRayGenKernel"); }

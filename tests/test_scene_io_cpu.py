@@ -94,3 +94,42 @@ def test_reference_env_map_matches_the_reference_reader():
     env = load_envmap(path)
     assert np.array_equal(env.rgb.view(np.uint32), ref.rgb.view(np.uint32))
     same_tables(env, ref.prob, ref.alias, ref.pdf, "night.hdr")
+
+
+# ---------------------------------------------------------------------------------------------- image output
+def test_png_and_hdr_writers_follow_saveImage(tmp_path):
+    """CLContext::saveImage (src/clcontext.cpp:386-465): '*.hdr' = accumulator / sample count as Radiance RGBE (checked by
+    reading it back with the RGBE reader, which is pinned to the reference's), otherwise byte = (uchar)(255 * clamp01(c)) of
+    the preview as PNG (checked with an independent decoder, Pillow).  Row 0 of the buffer is the bottom row of the picture
+    (DevIL origin lower-left, src/main.cpp:69-71).  The reference writes through DevIL, which is absent: file BYTES are
+    unpinned, pixel values are what is compared."""
+    from PIL import Image
+    from fluctus_b200.scene_io import write_image
+    rng = np.random.default_rng(21)
+    w, h = 37, 19
+    preview = rng.uniform(-0.2, 1.3, (h, w, 4)).astype(np.float32)
+    preview[0, 0, :3] = (0.0, 1.0, 0.5)
+    png = tmp_path / "out.png"
+    write_image(png, preview, w, h)
+    got = np.asarray(Image.open(png).convert("RGB"))
+    want = (np.float32(255) * np.clip(preview[..., :3], 0.0, 1.0)).astype(np.uint8)[::-1]  # C cast truncates; top row first in the file
+    assert got.shape == (h, w, 3) and np.array_equal(got, want)
+    # a 300 x 300 image needs more than one stored deflate block (65535 bytes each)
+    big = rng.uniform(0, 1, (300, 300, 4)).astype(np.float32)
+    write_image(tmp_path / "big.png", big, 300, 300)
+    assert np.array_equal(np.asarray(Image.open(tmp_path / "big.png").convert("RGB")), (np.float32(255) * big[..., :3]).astype(np.uint8)[::-1])
+
+    acc = rng.uniform(0, 40, (h, w, 4)).astype(np.float32)
+    acc[..., 3] = rng.integers(1, 9, (h, w))
+    acc[3, 4, :3] = 0.0
+    hdr = tmp_path / "out.hdr"
+    write_image(hdr, acc, w, h)
+    back = load_envmap(hdr).rgb  # (h, w, 3), top row first
+    lin = (acc[..., :3] / acc[..., 3:4])[::-1]
+    v = lin.max(axis=-1)
+    m, e = np.frexp(v)
+    scale = np.where(v >= 1e-32, (m.astype(np.float64) * 256.0 / np.maximum(v, 1e-38)).astype(np.float32), 0).astype(np.float32)
+    q = np.clip((lin * scale[..., None]).astype(np.int32), 0, 255).astype(np.float32)
+    want = q * np.ldexp(np.float32(1.0), e - 8)[..., None].astype(np.float32)
+    assert np.array_equal(back, np.where(v[..., None] >= 1e-32, want, 0).astype(np.float32))
+    assert np.all(np.abs(back - lin) <= np.maximum(v[..., None] / 128.0, 1e-30))  # RGBE: 8-bit mantissa shared by the pixel
