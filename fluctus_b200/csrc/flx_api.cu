@@ -78,6 +78,9 @@ struct flx_ctx
     uint32_t *scanTicket = nullptr;
     uint32_t numScanTiles = 0;
     uint32_t hostPixelIdx = 0; // CLContext::pixelIdx (clcontext.hpp:164)
+    bool pixelIdxAdvancedOnDevice = false; // flx_render advances the device copy (k_end_iteration); fetch before the host advances it again
+    uint32_t *pinnedPixelIdx = nullptr;    // staging ring for the asynchronous 4-byte writes of flx_update_pixel_index
+    int pixelIdxRingPos = 0;
 
     // pinned staging for asynchronous counter reads
     flx_QueueCounters *pinnedCounters = nullptr;
@@ -656,6 +659,7 @@ int flx_create(int device, uint32_t num_tasks, flx_ctx **out)
     CUB(cudaMalloc(&c->scanTiles, (size_t)c->numScanTiles * sizeof(unsigned long long)));
     CUB(cudaMalloc(&c->scanTicket, sizeof(uint32_t)));
     CUB(cudaMallocHost(&c->pinnedCounters, sizeof(flx_QueueCounters) * flx_ctx::kCounterRing));
+    CUB(cudaMallocHost(&c->pinnedPixelIdx, sizeof(uint32_t) * flx_ctx::kCounterRing));
     c->numSMs = prop.multiProcessorCount;
     c->maxDynSmem = (int)prop.sharedMemPerBlockOptin;
     CUB(cudaMalloc(&c->fetchCounters, 4 * sizeof(uint32_t)));
@@ -712,6 +716,8 @@ void flx_destroy(flx_ctx *c)
         cudaEventDestroy(c->evStop);
     if (c->pinnedCounters)
         cudaFreeHost(c->pinnedCounters);
+    if (c->pinnedPixelIdx)
+        cudaFreeHost(c->pinnedPixelIdx);
     freeDev(c->tris);
     freeDev(c->materials);
     freeDev(c->kdGamma);
@@ -1309,12 +1315,23 @@ int flx_update_pixel_index(flx_ctx *ctx, uint32_t num_pixels, uint32_t num_new_p
         return FLX_E_INVALID;
     REQUIRE(num_pixels > 0, "flx_update_pixel_index: zero pixels");
     CU(cudaSetDevice(ctx->device));
-    // the device copy is authoritative (flx_render advances it there); fetch, advance, write back
-    CU(cudaMemcpyAsync(&ctx->hostPixelIdx, ctx->currPixelIdx, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    ctx->hostPixelIdx = (ctx->hostPixelIdx + num_new_paths) % num_pixels; // clcontext.cpp:891-895
-    CU(cudaMemcpyAsync(ctx->currPixelIdx, &ctx->hostPixelIdx, sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
+    // reference: host-tracked index, advanced and written with a NON-blocking 4-byte copy (clcontext.cpp:891-895).  Same here;
+    // only after flx_render (which advances the device copy itself) the host value is refreshed first.
+    if (ctx->pixelIdxAdvancedOnDevice)
+    {
+        CU(cudaMemcpyAsync(&ctx->hostPixelIdx, ctx->currPixelIdx, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        ctx->pixelIdxAdvancedOnDevice = false;
+    }
+    ctx->hostPixelIdx = (ctx->hostPixelIdx + num_new_paths) % num_pixels;
+    if (ctx->pixelIdxRingPos == flx_ctx::kCounterRing) // every staging slot may still be in flight: drain before reusing them
+    {
+        CU(cudaStreamSynchronize(ctx->stream));
+        ctx->pixelIdxRingPos = 0;
+    }
+    uint32_t *slot = ctx->pinnedPixelIdx + ctx->pixelIdxRingPos++;
+    *slot = ctx->hostPixelIdx;
+    CU(cudaMemcpyAsync(ctx->currPixelIdx, slot, sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     return 0;
 }
 
@@ -1324,6 +1341,7 @@ int flx_reset_pixel_index(flx_ctx *ctx)
         return FLX_E_INVALID;
     CU(cudaSetDevice(ctx->device));
     ctx->hostPixelIdx = 0;
+    ctx->pixelIdxAdvancedOnDevice = false;
     CU(cudaMemsetAsync(ctx->currPixelIdx, 0, sizeof(uint32_t), ctx->stream));
     return 0;
 }
@@ -1335,6 +1353,8 @@ int flx_render(flx_ctx *ctx, uint32_t n_iterations)
         return rc;
     CU(cudaSetDevice(ctx->device));
     const IterationState it = makeIter(ctx);
+    if (n_iterations)
+        ctx->pixelIdxAdvancedOnDevice = true;
     for (uint32_t i = 0; i < n_iterations; i++) // tracer.cpp:433-439, 465
     {
         if ((rc = flx_enqueue_logic(ctx, 0)))
