@@ -64,6 +64,11 @@ struct flx_ctx
     cudaStream_t cur = nullptr;       // stream the next traversal launch goes to (== stream except inside flx_render)
     cudaEvent_t evFork = nullptr, evJoin = nullptr;
     int overlapTrace = 1;
+    // Every ABI call that touches the stream bumps opSeq; flx_enqueue_extrays remembers its number.  A flx_enqueue_shadowrays
+    // that comes DIRECTLY after it (the order of the reference's loop, tracer.cpp:253-254 / 437-438) may then run on the second
+    // stream from the fork point recorded before the extension launch: the two stages have disjoint inputs and outputs, and the
+    // main stream waits for the join before anything enqueued later, so the in-order semantics a caller sees are unchanged.
+    unsigned long long opSeq = 0, extSeq = ~0ull;
     int postprocessInLoop = 1;        // flx_render runs the display pass every iteration, like the reference's loop (tracer.cpp:447)
     uint32_t numTasks = 0;
     std::string error;
@@ -307,6 +312,7 @@ int checkReady(flx_ctx *ctx, bool needScene, bool needImage)
 {
     if (!ctx)
         return FLX_E_INVALID;
+    ctx->opSeq++;
     if (!ctx->paramsSet)
         return fail(ctx, FLX_E_NOT_READY, "flx_update_params has not been called");
     if (needImage && !ctx->pixels)
@@ -1052,6 +1058,9 @@ int flx_enqueue_extrays(flx_ctx *ctx)
     if (rc)
         return rc;
     CU(cudaSetDevice(ctx->device));
+    if (ctx->overlapTrace)
+        CU(cudaEventRecord(ctx->evFork, ctx->stream)); // a shadow-ray stage enqueued next may start from here (see flx_ctx::opSeq)
+    ctx->extSeq = ctx->opSeq;
     if (ctx->traceVariant >= 1)
         return launchPersistent<false>(ctx);
     Timed tm(ctx, FLX_K_EXTRAYS);
@@ -1063,12 +1072,8 @@ int flx_enqueue_extrays(flx_ctx *ctx)
     return launchCheck(ctx, "k_extrays");
 }
 
-int flx_enqueue_shadowrays(flx_ctx *ctx)
+static int launchShadow(flx_ctx *ctx)
 {
-    int rc = checkReady(ctx, true, true);
-    if (rc)
-        return rc;
-    CU(cudaSetDevice(ctx->device));
     if (ctx->traceVariant >= 1)
         return launchPersistent<true>(ctx);
     Timed tm(ctx, FLX_K_SHADOWRAYS);
@@ -1078,6 +1083,27 @@ int flx_enqueue_shadowrays(flx_ctx *ctx)
     else
         k_shadowrays<NoCount><<<grid, FLX_TRACE_BLOCK, 0, ctx->cur>>>(makeFrame(ctx), ctx->params, makeBvh(ctx), nullptr);
     return launchCheck(ctx, "k_shadowrays");
+}
+
+int flx_enqueue_shadowrays(flx_ctx *ctx)
+{
+    int rc = checkReady(ctx, true, true);
+    if (rc)
+        return rc;
+    CU(cudaSetDevice(ctx->device));
+    if (!(ctx->overlapTrace && ctx->extSeq + 1 == ctx->opSeq))
+        return launchShadow(ctx);
+    // directly after the extension stage: run beside it on the second stream, so its CTAs fill the SMs the extension kernel's
+    // tail leaves idle; everything enqueued later on the main stream waits for both
+    CU(cudaStreamWaitEvent(ctx->stream2, ctx->evFork, 0));
+    ctx->cur = ctx->stream2;
+    rc = launchShadow(ctx);
+    ctx->cur = ctx->stream;
+    if (rc)
+        return rc;
+    CU(cudaEventRecord(ctx->evJoin, ctx->stream2));
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->evJoin, 0));
+    return 0;
 }
 
 int flx_enqueue_logic(flx_ctx *ctx, int first_iteration)
@@ -1272,6 +1298,7 @@ int flx_enqueue_clear_queues(flx_ctx *ctx)
 {
     if (!ctx)
         return FLX_E_INVALID;
+    ctx->opSeq++;
     CU(cudaSetDevice(ctx->device));
     CU(cudaMemsetAsync(ctx->counters, 0, sizeof(flx_QueueCounters), ctx->stream));
     return 0;
@@ -1281,6 +1308,7 @@ int flx_enqueue_get_counters(flx_ctx *ctx, flx_QueueCounters *host_out)
 {
     if (!ctx)
         return FLX_E_INVALID;
+    ctx->opSeq++;
     REQUIRE(host_out != nullptr, "flx_enqueue_get_counters: null destination");
     CU(cudaSetDevice(ctx->device));
     if ((int)ctx->pendingCounterReads.size() >= flx_ctx::kCounterRing)
@@ -1300,6 +1328,7 @@ int flx_finish(flx_ctx *ctx)
 {
     if (!ctx)
         return FLX_E_INVALID;
+    ctx->opSeq++;
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
     for (auto &r : ctx->pendingCounterReads)
@@ -1313,6 +1342,7 @@ int flx_update_pixel_index(flx_ctx *ctx, uint32_t num_pixels, uint32_t num_new_p
 {
     if (!ctx)
         return FLX_E_INVALID;
+    ctx->opSeq++;
     REQUIRE(num_pixels > 0, "flx_update_pixel_index: zero pixels");
     CU(cudaSetDevice(ctx->device));
     // reference: host-tracked index, advanced and written with a NON-blocking 4-byte copy (clcontext.cpp:891-895).  Same here;
@@ -1339,6 +1369,7 @@ int flx_reset_pixel_index(flx_ctx *ctx)
 {
     if (!ctx)
         return FLX_E_INVALID;
+    ctx->opSeq++;
     CU(cudaSetDevice(ctx->device));
     ctx->hostPixelIdx = 0;
     ctx->pixelIdxAdvancedOnDevice = false;
@@ -1364,29 +1395,11 @@ int flx_render(flx_ctx *ctx, uint32_t n_iterations)
         if ((rc = flx_enqueue_materials(ctx)))
             return rc;
         k_snapshot_counters<<<1, 32, 0, ctx->stream>>>(it);
-        if (ctx->overlapTrace)
-        {
-            // the two traversal stages are independent (disjoint inputs and outputs): fork the shadow rays onto a second
-            // stream so their CTAs fill the SMs the extension kernel's tail leaves idle, join before the bookkeeping
-            CU(cudaEventRecord(ctx->evFork, ctx->stream));
-            CU(cudaStreamWaitEvent(ctx->stream2, ctx->evFork, 0));
-            if ((rc = flx_enqueue_extrays(ctx)))
-                return rc;
-            ctx->cur = ctx->stream2;
-            rc = flx_enqueue_shadowrays(ctx);
-            ctx->cur = ctx->stream;
-            if (rc)
-                return rc;
-            CU(cudaEventRecord(ctx->evJoin, ctx->stream2));
-            CU(cudaStreamWaitEvent(ctx->stream, ctx->evJoin, 0));
-        }
-        else
-        {
-            if ((rc = flx_enqueue_extrays(ctx)))
-                return rc;
-            if ((rc = flx_enqueue_shadowrays(ctx)))
-                return rc;
-        }
+        // extension then shadow rays: the second call overlaps the first on a second stream (see flx_enqueue_shadowrays)
+        if ((rc = flx_enqueue_extrays(ctx)))
+            return rc;
+        if ((rc = flx_enqueue_shadowrays(ctx)))
+            return rc;
         {
             Timed tm(ctx, FLX_K_END_ITERATION);
             k_end_iteration<<<1, 32, 0, ctx->stream>>>(it);
@@ -1421,6 +1434,7 @@ int flx_timer_begin(flx_ctx *ctx)
 {
     if (!ctx)
         return FLX_E_INVALID;
+    ctx->opSeq++;
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaEventRecord(ctx->evStart, ctx->stream));
@@ -1431,6 +1445,7 @@ int flx_timer_end(flx_ctx *ctx, float *elapsed_ms)
 {
     if (!ctx)
         return FLX_E_INVALID;
+    ctx->opSeq++;
     REQUIRE(elapsed_ms != nullptr, "flx_timer_end: null destination");
     CU(cudaSetDevice(ctx->device));
     CU(cudaEventRecord(ctx->evStop, ctx->stream));
@@ -1444,6 +1459,7 @@ int flx_set_tuning(flx_ctx *ctx, int key, int value)
 {
     if (!ctx)
         return FLX_E_INVALID;
+    ctx->opSeq++;
     switch (key)
     {
     case FLX_TUNE_TRACE_VARIANT:
@@ -1499,6 +1515,7 @@ int flx_set_counting(flx_ctx *ctx, int enabled)
 {
     if (!ctx)
         return FLX_E_INVALID;
+    ctx->opSeq++;
     CU(cudaSetDevice(ctx->device));
     ctx->counting = enabled != 0;
     if (ctx->counting)
@@ -1531,6 +1548,7 @@ int flx_reset_stats(flx_ctx *ctx)
 {
     if (!ctx)
         return FLX_E_INVALID;
+    ctx->opSeq++;
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
     drainEvents(ctx);
@@ -1558,6 +1576,7 @@ int flx_set_profiling(flx_ctx *ctx, int enabled)
 {
     if (!ctx)
         return FLX_E_INVALID;
+    ctx->opSeq++;
     ctx->profiling = enabled != 0;
     return 0;
 }
@@ -1623,6 +1642,7 @@ int flx_write_tasks(flx_ctx *ctx, const uint32_t *slots_in)
 {
     if (!ctx)
         return FLX_E_INVALID;
+    ctx->opSeq++;
     REQUIRE(slots_in != nullptr, "flx_write_tasks: null source");
     CU(cudaSetDevice(ctx->device));
     CU(cudaMemcpyAsync(ctx->tasks, slots_in, (size_t)ctx->numTasks * FLX_NUM_SLOTS * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -1646,6 +1666,7 @@ int flx_write_queue(flx_ctx *ctx, int queue_id, const uint32_t *entries, uint32_
 {
     if (!ctx)
         return FLX_E_INVALID;
+    ctx->opSeq++;
     REQUIRE(queue_id >= 0 && queue_id < 8 && (entries || n == 0) && n <= ctx->numTasks, "flx_write_queue: bad arguments");
     CU(cudaSetDevice(ctx->device));
     if (n)
@@ -1658,6 +1679,7 @@ int flx_write_counters(flx_ctx *ctx, const flx_QueueCounters *in)
 {
     if (!ctx)
         return FLX_E_INVALID;
+    ctx->opSeq++;
     REQUIRE(in != nullptr, "flx_write_counters: null source");
     CU(cudaSetDevice(ctx->device));
     CU(cudaMemcpyAsync(ctx->counters, in, sizeof *in, cudaMemcpyHostToDevice, ctx->stream));
