@@ -76,6 +76,8 @@ _SIGNATURES = {
     "flx_scene_triangles": (_P, [_P]),
     "flx_scene_materials": (_P, [_P]),
     "flx_scene_texture_name": (C.c_char_p, [_P, C.c_uint32]),
+    "flx_hierarchy_export": (C.c_int, [C.c_char_p, _P, C.c_uint32, _P, C.c_uint32]),
+    "flx_hierarchy_import": (C.c_int, [C.c_char_p, _P, C.POINTER(C.c_uint32), _P, C.POINTER(C.c_uint32)]),
     "flx_envmap_load": (C.c_int, [C.c_char_p, C.POINTER(_P)]),
     "flx_envmap_from_rgb": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(_P)]),
     "flx_envmap_free": (None, [_P]),

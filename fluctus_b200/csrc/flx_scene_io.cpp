@@ -1025,6 +1025,106 @@ int flx_write_image(const char *path, const float *rgba, uint32_t width, uint32_
     return write_png(p, bytes.data(), width, height) ? 0 : FLX_E_INVALID;
 }
 
+// ---- the reference's hierarchy cache file (BVH::exportTo / importFrom, src/bvh.cpp:102-192; data/hierarchies/hierarchy_<hash>.bin,
+// src/tracer.cpp:574-590): u32 nIndices, indices, u32 "node count", then per node 6 floats (box), u32 iStart/rightChild,
+// i32 parent, u8 nPrims = 33 bytes.  The reference writes the INDEX count into the node-count field (src/bvh.cpp:185), so on
+// reading the field is ignored and the node count is taken from the file length; on writing the true count goes in, which
+// the reference's own importer reads correctly.
+int flx_hierarchy_export(const char *path, const flx_Node *nodes, uint32_t n_nodes, const uint32_t *indices, uint32_t n_indices)
+{
+    if (!path || !nodes || !indices || n_nodes == 0 || n_indices == 0)
+    {
+        g_io_error = "flx_hierarchy_export: bad arguments";
+        return FLX_E_INVALID;
+    }
+    FILE *fp = std::fopen(path, "wb");
+    if (!fp)
+    {
+        g_io_error = std::string("cannot create ") + path;
+        return FLX_E_INVALID;
+    }
+    std::vector<unsigned char> buf;
+    buf.reserve(8 + (size_t)n_indices * 4 + (size_t)n_nodes * 33);
+    auto put = [&](const void *p, size_t n) { buf.insert(buf.end(), (const unsigned char *)p, (const unsigned char *)p + n); };
+    put(&n_indices, 4);
+    put(indices, (size_t)n_indices * 4);
+    put(&n_nodes, 4);
+    for (uint32_t i = 0; i < n_nodes; i++)
+    {
+        const flx_Node &n = nodes[i];
+        const float box[6] = {n.bmin.x, n.bmin.y, n.bmin.z, n.bmax.x, n.bmax.y, n.bmax.z};
+        put(box, sizeof box);
+        put(&n.iStartOrRightChild, 4);
+        put(&n.parent, 4);
+        put(&n.nPrims, 1);
+    }
+    const bool ok = std::fwrite(buf.data(), 1, buf.size(), fp) == buf.size();
+    if (std::fclose(fp) != 0 || !ok)
+    {
+        g_io_error = std::string("write error on ") + path;
+        return FLX_E_INVALID;
+    }
+    return 0;
+}
+
+// Two-call protocol: with nodes_out == NULL only the counts are returned; then call again with arrays of that size.
+int flx_hierarchy_import(const char *path, flx_Node *nodes_out, uint32_t *n_nodes, uint32_t *indices_out, uint32_t *n_indices)
+{
+    if (!path || !n_nodes || !n_indices)
+    {
+        g_io_error = "flx_hierarchy_import: bad arguments";
+        return FLX_E_INVALID;
+    }
+    FILE *fp = std::fopen(path, "rb");
+    if (!fp)
+    {
+        g_io_error = std::string("cannot open ") + path;
+        return FLX_E_INVALID;
+    }
+    std::fseek(fp, 0, SEEK_END);
+    const long size = std::ftell(fp);
+    std::fseek(fp, 0, SEEK_SET);
+    std::vector<unsigned char> buf(size > 0 ? (size_t)size : 0);
+    const bool ok = buf.empty() || std::fread(buf.data(), 1, buf.size(), fp) == buf.size();
+    std::fclose(fp);
+    uint32_t ni = 0;
+    if (ok && buf.size() >= 4)
+        std::memcpy(&ni, buf.data(), 4);
+    const size_t nodesAt = 4 + (size_t)ni * 4 + 4;
+    if (!ok || buf.size() < 8 || ni == 0 || buf.size() < nodesAt + 33)
+    {
+        g_io_error = std::string(path) + ": not a hierarchy cache file";
+        return FLX_E_INVALID;
+    }
+    const uint32_t nn = (uint32_t)((buf.size() - nodesAt) / 33);
+    if (nodes_out && indices_out)
+    {
+        if (*n_nodes < nn || *n_indices < ni)
+        {
+            g_io_error = "flx_hierarchy_import: arrays too small";
+            return FLX_E_INVALID;
+        }
+        std::memcpy(indices_out, buf.data() + 4, (size_t)ni * 4);
+        for (uint32_t i = 0; i < nn; i++)
+        {
+            const unsigned char *p = buf.data() + nodesAt + (size_t)i * 33;
+            flx_Node n;
+            std::memset(&n, 0, sizeof n);
+            float box[6];
+            std::memcpy(box, p, 24);
+            n.bmin = f3(box[0], box[1], box[2]);
+            n.bmax = f3(box[3], box[4], box[5]);
+            std::memcpy(&n.iStartOrRightChild, p + 24, 4);
+            std::memcpy(&n.parent, p + 28, 4);
+            n.nPrims = p[32];
+            nodes_out[i] = n;
+        }
+    }
+    *n_nodes = nn;
+    *n_indices = ni;
+    return 0;
+}
+
 void flx_envmap_free(flx_envmap *e) { delete e; }
 int32_t flx_envmap_width(const flx_envmap *e) { return e ? e->w : 0; }
 int32_t flx_envmap_height(const flx_envmap *e) { return e ? e->h : 0; }

@@ -79,3 +79,24 @@ def write_image(path, rgba, width, height):
     assert rgba.size == width * height * 4
     if lib.flx_write_image(str(path).encode(), rgba.ctypes.data_as(C.c_void_p), int(width), int(height)) != 0:
         raise _io_error(lib, "flx_write_image(%s)" % path)
+
+
+def export_hierarchy(path, nodes, indices):
+    """BVH::exportTo (src/bvh.cpp:174-192): the reference's hierarchy cache file, with the true node count."""
+    lib = _lib.load()
+    nodes, indices = np.ascontiguousarray(nodes), np.ascontiguousarray(indices, np.uint32)
+    if lib.flx_hierarchy_export(str(path).encode(), nodes.ctypes.data_as(C.c_void_p), len(nodes), indices.ctypes.data_as(C.c_void_p), len(indices)) != 0:
+        raise _io_error(lib, "flx_hierarchy_export(%s)" % path)
+
+
+def import_hierarchy(path):
+    """BVH::importFrom (src/bvh.cpp:102-152) -> (nodes, indices); reads files written by the reference or by export_hierarchy."""
+    from .structs import NODE_DTYPE
+    lib = _lib.load()
+    nn, ni = C.c_uint32(), C.c_uint32()
+    if lib.flx_hierarchy_import(str(path).encode(), None, C.byref(nn), None, C.byref(ni)) != 0:
+        raise _io_error(lib, "flx_hierarchy_import(%s)" % path)
+    nodes, indices = np.zeros(nn.value, NODE_DTYPE), np.zeros(ni.value, np.uint32)
+    if lib.flx_hierarchy_import(str(path).encode(), nodes.ctypes.data_as(C.c_void_p), C.byref(nn), indices.ctypes.data_as(C.c_void_p), C.byref(ni)) != 0:
+        raise _io_error(lib, "flx_hierarchy_import(%s)" % path)
+    return nodes, indices

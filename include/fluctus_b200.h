@@ -265,6 +265,14 @@ const float *flx_envmap_prob(const flx_envmap *env);
 const int32_t *flx_envmap_alias(const flx_envmap *env);
 const float *flx_envmap_pdf(const flx_envmap *env);
 
+/* The reference's hierarchy cache file (BVH::exportTo / importFrom, src/bvh.cpp:102-192; `data/hierarchies/hierarchy_<hash>.bin`,
+ * src/tracer.cpp:574-590, 742-751), both directions, so caches can be exchanged with the reference.  The reference writes the
+ * index count where the node count belongs (src/bvh.cpp:185): the importer here derives the node count from the file length,
+ * the exporter writes the true count (which the reference's importer handles).  Import is a two-call protocol: pass NULL arrays
+ * to get the counts, then arrays of at least that size (n_nodes / n_indices in: capacity, out: count). */
+int flx_hierarchy_export(const char *path, const flx_Node *nodes, uint32_t n_nodes, const uint32_t *indices, uint32_t n_indices);
+int flx_hierarchy_import(const char *path, flx_Node *nodes_out, uint32_t *n_nodes, uint32_t *indices_out, uint32_t *n_indices);
+
 /* End-to-end convenience used by bench.py's e2e leg: host scene in, host image out, all copies included. */
 size_t flx_device_bytes(const flx_ctx *ctx);
 

@@ -266,10 +266,43 @@ int main(int argc, char **argv)
 {
     if (argc < 4)
     {
-        fprintf(stderr, "usage: scene_tool obj|ply|env <in> <out.bin>\n");
+        fprintf(stderr, "usage: scene_tool obj|ply|env <in> <out.bin>\n"
+                        "       scene_tool cache-export obj|ply <model> <cache.bin>      (reference SBVH -> BVH::exportTo, src/bvh.cpp:174-192)\n"
+                        "       scene_tool cache-import <cache.bin> <out.bin>            (BVH::importFrom, src/bvh.cpp:102-152 -> indices + 48-byte nodes)\n");
         return 2;
     }
     const std::string mode = argv[1], in = argv[2], out = argv[3];
+    if (mode == "cache-export") // the reference's hierarchy cache file, written by the reference's own code
+    {
+        if (argc < 5)
+            return 2;
+        SceneData s;
+        defaultMaterial(s);
+        const bool ok = (in == "obj") ? loadObj(argv[3], s) : loadPly(argv[3], s);
+        if (!ok || s.tris.empty())
+            return 1;
+        ProgressView pv(nullptr);
+        SBVH bvh(&s.tris, SplitMode::SAH, &pv);
+        bvh.exportTo(argv[4]);
+        return 0;
+    }
+    if (mode == "cache-import") // ... and read back by the reference's own code
+    {
+        std::vector<RTTriangle> none;
+        BVH bvh(&none, in);
+        const auto &nodes = CLContext::nodes(bvh);
+        const auto &idx = CLContext::indices(bvh);
+        std::vector<Node> nodesOut(nodes);
+        for (auto &n : nodesOut)
+            memset((unsigned char *)&n + 41, 0, 7);
+        FILE *f = fopen(out.c_str(), "wb");
+        const uint32_t ni = idx.size(), nn = nodesOut.size();
+        put(f, ni); put(f, nn);
+        fwrite(idx.data(), sizeof(U32), ni, f);
+        fwrite(nodesOut.data(), sizeof(Node), nn, f);
+        fclose(f);
+        return 0;
+    }
     if (mode == "env")
     {
         EnvironmentMap env(in);

@@ -87,6 +87,11 @@ def build_case(name, blob_loader=None):
     raise KeyError(name)
 
 
+def build_ref_dir():
+    from oracle import build_ref
+    return build_ref.reference_dir()
+
+
 IO_FIXTURES = (("obj", "tricky.obj"), ("ply", "tricky.ply"), ("ply", "plain.ply"), ("env", "small_rle.hdr"))
 
 
@@ -124,6 +129,9 @@ def make_io_expected():
                 (ln,) = struct.unpack_from("<I", buf, off); off += 4
                 names.append(buf[off:off + ln].decode()); off += ln
             out[key + "_textures"] = np.array(names, dtype="U128")
+    # the reference's hierarchy cache file for the teapot, written by the reference's own BVH::exportTo (src/bvh.cpp:174-192)
+    subprocess.run([tool, "cache-export", "ply", os.path.join(build_ref_dir(), "assets", "teapot.ply"), os.path.join(HERE, "io", "teapot_hierarchy.bin")],
+                   check=True, capture_output=True)
     fix = os.path.join(HERE, "io", "expected.npz")
     np.savez_compressed(fix, **out)
     print("io fixtures:", os.path.getsize(fix), "bytes")

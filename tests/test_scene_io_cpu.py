@@ -133,3 +133,100 @@ def test_png_and_hdr_writers_follow_saveImage(tmp_path):
     want = q * np.ldexp(np.float32(1.0), e - 8)[..., None].astype(np.float32)
     assert np.array_equal(back, np.where(v[..., None] >= 1e-32, want, 0).astype(np.float32))
     assert np.all(np.abs(back - lin) <= np.maximum(v[..., None] / 128.0, 1e-30))  # RGBE: 8-bit mantissa shared by the pixel
+
+
+# ---------------------------------------------------------------------------------------------- hierarchy cache file
+def test_hierarchy_cache_written_by_the_reference_is_read_correctly():
+    """tests/golden/io/teapot_hierarchy.bin was written by the reference's BVH::exportTo (src/bvh.cpp:174-192) for its SBVH
+    of teapot.ply; the same build is stored in the teapot golden fixture.  The file's node-count field holds the index
+    count (the reference's bug, src/bvh.cpp:185): 3290 instead of 2065 -- the importer must not believe it."""
+    from fluctus_b200.scene_io import import_hierarchy
+    z = np.load(os.path.join(os.path.dirname(IO), "teapot_c1.npz"))
+    nodes, indices = import_hierarchy(os.path.join(IO, "teapot_hierarchy.bin"))
+    raw = open(os.path.join(IO, "teapot_hierarchy.bin"), "rb").read()
+    (ni,) = struct.unpack_from("<I", raw, 0)
+    (field,) = struct.unpack_from("<I", raw, 4 + 4 * ni)
+    assert field == ni and field != len(nodes)
+    assert np.array_equal(indices, z["scene_indices"])
+    assert nodes.tobytes() == z["scene_nodes"].tobytes()
+
+
+def test_hierarchy_cache_round_trip_and_reference_importer(tmp_path):
+    from fluctus_b200.scene_io import export_hierarchy, import_hierarchy
+    from fluctus_b200.scene import make_room_scene
+    room = make_room_scene(materials="mixed", n_blobs=8)
+    path = tmp_path / "room_hierarchy.bin"
+    export_hierarchy(path, room.nodes, room.indices)
+    nodes, indices = import_hierarchy(path)
+    assert np.array_equal(indices, room.indices)
+    keep = ["bmin", "bmax", "parent", "link", "nPrims"]
+    assert all(np.array_equal(nodes[k], room.nodes[k]) for k in keep)
+    with pytest.raises(FluctusError):
+        import_hierarchy(os.path.join(IO, "tricky.obj"))
+    # the reference's own importer (BVH::importFrom, src/bvh.cpp:102-152) reads what the exporter wrote
+    tool = os.path.join(os.path.dirname(os.path.dirname(IO)), "..", "oracle", "_ref", "scene_tool")
+    if not os.path.exists(tool):
+        pytest.skip("oracle/_ref/scene_tool not built (needs /root/reference)")
+    import subprocess
+    out = tmp_path / "imported.bin"
+    subprocess.run([tool, "cache-import", str(path), str(out)], check=True, capture_output=True)
+    buf = open(out, "rb").read()
+    ni, nn = struct.unpack_from("<2I", buf, 0)
+    assert (ni, nn) == (len(room.indices), len(room.nodes))
+    from fluctus_b200.structs import NODE_DTYPE
+    assert np.array_equal(np.frombuffer(buf, np.uint32, ni, 8), room.indices)
+    back = np.frombuffer(buf, NODE_DTYPE, nn, 8 + 4 * ni)
+    assert all(np.array_equal(back[k], room.nodes[k]) for k in keep)
+
+
+def test_number_reader_matches_the_reference_loader_on_random_literals(tmp_path):
+    """4000 random decimal literals (signs, fractions of 0-19 digits, exponents, leading '+', '.5'-style and other forms the
+    loader rejects) go through both loaders as normals / texture coordinates of sane triangles: every float must come out
+    with the same bits.  (The loader's reader is not strtod: e.g. it scales fraction digits one by one.)"""
+    tool = os.path.join(os.path.dirname(os.path.dirname(IO)), "..", "oracle", "_ref", "scene_tool")
+    if not os.path.exists(tool):
+        pytest.skip("oracle/_ref/scene_tool not built (needs /root/reference)")
+    import subprocess
+    rng = np.random.default_rng(2024)
+
+    def literal():
+        kind = rng.integers(0, 10)
+        sign = ["", "", "-", "+"][rng.integers(0, 4)]
+        ip = str(rng.integers(0, 10 ** int(rng.integers(1, 10))))
+        fp = "".join(str(d) for d in rng.integers(0, 10, int(rng.integers(0, 20))))
+        ex = "%s%s%d" % ("eE"[rng.integers(0, 2)], ["", "-", "+"][rng.integers(0, 3)], rng.integers(0, 40))
+        if kind == 0:
+            return sign + ip
+        if kind == 1:
+            return sign + ip + "." + fp
+        if kind == 2:
+            return sign + ip + "." + fp + ex
+        if kind == 3:
+            return sign + ip + ex
+        if kind == 4:
+            return sign + "." + fp + "5"      # no integer part: the loader yields the default 0
+        if kind == 5:
+            return sign + ip + "." + fp + "e"  # empty exponent: default 0
+        if kind == 6:
+            return "%.9g" % rng.normal(0, 10.0 ** rng.integers(-8, 8))
+        if kind == 7:
+            return repr(float(np.float32(rng.uniform(-1, 1))))
+        if kind == 8:
+            return sign + "0." + "0" * int(rng.integers(0, 12)) + ip
+        return sign + ip + "." + fp + "x"     # trailing junk is ignored
+    n = 1000
+    path = tmp_path / "numbers.obj"
+    with open(path, "w") as f:
+        for i in range(n):
+            f.write("v %d 0 0\nv %d 1 0\nv %d 0 1\n" % (i, i, i))
+        for i in range(n):
+            f.write("vn %s %s %s\nvt %s\n" % (literal(), literal(), literal(), literal()))
+        for i in range(n):
+            f.write("f %d/%d/%d %d/%d/%d %d/%d/%d\n" % ((3 * i + 1, i + 1, i + 1, 3 * i + 2, i + 1, i + 1, 3 * i + 3, i + 1, i + 1)))
+    blob = tmp_path / "numbers.bin"
+    subprocess.run([tool, "obj", str(path), str(blob)], check=True, capture_output=True)
+    buf = open(blob, "rb").read()
+    nt = struct.unpack_from("<6I", buf, 0)[1]
+    want = np.frombuffer(buf, TRIANGLE_DTYPE, nt, 24)
+    got = load_model(path).tris
+    assert nt == n and got.tobytes() == want.tobytes()
