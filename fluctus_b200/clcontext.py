@@ -18,7 +18,7 @@ class FluctusError(RuntimeError):
 
 
 KERNEL_IDS = {"reset": 0, "raygen": 1, "extrays": 2, "shadowrays": 3, "logic": 4, "materials": 5, "end_iteration": 6, "postprocess": 7,
-              "mk_reset": 8, "mk_raygen": 9, "mk_next_vertex": 10, "mk_sample_bsdf": 11, "mk_splat": 12}
+              "mk_reset": 8, "mk_raygen": 9, "mk_next_vertex": 10, "mk_sample_bsdf": 11, "mk_splat": 12, "logic_fused": 13}
 
 
 class CLContext:
@@ -187,7 +187,7 @@ class CLContext:
         self._check(self._lib.flx_timer_end(self._h, C.byref(ms)), "timerEnd")
         return ms.value
 
-    TUNING = {"trace_variant": 0, "fetch_threshold": 1, "trace_blocks_per_sm": 2, "top_nodes": 3, "inner_min": 4, "logic_min_blocks": 5, "fetch_chunk": 6, "overlap_trace": 7, "postprocess_in_loop": 10, "smem_stack": 11, "max_l1": 12, "ext_min_blocks": 8, "shadow_min_blocks": 9}
+    TUNING = {"trace_variant": 0, "fetch_threshold": 1, "trace_blocks_per_sm": 2, "top_nodes": 3, "inner_min": 4, "logic_min_blocks": 5, "fetch_chunk": 6, "overlap_trace": 7, "postprocess_in_loop": 10, "smem_stack": 11, "max_l1": 12, "fuse_stages": 13, "fused_min_blocks": 14, "ext_min_blocks": 8, "shadow_min_blocks": 9}
 
     def setTuning(self, **kv):
         for k, v in kv.items():

@@ -69,6 +69,11 @@ struct flx_ctx
     // stream from the fork point recorded before the extension launch: the two stages have disjoint inputs and outputs, and the
     // main stream waits for the join before anything enqueued later, so the in-order semantics a caller sees are unchanged.
     unsigned long long opSeq = 0, extSeq = ~0ull;
+    // Deferred stages of the per-stage ABI (fuseStages): flx_enqueue_logic only notes the request (1), a flx_enqueue_raygen that
+    // follows directly is noted too (2), and a flx_enqueue_materials after that launches the fused kernel for all three --
+    // the order of the reference's loop (tracer.cpp:247-251 / 433-435).  ANY other call first launches what is pending as the
+    // separate kernels, so nothing a caller can observe differs from immediate execution.
+    int pendingStages = 0, pendingFirstIteration = 0;
     int postprocessInLoop = 1;        // flx_render runs the display pass every iteration, like the reference's loop (tracer.cpp:447)
     uint32_t numTasks = 0;
     std::string error;
@@ -134,6 +139,8 @@ struct flx_ctx
     int smemStack = 0;        // variant 1: first 24 stack levels in shared memory ([level][thread], conflict-free)
     int fetchChunk = 32;     // queue entries a warp reserves per atomic
     int logicMinBlocks = 3;   // resident 256-thread CTAs per SM the logic kernel is compiled for (register budget)
+    int fuseStages = 1;       // flx_render: logic + raygen + materials as one kernel
+    int fusedMinBlocks = 3;   // register budget of that kernel (1..4 resident CTAs of 256 per SM; 3 measured best)
     int innerMin = 8;         // leave the inner-node phase when fewer lanes than this are still at inner nodes
     int traceBlocksPerSM = 0; // 0: occupancy calculator
     int numSMs = 148;
@@ -308,11 +315,27 @@ void drainEvents(flx_ctx *c)
     c->pendingEvents.clear();
 }
 
-int checkReady(flx_ctx *ctx, bool needScene, bool needImage)
+int flushPending(flx_ctx *ctx);
+// every ABI call that observes or changes device state passes through here (see flx_ctx::opSeq, flx_ctx::pendingStages)
+int touch(flx_ctx *ctx, bool keepPending = false)
+{
+    ctx->opSeq++;
+    return keepPending ? 0 : flushPending(ctx);
+}
+#define TOUCH(ctx)                                                                                                     \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        int rc_ = touch(ctx);                                                                                          \
+        if (rc_)                                                                                                       \
+            return rc_;                                                                                                \
+    } while (0)
+
+int checkReady(flx_ctx *ctx, bool needScene, bool needImage, bool keepPending = false)
 {
     if (!ctx)
         return FLX_E_INVALID;
-    ctx->opSeq++;
+    if (int rcTouch = touch(ctx, keepPending))
+        return rcTouch;
     if (!ctx->paramsSet)
         return fail(ctx, FLX_E_NOT_READY, "flx_update_params has not been called");
     if (needImage && !ctx->pixels)
@@ -693,6 +716,7 @@ void flx_destroy(flx_ctx *c)
     if (!c)
         return;
     cudaSetDevice(c->device);
+    c->pendingStages = 0; // deferred stages nobody asked the result of
     if (c->stream)
         cudaStreamSynchronize(c->stream);
     flx_comm_destroy(c);
@@ -768,6 +792,7 @@ int flx_upload_scene(flx_ctx *ctx, const flx_Triangle *tris, uint32_t n_tris, co
 {
     if (!ctx)
         return FLX_E_INVALID;
+    TOUCH(ctx);
     REQUIRE(tris && indices && nodes && materials, "flx_upload_scene: null array");
     REQUIRE(n_tris > 0 && n_indices > 0 && n_nodes > 0 && n_materials > 0, "flx_upload_scene: empty scene");
     REQUIRE(n_tex == 0 || (tex_desc && tex_data), "flx_upload_scene: texture descriptors without data");
@@ -826,6 +851,7 @@ int flx_build_bvh(flx_ctx *ctx, const flx_Triangle *tris, uint32_t n_tris, uint3
 {
     if (!ctx)
         return FLX_E_INVALID;
+    TOUCH(ctx);
     REQUIRE(tris && nodes_out && n_nodes_out && indices_out, "flx_build_bvh: null array");
     REQUIRE(n_tris > 0 && n_tris < 0x40000000u, "flx_build_bvh: triangle count out of range");
     REQUIRE(max_leaf >= 1 && max_leaf <= 255, "flx_build_bvh: max_leaf must be in 1..255 (nPrims is a byte, src/bvhnode.hpp:58)");
@@ -937,6 +963,7 @@ int flx_upload_envmap(flx_ctx *ctx, const float *rgb, int32_t w, int32_t h, cons
 {
     if (!ctx)
         return FLX_E_INVALID;
+    TOUCH(ctx);
     REQUIRE(rgb && prob && alias && pdf && w > 0 && h > 0, "flx_upload_envmap: bad arguments");
     const size_t n = (size_t)w * h;
     for (size_t i = 0; i < n; i++)
@@ -996,6 +1023,7 @@ int flx_resize(flx_ctx *ctx, uint32_t width, uint32_t height)
 {
     if (!ctx)
         return FLX_E_INVALID;
+    TOUCH(ctx);
     REQUIRE(width > 0 && height > 0 && (uint64_t)width * height < 0x7fffffffull, "flx_resize: bad image size");
     ctx->width = width;
     ctx->height = height;
@@ -1006,6 +1034,7 @@ int flx_set_tile(flx_ctx *ctx, uint32_t part, uint32_t n_parts, uint32_t stripe_
 {
     if (!ctx)
         return FLX_E_INVALID;
+    TOUCH(ctx);
     REQUIRE(n_parts > 0 && part < n_parts && stripe_rows > 0, "flx_set_tile: bad arguments");
     ctx->part = part;
     ctx->nParts = n_parts;
@@ -1019,6 +1048,7 @@ int flx_update_params(flx_ctx *ctx, const flx_RenderParams *p)
 {
     if (!ctx)
         return FLX_E_INVALID;
+    TOUCH(ctx);
     REQUIRE(p != nullptr, "flx_update_params: null params");
     REQUIRE(p->width > 0 && p->height > 0, "flx_update_params: empty image");
     if (ctx->pixels && (p->width != ctx->width || p->height != ctx->height))
@@ -1041,15 +1071,26 @@ int flx_enqueue_reset(flx_ctx *ctx)
     return launchCheck(ctx, "k_reset");
 }
 
-int flx_enqueue_raygen(flx_ctx *ctx)
+static int launchRaygen(flx_ctx *ctx)
 {
-    int rc = checkReady(ctx, false, true);
-    if (rc)
-        return rc;
-    CU(cudaSetDevice(ctx->device));
     Timed tm(ctx, FLX_K_RAYGEN);
     k_raygen<<<streamingGrid(ctx->numTasks), FLX_BLOCK, 0, ctx->stream>>>(makeFrame(ctx), ctx->params);
     return launchCheck(ctx, "k_raygen");
+}
+
+int flx_enqueue_raygen(flx_ctx *ctx)
+{
+    const bool afterLogic = ctx && ctx->pendingStages == 1;
+    int rc = checkReady(ctx, false, true, afterLogic);
+    if (rc)
+        return rc;
+    if (afterLogic) // logic is pending and this is the call that follows it in the reference's loop: keep deferring
+    {
+        ctx->pendingStages = 2;
+        return 0;
+    }
+    CU(cudaSetDevice(ctx->device));
+    return launchRaygen(ctx);
 }
 
 int flx_enqueue_extrays(flx_ctx *ctx)
@@ -1106,21 +1147,42 @@ int flx_enqueue_shadowrays(flx_ctx *ctx)
     return 0;
 }
 
-int flx_enqueue_logic(flx_ctx *ctx, int first_iteration)
+// wf_logic alone, or (fused) wf_logic + wf_raygen + wf_mat_* in one pass over the path state (k_logic<.., FUSED>)
+static int launchLogic(flx_ctx *ctx, int first_iteration, bool fused)
 {
-    int rc = checkReady(ctx, true, true);
-    if (rc)
-        return rc;
-    CU(cudaSetDevice(ctx->device));
     const uint32_t maxId = first_iteration ? std::min(ctx->tilePixels, ctx->numTasks) : ctx->numTasks; // wf_logic.cl:45
     const uint32_t tiles = (maxId + FLX_LOGIC_TILE - 1) / FLX_LOGIC_TILE;
     CU(cudaMemsetAsync(ctx->scanTiles, 0, (size_t)tiles * sizeof(unsigned long long), ctx->stream));
     CU(cudaMemsetAsync(ctx->scanTicket, 0, sizeof(uint32_t), ctx->stream));
     ScanState scan{ctx->scanTiles, ctx->scanTicket};
-    Timed tm(ctx, FLX_K_LOGIC);
+    Timed tm(ctx, fused ? FLX_K_LOGIC_FUSED : FLX_K_LOGIC);
     const Frame fr = makeFrame(ctx);
     const SceneView sc = makeScene(ctx);
     const bool sep = ctx->params.wfSeparateQueues != 0;
+    if (fused)
+    {
+        if (ctx->fusedMinBlocks == 4)
+        {
+            if (sep) k_logic<true, 4, true><<<tiles, FLX_BLOCK, 0, ctx->stream>>>(fr, ctx->params, sc, scan, maxId);
+            else k_logic<false, 4, true><<<tiles, FLX_BLOCK, 0, ctx->stream>>>(fr, ctx->params, sc, scan, maxId);
+        }
+        else if (ctx->fusedMinBlocks == 3)
+        {
+            if (sep) k_logic<true, 3, true><<<tiles, FLX_BLOCK, 0, ctx->stream>>>(fr, ctx->params, sc, scan, maxId);
+            else k_logic<false, 3, true><<<tiles, FLX_BLOCK, 0, ctx->stream>>>(fr, ctx->params, sc, scan, maxId);
+        }
+        else if (ctx->fusedMinBlocks == 1)
+        {
+            if (sep) k_logic<true, 1, true><<<tiles, FLX_BLOCK, 0, ctx->stream>>>(fr, ctx->params, sc, scan, maxId);
+            else k_logic<false, 1, true><<<tiles, FLX_BLOCK, 0, ctx->stream>>>(fr, ctx->params, sc, scan, maxId);
+        }
+        else
+        {
+            if (sep) k_logic<true, 2, true><<<tiles, FLX_BLOCK, 0, ctx->stream>>>(fr, ctx->params, sc, scan, maxId);
+            else k_logic<false, 2, true><<<tiles, FLX_BLOCK, 0, ctx->stream>>>(fr, ctx->params, sc, scan, maxId);
+        }
+        return launchCheck(ctx, "k_logic<fused>");
+    }
 #define LOGIC(SEP, MB) k_logic<SEP, MB><<<tiles, FLX_BLOCK, 0, ctx->stream>>>(fr, ctx->params, sc, scan, maxId)
     switch (ctx->logicMinBlocks)
     {
@@ -1132,12 +1194,52 @@ int flx_enqueue_logic(flx_ctx *ctx, int first_iteration)
     return launchCheck(ctx, "k_logic");
 }
 
-int flx_enqueue_materials(flx_ctx *ctx)
+int flx_enqueue_logic(flx_ctx *ctx, int first_iteration)
 {
     int rc = checkReady(ctx, true, true);
     if (rc)
         return rc;
     CU(cudaSetDevice(ctx->device));
+    if (ctx->fuseStages) // launched by whatever comes next: fused if that is raygen + materials, on its own otherwise
+    {
+        ctx->pendingStages = 1;
+        ctx->pendingFirstIteration = first_iteration;
+        return 0;
+    }
+    return launchLogic(ctx, first_iteration, false);
+}
+
+extern "C++"
+{
+namespace
+{
+int flushPending(flx_ctx *ctx)
+{
+    const int pending = ctx->pendingStages;
+    if (!pending)
+        return 0;
+    ctx->pendingStages = 0;
+    CU(cudaSetDevice(ctx->device));
+    int rc = launchLogic(ctx, ctx->pendingFirstIteration, false);
+    if (rc == 0 && pending == 2)
+        rc = launchRaygen(ctx);
+    return rc;
+}
+} // namespace
+} // extern "C++"
+
+int flx_enqueue_materials(flx_ctx *ctx)
+{
+    const bool completesIteration = ctx && ctx->pendingStages == 2;
+    int rc = checkReady(ctx, true, true, completesIteration);
+    if (rc)
+        return rc;
+    CU(cudaSetDevice(ctx->device));
+    if (completesIteration) // logic, raygen, materials arrived back to back: one pass over the path state does all three
+    {
+        ctx->pendingStages = 0;
+        return launchLogic(ctx, ctx->pendingFirstIteration, true);
+    }
     const unsigned grid = streamingGrid(ctx->numTasks);
     const Frame fr = makeFrame(ctx);
     const SceneView sc = makeScene(ctx);
@@ -1286,6 +1388,7 @@ int flx_read_preview(flx_ctx *ctx, float *rgba, size_t n_pixels)
 {
     if (!ctx)
         return FLX_E_INVALID;
+    TOUCH(ctx);
     REQUIRE(rgba != nullptr, "flx_read_preview: null destination");
     REQUIRE(ctx->preview && n_pixels <= ctx->tilePixels, "flx_read_preview: more pixels requested than the context owns");
     CU(cudaSetDevice(ctx->device));
@@ -1298,7 +1401,7 @@ int flx_enqueue_clear_queues(flx_ctx *ctx)
 {
     if (!ctx)
         return FLX_E_INVALID;
-    ctx->opSeq++;
+    TOUCH(ctx);
     CU(cudaSetDevice(ctx->device));
     CU(cudaMemsetAsync(ctx->counters, 0, sizeof(flx_QueueCounters), ctx->stream));
     return 0;
@@ -1308,7 +1411,7 @@ int flx_enqueue_get_counters(flx_ctx *ctx, flx_QueueCounters *host_out)
 {
     if (!ctx)
         return FLX_E_INVALID;
-    ctx->opSeq++;
+    TOUCH(ctx);
     REQUIRE(host_out != nullptr, "flx_enqueue_get_counters: null destination");
     CU(cudaSetDevice(ctx->device));
     if ((int)ctx->pendingCounterReads.size() >= flx_ctx::kCounterRing)
@@ -1328,7 +1431,7 @@ int flx_finish(flx_ctx *ctx)
 {
     if (!ctx)
         return FLX_E_INVALID;
-    ctx->opSeq++;
+    TOUCH(ctx);
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
     for (auto &r : ctx->pendingCounterReads)
@@ -1342,7 +1445,7 @@ int flx_update_pixel_index(flx_ctx *ctx, uint32_t num_pixels, uint32_t num_new_p
 {
     if (!ctx)
         return FLX_E_INVALID;
-    ctx->opSeq++;
+    TOUCH(ctx);
     REQUIRE(num_pixels > 0, "flx_update_pixel_index: zero pixels");
     CU(cudaSetDevice(ctx->device));
     // reference: host-tracked index, advanced and written with a NON-blocking 4-byte copy (clcontext.cpp:891-895).  Same here;
@@ -1369,7 +1472,7 @@ int flx_reset_pixel_index(flx_ctx *ctx)
 {
     if (!ctx)
         return FLX_E_INVALID;
-    ctx->opSeq++;
+    TOUCH(ctx);
     CU(cudaSetDevice(ctx->device));
     ctx->hostPixelIdx = 0;
     ctx->pixelIdxAdvancedOnDevice = false;
@@ -1388,12 +1491,20 @@ int flx_render(flx_ctx *ctx, uint32_t n_iterations)
         ctx->pixelIdxAdvancedOnDevice = true;
     for (uint32_t i = 0; i < n_iterations; i++) // tracer.cpp:433-439, 465
     {
-        if ((rc = flx_enqueue_logic(ctx, 0)))
-            return rc;
-        if ((rc = flx_enqueue_raygen(ctx)))
-            return rc;
-        if ((rc = flx_enqueue_materials(ctx)))
-            return rc;
+        if (ctx->fuseStages) // logic + raygen + materials in one pass over the path state; same state, queues and counters
+        {
+            if ((rc = launchLogic(ctx, 0, true)))
+                return rc;
+        }
+        else
+        {
+            if ((rc = flx_enqueue_logic(ctx, 0)))
+                return rc;
+            if ((rc = flx_enqueue_raygen(ctx)))
+                return rc;
+            if ((rc = flx_enqueue_materials(ctx)))
+                return rc;
+        }
         k_snapshot_counters<<<1, 32, 0, ctx->stream>>>(it);
         // extension then shadow rays: the second call overlaps the first on a second stream (see flx_enqueue_shadowrays)
         if ((rc = flx_enqueue_extrays(ctx)))
@@ -1416,6 +1527,7 @@ int flx_render_timed(flx_ctx *ctx, uint32_t n_iterations, float *elapsed_ms)
 {
     if (!ctx)
         return FLX_E_INVALID;
+    TOUCH(ctx);
     REQUIRE(elapsed_ms != nullptr, "flx_render_timed: null destination");
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -1434,7 +1546,7 @@ int flx_timer_begin(flx_ctx *ctx)
 {
     if (!ctx)
         return FLX_E_INVALID;
-    ctx->opSeq++;
+    TOUCH(ctx);
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaEventRecord(ctx->evStart, ctx->stream));
@@ -1445,7 +1557,7 @@ int flx_timer_end(flx_ctx *ctx, float *elapsed_ms)
 {
     if (!ctx)
         return FLX_E_INVALID;
-    ctx->opSeq++;
+    TOUCH(ctx);
     REQUIRE(elapsed_ms != nullptr, "flx_timer_end: null destination");
     CU(cudaSetDevice(ctx->device));
     CU(cudaEventRecord(ctx->evStop, ctx->stream));
@@ -1459,7 +1571,7 @@ int flx_set_tuning(flx_ctx *ctx, int key, int value)
 {
     if (!ctx)
         return FLX_E_INVALID;
-    ctx->opSeq++;
+    TOUCH(ctx);
     switch (key)
     {
     case FLX_TUNE_TRACE_VARIANT:
@@ -1499,6 +1611,13 @@ int flx_set_tuning(flx_ctx *ctx, int key, int value)
         REQUIRE(value == 2 || value == 3 || value == 4, "flx_set_tuning: logic min blocks must be 2, 3 or 4");
         ctx->logicMinBlocks = value;
         return 0;
+    case FLX_TUNE_FUSE_STAGES:
+        ctx->fuseStages = value != 0;
+        return 0;
+    case FLX_TUNE_FUSED_MIN_BLOCKS:
+        REQUIRE(value >= 1 && value <= 4, "flx_set_tuning: fused min blocks must be 1..4");
+        ctx->fusedMinBlocks = value;
+        return 0;
     case FLX_TUNE_TOP_NODES:
         REQUIRE(value >= 0 && value <= 4096, "flx_set_tuning: top nodes must be in 0..4096");
         ctx->topNodes = value;
@@ -1515,7 +1634,7 @@ int flx_set_counting(flx_ctx *ctx, int enabled)
 {
     if (!ctx)
         return FLX_E_INVALID;
-    ctx->opSeq++;
+    TOUCH(ctx);
     CU(cudaSetDevice(ctx->device));
     ctx->counting = enabled != 0;
     if (ctx->counting)
@@ -1527,6 +1646,7 @@ int flx_get_trace_counts(flx_ctx *ctx, flx_TraceCounts *ext, flx_TraceCounts *sh
 {
     if (!ctx)
         return FLX_E_INVALID;
+    TOUCH(ctx);
     REQUIRE(ext && shadow, "flx_get_trace_counts: null destination");
     CU(cudaSetDevice(ctx->device));
     unsigned long long h[10];
@@ -1548,7 +1668,7 @@ int flx_reset_stats(flx_ctx *ctx)
 {
     if (!ctx)
         return FLX_E_INVALID;
-    ctx->opSeq++;
+    TOUCH(ctx);
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
     drainEvents(ctx);
@@ -1565,6 +1685,7 @@ int flx_get_stats(flx_ctx *ctx, flx_RenderStats64 *out)
 {
     if (!ctx)
         return FLX_E_INVALID;
+    TOUCH(ctx);
     REQUIRE(out != nullptr, "flx_get_stats: null destination");
     CU(cudaSetDevice(ctx->device));
     CU(cudaMemcpyAsync(out, ctx->stats, sizeof *out, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1576,7 +1697,7 @@ int flx_set_profiling(flx_ctx *ctx, int enabled)
 {
     if (!ctx)
         return FLX_E_INVALID;
-    ctx->opSeq++;
+    TOUCH(ctx);
     ctx->profiling = enabled != 0;
     return 0;
 }
@@ -1585,6 +1706,7 @@ int flx_get_kernel_ms(flx_ctx *ctx, int kernel_id, float *total_ms, uint32_t *la
 {
     if (!ctx)
         return FLX_E_INVALID;
+    TOUCH(ctx);
     REQUIRE(kernel_id >= 0 && kernel_id < FLX_K_COUNT, "flx_get_kernel_ms: bad kernel id");
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -1600,6 +1722,7 @@ int flx_read_pixels(flx_ctx *ctx, float *rgba, size_t n_pixels)
 {
     if (!ctx)
         return FLX_E_INVALID;
+    TOUCH(ctx);
     REQUIRE(rgba != nullptr, "flx_read_pixels: null destination");
     REQUIRE(ctx->pixels && n_pixels <= ctx->tilePixels, "flx_read_pixels: more pixels requested than the context owns");
     CU(cudaSetDevice(ctx->device));
@@ -1631,6 +1754,7 @@ int flx_read_tasks(flx_ctx *ctx, uint32_t *slots_out)
 {
     if (!ctx)
         return FLX_E_INVALID;
+    TOUCH(ctx);
     REQUIRE(slots_out != nullptr, "flx_read_tasks: null destination");
     CU(cudaSetDevice(ctx->device));
     CU(cudaMemcpyAsync(slots_out, ctx->tasks, (size_t)ctx->numTasks * FLX_NUM_SLOTS * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1642,7 +1766,7 @@ int flx_write_tasks(flx_ctx *ctx, const uint32_t *slots_in)
 {
     if (!ctx)
         return FLX_E_INVALID;
-    ctx->opSeq++;
+    TOUCH(ctx);
     REQUIRE(slots_in != nullptr, "flx_write_tasks: null source");
     CU(cudaSetDevice(ctx->device));
     CU(cudaMemcpyAsync(ctx->tasks, slots_in, (size_t)ctx->numTasks * FLX_NUM_SLOTS * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -1654,6 +1778,7 @@ int flx_read_queue(flx_ctx *ctx, int queue_id, uint32_t *out, uint32_t max_entri
 {
     if (!ctx)
         return FLX_E_INVALID;
+    TOUCH(ctx);
     REQUIRE(queue_id >= 0 && queue_id < 8 && out, "flx_read_queue: bad arguments");
     CU(cudaSetDevice(ctx->device));
     const uint32_t n = std::min(max_entries, ctx->numTasks);
@@ -1666,7 +1791,7 @@ int flx_write_queue(flx_ctx *ctx, int queue_id, const uint32_t *entries, uint32_
 {
     if (!ctx)
         return FLX_E_INVALID;
-    ctx->opSeq++;
+    TOUCH(ctx);
     REQUIRE(queue_id >= 0 && queue_id < 8 && (entries || n == 0) && n <= ctx->numTasks, "flx_write_queue: bad arguments");
     CU(cudaSetDevice(ctx->device));
     if (n)
@@ -1679,7 +1804,7 @@ int flx_write_counters(flx_ctx *ctx, const flx_QueueCounters *in)
 {
     if (!ctx)
         return FLX_E_INVALID;
-    ctx->opSeq++;
+    TOUCH(ctx);
     REQUIRE(in != nullptr, "flx_write_counters: null source");
     CU(cudaSetDevice(ctx->device));
     CU(cudaMemcpyAsync(ctx->counters, in, sizeof *in, cudaMemcpyHostToDevice, ctx->stream));
@@ -1711,6 +1836,7 @@ int flx_comm_init(flx_ctx *ctx, const void *unique_id128, int rank, int nranks)
 {
     if (!ctx)
         return FLX_E_INVALID;
+    TOUCH(ctx);
     REQUIRE(unique_id128 && nranks > 0 && rank >= 0 && rank < nranks, "flx_comm_init: bad arguments");
     int rc = loadNccl(ctx);
     if (rc)

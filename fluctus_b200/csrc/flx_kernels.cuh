@@ -101,6 +101,41 @@ FLX_DEV void local_pixel_to_xy(const Frame &fr, uint32_t width, uint32_t local, 
     y = (stripe * fr.nParts + fr.part) * fr.stripeRows + within;
 }
 
+// one regenerated camera path (wf_raygen.cl:25-96): pixel, jitter, thin lens, reset of the per-path state
+FLX_DEV void raygen_path(const Frame &fr, const flx_RenderParams &prm, uint32_t gid, uint32_t pixelIdx, uint32_t seed)
+{
+    const Tasks &t = fr.tasks;
+    t.setu(FLX_S_PIXEL_INDEX, gid, pixelIdx);
+    uint32_t px, py;
+    local_pixel_to_xy(fr, prm.width, pixelIdx, px, py);
+    float x = (float)px, y = (float)py;
+    x += flx_rand(seed);
+    y += flx_rand(seed);
+    const float NDCx = x / (float)prm.width, NDCy = y / (float)prm.height;
+    float SCRx = 2.0f * NDCx - 1.0f, SCRy = 2.0f * NDCy - 1.0f;
+    SCRx *= (float)prm.width / (float)prm.height;
+    SCRx *= fr.tanHalfFov;
+    SCRy *= fr.tanHalfFov;
+
+    const V3 camPos = v3(prm.camera.pos), camRight = v3(prm.camera.right), camUp = v3(prm.camera.up), camDir = v3(prm.camera.dir);
+    V3 rayOrig = camPos;
+    const V3 target = ((rayOrig + camRight * SCRx) + camUp * SCRy) + camDir;
+    V3 rayDir = norm3(target - rayOrig);
+
+    // thin lens (wf_raygen.cl:59-63; disk sample utils.cl:75-80)
+    const V3 fp = camPos + rayDir * prm.camera.focalDist;
+    const float sqrt_r = sqrtf(flx_rand(seed));
+    const float th = FLX_2PI_F * flx_rand(seed);
+    const float rx = sqrt_r * flx_cosf(th), ry = sqrt_r * flx_sinf(th);
+    rayOrig = rayOrig + (prm.worldRadius * prm.camera.apertureSize) * (camRight * rx + camUp * ry);
+    rayDir = norm3(fp - rayOrig);
+
+    t.setv(FLX_S_ORIG, gid, rayOrig);
+    t.setv(FLX_S_DIR, gid, rayDir);
+    t.setu(FLX_S_SEED, gid, seed);
+    reset_path_fields(t, gid, prm.worldRadius);
+}
+
 __global__ void __launch_bounds__(FLX_BLOCK) k_raygen(const __grid_constant__ Frame fr, const __grid_constant__ flx_RenderParams prm)
 {
     const uint32_t count = fr.counters->raygenQueue;
@@ -117,40 +152,7 @@ __global__ void __launch_bounds__(FLX_BLOCK) k_raygen(const __grid_constant__ Fr
         if (valid)
         {
         gid = fr.queues[Q_RAYGEN][gd];
-        const Tasks &t = fr.tasks;
-        uint32_t seed = t.u(FLX_S_SEED, gid);
-
-        const uint32_t pixelIdx = (curr + gd) % fr.tilePixels;
-        t.setu(FLX_S_PIXEL_INDEX, gid, pixelIdx);
-        uint32_t px, py;
-        local_pixel_to_xy(fr, prm.width, pixelIdx, px, py);
-        float x = (float)px, y = (float)py;
-        x += flx_rand(seed);
-        y += flx_rand(seed);
-        const float NDCx = x / (float)prm.width, NDCy = y / (float)prm.height;
-        float SCRx = 2.0f * NDCx - 1.0f, SCRy = 2.0f * NDCy - 1.0f;
-        SCRx *= (float)prm.width / (float)prm.height;
-        SCRx *= fr.tanHalfFov;
-        SCRy *= fr.tanHalfFov;
-
-        const V3 camPos = v3(prm.camera.pos), camRight = v3(prm.camera.right), camUp = v3(prm.camera.up), camDir = v3(prm.camera.dir);
-        V3 rayOrig = camPos;
-        const V3 target = ((rayOrig + camRight * SCRx) + camUp * SCRy) + camDir;
-        V3 rayDir = norm3(target - rayOrig);
-
-        // thin lens (wf_raygen.cl:59-63; disk sample utils.cl:75-80)
-        const V3 fp = camPos + rayDir * prm.camera.focalDist;
-        const float sqrt_r = sqrtf(flx_rand(seed));
-        const float th = FLX_2PI_F * flx_rand(seed);
-        const float rx = sqrt_r * flx_cosf(th), ry = sqrt_r * flx_sinf(th);
-        rayOrig = rayOrig + (prm.worldRadius * prm.camera.apertureSize) * (camRight * rx + camUp * ry);
-        rayDir = norm3(fp - rayOrig);
-
-        t.setv(FLX_S_ORIG, gid, rayOrig);
-        t.setv(FLX_S_DIR, gid, rayDir);
-        t.setu(FLX_S_SEED, gid, seed);
-        reset_path_fields(t, gid, prm.worldRadius);
-
+        raygen_path(fr, prm, gid, (curr + gd) % fr.tilePixels, fr.tasks.u(FLX_S_SEED, gid));
         }
         __syncthreads();
         if (valid)
@@ -288,7 +290,42 @@ FLX_DEV void st_relaxed(unsigned long long *p, unsigned long long v) { asm volat
 
 FLX_DEV float luminance3(V3 v) { return (0.212671f * v.x + 0.715160f * v.y) + 0.072169f * v.z; } // utils.cl:237-240
 
-template <bool SEPARATE_QUEUES, int MIN_BLOCKS>
+// one path through its material (wf_mat_*.cl:33-62): BSDF value and pdf toward the pending light sample, then the continuation ray
+template <int MASK>
+FLX_DEV void material_path(const Tasks &t, const SceneView &sc, uint32_t gid, const Surface &s, const Mat &mat, bool backface, V3 dirIn, V3 L, V3 oldT, uint32_t seed)
+{
+    // BSDF value and pdf toward the pending light sample (wf_mat_*.cl:33-36)
+    const V3 bsdfNEE = bxdf_eval<MASK>(s, mat, backface, sc, dirIn, L);
+    const float bsdfPdfW = fmaxf(0.0f, bxdf_pdf<MASK>(s, mat, backface, sc, dirIn, L));
+    t.setv(FLX_S_LAST_BSDF, gid, bsdfNEE);
+    t.setf(FLX_S_LAST_PDF_IMPLICIT, gid, bsdfPdfW);
+
+    // continuation (wf_mat_*.cl:38-62)
+    float pdfW = 0.0f;
+    V3 newDir = v3(0.0f);
+    const V3 bsdf = bxdf_sample<MASK>(s, mat, backface, sc, dirIn, newDir, pdfW, seed);
+    const float costh = dot3(s.N, norm3(newDir));
+    V3 newT = v3(0.0f);
+    if (!(pdfW == 0.0f || is_zero3(bsdf)))
+        newT = ((oldT * bsdf) * costh) / pdfW;
+    const V3 orig = s.P + 1e-4f * newDir;
+    t.setv(FLX_S_LAST_T, gid, oldT);
+    t.setv(FLX_S_T, gid, newT);
+    t.setv(FLX_S_ORIG, gid, orig);
+    t.setv(FLX_S_DIR, gid, newDir);
+    t.setf(FLX_S_LAST_PDF_W, gid, pdfW);
+    t.setu(FLX_S_SEED, gid, seed);
+    t.setu(FLX_S_LAST_SPECULAR, gid, (mat.type & (FLX_BXDF_IDEAL_REFLECTION | FLX_BXDF_IDEAL_DIELECTRIC)) != 0 ? 1u : 0u);
+}
+
+
+// FUSED: the same thread also does what wf_raygen (for a path it has just terminated) and wf_mat_* (for a path it sends on)
+// would do next, instead of leaving that to two more passes over the path state.  Nothing crosses paths between those three
+// stages except the queue counters and the raygen-queue rank (known here from the look-back scan), so the state, the queues and
+// the counters after this one launch are exactly those after logic + raygen + materials.  Used by flx_render (and by the
+// per-stage ABI when the three calls arrive back to back, flx_api.cu); what it saves is the sparse second and third pass:
+// raygen touches ~1 in 5 paths (one 32-byte sector per 4 bytes used), the material stage re-reads what logic had in registers.
+template <bool SEPARATE_QUEUES, int MIN_BLOCKS, bool FUSED = false>
 __global__ void __launch_bounds__(FLX_BLOCK, MIN_BLOCKS) k_logic(const __grid_constant__ Frame fr, const __grid_constant__ flx_RenderParams prm, const SceneView sc,
                                                      const ScanState scan, const uint32_t maxId)
 {
@@ -423,12 +460,18 @@ __global__ void __launch_bounds__(FLX_BLOCK, MIN_BLOCKS) k_logic(const __grid_co
         {
             if (len > 0u)
                 atomicAdd(reinterpret_cast<float4 *>(fr.pixels) + pixIdx, make_float4(Ei.x, Ei.y, Ei.z, 1.0f)); // one 128-bit reduction
-            t.setu(FLX_S_SEED, gid, seed);
+            if (!FUSED) // FUSED: the camera-ray part below carries the seed on and stores it
+                t.setu(FLX_S_SEED, gid, seed);
         }
     }
 
     bool toMaterial = false, pushShadow = false;
     int matType = 0;
+    // FUSED: what the material part at the end of the kernel needs (dead code otherwise)
+    Mat fMat;
+    Surface fS;
+    bool fBackface = false, fHaveL = false;
+    V3 fL = v3(0.0f);
     if (live && !terminate)
     {
         Surface s;
@@ -446,6 +489,8 @@ __global__ void __launch_bounds__(FLX_BLOCK, MIN_BLOCKS) k_logic(const __grid_co
         t.setv(FLX_S_N, gid, N);
         t.setu(FLX_S_BACKFACE, gid, backface ? 1u : 0u);
 
+        bool wroteL = false; // FUSED: the light direction the material stage would read back from the shadowDir slot
+        V3 newL = v3(0.0f);
         const bool singular = (mat.type & (FLX_BXDF_IDEAL_REFLECTION | FLX_BXDF_IDEAL_DIELECTRIC)) != 0;
         if (prm.sampleExpl && !singular)
         {
@@ -470,6 +515,8 @@ __global__ void __launch_bounds__(FLX_BLOCK, MIN_BLOCKS) k_logic(const __grid_co
                 t.setf(FLX_S_LAST_LIGHT_PICK, gid, envMapProb);
                 t.setv(FLX_S_LAST_EMISSION, gid, Li);
                 pushShadow = true;
+                wroteL = true;
+                newL = L;
             }
             if (useArea)
             {
@@ -497,15 +544,26 @@ __global__ void __launch_bounds__(FLX_BLOCK, MIN_BLOCKS) k_logic(const __grid_co
                     t.setf(FLX_S_LAST_LIGHT_PICK, gid, lightPickProb);
                     t.setv(FLX_S_LAST_EMISSION, gid, v3(A.E));
                     pushShadow = true;
+                    wroteL = true;
+                    newL = L;
                 }
                 else
                     t.setu(FLX_S_SHADOW_BLOCKED, gid, 1u);
             }
         }
-        t.setu(FLX_S_SEED, gid, seed);
         toMaterial = true;
         matType = mat.type;
-
+        if (FUSED) // the material part runs at the very end, after the last barrier (threads with heavy BSDFs would otherwise hold up their CTA)
+        {
+            fMat = mat;
+            fS = s;
+            fS.N = N; // the material stage reads the flipped shading normal logic has just stored
+            fBackface = backface;
+            fHaveL = wroteL;
+            fL = newL;
+        }
+        else
+            t.setu(FLX_S_SEED, gid, seed);
     }
 
     // ---- shadow + material queues: ONE atomic per queue per 256-path tile.  All paths of a tile hammer the same
@@ -513,10 +571,10 @@ __global__ void __launch_bounds__(FLX_BLOCK, MIN_BLOCKS) k_logic(const __grid_co
     //      (ballot -> per-warp counts in shared memory -> one atomicAdd by one thread per queue) cuts them 8x versus the
     //      per-warp aggregation the reference's NVIDIA path does (wf_logic.cl:459-519, ptx_asm.cl:83-111).
     {
-        constexpr int NQ = SEPARATE_QUEUES ? 6 : 2; // slot 0: shadow, slots 1..: material queues
+        constexpr int NQ = SEPARATE_QUEUES ? 6 : 2; // slot 0: shadow, slots 1..: material queues; FUSED: slot NQ = extension queue
         constexpr int NW = FLX_BLOCK / 32;
-        __shared__ uint32_t s_cnt[6][NW];
-        __shared__ uint32_t s_qbase[6];
+        __shared__ uint32_t s_cnt[7][NW];
+        __shared__ uint32_t s_qbase[7];
         int q = -1; // material queue slot of this path (1-based), -1: none
         if (toMaterial)
         {
@@ -540,14 +598,19 @@ __global__ void __launch_bounds__(FLX_BLOCK, MIN_BLOCKS) k_logic(const __grid_co
             if (q == k)
                 myMask = m;
         }
+        // FUSED: every path that was regenerated or sent through its material is an extension ray of this iteration
+        const bool pushExt = FUSED && live && (terminate || q > 0);
+        const unsigned extMask = FUSED ? __ballot_sync(0xffffffffu, pushExt) : 0u;
+        if (FUSED && lane == 0)
+            s_cnt[NQ][warp] = __popc(extMask);
         __syncthreads();
-        if (threadIdx.x < NQ)
+        if (threadIdx.x < NQ + (FUSED ? 1 : 0))
         {
             uint32_t total = 0;
 #pragma unroll
             for (int w = 0; w < NW; w++)
                 total += s_cnt[threadIdx.x][w];
-            const int queueId = threadIdx.x == 0 ? Q_SHADOW : Q_DIFFUSE + (int)threadIdx.x - 1;
+            const int queueId = threadIdx.x == 0 ? Q_SHADOW : (threadIdx.x == NQ ? Q_EXT : Q_DIFFUSE + (int)threadIdx.x - 1);
             s_qbase[threadIdx.x] = total ? atomicAdd(counter_ptr(fr.counters, queueId), total) : 0u;
         }
         __syncthreads();
@@ -565,6 +628,13 @@ __global__ void __launch_bounds__(FLX_BLOCK, MIN_BLOCKS) k_logic(const __grid_co
             for (int w = 0; w < warp; w++)
                 slot += s_cnt[q][w];
             fr.queues[Q_DIFFUSE + q - 1][slot] = gid;
+        }
+        if (pushExt)
+        {
+            uint32_t slot = s_qbase[NQ] + __popc(extMask & below);
+            for (int w = 0; w < warp; w++)
+                slot += s_cnt[NQ][w];
+            fr.queues[Q_EXT][slot] = gid;
         }
     }
 
@@ -606,6 +676,24 @@ __global__ void __launch_bounds__(FLX_BLOCK, MIN_BLOCKS) k_logic(const __grid_co
     {
         const uint32_t rank = s_base + warpBase + __popc(termMask & ((1u << lane) - 1u));
         fr.queues[Q_RAYGEN][fr.counters->raygenQueue * 0u + rank] = gid;
+        if (FUSED) // wf_raygen for this path: its queue position is the rank just computed (wf_raygen.cl:25)
+            raygen_path(fr, prm, gid, (*fr.currPixelIdx + rank) % fr.tilePixels, seed);
+    }
+    if (FUSED && toMaterial)
+    {
+        bool hasQueue = true;
+        if (SEPARATE_QUEUES) // a type without a queue is dropped, as in the reference (wf_logic.cl:362-364)
+            hasQueue = matType == FLX_BXDF_DIFFUSE || matType == FLX_BXDF_GLOSSY || matType == FLX_BXDF_GGX_ROUGH_REFLECTION || matType == FLX_BXDF_GGX_ROUGH_DIELECTRIC ||
+                       matType == FLX_BXDF_IDEAL_REFLECTION || matType == FLX_BXDF_IDEAL_DIELECTRIC;
+        if (hasQueue)
+        {
+            constexpr int ALL = FLX_BXDF_DIFFUSE | FLX_BXDF_GLOSSY | FLX_BXDF_GGX_ROUGH_REFLECTION | FLX_BXDF_IDEAL_REFLECTION | FLX_BXDF_GGX_ROUGH_DIELECTRIC |
+                                FLX_BXDF_IDEAL_DIELECTRIC | FLX_BXDF_EMISSIVE;
+            const V3 L = fHaveL ? fL : t.v(FLX_S_SHADOW_DIR, gid); // no new light sample: whatever an earlier vertex left in the slot
+            material_path<ALL>(t, sc, gid, fS, fMat, fBackface, rayDir, L, T, seed);
+        }
+        else
+            t.setu(FLX_S_SEED, gid, seed);
     }
     // the last tile knows the total
     if (threadIdx.x == 0 && (tile + 1u) * FLX_LOGIC_TILE >= maxId && tile * FLX_LOGIC_TILE < maxId)
@@ -642,28 +730,7 @@ __global__ void __launch_bounds__(FLX_BLOCK) k_material(const __grid_constant__ 
         const V3 L = t.v(FLX_S_SHADOW_DIR, gid);
         const V3 oldT = t.v(FLX_S_T, gid);
 
-        // BSDF value and pdf toward the pending light sample (wf_mat_*.cl:33-36)
-        const V3 bsdfNEE = bxdf_eval<MASK>(s, mat, backface, sc, dirIn, L);
-        const float bsdfPdfW = fmaxf(0.0f, bxdf_pdf<MASK>(s, mat, backface, sc, dirIn, L));
-        t.setv(FLX_S_LAST_BSDF, gid, bsdfNEE);
-        t.setf(FLX_S_LAST_PDF_IMPLICIT, gid, bsdfPdfW);
-
-        // continuation (wf_mat_*.cl:38-62)
-        float pdfW = 0.0f;
-        V3 newDir = v3(0.0f);
-        const V3 bsdf = bxdf_sample<MASK>(s, mat, backface, sc, dirIn, newDir, pdfW, seed);
-        const float costh = dot3(s.N, norm3(newDir));
-        V3 newT = v3(0.0f);
-        if (!(pdfW == 0.0f || is_zero3(bsdf)))
-            newT = ((oldT * bsdf) * costh) / pdfW;
-        const V3 orig = s.P + 1e-4f * newDir;
-        t.setv(FLX_S_LAST_T, gid, oldT);
-        t.setv(FLX_S_T, gid, newT);
-        t.setv(FLX_S_ORIG, gid, orig);
-        t.setv(FLX_S_DIR, gid, newDir);
-        t.setf(FLX_S_LAST_PDF_W, gid, pdfW);
-        t.setu(FLX_S_SEED, gid, seed);
-        t.setu(FLX_S_LAST_SPECULAR, gid, (mat.type & (FLX_BXDF_IDEAL_REFLECTION | FLX_BXDF_IDEAL_DIELECTRIC)) != 0 ? 1u : 0u);
+        material_path<MASK>(t, sc, gid, s, mat, backface, dirIn, L, oldT, seed);
 
         }
         __syncthreads();

@@ -88,7 +88,8 @@ enum { FLX_OK = 0, FLX_E_INVALID = 10001, FLX_E_NO_DEVICE = 10002, FLX_E_NOT_REA
 
 /* kernel ids for flx_get_kernel_ms (reference instrument: CLContext::checkTracingPerf, clcontext.cpp:673-701) */
 enum { FLX_K_RESET = 0, FLX_K_RAYGEN, FLX_K_EXTRAYS, FLX_K_SHADOWRAYS, FLX_K_LOGIC, FLX_K_MATERIALS, FLX_K_END_ITERATION, FLX_K_POSTPROCESS,
-       FLX_K_MK_RESET, FLX_K_MK_RAYGEN, FLX_K_MK_NEXT_VERTEX, FLX_K_MK_SAMPLE_BSDF, FLX_K_MK_SPLAT, FLX_K_COUNT };
+       FLX_K_MK_RESET, FLX_K_MK_RAYGEN, FLX_K_MK_NEXT_VERTEX, FLX_K_MK_SAMPLE_BSDF, FLX_K_MK_SPLAT,
+       FLX_K_LOGIC_FUSED /* logic + raygen + materials in one kernel (flx_render) */, FLX_K_COUNT };
 
 typedef struct flx_ctx flx_ctx;
 
@@ -192,6 +193,8 @@ enum { FLX_TUNE_TRACE_VARIANT = 0,      /* 0: one ray per thread; 1 (default): p
        FLX_TUNE_SMEM_STACK = 11,        /* variant 1: keep the first 24 traversal-stack levels in shared memory (default 0: measured slower, L1 shrinks) */
        FLX_TUNE_MAX_L1 = 12,            /* variant 1: request the maximum L1 carve-out for the traversal kernels (default 0: measured 4 % slower) */
        FLX_TUNE_OVERLAP_TRACE = 7,      /* flx_render: run the shadow-ray kernel on a second stream, overlapping the extension kernel's tail (default 1) */
+       FLX_TUNE_FUSE_STAGES = 13,       /* flx_render: logic + raygen + materials as ONE kernel over the path state (default 1) */
+       FLX_TUNE_FUSED_MIN_BLOCKS = 14,  /* register budget of that kernel: compiled for 1..4 resident CTAs of 256 per SM (default 3) */
        FLX_TUNE_INNER_MIN = 4           /* leave the inner-node phase when fewer lanes than this are still at inner nodes (default 8) */ };
 int flx_set_tuning(flx_ctx *ctx, int key, int value);
 
