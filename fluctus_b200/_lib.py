@@ -54,6 +54,7 @@ _SIGNATURES = {
     "flx_get_kernel_ms": (C.c_int, [_P, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]),
     "flx_read_pixels": (C.c_int, [_P, _P, C.c_size_t]),
     "flx_read_tasks": (C.c_int, [_P, _P]),
+    "flx_read_traversal_layout": (C.c_int, [_P, _P, C.POINTER(C.c_uint32), _P, C.POINTER(C.c_uint32), C.POINTER(C.c_int32)]),
     "flx_write_tasks": (C.c_int, [_P, _P]),
     "flx_read_queue": (C.c_int, [_P, C.c_int, _P, C.c_uint32]),
     "flx_write_queue": (C.c_int, [_P, C.c_int, _P, C.c_uint32]),

@@ -187,7 +187,7 @@ class CLContext:
         self._check(self._lib.flx_timer_end(self._h, C.byref(ms)), "timerEnd")
         return ms.value
 
-    TUNING = {"trace_variant": 0, "fetch_threshold": 1, "trace_blocks_per_sm": 2, "top_nodes": 3, "inner_min": 4, "logic_min_blocks": 5, "fetch_chunk": 6, "overlap_trace": 7, "postprocess_in_loop": 10, "smem_stack": 11, "max_l1": 12, "fuse_stages": 13, "fused_min_blocks": 14, "ext_min_blocks": 8, "shadow_min_blocks": 9}
+    TUNING = {"trace_variant": 0, "fetch_threshold": 1, "trace_blocks_per_sm": 2, "top_nodes": 3, "inner_min": 4, "logic_min_blocks": 5, "fetch_chunk": 6, "overlap_trace": 7, "postprocess_in_loop": 10, "smem_stack": 11, "max_l1": 12, "fuse_stages": 13, "prefetch_children": 15, "repack_on_host": 16, "fused_min_blocks": 14, "ext_min_blocks": 8, "shadow_min_blocks": 9}
 
     def setTuning(self, **kv):
         for k, v in kv.items():
@@ -238,6 +238,15 @@ class CLContext:
         """reference: CLContext::saveImage (clcontext.cpp:386-465) -- '*.hdr': linear radiance as Radiance RGBE, otherwise the
         post-processed preview as 8-bit PNG."""
         self._check(self._lib.flx_save_image(self._h, str(filename).encode()), "saveImage")
+
+    def readTraversalLayout(self):
+        """(tnodes (n, 16) float32, ttris (m, 16) float32, rootRef): the uploaded hierarchy in the traversal layout (diagnostic)."""
+        nn, nt, root = C.c_uint32(), C.c_uint32(), C.c_int32()
+        self._check(self._lib.flx_read_traversal_layout(self._h, None, C.byref(nn), None, C.byref(nt), C.byref(root)), "readTraversalLayout")
+        tn, tt = np.zeros((nn.value, 16), np.float32), np.zeros((nt.value, 16), np.float32)
+        self._check(self._lib.flx_read_traversal_layout(self._h, self._ptr(tn) if tn.size else tn.ctypes.data_as(C.c_void_p), C.byref(nn),
+                                                        self._ptr(tt) if tt.size else tt.ctypes.data_as(C.c_void_p), C.byref(nt), C.byref(root)), "readTraversalLayout")
+        return tn, tt, root.value
 
     def readTasks(self):
         out = np.empty((64, self.NUM_TASKS), np.uint32)

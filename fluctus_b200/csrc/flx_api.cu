@@ -6,14 +6,17 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <queue>
 #include <string>
 #include <vector>
 
 #include "flx_bvh_build.cuh"
+#include "flx_bvh_repack.cuh"
 #include "flx_kernels.cuh"
 #include "flx_mk.cuh"
 #include "flx_trace_persistent.cuh"
@@ -138,6 +141,8 @@ struct flx_ctx
     int maxL1 = 0;
     int smemStack = 0;        // variant 1: first 24 stack levels in shared memory ([level][thread], conflict-free)
     int fetchChunk = 32;     // queue entries a warp reserves per atomic
+    int repackOnHost = 0;     // flx_upload_scene: build the traversal layout with the host code instead of the device kernels (checker)
+    int prefetchChildren = 0; // persistent kernels: prefetch both children of an inner node (1: L1, 2: L2) while its box tests run
     int logicMinBlocks = 3;   // resident 256-thread CTAs per SM the logic kernel is compiled for (register budget)
     int fuseStages = 1;       // flx_render: logic + raygen + materials as one kernel
     int fusedMinBlocks = 3;   // register budget of that kernel (1..4 resident CTAs of 256 per SM; 3 measured best)
@@ -247,6 +252,7 @@ BvhView makeBvh(const flx_ctx *c)
     b.nodes = c->tnodes;
     b.tris = c->ttris;
     b.rootRef = c->rootRef;
+    b.prefetch = c->prefetchChildren;
     return b;
 }
 
@@ -460,15 +466,143 @@ int repackBvh(flx_ctx *ctx, const flx_Triangle *tris, uint32_t nTris, const uint
     return 0;
 }
 
+// The treelet of repackBvh (pass 2) on its own: the inner nodes a random ray is most likely to visit, grown from the root by
+// always taking the pending node with the largest box area; returned in placement order.
+std::vector<uint32_t> pickTreelet(const flx_Node *nodes, uint32_t nNodes)
+{
+    std::vector<uint32_t> order;
+    const uint32_t kTreeletMax = 4096;
+    if (nodes[0].nPrims != 0)
+        return order;
+    auto area = [&](uint32_t i) {
+        const float dx = nodes[i].bmax.x - nodes[i].bmin.x, dy = nodes[i].bmax.y - nodes[i].bmin.y, dz = nodes[i].bmax.z - nodes[i].bmin.z;
+        return dx * dy + dx * dz + dy * dz;
+    };
+    typedef std::pair<float, uint32_t> Item; // (area, ~index): larger area first, lower index first on ties
+    std::priority_queue<Item> pq;
+    pq.push(Item(area(0), ~0u));
+    while (!pq.empty() && order.size() < kTreeletMax)
+    {
+        const uint32_t i = ~pq.top().second;
+        pq.pop();
+        order.push_back(i);
+        const uint32_t kids[2] = {i + 1, nodes[i].iStartOrRightChild};
+        for (uint32_t c : kids)
+            if (c < nNodes && nodes[c].nPrims == 0)
+                pq.push(Item(area(c), ~c));
+    }
+    return order;
+}
+
 template <class T> int uploadArray(flx_ctx *ctx, T *&dst, const T *src, size_t count, size_t minCount = 1)
 {
     freeDev(dst);
     const size_t bytes = std::max(count, minCount) * sizeof(T);
     CU(cudaMalloc(&dst, bytes));
-    CU(cudaMemset(dst, 0, bytes));
+    if (bytes > count * sizeof(T))
+        CU(cudaMemset(reinterpret_cast<unsigned char *>(dst) + count * sizeof(T), 0, bytes - count * sizeof(T)));
     if (count)
         CU(cudaMemcpy(dst, src, count * sizeof(T), cudaMemcpyHostToDevice));
     ctx->sceneBytes += bytes;
+    return 0;
+}
+
+// flx_bvh_repack.cuh driven from the host: nodes / indices go up as they are, the traversal layout is made on the device
+int repackOnDevice(flx_ctx *ctx, const uint32_t *indices, uint32_t nIndices, const flx_Node *nodes, uint32_t nNodes, uint32_t nTris)
+{
+    // sizes and the treelet come from one cheap pass over the host nodes
+    size_t nInner = 0, nLeafTris = 0;
+    for (uint32_t i = 0; i < nNodes; i++)
+    {
+        if (nodes[i].nPrims == 0)
+        {
+            const uint32_t r = nodes[i].iStartOrRightChild;
+            if (i + 1 >= nNodes || r >= nNodes || r <= i + 1)
+                return fail(ctx, FLX_E_INVALID, "node %u: child links out of range (left %u, right %u, %u nodes)", i, i + 1, r, nNodes);
+            nInner++;
+        }
+        else
+            nLeafTris += nodes[i].nPrims;
+    }
+    if (nLeafTris > 0x7ffffff0u)
+        return fail(ctx, FLX_E_INVALID, "too many leaf references");
+    const std::vector<uint32_t> treelet = pickTreelet(nodes, nNodes);
+
+    // one allocation for all temporaries (cudaMalloc / cudaFree are the expensive part of a small job like this)
+    auto align = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t szNodes = align((size_t)nNodes * sizeof(flx_Node)), szIdx = align((size_t)nIndices * 4), szTreelet = align(std::max<size_t>(treelet.size(), 1) * 4),
+                 szPerNode = align((size_t)nNodes * 4);
+    size_t tempBytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tempBytes, (uint32_t *)nullptr, (uint32_t *)nullptr, (int)nNodes, ctx->stream);
+    const size_t szScan = align(std::max<size_t>(tempBytes, 16));
+    unsigned char *pool = nullptr;
+    auto cleanup = [&]() { freeDev(pool); };
+    int rc = 0;
+    auto cu = [&](cudaError_t e, const char *what) {
+        if (e != cudaSuccess && rc == 0)
+            rc = fail(ctx, (int)e, "flx_upload_scene: %s failed: %s", what, cudaGetErrorString(e));
+    };
+    cudaStream_t st = ctx->stream;
+    cu(cudaMalloc(&pool, szNodes + szIdx + szTreelet + 5 * szPerNode + szScan + 256), "cudaMalloc");
+    unsigned char *cursor = pool;
+    auto take = [&](size_t bytes) { unsigned char *p = cursor; cursor += bytes; return p; };
+    flx_Node *dNodes = reinterpret_cast<flx_Node *>(take(szNodes));
+    uint32_t *dIndices = reinterpret_cast<uint32_t *>(take(szIdx)), *dTreelet = reinterpret_cast<uint32_t *>(take(szTreelet));
+    int *dPos = reinterpret_cast<int *>(take(szPerNode));
+    uint32_t *dFlag = reinterpret_cast<uint32_t *>(take(szPerNode)), *dPrims = reinterpret_cast<uint32_t *>(take(szPerNode));
+    uint32_t *dScanI = reinterpret_cast<uint32_t *>(take(szPerNode)), *dScanL = reinterpret_cast<uint32_t *>(take(szPerNode));
+    void *dTemp = take(szScan);
+    uint32_t *dError = reinterpret_cast<uint32_t *>(take(256));
+    freeDev(ctx->tnodes);
+    freeDev(ctx->ttris);
+    const size_t nodeBytes = std::max<size_t>(nInner, 1) * 64, triBytes = std::max<size_t>(nLeafTris, 1) * 64;
+    cu(cudaMalloc(&ctx->tnodes, nodeBytes), "cudaMalloc");
+    cu(cudaMalloc(&ctx->ttris, triBytes), "cudaMalloc");
+    if (rc == 0)
+    {
+        cu(cudaMemcpyAsync(dNodes, nodes, (size_t)nNodes * sizeof(flx_Node), cudaMemcpyHostToDevice, st), "node upload");
+        cu(cudaMemcpyAsync(dIndices, indices, (size_t)nIndices * 4, cudaMemcpyHostToDevice, st), "index upload");
+        if (!treelet.empty())
+            cu(cudaMemcpyAsync(dTreelet, treelet.data(), treelet.size() * 4, cudaMemcpyHostToDevice, st), "treelet upload");
+        cu(cudaMemsetAsync(dPos, 0xff, (size_t)nNodes * 4, st), "memset");
+        cu(cudaMemsetAsync(dError, 0, 4, st), "memset");
+        if (nInner == 0)
+            cu(cudaMemsetAsync(ctx->tnodes, 0, nodeBytes, st), "memset"); // every record is written by k_repack_emit otherwise
+    }
+    if (rc == 0)
+    {
+        RepackView r;
+        r.nodes = dNodes; r.indices = dIndices; r.tris = ctx->tris;
+        r.nNodes = nNodes; r.nIndices = nIndices; r.nTris = nTris; r.treeletCount = (uint32_t)treelet.size();
+        r.treeletPos = dPos; r.flagInner = dFlag; r.leafPrims = dPrims; r.scanInner = dScanI; r.scanLeaf = dScanL;
+        r.tnodes = ctx->tnodes; r.ttris = ctx->ttris; r.error = dError;
+        const unsigned grid = (nNodes + 255) / 256;
+        if (!treelet.empty())
+            k_repack_scatter_treelet<<<(unsigned)((treelet.size() + 255) / 256), 256, 0, st>>>(dTreelet, (uint32_t)treelet.size(), dPos);
+        k_repack_flags<<<grid, 256, 0, st>>>(r);
+        cu(cub::DeviceScan::ExclusiveSum(dTemp, tempBytes, dFlag, dScanI, (int)nNodes, st), "scan");
+        cu(cub::DeviceScan::ExclusiveSum(dTemp, tempBytes, dPrims, dScanL, (int)nNodes, st), "scan");
+        k_repack_emit<<<grid, 256, 0, st>>>(r);
+        cu(cudaGetLastError(), "repack launch");
+        uint32_t err = 0;
+        cu(cudaMemcpyAsync(&err, dError, 4, cudaMemcpyDeviceToHost, st), "error read-back");
+        cu(cudaStreamSynchronize(st), "repack");
+        if (rc == 0 && err)
+        {
+            const uint32_t kind = err >> 28, node = (err & 0x0fffffffu) - 1u;
+            rc = kind == 1 ? fail(ctx, FLX_E_INVALID, "node %u: child links out of range", node)
+                 : kind == 2 ? fail(ctx, FLX_E_INVALID, "leaf %u: index range exceeds %u indices", node, nIndices)
+                             : fail(ctx, FLX_E_INVALID, "leaf %u references triangle(s) outside the %u uploaded", node, nTris);
+        }
+    }
+    cleanup();
+    if (rc)
+        return rc;
+    ctx->sceneBytes += nodeBytes + triBytes;
+    ctx->rootRef = nodes[0].nPrims == 0 ? 0 : ~0; // the root is the first node the treelet places; a single-leaf scene starts at TTri 0
+    ctx->nTNodes = (uint32_t)nInner;
+    ctx->nTTris = (uint32_t)nLeafTris;
+    ctx->treeletNodes = (uint32_t)treelet.size();
     return 0;
 }
 
@@ -810,10 +944,15 @@ int flx_upload_scene(flx_ctx *ctx, const flx_Triangle *tris, uint32_t n_tris, co
         if ((size_t)tex_desc[i].offset + (size_t)tex_desc[i].width * tex_desc[i].height * 4 > tex_bytes || (tex_desc[i].offset & 3u) || tex_desc[i].width == 0 ||
             tex_desc[i].height == 0)
             return fail(ctx, FLX_E_INVALID, "texture %u: descriptor outside the %zu-byte blob", i, tex_bytes);
+    const bool timing = std::getenv("FLX_DEBUG_TIMING") != nullptr; // prints where the upload's wall time goes
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    const auto t0 = now();
     Repacked rp;
-    int rc = repackBvh(ctx, tris, n_tris, indices, n_indices, nodes, n_nodes, rp);
-    if (rc)
+    int rc = 0;
+    if (ctx->repackOnHost && (rc = repackBvh(ctx, tris, n_tris, indices, n_indices, nodes, n_nodes, rp)))
         return rc;
+    const auto t1 = now();
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->sceneReady = false;
@@ -831,16 +970,27 @@ int flx_upload_scene(flx_ctx *ctx, const flx_Triangle *tris, uint32_t n_tris, co
         return rc;
     if ((rc = uploadArray(ctx, ctx->texData, tex_data, tex_bytes, 4)))
         return rc;
+    ctx->nTris = n_tris;
+    if (!ctx->repackOnHost)
+    {
+        if ((rc = repackOnDevice(ctx, indices, n_indices, nodes, n_nodes, n_tris)))
+            return rc;
+        ctx->sceneReady = true;
+        if (timing)
+            std::fprintf(stderr, "flx_upload_scene: allocations + copies + repack on the device %.2f ms (%.1f MB resident)\n", ms(t1, now()), ctx->sceneBytes / 1e6);
+        return 0;
+    }
     if ((rc = uploadArray(ctx, ctx->tnodes, rp.nodes.data(), rp.nodes.size(), 4)))
         return rc;
     if ((rc = uploadArray(ctx, ctx->ttris, rp.tris.data(), rp.tris.size(), 4)))
         return rc;
     ctx->rootRef = rp.rootRef;
-    ctx->nTris = n_tris;
     ctx->nTNodes = (uint32_t)(rp.nodes.size() / 4);
     ctx->nTTris = (uint32_t)(rp.tris.size() / 4);
     ctx->treeletNodes = rp.treeletNodes;
     ctx->sceneReady = true;
+    if (timing)
+        std::fprintf(stderr, "flx_upload_scene: repack on the host %.2f ms, allocations + copies %.2f ms (%.1f MB)\n", ms(t0, t1), ms(t1, now()), ctx->sceneBytes / 1e6);
     return 0;
 }
 
@@ -1611,6 +1761,13 @@ int flx_set_tuning(flx_ctx *ctx, int key, int value)
         REQUIRE(value == 2 || value == 3 || value == 4, "flx_set_tuning: logic min blocks must be 2, 3 or 4");
         ctx->logicMinBlocks = value;
         return 0;
+    case FLX_TUNE_REPACK_ON_HOST:
+        ctx->repackOnHost = value != 0;
+        return 0;
+    case FLX_TUNE_PREFETCH_CHILDREN:
+        REQUIRE(value >= 0 && value <= 2, "flx_set_tuning: prefetch mode must be 0, 1 or 2");
+        ctx->prefetchChildren = value;
+        return 0;
     case FLX_TUNE_FUSE_STAGES:
         ctx->fuseStages = value != 0;
         return 0;
@@ -1747,6 +1904,29 @@ int flx_save_image(flx_ctx *ctx, const char *filename)
         return rc;
     if (flx_write_image(filename, host.data(), ctx->width, ctx->height) != 0)
         return fail(ctx, FLX_E_INVALID, "flx_save_image: %s", flx_io_last_error());
+    return 0;
+}
+
+// test/diagnostic: the traversal layout as it lives on the device (TNode and TTri records of 16 floats each)
+int flx_read_traversal_layout(flx_ctx *ctx, float *tnodes_out, uint32_t *n_tnodes, float *ttris_out, uint32_t *n_ttris, int32_t *root_ref)
+{
+    if (!ctx)
+        return FLX_E_INVALID;
+    TOUCH(ctx);
+    REQUIRE(n_tnodes && n_ttris, "flx_read_traversal_layout: null count");
+    REQUIRE(ctx->sceneReady, "flx_read_traversal_layout: no scene uploaded");
+    CU(cudaSetDevice(ctx->device));
+    if (tnodes_out && ttris_out)
+    {
+        REQUIRE(*n_tnodes >= ctx->nTNodes && *n_ttris >= ctx->nTTris, "flx_read_traversal_layout: arrays too small");
+        CU(cudaMemcpyAsync(tnodes_out, ctx->tnodes, (size_t)ctx->nTNodes * 64, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(ttris_out, ctx->ttris, (size_t)ctx->nTTris * 64, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    *n_tnodes = ctx->nTNodes;
+    *n_ttris = ctx->nTTris;
+    if (root_ref)
+        *root_ref = ctx->rootRef;
     return 0;
 }
 

@@ -56,6 +56,7 @@ struct BvhView
     const float4 *nodes; // TNode as 4 x float4
     const float4 *tris;  // TTri as 4 x float4
     int rootRef;
+    int prefetch;        // persistent kernels: 0 off, 1 prefetch both children into L1 as soon as their references are known, 2 into L2
 };
 
 // slab test of one child box (reference: intersectAABB, src/intersect.cl:41-60)

@@ -289,6 +289,21 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_trace_persistent(const __
                     q2 = make_float4(h1.v[0], h1.v[1], h1.v[2], h1.v[3]);
                     q3 = make_int4(__float_as_int(h1.v[4]), __float_as_int(h1.v[5]), 0, 0);
                 }
+                if (bvh.prefetch) // both children's records start their way up while the two box tests run
+                {
+                    const float4 *c0 = q3.x >= 0 ? bvh.nodes + 4 * (size_t)q3.x : bvh.tris + 4 * (size_t)(~q3.x);
+                    const float4 *c1 = q3.y >= 0 ? bvh.nodes + 4 * (size_t)q3.y : bvh.tris + 4 * (size_t)(~q3.y);
+                    if (bvh.prefetch == 1)
+                    {
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(c0));
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(c1));
+                    }
+                    else
+                    {
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(c0));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(c1));
+                    }
+                }
                 float ln, rn;
                 const bool lh = box_test(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, o, idir, tbest, ln);
                 const bool rh = box_test(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, o, idir, tbest, rn);

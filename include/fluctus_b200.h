@@ -193,6 +193,8 @@ enum { FLX_TUNE_TRACE_VARIANT = 0,      /* 0: one ray per thread; 1 (default): p
        FLX_TUNE_SMEM_STACK = 11,        /* variant 1: keep the first 24 traversal-stack levels in shared memory (default 0: measured slower, L1 shrinks) */
        FLX_TUNE_MAX_L1 = 12,            /* variant 1: request the maximum L1 carve-out for the traversal kernels (default 0: measured 4 % slower) */
        FLX_TUNE_OVERLAP_TRACE = 7,      /* flx_render: run the shadow-ray kernel on a second stream, overlapping the extension kernel's tail (default 1) */
+       FLX_TUNE_REPACK_ON_HOST = 16,    /* flx_upload_scene: make the traversal layout with the host code instead of the device kernels (default 0) */
+       FLX_TUNE_PREFETCH_CHILDREN = 15, /* persistent traversal: prefetch both children of an inner node while its box tests run (0 off, 1 L1, 2 L2) */
        FLX_TUNE_FUSE_STAGES = 13,       /* flx_render: logic + raygen + materials as ONE kernel over the path state (default 1) */
        FLX_TUNE_FUSED_MIN_BLOCKS = 14,  /* register budget of that kernel: compiled for 1..4 resident CTAs of 256 per SM (default 3) */
        FLX_TUNE_INNER_MIN = 4           /* leave the inner-node phase when fewer lanes than this are still at inner nodes (default 8) */ };
@@ -224,6 +226,8 @@ int flx_write_image(const char *path, const float *rgba, uint32_t width, uint32_
 
 /* Test/diagnostic access to the path state and queues (no reference equivalent; the reference's debugger did this). */
 int flx_read_tasks(flx_ctx *ctx, uint32_t *slots_out /* 64*num_tasks */);
+/* the hierarchy as repacked for traversal (16 floats per inner node / per leaf reference); NULL arrays: counts only */
+int flx_read_traversal_layout(flx_ctx *ctx, float *tnodes_out, uint32_t *n_tnodes, float *ttris_out, uint32_t *n_ttris, int32_t *root_ref);
 int flx_write_tasks(flx_ctx *ctx, const uint32_t *slots_in);
 int flx_read_queue(flx_ctx *ctx, int queue_id /* 0..7 = order of flx_QueueCounters */, uint32_t *out, uint32_t max_entries);
 int flx_write_queue(flx_ctx *ctx, int queue_id, const uint32_t *entries, uint32_t n);

@@ -78,3 +78,51 @@ def test_builder_rejects_bad_arguments():
             gpu.buildBVH(tris, max_leaf=0)
         with pytest.raises(FluctusError):
             gpu.buildBVH(tris, max_leaf=256)
+
+
+@pytest.mark.parametrize("name", ["room", "teapot", "conference", "built"])
+def test_device_repack_matches_the_host_repack(name):
+    """flx_upload_scene makes the traversal layout (TNode / TTri) on the device (flx_bvh_repack.cuh); the host code it replaced
+    stays as the checker behind a tuning knob: both must give the same bytes, on reference SBVHs and on a GPU-built tree."""
+    if name == "room":
+        scene = make_room_scene(materials="mixed", n_blobs=8)
+    elif name == "teapot":
+        scene = teapot_scene()
+    else:
+        scene = SceneData.load_blob(scene_blob("conference"))
+    layouts = []
+    for on_host in (1, 0):
+        with CLContext(256) as gpu:
+            if name == "built" and not on_host:
+                pass
+            gpu.setTuning(repack_on_host=on_host)
+            if name == "built":
+                nodes, idx, _ = gpu.buildBVH(scene.tris)
+                sc = SceneData(scene.tris, idx, nodes, scene.materials, scene.tex_desc, scene.tex_data)
+            else:
+                sc = scene
+            gpu.uploadSceneData(sc)
+            layouts.append(gpu.readTraversalLayout())
+    (hn, ht, hr), (dn, dt, dr) = layouts
+    assert hr == dr and hn.shape == dn.shape and ht.shape == dt.shape
+    assert np.array_equal(hn.view(np.uint32), dn.view(np.uint32)), "TNode records differ"
+    assert np.array_equal(ht.view(np.uint32), dt.view(np.uint32)), "TTri records differ"
+
+
+def test_device_repack_reports_bad_hierarchies():
+    from fluctus_b200.clcontext import FluctusError
+    room = make_room_scene(materials="diffuse")
+    for what in ("leaf_range", "tri_index", "child_link"):
+        nodes, indices = room.nodes.copy(), room.indices.copy()
+        leaf = int(np.flatnonzero(nodes["nPrims"] > 0)[-1])
+        inner = int(np.flatnonzero(nodes["nPrims"] == 0)[-1])
+        if what == "leaf_range":
+            nodes["link"][leaf] = len(indices)
+        elif what == "tri_index":
+            indices[nodes["link"][leaf]] = len(room.tris) + 7
+        else:
+            nodes["link"][inner] = len(nodes) + 3
+        bad = SceneData(room.tris, indices, nodes, room.materials, room.tex_desc, room.tex_data)
+        with CLContext(64) as gpu:
+            with pytest.raises(FluctusError):
+                gpu.uploadSceneData(bad)
