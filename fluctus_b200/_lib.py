@@ -16,7 +16,7 @@ _SIGNATURES = {
     "flx_create": (C.c_int, [C.c_int, C.c_uint32, C.POINTER(_P)]),
     "flx_destroy": (None, [_P]),
     "flx_upload_scene": (C.c_int, [_P, _P, C.c_uint32, _P, C.c_uint32, _P, C.c_uint32, _P, C.c_uint32, _P, C.c_uint32, _P, C.c_size_t]),
-    "flx_build_bvh": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, _P, C.c_uint32, C.POINTER(C.c_uint32), _P, C.POINTER(C.c_float)]),
+    "flx_build_bvh": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_int, _P, C.c_uint32, C.POINTER(C.c_uint32), _P, C.POINTER(C.c_float)]),
     "flx_upload_envmap": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _P]),
     "flx_resize": (C.c_int, [_P, C.c_uint32, C.c_uint32]),
     "flx_update_params": (C.c_int, [_P, C.POINTER(RenderParams)]),

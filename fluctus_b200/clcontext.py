@@ -68,15 +68,16 @@ class CLContext:
                                                self._ptr(scene.tex_desc), len(scene.tex_desc), self._ptr(scene.tex_data), scene.tex_data.nbytes),
                     "uploadSceneData")
 
-    def buildBVH(self, tris, max_leaf=8):
+    def buildBVH(self, tris, max_leaf=8, quality="fast"):
         """GPU hierarchy build (flx_build_bvh): what `new SBVH(&tris, ...)` gives the reference (src/scene.cpp:574-590) -- the
-        Node[] / index arrays in the reference's format -- in milliseconds.  Returns (nodes, indices, device_ms)."""
+        Node[] / index arrays in the reference's format -- in milliseconds.  quality: "fast" (LBVH) or "ploc" (locally-ordered clustering:
+        better trees, a few ms).  Returns (nodes, indices, device_ms)."""
         from .structs import NODE_DTYPE
         n = len(tris)
         nodes = np.zeros(max(2 * n - 1, 1), NODE_DTYPE)
         indices = np.zeros(n, np.uint32)
         n_nodes, ms = C.c_uint32(), C.c_float()
-        self._check(self._lib.flx_build_bvh(self._h, self._ptr(tris), n, int(max_leaf), self._ptr(nodes), len(nodes), C.byref(n_nodes), self._ptr(indices),
+        self._check(self._lib.flx_build_bvh(self._h, self._ptr(tris), n, int(max_leaf), {"fast": 0, "ploc": 1}[quality], self._ptr(nodes), len(nodes), C.byref(n_nodes), self._ptr(indices),
                                             C.byref(ms)), "buildBVH")
         return nodes[:n_nodes.value].copy(), indices, ms.value
 

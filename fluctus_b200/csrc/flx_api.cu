@@ -996,8 +996,8 @@ int flx_upload_scene(flx_ctx *ctx, const flx_Triangle *tris, uint32_t n_tris, co
 
 // ---- GPU hierarchy builder (flx_bvh_build.cuh): stands in for `new SBVH(&tris, mode)` / BVH::m_nodes + m_indices
 // (src/scene.cpp:574-590, src/sbvh.cpp:4-73) when build time matters more than tree quality
-int flx_build_bvh(flx_ctx *ctx, const flx_Triangle *tris, uint32_t n_tris, uint32_t max_leaf, flx_Node *nodes_out, uint32_t nodes_capacity, uint32_t *n_nodes_out,
-                  uint32_t *indices_out, float *build_ms)
+int flx_build_bvh(flx_ctx *ctx, const flx_Triangle *tris, uint32_t n_tris, uint32_t max_leaf, int quality, flx_Node *nodes_out, uint32_t nodes_capacity,
+                  uint32_t *n_nodes_out, uint32_t *indices_out, float *build_ms)
 {
     if (!ctx)
         return FLX_E_INVALID;
@@ -1005,6 +1005,7 @@ int flx_build_bvh(flx_ctx *ctx, const flx_Triangle *tris, uint32_t n_tris, uint3
     REQUIRE(tris && nodes_out && n_nodes_out && indices_out, "flx_build_bvh: null array");
     REQUIRE(n_tris > 0 && n_tris < 0x40000000u, "flx_build_bvh: triangle count out of range");
     REQUIRE(max_leaf >= 1 && max_leaf <= 255, "flx_build_bvh: max_leaf must be in 1..255 (nPrims is a byte, src/bvhnode.hpp:58)");
+    REQUIRE(quality == FLX_BVH_FAST || quality == FLX_BVH_PLOC, "flx_build_bvh: quality must be FLX_BVH_FAST or FLX_BVH_PLOC");
     CU(cudaSetDevice(ctx->device));
     const uint32_t n = n_tris, total = 2u * n - 1u;
     BvhBuild b;
@@ -1050,6 +1051,39 @@ int flx_build_bvh(flx_ctx *ctx, const flx_Triangle *tris, uint32_t n_tris, uint3
     BALLOC(b.nodesOut, total);
     BALLOC(b.indicesOut, n);
     b.tris = dTris;
+    PlocBuild pb;
+    memset(&pb, 0, sizeof pb);
+    void *scanTemp = nullptr;
+    size_t scanBytes = 0;
+    if (quality == FLX_BVH_PLOC)
+    {
+        pb.n = n;
+        pb.maxLeaf = max_leaf;
+        pb.keysSorted = b.keysSorted;
+        pb.primMin = b.primMin;
+        pb.primMax = b.primMax;
+        pb.bmin = b.bmin;
+        pb.bmax = b.bmax;
+        pb.parent = b.parent;
+        pb.cost = b.cost;
+        pb.size = b.size;
+        pb.collapsed = b.collapsed;
+        pb.nodesOut = b.nodesOut;
+        pb.indicesOut = b.indicesOut;
+        BALLOC(pb.left, total);
+        BALLOC(pb.right, total);
+        BALLOC(pb.prims, total);
+        BALLOC(pb.cidA, n);
+        BALLOC(pb.cidB, n);
+        BALLOC(pb.nn, n);
+        BALLOC(pb.flags, n);
+        BALLOC(pb.scan, n);
+        BALLOC(pb.depthMax, 1);
+        cub::DeviceScan::ExclusiveSum(nullptr, scanBytes, pb.flags, pb.scan, (int)n, ctx->stream);
+        unsigned char *t = nullptr;
+        BALLOC(t, scanBytes);
+        scanTemp = t;
+    }
     cub::DeviceRadixSort::SortKeys(nullptr, sortBytes, b.keys, b.keysSorted, (int)n, 0, 62, ctx->stream);
     {
         unsigned char *t = nullptr;
@@ -1077,18 +1111,57 @@ int flx_build_bvh(flx_ctx *ctx, const flx_Triangle *tris, uint32_t n_tris, uint3
         k_bvh_prims<<<gridN, FLX_BVH_BLOCK, 0, st>>>(b);
         k_bvh_morton<<<gridN, FLX_BVH_BLOCK, 0, st>>>(b);
         cu(cub::DeviceRadixSort::SortKeys(sortTemp, sortBytes, b.keys, b.keysSorted, (int)n, 0, 62, st), "radix sort");
-        if (n > 1)
-            k_bvh_hierarchy<<<gridN, FLX_BVH_BLOCK, 0, st>>>(b);
-        k_bvh_fit<<<gridN, FLX_BVH_BLOCK, 0, st>>>(b);
-        k_bvh_emit<<<gridT, FLX_BVH_BLOCK, 0, st>>>(b);
+        if (quality == FLX_BVH_PLOC)
+        {
+            cu(cudaMemsetAsync(pb.depthMax, 0, sizeof(uint32_t), st), "memset");
+            k_ploc_init<<<gridN, FLX_BVH_BLOCK, 0, st>>>(pb);
+            uint32_t m = n, nextId = n;
+            uint32_t *cid = pb.cidA, *cidNext = pb.cidB;
+            while (m > 1 && rc == 0) // every round merges at least the closest pair; typically a third of the clusters
+            {
+                const unsigned gridM = (m + FLX_BVH_BLOCK - 1) / FLX_BVH_BLOCK;
+                k_ploc_nearest<<<gridM, FLX_BVH_BLOCK, 0, st>>>(pb, cid, m);
+                k_ploc_flags<<<gridM, FLX_BVH_BLOCK, 0, st>>>(pb, m);
+                cu(cub::DeviceScan::ExclusiveSum(scanTemp, scanBytes, pb.flags, pb.scan, (int)m, st), "scan");
+                unsigned long long last[2] = {0, 0};
+                cu(cudaMemcpyAsync(&last[0], pb.scan + (m - 1), 8, cudaMemcpyDeviceToHost, st), "round read-back");
+                cu(cudaMemcpyAsync(&last[1], pb.flags + (m - 1), 8, cudaMemcpyDeviceToHost, st), "round read-back");
+                cu(cudaStreamSynchronize(st), "PLOC round");
+                const unsigned long long totals = last[0] + last[1];
+                const uint32_t kept = (uint32_t)(totals & 0xffffffffull), merged = (uint32_t)(totals >> 32);
+                if (rc == 0 && (merged == 0 || kept + merged != m))
+                    rc = fail(ctx, FLX_E_INVALID, "flx_build_bvh: PLOC round made no progress (%u clusters, %u merges)", m, merged);
+                if (rc)
+                    break;
+                k_ploc_apply<<<gridM, FLX_BVH_BLOCK, 0, st>>>(pb, cid, cidNext, m, nextId);
+                std::swap(cid, cidNext);
+                m = kept;
+                nextId += merged;
+            }
+            k_ploc_emit<<<gridT, FLX_BVH_BLOCK, 0, st>>>(pb);
+        }
+        else
+        {
+            if (n > 1)
+                k_bvh_hierarchy<<<gridN, FLX_BVH_BLOCK, 0, st>>>(b);
+            k_bvh_fit<<<gridN, FLX_BVH_BLOCK, 0, st>>>(b);
+            k_bvh_emit<<<gridT, FLX_BVH_BLOCK, 0, st>>>(b);
+        }
         cu(cudaGetLastError(), "kernel launch");
         cu(cudaEventRecord(ctx->evStop, st), "event");
     }
     uint32_t nNodes = 0;
     if (rc == 0)
     {
-        cu(cudaMemcpyAsync(&nNodes, b.size, sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "size read-back");
+        // the root: LBVH internal node 0 (or the single leaf, also id 0); PLOC: the last node created
+        const uint32_t rootId = quality == FLX_BVH_PLOC ? total - 1u : 0u;
+        uint32_t depth = 0;
+        cu(cudaMemcpyAsync(&nNodes, b.size + rootId, sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "size read-back");
+        if (quality == FLX_BVH_PLOC)
+            cu(cudaMemcpyAsync(&depth, pb.depthMax, sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "depth read-back");
         cu(cudaStreamSynchronize(st), "build");
+        if (rc == 0 && depth > 62) // the traversal stack holds 64 entries (src/bvh.cl:240); a radix tree cannot get there, this one could
+            rc = fail(ctx, FLX_E_INVALID, "flx_build_bvh: PLOC tree is %u levels deep (limit 62); use FLX_BVH_FAST for this input", depth);
     }
     if (rc == 0 && nNodes > nodes_capacity)
         rc = fail(ctx, FLX_E_INVALID, "flx_build_bvh: %u nodes do not fit the caller's %u", nNodes, nodes_capacity);
@@ -1297,7 +1370,8 @@ int flx_enqueue_shadowrays(flx_ctx *ctx)
     return 0;
 }
 
-// wf_logic alone, or (fused) wf_logic + wf_raygen + wf_mat_* in one pass over the path state (k_logic<.., FUSED>)
+static int launchMaterials(flx_ctx *ctx);
+// wf_logic alone, or (fused) wf_logic + wf_raygen + wf_mat_* in one pass over the path state (k_logic<.., FUSE>)
 static int launchLogic(flx_ctx *ctx, int first_iteration, bool fused)
 {
     const uint32_t maxId = first_iteration ? std::min(ctx->tilePixels, ctx->numTasks) : ctx->numTasks; // wf_logic.cl:45
@@ -1305,34 +1379,38 @@ static int launchLogic(flx_ctx *ctx, int first_iteration, bool fused)
     CU(cudaMemsetAsync(ctx->scanTiles, 0, (size_t)tiles * sizeof(unsigned long long), ctx->stream));
     CU(cudaMemsetAsync(ctx->scanTicket, 0, sizeof(uint32_t), ctx->stream));
     ScanState scan{ctx->scanTiles, ctx->scanTicket};
-    Timed tm(ctx, fused ? FLX_K_LOGIC_FUSED : FLX_K_LOGIC);
     const Frame fr = makeFrame(ctx);
     const SceneView sc = makeScene(ctx);
     const bool sep = ctx->params.wfSeparateQueues != 0;
     if (fused)
     {
-        if (ctx->fusedMinBlocks == 4)
+        // single material queue: logic + raygen + materials in one kernel; per-type queues: logic + raygen here, then the per-type
+        // material kernels (a warp of those sees one BSDF, which is the reason the queues exist)
         {
-            if (sep) k_logic<true, 4, true><<<tiles, FLX_BLOCK, 0, ctx->stream>>>(fr, ctx->params, sc, scan, maxId);
-            else k_logic<false, 4, true><<<tiles, FLX_BLOCK, 0, ctx->stream>>>(fr, ctx->params, sc, scan, maxId);
+            Timed tm(ctx, FLX_K_LOGIC_FUSED);
+#define FUSEDK(MB)                                                                                                                                             \
+    do                                                                                                                                                         \
+    {                                                                                                                                                          \
+        if (sep)                                                                                                                                               \
+            k_logic<true, MB, 1><<<tiles, FLX_BLOCK, 0, ctx->stream>>>(fr, ctx->params, sc, scan, maxId);                                                      \
+        else                                                                                                                                                   \
+            k_logic<false, MB, 2><<<tiles, FLX_BLOCK, 0, ctx->stream>>>(fr, ctx->params, sc, scan, maxId);                                                     \
+    } while (0)
+            switch (ctx->fusedMinBlocks)
+            {
+            case 4: FUSEDK(4); break;
+            case 2: FUSEDK(2); break;
+            case 1: FUSEDK(1); break;
+            default: FUSEDK(3); break;
+            }
+#undef FUSEDK
         }
-        else if (ctx->fusedMinBlocks == 3)
-        {
-            if (sep) k_logic<true, 3, true><<<tiles, FLX_BLOCK, 0, ctx->stream>>>(fr, ctx->params, sc, scan, maxId);
-            else k_logic<false, 3, true><<<tiles, FLX_BLOCK, 0, ctx->stream>>>(fr, ctx->params, sc, scan, maxId);
-        }
-        else if (ctx->fusedMinBlocks == 1)
-        {
-            if (sep) k_logic<true, 1, true><<<tiles, FLX_BLOCK, 0, ctx->stream>>>(fr, ctx->params, sc, scan, maxId);
-            else k_logic<false, 1, true><<<tiles, FLX_BLOCK, 0, ctx->stream>>>(fr, ctx->params, sc, scan, maxId);
-        }
-        else
-        {
-            if (sep) k_logic<true, 2, true><<<tiles, FLX_BLOCK, 0, ctx->stream>>>(fr, ctx->params, sc, scan, maxId);
-            else k_logic<false, 2, true><<<tiles, FLX_BLOCK, 0, ctx->stream>>>(fr, ctx->params, sc, scan, maxId);
-        }
-        return launchCheck(ctx, "k_logic<fused>");
+        int rc = launchCheck(ctx, "k_logic<fused>");
+        if (rc == 0 && sep)
+            rc = launchMaterials(ctx);
+        return rc;
     }
+    Timed tm(ctx, FLX_K_LOGIC);
 #define LOGIC(SEP, MB) k_logic<SEP, MB><<<tiles, FLX_BLOCK, 0, ctx->stream>>>(fr, ctx->params, sc, scan, maxId)
     switch (ctx->logicMinBlocks)
     {
@@ -1390,6 +1468,11 @@ int flx_enqueue_materials(flx_ctx *ctx)
         ctx->pendingStages = 0;
         return launchLogic(ctx, ctx->pendingFirstIteration, true);
     }
+    return launchMaterials(ctx);
+}
+
+static int launchMaterials(flx_ctx *ctx)
+{
     const unsigned grid = streamingGrid(ctx->numTasks);
     const Frame fr = makeFrame(ctx);
     const SceneView sc = makeScene(ctx);

@@ -282,3 +282,197 @@ __global__ void __launch_bounds__(FLX_BVH_BLOCK) k_bvh_emit(const BvhBuild b)
     }
     b.nodesOut[dfs] = out;
 }
+
+// ================================================================================================ PLOC
+// Second builder, for better trees at a few times the build cost: parallel locally-ordered clustering (Meister & Bittner 2018).
+// The Morton-sorted triangles start as one cluster each; every round each cluster looks R positions to either side for the
+// neighbour whose merged box has the smallest area (ties: the lower position), mutual pairs merge into a new node that takes
+// the lower partner's place, the array is compacted (one exclusive sum over (keep, merge) packed in 64 bits), until one cluster
+// is left.  SAH cost, collapse decision, surviving-subtree size and triangle count of a node are final the moment it is
+// created, so no separate bottom-up pass is needed.  The emit step is the general one (any binary tree): a node's depth-first
+// index and the position of its first triangle in the index list come from walking to the root (left child: +1 / +0,
+// right child: +1 + size(left sibling) / + triangles(left sibling)).
+// Deterministic like the LBVH path: with "lowest position wins ties" the lowest-positioned cluster of a closest pair always has
+// a mutual partner, so every round merges at least one pair; oracle/bvh_oracle.c restates it sequentially, bit for bit.
+//
+// Node ids: leaf j (sorted position) -> j; inner nodes -> n, n+1, ... in order of creation (by round, then by position).
+#define FLX_PLOC_RADIUS 16
+
+struct PlocBuild
+{
+    uint32_t n, maxLeaf;
+    const unsigned long long *keysSorted;
+    const float4 *primMin, *primMax;
+    float4 *bmin, *bmax;     // per node id (2n - 1)
+    int *left, *right, *parent;
+    float *cost;
+    uint32_t *size, *prims, *collapsed;
+    uint32_t *cidA, *cidB;   // cluster arrays (ping-pong): node id at each position
+    int *nn;                 // per position: chosen neighbour position
+    unsigned long long *flags, *scan; // per position: keep | merge << 32, and its exclusive sum
+    uint32_t *depthMax;
+    flx_Node *nodesOut;
+    uint32_t *indicesOut;
+};
+
+__global__ void __launch_bounds__(FLX_BVH_BLOCK) k_ploc_init(const PlocBuild b)
+{
+    const uint32_t j = blockIdx.x * FLX_BVH_BLOCK + threadIdx.x;
+    if (j >= b.n)
+        return;
+    const uint32_t tri = (uint32_t)(b.keysSorted[j] & 0xffffffffull);
+    const float4 lo = b.primMin[tri], hi = b.primMax[tri];
+    b.bmin[j] = lo;
+    b.bmax[j] = hi;
+    b.left[j] = -1;
+    b.right[j] = -1;
+    b.parent[j] = -1;
+    b.cost[j] = half_area(lo, hi) * 1.0f;
+    b.size[j] = 1u;
+    b.prims[j] = 1u;
+    b.collapsed[j] = 0u;
+    b.cidA[j] = j;
+}
+
+__global__ void __launch_bounds__(FLX_BVH_BLOCK) k_ploc_nearest(const PlocBuild b, const uint32_t *cid, const uint32_t m)
+{
+    __shared__ float4 s_lo[FLX_BVH_BLOCK + 2 * FLX_PLOC_RADIUS], s_hi[FLX_BVH_BLOCK + 2 * FLX_PLOC_RADIUS];
+    const int base = (int)(blockIdx.x * FLX_BVH_BLOCK) - FLX_PLOC_RADIUS;
+    for (int k = threadIdx.x; k < FLX_BVH_BLOCK + 2 * FLX_PLOC_RADIUS; k += FLX_BVH_BLOCK)
+    {
+        const int q = base + k;
+        if (q >= 0 && q < (int)m)
+        {
+            const uint32_t id = cid[q];
+            s_lo[k] = b.bmin[id];
+            s_hi[k] = b.bmax[id];
+        }
+    }
+    __syncthreads();
+    const int p = (int)(blockIdx.x * FLX_BVH_BLOCK + threadIdx.x);
+    if (p >= (int)m)
+        return;
+    const float4 lo = s_lo[threadIdx.x + FLX_PLOC_RADIUS], hi = s_hi[threadIdx.x + FLX_PLOC_RADIUS];
+    float best = 3.402823466e+38f;
+    int bestq = -1;
+    for (int d = -FLX_PLOC_RADIUS; d <= FLX_PLOC_RADIUS; d++) // ascending position: "<" keeps the lowest position on ties
+    {
+        const int q = p + d;
+        if (d == 0 || q < 0 || q >= (int)m)
+            continue;
+        const float4 qlo = s_lo[threadIdx.x + FLX_PLOC_RADIUS + d], qhi = s_hi[threadIdx.x + FLX_PLOC_RADIUS + d];
+        const float4 ulo = make_float4(fminf(lo.x, qlo.x), fminf(lo.y, qlo.y), fminf(lo.z, qlo.z), 0.0f);
+        const float4 uhi = make_float4(fmaxf(hi.x, qhi.x), fmaxf(hi.y, qhi.y), fmaxf(hi.z, qhi.z), 0.0f);
+        const float a = half_area(ulo, uhi);
+        if (a < best || bestq < 0)
+        {
+            best = a;
+            bestq = q;
+        }
+    }
+    b.nn[p] = bestq;
+}
+
+__global__ void __launch_bounds__(FLX_BVH_BLOCK) k_ploc_flags(const PlocBuild b, const uint32_t m)
+{
+    const int p = (int)(blockIdx.x * FLX_BVH_BLOCK + threadIdx.x);
+    if (p >= (int)m)
+        return;
+    const int q = b.nn[p];
+    const bool mutual = q >= 0 && b.nn[q] == p;
+    const unsigned long long keep = (mutual && q < p) ? 0ull : 1ull; // the upper partner of a pair disappears
+    const unsigned long long merge = (mutual && p < q) ? 1ull : 0ull; // the lower partner's place takes the new node
+    b.flags[p] = keep | (merge << 32);
+}
+
+__global__ void __launch_bounds__(FLX_BVH_BLOCK) k_ploc_apply(const PlocBuild b, const uint32_t *cid, uint32_t *cidNext, const uint32_t m, const uint32_t nextId)
+{
+    const int p = (int)(blockIdx.x * FLX_BVH_BLOCK + threadIdx.x);
+    if (p >= (int)m)
+        return;
+    const unsigned long long f = b.flags[p], s = b.scan[p];
+    if ((f & 1ull) == 0ull)
+        return;
+    const uint32_t pos = (uint32_t)(s & 0xffffffffull);
+    if ((f >> 32) == 0ull)
+    {
+        cidNext[pos] = cid[p];
+        return;
+    }
+    const uint32_t id = nextId + (uint32_t)(s >> 32);
+    const uint32_t l = cid[p], r = cid[b.nn[p]];
+    const float4 llo = b.bmin[l], lhi = b.bmax[l], rlo = b.bmin[r], rhi = b.bmax[r];
+    const float4 lo = make_float4(fminf(llo.x, rlo.x), fminf(llo.y, rlo.y), fminf(llo.z, rlo.z), 0.0f);
+    const float4 hi = make_float4(fmaxf(lhi.x, rhi.x), fmaxf(lhi.y, rhi.y), fmaxf(lhi.z, rhi.z), 0.0f);
+    const float area = half_area(lo, hi);
+    const uint32_t count = b.prims[l] + b.prims[r];
+    const float leafCost = area * (float)count;
+    const float innerCost = (area * 2.0f + b.cost[l]) + b.cost[r];
+    const bool collapse = count <= b.maxLeaf && leafCost <= innerCost;
+    b.bmin[id] = lo;
+    b.bmax[id] = hi;
+    b.left[id] = (int)l;
+    b.right[id] = (int)r;
+    b.parent[id] = -1;
+    b.parent[l] = (int)id;
+    b.parent[r] = (int)id;
+    b.cost[id] = collapse ? leafCost : innerCost;
+    b.size[id] = collapse ? 1u : 1u + b.size[l] + b.size[r];
+    b.prims[id] = count;
+    b.collapsed[id] = collapse ? 1u : 0u;
+    cidNext[pos] = id;
+}
+
+__global__ void __launch_bounds__(FLX_BVH_BLOCK) k_ploc_emit(const PlocBuild b)
+{
+    const uint32_t id = blockIdx.x * FLX_BVH_BLOCK + threadIdx.x;
+    const uint32_t total = 2u * b.n - 1u;
+    if (id >= total)
+        return;
+    uint32_t dfs = 0, firstPrim = 0, parentDelta = 0, depth = 0;
+    bool atRoot = true, alive = true;
+    int node = (int)id;
+    while (true)
+    {
+        const int p = b.parent[node];
+        if (p < 0)
+            break;
+        if (b.collapsed[p])
+            alive = false; // not a node of the output; its triangle still needs its place in the index list
+        const int l = b.left[p];
+        const bool isLeft = l == node;
+        const uint32_t step = isLeft ? 1u : 1u + b.size[l];
+        if (atRoot)
+        {
+            parentDelta = step;
+            atRoot = false;
+        }
+        dfs += step;
+        firstPrim += isLeft ? 0u : b.prims[l];
+        depth++;
+        node = p;
+    }
+    if (id < b.n) // a triangle: its place in the index list is its in-order rank, whether or not its leaf node survives
+        b.indicesOut[firstPrim] = (uint32_t)(b.keysSorted[id] & 0xffffffffull);
+    if (!alive)
+        return;
+    atomicMax(b.depthMax, depth);
+    flx_Node out;
+    const float4 lo = b.bmin[id], hi = b.bmax[id];
+    out.bmin.x = lo.x; out.bmin.y = lo.y; out.bmin.z = lo.z; out.bmin.w = 0.0f;
+    out.bmax.x = hi.x; out.bmax.y = hi.y; out.bmax.z = hi.z; out.bmax.w = 0.0f;
+    out.parent = atRoot ? -1 : (int)(dfs - parentDelta);
+    for (int k = 0; k < 7; k++)
+        out._pad[k] = 0;
+    if (id < b.n || b.collapsed[id])
+    {
+        out.iStartOrRightChild = firstPrim;
+        out.nPrims = (uint8_t)b.prims[id];
+    }
+    else
+    {
+        out.iStartOrRightChild = dfs + 1u + b.size[b.left[id]];
+        out.nPrims = 0;
+    }
+    b.nodesOut[dfs] = out;
+}

@@ -319,13 +319,17 @@ FLX_DEV void material_path(const Tasks &t, const SceneView &sc, uint32_t gid, co
 }
 
 
-// FUSED: the same thread also does what wf_raygen (for a path it has just terminated) and wf_mat_* (for a path it sends on)
+// Fused stages: the same thread also does what wf_raygen (for a path it has just terminated) and wf_mat_* (for a path it sends on)
 // would do next, instead of leaving that to two more passes over the path state.  Nothing crosses paths between those three
 // stages except the queue counters and the raygen-queue rank (known here from the look-back scan), so the state, the queues and
 // the counters after this one launch are exactly those after logic + raygen + materials.  Used by flx_render (and by the
 // per-stage ABI when the three calls arrive back to back, flx_api.cu); what it saves is the sparse second and third pass:
 // raygen touches ~1 in 5 paths (one 32-byte sector per 4 bytes used), the material stage re-reads what logic had in registers.
-template <bool SEPARATE_QUEUES, int MIN_BLOCKS, bool FUSED = false>
+// FUSE: 0 = wf_logic only; 1 = + the camera-ray part; 2 = + the material part as well.  The material part is worth fusing when all
+// materials go through one kernel anyway (the reference's single-queue mode, wavefrontAllMaterials): with per-type queues the
+// point of the separate kernels is that a warp sees ONE BSDF, and folding them into this kernel puts up to five heavy lobes into
+// every warp (Country Kitchen: 0.61 ms for the three kernels, 3.8 ms fully fused) -- so with wfSeparateQueues only level 1 is used.
+template <bool SEPARATE_QUEUES, int MIN_BLOCKS, int FUSE = 0>
 __global__ void __launch_bounds__(FLX_BLOCK, MIN_BLOCKS) k_logic(const __grid_constant__ Frame fr, const __grid_constant__ flx_RenderParams prm, const SceneView sc,
                                                      const ScanState scan, const uint32_t maxId)
 {
@@ -460,7 +464,7 @@ __global__ void __launch_bounds__(FLX_BLOCK, MIN_BLOCKS) k_logic(const __grid_co
         {
             if (len > 0u)
                 atomicAdd(reinterpret_cast<float4 *>(fr.pixels) + pixIdx, make_float4(Ei.x, Ei.y, Ei.z, 1.0f)); // one 128-bit reduction
-            if (!FUSED) // FUSED: the camera-ray part below carries the seed on and stores it
+            if (FUSE == 0) // fused: the camera-ray part below carries the seed on and stores it
                 t.setu(FLX_S_SEED, gid, seed);
         }
     }
@@ -553,7 +557,7 @@ __global__ void __launch_bounds__(FLX_BLOCK, MIN_BLOCKS) k_logic(const __grid_co
         }
         toMaterial = true;
         matType = mat.type;
-        if (FUSED) // the material part runs at the very end, after the last barrier (threads with heavy BSDFs would otherwise hold up their CTA)
+        if (FUSE == 2) // the material part runs at the very end, after the last barrier (threads with heavy BSDFs would otherwise hold up their CTA)
         {
             fMat = mat;
             fS = s;
@@ -599,12 +603,12 @@ __global__ void __launch_bounds__(FLX_BLOCK, MIN_BLOCKS) k_logic(const __grid_co
                 myMask = m;
         }
         // FUSED: every path that was regenerated or sent through its material is an extension ray of this iteration
-        const bool pushExt = FUSED && live && (terminate || q > 0);
-        const unsigned extMask = FUSED ? __ballot_sync(0xffffffffu, pushExt) : 0u;
-        if (FUSED && lane == 0)
+        const bool pushExt = FUSE >= 1 && live && (terminate || (FUSE == 2 && q > 0));
+        const unsigned extMask = FUSE >= 1 ? __ballot_sync(0xffffffffu, pushExt) : 0u;
+        if (FUSE >= 1 && lane == 0)
             s_cnt[NQ][warp] = __popc(extMask);
         __syncthreads();
-        if (threadIdx.x < NQ + (FUSED ? 1 : 0))
+        if (threadIdx.x < NQ + (FUSE >= 1 ? 1 : 0))
         {
             uint32_t total = 0;
 #pragma unroll
@@ -676,10 +680,10 @@ __global__ void __launch_bounds__(FLX_BLOCK, MIN_BLOCKS) k_logic(const __grid_co
     {
         const uint32_t rank = s_base + warpBase + __popc(termMask & ((1u << lane) - 1u));
         fr.queues[Q_RAYGEN][fr.counters->raygenQueue * 0u + rank] = gid;
-        if (FUSED) // wf_raygen for this path: its queue position is the rank just computed (wf_raygen.cl:25)
+        if (FUSE >= 1) // wf_raygen for this path: its queue position is the rank just computed (wf_raygen.cl:25)
             raygen_path(fr, prm, gid, (*fr.currPixelIdx + rank) % fr.tilePixels, seed);
     }
-    if (FUSED && toMaterial)
+    if (FUSE == 2 && toMaterial)
     {
         bool hasQueue = true;
         if (SEPARATE_QUEUES) // a type without a queue is dropped, as in the reference (wf_logic.cl:362-364)

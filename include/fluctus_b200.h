@@ -114,7 +114,9 @@ int flx_upload_scene(flx_ctx *ctx, const flx_Triangle *tris, uint32_t n_tris, co
  * = 8, src/bvh.hpp:70); no spatial splits, so every triangle is referenced exactly once (n_indices = n_tris).  Milliseconds
  * instead of seconds; the tree is of lower quality than the reference's SBVH (DESIGN.md 4.5 has the measured trade-off).
  * nodes_out must hold nodes_capacity >= 2 * n_tris - 1 records in the worst case; build_ms (may be NULL) = device time. */
-int flx_build_bvh(flx_ctx *ctx, const flx_Triangle *tris, uint32_t n_tris, uint32_t max_leaf, flx_Node *nodes_out, uint32_t nodes_capacity,
+enum { FLX_BVH_FAST = 0, /* LBVH: Morton order + binary radix tree + SAH collapse; a third of a millisecond for 300 k triangles */
+       FLX_BVH_PLOC = 1  /* parallel locally-ordered clustering (radius 16) on the Morton order + SAH collapse: better trees, a few ms */ };
+int flx_build_bvh(flx_ctx *ctx, const flx_Triangle *tris, uint32_t n_tris, uint32_t max_leaf, int quality, flx_Node *nodes_out, uint32_t nodes_capacity,
                   uint32_t *n_nodes_out, uint32_t *indices_out /* n_tris */, float *build_ms);
 
 /* CLContext::createEnvMap (clcontext.hpp:79; clcontext.cpp:467-511): rgb is w*h*3 floats; tables are w*h entries. */

@@ -92,11 +92,8 @@ static void emit(Ctx *c, const Sub *s, int32_t parent)
 
 static void release(Sub *s) { if (!s) return; release(s->l); release(s->r); free(s); }
 
-int port_build_lbvh(const Triangle *tris, uint32_t n, uint32_t maxLeaf, Node *nodes_out, uint32_t *n_nodes_out, uint32_t *indices_out)
+static void sorted_keys(const Triangle *tris, uint32_t n, f4 *pmin, f4 *pmax, uint64_t *keys)
 {
-    if (n == 0) return 1;
-    f4 *pmin = (f4 *)malloc(sizeof(f4) * n), *pmax = (f4 *)malloc(sizeof(f4) * n);
-    uint64_t *keys = (uint64_t *)malloc(sizeof(uint64_t) * n);
     float lo[3] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f}, hi[3] = {-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
     for (uint32_t i = 0; i < n; i++)
     {
@@ -115,6 +112,14 @@ int port_build_lbvh(const Triangle *tris, uint32_t n, uint32_t maxLeaf, Node *no
         keys[i] = ((uint64_t)m << 32) | (uint64_t)i;
     }
     qsort(keys, n, sizeof(uint64_t), cmp_u64);
+}
+
+int port_build_lbvh(const Triangle *tris, uint32_t n, uint32_t maxLeaf, Node *nodes_out, uint32_t *n_nodes_out, uint32_t *indices_out)
+{
+    if (n == 0) return 1;
+    f4 *pmin = (f4 *)malloc(sizeof(f4) * n), *pmax = (f4 *)malloc(sizeof(f4) * n);
+    uint64_t *keys = (uint64_t *)malloc(sizeof(uint64_t) * n);
+    sorted_keys(tris, n, pmin, pmax, keys);
     for (uint32_t i = 0; i < n; i++) indices_out[i] = (uint32_t)(keys[i] & 0xffffffffu);
     Ctx c = {keys, pmin, pmax, maxLeaf, nodes_out, 0};
     Sub *root = build(&c, 0, n - 1);
@@ -123,4 +128,105 @@ int port_build_lbvh(const Triangle *tris, uint32_t n, uint32_t maxLeaf, Node *no
     release(root);
     free(pmin); free(pmax); free(keys);
     return 0;
+}
+
+
+/* ================================================================ PLOC (the FLX_BVH_PLOC builder of flx_bvh_build.cuh)
+ * Locally-ordered clustering on the Morton order: every round each cluster picks, among the PLOC_RADIUS positions to either
+ * side, the neighbour whose merged box has the smallest area (lowest position on ties); mutual pairs merge into a new node
+ * that takes the lower partner's place; compaction keeps the order.  Node ids: leaf j (sorted position) -> j, inner nodes
+ * n, n+1, ... in order of creation (by round, then by position).  Emission is the general depth-first one. */
+#define PLOC_RADIUS 16
+typedef struct { f4 lo, hi; int left, right; float cost; uint32_t size, prims; int collapsed; } PNode;
+
+static void ploc_emit(const PNode *nd, uint32_t id, int32_t parent, Node *out, uint32_t *nOut, uint32_t *indices, uint32_t *nIdx, const uint64_t *keys, uint32_t n, int leafMode)
+{
+    /* leafMode: below a collapsed node only the triangles are listed, in order */
+    if (leafMode)
+    {
+        if (id < n) indices[(*nIdx)++] = (uint32_t)(keys[id] & 0xffffffffu);
+        else { ploc_emit(nd, (uint32_t)nd[id].left, 0, out, nOut, indices, nIdx, keys, n, 1); ploc_emit(nd, (uint32_t)nd[id].right, 0, out, nOut, indices, nIdx, keys, n, 1); }
+        return;
+    }
+    const uint32_t ind = (*nOut)++;
+    Node *o = &out[ind];
+    memset(o, 0, sizeof *o);
+    o->bmin = nd[id].lo; o->bmax = nd[id].hi; o->bmin.w = o->bmax.w = 0.0f;
+    o->parent = parent;
+    if (id < n || nd[id].collapsed)
+    {
+        o->link = *nIdx; o->nPrims = (uint8_t)nd[id].prims;
+        ploc_emit(nd, id, 0, out, nOut, indices, nIdx, keys, n, 1);
+        return;
+    }
+    ploc_emit(nd, (uint32_t)nd[id].left, (int32_t)ind, out, nOut, indices, nIdx, keys, n, 0);
+    o->link = *nOut;
+    ploc_emit(nd, (uint32_t)nd[id].right, (int32_t)ind, out, nOut, indices, nIdx, keys, n, 0);
+}
+
+int port_build_ploc(const Triangle *tris, uint32_t n, uint32_t maxLeaf, Node *nodes_out, uint32_t *n_nodes_out, uint32_t *indices_out)
+{
+    if (n == 0) return 1;
+    f4 *pmin = (f4 *)malloc(sizeof(f4) * n), *pmax = (f4 *)malloc(sizeof(f4) * n);
+    uint64_t *keys = (uint64_t *)malloc(sizeof(uint64_t) * n);
+    sorted_keys(tris, n, pmin, pmax, keys);
+    PNode *nd = (PNode *)calloc(2 * (size_t)n, sizeof(PNode));
+    uint32_t *cid = (uint32_t *)malloc(sizeof(uint32_t) * n), *next = (uint32_t *)malloc(sizeof(uint32_t) * n);
+    int *nn = (int *)malloc(sizeof(int) * n);
+    for (uint32_t j = 0; j < n; j++)
+    {
+        const uint32_t tri = (uint32_t)(keys[j] & 0xffffffffu);
+        nd[j].lo = pmin[tri]; nd[j].hi = pmax[tri]; nd[j].left = nd[j].right = -1;
+        nd[j].cost = half_area(nd[j].lo, nd[j].hi) * 1.0f; nd[j].size = 1; nd[j].prims = 1; nd[j].collapsed = 0;
+        cid[j] = j;
+    }
+    uint32_t m = n, nextId = n;
+    while (m > 1)
+    {
+        for (int p = 0; p < (int)m; p++)
+        {
+            float best = 3.402823466e+38f; int bestq = -1;
+            const PNode *a = &nd[cid[p]];
+            for (int d = -PLOC_RADIUS; d <= PLOC_RADIUS; d++)
+            {
+                const int q = p + d;
+                if (d == 0 || q < 0 || q >= (int)m) continue;
+                const PNode *b = &nd[cid[q]];
+                f4 lo, hi;
+                lo.x = fminf(a->lo.x, b->lo.x); lo.y = fminf(a->lo.y, b->lo.y); lo.z = fminf(a->lo.z, b->lo.z); lo.w = 0.0f;
+                hi.x = fmaxf(a->hi.x, b->hi.x); hi.y = fmaxf(a->hi.y, b->hi.y); hi.z = fmaxf(a->hi.z, b->hi.z); hi.w = 0.0f;
+                const float area = half_area(lo, hi);
+                if (area < best || bestq < 0) { best = area; bestq = q; }
+            }
+            nn[p] = bestq;
+        }
+        uint32_t kept = 0, merged = 0;
+        for (int p = 0; p < (int)m; p++)
+        {
+            const int q = nn[p];
+            const int mutual = q >= 0 && nn[q] == p;
+            if (mutual && q < p) continue;                 /* the upper partner disappears */
+            if (!(mutual && p < q)) { next[kept++] = cid[p]; continue; }
+            const uint32_t id = nextId + merged++, l = cid[p], r = cid[q];
+            PNode *o = &nd[id];
+            o->lo.x = fminf(nd[l].lo.x, nd[r].lo.x); o->lo.y = fminf(nd[l].lo.y, nd[r].lo.y); o->lo.z = fminf(nd[l].lo.z, nd[r].lo.z); o->lo.w = 0.0f;
+            o->hi.x = fmaxf(nd[l].hi.x, nd[r].hi.x); o->hi.y = fmaxf(nd[l].hi.y, nd[r].hi.y); o->hi.z = fmaxf(nd[l].hi.z, nd[r].hi.z); o->hi.w = 0.0f;
+            const float area = half_area(o->lo, o->hi);
+            const uint32_t count = nd[l].prims + nd[r].prims;
+            const float leafCost = area * (float)count;
+            const float innerCost = (area * 2.0f + nd[l].cost) + nd[r].cost;
+            const int collapse = count <= maxLeaf && leafCost <= innerCost;
+            o->left = (int)l; o->right = (int)r; o->cost = collapse ? leafCost : innerCost;
+            o->size = collapse ? 1u : 1u + nd[l].size + nd[r].size; o->prims = count; o->collapsed = collapse;
+            next[kept++] = id;
+        }
+        if (merged == 0) { free(pmin); free(pmax); free(keys); free(nd); free(cid); free(next); free(nn); return 2; }
+        uint32_t *t = cid; cid = next; next = t;
+        m = kept; nextId += merged;
+    }
+    uint32_t nOut = 0, nIdx = 0;
+    ploc_emit(nd, cid[0], -1, nodes_out, &nOut, indices_out, &nIdx, keys, n, 0);
+    *n_nodes_out = nOut;
+    free(pmin); free(pmax); free(keys); free(nd); free(cid); free(next); free(nn);
+    return nIdx == n ? 0 : 3;
 }

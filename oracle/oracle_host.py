@@ -252,7 +252,12 @@ class PortContext(_CpuContext):
     PREFIX = "port_"
 
 
-def build_lbvh(tris, max_leaf=8):
+def build_ploc(tris, max_leaf=8):
+    """CPU restatement of the FLX_BVH_PLOC builder (locally-ordered clustering) -> (nodes, indices)."""
+    return build_lbvh(tris, max_leaf, fn="port_build_ploc")
+
+
+def build_lbvh(tris, max_leaf=8, fn="port_build_lbvh"):
     """CPU restatement (oracle/bvh_oracle.c) of the GPU hierarchy builder flx_build_bvh -> (nodes, indices) in the
     reference's Node[] / index-list format."""
     from fluctus_b200.structs import NODE_DTYPE
@@ -261,8 +266,9 @@ def build_lbvh(tris, max_leaf=8):
     nodes = np.zeros(max(2 * n - 1, 1), NODE_DTYPE)
     indices = np.zeros(n, np.uint32)
     n_nodes = C.c_uint32()
-    lib.port_build_lbvh.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p]
-    rc = lib.port_build_lbvh(tris.ctypes.data, n, int(max_leaf), nodes.ctypes.data, C.byref(n_nodes), indices.ctypes.data)
+    f = getattr(lib, fn)
+    f.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p]
+    rc = f(tris.ctypes.data, n, int(max_leaf), nodes.ctypes.data, C.byref(n_nodes), indices.ctypes.data)
     if rc != 0:
-        raise RuntimeError("port_build_lbvh failed (%d)" % rc)
+        raise RuntimeError("%s failed (%d)" % (fn, rc))
     return nodes[:n_nodes.value].copy(), indices

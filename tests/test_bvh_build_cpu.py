@@ -13,7 +13,9 @@ from fluctus_b200.structs import TRIANGLE_DTYPE
 from conftest import scene_blob
 from parity_util import setup_context, validate_bvh
 
-from oracle.oracle_host import PortContext, build_lbvh, port_available
+from oracle.oracle_host import PortContext, build_lbvh, build_ploc, port_available
+
+BUILDERS = {"fast": build_lbvh, "ploc": build_ploc}
 
 pytestmark = pytest.mark.skipif(not port_available(), reason="oracle/liboracle.so not built (python oracle/build_oracle.py)")
 
@@ -31,17 +33,20 @@ def tri_soup(points):
     return t
 
 
+@pytest.mark.parametrize("quality", ["fast", "ploc"])
 @pytest.mark.parametrize("max_leaf", [1, 4, 8])
-def test_builder_output_honours_the_reference_contract(max_leaf):
+def test_builder_output_honours_the_reference_contract(max_leaf, quality):
     for scene in (make_room_scene(materials="mixed", n_blobs=8), teapot_scene()):
-        nodes, indices = build_lbvh(scene.tris, max_leaf)
+        nodes, indices = BUILDERS[quality](scene.tris, max_leaf)
         depth, leaves, sah = validate_bvh(nodes, indices, scene.tris, max_leaf)
-        assert depth < 62  # the traversal stack holds 64 entries (src/bvh.cl:240); a radix tree over 62-bit keys cannot be deeper
+        assert depth < 62  # the traversal stack holds 64 entries (src/bvh.cl:240); a radix tree over 62-bit keys cannot be deeper, PLOC is checked at build time
         if max_leaf == 1:
             assert leaves == len(scene.tris)
 
 
-def test_builder_edge_cases():
+@pytest.mark.parametrize("quality", ["fast", "ploc"])
+def test_builder_edge_cases(quality):
+    build_lbvh = BUILDERS[quality]
     rng = np.random.default_rng(5)
     one = tri_soup(rng.uniform(-1, 1, (1, 3, 3)).astype(np.float32))
     nodes, indices = build_lbvh(one)
@@ -61,19 +66,22 @@ def test_builder_edge_cases():
 def test_tree_quality_against_the_reference_sbvh():
     """SAH cost with the reference's constants (src/bvh.hpp:72-73).  No spatial splits and Morton order instead of a full
     sweep: worse than the reference's SBVH, but bounded -- the figure DESIGN.md quotes comes from here."""
-    for name, bound in (("conference", 2.0), ("teapot", 1.5)):
+    for name, bound, ploc_bound in (("conference", 2.0, 1.05), ("teapot", 1.5, 1.1)):
         scene = SceneData.load_blob(scene_blob(name))
         ref = validate_bvh(scene.nodes, scene.indices, scene.tris, unique_refs=False)
         mine = validate_bvh(*build_lbvh(scene.tris), scene.tris)
         assert mine[2] < bound * ref[2], (name, mine, ref)
+        ploc = validate_bvh(*build_ploc(scene.tris), scene.tris)  # locally-ordered clustering: on a par with the reference's SBVH
+        assert ploc[2] < ploc_bound * ref[2] and ploc[2] < mine[2], (name, ploc, ref)
 
 
-def test_rendering_with_the_built_tree_finds_the_same_hits():
+@pytest.mark.parametrize("quality", ["fast", "ploc"])
+def test_rendering_with_the_built_tree_finds_the_same_hits(quality):
     """Primary hits through the built tree and through the reference's SBVH (teapot fixture = reference PLY import + SBVH
     builder): bit-identical distance and triangle for all but grazing rays (shared edges, where which of two abutting
     triangles wins depends on the order boxes get culled), and there within 2 ulp; the accumulated image agrees."""
     scene = teapot_scene()
-    nodes, indices = build_lbvh(scene.tris)
+    nodes, indices = BUILDERS[quality](scene.tris)
     mine = SceneData(scene.tris, indices, nodes, scene.materials, scene.tex_desc, scene.tex_data)
     cam = dict(pos=(0, 1, 3.5), dir=(0, 0, -1), right=(1, 0, 0), up=(0, 1, 0), fov=60.0)
     W = H = 96

@@ -23,23 +23,28 @@ def same_tree(gpu_nodes, gpu_idx, cpu_nodes, cpu_idx, what):
     assert len(bad) == 0, "%s: %d nodes differ, first %d: %r vs %r" % (what, len(bad), bad[0], gpu_nodes[bad[0]], cpu_nodes[bad[0]])
 
 
-def build_both(tris, max_leaf=8):
-    from oracle.oracle_host import build_lbvh
+def build_both(tris, max_leaf=8, quality="fast"):
+    from oracle.oracle_host import build_lbvh, build_ploc
     with CLContext(1024) as gpu:
-        nodes, idx, ms = gpu.buildBVH(tris, max_leaf)
-    cn, ci = build_lbvh(tris, max_leaf)
+        nodes, idx, ms = gpu.buildBVH(tris, max_leaf, quality)
+    cn, ci = (build_ploc if quality == "ploc" else build_lbvh)(tris, max_leaf)
     return nodes, idx, cn, ci, ms
 
 
+QUALITIES = ["fast", "ploc"]
+
+
+@pytest.mark.parametrize("quality", QUALITIES)
 @pytest.mark.parametrize("max_leaf", [1, 8])
-def test_builder_matches_the_cpu_restatement(max_leaf):
+def test_builder_matches_the_cpu_restatement(max_leaf, quality):
     for name, scene in (("room", make_room_scene(materials="mixed", n_blobs=8)), ("teapot", teapot_scene())):
-        nodes, idx, cn, ci, _ = build_both(scene.tris, max_leaf)
-        same_tree(nodes, idx, cn, ci, "%s max_leaf=%d" % (name, max_leaf))
+        nodes, idx, cn, ci, _ = build_both(scene.tris, max_leaf, quality)
+        same_tree(nodes, idx, cn, ci, "%s max_leaf=%d %s" % (name, max_leaf, quality))
         validate_bvh(nodes, idx, scene.tris, max_leaf)
 
 
-def test_builder_edge_cases():
+@pytest.mark.parametrize("quality", QUALITIES)
+def test_builder_edge_cases(quality):
     rng = np.random.default_rng(5)
     cases = {"one": rng.uniform(-1, 1, (1, 3, 3)), "two": rng.uniform(-1, 1, (2, 3, 3)), "identical": np.repeat(rng.uniform(-1, 1, (1, 3, 3)), 37, axis=0),
              "ragged": rng.uniform(-1, 1, (1001, 3, 3)) * 1e-3 + rng.uniform(-50, 50, (1001, 1, 3))}
@@ -48,24 +53,26 @@ def test_builder_edge_cases():
     cases["flat"] = flat
     for name, pts in cases.items():
         tris = tri_soup(pts.astype(np.float32))
-        nodes, idx, cn, ci, _ = build_both(tris, 4)
-        same_tree(nodes, idx, cn, ci, name)
+        nodes, idx, cn, ci, _ = build_both(tris, 4, quality)
+        same_tree(nodes, idx, cn, ci, name + " " + quality)
 
 
+@pytest.mark.parametrize("quality", QUALITIES)
 @pytest.mark.parametrize("name", ["conference", "country_kitchen"])
-def test_builder_matches_on_reference_assets(name):
+def test_builder_matches_on_reference_assets(name, quality):
     scene = SceneData.load_blob(scene_blob(name))
-    nodes, idx, cn, ci, ms = build_both(scene.tris)
-    same_tree(nodes, idx, cn, ci, name)
+    nodes, idx, cn, ci, ms = build_both(scene.tris, 8, quality)
+    same_tree(nodes, idx, cn, ci, name + " " + quality)
     assert ms < 50.0, "build took %.2f ms" % ms  # the reference's SBVH build takes seconds
 
 
-def test_wavefront_through_the_built_tree_is_in_lockstep_with_the_oracle():
+@pytest.mark.parametrize("quality", QUALITIES)
+def test_wavefront_through_the_built_tree_is_in_lockstep_with_the_oracle(quality):
     room = make_room_scene(materials="mixed", textured=True, n_blobs=8)
     W, H, N = 96, 64, 6144
     params = room_params(room, W, H, max_bounces=6, separate_queues=True)
     with CLContext(N) as gpu:
-        nodes, idx, _ = gpu.buildBVH(room.tris)
+        nodes, idx, _ = gpu.buildBVH(room.tris, 8, quality)
         scene = SceneData(room.tris, idx, nodes, room.materials, room.tex_desc, room.tex_data)
         run_lockstep(gpu, oracle_ctx(N), scene, params, iterations=12)
 

@@ -20,13 +20,15 @@ def main():
         ref = SceneData.load_blob(os.path.join(ROOT, "oracle", "_ref", "scenes", scene_name + ".bin"))
         row = dict(scene=scene_name, triangles=len(ref.tris))
         with CLContext(N) as ctx:
-            ctx.buildBVH(ref.tris)  # warm-up (allocations, cub temp sizing)
-            times = [ctx.buildBVH(ref.tris)[2] for _ in range(5)]
-            nodes, idx, _ = ctx.buildBVH(ref.tris)
-            row.update(build_ms=round(min(times), 3), build_ms_all=[round(t, 3) for t in times])
-            mine = SceneData(ref.tris, idx, nodes, ref.materials, ref.tex_desc, ref.tex_data)
-            for label, sc in (("reference_sbvh", ref), ("gpu_lbvh", mine)):
-                depth, leaves, sah = validate_bvh(sc.nodes, sc.indices, sc.tris, unique_refs=(label == "gpu_lbvh"))
+            built = {}
+            for quality in ("fast", "ploc"):
+                ctx.buildBVH(ref.tris, 8, quality)  # warm-up (allocations, cub temp sizing)
+                times = [ctx.buildBVH(ref.tris, 8, quality)[2] for _ in range(5)]
+                nodes, idx, _ = ctx.buildBVH(ref.tris, 8, quality)
+                row["build_ms_" + quality] = round(min(times), 3)
+                built[quality] = SceneData(ref.tris, idx, nodes, ref.materials, ref.tex_desc, ref.tex_data)
+            for label, sc in (("reference_sbvh", ref), ("gpu_lbvh", built["fast"]), ("gpu_ploc", built["ploc"])):
+                depth, leaves, sah = validate_bvh(sc.nodes, sc.indices, sc.tris, unique_refs=(label != "reference_sbvh"))
                 params = params_for(scene_name, sc, W, H)
                 ctx.uploadSceneData(sc)
                 if scene_name in ENV_MAPS:
@@ -41,7 +43,8 @@ def main():
                 st = ctx.getStats()
                 row[label] = dict(nodes=len(sc.nodes), references=len(sc.indices), depth=depth, leaves=leaves, sah_cost=round(sah, 2),
                                   mrays_per_s=round((st.extensionRays + st.shadowRays) / ms / 1e3, 1))
-        row["throughput_ratio"] = round(row["gpu_lbvh"]["mrays_per_s"] / row["reference_sbvh"]["mrays_per_s"], 3)
+        row["throughput_ratio_lbvh"] = round(row["gpu_lbvh"]["mrays_per_s"] / row["reference_sbvh"]["mrays_per_s"], 3)
+        row["throughput_ratio_ploc"] = round(row["gpu_ploc"]["mrays_per_s"] / row["reference_sbvh"]["mrays_per_s"], 3)
         print(json.dumps(row), flush=True)
 
 

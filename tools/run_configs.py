@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--configs", default="C2,C3,C4,metric")
     ap.add_argument("--iters", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--tune", default="", help="comma-separated key=value tuning knobs (CLContext.setTuning)")
     a = ap.parse_args()
     from bench import a_ext_bytes, a_shadow_bytes, measured_peaks
     from bench_configs import ENV_MAPS, params_for
@@ -33,6 +34,8 @@ def main():
         scene = SceneData.load_blob(os.path.join(ROOT, "oracle", "_ref", "scenes", scene_name + ".bin"))
         params = params_for(scene_name, scene, W, H)
         with CLContext(N) as ctx:
+            if a.tune:
+                ctx.setTuning(**{k: int(v) for k, v in (kv.split("=") for kv in a.tune.split(","))})
             ctx.uploadSceneData(scene)
             if scene_name in ENV_MAPS:
                 ctx.createEnvMap(EnvMapData.load_blob(os.path.join(ROOT, "oracle", "_ref", "scenes", ENV_MAPS[scene_name] + ".env.bin")))
