@@ -66,6 +66,11 @@ struct flx_ctx
     cudaStream_t stream2 = nullptr;   // flx_render runs the shadow-ray kernel here so its start overlaps the extension kernel's tail
     cudaStream_t cur = nullptr;       // stream the next traversal launch goes to (== stream except inside flx_render)
     cudaEvent_t evFork = nullptr, evJoin = nullptr;
+    cudaStream_t stream3 = nullptr;   // flx_render runs the display pass here, beside the traversal stages (which never touch the accumulator)
+    cudaEvent_t evPostFork = nullptr, evPostJoin = nullptr;
+    cudaEvent_t evPixels = nullptr;   // recorded after every launch that writes the accumulator (logic's splat, the resets, mk splat)
+    bool pixelsEventValid = false;
+    int overlapPostprocess = 1;
     int overlapTrace = 1;
     // Every ABI call that touches the stream bumps opSeq; flx_enqueue_extrays remembers its number.  A flx_enqueue_shadowrays
     // that comes DIRECTLY after it (the order of the reference's loop, tracer.cpp:253-254 / 437-438) may then run on the second
@@ -357,6 +362,12 @@ int launchCheck(flx_ctx *ctx, const char *what)
     if (e != cudaSuccess)
         return fail(ctx, (int)e, "launch of %s failed: %s", what, cudaGetErrorString(e));
     return 0;
+}
+
+// after a launch that writes the accumulator: the display pass may start from here (flx_enqueue_postprocess)
+void markPixelsWritten(flx_ctx *ctx)
+{
+    ctx->pixelsEventValid = cudaEventRecord(ctx->evPixels, ctx->stream) == cudaSuccess;
 }
 
 unsigned streamingGrid(uint32_t n) { return std::max(1u, std::min((n + FLX_BLOCK - 1) / FLX_BLOCK, 148u * 16u)); }
@@ -799,6 +810,10 @@ int flx_create(int device, uint32_t num_tasks, flx_ctx **out)
     } while (0)
     CUB(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUB(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    CUB(cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking));
+    CUB(cudaEventCreateWithFlags(&c->evPostFork, cudaEventDisableTiming));
+    CUB(cudaEventCreateWithFlags(&c->evPostJoin, cudaEventDisableTiming));
+    CUB(cudaEventCreateWithFlags(&c->evPixels, cudaEventDisableTiming));
     c->cur = c->stream;
     CUB(cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming));
     CUB(cudaEventCreateWithFlags(&c->evJoin, cudaEventDisableTiming));
@@ -903,6 +918,14 @@ void flx_destroy(flx_ctx *c)
         cudaEventDestroy(c->evFork);
     if (c->evJoin)
         cudaEventDestroy(c->evJoin);
+    if (c->evPostFork)
+        cudaEventDestroy(c->evPostFork);
+    if (c->evPostJoin)
+        cudaEventDestroy(c->evPostJoin);
+    if (c->evPixels)
+        cudaEventDestroy(c->evPixels);
+    if (c->stream3)
+        cudaStreamDestroy(c->stream3);
     if (c->stream2)
         cudaStreamDestroy(c->stream2);
     if (c->stream)
@@ -1220,6 +1243,7 @@ int flx_upload_envmap(flx_ctx *ctx, const float *rgb, int32_t w, int32_t h, cons
 
 static int allocImage(flx_ctx *ctx)
 {
+    ctx->pixelsEventValid = false;
     const uint32_t rows = localRows(ctx->height, ctx->part, ctx->nParts, ctx->stripeRows);
     ctx->tilePixels = rows * ctx->width;
     CU(cudaSetDevice(ctx->device));
@@ -1291,6 +1315,7 @@ int flx_enqueue_reset(flx_ctx *ctx)
     const uint32_t n = std::max(ctx->numTasks, ctx->tilePixels); // clcontext.cpp:767
     Timed tm(ctx, FLX_K_RESET);
     k_reset<<<(n + FLX_BLOCK - 1) / FLX_BLOCK, FLX_BLOCK, 0, ctx->stream>>>(makeFrame(ctx), ctx->params);
+    markPixelsWritten(ctx);
     return launchCheck(ctx, "k_reset");
 }
 
@@ -1405,6 +1430,7 @@ static int launchLogic(flx_ctx *ctx, int first_iteration, bool fused)
             }
 #undef FUSEDK
         }
+        markPixelsWritten(ctx);
         int rc = launchCheck(ctx, "k_logic<fused>");
         if (rc == 0 && sep)
             rc = launchMaterials(ctx);
@@ -1419,6 +1445,7 @@ static int launchLogic(flx_ctx *ctx, int first_iteration, bool fused)
     default: if (sep) LOGIC(true, 3); else LOGIC(false, 3); break;
     }
 #undef LOGIC
+    markPixelsWritten(ctx);
     return launchCheck(ctx, "k_logic");
 }
 
@@ -1504,6 +1531,7 @@ int flx_enqueue_mk_reset(flx_ctx *ctx)
     const MkView mk = makeMk(ctx);
     Timed tm(ctx, FLX_K_MK_RESET);
     k_mk_reset<<<mkGrid(mk.limit), FLX_BLOCK, 0, ctx->stream>>>(makeFrame(ctx), mk.limit);
+    markPixelsWritten(ctx);
     return launchCheck(ctx, "k_mk_reset");
 }
 
@@ -1566,6 +1594,7 @@ int flx_enqueue_mk_splat(flx_ctx *ctx)
     const MkView mk = makeMk(ctx);
     Timed tm(ctx, FLX_K_MK_SPLAT);
     k_mk_splat<<<mkGrid(mk.limit), FLX_BLOCK, 0, ctx->stream>>>(makeFrame(ctx), mk);
+    markPixelsWritten(ctx);
     return launchCheck(ctx, "k_mk_splat");
 }
 
@@ -1578,6 +1607,7 @@ int flx_enqueue_mk_splat_preview(flx_ctx *ctx)
     const MkView mk = makeMk(ctx);
     Timed tm(ctx, FLX_K_MK_SPLAT);
     k_mk_splat_preview<<<mkGrid(mk.limit), FLX_BLOCK, 0, ctx->stream>>>(makeFrame(ctx), mk.limit);
+    markPixelsWritten(ctx);
     return launchCheck(ctx, "k_mk_splat_preview");
 }
 
@@ -1605,16 +1635,34 @@ int flx_render_single(flx_ctx *ctx, uint32_t spp)
     return 0;
 }
 
+static int launchPostprocess(flx_ctx *ctx)
+{
+    Timed tm(ctx, FLX_K_POSTPROCESS);
+    k_postprocess<<<streamingGrid(ctx->tilePixels), FLX_BLOCK, 0, ctx->cur>>>(reinterpret_cast<const float4 *>(ctx->pixels), reinterpret_cast<float4 *>(ctx->preview),
+                                                                            ctx->tilePixels, ctx->params.ppParams.exposure, ctx->params.ppParams.tmOperator);
+    return launchCheck(ctx, "k_postprocess");
+}
+
 int flx_enqueue_postprocess(flx_ctx *ctx)
 {
     int rc = checkReady(ctx, false, true);
     if (rc)
         return rc;
     CU(cudaSetDevice(ctx->device));
-    Timed tm(ctx, FLX_K_POSTPROCESS);
-    k_postprocess<<<streamingGrid(ctx->tilePixels), FLX_BLOCK, 0, ctx->stream>>>(reinterpret_cast<const float4 *>(ctx->pixels), reinterpret_cast<float4 *>(ctx->preview),
-                                                                               ctx->tilePixels, ctx->params.ppParams.exposure, ctx->params.ppParams.tmOperator);
-    return launchCheck(ctx, "k_postprocess");
+    if (!(ctx->overlapPostprocess && ctx->pixelsEventValid))
+        return launchPostprocess(ctx);
+    // The accumulator has not changed since the event recorded after its last writer (normally this iteration's logic stage),
+    // and what was enqueued since (the traversal stages, the counter bookkeeping) does not touch it: start from that event on
+    // the third stream, beside that work; the main stream joins before anything enqueued later.
+    CU(cudaStreamWaitEvent(ctx->stream3, ctx->evPixels, 0));
+    ctx->cur = ctx->stream3;
+    rc = launchPostprocess(ctx);
+    ctx->cur = ctx->stream;
+    if (rc)
+        return rc;
+    CU(cudaEventRecord(ctx->evPostJoin, ctx->stream3));
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->evPostJoin, 0));
+    return 0;
 }
 
 int flx_read_preview(flx_ctx *ctx, float *rgba, size_t n_pixels)
@@ -1738,6 +1786,22 @@ int flx_render(flx_ctx *ctx, uint32_t n_iterations)
             if ((rc = flx_enqueue_materials(ctx)))
                 return rc;
         }
+        // The display pass reads the accumulator, which only the logic stage writes (splat): the picture after this iteration is
+        // fixed from here on, so the pass can run beside the two traversal stages instead of after them (tracer.cpp:447 runs it
+        // last; same input, same output).  Joined before the next iteration's logic may splat again.  Level 2 only: in this
+        // loop it gains 0.4 % and makes the extension kernel's own elapsed time (the roofline's denominator) meaningless.
+        const bool postBeside = ctx->postprocessInLoop && ctx->overlapPostprocess == 2;
+        if (postBeside)
+        {
+            CU(cudaEventRecord(ctx->evPostFork, ctx->stream));
+            CU(cudaStreamWaitEvent(ctx->stream3, ctx->evPostFork, 0));
+            ctx->cur = ctx->stream3;
+            rc = launchPostprocess(ctx);
+            ctx->cur = ctx->stream;
+            if (rc)
+                return rc;
+            CU(cudaEventRecord(ctx->evPostJoin, ctx->stream3));
+        }
         k_snapshot_counters<<<1, 32, 0, ctx->stream>>>(it);
         // extension then shadow rays: the second call overlaps the first on a second stream (see flx_enqueue_shadowrays)
         if ((rc = flx_enqueue_extrays(ctx)))
@@ -1750,7 +1814,9 @@ int flx_render(flx_ctx *ctx, uint32_t n_iterations)
         }
         if ((rc = launchCheck(ctx, "k_end_iteration")))
             return rc;
-        if (ctx->postprocessInLoop && (rc = flx_enqueue_postprocess(ctx))) // tracer.cpp:447
+        if (postBeside)
+            CU(cudaStreamWaitEvent(ctx->stream, ctx->evPostJoin, 0));
+        else if (ctx->postprocessInLoop && (rc = flx_enqueue_postprocess(ctx))) // tracer.cpp:447
             return rc;
     }
     return 0;
@@ -1835,6 +1901,10 @@ int flx_set_tuning(flx_ctx *ctx, int key, int value)
         return 0;
     case FLX_TUNE_OVERLAP_TRACE:
         ctx->overlapTrace = value != 0;
+        return 0;
+    case FLX_TUNE_OVERLAP_POSTPROCESS:
+        REQUIRE(value >= 0 && value <= 2, "flx_set_tuning: display-pass overlap must be 0, 1 or 2");
+        ctx->overlapPostprocess = value;
         return 0;
     case FLX_TUNE_FETCH_CHUNK:
         REQUIRE(value >= 32 && value <= 4096, "flx_set_tuning: fetch chunk must be in 32..4096");
