@@ -679,7 +679,7 @@ __global__ void __launch_bounds__(FLX_BLOCK, MIN_BLOCKS) k_logic(const __grid_co
     if (live && terminate)
     {
         const uint32_t rank = s_base + warpBase + __popc(termMask & ((1u << lane) - 1u));
-        fr.queues[Q_RAYGEN][fr.counters->raygenQueue * 0u + rank] = gid;
+        fr.queues[Q_RAYGEN][rank] = gid;
         if (FUSE >= 1) // wf_raygen for this path: its queue position is the rank just computed (wf_raygen.cl:25)
             raygen_path(fr, prm, gid, (*fr.currPixelIdx + rank) % fr.tilePixels, seed);
     }

@@ -100,8 +100,6 @@ def test_device_repack_matches_the_host_repack(name):
     layouts = []
     for on_host in (1, 0):
         with CLContext(256) as gpu:
-            if name == "built" and not on_host:
-                pass
             gpu.setTuning(repack_on_host=on_host)
             if name == "built":
                 nodes, idx, _ = gpu.buildBVH(scene.tris)

@@ -1,3 +1,6 @@
+"""Where the end-to-end time of bench.py's e2e leg goes (GPU box): context creation, scene upload (+ hierarchy repack), image
+allocation, prologue, the per-stage loop of Tracer.iterate() and the image read-back, next to the fused loop's per-iteration time.
+FLX_DEBUG_TIMING=1 additionally prints flx_upload_scene's own split."""
 import os, sys, time
 ROOT = os.getcwd()
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
