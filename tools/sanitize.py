@@ -47,8 +47,9 @@ def main():
                 assert np.isfinite(pix).all()
     # the hierarchy builder, incl. the one- and two-triangle cases and a scene rendered through its tree
     with CLContext(1500) as ctx:
-        for n in (1, 2, len(scene.tris)):
-            nodes, idx, _ = ctx.buildBVH(scene.tris[:n], 8 if n > 2 else 1)
+        for quality in ("fast", "ploc"):
+            for n in (1, 2, len(scene.tris)):
+                nodes, idx, _ = ctx.buildBVH(scene.tris[:n], 8 if n > 2 else 1, quality)
         from fluctus_b200 import SceneData
         built = SceneData(scene.tris, idx, nodes, scene.materials, scene.tex_desc, scene.tex_data)
         params = room_params(built, 40, 24, max_bounces=3)
@@ -57,6 +58,11 @@ def main():
         tr = Tracer(ctx, params)
         tr.start()
         ctx.render(3)
+        ctx.setTuning(fuse_stages=0, overlap_postprocess=2, repack_on_host=1)
+        ctx.uploadSceneData(built)
+        tr.start()
+        ctx.render(2)
+        tr.iterate()
         assert np.isfinite(ctx.readPixels()).all()
     print("SANITIZE_RUN_OK")
 
