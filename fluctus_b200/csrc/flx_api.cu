@@ -1102,6 +1102,7 @@ int flx_build_bvh(flx_ctx *ctx, const flx_Triangle *tris, uint32_t n_tris, uint3
         BALLOC(pb.flags, n);
         BALLOC(pb.scan, n);
         BALLOC(pb.depthMax, 1);
+        BALLOC(pb.state, 2);
         cub::DeviceScan::ExclusiveSum(nullptr, scanBytes, pb.flags, pb.scan, (int)n, ctx->stream);
         unsigned char *t = nullptr;
         BALLOC(t, scanBytes);
@@ -1138,28 +1139,30 @@ int flx_build_bvh(flx_ctx *ctx, const flx_Triangle *tris, uint32_t n_tris, uint3
         {
             cu(cudaMemsetAsync(pb.depthMax, 0, sizeof(uint32_t), st), "memset");
             k_ploc_init<<<gridN, FLX_BVH_BLOCK, 0, st>>>(pb);
-            uint32_t m = n, nextId = n;
+            // Rounds are enqueued in batches without waiting: the cluster count and the next node id live on the device, every
+            // kernel reads them there.  After a batch the host fetches the count -- to stop, and to shrink the grids.  A round
+            // with one cluster left is a no-op, so overshooting inside a batch is harmless.
+            uint32_t bound = n; // cluster count as last seen by the host
             uint32_t *cid = pb.cidA, *cidNext = pb.cidB;
-            while (m > 1 && rc == 0) // every round merges at least the closest pair; typically a third of the clusters
+            const int kBatch = 8;
+            while (bound > 1 && rc == 0)
             {
-                const unsigned gridM = (m + FLX_BVH_BLOCK - 1) / FLX_BVH_BLOCK;
-                k_ploc_nearest<<<gridM, FLX_BVH_BLOCK, 0, st>>>(pb, cid, m);
-                k_ploc_flags<<<gridM, FLX_BVH_BLOCK, 0, st>>>(pb, m);
-                cu(cub::DeviceScan::ExclusiveSum(scanTemp, scanBytes, pb.flags, pb.scan, (int)m, st), "scan");
-                unsigned long long last[2] = {0, 0};
-                cu(cudaMemcpyAsync(&last[0], pb.scan + (m - 1), 8, cudaMemcpyDeviceToHost, st), "round read-back");
-                cu(cudaMemcpyAsync(&last[1], pb.flags + (m - 1), 8, cudaMemcpyDeviceToHost, st), "round read-back");
-                cu(cudaStreamSynchronize(st), "PLOC round");
-                const unsigned long long totals = last[0] + last[1];
-                const uint32_t kept = (uint32_t)(totals & 0xffffffffull), merged = (uint32_t)(totals >> 32);
-                if (rc == 0 && (merged == 0 || kept + merged != m))
-                    rc = fail(ctx, FLX_E_INVALID, "flx_build_bvh: PLOC round made no progress (%u clusters, %u merges)", m, merged);
-                if (rc)
-                    break;
-                k_ploc_apply<<<gridM, FLX_BVH_BLOCK, 0, st>>>(pb, cid, cidNext, m, nextId);
-                std::swap(cid, cidNext);
-                m = kept;
-                nextId += merged;
+                const unsigned gridM = (bound + FLX_BVH_BLOCK - 1) / FLX_BVH_BLOCK;
+                for (int r = 0; r < kBatch; r++)
+                {
+                    k_ploc_nearest<<<gridM, FLX_BVH_BLOCK, 0, st>>>(pb, cid);
+                    k_ploc_flags<<<gridM, FLX_BVH_BLOCK, 0, st>>>(pb, bound);
+                    cu(cub::DeviceScan::ExclusiveSum(scanTemp, scanBytes, pb.flags, pb.scan, (int)bound, st), "scan");
+                    k_ploc_apply<<<gridM, FLX_BVH_BLOCK, 0, st>>>(pb, cid, cidNext);
+                    k_ploc_advance<<<1, 32, 0, st>>>(pb);
+                    std::swap(cid, cidNext);
+                }
+                uint32_t left = 0;
+                cu(cudaMemcpyAsync(&left, pb.state, sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "round read-back");
+                cu(cudaStreamSynchronize(st), "PLOC rounds");
+                if (rc == 0 && (left == 0 || left >= bound)) // every round merges at least the closest pair
+                    rc = fail(ctx, FLX_E_INVALID, "flx_build_bvh: PLOC made no progress (%u clusters after a batch that started with %u)", left, bound);
+                bound = left;
             }
             k_ploc_emit<<<gridT, FLX_BVH_BLOCK, 0, st>>>(pb);
         }

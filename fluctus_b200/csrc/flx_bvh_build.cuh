@@ -311,6 +311,7 @@ struct PlocBuild
     int *nn;                 // per position: chosen neighbour position
     unsigned long long *flags, *scan; // per position: keep | merge << 32, and its exclusive sum
     uint32_t *depthMax;
+    uint32_t *state;         // {clusters left, next node id}: lives on the device so rounds can be enqueued without a host round trip
     flx_Node *nodesOut;
     uint32_t *indicesOut;
 };
@@ -332,10 +333,18 @@ __global__ void __launch_bounds__(FLX_BVH_BLOCK) k_ploc_init(const PlocBuild b)
     b.prims[j] = 1u;
     b.collapsed[j] = 0u;
     b.cidA[j] = j;
+    if (j == 0)
+    {
+        b.state[0] = b.n;
+        b.state[1] = b.n;
+    }
 }
 
-__global__ void __launch_bounds__(FLX_BVH_BLOCK) k_ploc_nearest(const PlocBuild b, const uint32_t *cid, const uint32_t m)
+__global__ void __launch_bounds__(FLX_BVH_BLOCK) k_ploc_nearest(const PlocBuild b, const uint32_t *cid)
 {
+    const uint32_t m = b.state[0];
+    if (blockIdx.x * FLX_BVH_BLOCK >= m)
+        return;
     __shared__ float4 s_lo[FLX_BVH_BLOCK + 2 * FLX_PLOC_RADIUS], s_hi[FLX_BVH_BLOCK + 2 * FLX_PLOC_RADIUS];
     const int base = (int)(blockIdx.x * FLX_BVH_BLOCK) - FLX_PLOC_RADIUS;
     for (int k = threadIdx.x; k < FLX_BVH_BLOCK + 2 * FLX_PLOC_RADIUS; k += FLX_BVH_BLOCK)
@@ -373,11 +382,19 @@ __global__ void __launch_bounds__(FLX_BVH_BLOCK) k_ploc_nearest(const PlocBuild 
     b.nn[p] = bestq;
 }
 
-__global__ void __launch_bounds__(FLX_BVH_BLOCK) k_ploc_flags(const PlocBuild b, const uint32_t m)
+// bound: the number of positions the following scan covers (the cluster count as last known to the host); positions past the
+// current count contribute zeros
+__global__ void __launch_bounds__(FLX_BVH_BLOCK) k_ploc_flags(const PlocBuild b, const uint32_t bound)
 {
+    const uint32_t m = b.state[0];
     const int p = (int)(blockIdx.x * FLX_BVH_BLOCK + threadIdx.x);
-    if (p >= (int)m)
+    if (p >= (int)bound)
         return;
+    if (p >= (int)m)
+    {
+        b.flags[p] = 0ull;
+        return;
+    }
     const int q = b.nn[p];
     const bool mutual = q >= 0 && b.nn[q] == p;
     const unsigned long long keep = (mutual && q < p) ? 0ull : 1ull; // the upper partner of a pair disappears
@@ -385,8 +402,9 @@ __global__ void __launch_bounds__(FLX_BVH_BLOCK) k_ploc_flags(const PlocBuild b,
     b.flags[p] = keep | (merge << 32);
 }
 
-__global__ void __launch_bounds__(FLX_BVH_BLOCK) k_ploc_apply(const PlocBuild b, const uint32_t *cid, uint32_t *cidNext, const uint32_t m, const uint32_t nextId)
+__global__ void __launch_bounds__(FLX_BVH_BLOCK) k_ploc_apply(const PlocBuild b, const uint32_t *cid, uint32_t *cidNext)
 {
+    const uint32_t m = b.state[0], nextId = b.state[1];
     const int p = (int)(blockIdx.x * FLX_BVH_BLOCK + threadIdx.x);
     if (p >= (int)m)
         return;
@@ -421,6 +439,17 @@ __global__ void __launch_bounds__(FLX_BVH_BLOCK) k_ploc_apply(const PlocBuild b,
     b.prims[id] = count;
     b.collapsed[id] = collapse ? 1u : 0u;
     cidNext[pos] = id;
+}
+
+// one thread, after k_ploc_apply: the totals of the round's exclusive sum become the new cluster count / next node id
+__global__ void k_ploc_advance(const PlocBuild b)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0)
+        return;
+    const uint32_t m = b.state[0];
+    const unsigned long long totals = b.scan[m - 1] + b.flags[m - 1];
+    b.state[0] = (uint32_t)(totals & 0xffffffffull);
+    b.state[1] += (uint32_t)(totals >> 32);
 }
 
 __global__ void __launch_bounds__(FLX_BVH_BLOCK) k_ploc_emit(const PlocBuild b)
