@@ -138,6 +138,78 @@ class Tracer:
         c.finishQueue()
         self.iteration += 1
 
+    # ---- the reference's own benchmark protocol
+    def runBenchmarkScene(self, scene_name, render_len=30.0, use_wavefront=True, log_every=0.5, clock=None):
+        """One scene of Tracer::runBenchmark (src/tracer.cpp:372-383, 416-503): reset BOTH integrators' state and the queue
+        counters (no prologue: the first logic pass finds every path at length 0 and sends it to raygen), then iterate for
+        `render_len` seconds of wall time, synchronising every iteration, and log Mrays/s every `log_every` seconds as CSV
+        rows `scene;time;primary;extension;shadow;total;samples` (the format plot_benchmarks.py reads).  Returns
+        (rows, summary) where summary = Mrays/s over the whole run: primary, extension, shadow, samples, total."""
+        import time
+        clock = clock or time.perf_counter
+        c, p = self.clctx, self.params
+        self.iteration = 0
+        c.updateParams(p)
+        c.enqueueResetKernel(p)
+        c.enqueueWfResetKernel(p)
+        c.enqueueClearWfQueues()
+        c.finishQueue()
+        c.resetStats()
+        rows, log = [], []
+        acc = dict(primaryRays=0, extensionRays=0, shadowRays=0, samples=0)
+        mk_prev = (0, 0, 0, 0)
+        start = curr = last_log = clock()
+
+        def log_stats(elapsed, delta_t):
+            nonlocal acc, last_log
+            s = 1e6 * delta_t
+            log.append(dict(acc))
+            rows.append("%s;%g;%g;%g;%g;%g;%g" % (scene_name, elapsed, acc["primaryRays"] / s, acc["extensionRays"] / s, acc["shadowRays"] / s,
+                                                  (acc["primaryRays"] + acc["extensionRays"] + acc["shadowRays"]) / s, acc["samples"] / s))
+            acc = dict(primaryRays=0, extensionRays=0, shadowRays=0, samples=0)
+            last_log = clock()
+
+        while curr - start < render_len:
+            cnt = QueueCounters()
+            if use_wavefront:
+                c.enqueueWfLogicKernel(p, False)
+                c.enqueueWfRaygenKernel(p)
+                c.enqueueWfMaterialKernels(p)
+                c.enqueueGetCounters(cnt)
+                c.enqueueWfExtRayKernel(p)
+                c.enqueueWfShadowRayKernel(p)
+                c.enqueueClearWfQueues()
+            else:
+                c.enqueueRayGenKernel(p)
+                c.enqueueNextVertexKernel(p)
+                c.enqueueBsdfSampleKernel(p)
+                c.enqueueSplatKernel(p)
+            c.enqueuePostprocessKernel(p)
+            c.finishQueue()
+            if use_wavefront:
+                acc["extensionRays"] += cnt.extensionQueue
+                acc["shadowRays"] += cnt.shadowQueue
+                acc["primaryRays"] += cnt.raygenQueue
+                acc["samples"] += cnt.raygenQueue if self.iteration > 0 else 0
+            else:  # fetchStatsAsync: the microkernels count on the device
+                st = c.getStats()
+                now = (int(st.primaryRays), int(st.extensionRays), int(st.shadowRays), int(st.samples))
+                for k, a, b in zip(("primaryRays", "extensionRays", "shadowRays", "samples"), now, mk_prev):
+                    acc[k] += a - b
+                mk_prev = now
+            c.updatePixelIndex(self._num_pixels(), cnt.raygenQueue)
+            if curr - last_log > log_every:
+                log_stats(curr - start, curr - last_log)
+            self.iteration += 1
+            curr = clock()
+        log_stats(curr - start, max(curr - last_log, 1e-9))
+        total_t = 1e6 * (curr - start)
+        sums = {k: sum(entry[k] for entry in log) for k in ("primaryRays", "extensionRays", "shadowRays", "samples")}
+        summary = dict(primary=sums["primaryRays"] / total_t, extension=sums["extensionRays"] / total_t, shadow=sums["shadowRays"] / total_t,
+                       samples=sums["samples"] / total_t, total=(sums["primaryRays"] + sums["extensionRays"] + sums["shadowRays"]) / total_t,
+                       iterations=self.iteration, seconds=curr - start)
+        return rows, summary
+
     def _num_pixels(self):
         tp = getattr(self.clctx, "tilePixels", None)
         return tp() if tp else self.params.width * self.params.height

@@ -4,7 +4,7 @@
 Runs oracle/_ref/scene_tool (the reference's own OBJ/PLY import, SBVH builder and env-map table code, see
 oracle/ref_shim/scene_tool.cpp) on the reference's assets and writes the scene blobs the tests and bench.py load:
 
-    oracle/_ref/scenes/{teapot,conference,luxball,country_kitchen}.bin  (+ .tex.npz for textured scenes)
+    oracle/_ref/scenes/{teapot,conference,luxball,country_kitchen,egyptcat}.bin  (+ .tex.npz for textured scenes)
     oracle/_ref/scenes/night.env.bin
 
 Blobs are git-ignored (they derive from /root/reference/assets) but are NOT gpurun-ignored, so they travel to the
@@ -27,6 +27,7 @@ SCENES = {
     "conference": ("obj", "assets/conference/conference.obj"),
     "luxball": ("obj", "assets/luxball/luxball.obj"),
     "country_kitchen": ("obj", "assets/country_kitchen/Country-Kitchen.obj"),
+    "egyptcat": ("obj", "assets/egyptcat/egyptcat.obj"),  # first scene of the reference's own benchmark protocol (tracer.cpp:384-389)
 }
 ENVMAPS = {"night": "assets/env_maps/night.hdr"}
 

@@ -179,3 +179,29 @@ def test_env_tables_reproduce_reference_builder_bit_for_bit():
     ref = fx.EnvMapData.load_blob(p)
     mine = fx.EnvMapData.from_rgb(ref.rgb)
     assert np.array_equal(mine.pdf, ref.pdf) and np.array_equal(mine.prob, ref.prob) and np.array_equal(mine.alias, ref.alias)
+
+
+@pytest.mark.skipif(not port_available(), reason="oracle/liboracle.so not built")
+@pytest.mark.parametrize("wavefront", [True, False])
+def test_benchmark_protocol_replays_the_reference_loop_and_csv(wavefront):
+    """Tracer.runBenchmarkScene = one scene of Tracer::runBenchmark (src/tracer.cpp:372-383, 416-503), here driven on the CPU
+    oracle with a fake clock: the CSV rows have the reference's seven columns (what plot_benchmarks.py parses), the logged
+    intervals add up to the totals, both integrators run, and the wavefront start-up without a prologue works (every path is
+    found at length 0 by the first logic pass and regenerated)."""
+    from oracle.oracle_host import PortContext
+    scene = make_room_scene(materials="diffuse")
+    W, H, N = 24, 16, 24 * 16
+    params = room_params(scene, W, H, max_bounces=2)
+    ctx = PortContext(N)
+    ctx.uploadSceneData(scene)
+    ctx.setupPixelStorage(W, H)
+    ticks = iter(np.arange(0.0, 100.0, 0.2))
+    tr = fx.Tracer(ctx, params)
+    rows, summary = tr.runBenchmarkScene("assets/room", render_len=2.0, use_wavefront=wavefront, log_every=0.5, clock=lambda: float(next(ticks)))
+    assert len(rows) >= 2 and all(len(r.split(";")) == 7 and r.startswith("assets/room;") for r in rows)
+    vals = np.array([[float(x) for x in r.split(";")[1:]] for r in rows])
+    assert np.allclose(vals[:, 4], vals[:, 1] + vals[:, 2] + vals[:, 3])  # total = primary + extension + shadow
+    assert summary["iterations"] >= 5 and summary["primary"] > 0 and summary["extension"] > 0 and summary["shadow"] > 0 and summary["samples"] > 0
+    assert abs(summary["total"] - (summary["primary"] + summary["extension"] + summary["shadow"])) < 1e-9
+    pix = ctx.readPixels()
+    assert pix[:, 3].sum() > 0 and np.isfinite(pix).all()
