@@ -161,6 +161,8 @@ struct flx_ctx
     uint32_t *mkScratch = nullptr;  // MK_X_SLOTS x numTasks
     uint32_t *mkRayQueue = nullptr; // 2 x numTasks candidate shadow rays
     uint32_t *mkRayCount = nullptr;
+    uint32_t *mkTypeQueues = nullptr; // MK_NUM_LISTS x numTasks: vertices to shade, by BSDF type
+    uint32_t *mkTypeCounts = nullptr;
 
     // timing
     cudaEvent_t evStart = nullptr, evStop = nullptr;
@@ -728,6 +730,8 @@ static int ensureMk(flx_ctx *ctx)
     CU(cudaMalloc(&ctx->mkScratch, (size_t)ctx->numTasks * MK_X_SLOTS * sizeof(uint32_t)));
     CU(cudaMalloc(&ctx->mkRayQueue, (size_t)ctx->numTasks * 2 * sizeof(uint32_t)));
     CU(cudaMalloc(&ctx->mkRayCount, sizeof(uint32_t)));
+    CU(cudaMalloc(&ctx->mkTypeQueues, (size_t)ctx->numTasks * MK_NUM_LISTS * sizeof(uint32_t)));
+    CU(cudaMalloc(&ctx->mkTypeCounts, MK_NUM_LISTS * sizeof(uint32_t)));
     CU(cudaMemsetAsync(ctx->mkScratch, 0, (size_t)ctx->numTasks * MK_X_SLOTS * sizeof(uint32_t), ctx->stream));
     CU(cudaMemsetAsync(ctx->mkRayCount, 0, sizeof(uint32_t), ctx->stream));
     return 0;
@@ -740,6 +744,8 @@ static MkView makeMk(const flx_ctx *c)
     m.scratch.n = c->numTasks;
     m.rayQueue = c->mkRayQueue;
     m.rayCount = c->mkRayCount;
+    m.typeQueues = c->mkTypeQueues;
+    m.typeCounts = c->mkTypeCounts;
     m.limit = std::min(c->tilePixels, c->numTasks); // min(width * height, numTasks), e.g. mk_raygen.cl:9
     m.stats = c->stats;
     return m;
@@ -889,6 +895,8 @@ void flx_destroy(flx_ctx *c)
     freeDev(c->mkScratch);
     freeDev(c->mkRayQueue);
     freeDev(c->mkRayCount);
+    freeDev(c->mkTypeQueues);
+    freeDev(c->mkTypeCounts);
     if (c->evStart)
         cudaEventDestroy(c->evStart);
     if (c->evStop)
@@ -1575,16 +1583,23 @@ int flx_enqueue_mk_sample_bsdf(flx_ctx *ctx)
     const SceneView sc = makeScene(ctx);
     Timed tm(ctx, FLX_K_MK_SAMPLE_BSDF);
     const bool nee = ctx->params.sampleExpl && (ctx->params.useEnvMap || ctx->params.useAreaLight);
-    if (nee)
-    {
-        CU(cudaMemsetAsync(ctx->mkRayCount, 0, sizeof(uint32_t), ctx->stream));
-        k_mk_nee_prepare<<<mkGrid(mk.limit), FLX_BLOCK, 0, ctx->stream>>>(fr, ctx->params, sc, mk);
-        if ((rc = launchCheck(ctx, "k_mk_nee_prepare")) || (rc = launchMkTrace<true>(ctx, mk)))
-            return rc;
-    }
-    else // no light samples: the shading kernel continues from the stored seed
-        k_mk_copy_seed<<<mkGrid(mk.limit), FLX_BLOCK, 0, ctx->stream>>>(fr, mk);
-    k_mk_shade<<<mkGrid(mk.limit), FLX_BLOCK, 0, ctx->stream>>>(fr, ctx->params, sc, mk);
+    CU(cudaMemsetAsync(ctx->mkRayCount, 0, sizeof(uint32_t), ctx->stream));
+    CU(cudaMemsetAsync(ctx->mkTypeCounts, 0, MK_NUM_LISTS * sizeof(uint32_t), ctx->stream));
+    k_mk_nee_prepare<<<mkGrid(mk.limit), FLX_BLOCK, 0, ctx->stream>>>(fr, ctx->params, sc, mk); // light samples (if any) + shading lists
+    if ((rc = launchCheck(ctx, "k_mk_nee_prepare")))
+        return rc;
+    if (nee && (rc = launchMkTrace<true>(ctx, mk)))
+        return rc;
+    // one shading launch per BSDF type, each over its own list (a warp sees one BSDF)
+    const unsigned grid = streamingGrid(mk.limit);
+    constexpr int ALL = FLX_BXDF_DIFFUSE | FLX_BXDF_GLOSSY | FLX_BXDF_GGX_ROUGH_REFLECTION | FLX_BXDF_IDEAL_REFLECTION | FLX_BXDF_GGX_ROUGH_DIELECTRIC |
+                        FLX_BXDF_IDEAL_DIELECTRIC | FLX_BXDF_EMISSIVE;
+    k_mk_shade<FLX_BXDF_DIFFUSE><<<grid, FLX_BLOCK, 0, ctx->stream>>>(fr, ctx->params, sc, mk, MK_L_DIFFUSE);
+    k_mk_shade<FLX_BXDF_GLOSSY><<<grid, FLX_BLOCK, 0, ctx->stream>>>(fr, ctx->params, sc, mk, MK_L_GLOSSY);
+    k_mk_shade<FLX_BXDF_GGX_ROUGH_REFLECTION><<<grid, FLX_BLOCK, 0, ctx->stream>>>(fr, ctx->params, sc, mk, MK_L_GGX_REFL);
+    k_mk_shade<FLX_BXDF_GGX_ROUGH_DIELECTRIC><<<grid, FLX_BLOCK, 0, ctx->stream>>>(fr, ctx->params, sc, mk, MK_L_GGX_REFR);
+    k_mk_shade<FLX_BXDF_IDEAL_REFLECTION | FLX_BXDF_IDEAL_DIELECTRIC><<<grid, FLX_BLOCK, 0, ctx->stream>>>(fr, ctx->params, sc, mk, MK_L_DELTA);
+    k_mk_shade<ALL><<<grid, FLX_BLOCK, 0, ctx->stream>>>(fr, ctx->params, sc, mk, MK_L_OTHER);
     return launchCheck(ctx, "k_mk_shade");
 }
 

@@ -6,7 +6,7 @@
 //   k_mk_reset          (reference: src/mk_reset.cl:4-43)
 //   k_mk_raygen         (reference: src/mk_raygen.cl:5-63)
 //   nextVertex          (reference: src/mk_next_vertex.cl:7-123)  = k_trace_persistent<closest, TRACE_MK_NEXT> + k_mk_next_vertex_logic
-//   sampleBsdf          (reference: src/mk_sample_bsdf.cl:11-197) = k_mk_nee_prepare + k_trace_persistent<any, TRACE_MK_NEE> + k_mk_shade
+//   sampleBsdf          (reference: src/mk_sample_bsdf.cl:11-197) = k_mk_nee_prepare + k_trace_persistent<any, TRACE_MK_NEE> + k_mk_shade<type> per BSDF type
 //   k_mk_splat          (reference: src/mk_splat.cl:5-41)
 //   k_mk_splat_preview  (reference: src/mk_splat_preview.cl:5-25)
 //
@@ -35,11 +35,26 @@ enum {
     MK_X_SLOTS = 14
 };
 
+// Shading lists: like the wavefront integrator's material queues (wf_logic.cl:322-372), so that a warp of the shading kernel sees
+// one BSDF.  The reference's sampleBsdf evaluates whatever material each path hit in one kernel; the result per path is the same.
+enum { MK_L_DIFFUSE = 0, MK_L_GLOSSY, MK_L_GGX_REFL, MK_L_GGX_REFR, MK_L_DELTA, MK_L_OTHER, MK_NUM_LISTS };
+FLX_DEV int mk_list_of(int type)
+{
+    if (type == FLX_BXDF_DIFFUSE) return MK_L_DIFFUSE;
+    if (type == FLX_BXDF_GLOSSY) return MK_L_GLOSSY;
+    if (type == FLX_BXDF_GGX_ROUGH_REFLECTION) return MK_L_GGX_REFL;
+    if (type == FLX_BXDF_GGX_ROUGH_DIELECTRIC) return MK_L_GGX_REFR;
+    if (type == FLX_BXDF_IDEAL_REFLECTION || type == FLX_BXDF_IDEAL_DIELECTRIC) return MK_L_DELTA;
+    return MK_L_OTHER; // emissive or unknown: the all-lobes kernel (bxdf.cl's switch falls through to black / white)
+}
+
 struct MkView
 {
     Tasks scratch;
     uint32_t *rayQueue; // entries 2 * path + which
     uint32_t *rayCount;
+    uint32_t *typeQueues; // MK_NUM_LISTS lists of numTasks path indices: the vertices to shade, by BSDF type
+    uint32_t *typeCounts; // MK_NUM_LISTS counts
     uint32_t limit;     // min(width * height, numTasks): the paths the microkernels touch (e.g. mk_raygen.cl:9)
     flx_RenderStats64 *stats;
 };
@@ -223,10 +238,12 @@ __global__ void __launch_bounds__(FLX_BLOCK) k_mk_nee_prepare(const __grid_const
     const bool live = gid < mk.limit && t.u(FLX_S_PHASE, gid) == (uint32_t)MK_SAMPLE_BSDF;
     uint32_t shadowRays = 0;
     bool push0 = false, push1 = false;
+    int list = -1;
     if (live)
     {
         uint32_t seed = t.u(FLX_S_SEED, gid);
         const MkVertex v = mk_load_vertex(t, gid, sc);
+        list = mk_list_of(v.mat.type);
         if (prm.sampleExpl && !v.singular)
         {
             x.setv(MK_X_ORIG, gid, v.orig);
@@ -281,27 +298,36 @@ __global__ void __launch_bounds__(FLX_BLOCK) k_mk_nee_prepare(const __grid_const
         mk.rayQueue[slot++] = 2u * gid;
     if (push1)
         mk.rayQueue[slot] = 2u * gid + 1u;
+    // ... and every vertex to the shading list of its BSDF type: one atomic per warp per type present
+#pragma unroll
+    for (int k = 0; k < MK_NUM_LISTS; k++)
+    {
+        const unsigned m = __ballot_sync(0xffffffffu, list == k);
+        if (m == 0u)
+            continue;
+        uint32_t lbase = 0;
+        const int leader = __ffs(m) - 1;
+        if (lane == leader)
+            lbase = atomicAdd(mk.typeCounts + k, (uint32_t)__popc(m));
+        lbase = __shfl_sync(0xffffffffu, lbase, leader);
+        if (list == k)
+            mk.typeQueues[(size_t)k * fr.numTasks + lbase + __popc(m & ((1u << lane) - 1u))] = gid;
+    }
     mk_stat_add(reinterpret_cast<unsigned long long *>(&mk.stats->shadowRays), shadowRays, s_part);
 }
 
-// explicit sampling off (or no light at all): nothing to prepare, the shading kernel just continues from the stored seed
-__global__ void __launch_bounds__(FLX_BLOCK) k_mk_copy_seed(const __grid_constant__ Frame fr, const MkView mk)
-{
-    const uint32_t gid = blockIdx.x * FLX_BLOCK + threadIdx.x;
-    if (gid < mk.limit)
-        mk.scratch.setu(MK_X_SEED, gid, fr.tasks.u(FLX_S_SEED, gid));
-}
-
 // ------------------------------------------------------------------------------------------------ sampleBsdf, part 2: shading
-__global__ void __launch_bounds__(FLX_BLOCK) k_mk_shade(const __grid_constant__ Frame fr, const __grid_constant__ flx_RenderParams prm, const SceneView sc, const MkView mk)
+template <int ALL> // the lobes compiled in: one shading list's BSDF type(s), like the wavefront material kernels
+__global__ void __launch_bounds__(FLX_BLOCK) k_mk_shade(const __grid_constant__ Frame fr, const __grid_constant__ flx_RenderParams prm, const SceneView sc, const MkView mk,
+                                                        const int list)
 {
-    constexpr int ALL = FLX_BXDF_DIFFUSE | FLX_BXDF_GLOSSY | FLX_BXDF_GGX_ROUGH_REFLECTION | FLX_BXDF_IDEAL_REFLECTION | FLX_BXDF_GGX_ROUGH_DIELECTRIC |
-                        FLX_BXDF_IDEAL_DIELECTRIC | FLX_BXDF_EMISSIVE;
-    const uint32_t gid = blockIdx.x * FLX_BLOCK + threadIdx.x;
     const Tasks &t = fr.tasks;
     const Tasks &x = mk.scratch;
-    if (gid >= mk.limit || t.u(FLX_S_PHASE, gid) != (uint32_t)MK_SAMPLE_BSDF)
-        return;
+    const uint32_t count = mk.typeCounts[list];
+    const uint32_t *queue = mk.typeQueues + (size_t)list * fr.numTasks;
+    for (uint32_t idx = blockIdx.x * FLX_BLOCK + threadIdx.x; idx < count; idx += gridDim.x * FLX_BLOCK)
+    {
+    const uint32_t gid = queue[idx];
     uint32_t seed = x.u(MK_X_SEED, gid);
     const MkVertex v = mk_load_vertex(t, gid, sc);
     const V3 T = t.v(FLX_S_T, gid);
@@ -375,6 +401,7 @@ __global__ void __launch_bounds__(FLX_BLOCK) k_mk_shade(const __grid_constant__ 
     t.setu(FLX_S_SEED, gid, seed);
     t.setu(FLX_S_LAST_SPECULAR, gid, v.singular ? 1u : 0u);
     t.setu(FLX_S_PHASE, gid, terminate ? (uint32_t)MK_SPLAT_SAMPLE : (uint32_t)MK_RT_NEXT_VERTEX);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ splat
