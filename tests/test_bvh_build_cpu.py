@@ -104,3 +104,28 @@ def test_rendering_with_the_built_tree_finds_the_same_hits(quality):
     assert np.array_equal(images[0][:, 3], images[1][:, 3]) or abs(images[0][:, 3].sum() - images[1][:, 3].sum()) < 0.01 * images[0][:, 3].sum()
     ma, mb = images[0][:, :3].sum() / images[0][:, 3].sum(), images[1][:, :3].sum() / images[1][:, 3].sum()
     assert abs(ma - mb) < 0.02 * abs(ma)
+
+
+@pytest.mark.parametrize("quality", ["fast", "ploc"])
+def test_builders_on_random_soups(quality):
+    """Randomised inputs: uniform, tightly clustered (many triangles per Morton cell), long slivers spanning the scene, exact
+    duplicates and sizes around powers of two -- the output contract must hold for all of them."""
+    rng = np.random.default_rng(77)
+    for trial in range(12):
+        n = int(rng.choice([3, 17, 64, 65, 255, 256, 257, 1000, 2049]))
+        kind = trial % 4
+        if kind == 0:
+            pts = rng.uniform(-1, 1, (n, 3, 3))
+        elif kind == 1:
+            pts = rng.normal(0, 1e-4, (n, 3, 3)) + rng.choice([-1.0, 0.0, 1.0], (n, 1, 3))
+        elif kind == 2:
+            pts = rng.uniform(-1, 1, (n, 1, 3)) + rng.normal(0, 0.01, (n, 3, 3))
+            pts[::7, 1] = pts[::7, 0] + rng.uniform(-2, 2, (len(pts[::7]), 3))  # slivers
+        else:
+            base = rng.uniform(-1, 1, (max(n // 4, 1), 3, 3))
+            pts = base[rng.integers(0, len(base), n)]  # exact duplicates
+        tris = tri_soup(pts.astype(np.float32))
+        for max_leaf in (1, 8):
+            nodes, indices = BUILDERS[quality](tris, max_leaf)
+            depth, leaves, sah = validate_bvh(nodes, indices, tris, max_leaf)
+            assert depth <= 62

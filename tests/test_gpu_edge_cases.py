@@ -175,3 +175,51 @@ def test_full_size_is_deterministic_and_matches_fused_loop():
         compare_pixels(a.readPixels(), b.readPixels(), "per-stage vs fused at full size", rtol=1e-5)
         st = b.getStats()
         assert (st.extensionRays, st.shadowRays, st.primaryRays) == (ta.stats["extensionRays"], ta.stats["shadowRays"], ta.stats["primaryRays"])
+
+
+@pytest.mark.parametrize("separate", [False, True])
+def test_every_stage_boundary_is_observable_despite_deferred_fusion(separate):
+    """The per-stage ABI defers logic (+ raygen) so that logic, raygen, materials arriving back to back run as one fused kernel
+    (flx_ctx::pendingStages).  An observer must not be able to tell: reading the path state after ANY single stage call has to
+    show exactly what the reference's kernel sequence has produced up to that call.  Stage by stage against the oracle, with a
+    read-back after every call (which forces the pending stages out as the separate kernels), interleaved with iterations that
+    are left to fuse."""
+    from fluctus_b200 import QueueCounters
+    from parity_util import compare_counters, compare_tasks, setup_context
+    from test_gpu_parity import oracle_ctx
+    scene = make_room_scene(materials="mixed", textured=True, n_blobs=8)
+    W, H, N = 64, 48, 4096
+    params = room_params(scene, W, H, max_bounces=4, separate_queues=separate)
+    with CLContext(N) as gpu:
+        cpu = oracle_ctx(N)
+        tg, tc = setup_context(gpu, scene, params), setup_context(cpu, scene, params)
+        tg.start()
+        tc.start()
+        stages = ["enqueueWfLogicKernel", "enqueueWfRaygenKernel", "enqueueWfMaterialKernels", "enqueueWfExtRayKernel", "enqueueWfShadowRayKernel"]
+        for it in range(6):
+            if it % 2 == 1:  # an iteration nobody looks into: logic + raygen + materials fuse
+                cg, cc = tg.iterate(), tc.iterate()
+                compare_counters(cg, cc, "fused iteration %d" % it)
+                compare_tasks(gpu.readTasks(), cpu.readTasks(), "after fused iteration %d" % it)
+                continue
+            for stage in stages:
+                for c in (gpu, cpu):
+                    if stage == "enqueueWfLogicKernel":
+                        c.enqueueWfLogicKernel(params, False)
+                    else:
+                        getattr(c, stage)(params)
+                if it % 4 == 2 and stage == "enqueueWfLogicKernel":
+                    continue  # first look after raygen: logic AND raygen are pending and have to come out as two kernels
+                compare_tasks(gpu.readTasks(), cpu.readTasks(), "iteration %d after %s" % (it, stage))
+                compare_counters(gpu.readCounters(), cpu.readCounters(), "iteration %d after %s" % (it, stage))
+            cnts = []
+            for c, tr in ((gpu, tg), (cpu, tc)):
+                cnt = c.readCounters()
+                c.enqueueClearWfQueues()
+                c.enqueuePostprocessKernel(params)
+                c.finishQueue()
+                c.updatePixelIndex(W * H, cnt.raygenQueue)
+                cnts.append(cnt)
+            compare_counters(cnts[0], cnts[1], "iteration %d" % it)
+            from parity_util import compare_pixels
+            compare_pixels(gpu.readPixels(), cpu.readPixels(), "iteration %d" % it, rtol=1e-5)
