@@ -68,6 +68,8 @@ _SIGNATURES = {
     "flx_device_bytes": (C.c_size_t, [_P]),
     "flx_io_last_error": (C.c_char_p, []),
     "flx_save_image": (C.c_int, [_P, C.c_char_p]),
+    "flx_checkpoint_save": (C.c_int, [_P, C.c_char_p]),
+    "flx_checkpoint_load": (C.c_int, [_P, C.c_char_p]),
     "flx_write_image": (C.c_int, [C.c_char_p, _P, C.c_uint32, C.c_uint32]),
     "flx_scene_load": (C.c_int, [C.c_char_p, C.POINTER(_P)]),
     "flx_scene_free": (None, [_P]),

@@ -240,6 +240,13 @@ class CLContext:
         post-processed preview as 8-bit PNG."""
         self._check(self._lib.flx_save_image(self._h, str(filename).encode()), "saveImage")
 
+    def saveCheckpoint(self, path):
+        """Everything an interrupted render needs to continue (path state, queues, counters, pixel index, statistics, accumulator)."""
+        self._check(self._lib.flx_checkpoint_save(self._h, str(path).encode()), "saveCheckpoint")
+
+    def loadCheckpoint(self, path):
+        self._check(self._lib.flx_checkpoint_load(self._h, str(path).encode()), "loadCheckpoint")
+
     def readTraversalLayout(self):
         """(tnodes (n, 16) float32, ttris (m, 16) float32, rootRef): the uploaded hierarchy in the traversal layout (diagnostic)."""
         nn, nt, root = C.c_uint32(), C.c_uint32(), C.c_int32()

@@ -2163,6 +2163,104 @@ int flx_write_counters(flx_ctx *ctx, const flx_QueueCounters *in)
     return 0;
 }
 
+// ---- checkpoint / resume (new; SURVEY 5: the reference can only restart a render from scratch -- its caches hold the
+// hierarchy, the camera state and compiled kernels, never the accumulator).  One file holds everything an interrupted
+// wavefront or microkernel render needs to continue bit-identically: path state, queues, counters, pixel index, statistics
+// and the accumulator.  Scene, environment map and params are NOT in it: upload them as usual, then load.
+namespace
+{
+struct CheckpointHeader
+{
+    char magic[8]; // "FLXCKPT1"
+    uint32_t numTasks, width, height, tilePixels, part, nParts, stripeRows, hostPixelIdx;
+};
+} // namespace
+
+int flx_checkpoint_save(flx_ctx *ctx, const char *path)
+{
+    int rc = checkReady(ctx, false, true);
+    if (rc)
+        return rc;
+    REQUIRE(path != nullptr, "flx_checkpoint_save: null path");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CheckpointHeader h;
+    memset(&h, 0, sizeof h);
+    memcpy(h.magic, "FLXCKPT1", 8);
+    h.numTasks = ctx->numTasks; h.width = ctx->width; h.height = ctx->height; h.tilePixels = ctx->tilePixels;
+    h.part = ctx->part; h.nParts = ctx->nParts; h.stripeRows = ctx->stripeRows;
+    CU(cudaMemcpy(&h.hostPixelIdx, ctx->currPixelIdx, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    FILE *fp = std::fopen(path, "wb");
+    if (!fp)
+        return fail(ctx, FLX_E_INVALID, "flx_checkpoint_save: cannot create %s", path);
+    bool ok = std::fwrite(&h, sizeof h, 1, fp) == 1;
+    std::vector<unsigned char> buf;
+    auto dump = [&](const void *dev, size_t bytes) {
+        buf.resize(bytes);
+        if (cudaMemcpy(buf.data(), dev, bytes, cudaMemcpyDeviceToHost) != cudaSuccess)
+            ok = false;
+        ok = ok && std::fwrite(buf.data(), 1, bytes, fp) == bytes;
+    };
+    dump(ctx->tasks, (size_t)ctx->numTasks * FLX_NUM_SLOTS * 4);
+    for (int q = 0; q < 8; q++)
+        dump(ctx->queues[q], (size_t)ctx->numTasks * 4);
+    dump(ctx->counters, sizeof(flx_QueueCounters));
+    dump(ctx->stats, sizeof(flx_RenderStats64));
+    dump(ctx->pixels, (size_t)ctx->tilePixels * 16);
+    ok = (std::fclose(fp) == 0) && ok;
+    if (!ok)
+        return fail(ctx, FLX_E_INVALID, "flx_checkpoint_save: write error on %s", path);
+    return 0;
+}
+
+int flx_checkpoint_load(flx_ctx *ctx, const char *path)
+{
+    int rc = checkReady(ctx, false, true);
+    if (rc)
+        return rc;
+    REQUIRE(path != nullptr, "flx_checkpoint_load: null path");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    FILE *fp = std::fopen(path, "rb");
+    if (!fp)
+        return fail(ctx, FLX_E_INVALID, "flx_checkpoint_load: cannot open %s", path);
+    CheckpointHeader h;
+    if (std::fread(&h, sizeof h, 1, fp) != 1 || memcmp(h.magic, "FLXCKPT1", 8) != 0)
+    {
+        std::fclose(fp);
+        return fail(ctx, FLX_E_INVALID, "flx_checkpoint_load: %s is not a checkpoint", path);
+    }
+    if (h.numTasks != ctx->numTasks || h.width != ctx->width || h.height != ctx->height || h.tilePixels != ctx->tilePixels || h.part != ctx->part ||
+        h.nParts != ctx->nParts || h.stripeRows != ctx->stripeRows)
+    {
+        std::fclose(fp);
+        return fail(ctx, FLX_E_INVALID, "flx_checkpoint_load: checkpoint is for %u paths, %ux%u, tile %u/%u; this context has %u paths, %ux%u, tile %u/%u", h.numTasks,
+                    h.width, h.height, h.part, h.nParts, ctx->numTasks, ctx->width, ctx->height, ctx->part, ctx->nParts);
+    }
+    bool ok = true;
+    std::vector<unsigned char> buf;
+    auto restore = [&](void *dev, size_t bytes) {
+        buf.resize(bytes);
+        ok = ok && std::fread(buf.data(), 1, bytes, fp) == bytes;
+        if (ok && cudaMemcpy(dev, buf.data(), bytes, cudaMemcpyHostToDevice) != cudaSuccess)
+            ok = false;
+    };
+    restore(ctx->tasks, (size_t)ctx->numTasks * FLX_NUM_SLOTS * 4);
+    for (int q = 0; q < 8; q++)
+        restore(ctx->queues[q], (size_t)ctx->numTasks * 4);
+    restore(ctx->counters, sizeof(flx_QueueCounters));
+    restore(ctx->stats, sizeof(flx_RenderStats64));
+    restore(ctx->pixels, (size_t)ctx->tilePixels * 16);
+    std::fclose(fp);
+    if (!ok)
+        return fail(ctx, FLX_E_INVALID, "flx_checkpoint_load: %s is truncated", path);
+    ctx->hostPixelIdx = h.hostPixelIdx;
+    ctx->pixelIdxAdvancedOnDevice = false;
+    CU(cudaMemcpy(ctx->currPixelIdx, &h.hostPixelIdx, sizeof(uint32_t), cudaMemcpyHostToDevice));
+    markPixelsWritten(ctx);
+    return 0;
+}
+
 // ---- NCCL gather of the per-tile radiance buffers: the only collective of the path
 int flx_comm_unique_id(void *out128)
 {

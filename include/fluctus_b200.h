@@ -228,6 +228,13 @@ int flx_read_pixels(flx_ctx *ctx, float *rgba, size_t n_pixels);
 int flx_save_image(flx_ctx *ctx, const char *filename);
 int flx_write_image(const char *path, const float *rgba, uint32_t width, uint32_t height);
 
+/* Checkpoint / resume (new).  The reference can only restart a render: its caches hold the hierarchy, camera state and kernel
+ * binaries, never the accumulator.  One file = path state, queues, counters, pixel index, statistics, accumulator of
+ * this context; an interrupted wavefront or microkernel render continues from it with a bit-identical path state.  Scene,
+ * environment map, image size, tile and params are not stored: set them up as usual (same num_tasks), then load. */
+int flx_checkpoint_save(flx_ctx *ctx, const char *path);
+int flx_checkpoint_load(flx_ctx *ctx, const char *path);
+
 /* Test/diagnostic access to the path state and queues (no reference equivalent; the reference's debugger did this). */
 int flx_read_tasks(flx_ctx *ctx, uint32_t *slots_out /* 64*num_tasks */);
 /* the hierarchy as repacked for traversal (16 floats per inner node / per leaf reference); NULL arrays: counts only */

@@ -91,6 +91,9 @@ class CLContext
 
     void saveImage(const std::string &filename, const RenderParams &) { verify(flx_save_image(ctx, filename.c_str()), "saveImage"); } // clcontext.hpp:78
 
+    void saveCheckpoint(const std::string &path) { verify(flx_checkpoint_save(ctx, path.c_str()), "saveCheckpoint"); }   // new: resumable renders
+    void loadCheckpoint(const std::string &path) { verify(flx_checkpoint_load(ctx, path.c_str()), "loadCheckpoint"); }
+
     // ---- microkernel integrator (clcontext.hpp:35-40; the one Tracer::renderSingle uses, tracer.cpp:95-169)
     void enqueueResetKernel(const RenderParams &) { verify(flx_enqueue_mk_reset(ctx), "enqueueResetKernel"); }
     void enqueueRayGenKernel(const RenderParams &) { verify(flx_enqueue_mk_raygen(ctx), "enqueueRayGenKernel"); }

@@ -223,3 +223,42 @@ def test_every_stage_boundary_is_observable_despite_deferred_fusion(separate):
             compare_counters(cnts[0], cnts[1], "iteration %d" % it)
             from parity_util import compare_pixels
             compare_pixels(gpu.readPixels(), cpu.readPixels(), "iteration %d" % it, rtol=1e-5)
+
+
+def test_checkpoint_resume_continues_bit_identically(tmp_path):
+    """flx_checkpoint_save / _load: a render interrupted after 7 iterations and resumed in a NEW context ends with the same path
+    state, queues, counters and statistics as the uninterrupted one (radiance up to the order of float atomics); a checkpoint
+    of another shape is refused."""
+    from parity_util import compare_pixels, compare_tasks, setup_context
+    scene = make_room_scene(materials="mixed", textured=True, n_blobs=8)
+    W, H, N = 64, 48, 4096
+    params = room_params(scene, W, H, max_bounces=4, separate_queues=True)
+    ck = tmp_path / "render.ckpt"
+    with CLContext(N) as a:
+        ta = setup_context(a, scene, params)
+        ta.start()
+        for _ in range(7):
+            ta.iterate()
+        a.saveCheckpoint(ck)
+        a.render(3)
+        for _ in range(4):
+            ta.iterate()
+        want_tasks, want_pix, want_stats = a.readTasks(), a.readPixels(), a.getStats()
+        want_cnt = a.readCounters()
+    with CLContext(N) as b:
+        tb = setup_context(b, scene, params)
+        b.loadCheckpoint(ck)
+        b.render(3)
+        for _ in range(4):
+            tb.iterate()
+        compare_tasks(b.readTasks(), want_tasks, "resumed render")
+        compare_pixels(b.readPixels(), want_pix, "resumed render", rtol=1e-5)
+        got = b.getStats()
+        assert (got.extensionRays, got.shadowRays, got.primaryRays, got.iterations) == (want_stats.extensionRays, want_stats.shadowRays, want_stats.primaryRays, want_stats.iterations)
+        assert b.readCounters().as_dict() == want_cnt.as_dict()
+    with CLContext(N // 2) as c:
+        setup_context(c, scene, params)
+        with pytest.raises(FluctusError, match="checkpoint is for"):
+            c.loadCheckpoint(ck)
+        with pytest.raises(FluctusError):
+            c.loadCheckpoint(tmp_path / "missing.ckpt")
