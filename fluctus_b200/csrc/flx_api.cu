@@ -115,6 +115,8 @@ struct flx_ctx
     float4 *tnodes = nullptr, *ttris = nullptr;
     int rootRef = 0;
     uint32_t nTris = 0, nTNodes = 0, nTTris = 0, treeletNodes = 0;
+    uint32_t materialTypes = 0;  // OR of the uploaded materials' type bits (Scene::getMaterialTypes, src/scene.cpp:25,299): kernels for
+    bool otherTypes = false;     // BSDF types the scene does not contain are not launched; otherTypes: a type none of the lists knows
     bool sceneReady = false;
     size_t sceneBytes = 0;
 
@@ -992,6 +994,16 @@ int flx_upload_scene(flx_ctx *ctx, const flx_Triangle *tris, uint32_t n_tris, co
         return rc;
     if ((rc = uploadArray(ctx, ctx->materials, materials, n_materials)))
         return rc;
+    ctx->materialTypes = 0;
+    ctx->otherTypes = false;
+    for (uint32_t i = 0; i < n_materials; i++)
+    {
+        const int ty = materials[i].type;
+        ctx->materialTypes |= (uint32_t)ty;
+        if (ty != FLX_BXDF_DIFFUSE && ty != FLX_BXDF_GLOSSY && ty != FLX_BXDF_GGX_ROUGH_REFLECTION && ty != FLX_BXDF_GGX_ROUGH_DIELECTRIC && ty != FLX_BXDF_IDEAL_REFLECTION &&
+            ty != FLX_BXDF_IDEAL_DIELECTRIC)
+            ctx->otherTypes = true;
+    }
     std::vector<float4> kdGamma(n_materials);
     for (uint32_t i = 0; i < n_materials; i++) // matGetAlbedo of an untextured material (utils.cl:136-141), hoisted out of the kernels
         kdGamma[i] = make_float4(flx_powf(materials[i].Kd.x, 2.2f), flx_powf(materials[i].Kd.y, 2.2f), flx_powf(materials[i].Kd.z, 2.2f), 0.0f);
@@ -1517,11 +1529,18 @@ static int launchMaterials(flx_ctx *ctx)
     Timed tm(ctx, FLX_K_MATERIALS);
     if (ctx->params.wfSeparateQueues) // clcontext.cpp:798-812
     {
-        k_material<FLX_BXDF_DIFFUSE><<<grid, FLX_BLOCK, 0, ctx->stream>>>(fr, sc, Q_DIFFUSE);
-        k_material<FLX_BXDF_GLOSSY><<<grid, FLX_BLOCK, 0, ctx->stream>>>(fr, sc, Q_GLOSSY);
-        k_material<FLX_BXDF_GGX_ROUGH_REFLECTION><<<grid, FLX_BLOCK, 0, ctx->stream>>>(fr, sc, Q_GGXREFL);
-        k_material<FLX_BXDF_GGX_ROUGH_DIELECTRIC><<<grid, FLX_BLOCK, 0, ctx->stream>>>(fr, sc, Q_GGXREFR);
-        k_material<FLX_BXDF_IDEAL_REFLECTION | FLX_BXDF_IDEAL_DIELECTRIC><<<grid, FLX_BLOCK, 0, ctx->stream>>>(fr, sc, Q_DELTA);
+        // a queue whose BSDF type no uploaded material has stays empty: its kernel is not launched
+        const uint32_t have = ctx->materialTypes;
+        if (have & FLX_BXDF_DIFFUSE)
+            k_material<FLX_BXDF_DIFFUSE><<<grid, FLX_BLOCK, 0, ctx->stream>>>(fr, sc, Q_DIFFUSE);
+        if (have & FLX_BXDF_GLOSSY)
+            k_material<FLX_BXDF_GLOSSY><<<grid, FLX_BLOCK, 0, ctx->stream>>>(fr, sc, Q_GLOSSY);
+        if (have & FLX_BXDF_GGX_ROUGH_REFLECTION)
+            k_material<FLX_BXDF_GGX_ROUGH_REFLECTION><<<grid, FLX_BLOCK, 0, ctx->stream>>>(fr, sc, Q_GGXREFL);
+        if (have & FLX_BXDF_GGX_ROUGH_DIELECTRIC)
+            k_material<FLX_BXDF_GGX_ROUGH_DIELECTRIC><<<grid, FLX_BLOCK, 0, ctx->stream>>>(fr, sc, Q_GGXREFR);
+        if (have & (FLX_BXDF_IDEAL_REFLECTION | FLX_BXDF_IDEAL_DIELECTRIC))
+            k_material<FLX_BXDF_IDEAL_REFLECTION | FLX_BXDF_IDEAL_DIELECTRIC><<<grid, FLX_BLOCK, 0, ctx->stream>>>(fr, sc, Q_DELTA);
     }
     else
     {
@@ -1594,12 +1613,19 @@ int flx_enqueue_mk_sample_bsdf(flx_ctx *ctx)
     const unsigned grid = streamingGrid(mk.limit);
     constexpr int ALL = FLX_BXDF_DIFFUSE | FLX_BXDF_GLOSSY | FLX_BXDF_GGX_ROUGH_REFLECTION | FLX_BXDF_IDEAL_REFLECTION | FLX_BXDF_GGX_ROUGH_DIELECTRIC |
                         FLX_BXDF_IDEAL_DIELECTRIC | FLX_BXDF_EMISSIVE;
-    k_mk_shade<FLX_BXDF_DIFFUSE><<<grid, FLX_BLOCK, 0, ctx->stream>>>(fr, ctx->params, sc, mk, MK_L_DIFFUSE);
-    k_mk_shade<FLX_BXDF_GLOSSY><<<grid, FLX_BLOCK, 0, ctx->stream>>>(fr, ctx->params, sc, mk, MK_L_GLOSSY);
-    k_mk_shade<FLX_BXDF_GGX_ROUGH_REFLECTION><<<grid, FLX_BLOCK, 0, ctx->stream>>>(fr, ctx->params, sc, mk, MK_L_GGX_REFL);
-    k_mk_shade<FLX_BXDF_GGX_ROUGH_DIELECTRIC><<<grid, FLX_BLOCK, 0, ctx->stream>>>(fr, ctx->params, sc, mk, MK_L_GGX_REFR);
-    k_mk_shade<FLX_BXDF_IDEAL_REFLECTION | FLX_BXDF_IDEAL_DIELECTRIC><<<grid, FLX_BLOCK, 0, ctx->stream>>>(fr, ctx->params, sc, mk, MK_L_DELTA);
-    k_mk_shade<ALL><<<grid, FLX_BLOCK, 0, ctx->stream>>>(fr, ctx->params, sc, mk, MK_L_OTHER);
+    const uint32_t have = ctx->materialTypes; // lists of BSDF types the scene does not contain stay empty: not launched
+    if (have & FLX_BXDF_DIFFUSE)
+        k_mk_shade<FLX_BXDF_DIFFUSE><<<grid, FLX_BLOCK, 0, ctx->stream>>>(fr, ctx->params, sc, mk, MK_L_DIFFUSE);
+    if (have & FLX_BXDF_GLOSSY)
+        k_mk_shade<FLX_BXDF_GLOSSY><<<grid, FLX_BLOCK, 0, ctx->stream>>>(fr, ctx->params, sc, mk, MK_L_GLOSSY);
+    if (have & FLX_BXDF_GGX_ROUGH_REFLECTION)
+        k_mk_shade<FLX_BXDF_GGX_ROUGH_REFLECTION><<<grid, FLX_BLOCK, 0, ctx->stream>>>(fr, ctx->params, sc, mk, MK_L_GGX_REFL);
+    if (have & FLX_BXDF_GGX_ROUGH_DIELECTRIC)
+        k_mk_shade<FLX_BXDF_GGX_ROUGH_DIELECTRIC><<<grid, FLX_BLOCK, 0, ctx->stream>>>(fr, ctx->params, sc, mk, MK_L_GGX_REFR);
+    if (have & (FLX_BXDF_IDEAL_REFLECTION | FLX_BXDF_IDEAL_DIELECTRIC))
+        k_mk_shade<FLX_BXDF_IDEAL_REFLECTION | FLX_BXDF_IDEAL_DIELECTRIC><<<grid, FLX_BLOCK, 0, ctx->stream>>>(fr, ctx->params, sc, mk, MK_L_DELTA);
+    if (ctx->otherTypes)
+        k_mk_shade<ALL><<<grid, FLX_BLOCK, 0, ctx->stream>>>(fr, ctx->params, sc, mk, MK_L_OTHER);
     return launchCheck(ctx, "k_mk_shade");
 }
 
