@@ -127,6 +127,9 @@ struct flx_ctx
 
     // image
     float *pixels = nullptr, *denoiserAlbedo = nullptr, *denoiserNormal = nullptr, *preview = nullptr;
+    uint8_t *dirtyPixels = nullptr;  // per pixel: accumulator changed since the display pass last saw it (k_postprocess)
+    bool previewStale = true;        // the whole preview must be recomputed (new image, new exposure / tone-map operator, checkpoint)
+    int dirtyPostprocess = 1;        // 0: recompute every pixel every pass
     uint32_t width = 0, height = 0, tilePixels = 0;
     uint32_t part = 0, nParts = 1, stripeRows = 1;
     float *gatherBuf = nullptr, *fullImage = nullptr; // rank-major gather target and de-interleaved full image (root)
@@ -226,6 +229,7 @@ Frame makeFrame(const flx_ctx *c)
     for (int i = 0; i < 8; i++)
         f.queues[i] = c->queues[i];
     f.pixels = c->pixels;
+    f.dirty = c->dirtyPixels;
     f.denoiserAlbedo = c->denoiserAlbedo;
     f.denoiserNormal = c->denoiserNormal;
     f.currPixelIdx = c->currPixelIdx;
@@ -816,9 +820,15 @@ int flx_create(int device, uint32_t num_tasks, flx_ctx **out)
             return bail((int)e_);                                                                                      \
         }                                                                                                              \
     } while (0)
-    CUB(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    CUB(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
-    CUB(cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking));
+    // The main stream gets the highest priority, the two side streams the lowest: when the shadow-ray kernel (stream2) and the
+    // extension kernel (main) are both ready, the block scheduler places the extension kernel's CTAs first -- it is the longer of
+    // the two, and the shadow kernel then fills the SMs its tail frees.  Without priorities the order is a coin toss (and with
+    // the shadow kernel first the extension kernel's own elapsed time, the roofline's denominator, includes its wait).
+    int prioLow = 0, prioHigh = 0;
+    CUB(cudaDeviceGetStreamPriorityRange(&prioLow, &prioHigh));
+    CUB(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prioHigh));
+    CUB(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prioLow));
+    CUB(cudaStreamCreateWithPriority(&c->stream3, cudaStreamNonBlocking, prioLow));
     CUB(cudaEventCreateWithFlags(&c->evPostFork, cudaEventDisableTiming));
     CUB(cudaEventCreateWithFlags(&c->evPostJoin, cudaEventDisableTiming));
     CUB(cudaEventCreateWithFlags(&c->evPixels, cudaEventDisableTiming));
@@ -922,6 +932,7 @@ void flx_destroy(flx_ctx *c)
     freeDev(c->denoiserAlbedo);
     freeDev(c->denoiserNormal);
     freeDev(c->preview);
+    freeDev(c->dirtyPixels);
     freeDev(c->gatherBuf);
     freeDev(c->fullImage);
     if (c->evFork)
@@ -1275,6 +1286,8 @@ static int allocImage(flx_ctx *ctx)
     freeDev(ctx->denoiserAlbedo);
     freeDev(ctx->denoiserNormal);
     freeDev(ctx->preview);
+    freeDev(ctx->dirtyPixels);
+    ctx->previewStale = true;
     if (ctx->tilePixels == 0)
         return fail(ctx, FLX_E_INVALID, "tile %u of %u owns no rows of a %ux%u image", ctx->part, ctx->nParts, ctx->width, ctx->height);
     const size_t bytes = (size_t)ctx->tilePixels * 4 * sizeof(float);
@@ -1282,6 +1295,8 @@ static int allocImage(flx_ctx *ctx)
     CU(cudaMalloc(&ctx->denoiserAlbedo, bytes));
     CU(cudaMalloc(&ctx->denoiserNormal, bytes));
     CU(cudaMalloc(&ctx->preview, bytes));
+    CU(cudaMalloc(&ctx->dirtyPixels, ctx->tilePixels));
+    CU(cudaMemset(ctx->dirtyPixels, 1, ctx->tilePixels));
     CU(cudaMemset(ctx->preview, 0, bytes));
     CU(cudaMemset(ctx->pixels, 0, bytes));
     CU(cudaMemset(ctx->denoiserAlbedo, 0, bytes));
@@ -1323,6 +1338,8 @@ int flx_update_params(flx_ctx *ctx, const flx_RenderParams *p)
     REQUIRE(p->width > 0 && p->height > 0, "flx_update_params: empty image");
     if (ctx->pixels && (p->width != ctx->width || p->height != ctx->height))
         return fail(ctx, FLX_E_INVALID, "params are %ux%u but pixel storage is %ux%u: call flx_resize first", p->width, p->height, ctx->width, ctx->height);
+    if (!ctx->paramsSet || p->ppParams.exposure != ctx->params.ppParams.exposure || p->ppParams.tmOperator != ctx->params.ppParams.tmOperator)
+        ctx->previewStale = true; // the display pass maps every pixel differently now
     ctx->params = *p;
     ctx->tanHalfFov = flx_tanf(0.5f * p->camera.fov * 3.14159265358979323846f / 180); // toRad, geom.h:22; wf_raygen.cl:50
     ctx->paramsSet = true;
@@ -1682,8 +1699,11 @@ int flx_render_single(flx_ctx *ctx, uint32_t spp)
 static int launchPostprocess(flx_ctx *ctx)
 {
     Timed tm(ctx, FLX_K_POSTPROCESS);
+    const int all = (ctx->previewStale || !ctx->dirtyPostprocess) ? 1 : 0;
     k_postprocess<<<streamingGrid(ctx->tilePixels), FLX_BLOCK, 0, ctx->cur>>>(reinterpret_cast<const float4 *>(ctx->pixels), reinterpret_cast<float4 *>(ctx->preview),
-                                                                            ctx->tilePixels, ctx->params.ppParams.exposure, ctx->params.ppParams.tmOperator);
+                                                                            ctx->dirtyPixels, all, ctx->tilePixels, ctx->params.ppParams.exposure,
+                                                                            ctx->params.ppParams.tmOperator);
+    ctx->previewStale = false;
     return launchCheck(ctx, "k_postprocess");
 }
 
@@ -1945,6 +1965,9 @@ int flx_set_tuning(flx_ctx *ctx, int key, int value)
         return 0;
     case FLX_TUNE_OVERLAP_TRACE:
         ctx->overlapTrace = value != 0;
+        return 0;
+    case FLX_TUNE_DIRTY_POSTPROCESS:
+        ctx->dirtyPostprocess = value != 0;
         return 0;
     case FLX_TUNE_OVERLAP_POSTPROCESS:
         REQUIRE(value >= 0 && value <= 2, "flx_set_tuning: display-pass overlap must be 0, 1 or 2");
@@ -2283,6 +2306,7 @@ int flx_checkpoint_load(flx_ctx *ctx, const char *path)
     ctx->hostPixelIdx = h.hostPixelIdx;
     ctx->pixelIdxAdvancedOnDevice = false;
     CU(cudaMemcpy(ctx->currPixelIdx, &h.hostPixelIdx, sizeof(uint32_t), cudaMemcpyHostToDevice));
+    ctx->previewStale = true;
     markPixelsWritten(ctx);
     return 0;
 }

@@ -25,6 +25,7 @@ struct Frame
     flx_QueueCounters *counters;
     uint32_t *queues[8]; // order of flx_QueueCounters: raygen, extension, shadow, diffuse, glossy, ggxRefl, ggxRefr, delta
     float *pixels;       // tilePixels x float4
+    uint8_t *dirty;      // tilePixels: 1 = the accumulator of this pixel changed since the display pass last looked at it
     float *denoiserAlbedo, *denoiserNormal;
     uint32_t *currPixelIdx;
     uint32_t numTasks;
@@ -79,6 +80,7 @@ __global__ void __launch_bounds__(FLX_BLOCK) k_reset(const __grid_constant__ Fra
         reinterpret_cast<float4 *>(fr.pixels)[gid] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         reinterpret_cast<float4 *>(fr.denoiserNormal)[gid] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         reinterpret_cast<float4 *>(fr.denoiserAlbedo)[gid] = make_float4(0.1f, 0.1f, 0.1f, 0.0f);
+        fr.dirty[gid] = 1;
     }
     if (gid >= fr.numTasks)
         return;
@@ -463,7 +465,10 @@ __global__ void __launch_bounds__(FLX_BLOCK, MIN_BLOCKS) k_logic(const __grid_co
         if (terminate)
         {
             if (len > 0u)
+            {
                 atomicAdd(reinterpret_cast<float4 *>(fr.pixels) + pixIdx, make_float4(Ei.x, Ei.y, Ei.z, 1.0f)); // one 128-bit reduction
+                fr.dirty[pixIdx] = 1;
+            }
             if (FUSE == 0) // fused: the camera-ray part below carries the seed on and stores it
                 t.setu(FLX_S_SEED, gid, seed);
         }
@@ -753,13 +758,20 @@ FLX_DEV float uc2_curve(float x)
     const float A = 0.22, B = 0.30, C = 0.10, D = 0.20, E = 0.01, F = 0.30; // double literals rounded to float, as in the reference
     return (x * (A * x + C * B) + D * E) / (x * (A * x + B) + D * F) - E / F;
 }
-__global__ void __launch_bounds__(FLX_BLOCK) k_postprocess(const float4 *__restrict__ pixels, float4 *__restrict__ preview, uint32_t nPixels, float exposure,
-                                                           uint32_t tmOperator)
+// Only pixels whose accumulator changed since the last pass are recomputed (`dirty`, set by every kernel that writes the
+// accumulator; `all` after anything else that invalidates the preview: new image, new exposure / operator): an iteration splats
+// into at most a fifth of the pixels, and the three pinned double-precision pow per pixel are what this pass costs.  The
+// preview buffer after the pass is the same as if every pixel had been recomputed.
+__global__ void __launch_bounds__(FLX_BLOCK) k_postprocess(const float4 *__restrict__ pixels, float4 *__restrict__ preview, uint8_t *__restrict__ dirty, const int all,
+                                                           uint32_t nPixels, float exposure, uint32_t tmOperator)
 {
     const float W = 11.2, exposureBias = 2.0;
     const float white = uc2_curve(W);
     for (uint32_t i = blockIdx.x * FLX_BLOCK + threadIdx.x; i < nPixels; i += gridDim.x * FLX_BLOCK)
     {
+        if (!all && !dirty[i])
+            continue;
+        dirty[i] = 0;
         float4 c = pixels[i];
         if (c.w > 0.0f)
         {

@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(FLX_BLOCK) k_mk_reset(const __grid_constant__ 
     reinterpret_cast<float4 *>(fr.pixels)[gid] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     reinterpret_cast<float4 *>(fr.denoiserNormal)[gid] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     reinterpret_cast<float4 *>(fr.denoiserAlbedo)[gid] = make_float4(0.1f, 0.1f, 0.1f, 0.0f);
+    fr.dirty[gid] = 1;
     const Tasks &t = fr.tasks;
     t.setu(FLX_S_PHASE, gid, (uint32_t)MK_GENERATE_CAMERA_RAY);
     t.setv(FLX_S_EI, gid, v3(0.0f));
@@ -420,6 +421,7 @@ __global__ void __launch_bounds__(FLX_BLOCK) k_mk_splat(const __grid_constant__ 
         if (prev.w > 0.0f)
             color = make_float4(color.x + prev.x, color.y + prev.y, color.z + prev.z, color.w + prev.w);
         *px = color;
+        fr.dirty[gid] = 1;
         t.setv(FLX_S_EI, gid, v3(0.0f));
         t.setv(FLX_S_T, gid, v3(1.0f));
         t.setu(FLX_S_PATH_LEN, gid, 0u);
@@ -438,6 +440,7 @@ __global__ void __launch_bounds__(FLX_BLOCK) k_mk_splat_preview(const __grid_con
     const Tasks &t = fr.tasks;
     const V3 Ei = t.v(FLX_S_EI, gid);
     reinterpret_cast<float4 *>(fr.pixels)[gid] = make_float4(Ei.x, Ei.y, Ei.z, 0.0f);
+    fr.dirty[gid] = 1;
     t.setv(FLX_S_EI, gid, v3(0.0f));
     t.setv(FLX_S_T, gid, v3(1.0f));
     t.setu(FLX_S_PATH_LEN, gid, 0u);
