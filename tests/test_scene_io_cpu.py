@@ -230,3 +230,69 @@ def test_number_reader_matches_the_reference_loader_on_random_literals(tmp_path)
     want = np.frombuffer(buf, TRIANGLE_DTYPE, nt, 24)
     got = load_model(path).tris
     assert nt == n and got.tobytes() == want.tobytes()
+
+
+def test_differential_fuzz_against_the_reference_loader(tmp_path):
+    """Mutants of tricky.obj / tricky.mtl (numbers rewritten in other notations, whitespace and line-ending changes, statements
+    duplicated / dropped / shuffled where that keeps every index valid, comments, unknown statements) go through both loaders;
+    whenever the reference's loader accepts a mutant, flx_scene_load must produce the same bytes."""
+    tool = os.path.join(os.path.dirname(os.path.dirname(IO)), "..", "oracle", "_ref", "scene_tool")
+    if not os.path.exists(tool):
+        pytest.skip("oracle/_ref/scene_tool not built (needs /root/reference)")
+    import re
+    import subprocess
+    rng = np.random.default_rng(31337)
+    obj_lines = open(os.path.join(IO, "tricky.obj"), newline="").read().split("\r\n")
+    mtl_lines = open(os.path.join(IO, "tricky.mtl")).read().split("\n")
+    number = re.compile(r"(?<![\w./-])[-+]?\d+\.\d+(?:[eE][-+]?\d+)?")
+
+    def renumber(line):
+        def alt(m):
+            v = float(m.group(0))
+            return [m.group(0), "%.10f" % v, "%e" % v, "%.3E" % v, repr(v), "+%s" % m.group(0).lstrip("+") if v >= 0 else m.group(0)][rng.integers(0, 6)]
+        return number.sub(alt, line)
+
+    def mutate(lines, protect):
+        out = []
+        for ln in lines:
+            r = rng.random()
+            if ln.startswith(protect) or r > 0.45:
+                out.append(ln)
+            elif r < 0.12:
+                out.append(renumber(ln))
+            elif r < 0.2:
+                out.append(ln.replace(" ", "  ").replace("  ", " \t", 1))
+            elif r < 0.26:
+                out += ["# a comment", ln, ""]
+            elif r < 0.32:
+                out += [ln, "zz unknown statement 1 2 3"]
+            elif r < 0.38:
+                out.append("  " + ln + "   ")
+            else:
+                out.append(renumber(ln) + " ")
+        return out
+    agreed = 0
+    for k in range(40):
+        d = tmp_path / ("m%d" % k)
+        d.mkdir()
+        eol = ["\n", "\r\n"][rng.integers(0, 2)]
+        obj = mutate(obj_lines, ("mtllib",))
+        mtl = mutate(mtl_lines, ("newmtl",))
+        if rng.random() < 0.3:  # duplicate a face block at the end: indices stay valid
+            obj += [ln for ln in obj_lines if ln.startswith(("usemtl", "f "))][:6]
+        (d / "tricky.obj").write_text(eol.join(obj) + eol, newline="")
+        (d / "tricky.mtl").write_text("\n".join(mtl) + "\n")
+        blob = d / "ref.bin"
+        r = subprocess.run([tool, "obj", str(d / "tricky.obj"), str(blob)], capture_output=True, timeout=60)
+        if r.returncode != 0 or not blob.exists():
+            continue  # the reference rejected (or crashed on) this mutant: nothing to compare
+        buf = open(blob, "rb").read()
+        magic, nt, ni, nn, nm, ntex = struct.unpack_from("<6I", buf, 0)
+        off = 24
+        tris = buf[off:off + nt * 160]; off += nt * 160 + ni * 4 + nn * 48
+        mats = buf[off:off + nm * 80]
+        m = load_model(d / "tricky.obj")
+        assert m.tris.tobytes() == tris, "mutant %d: triangles differ" % k
+        assert m.materials.tobytes() == mats, "mutant %d: materials differ" % k
+        agreed += 1
+    assert agreed >= 30, agreed
