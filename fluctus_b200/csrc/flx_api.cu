@@ -152,6 +152,7 @@ struct flx_ctx
     int smemStack = 0;        // variant 1: first 24 stack levels in shared memory ([level][thread], conflict-free)
     int fetchChunk = 32;     // queue entries a warp reserves per atomic
     int repackOnHost = 0;     // flx_upload_scene: build the traversal layout with the host code instead of the device kernels (checker)
+    int l2Persist = 0;        // 0 off; 1 / 2: persisting-L2 access window over the TTri / TNode array on the two traversal streams
     int prefetchChildren = 0; // persistent kernels: prefetch both children of an inner node (1: L1, 2: L2) while its box tests run
     int logicMinBlocks = 3;   // resident 256-thread CTAs per SM the logic kernel is compiled for (register budget)
     int fuseStages = 1;       // flx_render: logic + raygen + materials as one kernel
@@ -743,6 +744,41 @@ static int ensureMk(flx_ctx *ctx)
     return 0;
 }
 
+// L2 residency hint for the traversal working set: the repacked hierarchy fits the 126 MB L2 but shares it with the streamed path
+// state.  One access-policy window per stream, so one array is covered: 1 = TTri (the larger, more randomly read), 2 = TNode.
+static int applyL2Persist(flx_ctx *ctx)
+{
+    if (!ctx->sceneReady)
+        return 0;
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof attr);
+    if (ctx->l2Persist)
+    {
+        cudaDeviceProp prop;
+        CU(cudaGetDeviceProperties(&prop, ctx->device));
+        const void *base = ctx->l2Persist == 1 ? (const void *)ctx->ttris : (const void *)ctx->tnodes;
+        size_t bytes = (ctx->l2Persist == 1 ? (size_t)ctx->nTTris : (size_t)ctx->nTNodes) * 64;
+        bytes = std::min(bytes, (size_t)prop.accessPolicyMaxWindowSize);
+        CU(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min(bytes, (size_t)prop.persistingL2CacheMaxSize)));
+        attr.accessPolicyWindow.base_ptr = const_cast<void *>(base);
+        attr.accessPolicyWindow.num_bytes = bytes;
+        attr.accessPolicyWindow.hitRatio = 1.0f;
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    }
+    else
+    {
+        attr.accessPolicyWindow.num_bytes = 0; // disables the window
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyNormal;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+    }
+    CU(cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+    CU(cudaStreamSetAttribute(ctx->stream2, cudaStreamAttributeAccessPolicyWindow, &attr));
+    if (!ctx->l2Persist)
+        CU(cudaCtxResetPersistingL2Cache());
+    return 0;
+}
+
 static MkView makeMk(const flx_ctx *c)
 {
     MkView m;
@@ -1030,6 +1066,8 @@ int flx_upload_scene(flx_ctx *ctx, const flx_Triangle *tris, uint32_t n_tris, co
         if ((rc = repackOnDevice(ctx, indices, n_indices, nodes, n_nodes, n_tris)))
             return rc;
         ctx->sceneReady = true;
+        if (ctx->l2Persist && (rc = applyL2Persist(ctx)))
+            return rc;
         if (timing)
             std::fprintf(stderr, "flx_upload_scene: allocations + copies + repack on the device %.2f ms (%.1f MB resident)\n", ms(t1, now()), ctx->sceneBytes / 1e6);
         return 0;
@@ -1043,6 +1081,8 @@ int flx_upload_scene(flx_ctx *ctx, const flx_Triangle *tris, uint32_t n_tris, co
     ctx->nTTris = (uint32_t)(rp.tris.size() / 4);
     ctx->treeletNodes = rp.treeletNodes;
     ctx->sceneReady = true;
+    if (ctx->l2Persist && (rc = applyL2Persist(ctx)))
+        return rc;
     if (timing)
         std::fprintf(stderr, "flx_upload_scene: repack on the host %.2f ms, allocations + copies %.2f ms (%.1f MB)\n", ms(t0, t1), ms(t1, now()), ctx->sceneBytes / 1e6);
     return 0;
@@ -1981,6 +2021,11 @@ int flx_set_tuning(flx_ctx *ctx, int key, int value)
         REQUIRE(value == 2 || value == 3 || value == 4, "flx_set_tuning: logic min blocks must be 2, 3 or 4");
         ctx->logicMinBlocks = value;
         return 0;
+    case FLX_TUNE_L2_PERSIST:
+        REQUIRE(value >= 0 && value <= 2, "flx_set_tuning: L2 persistence must be 0, 1 (TTri) or 2 (TNode)");
+        ctx->l2Persist = value;
+        CU(cudaSetDevice(ctx->device));
+        return applyL2Persist(ctx);
     case FLX_TUNE_REPACK_ON_HOST:
         ctx->repackOnHost = value != 0;
         return 0;

@@ -195,6 +195,8 @@ enum { FLX_TUNE_TRACE_VARIANT = 0,      /* 0: one ray per thread; 1 (default): p
        FLX_TUNE_SMEM_STACK = 11,        /* variant 1: keep the first 24 traversal-stack levels in shared memory (default 0: measured slower, L1 shrinks) */
        FLX_TUNE_MAX_L1 = 12,            /* variant 1: request the maximum L1 carve-out for the traversal kernels (default 0: measured 4 % slower) */
        FLX_TUNE_OVERLAP_TRACE = 7,      /* flx_render: run the shadow-ray kernel on a second stream, overlapping the extension kernel's tail (default 1) */
+       FLX_TUNE_L2_PERSIST = 19,          /* persisting-L2 access window for the traversal streams: 0 off (default), 1 over the TTri array, 2 over the TNode array;
+                                             set after flx_upload_scene */
        FLX_TUNE_DIRTY_POSTPROCESS = 18,   /* display pass recomputes only the pixels whose accumulator changed since its last run (default 1) */
        FLX_TUNE_OVERLAP_POSTPROCESS = 17, /* display pass beside the traversal stages on a third stream: 0 never, 1 (default) in the per-stage ABI
                                              (flx_enqueue_postprocess starts from the accumulator's last writer), 2 also inside flx_render */
