@@ -177,3 +177,36 @@ def test_port_mk_matches_golden(name):
     compare_pixels(out["pixels"], z["pixels"], name, exact_rgb=True)
     compare_pixels(out["preview"], z["preview"], name + " preview", exact_rgb=True)
     assert list(out["stats"]) == list(z["stats"])
+
+
+# ---------------------------------------------------------------------------------------------- the other BASELINE scenes, small
+def _kitchen():
+    scene = SceneData.load_blob(scene_blob("country_kitchen"))
+    envp = os.path.join(os.path.dirname(scene_blob("country_kitchen")), "night.env.bin")
+    if not os.path.exists(envp):
+        pytest.skip("env map blob missing")
+    from bench_configs import kitchen_params
+    return scene, EnvMapData.load_blob(envp), kitchen_params
+
+
+@needs_ref
+@needs_port
+def test_port_matches_reference_kernels_country_kitchen_and_luxball():
+    """C3 (GGX / glossy / mirror / dielectric materials, 11 textures, a bump map, night.hdr alias-method IBL, separate queues) and
+    C4 (ideal dielectric, 16 bounces) at thumbnail size: restatement == the reference's kernels, wavefront integrator."""
+    scene, env, kitchen_params = _kitchen()
+    W, H = 48, 27
+    run_lockstep(PortContext(W * H), RefContext(W * H), scene, kitchen_params(scene, W, H), iterations=10, env=env, check_every=3, exact_rgb=True)
+    from bench_configs import luxball_params
+    lux = SceneData.load_blob(scene_blob("luxball"))
+    run_lockstep(PortContext(W * H), RefContext(W * H), lux, luxball_params(lux, W, H), iterations=18, check_every=6, exact_rgb=True)
+
+
+@needs_ref
+@needs_port
+def test_port_mk_matches_reference_kernels_country_kitchen():
+    """the microkernel integrator on C3: every BSDF type, textures, env-map + MIS in one sampleBsdf kernel"""
+    scene, env, kitchen_params = _kitchen()
+    W, H = 40, 24
+    params = kitchen_params(scene, W, H, max_bounces=4)
+    run_mk_lockstep(PortContext(W * H), RefContext(W * H), scene, params, spp=2, env=env, check_every=2)
