@@ -296,3 +296,32 @@ def test_differential_fuzz_against_the_reference_loader(tmp_path):
         assert m.materials.tobytes() == mats, "mutant %d: materials differ" % k
         agreed += 1
     assert agreed >= 30, agreed
+
+
+def test_malformed_files_are_rejected_not_crashed_on(tmp_path):
+    """truncated / corrupted inputs of every reader: an error comes back (the reference's readers print and exit, or read past
+    the end); nothing crashes and nothing half-read is returned"""
+    from fluctus_b200.scene_io import import_hierarchy
+    hdr = open(os.path.join(IO, "small_rle.hdr"), "rb").read()
+    for name, data in (("cut_header.hdr", hdr[:20]), ("cut_pixels.hdr", hdr[:200]), ("bad_width.hdr", hdr.replace(b"+X 16", b"+X 17")),
+                       ("no_size.hdr", hdr.replace(b"-Y 8 +X 16", b"nonsense")), ("zero_run.hdr", hdr[:hdr.index(b"+X 16\n") + 10] + bytes([128, 0]) * 40)):
+        p = tmp_path / name
+        p.write_bytes(data)
+        with pytest.raises(FluctusError):
+            load_envmap(p)
+    cache = open(os.path.join(IO, "teapot_hierarchy.bin"), "rb").read()
+    for name, data in (("empty.bin", b""), ("cut_indices.bin", cache[:1000]), ("no_nodes.bin", cache[:4 + 4 * struct.unpack_from("<I", cache, 0)[0] + 4])):
+        p = tmp_path / name
+        p.write_bytes(data)
+        with pytest.raises(FluctusError):
+            import_hierarchy(p)
+    for name, text in (("index_out_of_range.obj", "v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 7\n"), ("negative_out_of_range.obj", "v 0 0 0\nv 1 0 0\nv 0 1 0\nf -1 -2 -9\n"),
+                       ("no_faces.obj", "v 0 0 0\nv 1 0 0\n"), ("normal_out_of_range.obj", "v 0 0 0\nv 1 0 0\nv 0 1 0\nvn 0 0 1\nf 1//1 2//1 3//5\n")):
+        p = tmp_path / name
+        p.write_text(text)
+        with pytest.raises(FluctusError):
+            load_model(p)
+    p = tmp_path / "bad_face.ply"
+    p.write_text("ply\nformat ascii 1.0\nelement vertex 3\nproperty float x\nproperty float y\nproperty float z\nelement face 1\nproperty list uchar int vertex_indices\nend_header\n0 0 0\n1 0 0\n0 1 0\n3 0 1 9\n")
+    with pytest.raises(FluctusError):
+        load_model(p)
