@@ -7,8 +7,9 @@
 //
 // Camera: there are no saved camera states in the reference tree (data/states is empty), so the camera is placed to frame
 // the scene's bounding box; the light is the reference's "headlamp" (Tracer::updateAreaLight, src/tracer.cpp:820-826:
-// the area light sits just behind the camera and faces along the view direction).  Textures are not decoded here (the
-// reference uses DevIL); textured materials fall back to their constants.
+// the area light sits just behind the camera and faces along the view direction).  PNG textures are decoded by the library
+// (flx_image_load) and packed like CLContext::packTextures; materials whose texture is in another format (JPEG) fall back to
+// their constants.
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -48,8 +49,49 @@ int main(int argc, char **argv)
             throw std::runtime_error(flx_io_last_error());
         const uint32_t nTris = flx_scene_num_triangles(scene);
         std::vector<flx_Material> mats(flx_scene_materials(scene), flx_scene_materials(scene) + flx_scene_num_materials(scene));
-        for (auto &m : mats)
-            m.map_Kd = m.map_Ks = m.map_N = -1;
+        // textures: PNG files are decoded by the library; anything else (JPEG) is left out and the materials that use it fall
+        // back to their constants
+        const std::string modelPath = argv[1];
+        const std::string folder = modelPath.substr(0, modelPath.find_last_of('/') + 1);
+        const uint32_t nTex = flx_scene_num_textures(scene);
+        std::vector<uint8_t *> images(nTex, nullptr);
+        std::vector<uint32_t> texW(nTex, 1), texH(nTex, 1);
+        static uint8_t white[4] = {255, 255, 255, 255};
+        uint32_t decoded = 0;
+        for (uint32_t i = 0; i < nTex; i++)
+        {
+            if (flx_image_load((folder + flx_scene_texture_name(scene, i)).c_str(), &texW[i], &texH[i], &images[i]) == 0)
+                decoded++;
+            else
+            {
+                images[i] = nullptr;
+                texW[i] = texH[i] = 1;
+                for (auto &m : mats)
+                {
+                    if (m.map_Kd == (int)i) m.map_Kd = -1;
+                    if (m.map_Ks == (int)i) m.map_Ks = -1;
+                    if (m.map_N == (int)i) m.map_N = -1;
+                }
+            }
+        }
+        std::vector<const uint8_t *> imagePtrs(nTex);
+        for (uint32_t i = 0; i < nTex; i++)
+            imagePtrs[i] = images[i] ? images[i] : white;
+        std::vector<flx_TexDescriptor> texDesc(nTex);
+        size_t texBytes = 0;
+        std::vector<uint8_t> texBlob;
+        if (nTex)
+        {
+            if (flx_pack_textures(imagePtrs.data(), texW.data(), texH.data(), nTex, nullptr, nullptr, &texBytes) != 0)
+                throw std::runtime_error(flx_io_last_error());
+            texBlob.resize(texBytes);
+            if (flx_pack_textures(imagePtrs.data(), texW.data(), texH.data(), nTex, texDesc.data(), texBlob.data(), &texBytes) != 0)
+                throw std::runtime_error(flx_io_last_error());
+        }
+        for (uint8_t *im : images)
+            flx_image_free(im);
+        if (nTex)
+            std::fprintf(stderr, "textures: %u of %u decoded (PNG); the others fall back to material constants\n", decoded, nTex);
 
         CLContext clctx(W * H);
         std::vector<flx_Node> nodes(2 * (size_t)nTris);
@@ -64,6 +106,8 @@ int main(int argc, char **argv)
         s.indices = indices.data(); s.numIndices = nTris;
         s.nodes = nodes.data(); s.numNodes = nNodes;
         s.materials = mats.data(); s.numMaterials = (uint32_t)mats.size();
+        s.textures = nTex ? texDesc.data() : nullptr; s.numTextures = nTex;
+        s.texData = nTex ? texBlob.data() : nullptr; s.texBytes = texBytes;
         clctx.uploadSceneData(s);
         if (env)
         {

@@ -79,6 +79,9 @@ _SIGNATURES = {
     "flx_scene_triangles": (_P, [_P]),
     "flx_scene_materials": (_P, [_P]),
     "flx_scene_texture_name": (C.c_char_p, [_P, C.c_uint32]),
+    "flx_image_load": (C.c_int, [C.c_char_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(_P)]),
+    "flx_image_free": (None, [_P]),
+    "flx_pack_textures": (C.c_int, [_P, _P, _P, C.c_uint32, _P, _P, C.POINTER(C.c_size_t)]),
     "flx_hierarchy_export": (C.c_int, [C.c_char_p, _P, C.c_uint32, _P, C.c_uint32]),
     "flx_hierarchy_import": (C.c_int, [C.c_char_p, _P, C.POINTER(C.c_uint32), _P, C.POINTER(C.c_uint32)]),
     "flx_envmap_load": (C.c_int, [C.c_char_p, C.POINTER(_P)]),

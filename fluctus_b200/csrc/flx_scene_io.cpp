@@ -17,6 +17,7 @@
 // Image decoding (textures) is not done here: the reference uses DevIL, which is not available; callers decode the named
 // files themselves and pass RGBA8 to flx_upload_scene.
 #include <algorithm>
+#include <cctype>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -912,6 +913,339 @@ bool write_hdr(const std::string &path, const float *rgb, uint32_t w, uint32_t h
     return ok;
 }
 
+// ---- PNG decoding (textures).  The reference decodes images through DevIL (src/texture.cpp:16-40: ilLoadImage, then
+// ilCopyPixels(... IL_RGBA, IL_UNSIGNED_BYTE ...) with the origin set to lower-left, src/main.cpp:69-71).  PNG is lossless, so any
+// conforming decoder yields the same RGBA8 bytes; this one covers what DevIL's conversion to RGBA8 covers for PNG: 8- and 16-bit
+// (high byte kept) grey, grey+alpha, RGB, RGBA and 1/2/4/8-bit palette or grey, tRNS transparency for palettes, all five
+// scanline filters, non-interlaced.  JPEG is lossy and decoder-dependent ("texture decode parity unpinned"); it is not
+// decoded here -- callers pass such textures decoded.
+struct BitReader
+{
+    const unsigned char *p, *end;
+    uint32_t acc = 0;
+    int n = 0;
+    bool bad = false;
+    uint32_t bits(int k)
+    {
+        while (n < k)
+        {
+            if (p >= end)
+            {
+                bad = true;
+                return 0;
+            }
+            acc |= (uint32_t)(*p++) << n;
+            n += 8;
+        }
+        const uint32_t v = acc & ((k == 32) ? 0xffffffffu : ((1u << k) - 1u));
+        acc >>= k;
+        n -= k;
+        return v;
+    }
+};
+
+struct Huffman // canonical code, decoded bit by bit (count / symbol tables, RFC 1951 section 3.2.2)
+{
+    uint16_t count[16] = {0};
+    uint16_t symbol[288] = {0};
+    void build(const unsigned char *lengths, int nsym)
+    {
+        for (int i = 0; i < 16; i++)
+            count[i] = 0;
+        for (int i = 0; i < nsym; i++)
+            count[lengths[i]]++;
+        count[0] = 0;
+        uint16_t offs[16];
+        offs[1] = 0;
+        for (int i = 1; i < 15; i++)
+            offs[i + 1] = offs[i] + count[i];
+        for (int i = 0; i < nsym; i++)
+            if (lengths[i])
+                symbol[offs[lengths[i]]++] = (uint16_t)i;
+    }
+    int decode(BitReader &br) const
+    {
+        int code = 0, first = 0, index = 0;
+        for (int len = 1; len <= 15; len++)
+        {
+            code |= (int)br.bits(1);
+            if (br.bad)
+                return -1;
+            const int c = count[len];
+            if (code - c < first)
+                return symbol[index + (code - first)];
+            index += c;
+            first += c;
+            first <<= 1;
+            code <<= 1;
+        }
+        return -1;
+    }
+};
+
+bool inflate_zlib(const unsigned char *src, size_t n, std::vector<unsigned char> &out)
+{
+    if (n < 6 || (src[0] & 0x0f) != 8 || ((src[0] << 8 | src[1]) % 31) != 0 || (src[1] & 0x20))
+        return false;
+    BitReader br{src + 2, src + n};
+    static const uint16_t lenBase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+    static const uint16_t lenExtra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+    static const uint16_t distBase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+    static const uint16_t distExtra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+    for (;;)
+    {
+        const uint32_t last = br.bits(1), type = br.bits(2);
+        if (br.bad || type == 3)
+            return false;
+        if (type == 0)
+        {
+            br.acc = 0;
+            br.n = 0; // to the byte boundary
+            if (br.end - br.p < 4)
+                return false;
+            const uint32_t len = br.p[0] | (br.p[1] << 8), nlen = br.p[2] | (br.p[3] << 8);
+            br.p += 4;
+            if ((len ^ 0xffffu) != nlen || (size_t)(br.end - br.p) < len)
+                return false;
+            out.insert(out.end(), br.p, br.p + len);
+            br.p += len;
+        }
+        else
+        {
+            Huffman lit, dist;
+            unsigned char lengths[320];
+            if (type == 1)
+            {
+                for (int i = 0; i < 288; i++)
+                    lengths[i] = i < 144 ? 8 : (i < 256 ? 9 : (i < 280 ? 7 : 8));
+                lit.build(lengths, 288);
+                for (int i = 0; i < 30; i++)
+                    lengths[i] = 5;
+                dist.build(lengths, 30);
+            }
+            else
+            {
+                const int hlit = (int)br.bits(5) + 257, hdist = (int)br.bits(5) + 1, hclen = (int)br.bits(4) + 4;
+                if (br.bad || hlit > 286 || hdist > 30)
+                    return false;
+                static const unsigned char order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+                unsigned char cl[19] = {0};
+                for (int i = 0; i < hclen; i++)
+                    cl[order[i]] = (unsigned char)br.bits(3);
+                Huffman clh;
+                clh.build(cl, 19);
+                int i = 0;
+                while (i < hlit + hdist)
+                {
+                    const int sym = clh.decode(br);
+                    if (sym < 0)
+                        return false;
+                    if (sym < 16)
+                        lengths[i++] = (unsigned char)sym;
+                    else
+                    {
+                        int rep, val = 0;
+                        if (sym == 16)
+                        {
+                            if (i == 0)
+                                return false;
+                            val = lengths[i - 1];
+                            rep = 3 + (int)br.bits(2);
+                        }
+                        else if (sym == 17)
+                            rep = 3 + (int)br.bits(3);
+                        else
+                            rep = 11 + (int)br.bits(7);
+                        if (br.bad || i + rep > hlit + hdist)
+                            return false;
+                        while (rep--)
+                            lengths[i++] = (unsigned char)val;
+                    }
+                }
+                lit.build(lengths, hlit);
+                dist.build(lengths + hlit, hdist);
+            }
+            for (;;)
+            {
+                const int sym = lit.decode(br);
+                if (sym < 0)
+                    return false;
+                if (sym < 256)
+                    out.push_back((unsigned char)sym);
+                else if (sym == 256)
+                    break;
+                else
+                {
+                    if (sym > 285)
+                        return false;
+                    const int len = lenBase[sym - 257] + (int)br.bits(lenExtra[sym - 257]);
+                    const int ds = dist.decode(br);
+                    if (ds < 0 || ds > 29)
+                        return false;
+                    const size_t d = distBase[ds] + br.bits(distExtra[ds]);
+                    if (br.bad || d > out.size())
+                        return false;
+                    const size_t from = out.size() - d;
+                    for (int k = 0; k < len; k++)
+                        out.push_back(out[from + k]);
+                }
+            }
+        }
+        if (last)
+            return !br.bad;
+    }
+}
+
+// -> RGBA8, row 0 = BOTTOM row (the reference's DevIL origin)
+bool decode_png(const std::string &path, uint32_t &w, uint32_t &h, std::vector<unsigned char> &rgba)
+{
+    FILE *fp = std::fopen(path.c_str(), "rb");
+    if (!fp)
+    {
+        g_io_error = "cannot open " + path;
+        return false;
+    }
+    std::fseek(fp, 0, SEEK_END);
+    const long size = std::ftell(fp);
+    std::fseek(fp, 0, SEEK_SET);
+    std::vector<unsigned char> file(size > 0 ? (size_t)size : 0);
+    const bool readOk = file.empty() || std::fread(file.data(), 1, file.size(), fp) == file.size();
+    std::fclose(fp);
+    auto bad = [&](const char *why) {
+        g_io_error = path + ": " + why;
+        return false;
+    };
+    static const unsigned char sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    if (!readOk || file.size() < 8 + 25 || std::memcmp(file.data(), sig, 8) != 0)
+        return bad("not a PNG file");
+    auto be32 = [&](size_t at) { return ((uint32_t)file[at] << 24) | ((uint32_t)file[at + 1] << 16) | ((uint32_t)file[at + 2] << 8) | file[at + 3]; };
+    int depth = 0, colour = 0, interlace = 0;
+    std::vector<unsigned char> idat, palette, trns;
+    bool haveHeader = false, done = false;
+    for (size_t at = 8; at + 12 <= file.size() && !done;)
+    {
+        const uint32_t len = be32(at);
+        if (len > file.size() - at - 12)
+            return bad("truncated chunk");
+        const char *type = reinterpret_cast<const char *>(&file[at + 4]);
+        const unsigned char *body = &file[at + 8];
+        if (crc32_of(&file[at + 4], (size_t)len + 4, 0) != be32(at + 8 + len))
+            return bad("chunk checksum mismatch");
+        if (!std::memcmp(type, "IHDR", 4))
+        {
+            if (len != 13)
+                return bad("bad IHDR");
+            w = be32(at + 8);
+            h = be32(at + 12);
+            depth = body[8];
+            colour = body[9];
+            interlace = body[12];
+            if (body[10] != 0 || body[11] != 0)
+                return bad("unknown compression / filter method");
+            haveHeader = true;
+        }
+        else if (!std::memcmp(type, "PLTE", 4))
+            palette.assign(body, body + len);
+        else if (!std::memcmp(type, "tRNS", 4))
+            trns.assign(body, body + len);
+        else if (!std::memcmp(type, "IDAT", 4))
+            idat.insert(idat.end(), body, body + len);
+        else if (!std::memcmp(type, "IEND", 4))
+            done = true;
+        at += (size_t)len + 12;
+    }
+    if (!haveHeader || w == 0 || h == 0 || (uint64_t)w * h > (1ull << 28))
+        return bad("missing or unreasonable header");
+    if (interlace)
+        return bad("interlaced PNG is not supported");
+    int channels;
+    switch (colour)
+    {
+    case 0: channels = 1; break;
+    case 2: channels = 3; break;
+    case 3: channels = 1; break;
+    case 4: channels = 2; break;
+    case 6: channels = 4; break;
+    default: return bad("unknown colour type");
+    }
+    const bool depthOk = (colour == 0 && (depth == 1 || depth == 2 || depth == 4 || depth == 8 || depth == 16)) || (colour == 3 && (depth == 1 || depth == 2 || depth == 4 || depth == 8)) ||
+                         ((colour == 2 || colour == 4 || colour == 6) && (depth == 8 || depth == 16));
+    if (!depthOk)
+        return bad("unsupported bit depth");
+    if (colour == 3 && palette.size() < 3)
+        return bad("palette image without a palette");
+    std::vector<unsigned char> raw;
+    const size_t rowBytes = ((size_t)w * channels * depth + 7) / 8, bpp = std::max<size_t>(1, (size_t)channels * depth / 8);
+    raw.reserve((rowBytes + 1) * h);
+    if (!inflate_zlib(idat.data(), idat.size(), raw) || raw.size() < (rowBytes + 1) * h)
+        return bad("corrupt image data");
+    // undo the scanline filters in place (PNG specification, section 9)
+    std::vector<unsigned char> zero(rowBytes, 0);
+    for (uint32_t y = 0; y < h; y++)
+    {
+        unsigned char *cur = &raw[(rowBytes + 1) * y + 1];
+        const unsigned char *up = y ? &raw[(rowBytes + 1) * (y - 1) + 1] : zero.data();
+        const int filter = raw[(rowBytes + 1) * y];
+        for (size_t x = 0; x < rowBytes; x++)
+        {
+            const int a = x >= bpp ? cur[x - bpp] : 0, b = up[x], c = x >= bpp ? up[x - bpp] : 0;
+            int pred = 0;
+            if (filter == 1) pred = a;
+            else if (filter == 2) pred = b;
+            else if (filter == 3) pred = (a + b) >> 1;
+            else if (filter == 4)
+            {
+                const int pa = std::abs(b - c), pb = std::abs(a - c), pc = std::abs(a + b - 2 * c);
+                pred = (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
+            }
+            else if (filter != 0)
+                return bad("unknown scanline filter");
+            cur[x] = (unsigned char)(cur[x] + pred);
+        }
+    }
+    rgba.assign((size_t)w * h * 4, 255);
+    for (uint32_t y = 0; y < h; y++)
+    {
+        const unsigned char *row = &raw[(rowBytes + 1) * y + 1];
+        unsigned char *dst = &rgba[(size_t)(h - 1 - y) * w * 4]; // flip: row 0 of the result is the bottom row
+        for (uint32_t x = 0; x < w; x++, dst += 4)
+        {
+            auto sample = [&](int ch) -> int { // channel value as 8 bits (16-bit: high byte; < 8-bit grey: scaled to 0..255)
+                if (depth == 8)
+                    return row[(size_t)x * channels + ch];
+                if (depth == 16)
+                    return row[((size_t)x * channels + ch) * 2];
+                const size_t bit = (size_t)x * depth;
+                const int v = (row[bit >> 3] >> (8 - depth - (bit & 7))) & ((1 << depth) - 1);
+                return colour == 3 ? v : v * 255 / ((1 << depth) - 1);
+            };
+            if (colour == 3)
+            {
+                const size_t idx = (size_t)sample(0);
+                if (idx * 3 + 2 >= palette.size())
+                    return bad("palette index out of range");
+                dst[0] = palette[idx * 3];
+                dst[1] = palette[idx * 3 + 1];
+                dst[2] = palette[idx * 3 + 2];
+                dst[3] = idx < trns.size() ? trns[idx] : 255;
+            }
+            else if (colour == 0 || colour == 4)
+            {
+                dst[0] = dst[1] = dst[2] = (unsigned char)sample(0);
+                dst[3] = colour == 4 ? (unsigned char)sample(1) : 255;
+            }
+            else
+            {
+                dst[0] = (unsigned char)sample(0);
+                dst[1] = (unsigned char)sample(1);
+                dst[2] = (unsigned char)sample(2);
+                dst[3] = colour == 6 ? (unsigned char)sample(3) : 255;
+            }
+        }
+    }
+    return true;
+}
+
 bool ends_with(const std::string &s, const char *suffix)
 {
     const size_t n = std::strlen(suffix);
@@ -1122,6 +1456,84 @@ int flx_hierarchy_import(const char *path, flx_Node *nodes_out, uint32_t *n_node
     }
     *n_nodes = nn;
     *n_indices = ni;
+    return 0;
+}
+
+// Decode one image file to RGBA8 with the reference's conventions (4 channels, row 0 = bottom row).  PNG only (see decode_png);
+// the buffer belongs to the library until flx_image_free.
+int flx_image_load(const char *path, uint32_t *width, uint32_t *height, uint8_t **rgba)
+{
+    if (!path || !width || !height || !rgba)
+    {
+        g_io_error = "flx_image_load: null argument";
+        return FLX_E_INVALID;
+    }
+    *rgba = nullptr;
+    std::string lower(path);
+    for (char &c : lower)
+        c = (char)std::tolower((unsigned char)c);
+    if (!ends_with(lower, ".png"))
+    {
+        g_io_error = std::string(path) + ": only PNG is decoded here (JPEG is lossy and decoder-dependent: pass such textures decoded)";
+        return FLX_E_INVALID;
+    }
+    std::vector<unsigned char> pixels;
+    uint32_t w = 0, h = 0;
+    if (!decode_png(path, w, h, pixels))
+        return FLX_E_INVALID;
+    uint8_t *out = (uint8_t *)std::malloc(pixels.size());
+    if (!out)
+    {
+        g_io_error = "flx_image_load: out of memory";
+        return FLX_E_INVALID;
+    }
+    std::memcpy(out, pixels.data(), pixels.size());
+    *rgba = out;
+    *width = w;
+    *height = h;
+    return 0;
+}
+
+void flx_image_free(uint8_t *rgba) { std::free(rgba); }
+
+// CLContext::packTextures (src/clcontext.cpp:570-611): descriptors {byte offset, width, height} + the RGBA8 images back to back.
+// images[i] / widths[i] / heights[i]: the decoded textures in the scene's texture order.  Two-call protocol: blob_out == NULL
+// returns the size needed.
+int flx_pack_textures(const uint8_t *const *images, const uint32_t *widths, const uint32_t *heights, uint32_t n_tex, flx_TexDescriptor *desc_out, uint8_t *blob_out,
+                      size_t *blob_bytes)
+{
+    if ((n_tex && (!images || !widths || !heights)) || !blob_bytes)
+    {
+        g_io_error = "flx_pack_textures: null argument";
+        return FLX_E_INVALID;
+    }
+    size_t total = 0;
+    for (uint32_t i = 0; i < n_tex; i++)
+        total += (size_t)widths[i] * heights[i] * 4;
+    if (total > 0xffffffffull)
+    {
+        g_io_error = "flx_pack_textures: more than 4 GiB of texture data (offsets are 32-bit, src/geom.h:126-131)";
+        return FLX_E_INVALID;
+    }
+    if (blob_out && desc_out)
+    {
+        if (*blob_bytes < total)
+        {
+            g_io_error = "flx_pack_textures: blob too small";
+            return FLX_E_INVALID;
+        }
+        size_t off = 0;
+        for (uint32_t i = 0; i < n_tex; i++)
+        {
+            const size_t len = (size_t)widths[i] * heights[i] * 4;
+            desc_out[i].offset = (uint32_t)off;
+            desc_out[i].width = widths[i];
+            desc_out[i].height = heights[i];
+            std::memcpy(blob_out + off, images[i], len);
+            off += len;
+        }
+    }
+    *blob_bytes = total;
     return 0;
 }
 

@@ -100,3 +100,33 @@ def import_hierarchy(path):
     if lib.flx_hierarchy_import(str(path).encode(), nodes.ctypes.data_as(C.c_void_p), C.byref(nn), indices.ctypes.data_as(C.c_void_p), C.byref(ni)) != 0:
         raise _io_error(lib, "flx_hierarchy_import(%s)" % path)
     return nodes, indices
+
+
+def load_image(path):
+    """PNG -> (h, w, 4) uint8, row 0 = bottom row, the reference's in-memory texture form (flx_image_load)."""
+    lib = _lib.load()
+    w, h, ptr = C.c_uint32(), C.c_uint32(), C.c_void_p()
+    if lib.flx_image_load(str(path).encode(), C.byref(w), C.byref(h), C.byref(ptr)) != 0:
+        raise _io_error(lib, "flx_image_load(%s)" % path)
+    try:
+        return np.frombuffer(C.string_at(ptr, w.value * h.value * 4), np.uint8).reshape(h.value, w.value, 4).copy()
+    finally:
+        lib.flx_image_free(ptr)
+
+
+def pack_textures(images):
+    """CLContext::packTextures through the C ABI: list of (h, w, 4) uint8 arrays -> (descriptors, blob)."""
+    from .structs import TEXDESC_DTYPE
+    lib = _lib.load()
+    images = [np.ascontiguousarray(im, np.uint8) for im in images]
+    n = len(images)
+    ptrs = (C.c_void_p * max(n, 1))(*[im.ctypes.data for im in images])
+    ws = (C.c_uint32 * max(n, 1))(*[im.shape[1] for im in images])
+    hs = (C.c_uint32 * max(n, 1))(*[im.shape[0] for im in images])
+    size = C.c_size_t()
+    if lib.flx_pack_textures(ptrs, ws, hs, n, None, None, C.byref(size)) != 0:
+        raise _io_error(lib, "flx_pack_textures")
+    desc, blob = np.zeros(n, TEXDESC_DTYPE), np.zeros(size.value, np.uint8)
+    if lib.flx_pack_textures(ptrs, ws, hs, n, desc.ctypes.data_as(C.c_void_p), blob.ctypes.data_as(C.c_void_p), C.byref(size)) != 0:
+        raise _io_error(lib, "flx_pack_textures")
+    return desc, blob

@@ -286,6 +286,15 @@ const float *flx_envmap_prob(const flx_envmap *env);
 const int32_t *flx_envmap_alias(const flx_envmap *env);
 const float *flx_envmap_pdf(const flx_envmap *env);
 
+/* Textures.  flx_image_load decodes a PNG to the reference's in-memory form (RGBA8, row 0 = bottom row; src/texture.cpp:16-40 with
+ * DevIL's origin at lower-left, src/main.cpp:69-71); JPEG is not decoded (lossy, decoder-dependent: SURVEY 8c) -- pass such images
+ * decoded.  flx_pack_textures = CLContext::packTextures (src/clcontext.cpp:570-611): descriptors + images back to back, the two
+ * arrays flx_upload_scene takes; with blob_out == NULL it only reports the size. */
+int flx_image_load(const char *path, uint32_t *width, uint32_t *height, uint8_t **rgba);
+void flx_image_free(uint8_t *rgba);
+int flx_pack_textures(const uint8_t *const *images, const uint32_t *widths, const uint32_t *heights, uint32_t n_tex, flx_TexDescriptor *desc_out, uint8_t *blob_out,
+                      size_t *blob_bytes);
+
 /* The reference's hierarchy cache file (BVH::exportTo / importFrom, src/bvh.cpp:102-192; `data/hierarchies/hierarchy_<hash>.bin`,
  * src/tracer.cpp:574-590, 742-751), both directions, so caches can be exchanged with the reference.  The reference writes the
  * index count where the node count belongs (src/bvh.cpp:185): the importer here derives the node count from the file length,

@@ -148,6 +148,28 @@ def test_file_to_picture_pipeline_without_reference_code(tmp_path):
     assert lin.shape == (96, 160, 3) and np.isfinite(lin).all() and lin.max() > 0
     r = subprocess.run([exe, str(tmp_path / "missing.obj"), str(png)], capture_output=True, text=True, timeout=60)
     assert r.returncode == 1 and "cannot open" in r.stderr
+    # a textured model: the PNG texture is decoded and packed by the library, the (missing) JPEG falls back to the material constant
+    tex = np.zeros((8, 8, 3), np.uint8)
+    tex[..., 1] = 255  # pure green albedo
+    Image.fromarray(tex, "RGB").save(tmp_path / "green.png")
+    with open(tmp_path / "tex.mtl", "w") as f:
+        f.write("newmtl painted\nKd 1 0 0\nmap_Kd green.png\nnewmtl photo\nKd 0.5 0.5 0.5\nmap_Kd missing.jpg\n")
+    with open(tmp_path / "tex.obj", "w") as f:
+        f.write("mtllib tex.mtl\n")
+        for t in room.tris:
+            for v in ("v0", "v1", "v2"):
+                f.write("v %.9g %.9g %.9g\n" % tuple(t[v]["p"][:3]))
+        f.write("vt 0.5 0.5\nusemtl painted\n")
+        for i in range(len(room.tris)):
+            if i == len(room.tris) // 2:
+                f.write("usemtl photo\n")
+            f.write("f %d/1 %d/1 %d/1\n" % (3 * i + 1, 3 * i + 2, 3 * i + 3))
+    out = tmp_path / "tex.png"
+    r = subprocess.run([exe, str(tmp_path / "tex.obj"), str(out), "96", "64", "8", "2"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert "1 of 2 decoded" in r.stderr
+    img = np.asarray(Image.open(out).convert("RGB")).astype(np.float64)
+    assert img[..., 1].mean() > 1.5 * img[..., 0].mean()  # the green texture shows (the red Kd it overrides would not)
 
 
 def test_mk_tiled_contexts_cover_the_image():

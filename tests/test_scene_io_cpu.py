@@ -325,3 +325,80 @@ def test_malformed_files_are_rejected_not_crashed_on(tmp_path):
     p.write_text("ply\nformat ascii 1.0\nelement vertex 3\nproperty float x\nproperty float y\nproperty float z\nelement face 1\nproperty list uchar int vertex_indices\nend_header\n0 0 0\n1 0 0\n0 1 0\n3 0 1 9\n")
     with pytest.raises(FluctusError):
         load_model(p)
+
+
+# ---------------------------------------------------------------------------------------------- textures
+def test_png_decoder_matches_an_independent_decoder(tmp_path):
+    """flx_image_load against Pillow on PNGs of every colour type and bit depth Pillow can write (grey 1/8/16 bit, grey+alpha,
+    RGB, RGBA, palette with and without transparency), sizes that are not multiples of anything, compression levels that make
+    the encoder use stored, fixed and dynamic Huffman blocks, and -- where present -- the reference's own PNG textures.
+    PNG is lossless: the RGBA8 bytes must be identical (rows bottom-up, DevIL's lower-left origin in the reference)."""
+    from PIL import Image
+    from fluctus_b200.scene_io import load_image
+    rng = np.random.default_rng(9)
+
+    def check(path):
+        want = np.asarray(Image.open(path).convert("RGBA"), dtype=np.uint8)[::-1]
+        got = load_image(path)
+        assert got.shape == want.shape and np.array_equal(got, want), path
+
+    smooth = (np.add.outer(np.arange(37), np.arange(53)) * 3 % 256).astype(np.uint8)
+    noise = rng.integers(0, 256, (37, 53), dtype=np.uint8)
+    k = 0
+    for base in (smooth, noise):
+        for mode in ("L", "LA", "RGB", "RGBA", "P", "1"):
+            for level in (0, 1, 9):
+                if mode == "L":
+                    im = Image.fromarray(base, "L")
+                elif mode == "LA":
+                    im = Image.fromarray(np.stack([base, base[::-1]], axis=-1), "LA")
+                elif mode == "RGB":
+                    im = Image.fromarray(np.stack([base, base.T[:37, :53] if base.T.shape == base.shape else base[::-1], 255 - base], axis=-1), "RGB")
+                elif mode == "RGBA":
+                    im = Image.fromarray(np.stack([base, base[::-1], 255 - base, base[:, ::-1]], axis=-1), "RGBA")
+                elif mode == "P":
+                    im = Image.fromarray(base, "L").quantize(17)
+                else:
+                    im = Image.fromarray(base, "L").convert("1")
+                p = tmp_path / ("t%d.png" % k)
+                k += 1
+                im.save(p, compress_level=level)
+                check(p)
+    pal = Image.fromarray(noise % 5, "P")
+    pal.putpalette([10, 20, 30, 200, 100, 0, 0, 0, 255, 255, 255, 255, 9, 99, 199])
+    pal.save(tmp_path / "trns.png", transparency=bytes([0, 128, 255, 7, 200]))
+    check(tmp_path / "trns.png")
+    Image.fromarray(noise.astype(np.uint16) * 257).save(tmp_path / "g16.png")  # uint16 -> mode I;16
+    got = load_image(tmp_path / "g16.png")  # 16-bit grey: the high byte of every sample
+    assert np.array_equal(got[..., 0], noise[::-1]) and np.array_equal(got[..., 3], np.full_like(noise, 255))
+    for rel in ("egyptcat/EgyptCat.png", "country_kitchen/textures/Kitchen-carrot-uv.png", "country_kitchen/textures/Kitchen-mushroom-texture.png"):
+        if os.path.exists(os.path.join(REF_ASSETS, rel)):
+            check(os.path.join(REF_ASSETS, rel))
+    with pytest.raises(FluctusError):
+        load_image(os.path.join(IO, "tricky.obj"))
+    bad = tmp_path / "cut.png"
+    bad.write_bytes(open(tmp_path / "t0.png", "rb").read()[:60])
+    with pytest.raises(FluctusError):
+        load_image(bad)
+
+
+def test_texture_packing_matches_packTextures():
+    """flx_pack_textures = CLContext::packTextures (src/clcontext.cpp:570-611); same descriptors and blob as the Python helper the
+    scene blobs were made with, and -- where the reference's assets are present -- the egyptcat texture decoded + packed in C
+    equals the blob the tests render with."""
+    from fluctus_b200.scene import pack_textures as pack_py
+    from fluctus_b200.scene_io import load_image, pack_textures
+    rng = np.random.default_rng(4)
+    images = [rng.integers(0, 256, (h, w, 4), dtype=np.uint8) for h, w in ((3, 5), (16, 16), (1, 7))]
+    desc, blob = pack_textures(images)
+    assert [tuple(d) for d in desc] == [(0, 5, 3), (60, 16, 16), (60 + 1024, 7, 1)]
+    assert np.array_equal(blob, np.concatenate([im.reshape(-1) for im in images]))
+    assert pack_textures([])[1].size == 0
+    png = os.path.join(REF_ASSETS, "egyptcat", "EgyptCat.png")
+    side = os.path.join(os.path.dirname(scene_blob("teapot")), "egyptcat.tex.npz")
+    if os.path.exists(png) and os.path.exists(side):
+        z = np.load(side)
+        d2, b2 = pack_textures([load_image(png)])
+        assert np.array_equal(d2.view(np.uint32).reshape(-1, 3), z["desc"]) and np.array_equal(b2, z["data"])
+        d3, b3 = pack_py([png])
+        assert np.array_equal(b3, b2)
