@@ -199,3 +199,19 @@ def test_mk_tiled_contexts_cover_the_image():
     row_a, row_b = full[..., :3].mean(axis=(1, 2)), solo[..., :3].mean(axis=(1, 2))
     assert np.allclose(row_a, row_b, rtol=0.08, atol=1e-3), np.abs(row_a - row_b).max()
     assert abs(full[..., :3].mean() - solo[..., :3].mean()) < 0.02 * solo[..., :3].mean()
+
+
+def test_mk_country_kitchen_c3_small():
+    """BASELINE config C3 through the microkernel integrator at thumbnail size: every BSDF type on its own shading list, 11 textures
+    and a bump map, night.hdr alias-method IBL with MIS -- kernel by kernel against the reference's mk kernels."""
+    from fluctus_b200 import EnvMapData
+    from conftest import SCENES_DIR
+    scene = SceneData.load_blob(scene_blob("country_kitchen"))
+    envp = os.path.join(SCENES_DIR, "night.env.bin")
+    if not os.path.exists(envp):
+        pytest.skip("env map blob missing")
+    from bench_configs import kitchen_params
+    W, H = 64, 36
+    params = kitchen_params(scene, W, H, max_bounces=5)
+    with CLContext(W * H) as gpu:
+        run_mk_lockstep(gpu, oracle_ctx(W * H), scene, params, spp=2, env=EnvMapData.load_blob(envp), check_every=2)
