@@ -8,8 +8,8 @@ There is no CPU fallback: importing CLContext works anywhere, creating one needs
 from .structs import (RenderParams, QueueCounters, RenderStats64, Camera, AreaLight, NODE_DTYPE, TRIANGLE_DTYPE, MATERIAL_DTYPE,
                       TEXDESC_DTYPE, SLOT, BXDF)
 from .scene import SceneData, EnvMapData, make_params, look_at
-from .clcontext import CLContext, FluctusError
+from .clcontext import CLContext, FluctusError, pinned_empty, pinned_copy
 from .tracer import Tracer
 
-__all__ = ["CLContext", "FluctusError", "Tracer", "SceneData", "EnvMapData", "RenderParams", "QueueCounters", "RenderStats64", "Camera",
+__all__ = ["CLContext", "FluctusError", "pinned_empty", "pinned_copy", "Tracer", "SceneData", "EnvMapData", "RenderParams", "QueueCounters", "RenderStats64", "Camera",
            "AreaLight", "make_params", "look_at", "NODE_DTYPE", "TRIANGLE_DTYPE", "MATERIAL_DTYPE", "TEXDESC_DTYPE", "SLOT", "BXDF"]

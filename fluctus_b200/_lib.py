@@ -66,6 +66,8 @@ _SIGNATURES = {
     "flx_gather_pixels": (C.c_int, [_P, C.c_int, _P]),
     "flx_comm_destroy": (C.c_int, [_P]),
     "flx_device_bytes": (C.c_size_t, [_P]),
+    "flx_host_alloc": (C.c_int, [C.POINTER(_P), C.c_size_t]),
+    "flx_host_free": (None, [_P]),
     "flx_io_last_error": (C.c_char_p, []),
     "flx_save_image": (C.c_int, [_P, C.c_char_p]),
     "flx_checkpoint_save": (C.c_int, [_P, C.c_char_p]),

@@ -18,7 +18,43 @@ class FluctusError(RuntimeError):
 
 
 KERNEL_IDS = {"reset": 0, "raygen": 1, "extrays": 2, "shadowrays": 3, "logic": 4, "materials": 5, "end_iteration": 6, "postprocess": 7,
-              "mk_reset": 8, "mk_raygen": 9, "mk_next_vertex": 10, "mk_sample_bsdf": 11, "mk_splat": 12, "logic_fused": 13}
+              "mk_reset": 8, "mk_raygen": 9, "mk_next_vertex": 10, "mk_sample_bsdf": 11, "mk_splat": 12, "logic_fused": 13, "gather": 14}
+
+
+class _PinnedBlock:
+    """Owner of one flx_host_alloc block; numpy arrays made over it keep it alive through their .base chain."""
+
+    def __init__(self, lib, nbytes):
+        self._lib, self.ptr, self.nbytes = lib, C.c_void_p(), int(nbytes)
+        rc = lib.flx_host_alloc(C.byref(self.ptr), self.nbytes)
+        if rc != 0:
+            msg = lib.flx_last_error(None)
+            raise FluctusError("flx_host_alloc(%d) failed (%d): %s" % (nbytes, rc, msg.decode() if msg else "?"))
+        self.buffer = (C.c_ubyte * self.nbytes).from_address(self.ptr.value)
+        self.buffer._owner = self
+
+    def __del__(self):
+        try:
+            if self.ptr.value:
+                self._lib.flx_host_free(self.ptr)
+                self.ptr = C.c_void_p()
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype):
+    """A numpy array in page-locked host memory (flx_host_alloc): copies between it and the device are DMA transfers at link
+    speed.  The reference's analogue is the GL pixel-buffer object the picture is rendered into (src/clcontext.cpp:326-384)."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) if np.ndim(shape) else int(shape)
+    block = _PinnedBlock(_lib.load(), max(n * dtype.itemsize, 1))
+    return np.frombuffer(block.buffer, dtype=dtype, count=n).reshape(shape)
+
+
+def pinned_copy(a):
+    out = pinned_empty(a.shape, a.dtype)
+    out[...] = a
+    return out
 
 
 class CLContext:
@@ -229,9 +265,13 @@ class CLContext:
     def tilePixels(self):
         return int(self._lib.flx_tile_pixels(self._h))
 
-    def readPixels(self):
+    def readPixels(self, out=None):
+        """The accumulator (RGB sums, sample count) of this context's pixels.  `out`: a caller's (tilePixels, 4) float32 array to
+        fill -- e.g. one from pinned_empty(), which makes the copy a DMA transfer."""
         n = self.tilePixels()
-        out = np.empty((n, 4), np.float32)
+        if out is None:
+            out = np.empty((n, 4), np.float32)
+        assert out.dtype == np.float32 and out.size == n * 4 and out.flags.c_contiguous
         self._check(self._lib.flx_read_pixels(self._h, self._ptr(out), n), "readPixels")
         return out
 

@@ -13,6 +13,7 @@
 #include <cstring>
 #include <queue>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "flx_bvh_build.cuh"
@@ -119,6 +120,7 @@ struct flx_ctx
     bool otherTypes = false;     // BSDF types the scene does not contain are not launched; otherTypes: a type none of the lists knows
     bool sceneReady = false;
     size_t sceneBytes = 0;
+    uint64_t sceneHash = 0;      // fingerprint of the uploaded scene (sizes, materials, a sample of nodes and triangles): checkpoints carry it
 
     // environment map
     float *envRGBA = nullptr, *probTable = nullptr, *pdfTable = nullptr;
@@ -133,7 +135,18 @@ struct flx_ctx
     uint32_t width = 0, height = 0, tilePixels = 0;
     uint32_t part = 0, nParts = 1, stripeRows = 1;
     float *gatherBuf = nullptr, *fullImage = nullptr; // rank-major gather target and de-interleaved full image (root)
-    size_t gatherBufPixels = 0;
+    size_t gatherBufPixels = 0, fullImagePixels = 0;  // capacities, tracked separately (a resize can grow one and not the other)
+    // The gather runs on its own stream from a SNAPSHOT of the accumulator (one device-to-device copy on the render stream, a
+    // few microseconds), so the render stream goes on splatting into `pixels` while NCCL moves the snapshot: the collective is
+    // off the critical path even when it runs every iteration.  evGatherDone guards the snapshot against the next gather.
+    cudaStream_t gatherStream = nullptr;
+    cudaEvent_t evSnapshot = nullptr, evGatherDone = nullptr; // evGatherDone: the most recent gather has finished
+    cudaEvent_t evSnapshotFree[2] = {nullptr, nullptr};        // the gather that read snapshot buffer k has finished
+    float *gatherSnapshot = nullptr;                           // TWO snapshot buffers, used alternately (double-buffered accumulator)
+    size_t gatherSnapshotPixels = 0;
+    int gatherParity = 0;
+    bool gatherInFlight = false, snapshotBusy[2] = {false, false};
+    unsigned char *imageBlock = nullptr; // pixels | denoiserAlbedo | denoiserNormal | preview | dirtyPixels in one allocation
 
     flx_RenderParams params;
     bool paramsSet = false;
@@ -161,6 +174,7 @@ struct flx_ctx
     int traceBlocksPerSM = 0; // 0: occupancy calculator
     int numSMs = 148;
     int maxDynSmem = 48 * 1024;
+    int occExt[3] = {0, 0, 0}, occShadow[3] = {0, 0, 0}; // resident CTAs per SM of the persistent kernels (min-blocks 8, 9, 10), asked once
     uint32_t *fetchCounters = nullptr; // [0] extension, [1] shadow, [2] microkernel nextVertex, [3] microkernel light samples
 
     // microkernel integrator (flx_mk.cuh), allocated on first use
@@ -325,14 +339,21 @@ struct Timed
 
 void drainEvents(flx_ctx *c)
 {
+    std::vector<EventPair> notReady; // e.g. a gather still running on its own stream: asked again at the next drain
     for (auto &e : c->pendingEvents)
     {
         float ms = 0.0f;
-        if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess)
+        const cudaError_t r = cudaEventElapsedTime(&ms, e.a, e.b);
+        if (r == cudaErrorNotReady)
+        {
+            notReady.push_back(e);
+            continue;
+        }
+        if (r == cudaSuccess)
             c->kernelMs[e.kernel] += ms;
         c->freeEvents.push_back(e);
     }
-    c->pendingEvents.clear();
+    c->pendingEvents.swap(notReady);
 }
 
 int flushPending(flx_ctx *ctx);
@@ -381,6 +402,36 @@ void markPixelsWritten(flx_ctx *ctx)
 
 unsigned streamingGrid(uint32_t n) { return std::max(1u, std::min((n + FLX_BLOCK - 1) / FLX_BLOCK, 148u * 16u)); }
 
+// Depth of the deepest leaf (root = 0).  Links only go forward in the reference's depth-first layout, so one pass from the front
+// sees every parent before its children.  The traversal stack holds FLX_STACK_DEPTH entries (reference: uint stack[64],
+// src/bvh.cl:240) and a ray at a leaf of depth d can have d entries pending, so a deeper tree would overrun it: the in-repo
+// builders stop at 62, a caller's array or an imported cache file (flx_hierarchy_import) is checked here.  Assumes the links
+// were range-checked (child > parent) by the caller.
+uint32_t hierarchyDepth(const flx_Node *nodes, uint32_t nNodes)
+{
+    std::vector<uint16_t> depth(nNodes, 0);
+    uint32_t deepest = 0;
+    for (uint32_t i = 0; i < nNodes; i++)
+    {
+        if (nodes[i].nPrims != 0)
+            continue;
+        const uint32_t d = std::min<uint32_t>(depth[i] + 1u, 0xffffu);
+        depth[i + 1] = (uint16_t)d;
+        depth[nodes[i].iStartOrRightChild] = (uint16_t)d;
+        deepest = std::max(deepest, d);
+    }
+    return deepest;
+}
+
+// every triangle's material index against the material count, on the device copy (reading 160-byte records on the host just for
+// one int each costs more than the whole upload); error = first offending triangle + 1
+__global__ void __launch_bounds__(256) k_validate_triangles(const flx_Triangle *tris, uint32_t nTris, uint32_t nMaterials, uint32_t *error)
+{
+    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    if (i < nTris && (tris[i].matId < 0 || (uint32_t)tris[i].matId >= nMaterials))
+        atomicMin(error, i + 1u);
+}
+
 // ---- BVH repack: reference Node[] (48 B, DFS, left = self + 1) + indices + Triangle[] (160 B)
 //      -> TNode[] (64 B, inner nodes only) + TTri[] (48 B per leaf reference). See flx_trace.cuh.
 struct Repacked
@@ -417,6 +468,8 @@ int repackBvh(flx_ctx *ctx, const flx_Triangle *tris, uint32_t nTris, const uint
             nLeafTris += n;
         }
     }
+    if (const uint32_t deep = hierarchyDepth(nodes, nNodes); deep > FLX_STACK_DEPTH)
+        return fail(ctx, FLX_E_INVALID, "hierarchy is %u levels deep; the traversal stack holds %d entries (reference: uint stack[64], bvh.cl:240)", deep, FLX_STACK_DEPTH);
     // pass 2: number the inner nodes -- first a treelet grown from the root by always taking the pending node with the
     // largest box area (the nodes a random ray is most likely to visit; any prefix of this order is a connected
     // top-of-tree, which is what the TOP traversal variant stages in shared memory), then everything else in DFS order.
@@ -519,16 +572,19 @@ template <class T> int uploadArray(flx_ctx *ctx, T *&dst, const T *src, size_t c
     freeDev(dst);
     const size_t bytes = std::max(count, minCount) * sizeof(T);
     CU(cudaMalloc(&dst, bytes));
+    // On the context's stream (the work streams are cudaStreamNonBlocking: the legacy default stream does not order against
+    // them).  A pinned source (flx_host_alloc) goes by DMA at link speed; a pageable one is staged by the driver before the call
+    // returns.  Callers synchronise the stream before they return, so the source is borrowed for the call only.
     if (bytes > count * sizeof(T))
-        CU(cudaMemset(reinterpret_cast<unsigned char *>(dst) + count * sizeof(T), 0, bytes - count * sizeof(T)));
+        CU(cudaMemsetAsync(reinterpret_cast<unsigned char *>(dst) + count * sizeof(T), 0, bytes - count * sizeof(T), ctx->stream));
     if (count)
-        CU(cudaMemcpy(dst, src, count * sizeof(T), cudaMemcpyHostToDevice));
+        CU(cudaMemcpyAsync(dst, src, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
     ctx->sceneBytes += bytes;
     return 0;
 }
 
 // flx_bvh_repack.cuh driven from the host: nodes / indices go up as they are, the traversal layout is made on the device
-int repackOnDevice(flx_ctx *ctx, const uint32_t *indices, uint32_t nIndices, const flx_Node *nodes, uint32_t nNodes, uint32_t nTris)
+int repackOnDevice(flx_ctx *ctx, const uint32_t *indices, uint32_t nIndices, const flx_Node *nodes, uint32_t nNodes, uint32_t nTris, uint32_t nMaterials)
 {
     // sizes and the treelet come from one cheap pass over the host nodes
     size_t nInner = 0, nLeafTris = 0;
@@ -546,6 +602,8 @@ int repackOnDevice(flx_ctx *ctx, const uint32_t *indices, uint32_t nIndices, con
     }
     if (nLeafTris > 0x7ffffff0u)
         return fail(ctx, FLX_E_INVALID, "too many leaf references");
+    if (const uint32_t deep = hierarchyDepth(nodes, nNodes); deep > FLX_STACK_DEPTH)
+        return fail(ctx, FLX_E_INVALID, "hierarchy is %u levels deep; the traversal stack holds %d entries (reference: uint stack[64], bvh.cl:240)", deep, FLX_STACK_DEPTH);
     const std::vector<uint32_t> treelet = pickTreelet(nodes, nNodes);
 
     // one allocation for all temporaries (cudaMalloc / cudaFree are the expensive part of a small job like this)
@@ -572,7 +630,7 @@ int repackOnDevice(flx_ctx *ctx, const uint32_t *indices, uint32_t nIndices, con
     uint32_t *dFlag = reinterpret_cast<uint32_t *>(take(szPerNode)), *dPrims = reinterpret_cast<uint32_t *>(take(szPerNode));
     uint32_t *dScanI = reinterpret_cast<uint32_t *>(take(szPerNode)), *dScanL = reinterpret_cast<uint32_t *>(take(szPerNode));
     void *dTemp = take(szScan);
-    uint32_t *dError = reinterpret_cast<uint32_t *>(take(256));
+    uint32_t *dError = reinterpret_cast<uint32_t *>(take(256)); // [0] hierarchy error, [1] first triangle with a bad material + 1
     freeDev(ctx->tnodes);
     freeDev(ctx->ttris);
     const size_t nodeBytes = std::max<size_t>(nInner, 1) * 64, triBytes = std::max<size_t>(nLeafTris, 1) * 64;
@@ -586,6 +644,7 @@ int repackOnDevice(flx_ctx *ctx, const uint32_t *indices, uint32_t nIndices, con
             cu(cudaMemcpyAsync(dTreelet, treelet.data(), treelet.size() * 4, cudaMemcpyHostToDevice, st), "treelet upload");
         cu(cudaMemsetAsync(dPos, 0xff, (size_t)nNodes * 4, st), "memset");
         cu(cudaMemsetAsync(dError, 0, 4, st), "memset");
+        cu(cudaMemsetAsync(dError + 1, 0xff, 4, st), "memset");
         if (nInner == 0)
             cu(cudaMemsetAsync(ctx->tnodes, 0, nodeBytes, st), "memset"); // every record is written by k_repack_emit otherwise
     }
@@ -603,10 +662,14 @@ int repackOnDevice(flx_ctx *ctx, const uint32_t *indices, uint32_t nIndices, con
         cu(cub::DeviceScan::ExclusiveSum(dTemp, tempBytes, dFlag, dScanI, (int)nNodes, st), "scan");
         cu(cub::DeviceScan::ExclusiveSum(dTemp, tempBytes, dPrims, dScanL, (int)nNodes, st), "scan");
         k_repack_emit<<<grid, 256, 0, st>>>(r);
+        k_validate_triangles<<<(nTris + 255) / 256, 256, 0, st>>>(ctx->tris, nTris, nMaterials, dError + 1);
         cu(cudaGetLastError(), "repack launch");
-        uint32_t err = 0;
-        cu(cudaMemcpyAsync(&err, dError, 4, cudaMemcpyDeviceToHost, st), "error read-back");
+        uint32_t errs[2] = {0, 0xffffffffu};
+        cu(cudaMemcpyAsync(errs, dError, 8, cudaMemcpyDeviceToHost, st), "error read-back");
         cu(cudaStreamSynchronize(st), "repack");
+        const uint32_t err = errs[0];
+        if (rc == 0 && errs[1] != 0xffffffffu)
+            rc = fail(ctx, FLX_E_INVALID, "triangle %u has a material index outside the %u uploaded", errs[1] - 1u, nMaterials);
         if (rc == 0 && err)
         {
             const uint32_t kind = err >> 28, node = (err & 0x0fffffffu) - 1u;
@@ -680,8 +743,16 @@ template <bool ANYHIT, class COUNT, int MINB, int SDEPTH> static int launchPersi
     if (SDEPTH == 0 && ctx->maxL1) // the L1 is what this kernel lives on: ask for the largest L1 carve-out
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1));
     int perSM = ctx->traceBlocksPerSM;
+    // the production instantiation (no counters, local-memory stack) asks the occupancy calculator once per context
+    int *cached = (std::is_same<COUNT, NoCount>::value && SDEPTH == 0 && !ctx->maxL1) ? &(ANYHIT ? ctx->occShadow : ctx->occExt)[MINB - 8] : nullptr;
+    if (perSM <= 0 && cached && *cached > 0)
+        perSM = *cached;
     if (perSM <= 0)
+    {
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, FLX_TRACE_BLOCK, smem));
+        if (cached)
+            *cached = perSM;
+    }
     const unsigned grid = (unsigned)std::max(1, perSM) * (unsigned)ctx->numSMs;
     kern<<<grid, FLX_TRACE_BLOCK, smem, ctx->cur>>>(makeFrame(ctx), ctx->params, makeBvh(ctx), ctx->tris, fetch, ctx->fetchThreshold, ctx->innerMin, ctx->fetchChunk, 0, counts, MkView{});
     return 0;
@@ -812,7 +883,53 @@ template <bool ANYHIT> static int launchMkTrace(flx_ctx *ctx, const MkView &mk)
     return launchCheck(ctx, ANYHIT ? "k_trace_persistent<mk light samples>" : "k_trace_persistent<mk nextVertex>");
 }
 
+// With lazy module loading (the CUDA default) a kernel's code is loaded at its first launch, i.e. inside whatever the caller is
+// timing.  The reference builds all its kernels in CLContext's constructor (clcontext.cpp:18-69); the analogue here is to touch
+// every kernel of the default render loop once when the context is created.
+static void preloadKernels()
+{
+    cudaFuncAttributes a;
+#define PRELOAD(k) cudaFuncGetAttributes(&a, k)
+    PRELOAD(k_reset);
+    PRELOAD(k_raygen);
+    PRELOAD((k_trace_persistent<false, NoCount, FLX_TRACE_BLOCK, false, 9, 0>));
+    PRELOAD((k_trace_persistent<true, NoCount, FLX_TRACE_BLOCK, false, 10, 0>));
+    PRELOAD((k_logic<false, 3, 2>));
+    PRELOAD((k_logic<true, 3, 1>));
+    PRELOAD((k_logic<false, 3, 0>));
+    PRELOAD((k_logic<true, 3, 0>));
+    constexpr int ALL = FLX_BXDF_DIFFUSE | FLX_BXDF_GLOSSY | FLX_BXDF_GGX_ROUGH_REFLECTION | FLX_BXDF_IDEAL_REFLECTION | FLX_BXDF_GGX_ROUGH_DIELECTRIC |
+                        FLX_BXDF_IDEAL_DIELECTRIC | FLX_BXDF_EMISSIVE;
+    PRELOAD(k_material<ALL>);
+    PRELOAD(k_material<FLX_BXDF_DIFFUSE>);
+    PRELOAD(k_material<FLX_BXDF_GLOSSY>);
+    PRELOAD(k_material<FLX_BXDF_GGX_ROUGH_REFLECTION>);
+    PRELOAD(k_material<FLX_BXDF_GGX_ROUGH_DIELECTRIC>);
+    PRELOAD((k_material<FLX_BXDF_IDEAL_REFLECTION | FLX_BXDF_IDEAL_DIELECTRIC>));
+    PRELOAD(k_postprocess);
+    PRELOAD(k_snapshot_counters);
+    PRELOAD(k_end_iteration);
+    PRELOAD(k_repack_scatter_treelet);
+    PRELOAD(k_repack_flags);
+    PRELOAD(k_repack_emit);
+    PRELOAD(k_validate_triangles);
+#undef PRELOAD
+    cudaGetLastError();
+}
+
 // ================================================================================================ C ABI
+// No C++ exception may cross the C ABI (std::bad_alloc from a host-side staging vector would otherwise end in std::terminate in
+// the caller's process): every int-returning entry point is a function-try-block that turns it into an error code + message.
+#define FLX_API_CATCH(c)                                                                                               \
+    catch (const std::exception &e_)                                                                                   \
+    {                                                                                                                  \
+        return fail((c), FLX_E_INVALID, "out of memory or internal error: %s", e_.what());                             \
+    }                                                                                                                  \
+    catch (...)                                                                                                        \
+    {                                                                                                                  \
+        return fail((c), FLX_E_INVALID, "internal error");                                                             \
+    }
+
 extern "C"
 {
 const char *flx_version(void) { return "fluctus_b200 0.1 (sm_100a)"; }
@@ -820,6 +937,7 @@ const char *flx_version(void) { return "fluctus_b200 0.1 (sm_100a)"; }
 const char *flx_last_error(const flx_ctx *ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
 
 int flx_create(int device, uint32_t num_tasks, flx_ctx **out)
+try
 {
     flx_ctx *ctx = nullptr; // for the CU/REQUIRE macros: errors land in the thread-local create message
     if (!out || num_tasks == 0)
@@ -908,11 +1026,13 @@ int flx_create(int device, uint32_t num_tasks, flx_ctx **out)
     CUB(cudaMemset(c->probTable, 0, sizeof(float)));
     CUB(cudaMemset(c->pdfTable, 0, sizeof(float)));
     CUB(cudaMemset(c->aliasTable, 0, sizeof(int32_t)));
+    preloadKernels();
     CUB(cudaStreamSynchronize(c->stream));
 #undef CUB
     *out = c;
     return 0;
 }
+FLX_API_CATCH((flx_ctx *)nullptr)
 
 void flx_destroy(flx_ctx *c)
 {
@@ -922,6 +1042,8 @@ void flx_destroy(flx_ctx *c)
     c->pendingStages = 0; // deferred stages nobody asked the result of
     if (c->stream)
         cudaStreamSynchronize(c->stream);
+    if (c->gatherStream)
+        cudaStreamSynchronize(c->gatherStream);
     flx_comm_destroy(c);
     drainEvents(c);
     for (auto &e : c->freeEvents)
@@ -964,13 +1086,19 @@ void flx_destroy(flx_ctx *c)
     freeDev(c->probTable);
     freeDev(c->pdfTable);
     freeDev(c->aliasTable);
-    freeDev(c->pixels);
-    freeDev(c->denoiserAlbedo);
-    freeDev(c->denoiserNormal);
-    freeDev(c->preview);
-    freeDev(c->dirtyPixels);
+    freeDev(c->imageBlock);
     freeDev(c->gatherBuf);
     freeDev(c->fullImage);
+    freeDev(c->gatherSnapshot);
+    if (c->evSnapshot)
+        cudaEventDestroy(c->evSnapshot);
+    if (c->evGatherDone)
+        cudaEventDestroy(c->evGatherDone);
+    for (cudaEvent_t e : c->evSnapshotFree)
+        if (e)
+            cudaEventDestroy(e);
+    if (c->gatherStream)
+        cudaStreamDestroy(c->gatherStream);
     if (c->evFork)
         cudaEventDestroy(c->evFork);
     if (c->evJoin)
@@ -993,6 +1121,28 @@ void flx_destroy(flx_ctx *c)
 uint32_t flx_num_tasks(const flx_ctx *ctx) { return ctx ? ctx->numTasks : 0; }
 uint32_t flx_tile_pixels(const flx_ctx *ctx) { return ctx ? ctx->tilePixels : 0; }
 
+// Page-locked host memory for the arrays a caller hands to flx_upload_scene / receives from flx_read_pixels: those copies then
+// go by DMA at link speed instead of through the driver's staging buffer (the reference's analogue: the GL pixel-buffer object
+// its kernels write the picture into, clcontext.cpp:326-384 -- no pageable host copy there either).
+int flx_host_alloc(void **out, size_t bytes)
+try
+{
+    if (!out || bytes == 0)
+        return fail(nullptr, FLX_E_INVALID, "flx_host_alloc: bad arguments");
+    *out = nullptr;
+    const cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess)
+        return fail(nullptr, (int)e, "flx_host_alloc: cudaHostAlloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    return 0;
+}
+FLX_API_CATCH((flx_ctx *)nullptr)
+
+void flx_host_free(void *p)
+{
+    if (p)
+        cudaFreeHost(p);
+}
+
 size_t flx_device_bytes(const flx_ctx *ctx)
 {
     if (!ctx)
@@ -1000,19 +1150,36 @@ size_t flx_device_bytes(const flx_ctx *ctx)
     return (size_t)ctx->numTasks * (FLX_NUM_SLOTS + 8) * 4 + ctx->sceneBytes + (size_t)ctx->tilePixels * 48;
 }
 
+static int uploadSceneImpl(flx_ctx *ctx, const flx_Triangle *tris, uint32_t n_tris, const uint32_t *indices, uint32_t n_indices, const flx_Node *nodes,
+                           uint32_t n_nodes, const flx_Material *materials, uint32_t n_materials, const flx_TexDescriptor *tex_desc, uint32_t n_tex,
+                           const uint8_t *tex_data, size_t tex_bytes);
+
 int flx_upload_scene(flx_ctx *ctx, const flx_Triangle *tris, uint32_t n_tris, const uint32_t *indices, uint32_t n_indices, const flx_Node *nodes,
                      uint32_t n_nodes, const flx_Material *materials, uint32_t n_materials, const flx_TexDescriptor *tex_desc, uint32_t n_tex,
                      const uint8_t *tex_data, size_t tex_bytes)
+try
 {
     if (!ctx)
         return FLX_E_INVALID;
     TOUCH(ctx);
+    const int rc = uploadSceneImpl(ctx, tris, n_tris, indices, n_indices, nodes, n_nodes, materials, n_materials, tex_desc, n_tex, tex_data, tex_bytes);
+    if (rc) // the copies are asynchronous: whatever was enqueued before the failure must be done with the caller's arrays
+        cudaStreamSynchronize(ctx->stream);
+    return rc;
+}
+FLX_API_CATCH(ctx)
+
+static int uploadSceneImpl(flx_ctx *ctx, const flx_Triangle *tris, uint32_t n_tris, const uint32_t *indices, uint32_t n_indices, const flx_Node *nodes,
+                           uint32_t n_nodes, const flx_Material *materials, uint32_t n_materials, const flx_TexDescriptor *tex_desc, uint32_t n_tex,
+                           const uint8_t *tex_data, size_t tex_bytes)
+{
     REQUIRE(tris && indices && nodes && materials, "flx_upload_scene: null array");
     REQUIRE(n_tris > 0 && n_indices > 0 && n_nodes > 0 && n_materials > 0, "flx_upload_scene: empty scene");
     REQUIRE(n_tex == 0 || (tex_desc && tex_data), "flx_upload_scene: texture descriptors without data");
-    for (uint32_t i = 0; i < n_tris; i++)
-        if (tris[i].matId < 0 || (uint32_t)tris[i].matId >= n_materials)
-            return fail(ctx, FLX_E_INVALID, "triangle %u has material %d of %u", i, tris[i].matId, n_materials);
+    if (ctx->repackOnHost) // the device repack checks the material indices on the device copy (k_validate_triangles)
+        for (uint32_t i = 0; i < n_tris; i++)
+            if (tris[i].matId < 0 || (uint32_t)tris[i].matId >= n_materials)
+                return fail(ctx, FLX_E_INVALID, "triangle %u has a material index outside the %u uploaded", i, n_materials);
     for (uint32_t i = 0; i < n_materials; i++)
     {
         const int maps[3] = {materials[i].map_Kd, materials[i].map_Ks, materials[i].map_N};
@@ -1024,6 +1191,25 @@ int flx_upload_scene(flx_ctx *ctx, const flx_Triangle *tris, uint32_t n_tris, co
         if ((size_t)tex_desc[i].offset + (size_t)tex_desc[i].width * tex_desc[i].height * 4 > tex_bytes || (tex_desc[i].offset & 3u) || tex_desc[i].width == 0 ||
             tex_desc[i].height == 0)
             return fail(ctx, FLX_E_INVALID, "texture %u: descriptor outside the %zu-byte blob", i, tex_bytes);
+    {
+        // Cheap fingerprint for flx_checkpoint_save / _load: the sizes, every material, and a sample of nodes and triangles
+        // (hashing the ~60 MB of a scene in full would cost more than uploading it).
+        uint64_t hsh = 14695981039346656037ull;
+        const uint32_t sizes[5] = {n_tris, n_indices, n_nodes, n_materials, n_tex};
+        hsh = hsh * 1099511628211ull ^ 0;
+        for (uint32_t v : sizes)
+            hsh = (hsh ^ v) * 1099511628211ull;
+        for (uint32_t i = 0; i < n_materials; i++)
+            for (size_t b = 0; b < 72; b++) // up to and including `type`; the struct's tail is padding
+                hsh = (hsh ^ reinterpret_cast<const unsigned char *>(materials + i)[b]) * 1099511628211ull;
+        for (uint32_t i = 0; i < n_nodes; i += std::max(1u, n_nodes / 512u))
+            for (size_t b = 0; b < 41; b++)
+                hsh = (hsh ^ reinterpret_cast<const unsigned char *>(nodes + i)[b]) * 1099511628211ull;
+        for (uint32_t i = 0; i < n_tris; i += std::max(1u, n_tris / 512u))
+            for (size_t b = 0; b < 12; b++)
+                hsh = (hsh ^ reinterpret_cast<const unsigned char *>(&tris[i].v0.p)[b]) * 1099511628211ull;
+        ctx->sceneHash = hsh;
+    }
     const bool timing = std::getenv("FLX_DEBUG_TIMING") != nullptr; // prints where the upload's wall time goes
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
@@ -1063,7 +1249,7 @@ int flx_upload_scene(flx_ctx *ctx, const flx_Triangle *tris, uint32_t n_tris, co
     ctx->nTris = n_tris;
     if (!ctx->repackOnHost)
     {
-        if ((rc = repackOnDevice(ctx, indices, n_indices, nodes, n_nodes, n_tris)))
+        if ((rc = repackOnDevice(ctx, indices, n_indices, nodes, n_nodes, n_tris, n_materials)))
             return rc;
         ctx->sceneReady = true;
         if (ctx->l2Persist && (rc = applyL2Persist(ctx)))
@@ -1080,6 +1266,7 @@ int flx_upload_scene(flx_ctx *ctx, const flx_Triangle *tris, uint32_t n_tris, co
     ctx->nTNodes = (uint32_t)(rp.nodes.size() / 4);
     ctx->nTTris = (uint32_t)(rp.tris.size() / 4);
     ctx->treeletNodes = rp.treeletNodes;
+    CU(cudaStreamSynchronize(ctx->stream)); // the copies above borrow the caller's (and this function's) host arrays
     ctx->sceneReady = true;
     if (ctx->l2Persist && (rc = applyL2Persist(ctx)))
         return rc;
@@ -1092,6 +1279,7 @@ int flx_upload_scene(flx_ctx *ctx, const flx_Triangle *tris, uint32_t n_tris, co
 // (src/scene.cpp:574-590, src/sbvh.cpp:4-73) when build time matters more than tree quality
 int flx_build_bvh(flx_ctx *ctx, const flx_Triangle *tris, uint32_t n_tris, uint32_t max_leaf, int quality, flx_Node *nodes_out, uint32_t nodes_capacity,
                   uint32_t *n_nodes_out, uint32_t *indices_out, float *build_ms)
+try
 {
     if (!ctx)
         return FLX_E_INVALID;
@@ -1278,8 +1466,10 @@ int flx_build_bvh(flx_ctx *ctx, const flx_Triangle *tris, uint32_t n_tris, uint3
     release();
     return rc;
 }
+FLX_API_CATCH(ctx)
 
 int flx_upload_envmap(flx_ctx *ctx, const float *rgb, int32_t w, int32_t h, const float *prob, const int32_t *alias, const float *pdf)
+try
 {
     if (!ctx)
         return FLX_E_INVALID;
@@ -1310,10 +1500,12 @@ int flx_upload_envmap(flx_ctx *ctx, const float *rgb, int32_t w, int32_t h, cons
     if ((rc = uploadArray(ctx, ctx->pdfTable, pdf, n)))
         return rc;
     (void)before;
+    CU(cudaStreamSynchronize(ctx->stream));
     ctx->envW = w;
     ctx->envH = h;
     return 0;
 }
+FLX_API_CATCH(ctx)
 
 static int allocImage(flx_ctx *ctx)
 {
@@ -1322,29 +1514,36 @@ static int allocImage(flx_ctx *ctx)
     ctx->tilePixels = rows * ctx->width;
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
-    freeDev(ctx->pixels);
-    freeDev(ctx->denoiserAlbedo);
-    freeDev(ctx->denoiserNormal);
-    freeDev(ctx->preview);
-    freeDev(ctx->dirtyPixels);
+    if (ctx->gatherStream)
+        CU(cudaStreamSynchronize(ctx->gatherStream));
+    ctx->gatherInFlight = false;
+    freeDev(ctx->imageBlock);
+    ctx->pixels = ctx->denoiserAlbedo = ctx->denoiserNormal = ctx->preview = nullptr;
+    ctx->dirtyPixels = nullptr;
+    // the gather buffers are sized for an image and a tiling: a new image or tiling starts from none
+    freeDev(ctx->gatherBuf);
+    freeDev(ctx->fullImage);
+    freeDev(ctx->gatherSnapshot);
+    ctx->gatherBufPixels = ctx->fullImagePixels = ctx->gatherSnapshotPixels = 0;
+    ctx->snapshotBusy[0] = ctx->snapshotBusy[1] = false;
     ctx->previewStale = true;
     if (ctx->tilePixels == 0)
         return fail(ctx, FLX_E_INVALID, "tile %u of %u owns no rows of a %ux%u image", ctx->part, ctx->nParts, ctx->width, ctx->height);
+    // one allocation, two asynchronous fills (the reference makes three buffers + two GL PBOs, clcontext.cpp:326-384)
     const size_t bytes = (size_t)ctx->tilePixels * 4 * sizeof(float);
-    CU(cudaMalloc(&ctx->pixels, bytes));
-    CU(cudaMalloc(&ctx->denoiserAlbedo, bytes));
-    CU(cudaMalloc(&ctx->denoiserNormal, bytes));
-    CU(cudaMalloc(&ctx->preview, bytes));
-    CU(cudaMalloc(&ctx->dirtyPixels, ctx->tilePixels));
-    CU(cudaMemset(ctx->dirtyPixels, 1, ctx->tilePixels));
-    CU(cudaMemset(ctx->preview, 0, bytes));
-    CU(cudaMemset(ctx->pixels, 0, bytes));
-    CU(cudaMemset(ctx->denoiserAlbedo, 0, bytes));
-    CU(cudaMemset(ctx->denoiserNormal, 0, bytes));
+    CU(cudaMalloc(&ctx->imageBlock, 4 * bytes + ctx->tilePixels));
+    ctx->pixels = reinterpret_cast<float *>(ctx->imageBlock);
+    ctx->denoiserAlbedo = reinterpret_cast<float *>(ctx->imageBlock + bytes);
+    ctx->denoiserNormal = reinterpret_cast<float *>(ctx->imageBlock + 2 * bytes);
+    ctx->preview = reinterpret_cast<float *>(ctx->imageBlock + 3 * bytes);
+    ctx->dirtyPixels = ctx->imageBlock + 4 * bytes;
+    CU(cudaMemsetAsync(ctx->imageBlock, 0, 4 * bytes, ctx->stream));
+    CU(cudaMemsetAsync(ctx->dirtyPixels, 1, ctx->tilePixels, ctx->stream));
     return 0;
 }
 
 int flx_resize(flx_ctx *ctx, uint32_t width, uint32_t height)
+try
 {
     if (!ctx)
         return FLX_E_INVALID;
@@ -1354,8 +1553,10 @@ int flx_resize(flx_ctx *ctx, uint32_t width, uint32_t height)
     ctx->height = height;
     return allocImage(ctx);
 }
+FLX_API_CATCH(ctx)
 
 int flx_set_tile(flx_ctx *ctx, uint32_t part, uint32_t n_parts, uint32_t stripe_rows)
+try
 {
     if (!ctx)
         return FLX_E_INVALID;
@@ -1368,8 +1569,10 @@ int flx_set_tile(flx_ctx *ctx, uint32_t part, uint32_t n_parts, uint32_t stripe_
         return allocImage(ctx);
     return 0;
 }
+FLX_API_CATCH(ctx)
 
 int flx_update_params(flx_ctx *ctx, const flx_RenderParams *p)
+try
 {
     if (!ctx)
         return FLX_E_INVALID;
@@ -1385,8 +1588,10 @@ int flx_update_params(flx_ctx *ctx, const flx_RenderParams *p)
     ctx->paramsSet = true;
     return 0;
 }
+FLX_API_CATCH(ctx)
 
 int flx_enqueue_reset(flx_ctx *ctx)
+try
 {
     int rc = checkReady(ctx, false, true);
     if (rc)
@@ -1398,6 +1603,7 @@ int flx_enqueue_reset(flx_ctx *ctx)
     markPixelsWritten(ctx);
     return launchCheck(ctx, "k_reset");
 }
+FLX_API_CATCH(ctx)
 
 static int launchRaygen(flx_ctx *ctx)
 {
@@ -1407,6 +1613,7 @@ static int launchRaygen(flx_ctx *ctx)
 }
 
 int flx_enqueue_raygen(flx_ctx *ctx)
+try
 {
     const bool afterLogic = ctx && ctx->pendingStages == 1;
     int rc = checkReady(ctx, false, true, afterLogic);
@@ -1420,8 +1627,10 @@ int flx_enqueue_raygen(flx_ctx *ctx)
     CU(cudaSetDevice(ctx->device));
     return launchRaygen(ctx);
 }
+FLX_API_CATCH(ctx)
 
 int flx_enqueue_extrays(flx_ctx *ctx)
+try
 {
     int rc = checkReady(ctx, true, true);
     if (rc)
@@ -1440,6 +1649,7 @@ int flx_enqueue_extrays(flx_ctx *ctx)
         k_extrays<NoCount><<<grid, FLX_TRACE_BLOCK, 0, ctx->cur>>>(makeFrame(ctx), ctx->params, makeBvh(ctx), ctx->tris, nullptr);
     return launchCheck(ctx, "k_extrays");
 }
+FLX_API_CATCH(ctx)
 
 static int launchShadow(flx_ctx *ctx)
 {
@@ -1455,6 +1665,7 @@ static int launchShadow(flx_ctx *ctx)
 }
 
 int flx_enqueue_shadowrays(flx_ctx *ctx)
+try
 {
     int rc = checkReady(ctx, true, true);
     if (rc)
@@ -1474,6 +1685,7 @@ int flx_enqueue_shadowrays(flx_ctx *ctx)
     CU(cudaStreamWaitEvent(ctx->stream, ctx->evJoin, 0));
     return 0;
 }
+FLX_API_CATCH(ctx)
 
 static int launchMaterials(flx_ctx *ctx);
 // wf_logic alone, or (fused) wf_logic + wf_raygen + wf_mat_* in one pass over the path state (k_logic<.., FUSE>)
@@ -1530,6 +1742,7 @@ static int launchLogic(flx_ctx *ctx, int first_iteration, bool fused)
 }
 
 int flx_enqueue_logic(flx_ctx *ctx, int first_iteration)
+try
 {
     int rc = checkReady(ctx, true, true);
     if (rc)
@@ -1543,6 +1756,7 @@ int flx_enqueue_logic(flx_ctx *ctx, int first_iteration)
     }
     return launchLogic(ctx, first_iteration, false);
 }
+FLX_API_CATCH(ctx)
 
 extern "C++"
 {
@@ -1564,6 +1778,7 @@ int flushPending(flx_ctx *ctx)
 } // extern "C++"
 
 int flx_enqueue_materials(flx_ctx *ctx)
+try
 {
     const bool completesIteration = ctx && ctx->pendingStages == 2;
     int rc = checkReady(ctx, true, true, completesIteration);
@@ -1577,6 +1792,7 @@ int flx_enqueue_materials(flx_ctx *ctx)
     }
     return launchMaterials(ctx);
 }
+FLX_API_CATCH(ctx)
 
 static int launchMaterials(flx_ctx *ctx)
 {
@@ -1610,6 +1826,7 @@ static int launchMaterials(flx_ctx *ctx)
 
 // ---- microkernel integrator (CLContext::enqueueResetKernel ... enqueueSplatPreviewKernel, clcontext.cpp:709-750)
 int flx_enqueue_mk_reset(flx_ctx *ctx)
+try
 {
     int rc = checkReady(ctx, false, true);
     if (rc || (rc = ensureMk(ctx)))
@@ -1621,8 +1838,10 @@ int flx_enqueue_mk_reset(flx_ctx *ctx)
     markPixelsWritten(ctx);
     return launchCheck(ctx, "k_mk_reset");
 }
+FLX_API_CATCH(ctx)
 
 int flx_enqueue_mk_raygen(flx_ctx *ctx)
+try
 {
     int rc = checkReady(ctx, false, true);
     if (rc || (rc = ensureMk(ctx)))
@@ -1633,8 +1852,10 @@ int flx_enqueue_mk_raygen(flx_ctx *ctx)
     k_mk_raygen<<<mkGrid(mk.limit), FLX_BLOCK, 0, ctx->stream>>>(makeFrame(ctx), ctx->params, mk.limit);
     return launchCheck(ctx, "k_mk_raygen");
 }
+FLX_API_CATCH(ctx)
 
 int flx_enqueue_mk_next_vertex(flx_ctx *ctx)
+try
 {
     int rc = checkReady(ctx, true, true);
     if (rc || (rc = ensureMk(ctx)))
@@ -1647,8 +1868,10 @@ int flx_enqueue_mk_next_vertex(flx_ctx *ctx)
     k_mk_next_vertex_logic<<<mkGrid(mk.limit), FLX_BLOCK, 0, ctx->stream>>>(makeFrame(ctx), ctx->params, makeScene(ctx), mk);
     return launchCheck(ctx, "k_mk_next_vertex_logic");
 }
+FLX_API_CATCH(ctx)
 
 int flx_enqueue_mk_sample_bsdf(flx_ctx *ctx)
+try
 {
     int rc = checkReady(ctx, true, true);
     if (rc || (rc = ensureMk(ctx)))
@@ -1685,8 +1908,10 @@ int flx_enqueue_mk_sample_bsdf(flx_ctx *ctx)
         k_mk_shade<ALL><<<grid, FLX_BLOCK, 0, ctx->stream>>>(fr, ctx->params, sc, mk, MK_L_OTHER);
     return launchCheck(ctx, "k_mk_shade");
 }
+FLX_API_CATCH(ctx)
 
 int flx_enqueue_mk_splat(flx_ctx *ctx)
+try
 {
     int rc = checkReady(ctx, false, true);
     if (rc || (rc = ensureMk(ctx)))
@@ -1698,8 +1923,10 @@ int flx_enqueue_mk_splat(flx_ctx *ctx)
     markPixelsWritten(ctx);
     return launchCheck(ctx, "k_mk_splat");
 }
+FLX_API_CATCH(ctx)
 
 int flx_enqueue_mk_splat_preview(flx_ctx *ctx)
+try
 {
     int rc = checkReady(ctx, false, true);
     if (rc || (rc = ensureMk(ctx)))
@@ -1711,10 +1938,12 @@ int flx_enqueue_mk_splat_preview(flx_ctx *ctx)
     markPixelsWritten(ctx);
     return launchCheck(ctx, "k_mk_splat_preview");
 }
+FLX_API_CATCH(ctx)
 
 // Tracer::renderSingle's loop (tracer.cpp:124-150), spp times, no host round trips: camera rays, (maxBounces + 1) x
 // (nextVertex, sampleBsdf), splat, display pass.
 int flx_render_single(flx_ctx *ctx, uint32_t spp)
+try
 {
     int rc = checkReady(ctx, true, true);
     if (rc)
@@ -1735,6 +1964,7 @@ int flx_render_single(flx_ctx *ctx, uint32_t spp)
     }
     return 0;
 }
+FLX_API_CATCH(ctx)
 
 static int launchPostprocess(flx_ctx *ctx)
 {
@@ -1748,6 +1978,7 @@ static int launchPostprocess(flx_ctx *ctx)
 }
 
 int flx_enqueue_postprocess(flx_ctx *ctx)
+try
 {
     int rc = checkReady(ctx, false, true);
     if (rc)
@@ -1768,8 +1999,10 @@ int flx_enqueue_postprocess(flx_ctx *ctx)
     CU(cudaStreamWaitEvent(ctx->stream, ctx->evPostJoin, 0));
     return 0;
 }
+FLX_API_CATCH(ctx)
 
 int flx_read_preview(flx_ctx *ctx, float *rgba, size_t n_pixels)
+try
 {
     if (!ctx)
         return FLX_E_INVALID;
@@ -1781,8 +2014,10 @@ int flx_read_preview(flx_ctx *ctx, float *rgba, size_t n_pixels)
     CU(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
+FLX_API_CATCH(ctx)
 
 int flx_enqueue_clear_queues(flx_ctx *ctx)
+try
 {
     if (!ctx)
         return FLX_E_INVALID;
@@ -1791,8 +2026,10 @@ int flx_enqueue_clear_queues(flx_ctx *ctx)
     CU(cudaMemsetAsync(ctx->counters, 0, sizeof(flx_QueueCounters), ctx->stream));
     return 0;
 }
+FLX_API_CATCH(ctx)
 
 int flx_enqueue_get_counters(flx_ctx *ctx, flx_QueueCounters *host_out)
+try
 {
     if (!ctx)
         return FLX_E_INVALID;
@@ -1811,22 +2048,31 @@ int flx_enqueue_get_counters(flx_ctx *ctx, flx_QueueCounters *host_out)
     ctx->pendingCounterReads.push_back({slot, host_out});
     return 0;
 }
+FLX_API_CATCH(ctx)
 
 int flx_finish(flx_ctx *ctx)
+try
 {
     if (!ctx)
         return FLX_E_INVALID;
     TOUCH(ctx);
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->gatherInFlight) // the caller sees ONE in-order queue: a gather enqueued before this call is complete after it
+    {
+        CU(cudaEventSynchronize(ctx->evGatherDone));
+        ctx->gatherInFlight = false;
+    }
     for (auto &r : ctx->pendingCounterReads)
         *r.second = ctx->pinnedCounters[r.first];
     ctx->pendingCounterReads.clear();
     drainEvents(ctx);
     return 0;
 }
+FLX_API_CATCH(ctx)
 
 int flx_update_pixel_index(flx_ctx *ctx, uint32_t num_pixels, uint32_t num_new_paths)
+try
 {
     if (!ctx)
         return FLX_E_INVALID;
@@ -1852,8 +2098,10 @@ int flx_update_pixel_index(flx_ctx *ctx, uint32_t num_pixels, uint32_t num_new_p
     CU(cudaMemcpyAsync(ctx->currPixelIdx, slot, sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     return 0;
 }
+FLX_API_CATCH(ctx)
 
 int flx_reset_pixel_index(flx_ctx *ctx)
+try
 {
     if (!ctx)
         return FLX_E_INVALID;
@@ -1864,8 +2112,10 @@ int flx_reset_pixel_index(flx_ctx *ctx)
     CU(cudaMemsetAsync(ctx->currPixelIdx, 0, sizeof(uint32_t), ctx->stream));
     return 0;
 }
+FLX_API_CATCH(ctx)
 
 int flx_render(flx_ctx *ctx, uint32_t n_iterations)
+try
 {
     int rc = checkReady(ctx, true, true);
     if (rc)
@@ -1925,8 +2175,10 @@ int flx_render(flx_ctx *ctx, uint32_t n_iterations)
     }
     return 0;
 }
+FLX_API_CATCH(ctx)
 
 int flx_render_timed(flx_ctx *ctx, uint32_t n_iterations, float *elapsed_ms)
+try
 {
     if (!ctx)
         return FLX_E_INVALID;
@@ -1944,8 +2196,10 @@ int flx_render_timed(flx_ctx *ctx, uint32_t n_iterations, float *elapsed_ms)
     drainEvents(ctx);
     return 0;
 }
+FLX_API_CATCH(ctx)
 
 int flx_timer_begin(flx_ctx *ctx)
+try
 {
     if (!ctx)
         return FLX_E_INVALID;
@@ -1955,22 +2209,28 @@ int flx_timer_begin(flx_ctx *ctx)
     CU(cudaEventRecord(ctx->evStart, ctx->stream));
     return 0;
 }
+FLX_API_CATCH(ctx)
 
 int flx_timer_end(flx_ctx *ctx, float *elapsed_ms)
+try
 {
     if (!ctx)
         return FLX_E_INVALID;
     TOUCH(ctx);
     REQUIRE(elapsed_ms != nullptr, "flx_timer_end: null destination");
     CU(cudaSetDevice(ctx->device));
+    if (ctx->gatherInFlight) // a gather still running on its own stream belongs to the timed work
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->evGatherDone, 0));
     CU(cudaEventRecord(ctx->evStop, ctx->stream));
     CU(cudaEventSynchronize(ctx->evStop));
     CU(cudaEventElapsedTime(elapsed_ms, ctx->evStart, ctx->evStop));
     drainEvents(ctx);
     return 0;
 }
+FLX_API_CATCH(ctx)
 
 int flx_set_tuning(flx_ctx *ctx, int key, int value)
+try
 {
     if (!ctx)
         return FLX_E_INVALID;
@@ -2051,8 +2311,10 @@ int flx_set_tuning(flx_ctx *ctx, int key, int value)
     }
     return fail(ctx, FLX_E_INVALID, "flx_set_tuning: unknown key %d", key);
 }
+FLX_API_CATCH(ctx)
 
 int flx_set_counting(flx_ctx *ctx, int enabled)
+try
 {
     if (!ctx)
         return FLX_E_INVALID;
@@ -2063,8 +2325,10 @@ int flx_set_counting(flx_ctx *ctx, int enabled)
         CU(cudaMemsetAsync(ctx->traceCounts, 0, 10 * sizeof(unsigned long long), ctx->stream));
     return 0;
 }
+FLX_API_CATCH(ctx)
 
 int flx_get_trace_counts(flx_ctx *ctx, flx_TraceCounts *ext, flx_TraceCounts *shadow)
+try
 {
     if (!ctx)
         return FLX_E_INVALID;
@@ -2085,14 +2349,18 @@ int flx_get_trace_counts(flx_ctx *ctx, flx_TraceCounts *ext, flx_TraceCounts *sh
     }
     return 0;
 }
+FLX_API_CATCH(ctx)
 
 int flx_reset_stats(flx_ctx *ctx)
+try
 {
     if (!ctx)
         return FLX_E_INVALID;
     TOUCH(ctx);
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->gatherStream)
+        CU(cudaStreamSynchronize(ctx->gatherStream));
     drainEvents(ctx);
     CU(cudaMemsetAsync(ctx->stats, 0, sizeof(flx_RenderStats64), ctx->stream));
     for (int k = 0; k < FLX_K_COUNT; k++)
@@ -2102,8 +2370,10 @@ int flx_reset_stats(flx_ctx *ctx)
     }
     return 0;
 }
+FLX_API_CATCH(ctx)
 
 int flx_get_stats(flx_ctx *ctx, flx_RenderStats64 *out)
+try
 {
     if (!ctx)
         return FLX_E_INVALID;
@@ -2114,8 +2384,10 @@ int flx_get_stats(flx_ctx *ctx, flx_RenderStats64 *out)
     CU(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
+FLX_API_CATCH(ctx)
 
 int flx_set_profiling(flx_ctx *ctx, int enabled)
+try
 {
     if (!ctx)
         return FLX_E_INVALID;
@@ -2123,8 +2395,10 @@ int flx_set_profiling(flx_ctx *ctx, int enabled)
     ctx->profiling = enabled != 0;
     return 0;
 }
+FLX_API_CATCH(ctx)
 
 int flx_get_kernel_ms(flx_ctx *ctx, int kernel_id, float *total_ms, uint32_t *launches)
+try
 {
     if (!ctx)
         return FLX_E_INVALID;
@@ -2132,6 +2406,8 @@ int flx_get_kernel_ms(flx_ctx *ctx, int kernel_id, float *total_ms, uint32_t *la
     REQUIRE(kernel_id >= 0 && kernel_id < FLX_K_COUNT, "flx_get_kernel_ms: bad kernel id");
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->gatherStream)
+        CU(cudaStreamSynchronize(ctx->gatherStream));
     drainEvents(ctx);
     if (total_ms)
         *total_ms = (float)ctx->kernelMs[kernel_id];
@@ -2139,8 +2415,10 @@ int flx_get_kernel_ms(flx_ctx *ctx, int kernel_id, float *total_ms, uint32_t *la
         *launches = ctx->kernelLaunches[kernel_id];
     return 0;
 }
+FLX_API_CATCH(ctx)
 
 int flx_read_pixels(flx_ctx *ctx, float *rgba, size_t n_pixels)
+try
 {
     if (!ctx)
         return FLX_E_INVALID;
@@ -2152,9 +2430,11 @@ int flx_read_pixels(flx_ctx *ctx, float *rgba, size_t n_pixels)
     CU(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
+FLX_API_CATCH(ctx)
 
 // CLContext::saveImage (clcontext.hpp:78; clcontext.cpp:386-465): *.hdr from the accumulator, anything else from the preview
 int flx_save_image(flx_ctx *ctx, const char *filename)
+try
 {
     int rc = checkReady(ctx, false, true);
     if (rc)
@@ -2171,9 +2451,11 @@ int flx_save_image(flx_ctx *ctx, const char *filename)
         return fail(ctx, FLX_E_INVALID, "flx_save_image: %s", flx_io_last_error());
     return 0;
 }
+FLX_API_CATCH(ctx)
 
 // test/diagnostic: the traversal layout as it lives on the device (TNode and TTri records of 16 floats each)
 int flx_read_traversal_layout(flx_ctx *ctx, float *tnodes_out, uint32_t *n_tnodes, float *ttris_out, uint32_t *n_ttris, int32_t *root_ref)
+try
 {
     if (!ctx)
         return FLX_E_INVALID;
@@ -2194,8 +2476,10 @@ int flx_read_traversal_layout(flx_ctx *ctx, float *tnodes_out, uint32_t *n_tnode
         *root_ref = ctx->rootRef;
     return 0;
 }
+FLX_API_CATCH(ctx)
 
 int flx_read_tasks(flx_ctx *ctx, uint32_t *slots_out)
+try
 {
     if (!ctx)
         return FLX_E_INVALID;
@@ -2206,8 +2490,10 @@ int flx_read_tasks(flx_ctx *ctx, uint32_t *slots_out)
     CU(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
+FLX_API_CATCH(ctx)
 
 int flx_write_tasks(flx_ctx *ctx, const uint32_t *slots_in)
+try
 {
     if (!ctx)
         return FLX_E_INVALID;
@@ -2218,8 +2504,10 @@ int flx_write_tasks(flx_ctx *ctx, const uint32_t *slots_in)
     CU(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
+FLX_API_CATCH(ctx)
 
 int flx_read_queue(flx_ctx *ctx, int queue_id, uint32_t *out, uint32_t max_entries)
+try
 {
     if (!ctx)
         return FLX_E_INVALID;
@@ -2231,8 +2519,10 @@ int flx_read_queue(flx_ctx *ctx, int queue_id, uint32_t *out, uint32_t max_entri
     CU(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
+FLX_API_CATCH(ctx)
 
 int flx_write_queue(flx_ctx *ctx, int queue_id, const uint32_t *entries, uint32_t n)
+try
 {
     if (!ctx)
         return FLX_E_INVALID;
@@ -2244,8 +2534,10 @@ int flx_write_queue(flx_ctx *ctx, int queue_id, const uint32_t *entries, uint32_
     CU(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
+FLX_API_CATCH(ctx)
 
 int flx_write_counters(flx_ctx *ctx, const flx_QueueCounters *in)
+try
 {
     if (!ctx)
         return FLX_E_INVALID;
@@ -2256,6 +2548,7 @@ int flx_write_counters(flx_ctx *ctx, const flx_QueueCounters *in)
     CU(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
+FLX_API_CATCH(ctx)
 
 // ---- checkpoint / resume (new; SURVEY 5: the reference can only restart a render from scratch -- its caches hold the
 // hierarchy, the camera state and compiled kernels, never the accumulator).  One file holds everything an interrupted
@@ -2265,12 +2558,30 @@ namespace
 {
 struct CheckpointHeader
 {
-    char magic[8]; // "FLXCKPT1"
+    char magic[8]; // "FLXCKPT2"
     uint32_t numTasks, width, height, tilePixels, part, nParts, stripeRows, hostPixelIdx;
+    uint64_t sceneHash, paramsHash; // what the path state was computed FOR: resuming against anything else gives a wrong picture
 };
+
+uint64_t fnv1a(uint64_t h, const void *data, size_t bytes)
+{
+    const unsigned char *p = static_cast<const unsigned char *>(data);
+    for (size_t i = 0; i < bytes; i++)
+        h = (h ^ p[i]) * 1099511628211ull;
+    return h;
+}
+
+// everything in RenderParams that decides the accumulator (the display-only ppParams do not)
+uint64_t paramsFingerprint(const flx_RenderParams &p)
+{
+    flx_RenderParams q = p;
+    memset(&q.ppParams, 0, sizeof q.ppParams);
+    return fnv1a(14695981039346656037ull, &q, sizeof q);
+}
 } // namespace
 
 int flx_checkpoint_save(flx_ctx *ctx, const char *path)
+try
 {
     int rc = checkReady(ctx, false, true);
     if (rc)
@@ -2280,10 +2591,13 @@ int flx_checkpoint_save(flx_ctx *ctx, const char *path)
     CU(cudaStreamSynchronize(ctx->stream));
     CheckpointHeader h;
     memset(&h, 0, sizeof h);
-    memcpy(h.magic, "FLXCKPT1", 8);
+    memcpy(h.magic, "FLXCKPT2", 8);
     h.numTasks = ctx->numTasks; h.width = ctx->width; h.height = ctx->height; h.tilePixels = ctx->tilePixels;
     h.part = ctx->part; h.nParts = ctx->nParts; h.stripeRows = ctx->stripeRows;
-    CU(cudaMemcpy(&h.hostPixelIdx, ctx->currPixelIdx, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    h.sceneHash = ctx->sceneHash;
+    h.paramsHash = paramsFingerprint(ctx->params);
+    CU(cudaMemcpyAsync(&h.hostPixelIdx, ctx->currPixelIdx, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
     FILE *fp = std::fopen(path, "wb");
     if (!fp)
         return fail(ctx, FLX_E_INVALID, "flx_checkpoint_save: cannot create %s", path);
@@ -2291,7 +2605,7 @@ int flx_checkpoint_save(flx_ctx *ctx, const char *path)
     std::vector<unsigned char> buf;
     auto dump = [&](const void *dev, size_t bytes) {
         buf.resize(bytes);
-        if (cudaMemcpy(buf.data(), dev, bytes, cudaMemcpyDeviceToHost) != cudaSuccess)
+        if (cudaMemcpyAsync(buf.data(), dev, bytes, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess)
             ok = false;
         ok = ok && std::fwrite(buf.data(), 1, bytes, fp) == bytes;
     };
@@ -2306,8 +2620,10 @@ int flx_checkpoint_save(flx_ctx *ctx, const char *path)
         return fail(ctx, FLX_E_INVALID, "flx_checkpoint_save: write error on %s", path);
     return 0;
 }
+FLX_API_CATCH(ctx)
 
 int flx_checkpoint_load(flx_ctx *ctx, const char *path)
+try
 {
     int rc = checkReady(ctx, false, true);
     if (rc)
@@ -2319,10 +2635,10 @@ int flx_checkpoint_load(flx_ctx *ctx, const char *path)
     if (!fp)
         return fail(ctx, FLX_E_INVALID, "flx_checkpoint_load: cannot open %s", path);
     CheckpointHeader h;
-    if (std::fread(&h, sizeof h, 1, fp) != 1 || memcmp(h.magic, "FLXCKPT1", 8) != 0)
+    if (std::fread(&h, sizeof h, 1, fp) != 1 || memcmp(h.magic, "FLXCKPT2", 8) != 0)
     {
         std::fclose(fp);
-        return fail(ctx, FLX_E_INVALID, "flx_checkpoint_load: %s is not a checkpoint", path);
+        return fail(ctx, FLX_E_INVALID, "flx_checkpoint_load: %s is not a checkpoint (or one of an older format)", path);
     }
     if (h.numTasks != ctx->numTasks || h.width != ctx->width || h.height != ctx->height || h.tilePixels != ctx->tilePixels || h.part != ctx->part ||
         h.nParts != ctx->nParts || h.stripeRows != ctx->stripeRows)
@@ -2331,33 +2647,59 @@ int flx_checkpoint_load(flx_ctx *ctx, const char *path)
         return fail(ctx, FLX_E_INVALID, "flx_checkpoint_load: checkpoint is for %u paths, %ux%u, tile %u/%u; this context has %u paths, %ux%u, tile %u/%u", h.numTasks,
                     h.width, h.height, h.part, h.nParts, ctx->numTasks, ctx->width, ctx->height, ctx->part, ctx->nParts);
     }
-    bool ok = true;
-    std::vector<unsigned char> buf;
-    auto restore = [&](void *dev, size_t bytes) {
-        buf.resize(bytes);
-        ok = ok && std::fread(buf.data(), 1, bytes, fp) == bytes;
-        if (ok && cudaMemcpy(dev, buf.data(), bytes, cudaMemcpyHostToDevice) != cudaSuccess)
-            ok = false;
-    };
-    restore(ctx->tasks, (size_t)ctx->numTasks * FLX_NUM_SLOTS * 4);
-    for (int q = 0; q < 8; q++)
-        restore(ctx->queues[q], (size_t)ctx->numTasks * 4);
-    restore(ctx->counters, sizeof(flx_QueueCounters));
-    restore(ctx->stats, sizeof(flx_RenderStats64));
-    restore(ctx->pixels, (size_t)ctx->tilePixels * 16);
+    if (h.sceneHash != ctx->sceneHash || h.paramsHash != paramsFingerprint(ctx->params))
+    {
+        std::fclose(fp);
+        return fail(ctx, FLX_E_INVALID, "flx_checkpoint_load: the checkpoint was written for a different %s; its path state would continue into a wrong picture",
+                    h.sceneHash != ctx->sceneHash ? "scene" : "camera / light / sampling setup (RenderParams)");
+    }
+    // Read and VALIDATE everything on the host before the first byte reaches the device: the kernels index the path state with
+    // queue entries and the accumulator with the pixelIndex slot, so a damaged file must not get that far.
+    const size_t n = ctx->numTasks;
+    std::vector<uint32_t> tasks(n * FLX_NUM_SLOTS), queues(n * 8);
+    flx_QueueCounters counters;
+    flx_RenderStats64 stats;
+    std::vector<float> pixels((size_t)ctx->tilePixels * 4);
+    bool ok = std::fread(tasks.data(), 4, tasks.size(), fp) == tasks.size() && std::fread(queues.data(), 4, queues.size(), fp) == queues.size() &&
+              std::fread(&counters, sizeof counters, 1, fp) == 1 && std::fread(&stats, sizeof stats, 1, fp) == 1 &&
+              std::fread(pixels.data(), 4, pixels.size(), fp) == pixels.size();
     std::fclose(fp);
     if (!ok)
         return fail(ctx, FLX_E_INVALID, "flx_checkpoint_load: %s is truncated", path);
+    if (h.hostPixelIdx >= ctx->tilePixels)
+        return fail(ctx, FLX_E_INVALID, "flx_checkpoint_load: pixel index %u outside the %u-pixel image", h.hostPixelIdx, ctx->tilePixels);
+    const uint32_t *cnt = reinterpret_cast<const uint32_t *>(&counters);
+    for (int q = 0; q < 8; q++)
+    {
+        if (cnt[q] > n)
+            return fail(ctx, FLX_E_INVALID, "flx_checkpoint_load: queue %d holds %u entries, more than the %zu paths", q, cnt[q], n);
+        for (uint32_t k = 0; k < cnt[q]; k++)
+            if (queues[(size_t)q * n + k] >= n)
+                return fail(ctx, FLX_E_INVALID, "flx_checkpoint_load: queue %d entry %u names path %u of %zu", q, k, queues[(size_t)q * n + k], n);
+    }
+    for (size_t g = 0; g < n; g++)
+        if (tasks[(size_t)FLX_S_PIXEL_INDEX * n + g] >= ctx->tilePixels)
+            return fail(ctx, FLX_E_INVALID, "flx_checkpoint_load: path %zu splats into pixel %u of %u", g, tasks[(size_t)FLX_S_PIXEL_INDEX * n + g], ctx->tilePixels);
+    // on the context's stream (the work streams do not order against the legacy default stream), one synchronisation at the end
+    CU(cudaMemcpyAsync(ctx->tasks, tasks.data(), tasks.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    for (int q = 0; q < 8; q++)
+        CU(cudaMemcpyAsync(ctx->queues[q], queues.data() + (size_t)q * n, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->counters, &counters, sizeof counters, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->stats, &stats, sizeof stats, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->pixels, pixels.data(), pixels.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->currPixelIdx, &h.hostPixelIdx, sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
     ctx->hostPixelIdx = h.hostPixelIdx;
     ctx->pixelIdxAdvancedOnDevice = false;
-    CU(cudaMemcpy(ctx->currPixelIdx, &h.hostPixelIdx, sizeof(uint32_t), cudaMemcpyHostToDevice));
     ctx->previewStale = true;
     markPixelsWritten(ctx);
     return 0;
 }
+FLX_API_CATCH(ctx)
 
 // ---- NCCL gather of the per-tile radiance buffers: the only collective of the path
 int flx_comm_unique_id(void *out128)
+try
 {
     flx_ctx tmp;
     flx_ctx *ctx = &tmp;
@@ -2375,8 +2717,10 @@ int flx_comm_unique_id(void *out128)
     }
     return 0;
 }
+FLX_API_CATCH((flx_ctx *)nullptr)
 
 int flx_comm_init(flx_ctx *ctx, const void *unique_id128, int rank, int nranks)
+try
 {
     if (!ctx)
         return FLX_E_INVALID;
@@ -2395,8 +2739,10 @@ int flx_comm_init(flx_ctx *ctx, const void *unique_id128, int rank, int nranks)
     ctx->nranks = nranks;
     return 0;
 }
+FLX_API_CATCH(ctx)
 
 int flx_comm_destroy(flx_ctx *ctx)
+try
 {
     if (!ctx)
         return FLX_E_INVALID;
@@ -2405,8 +2751,10 @@ int flx_comm_destroy(flx_ctx *ctx)
     ctx->comm = nullptr;
     return 0;
 }
+FLX_API_CATCH(ctx)
 
 int flx_gather_pixels(flx_ctx *ctx, int root, float *full_rgba_host_or_null)
+try
 {
     int rc = checkReady(ctx, false, true);
     if (rc)
@@ -2424,37 +2772,87 @@ int flx_gather_pixels(flx_ctx *ctx, int root, float *full_rgba_host_or_null)
         maxTile = std::max(maxTile, tileOf[r]);
     }
     const size_t fullPixels = (size_t)ctx->width * ctx->height;
+    const bool grow = (ctx->rank == root && (ctx->gatherBufPixels < (size_t)maxTile * ctx->nranks || ctx->fullImagePixels < fullPixels)) ||
+                      ctx->gatherSnapshotPixels < ctx->tilePixels;
+    if (grow && ctx->gatherStream) // a gather still in flight uses the buffers about to be replaced
+        CU(cudaStreamSynchronize(ctx->gatherStream));
     if (ctx->rank == root && ctx->gatherBufPixels < (size_t)maxTile * ctx->nranks)
     {
         freeDev(ctx->gatherBuf);
-        freeDev(ctx->fullImage);
+        ctx->gatherBufPixels = 0;
         CU(cudaMalloc(&ctx->gatherBuf, (size_t)maxTile * ctx->nranks * 16));
-        CU(cudaMalloc(&ctx->fullImage, fullPixels * 16));
         ctx->gatherBufPixels = (size_t)maxTile * ctx->nranks;
     }
+    if (ctx->rank == root && ctx->fullImagePixels < fullPixels)
+    {
+        freeDev(ctx->fullImage);
+        ctx->fullImagePixels = 0;
+        CU(cudaMalloc(&ctx->fullImage, fullPixels * 16));
+        ctx->fullImagePixels = fullPixels;
+    }
+    if (ctx->gatherSnapshotPixels < ctx->tilePixels)
+    {
+        freeDev(ctx->gatherSnapshot);
+        ctx->gatherSnapshotPixels = 0;
+        CU(cudaMalloc(&ctx->gatherSnapshot, (size_t)ctx->tilePixels * 16 * 2));
+        ctx->gatherSnapshotPixels = ctx->tilePixels;
+        ctx->snapshotBusy[0] = ctx->snapshotBusy[1] = false;
+    }
+    if (!ctx->gatherStream)
+    {
+        int prioLow = 0, prioHigh = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&prioLow, &prioHigh));
+        CU(cudaStreamCreateWithPriority(&ctx->gatherStream, cudaStreamNonBlocking, prioLow));
+        CU(cudaEventCreateWithFlags(&ctx->evSnapshot, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx->evGatherDone, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx->evSnapshotFree[0], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx->evSnapshotFree[1], cudaEventDisableTiming));
+    }
+    // the frame as of now: a snapshot on the render stream (ordered after the last splat, before the next) into the buffer
+    // the gather before the previous one used -- so the render stream only ever waits for a gather two frames old
+    const int par = ctx->gatherParity;
+    ctx->gatherParity ^= 1;
+    float *snapshot = ctx->gatherSnapshot + (size_t)par * ctx->gatherSnapshotPixels * 4;
+    if (ctx->snapshotBusy[par])
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->evSnapshotFree[par], 0));
+    CU(cudaMemcpyAsync(snapshot, ctx->pixels, (size_t)ctx->tilePixels * 16, cudaMemcpyDeviceToDevice, ctx->stream));
+    CU(cudaEventRecord(ctx->evSnapshot, ctx->stream));
+    CU(cudaStreamWaitEvent(ctx->gatherStream, ctx->evSnapshot, 0));
+    ctx->cur = ctx->gatherStream;
+    {
+    Timed tm(ctx, FLX_K_GATHER); // NCCL send/recv group + de-interleave, on the gather stream
     const int ncclFloat = 7; // ncclFloat32
     int r = ctx->nccl.GroupStart();
     if (r == 0)
-        r = ctx->nccl.Send(ctx->pixels, (size_t)ctx->tilePixels * 4, ncclFloat, root, ctx->comm, ctx->stream);
+        r = ctx->nccl.Send(snapshot, (size_t)ctx->tilePixels * 4, ncclFloat, root, ctx->comm, ctx->gatherStream);
     if (r == 0 && ctx->rank == root)
         for (int src = 0; src < ctx->nranks && r == 0; src++)
-            r = ctx->nccl.Recv(ctx->gatherBuf + (size_t)src * maxTile * 4, (size_t)tileOf[src] * 4, ncclFloat, src, ctx->comm, ctx->stream);
+            r = ctx->nccl.Recv(ctx->gatherBuf + (size_t)src * maxTile * 4, (size_t)tileOf[src] * 4, ncclFloat, src, ctx->comm, ctx->gatherStream);
     const int r2 = ctx->nccl.GroupEnd();
     if (r != 0 || r2 != 0)
-        return fail(ctx, FLX_E_NCCL, "NCCL gather failed: %s", ctx->nccl.GetErrorString(r != 0 ? r : r2));
-    if (ctx->rank == root)
     {
-        k_deinterleave<<<(unsigned)((fullPixels + 255) / 256), 256, 0, ctx->stream>>>(reinterpret_cast<const float4 *>(ctx->gatherBuf),
-                                                                                      reinterpret_cast<float4 *>(ctx->fullImage), ctx->width, ctx->height,
-                                                                                      ctx->nParts, ctx->stripeRows, maxTile);
-        if ((rc = launchCheck(ctx, "k_deinterleave")))
-            return rc;
-        if (full_rgba_host_or_null)
-        {
-            CU(cudaMemcpyAsync(full_rgba_host_or_null, ctx->fullImage, fullPixels * 16, cudaMemcpyDeviceToHost, ctx->stream));
-            CU(cudaStreamSynchronize(ctx->stream));
-        }
+        ctx->cur = ctx->stream;
+        return fail(ctx, FLX_E_NCCL, "NCCL gather failed: %s", ctx->nccl.GetErrorString(r != 0 ? r : r2));
+    }
+    if (ctx->rank == root)
+        k_deinterleave<<<(unsigned)((fullPixels + 255) / 256), 256, 0, ctx->gatherStream>>>(reinterpret_cast<const float4 *>(ctx->gatherBuf),
+                                                                                            reinterpret_cast<float4 *>(ctx->fullImage), ctx->width, ctx->height,
+                                                                                            ctx->nParts, ctx->stripeRows, maxTile);
+    }
+    ctx->cur = ctx->stream;
+    if ((rc = launchCheck(ctx, "k_deinterleave")))
+        return rc;
+    CU(cudaEventRecord(ctx->evGatherDone, ctx->gatherStream));
+    CU(cudaEventRecord(ctx->evSnapshotFree[par], ctx->gatherStream));
+    ctx->gatherInFlight = true;
+    ctx->snapshotBusy[par] = true;
+    if (ctx->rank == root && full_rgba_host_or_null)
+    {
+        CU(cudaMemcpyAsync(full_rgba_host_or_null, ctx->fullImage, fullPixels * 16, cudaMemcpyDeviceToHost, ctx->gatherStream));
+        CU(cudaStreamSynchronize(ctx->gatherStream));
     }
     return 0;
 }
+FLX_API_CATCH(ctx)
+
 } // extern "C"

@@ -86,7 +86,11 @@ __global__ void __launch_bounds__(FLX_BLOCK) k_reset(const __grid_constant__ Fra
         return;
     reset_path_fields(fr.tasks, gid, prm.worldRadius);
     fr.tasks.setu(FLX_S_PIXEL_INDEX, gid, 0u);
-    fr.tasks.setu(FLX_S_SEED, gid, gid);
+    // seed = gid (wf_reset.cl:59).  Tiled over several GPUs every part runs the same gid range; with equal seeds all parts would
+    // draw the same random sequences for different stripes of the image -- unbiased, but the noise pattern would repeat from
+    // stripe to stripe.  So part p starts its seeds at p * numTasks (the hash inside flx_rand decorrelates neighbouring seeds);
+    // part 0, and therefore the untiled single-GPU case, is the reference's.
+    fr.tasks.setu(FLX_S_SEED, gid, gid + fr.part * fr.numTasks);
     fr.queues[Q_RAYGEN][gid] = gid;
     if (gid == 0)
         fr.counters->raygenQueue = fr.numTasks;

@@ -24,6 +24,7 @@
 #include <cstring>
 #include <fstream>
 #include <map>
+#include <memory>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -521,20 +522,41 @@ bool load_ply(const std::string &path, flx_scene &s) // src/scene.cpp:422-553, 8
         int lines;
         std::vector<std::string> props;
     };
+    // sizes in the header are claims: an element of n lines needs at least 2n bytes of file
+    in.seekg(0, std::ios::end);
+    const long long fileSize = (long long)in.tellg();
+    in.seekg(0, std::ios::beg);
     std::vector<Element> elements;
     std::string line, type = "none";
     int count = 0;
+    bool sawEnd = false;
     std::vector<std::string> props;
     while (std::getline(in, line))
     {
         std::istringstream iss(line);
         std::string tok;
         iss >> tok;
-        if (tok == "element")
+        if (tok == "format")
+        {
+            std::string fmt;
+            iss >> fmt;
+            if (fmt != "ascii") // the reference reads every PLY as text (src/scene.cpp:422-553); a binary body would parse as garbage
+            {
+                g_io_error = path + ": only ASCII PLY is supported (format is '" + fmt + "')";
+                return false;
+            }
+        }
+        else if (tok == "element")
         {
             elements.push_back(Element{type, count, props});
             props.clear();
+            count = -1;
             iss >> type >> count;
+            if (!iss || count < 0 || 2ll * count > fileSize)
+            {
+                g_io_error = path + ": element '" + type + "' claims a line count the file cannot hold";
+                return false;
+            }
         }
         else if (tok == "property")
         {
@@ -545,15 +567,25 @@ bool load_ply(const std::string &path, flx_scene &s) // src/scene.cpp:422-553, 8
         else if (tok == "end_header")
         {
             elements.push_back(Element{type, count, props});
+            sawEnd = true;
             break;
         }
+    }
+    if (!sawEnd)
+    {
+        g_io_error = path + ": no end_header";
+        return false;
     }
     std::vector<flx_float3> P, N;
     std::vector<unsigned> F;
     for (const Element &e : elements)
         for (int i = 0; i < e.lines; i++)
         {
-            std::getline(in, line);
+            if (!std::getline(in, line))
+            {
+                g_io_error = path + ": body ends before element '" + e.name + "' is complete";
+                return false;
+            }
             std::istringstream iss(line);
             if (e.name == "vertex")
             {
@@ -590,6 +622,11 @@ bool load_ply(const std::string &path, flx_scene &s) // src/scene.cpp:422-553, 8
                 }
             }
         }
+    if (!N.empty() && N.size() != P.size()) // e.g. two vertex elements of which one has normals: N[F[..]] would run off the end
+    {
+        g_io_error = path + ": some vertices have normals and some do not";
+        return false;
+    }
     for (size_t f = 0; f + 2 < F.size(); f += 3)
     {
         flx_Vertex V[3];
@@ -643,6 +680,17 @@ bool read_rgbe(const std::string &path, flx_envmap &e)
     if (!std::fgets(buf, sizeof buf, fp) || std::sscanf(buf, "-Y %d +X %d", &e.h, &e.w) < 2 || e.w <= 0 || e.h <= 0)
         return bail("missing image size specifier");
     const int w = e.w, h = e.h;
+    {
+        // The size line is a claim.  Flat data needs 4 bytes per pixel; a run-length scanline packs at most 127 bytes of a
+        // channel into 2, so w * h pixels need at least w * h * 4 * 2 / 127 bytes.  (Also keeps w * h inside an int for the tables.)
+        const long at = std::ftell(fp);
+        std::fseek(fp, 0, SEEK_END);
+        const long long rest = (long long)std::ftell(fp) - at;
+        std::fseek(fp, at, SEEK_SET);
+        const unsigned long long pixels = (unsigned long long)w * (unsigned long long)h;
+        if (pixels > (1ull << 28) || pixels * 8ull / 127ull > (unsigned long long)std::max(rest, 0ll))
+            return bail("image size specifier larger than the file can hold");
+    }
     e.rgb.assign((size_t)w * h * 3, 0.0f);
     auto to_float = [](const unsigned char p[4], float *out) { // rgbe.cpp:95-107
         if (p[3])
@@ -983,7 +1031,9 @@ struct Huffman // canonical code, decoded bit by bit (count / symbol tables, RFC
     }
 };
 
-bool inflate_zlib(const unsigned char *src, size_t n, std::vector<unsigned char> &out)
+// maxOut: the caller knows how much it expects (PNG: rows x (1 + row bytes)); a stream that inflates beyond it is rejected
+// instead of being allowed to grow without bound (a 1 KB stream can expand ~1000-fold per level of nesting)
+bool inflate_zlib(const unsigned char *src, size_t n, std::vector<unsigned char> &out, size_t maxOut)
 {
     if (n < 6 || (src[0] & 0x0f) != 8 || ((src[0] << 8 | src[1]) % 31) != 0 || (src[1] & 0x20))
         return false;
@@ -1005,7 +1055,7 @@ bool inflate_zlib(const unsigned char *src, size_t n, std::vector<unsigned char>
                 return false;
             const uint32_t len = br.p[0] | (br.p[1] << 8), nlen = br.p[2] | (br.p[3] << 8);
             br.p += 4;
-            if ((len ^ 0xffffu) != nlen || (size_t)(br.end - br.p) < len)
+            if ((len ^ 0xffffu) != nlen || (size_t)(br.end - br.p) < len || out.size() + len > maxOut)
                 return false;
             out.insert(out.end(), br.p, br.p + len);
             br.p += len;
@@ -1071,7 +1121,11 @@ bool inflate_zlib(const unsigned char *src, size_t n, std::vector<unsigned char>
                 if (sym < 0)
                     return false;
                 if (sym < 256)
+                {
+                    if (out.size() >= maxOut)
+                        return false;
                     out.push_back((unsigned char)sym);
+                }
                 else if (sym == 256)
                     break;
                 else
@@ -1083,7 +1137,7 @@ bool inflate_zlib(const unsigned char *src, size_t n, std::vector<unsigned char>
                     if (ds < 0 || ds > 29)
                         return false;
                     const size_t d = distBase[ds] + br.bits(distExtra[ds]);
-                    if (br.bad || d > out.size())
+                    if (br.bad || d > out.size() || out.size() + (size_t)len > maxOut)
                         return false;
                     const size_t from = out.size() - d;
                     for (int k = 0; k < len; k++)
@@ -1177,7 +1231,7 @@ bool decode_png(const std::string &path, uint32_t &w, uint32_t &h, std::vector<u
     std::vector<unsigned char> raw;
     const size_t rowBytes = ((size_t)w * channels * depth + 7) / 8, bpp = std::max<size_t>(1, (size_t)channels * depth / 8);
     raw.reserve((rowBytes + 1) * h);
-    if (!inflate_zlib(idat.data(), idat.size(), raw) || raw.size() < (rowBytes + 1) * h)
+    if (!inflate_zlib(idat.data(), idat.size(), raw, (rowBytes + 1) * h) || raw.size() < (rowBytes + 1) * h)
         return bad("corrupt image data");
     // undo the scanline filters in place (PNG specification, section 9)
     std::vector<unsigned char> zero(rowBytes, 0);
@@ -1253,11 +1307,26 @@ bool ends_with(const std::string &s, const char *suffix)
 }
 } // namespace
 
+// No C++ exception may cross the C ABI (std::bad_alloc / std::length_error from a container sized by a hostile file would end
+// in std::terminate inside the caller's process): every int-returning entry point is a function-try-block.
+#define FLX_IO_CATCH                                                                                                   \
+    catch (const std::exception &e)                                                                                    \
+    {                                                                                                                  \
+        g_io_error = std::string("out of memory or internal error: ") + e.what();                                      \
+        return FLX_E_INVALID;                                                                                          \
+    }                                                                                                                  \
+    catch (...)                                                                                                        \
+    {                                                                                                                  \
+        g_io_error = "internal error";                                                                                 \
+        return FLX_E_INVALID;                                                                                          \
+    }
+
 extern "C"
 {
 const char *flx_io_last_error(void) { return g_io_error.c_str(); }
 
 int flx_scene_load(const char *path, flx_scene **out)
+try
 {
     if (!path || !out)
     {
@@ -1265,7 +1334,8 @@ int flx_scene_load(const char *path, flx_scene **out)
         return FLX_E_INVALID;
     }
     *out = nullptr;
-    flx_scene *s = new flx_scene();
+    std::unique_ptr<flx_scene> owner(new flx_scene());
+    flx_scene *s = owner.get();
     push_default_material(*s);
     const std::string p(path);
     bool ok = false;
@@ -1281,13 +1351,11 @@ int flx_scene_load(const char *path, flx_scene **out)
         ok = false;
     }
     if (!ok)
-    {
-        delete s;
         return FLX_E_INVALID;
-    }
-    *out = s;
+    *out = owner.release();
     return 0;
 }
+FLX_IO_CATCH
 
 void flx_scene_free(flx_scene *s) { delete s; }
 uint32_t flx_scene_num_triangles(const flx_scene *s) { return s ? (uint32_t)s->tris.size() : 0; }
@@ -1298,6 +1366,7 @@ const flx_Material *flx_scene_materials(const flx_scene *s) { return s ? s->mats
 const char *flx_scene_texture_name(const flx_scene *s, uint32_t i) { return (s && i < s->texNames.size()) ? s->texNames[i].c_str() : nullptr; }
 
 int flx_envmap_load(const char *path, flx_envmap **out)
+try
 {
     if (!path || !out)
     {
@@ -1305,37 +1374,40 @@ int flx_envmap_load(const char *path, flx_envmap **out)
         return FLX_E_INVALID;
     }
     *out = nullptr;
-    flx_envmap *e = new flx_envmap();
+    std::unique_ptr<flx_envmap> owner(new flx_envmap());
+    flx_envmap *e = owner.get();
     if (!read_rgbe(path, *e))
-    {
-        delete e;
         return FLX_E_INVALID;
-    }
     importance_tables(*e);
-    *out = e;
+    *out = owner.release();
     return 0;
 }
+FLX_IO_CATCH
 
 int flx_envmap_from_rgb(const float *rgb, int32_t w, int32_t h, flx_envmap **out)
+try
 {
-    if (!rgb || !out || w <= 0 || h <= 0)
+    if (!rgb || !out || w <= 0 || h <= 0 || (unsigned long long)w * (unsigned long long)h > (1ull << 28))
     {
         g_io_error = "flx_envmap_from_rgb: bad arguments";
         return FLX_E_INVALID;
     }
-    flx_envmap *e = new flx_envmap();
+    std::unique_ptr<flx_envmap> owner(new flx_envmap());
+    flx_envmap *e = owner.get();
     e->w = w;
     e->h = h;
     e->rgb.assign(rgb, rgb + (size_t)w * h * 3);
     importance_tables(*e);
-    *out = e;
+    *out = owner.release();
     return 0;
 }
+FLX_IO_CATCH
 
 // CLContext::saveImage's two conversions (src/clcontext.cpp:407-451) on host buffers of n_pixels RGBA floats, row 0 = bottom row:
 // *.hdr / *.HDR: the raw accumulator divided by its sample count, linear and unclamped, as Radiance RGBE;
 // anything else: the post-processed preview (already tone-mapped and gamma-corrected) as 8-bit PNG, byte = (uchar)(255 * clamp01(c)).
 int flx_write_image(const char *path, const float *rgba, uint32_t width, uint32_t height)
+try
 {
     if (!path || !rgba || width == 0 || height == 0)
     {
@@ -1358,6 +1430,7 @@ int flx_write_image(const char *path, const float *rgba, uint32_t width, uint32_
             bytes[3 * i + c] = (unsigned char)(255 * std::max(0.0f, std::min(1.0f, rgba[4 * i + c])));
     return write_png(p, bytes.data(), width, height) ? 0 : FLX_E_INVALID;
 }
+FLX_IO_CATCH
 
 // ---- the reference's hierarchy cache file (BVH::exportTo / importFrom, src/bvh.cpp:102-192; data/hierarchies/hierarchy_<hash>.bin,
 // src/tracer.cpp:574-590): u32 nIndices, indices, u32 "node count", then per node 6 floats (box), u32 iStart/rightChild,
@@ -1365,6 +1438,7 @@ int flx_write_image(const char *path, const float *rgba, uint32_t width, uint32_
 // reading the field is ignored and the node count is taken from the file length; on writing the true count goes in, which
 // the reference's own importer reads correctly.
 int flx_hierarchy_export(const char *path, const flx_Node *nodes, uint32_t n_nodes, const uint32_t *indices, uint32_t n_indices)
+try
 {
     if (!path || !nodes || !indices || n_nodes == 0 || n_indices == 0)
     {
@@ -1400,9 +1474,11 @@ int flx_hierarchy_export(const char *path, const flx_Node *nodes, uint32_t n_nod
     }
     return 0;
 }
+FLX_IO_CATCH
 
 // Two-call protocol: with nodes_out == NULL only the counts are returned; then call again with arrays of that size.
 int flx_hierarchy_import(const char *path, flx_Node *nodes_out, uint32_t *n_nodes, uint32_t *indices_out, uint32_t *n_indices)
+try
 {
     if (!path || !n_nodes || !n_indices)
     {
@@ -1458,10 +1534,12 @@ int flx_hierarchy_import(const char *path, flx_Node *nodes_out, uint32_t *n_node
     *n_indices = ni;
     return 0;
 }
+FLX_IO_CATCH
 
 // Decode one image file to RGBA8 with the reference's conventions (4 channels, row 0 = bottom row).  PNG only (see decode_png);
 // the buffer belongs to the library until flx_image_free.
 int flx_image_load(const char *path, uint32_t *width, uint32_t *height, uint8_t **rgba)
+try
 {
     if (!path || !width || !height || !rgba)
     {
@@ -1493,6 +1571,7 @@ int flx_image_load(const char *path, uint32_t *width, uint32_t *height, uint8_t 
     *height = h;
     return 0;
 }
+FLX_IO_CATCH
 
 void flx_image_free(uint8_t *rgba) { std::free(rgba); }
 
@@ -1501,6 +1580,7 @@ void flx_image_free(uint8_t *rgba) { std::free(rgba); }
 // returns the size needed.
 int flx_pack_textures(const uint8_t *const *images, const uint32_t *widths, const uint32_t *heights, uint32_t n_tex, flx_TexDescriptor *desc_out, uint8_t *blob_out,
                       size_t *blob_bytes)
+try
 {
     if ((n_tex && (!images || !widths || !heights)) || !blob_bytes)
     {
@@ -1536,6 +1616,7 @@ int flx_pack_textures(const uint8_t *const *images, const uint32_t *widths, cons
     *blob_bytes = total;
     return 0;
 }
+FLX_IO_CATCH
 
 void flx_envmap_free(flx_envmap *e) { delete e; }
 int32_t flx_envmap_width(const flx_envmap *e) { return e ? e->w : 0; }

@@ -47,6 +47,18 @@ class SceneData:
     def material_types(self):
         return int(np.bitwise_or.reduce(self.materials["type"])) if len(self.materials) else 0
 
+    def pinned(self):
+        """The same scene with every array in page-locked host memory (flx_host_alloc), so uploadSceneData copies by DMA."""
+        from .clcontext import pinned_copy
+        out = SceneData.__new__(SceneData)
+        for k in ("tris", "indices", "nodes", "materials", "tex_desc", "tex_data"):
+            a = getattr(self, k)
+            setattr(out, k, pinned_copy(a) if a.size else a)
+        out.name = self.name
+        if hasattr(self, "texture_names"):
+            out.texture_names = self.texture_names
+        return out
+
     def nbytes(self):
         return self.tris.nbytes + self.indices.nbytes + self.nodes.nbytes + self.materials.nbytes + self.tex_desc.nbytes + self.tex_data.nbytes
 

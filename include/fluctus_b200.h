@@ -89,7 +89,8 @@ enum { FLX_OK = 0, FLX_E_INVALID = 10001, FLX_E_NO_DEVICE = 10002, FLX_E_NOT_REA
 /* kernel ids for flx_get_kernel_ms (reference instrument: CLContext::checkTracingPerf, clcontext.cpp:673-701) */
 enum { FLX_K_RESET = 0, FLX_K_RAYGEN, FLX_K_EXTRAYS, FLX_K_SHADOWRAYS, FLX_K_LOGIC, FLX_K_MATERIALS, FLX_K_END_ITERATION, FLX_K_POSTPROCESS,
        FLX_K_MK_RESET, FLX_K_MK_RAYGEN, FLX_K_MK_NEXT_VERTEX, FLX_K_MK_SAMPLE_BSDF, FLX_K_MK_SPLAT,
-       FLX_K_LOGIC_FUSED /* logic + raygen + materials in one kernel (flx_render) */, FLX_K_COUNT };
+       FLX_K_LOGIC_FUSED /* logic + raygen + materials in one kernel (flx_render) */,
+       FLX_K_GATHER /* the NCCL gather of the tile accumulators + de-interleave, on its own stream (flx_gather_pixels) */, FLX_K_COUNT };
 
 typedef struct flx_ctx flx_ctx;
 
@@ -257,6 +258,9 @@ uint32_t flx_tile_pixels(const flx_ctx *ctx);
  * NCCL is resolved at run time (dlopen of libnccl.so.2, i.e. the copy torch.distributed already loaded). */
 int flx_comm_unique_id(void *out128);
 int flx_comm_init(flx_ctx *ctx, const void *unique_id128, int rank, int nranks);
+/* Asynchronous like the enqueue calls: the frame gathered is the accumulator as of this call (a device-side snapshot taken in
+ * stream order), the transfer runs on the library's gather stream beside whatever is enqueued next, and is complete after
+ * flx_finish -- or on return when a host destination is given.  Device time per call: flx_get_kernel_ms(FLX_K_GATHER). */
 int flx_gather_pixels(flx_ctx *ctx, int root, float *full_rgba_host_or_null);
 int flx_comm_destroy(flx_ctx *ctx);
 
@@ -303,7 +307,14 @@ int flx_pack_textures(const uint8_t *const *images, const uint32_t *widths, cons
 int flx_hierarchy_export(const char *path, const flx_Node *nodes, uint32_t n_nodes, const uint32_t *indices, uint32_t n_indices);
 int flx_hierarchy_import(const char *path, flx_Node *nodes_out, uint32_t *n_nodes, uint32_t *indices_out, uint32_t *n_indices);
 
-/* End-to-end convenience used by bench.py's e2e leg: host scene in, host image out, all copies included. */
+/* Page-locked host memory (new).  Arrays handed to flx_upload_scene / flx_upload_envmap or filled by flx_read_pixels /
+ * flx_read_preview / flx_gather_pixels may live anywhere; when they live in memory from flx_host_alloc the copy is a DMA at link
+ * speed instead of a trip through the driver's staging buffer.  The reference's analogue is the GL pixel-buffer object its
+ * kernels render into (src/clcontext.cpp:326-384).  Error text: flx_last_error(NULL). */
+int flx_host_alloc(void **out, size_t bytes);
+void flx_host_free(void *p);
+
+/* device memory held by the context: path state + queues + scene + image buffers */
 size_t flx_device_bytes(const flx_ctx *ctx);
 
 #ifdef __cplusplus

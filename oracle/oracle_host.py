@@ -50,11 +50,16 @@ class _CpuContext:
     LIB = None
     PREFIX = None
 
-    def __init__(self, num_tasks, parallel=False):
+    def __init__(self, num_tasks, parallel=False, parallel_trace=False):
+        """parallel: every kernel through the OpenMP build (CPU baseline; queue order then depends on thread timing).
+        parallel_trace: only the two traversal kernels through the OpenMP build -- they push to no queue and every work-item
+        writes its own path's slots only, so the result is the serial one; what stays serial (reset, raygen, logic, materials)
+        is what decides queue order.  This is the deterministic oracle for the full-size parity tests."""
         if not os.path.exists(self.LIB):
             raise FileNotFoundError(self.LIB)
         self.lib = C.CDLL(self.LIB)
         self.prefix = self.PREFIX + ("par_" if parallel else "")
+        self.trace_prefix = self.PREFIX + ("par_" if (parallel or parallel_trace) else "")
         self.NUM_TASKS = int(num_tasks)
         n = self.NUM_TASKS
         self.tasks = np.zeros((64, n), np.uint32)
@@ -121,7 +126,7 @@ class _CpuContext:
         return b
 
     def _run(self, name, n, first=0):
-        fn = getattr(self.lib, self.prefix + name)
+        fn = getattr(self.lib, (self.trace_prefix if name in ("ext", "shadow") else self.prefix) + name)
         fn.argtypes = [C.POINTER(RefBufs), C.c_size_t, C.c_size_t]
         fn.restype = None
         b = self._bufs(first)

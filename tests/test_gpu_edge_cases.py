@@ -262,3 +262,137 @@ def test_checkpoint_resume_continues_bit_identically(tmp_path):
             c.loadCheckpoint(ck)
         with pytest.raises(FluctusError):
             c.loadCheckpoint(tmp_path / "missing.ckpt")
+    # a checkpoint continues the render it was written for: another scene, or another camera / light / sampling setup, is refused
+    with CLContext(N) as d:
+        other = make_room_scene(materials="diffuse", n_blobs=3)
+        setup_context(d, other, room_params(other, W, H, max_bounces=4, separate_queues=True))
+        with pytest.raises(FluctusError, match="different scene"):
+            d.loadCheckpoint(ck)
+        p2 = room_params(scene, W, H, max_bounces=5, separate_queues=True)
+        setup_context(d, scene, p2)
+        with pytest.raises(FluctusError, match="RenderParams"):
+            d.loadCheckpoint(ck)
+        p3 = room_params(scene, W, H, max_bounces=4, separate_queues=True)
+        p3.ppParams.exposure = 2.5  # display-only: does not decide the accumulator, so the checkpoint still fits
+        setup_context(d, scene, p3)
+        d.loadCheckpoint(ck)
+        # a damaged payload must not reach the device: a queue entry naming a path that does not exist, a counter beyond N
+        raw = bytearray(open(ck, "rb").read())
+        header = 8 + 8 * 4 + 16
+        q0 = header + N * 64 * 4  # first entry of the raygen queue
+        bad = bytearray(raw)
+        bad[q0:q0 + 4] = (N + 7).to_bytes(4, "little")
+        cnt_at = header + N * 64 * 4 + 8 * N * 4
+        if int.from_bytes(raw[cnt_at:cnt_at + 4], "little") == 0:  # make sure that entry is live
+            bad[cnt_at:cnt_at + 4] = (1).to_bytes(4, "little")
+        (tmp_path / "bad_entry.ckpt").write_bytes(bad)
+        with pytest.raises(FluctusError, match="names path"):
+            d.loadCheckpoint(tmp_path / "bad_entry.ckpt")
+        bad = bytearray(raw)
+        bad[cnt_at + 4:cnt_at + 8] = (N + 1).to_bytes(4, "little")
+        (tmp_path / "bad_counter.ckpt").write_bytes(bad)
+        with pytest.raises(FluctusError, match="more than the"):
+            d.loadCheckpoint(tmp_path / "bad_counter.ckpt")
+        (tmp_path / "cut.ckpt").write_bytes(raw[:len(raw) // 2])
+        with pytest.raises(FluctusError, match="truncated"):
+            d.loadCheckpoint(tmp_path / "cut.ckpt")
+        d.loadCheckpoint(ck)  # and the context still works
+        d.render(2)
+        assert np.isfinite(d.readPixels()).all()
+
+
+def test_hierarchy_deeper_than_the_traversal_stack_is_refused(tmp_path):
+    """The traversal keeps 64 stack entries (reference: uint stack[64], src/bvh.cl:240) and pushes without a bounds check, like the
+    reference.  The in-repo builders stop at depth 62; a caller's Node[] -- or a cache file read by flx_hierarchy_import, which
+    checks no structure -- can be deeper: a right-leaning chain of 80 inner nodes must be refused at upload, by the device repack
+    and by the host repack alike, and a chain of 60 must still render."""
+    from fluctus_b200.scene_io import export_hierarchy, import_hierarchy
+    from fluctus_b200.structs import NODE_DTYPE
+
+    def chain(depth):
+        n_tris = depth + 1
+        tris = np.array([_tri((k, 0, 0), (k + 0.9, 0, 0), (k, 0.9, 0), 0) for k in range(n_tris)], TRIANGLE_DTYPE)
+        nodes = np.zeros(2 * depth + 1, NODE_DTYPE)
+        # inner node 2k has the leaf 2k+1 on the left and the next inner node (or the last leaf) on the right
+        for k in range(depth):
+            i = 2 * k
+            nodes[i]["bmin"][:3], nodes[i]["bmax"][:3] = (k, 0, 0), (n_tris, 0.9, 0)
+            nodes[i]["parent"], nodes[i]["link"], nodes[i]["nPrims"] = (i - 2 if k else -1), i + 2, 0
+            nodes[i + 1]["bmin"][:3], nodes[i + 1]["bmax"][:3] = (k, 0, 0), (k + 0.9, 0.9, 0)
+            nodes[i + 1]["parent"], nodes[i + 1]["link"], nodes[i + 1]["nPrims"] = i, k, 1
+        last = 2 * depth
+        nodes[last]["bmin"][:3], nodes[last]["bmax"][:3] = (depth, 0, 0), (depth + 0.9, 0.9, 0)
+        nodes[last]["parent"], nodes[last]["link"], nodes[last]["nPrims"] = last - 2, depth, 1
+        return SceneData(tris, np.arange(n_tris, dtype=np.uint32), nodes, np.array([_material()], MATERIAL_DTYPE))
+
+    deep, fine = chain(80), chain(60)
+    cache = tmp_path / "deep.bin"
+    export_hierarchy(cache, deep.nodes, deep.indices)
+    nodes, indices = import_hierarchy(cache)  # the importer takes it: structure is the uploader's business
+    assert len(nodes) == len(deep.nodes)
+    with CLContext(256) as gpu:
+        for on_host in (0, 1):
+            gpu.setTuning(repack_on_host=on_host)
+            with pytest.raises(FluctusError, match="levels deep"):
+                gpu.uploadSceneData(SceneData(deep.tris, indices, nodes, deep.materials))
+            gpu.uploadSceneData(fine)
+        cam = look_at((30.0, 0.4, 40.0), (30.0, 0.4, 0.0), fov=80.0)
+        light = dict(pos=(30.0, 0.4, 10.0), N=(0.0, 0.0, -1.0), right=(1.0, 0.0, 0.0), up=(0.0, 1.0, 0.0), size=(20.0, 0.5), E=(5.0, 5.0, 5.0))
+        params = make_params(64, 8, cam, fine.world_radius, len(fine.tris), light=light, max_bounces=2)
+        run_lockstep(gpu, oracle_ctx(256), fine, params, iterations=4)
+
+
+def test_pinned_host_memory_gives_the_same_bytes():
+    """flx_host_alloc: uploading from and reading into page-locked arrays (the DMA path bench.py's e2e leg uses) gives exactly what
+    the pageable path gives."""
+    from fluctus_b200 import pinned_empty
+    scene = make_room_scene(materials="mixed", textured=True)
+    W, H, N = 64, 40, 2048
+    params = room_params(scene, W, H, max_bounces=3)
+    with CLContext(N) as a, CLContext(N) as b:
+        ta, tb = setup_context(a, scene, params), setup_context(b, scene.pinned(), params)
+        ta.start(); tb.start()
+        for _ in range(5):
+            ta.iterate(); tb.iterate()
+        out = pinned_empty((W * H, 4), np.float32)
+        got = b.readPixels(out)
+        assert got is out
+        compare_tasks(a.readTasks(), b.readTasks(), "pinned vs pageable upload")
+        compare_pixels(a.readPixels(), out, "pinned vs pageable read-back", rtol=1e-5)
+
+
+def test_gather_on_its_own_stream_single_rank(tmp_path):
+    """flx_gather_pixels with a one-rank communicator (NCCL send/recv to self): the gather runs on the library's gather stream from
+    a snapshot, so (1) the frame it delivers is the accumulator AS OF THE CALL even though rendering continues right behind it,
+    (2) gathers every iteration do not disturb the render (same path state as without), (3) a resize between gathers gets fresh
+    buffers of the right size (the full-image buffer kept its old size)."""
+    scene = make_room_scene(materials="mixed")
+    N = 4096
+    with CLContext(N) as a, CLContext(N) as b:
+        try:
+            uid = a.commUniqueId()
+            a.setTile(0, 1, 8)
+            a.commInit(uid, 0, 1)
+        except FluctusError as e:
+            pytest.skip("NCCL not usable here: %s" % e)
+        for (W, H) in ((64, 9), (64, 16), (48, 8)):
+            params = room_params(scene, W, H, max_bounces=3)
+            ta, tb = setup_context(a, scene, params), setup_context(b, scene, params)
+            ta.start(); tb.start()
+            frames = []
+            for it in range(6):
+                a.render(1); b.render(1)
+                want = b.readPixels()
+                full = np.zeros((W * H, 4), np.float32)
+                if it % 2 == 0:
+                    a.gatherPixels(0, full)          # blocking form: host image on return
+                    frames.append((want, full))
+                else:
+                    a.gatherPixels(0)                # asynchronous form: rendering continues behind it
+                    a.render(1); b.render(1)
+            a.finishQueue()
+            for want, full in frames:
+                compare_pixels(full, want, "gathered frame %dx%d" % (W, H), rtol=1e-5)
+            compare_tasks(a.readTasks(), b.readTasks(), "render with gathers vs without (%dx%d)" % (W, H))
+            g_ms, g_n = a.checkTracingPerf()["gather"]
+            assert g_n >= 6

@@ -1,0 +1,86 @@
+"""GPU parity at the sizes SURVEY 8(d) sets -- and at the metric's own size -- against the reference's kernels compiled for
+the host (oracle/_ref).
+
+The thumbnails of test_gpu_parity.py keep a persistent-threads warp busy with a few hundred rays; here the queues hold
+10^5..2*10^6 entries, so the chunked queue fetch (flx_trace_persistent.cuh: chunk reservation, shrink near the tail, drain),
+the look-back scan over thousands of logic tiles and the CTA-aggregated queue atomics run in the regime the benchmark
+measures -- compared with the ORACLE, not with another GPU variant.
+
+The oracle runs reset / raygen / logic / materials serially (they decide queue order) and the two traversal kernels
+through its OpenMP build (`parallel_trace`: every work-item writes only its own path's slots, so the result is the serial
+one -- tests/test_oracle_cpu.py::test_parallel_trace_oracle_is_the_serial_oracle)."""
+import numpy as np
+import pytest
+
+from fluctus_b200 import CLContext, SceneData
+
+from conftest import scene_blob
+from parity_util import run_lockstep
+
+pytestmark = pytest.mark.gpu
+
+
+def oracle_ctx(n):
+    from oracle.oracle_host import RefContext, PortContext, ref_available, port_available
+    if ref_available():
+        return RefContext(n, parallel_trace=True)
+    if port_available():
+        return PortContext(n, parallel_trace=True)
+    pytest.skip("no oracle library built")
+
+
+def test_conference_c2_320x180_64_iterations():
+    """SURVEY 8(d) parity measurement, first size: C2 camera / light at 320x180, one path per pixel, K = 64 iterations."""
+    scene = SceneData.load_blob(scene_blob("conference"))
+    from bench_configs import conference_params
+    W, H = 320, 180
+    params = conference_params(scene, W, H)
+    with CLContext(W * H) as gpu:
+        run_lockstep(gpu, oracle_ctx(W * H), scene, params, iterations=64, check_every=8)
+
+
+def test_conference_c2_1280x720_65536_paths():
+    """SURVEY 8(d) parity measurement, second size: C2 at its full 1280x720 with N = 2^16 paths in flight (the pixel counter
+    walks the image in 14 iterations; 32 iterations here)."""
+    scene = SceneData.load_blob(scene_blob("conference"))
+    from bench_configs import conference_params
+    W, H, N = 1280, 720, 1 << 16
+    params = conference_params(scene, W, H)
+    with CLContext(N) as gpu:
+        run_lockstep(gpu, oracle_ctx(N), scene, params, iterations=32, check_every=8)
+
+
+def test_conference_metric_size_lockstep():
+    """The metric row itself: 1920x1080, N = 2^21 paths in flight, prologue + 3 iterations in lockstep with the oracle --
+    2 M-entry extension queue, ~1.4 M-entry shadow queue, 8192 logic tiles.  Complete path state bit for bit, queue
+    membership, raygen order, counters, accumulator."""
+    scene = SceneData.load_blob(scene_blob("conference"))
+    from bench_configs import conference_params
+    W, H, N = 1920, 1080, 1 << 21
+    params = conference_params(scene, W, H)
+    with CLContext(N) as gpu:
+        tg, tc = run_lockstep(gpu, oracle_ctx(N), scene, params, iterations=3)
+        assert tg.stats == tc.stats and tg.stats["extensionRays"] == 3 * N
+
+
+def test_conference_metric_size_fused_render_matches_oracle():
+    """Same size through flx_render (the loop bench.py times: fused logic+raygen+materials, device-side bookkeeping, shadow
+    kernel beside the extension kernel): state after 3 iterations == the oracle's."""
+    from parity_util import compare_pixels, compare_tasks, setup_context
+    scene = SceneData.load_blob(scene_blob("conference"))
+    from bench_configs import conference_params
+    W, H, N = 1920, 1080, 1 << 21
+    params = conference_params(scene, W, H)
+    cpu = oracle_ctx(N)
+    with CLContext(N) as gpu:
+        tg, tc = setup_context(gpu, scene, params), setup_context(cpu, scene, params)
+        tg.start()
+        tc.start()
+        gpu.resetStats()
+        tg.render(3)
+        for _ in range(3):
+            tc.iterate()
+        compare_tasks(gpu.readTasks(), cpu.readTasks(), "flx_render(3) at 1920x1080, N=2^21")
+        compare_pixels(gpu.readPixels(), cpu.readPixels(), "flx_render(3) at 1920x1080, N=2^21", rtol=1e-5)
+        st = gpu.getStats()
+        assert (st.extensionRays, st.shadowRays, st.primaryRays) == (tc.stats["extensionRays"], tc.stats["shadowRays"], tc.stats["primaryRays"])

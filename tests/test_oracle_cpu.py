@@ -210,3 +210,16 @@ def test_port_mk_matches_reference_kernels_country_kitchen():
     W, H = 40, 24
     params = kitchen_params(scene, W, H, max_bounces=4)
     run_mk_lockstep(PortContext(W * H), RefContext(W * H), scene, params, spp=2, env=env, check_every=2)
+
+
+@needs_ref
+def test_parallel_trace_oracle_is_the_serial_oracle():
+    """The oracle mode the full-size GPU parity tests use (tests/test_gpu_parity_large.py): traversal kernels through the
+    OpenMP build, everything that decides queue order serial.  Must be bit-identical to the all-serial oracle."""
+    scene = SceneData.load_blob(scene_blob("conference"))
+    from bench_configs import conference_params
+    W, H = 128, 72
+    params = conference_params(scene, W, H)
+    run_lockstep(RefContext(W * H, parallel_trace=True), RefContext(W * H), scene, params, iterations=8, check_every=4, exact_rgb=True)
+    if port_available():
+        run_lockstep(PortContext(W * H, parallel_trace=True), RefContext(W * H), scene, params, iterations=4, check_every=4, exact_rgb=True)

@@ -327,6 +327,52 @@ def test_malformed_files_are_rejected_not_crashed_on(tmp_path):
         load_model(p)
 
 
+def test_sizes_claimed_by_a_file_are_checked_against_the_file(tmp_path):
+    """Sizes read from a file are claims: a header that announces more than the file can hold is refused before anything is
+    allocated from it, short bodies are errors (not silently repeated lines), a binary PLY is not parsed as text, and no C++
+    exception crosses the C ABI (this process is still alive afterwards)."""
+    import zlib
+    from fluctus_b200.scene_io import load_image
+    hdr = open(os.path.join(IO, "small_rle.hdr"), "rb").read()
+    huge = tmp_path / "huge.hdr"
+    huge.write_bytes(hdr.replace(b"-Y 8 +X 16", b"-Y 2000000000 +X 2000000000"))
+    with pytest.raises(FluctusError, match="larger than the file"):
+        load_envmap(huge)
+    big_flat = tmp_path / "big_flat.hdr"  # 4-pixel-wide images are stored flat: 40000 x 4 pixels claimed, 128 bytes present
+    big_flat.write_bytes(hdr.replace(b"-Y 8 +X 16", b"-Y 40000 +X 4"))
+    with pytest.raises(FluctusError):
+        load_envmap(big_flat)
+    head = "ply\nformat %s 1.0\nelement vertex %d\nproperty float x\nproperty float y\nproperty float z\n%selement face %d\nproperty list uchar int vertex_indices\nend_header\n"
+    body = "0 0 0\n1 0 0\n0 1 0\n3 0 1 2\n"
+    cases = {"binary.ply": head % ("binary_little_endian", 3, "", 1) + body,
+             "bomb.ply": head % ("ascii", 2000000000, "", 1) + body,
+             "negative.ply": head % ("ascii", -3, "", 1) + body,
+             "short_body.ply": head % ("ascii", 3, "", 1) + "0 0 0\n1 0 0\n",
+             "no_end.ply": (head % ("ascii", 3, "", 1)).replace("end_header\n", ""),
+             # two vertex elements, only the second with normals: the normal array is shorter than the position array
+             "mixed_normals.ply": "ply\nformat ascii 1.0\nelement vertex 2\nproperty float x\nproperty float y\nproperty float z\nelement vertex 1\nproperty float x\n"
+                                  "property float y\nproperty float z\nproperty float nx\nproperty float ny\nproperty float nz\nelement face 1\n"
+                                  "property list uchar int vertex_indices\nend_header\n0 0 0\n1 0 0\n0 1 0 0 0 1\n3 0 1 2\n"}
+    for name, text in cases.items():
+        p = tmp_path / name
+        p.write_text(text)
+        with pytest.raises(FluctusError):
+            load_model(p)
+    ok = tmp_path / "ok.ply"  # the same header with honest numbers loads
+    ok.write_text(head % ("ascii", 3, "", 1) + body)
+    assert len(load_model(ok).tris) == 1
+    # a PNG whose compressed stream inflates to far more than its header announces (a "zip bomb"): refused, not inflated
+    def chunk(kind, data):
+        return struct.pack(">I", len(data)) + kind + data + struct.pack(">I", zlib.crc32(kind + data) & 0xffffffff)
+    bomb = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", 2, 2, 8, 6, 0, 0, 0)) + chunk(b"IDAT", zlib.compress(bytes(64 << 20), 9)) + chunk(b"IEND", b"")
+    p = tmp_path / "bomb.png"
+    p.write_bytes(bomb)
+    with pytest.raises(FluctusError):
+        load_image(p)
+    with pytest.raises(FluctusError):
+        envmap_from_rgb(np.zeros((1, 1, 3), np.float32)[:0])
+
+
 # ---------------------------------------------------------------------------------------------- textures
 def test_png_decoder_matches_an_independent_decoder(tmp_path):
     """flx_image_load against Pillow on PNGs of every colour type and bit depth Pillow can write (grey 1/8/16 bit, grey+alpha,
