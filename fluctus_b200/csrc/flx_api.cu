@@ -20,6 +20,7 @@
 #include "flx_bvh_repack.cuh"
 #include "flx_kernels.cuh"
 #include "flx_mk.cuh"
+#include "flx_trace_greedy.cuh"
 #include "flx_trace_persistent.cuh"
 
 static_assert(sizeof(flx_RenderParams) == 240, "RenderParams layout (geom.h:163-180)");
@@ -157,7 +158,9 @@ struct flx_ctx
     bool counting = false;
 
     // tuning knobs (flx_set_tuning)
-    int traceVariant = 1;     // 0: one ray per thread, 1: persistent threads + dynamic fetch, 2: 1 + top-of-tree treelet in shared memory
+    int traceVariant = 1;     // 0: one ray per thread, 1: persistent threads + dynamic fetch, while-while phases (production), 2: 1 + top-of-tree
+                              // treelet in shared memory, 3: persistent threads, one majority step per iteration (flx_trace_greedy.cuh; measured equal)
+    int innerBias = 0;        // variant 3: an inner-node step runs when lanes-at-inner + bias >= lanes-at-triangle
     int topNodes = 2047;      // variant 2: treelet nodes staged per CTA (64 B each)
     int fetchThreshold = 16;  // refill when fewer lanes than this still hold a ray
     int extMinBlocks = 9, shadowMinBlocks = 10; // variant 1: resident 128-thread CTAs per SM the kernels are compiled for
@@ -758,8 +761,28 @@ template <bool ANYHIT, class COUNT, int MINB, int SDEPTH> static int launchPersi
     return 0;
 }
 
+template <bool ANYHIT, class COUNT, int MINB> static int launchGreedy(flx_ctx *ctx, uint32_t *fetch, unsigned long long *counts)
+{
+    auto kern = k_trace_greedy<ANYHIT, COUNT, MINB>;
+    int perSM = ctx->traceBlocksPerSM;
+    if (perSM <= 0)
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, FLX_TRACE_BLOCK, 0));
+    const unsigned grid = (unsigned)std::max(1, perSM) * (unsigned)ctx->numSMs;
+    kern<<<grid, FLX_TRACE_BLOCK, 0, ctx->cur>>>(makeFrame(ctx), ctx->params, makeBvh(ctx), ctx->tris, fetch, ctx->fetchThreshold, ctx->fetchChunk, ctx->innerBias, counts, MkView{});
+    return 0;
+}
+
 template <bool ANYHIT, class COUNT> static int launchPersistentT(flx_ctx *ctx, uint32_t *fetch, unsigned long long *counts)
 {
+    if (ctx->traceVariant == 3)
+    {
+        switch (ANYHIT ? ctx->shadowMinBlocks : ctx->extMinBlocks)
+        {
+        case 8: return launchGreedy<ANYHIT, COUNT, 8>(ctx, fetch, counts);
+        case 9: return launchGreedy<ANYHIT, COUNT, 9>(ctx, fetch, counts);
+        default: return launchGreedy<ANYHIT, COUNT, 10>(ctx, fetch, counts);
+        }
+    }
     if (ctx->traceVariant == 2)
     {
         constexpr int BLOCK = 1024; // one persistent CTA per SM owns the staged treelet
@@ -874,8 +897,17 @@ template <bool ANYHIT> static int launchMkTrace(flx_ctx *ctx, const MkView &mk)
     constexpr int MINB = ANYHIT ? 10 : 9;
     uint32_t *fetch = ctx->fetchCounters + (ANYHIT ? 3 : 2);
     CU(cudaMemsetAsync(fetch, 0, sizeof(uint32_t), ctx->stream));
-    auto kern = k_trace_persistent<ANYHIT, NoCount, FLX_TRACE_BLOCK, false, MINB, 0, MODE>;
     int perSM = ctx->traceBlocksPerSM;
+    if (ctx->traceVariant == 3)
+    {
+        auto kern = k_trace_greedy<ANYHIT, NoCount, MINB, MODE>;
+        if (perSM <= 0)
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, FLX_TRACE_BLOCK, 0));
+        const unsigned grid = (unsigned)std::max(1, perSM) * (unsigned)ctx->numSMs;
+        kern<<<grid, FLX_TRACE_BLOCK, 0, ctx->stream>>>(makeFrame(ctx), ctx->params, makeBvh(ctx), ctx->tris, fetch, ctx->fetchThreshold, ctx->fetchChunk, ctx->innerBias, nullptr, mk);
+        return launchCheck(ctx, ANYHIT ? "k_trace_greedy<mk light samples>" : "k_trace_greedy<mk nextVertex>");
+    }
+    auto kern = k_trace_persistent<ANYHIT, NoCount, FLX_TRACE_BLOCK, false, MINB, 0, MODE>;
     if (perSM <= 0)
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, FLX_TRACE_BLOCK, 0));
     const unsigned grid = (unsigned)std::max(1, perSM) * (unsigned)ctx->numSMs;
@@ -2238,8 +2270,12 @@ try
     switch (key)
     {
     case FLX_TUNE_TRACE_VARIANT:
-        REQUIRE(value >= 0 && value <= 2, "flx_set_tuning: trace variant must be 0, 1 or 2");
+        REQUIRE(value >= 0 && value <= 3, "flx_set_tuning: trace variant must be 0, 1, 2 or 3");
         ctx->traceVariant = value;
+        return 0;
+    case FLX_TUNE_INNER_BIAS:
+        REQUIRE(value >= -32 && value <= 32, "flx_set_tuning: inner bias must be in -32..32");
+        ctx->innerBias = value;
         return 0;
     case FLX_TUNE_FETCH_THRESHOLD:
         REQUIRE(value >= 1 && value <= 32, "flx_set_tuning: fetch threshold must be in 1..32");

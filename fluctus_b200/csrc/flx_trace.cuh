@@ -41,14 +41,19 @@ struct NoCount
     FLX_DEV void leaf() {}
     FLX_DEV void tri() {}
     FLX_DEV void update() {}
+    FLX_DEV void hit() {}
+    FLX_DEV void leafEnd() {}
 };
 struct RayCount
 {
-    unsigned V = 0, B = 0, T = 0, U = 0;
+    unsigned V = 0, B = 0, T = 0, U = 0, leafImproved = 0;
     FLX_DEV void inner() { V++; B += 2; }
     FLX_DEV void leaf() { V++; }
     FLX_DEV void tri() { T++; }
     FLX_DEV void update() { U++; }
+    // flx_trace_greedy.cuh folds a leaf's best into the ray's best triangle by triangle; U stays "leaves that improved the hit"
+    FLX_DEV void hit() { leafImproved = 1; }
+    FLX_DEV void leafEnd() { U += leafImproved; leafImproved = 0; }
 };
 
 struct BvhView

@@ -183,8 +183,10 @@ int flx_timer_begin(flx_ctx *ctx);
 int flx_timer_end(flx_ctx *ctx, float *elapsed_ms);
 
 /* Tuning knobs; results never depend on them (tests/test_gpu_parity.py runs the parity suite over the variants). */
-enum { FLX_TUNE_TRACE_VARIANT = 0,      /* 0: one ray per thread; 1 (default): persistent threads with dynamic ray fetch; 2: 1 + the top-of-tree
-                                           treelet staged in shared memory by the bulk-copy engine, one CTA per SM */
+enum { FLX_TUNE_TRACE_VARIANT = 0,      /* 0: one ray per thread; 1 (default): persistent threads with dynamic ray fetch, while-while phases; 2: 1 + the
+                                           top-of-tree treelet staged in shared memory by the bulk-copy engine, one CTA per SM; 3: persistent threads, one
+                                           step of the majority kind (inner node / one triangle) per iteration (flx_trace_greedy.cuh; measured equal to 1) */
+       FLX_TUNE_INNER_BIAS = 20,        /* variant 3: run an inner-node step when lanes-at-inner + bias >= lanes-at-a-triangle (default 0) */
        FLX_TUNE_FETCH_THRESHOLD = 1,    /* persistent variant: refill a warp when fewer lanes than this hold a ray (default 16) */
        FLX_TUNE_TRACE_BLOCKS_PER_SM = 2,/* variant 1: resident CTAs per SM, 0 = occupancy calculator */
        FLX_TUNE_TOP_NODES = 3,          /* variant 2: treelet nodes (64 B each) staged per CTA, default 2047 */

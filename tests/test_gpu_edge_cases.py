@@ -119,15 +119,15 @@ def _full_size_conference():
 
 def test_full_size_invariants_and_kernel_variants_agree():
     """BASELINE metric configuration (conference 1920x1080, 8 bounces, N = 2^21) -- too big for the serial oracle, so:
-    (1) the three traversal kernels (one ray per thread / persistent / persistent + smem treelet) must leave bit-identical
-        path state and counters,
+    (1) the four traversal kernels (one ray per thread / persistent, one majority step per iteration [production] / round-1
+        persistent + smem treelet / round-1 persistent) must leave bit-identical path state and counters,
     (2) every iteration the extension queue is a permutation of all paths and queue lengths are consistent,
     (3) every terminated path with at least one segment splats exactly once: sum of pixel weights == regenerated paths,
     (4) radiance is finite and non-negative."""
     scene, params = _full_size_conference()
     N, iters = 1 << 21, 12
     states, pixels, counters = [], [], []
-    for variant in (0, 1, 2):
+    for variant in (0, 1, 2, 3):
         with CLContext(N) as gpu:
             gpu.setTuning(trace_variant=variant)
             tr = setup_context(gpu, scene, params)
@@ -153,8 +153,8 @@ def test_full_size_invariants_and_kernel_variants_agree():
             states.append(alive)
             pixels.append(pix)
             counters.append(cs)
-    assert counters[0] == counters[1] == counters[2]
-    for k in (1, 2):
+    assert counters[0] == counters[1] == counters[2] == counters[3]
+    for k in (1, 2, 3):
         compare_tasks(states[0], states[k], "trace variant 0 vs %d at full size" % k)
         compare_pixels(pixels[0], pixels[k], "trace variant 0 vs %d at full size" % k, rtol=1e-5)
 

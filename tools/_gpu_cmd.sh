@@ -2,17 +2,12 @@
 # GPU job of the moment (edited per gpurun call; kept for the record of what was run)
 set -x
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv
-nproc
-timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -25
-timeout 600 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/r2_bench_a.json 2> gpurun_out/r2_bench_a.err; tail -c 600 gpurun_out/r2_bench_a.err
-python - <<'P'
-import json
-d=json.load(open('gpurun_out/r2_bench_a.json'))
-print({k:d[k] for k in ('value','ms_per_step','blocks','e2e','clocks')})
-print(d['roofline']['kernel_share_of_step'], d['roofline']['avg_launch_ms'], d['roofline']['shadow']['avg_launch_ms'], d['cpu_baseline'])
-P
-FLX_DEBUG_TIMING=1 timeout 300 python tools/e2e_breakdown.py 2>&1 | tail -12
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_base_launches.csv python tools/prof_step.py > gpurun_out/r2_base_launches.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_trace_persistent|k_logic' -s 24 -c 3 -o gpurun_out/r2_base_prof python tools/prof_step.py > gpurun_out/r2_base_prof.log 2>&1
-tail -3 gpurun_out/r2_base_prof.log
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_edge_cases.py tests/test_gpu_mk.py -x -q 2>&1 | tail -15
+for t in "trace_variant=3" "trace_variant=1" "trace_variant=1,inner_bias=4" "trace_variant=1,inner_bias=8" "trace_variant=1,inner_bias=-4" "trace_variant=1,fetch_threshold=20" "trace_variant=1,fetch_threshold=24" "trace_variant=1,fetch_threshold=12" "trace_variant=1,ext_min_blocks=8" "trace_variant=1,ext_min_blocks=10" "trace_variant=1,overlap_trace=0" "trace_variant=3,overlap_trace=0"; do
+  echo "== $t"
+  timeout 300 python bench.py --steps 40 --warmup 10 --no-e2e --no-cpu-baseline --min-seconds 0.2 --tune $t | python -c "
+import sys,json
+d=json.loads(sys.stdin.read()); r=d['roofline']
+print(round(d['value'],1), round(d['ms_per_step'],4), 'ext', r['avg_launch_ms'], 'shadow', r['shadow']['avg_launch_ms'], r['kernel_share_of_step'])"
+done
+timeout 600 python -m pytest tests/test_gpu_parity_large.py -x -q 2>&1 | tail -5

@@ -17,7 +17,7 @@ def main():
     scene = make_room_scene(materials="mixed", textured=True)
     rng = np.random.default_rng(3)
     env = EnvMapData.from_rgb(rng.uniform(0.0, 0.4, size=(16, 32, 3)).astype(np.float32))
-    for variant in (0, 1, 2):
+    for variant in (0, 1, 2, 3):
         for separate in (False, True):
             params = room_params(scene, 40, 24, max_bounces=4, separate_queues=separate, use_env_map=True, env_map_strength=1.5)
             with CLContext(1500) as ctx:
