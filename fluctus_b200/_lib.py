@@ -35,6 +35,8 @@ _SIGNATURES = {
     "flx_enqueue_mk_splat_preview": (C.c_int, [_P]),
     "flx_render_single": (C.c_int, [_P, C.c_uint32]),
     "flx_read_preview": (C.c_int, [_P, _P, C.c_size_t]),
+    "flx_set_denoiser": (C.c_int, [_P, C.c_int]),
+    "flx_read_denoiser_aov": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_size_t]),
     "flx_enqueue_clear_queues": (C.c_int, [_P]),
     "flx_enqueue_get_counters": (C.c_int, [_P, C.POINTER(QueueCounters)]),
     "flx_finish": (C.c_int, [_P]),

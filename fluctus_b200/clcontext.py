@@ -178,6 +178,17 @@ class CLContext:
         """reference: clcontext.hpp:41 -- normalise / exposure / tone map / gamma into the preview buffer."""
         self._check(self._lib.flx_enqueue_postprocess(self._h), "enqueuePostprocessKernel")
 
+    def setDenoiser(self, enabled):
+        """reference: Tracer::useDenoiser (kernels rebuilt with -DUSE_OPTIX_DENOISER): accumulate the normal / albedo feature buffers."""
+        self._check(self._lib.flx_set_denoiser(self._h, 1 if enabled else 0), "setDenoiser")
+
+    def readDenoiserAOV(self, which, processed=False):
+        """which: "normal" | "albedo"; processed: the display pass's output instead of the raw accumulator."""
+        n = self.tilePixels()
+        out = np.empty((n, 4), np.float32)
+        self._check(self._lib.flx_read_denoiser_aov(self._h, {"normal": 0, "albedo": 1}[which], 1 if processed else 0, self._ptr(out), n), "readDenoiserAOV")
+        return out
+
     def readPreview(self):
         n = self.tilePixels()
         out = np.empty((n, 4), np.float32)
@@ -224,7 +235,7 @@ class CLContext:
         self._check(self._lib.flx_timer_end(self._h, C.byref(ms)), "timerEnd")
         return ms.value
 
-    TUNING = {"trace_variant": 0, "fetch_threshold": 1, "trace_blocks_per_sm": 2, "top_nodes": 3, "inner_min": 4, "logic_min_blocks": 5, "fetch_chunk": 6, "overlap_trace": 7, "postprocess_in_loop": 10, "smem_stack": 11, "max_l1": 12, "fuse_stages": 13, "prefetch_children": 15, "repack_on_host": 16, "overlap_postprocess": 17, "dirty_postprocess": 18, "l2_persist": 19, "fused_min_blocks": 14, "ext_min_blocks": 8, "shadow_min_blocks": 9, "inner_bias": 20}
+    TUNING = {"trace_variant": 0, "fetch_threshold": 1, "trace_blocks_per_sm": 2, "top_nodes": 3, "inner_min": 4, "logic_min_blocks": 5, "fetch_chunk": 6, "overlap_trace": 7, "postprocess_in_loop": 10, "smem_stack": 11, "max_l1": 12, "fuse_stages": 13, "prefetch_children": 15, "repack_on_host": 16, "overlap_postprocess": 17, "dirty_postprocess": 18, "l2_persist": 19, "fused_min_blocks": 14, "ext_min_blocks": 8, "shadow_min_blocks": 9, "inner_bias": 20, "gather_priority": 21}
 
     def setTuning(self, **kv):
         for k, v in kv.items():

@@ -148,6 +148,8 @@ struct flx_ctx
     int gatherParity = 0;
     bool gatherInFlight = false, snapshotBusy[2] = {false, false};
     unsigned char *imageBlock = nullptr; // pixels | denoiserAlbedo | denoiserNormal | preview | dirtyPixels in one allocation
+    int denoiser = 0;                    // flx_set_denoiser: accumulate the feature buffers (reference: Tracer::useDenoiser -> -DUSE_OPTIX_DENOISER)
+    float *aovOut = nullptr;             // display-pass outputs of the two feature buffers (normal | albedo), allocated on first use
 
     flx_RenderParams params;
     bool paramsSet = false;
@@ -160,6 +162,7 @@ struct flx_ctx
     // tuning knobs (flx_set_tuning)
     int traceVariant = 1;     // 0: one ray per thread, 1: persistent threads + dynamic fetch, while-while phases (production), 2: 1 + top-of-tree
                               // treelet in shared memory, 3: persistent threads, one majority step per iteration (flx_trace_greedy.cuh; measured equal)
+    int gatherPriority = 0;   // 1: the gather stream gets the render stream's (high) priority instead of the lowest
     int innerBias = 0;        // variant 3: an inner-node step runs when lanes-at-inner + bias >= lanes-at-triangle
     int topNodes = 2047;      // variant 2: treelet nodes staged per CTA (64 B each)
     int fetchThreshold = 16;  // refill when fewer lanes than this still hold a ray
@@ -250,6 +253,7 @@ Frame makeFrame(const flx_ctx *c)
     f.dirty = c->dirtyPixels;
     f.denoiserAlbedo = c->denoiserAlbedo;
     f.denoiserNormal = c->denoiserNormal;
+    f.denoiser = c->denoiser;
     f.currPixelIdx = c->currPixelIdx;
     f.numTasks = c->numTasks;
     f.tilePixels = c->tilePixels;
@@ -1119,6 +1123,7 @@ void flx_destroy(flx_ctx *c)
     freeDev(c->pdfTable);
     freeDev(c->aliasTable);
     freeDev(c->imageBlock);
+    freeDev(c->aovOut);
     freeDev(c->gatherBuf);
     freeDev(c->fullImage);
     freeDev(c->gatherSnapshot);
@@ -1550,6 +1555,7 @@ static int allocImage(flx_ctx *ctx)
         CU(cudaStreamSynchronize(ctx->gatherStream));
     ctx->gatherInFlight = false;
     freeDev(ctx->imageBlock);
+    freeDev(ctx->aovOut);
     ctx->pixels = ctx->denoiserAlbedo = ctx->denoiserNormal = ctx->preview = nullptr;
     ctx->dirtyPixels = nullptr;
     // the gather buffers are sized for an image and a tiling: a new image or tiling starts from none
@@ -2006,6 +2012,15 @@ static int launchPostprocess(flx_ctx *ctx)
                                                                             ctx->dirtyPixels, all, ctx->tilePixels, ctx->params.ppParams.exposure,
                                                                             ctx->params.ppParams.tmOperator);
     ctx->previewStale = false;
+    if (ctx->denoiser) // mk_postprocess.cl:49-54: the feature buffers go out with the picture
+    {
+        if (!ctx->aovOut)
+            CU(cudaMalloc(&ctx->aovOut, (size_t)ctx->tilePixels * 32));
+        float4 *out = reinterpret_cast<float4 *>(ctx->aovOut);
+        k_postprocess_aovs<<<streamingGrid(ctx->tilePixels), FLX_BLOCK, 0, ctx->cur>>>(reinterpret_cast<const float4 *>(ctx->denoiserNormal),
+                                                                                     reinterpret_cast<const float4 *>(ctx->denoiserAlbedo), out, out + ctx->tilePixels,
+                                                                                     ctx->tilePixels);
+    }
     return launchCheck(ctx, "k_postprocess");
 }
 
@@ -2029,6 +2044,38 @@ try
         return rc;
     CU(cudaEventRecord(ctx->evPostJoin, ctx->stream3));
     CU(cudaStreamWaitEvent(ctx->stream, ctx->evPostJoin, 0));
+    return 0;
+}
+FLX_API_CATCH(ctx)
+
+// Tracer::useDenoiser (reference: src/kernel_impl.hpp:53, 346, 380, 443 add -DUSE_OPTIX_DENOISER to the logic, nextVertex,
+// sampleBsdf and post-process kernels).  The OptiX denoiser itself is out of scope; the feature buffers it consumes are not.
+int flx_set_denoiser(flx_ctx *ctx, int enabled)
+try
+{
+    if (!ctx)
+        return FLX_E_INVALID;
+    TOUCH(ctx);
+    ctx->denoiser = enabled != 0;
+    return 0;
+}
+FLX_API_CATCH(ctx)
+
+// which: 0 = first-hit normal, 1 = first-diffuse-hit albedo; processed: 0 = the raw accumulators (sums, w = sample count), 1 = as the
+// display pass hands them to the denoiser (divided by w where w > 1; run flx_enqueue_postprocess first)
+int flx_read_denoiser_aov(flx_ctx *ctx, int which, int processed, float *rgba, size_t n_pixels)
+try
+{
+    if (!ctx)
+        return FLX_E_INVALID;
+    TOUCH(ctx);
+    REQUIRE(rgba != nullptr && (which == 0 || which == 1), "flx_read_denoiser_aov: bad arguments");
+    REQUIRE(ctx->pixels && n_pixels <= ctx->tilePixels, "flx_read_denoiser_aov: more pixels requested than the context owns");
+    REQUIRE(!processed || ctx->aovOut, "flx_read_denoiser_aov: no display pass has run with the denoiser buffers enabled");
+    const float *src = processed ? ctx->aovOut + (which ? (size_t)ctx->tilePixels * 4 : 0) : (which ? ctx->denoiserAlbedo : ctx->denoiserNormal);
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(rgba, src, n_pixels * 4 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 FLX_API_CATCH(ctx)
@@ -2272,6 +2319,10 @@ try
     case FLX_TUNE_TRACE_VARIANT:
         REQUIRE(value >= 0 && value <= 3, "flx_set_tuning: trace variant must be 0, 1, 2 or 3");
         ctx->traceVariant = value;
+        return 0;
+    case FLX_TUNE_GATHER_PRIORITY:
+        REQUIRE(ctx->gatherStream == nullptr, "flx_set_tuning: the gather stream already exists (set its priority before the first flx_gather_pixels)");
+        ctx->gatherPriority = value != 0;
         return 0;
     case FLX_TUNE_INNER_BIAS:
         REQUIRE(value >= -32 && value <= 32, "flx_set_tuning: inner bias must be in -32..32");
@@ -2838,7 +2889,9 @@ try
     {
         int prioLow = 0, prioHigh = 0;
         CU(cudaDeviceGetStreamPriorityRange(&prioLow, &prioHigh));
-        CU(cudaStreamCreateWithPriority(&ctx->gatherStream, cudaStreamNonBlocking, prioLow));
+        // Low priority by default: the render kernels are persistent and fill every SM, so NCCL's few CTAs get their slots when a
+        // traversal kernel's CTAs retire; with the high priority they are placed ahead of the next render kernel's CTAs instead.
+        CU(cudaStreamCreateWithPriority(&ctx->gatherStream, cudaStreamNonBlocking, ctx->gatherPriority ? prioHigh : prioLow));
         CU(cudaEventCreateWithFlags(&ctx->evSnapshot, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&ctx->evGatherDone, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&ctx->evSnapshotFree[0], cudaEventDisableTiming));

@@ -27,6 +27,7 @@ struct Frame
     float *pixels;       // tilePixels x float4
     uint8_t *dirty;      // tilePixels: 1 = the accumulator of this pixel changed since the display pass last looked at it
     float *denoiserAlbedo, *denoiserNormal;
+    int denoiser;        // accumulate the denoiser feature buffers (the reference's -DUSE_OPTIX_DENOISER, kernel_impl.hpp:53): flx_set_denoiser
     uint32_t *currPixelIdx;
     uint32_t numTasks;
     // image / tile geometry (flx_set_tile): local pixel -> full-image pixel
@@ -325,6 +326,31 @@ FLX_DEV void material_path(const Tasks &t, const SceneView &sc, uint32_t gid, co
 }
 
 
+// Denoiser feature buffers (reference: the USE_OPTIX_DENOISER blocks, src/wf_logic.cl:186-209, src/mk_next_vertex.cl:60-70,
+// src/mk_sample_bsdf.cl:56-66).  First-hit shading normal in camera space: rows right, up, -dir of the camera frame (a rotation,
+// so its inverse transpose is itself), w counts the samples; albedo = Kd (texture or constant, NOT gamma-corrected) at the first
+// non-singular vertex of the path, once per path (firstDiffuseHit).
+FLX_DEV float4 denoiser_normal(const flx_RenderParams &prm, V3 N)
+{
+    const V3 r1 = v3(prm.camera.right), r2 = v3(prm.camera.up), r3 = -v3(prm.camera.dir);
+    return make_float4(dot3(r1, N), dot3(r2, N), dot3(r3, N), 1.0f);
+}
+// wavefront flavour: several paths in flight may hold the same pixel, so the adds are atomic (the reference builds with
+// -DFLT_FLOAT_ATOMICS, clcontext.cpp:145).  Out of line: it is off in the default configuration and must not cost registers there.
+__device__ __noinline__ void denoiser_aov_wf(const Frame &fr, const flx_RenderParams &prm, const SceneView &sc, uint32_t gid, uint32_t len, uint32_t pixIdx, V3 N, const Mat &mat,
+                                            float u, float v)
+{
+    if (len == 1u)
+        atomicAdd(reinterpret_cast<float4 *>(fr.denoiserNormal) + pixIdx, denoiser_normal(prm, N));
+    const bool isDiffuse = (mat.type & (FLX_BXDF_IDEAL_REFLECTION | FLX_BXDF_IDEAL_DIELECTRIC)) == 0;
+    if (isDiffuse && fr.tasks.u(FLX_S_FIRST_DIFFUSE, gid) == 0u)
+    {
+        fr.tasks.setu(FLX_S_FIRST_DIFFUSE, gid, 1u);
+        const V3 albedo = mat_float3(mat.Kd, u, v, mat.map_Kd, sc);
+        atomicAdd(reinterpret_cast<float4 *>(fr.denoiserAlbedo) + pixIdx, make_float4(albedo.x, albedo.y, albedo.z, 1.0f));
+    }
+}
+
 // Fused stages: the same thread also does what wf_raygen (for a path it has just terminated) and wf_mat_* (for a path it sends on)
 // would do next, instead of leaving that to two more passes over the path state.  Nothing crosses paths between those three
 // stages except the queue counters and the raygen-queue rank (known here from the look-back scan), so the state, the queues and
@@ -499,6 +525,8 @@ __global__ void __launch_bounds__(FLX_BLOCK, MIN_BLOCKS) k_logic(const __grid_co
         if (backface)
             N = N * -1.0f;
         const V3 orig = s.P - 1e-3f * rayDir;
+        if (fr.denoiser) // wf_logic.cl:186-209 (before the hit record is written back, like there)
+            denoiser_aov_wf(fr, prm, sc, gid, len, pixIdx, N, mat, hU, hV);
         t.setv(FLX_S_N, gid, N);
         t.setu(FLX_S_BACKFACE, gid, backface ? 1u : 0u);
 
@@ -766,6 +794,19 @@ FLX_DEV float uc2_curve(float x)
 // accumulator; `all` after anything else that invalidates the preview: new image, new exposure / operator): an iteration splats
 // into at most a fifth of the pixels, and the three pinned double-precision pow per pixel are what this pass costs.  The
 // preview buffer after the pass is the same as if every pixel had been recomputed.
+// the denoiser feature buffers as the display pass hands them on (mk_postprocess.cl:49-54): divided by their sample count once
+// that exceeds 1 (sic: "> 1.0f", so a single sample is passed through as it is -- same value)
+__global__ void __launch_bounds__(FLX_BLOCK) k_postprocess_aovs(const float4 *__restrict__ normal, const float4 *__restrict__ albedo, float4 *__restrict__ normalOut,
+                                                                float4 *__restrict__ albedoOut, uint32_t nPixels)
+{
+    for (uint32_t i = blockIdx.x * FLX_BLOCK + threadIdx.x; i < nPixels; i += gridDim.x * FLX_BLOCK)
+    {
+        const float4 n = normal[i], a = albedo[i];
+        normalOut[i] = n.w > 1.0f ? make_float4(n.x / n.w, n.y / n.w, n.z / n.w, n.w / n.w) : n;
+        albedoOut[i] = a.w > 1.0f ? make_float4(a.x / a.w, a.y / a.w, a.z / a.w, a.w / a.w) : a;
+    }
+}
+
 __global__ void __launch_bounds__(FLX_BLOCK) k_postprocess(const float4 *__restrict__ pixels, float4 *__restrict__ preview, uint8_t *__restrict__ dirty, const int all,
                                                            uint32_t nPixels, float exposure, uint32_t tmOperator)
 {

@@ -152,6 +152,12 @@ __global__ void __launch_bounds__(FLX_BLOCK) k_mk_next_vertex_logic(const __grid
     {
         const uint32_t len = t.u(FLX_S_PATH_LEN, gid); // already incremented
         (len == 1u ? primary : extension) = 1u;
+        if (fr.denoiser && len == 1u) // mk_next_vertex.cl:60-70: first-hit normal (zero for a miss); path g owns pixel g, no atomics
+        {
+            float4 *dst = reinterpret_cast<float4 *>(fr.denoiserNormal) + gid;
+            const float4 prev = *dst, add = denoiser_normal(prm, t.v(FLX_S_N, gid));
+            *dst = make_float4(prev.x + add.x, prev.y + add.y, prev.z + add.z, prev.w + add.w);
+        }
         const int hitI = (int)t.u(FLX_S_HIT_I, gid);
         const bool hitLight = t.u(FLX_S_AREA_LIGHT_HIT, gid) != 0u;
         uint32_t phase = (uint32_t)MK_SAMPLE_BSDF;
@@ -245,6 +251,14 @@ __global__ void __launch_bounds__(FLX_BLOCK) k_mk_nee_prepare(const __grid_const
         uint32_t seed = t.u(FLX_S_SEED, gid);
         const MkVertex v = mk_load_vertex(t, gid, sc);
         list = mk_list_of(v.mat.type);
+        if (fr.denoiser && !v.singular && t.u(FLX_S_FIRST_DIFFUSE, gid) == 0u) // mk_sample_bsdf.cl:56-66
+        {
+            t.setu(FLX_S_FIRST_DIFFUSE, gid, 1u);
+            const V3 albedo = mat_float3(v.mat.Kd, v.s.u, v.s.v, v.mat.map_Kd, sc); // not gamma-corrected
+            float4 *dst = reinterpret_cast<float4 *>(fr.denoiserAlbedo) + gid;
+            const float4 prev = *dst;
+            *dst = make_float4(prev.x + albedo.x, prev.y + albedo.y, prev.z + albedo.z, prev.w + 1.0f);
+        }
         if (prm.sampleExpl && !v.singular)
         {
             x.setv(MK_X_ORIG, gid, v.orig);

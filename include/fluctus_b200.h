@@ -144,6 +144,15 @@ int flx_enqueue_materials(flx_ctx *ctx); /* 5 per-type kernels or the single-que
 int flx_enqueue_postprocess(flx_ctx *ctx);
 int flx_read_preview(flx_ctx *ctx, float *rgba, size_t n_pixels);
 
+/* Denoiser feature buffers (reference: Tracer::useDenoiser -> -DUSE_OPTIX_DENOISER on the logic, nextVertex, sampleBsdf and
+ * post-process kernels, src/kernel_impl.hpp:53,346,380,443; the code is src/wf_logic.cl:186-209, src/mk_next_vertex.cl:60-70,
+ * src/mk_sample_bsdf.cl:56-66, src/mk_postprocess.cl:49-54).  While enabled, both integrators accumulate the first-hit shading
+ * normal in camera space and the albedo at the path's first non-singular vertex per pixel (RGB sums, w = sample count), and the
+ * display pass also writes both divided by their count.  The OptiX denoiser itself is not part of this library: attach any.
+ * flx_read_denoiser_aov: which 0 = normal, 1 = albedo; processed 0 = raw accumulator, 1 = display-pass output. */
+int flx_set_denoiser(flx_ctx *ctx, int enabled);
+int flx_read_denoiser_aov(flx_ctx *ctx, int which, int processed, float *rgba, size_t n_pixels);
+
 /* The reference's other integrator, the "microkernel" path tracer (one path per pixel, a phase word per path): the one
  * Tracer::renderSingle uses for final frames with an exact sample count per pixel (src/tracer.cpp:95-169) and the
  * non-wavefront branch of Tracer::update (src/tracer.cpp:267-299).  CLContext::enqueueResetKernel / enqueueRayGenKernel /
@@ -186,6 +195,7 @@ int flx_timer_end(flx_ctx *ctx, float *elapsed_ms);
 enum { FLX_TUNE_TRACE_VARIANT = 0,      /* 0: one ray per thread; 1 (default): persistent threads with dynamic ray fetch, while-while phases; 2: 1 + the
                                            top-of-tree treelet staged in shared memory by the bulk-copy engine, one CTA per SM; 3: persistent threads, one
                                            step of the majority kind (inner node / one triangle) per iteration (flx_trace_greedy.cuh; measured equal to 1) */
+       FLX_TUNE_GATHER_PRIORITY = 21,   /* stream priority of the NCCL gather: 0 (default) lowest, 1 = the render stream's; set before the first gather */
        FLX_TUNE_INNER_BIAS = 20,        /* variant 3: run an inner-node step when lanes-at-inner + bias >= lanes-at-a-triangle (default 0) */
        FLX_TUNE_FETCH_THRESHOLD = 1,    /* persistent variant: refill a warp when fewer lanes than this hold a ray (default 16) */
        FLX_TUNE_TRACE_BLOCKS_PER_SM = 2,/* variant 1: resident CTAs per SM, 0 = occupancy calculator */

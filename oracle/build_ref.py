@@ -57,6 +57,21 @@ KERNEL_TUS = {
     "mk_splat_preview": ("REF_TU_MK_SPLAT_PREVIEW", []),
 }
 
+WF = ["reset", "raygen", "ext", "shadow", "logic_single", "logic_separate", "mat_all", "mat_diffuse", "mat_glossy", "mat_ggx_refl", "mat_ggx_refr", "mat_delta", "postprocess"]
+# Variants of the build, for the self-consistency pins of SURVEY 8(c) and the denoiser feature buffers.  Each: symbol infix ->
+# (kernels, defines added, defines removed, also the OpenMP flavour?).  The base build ("" infix) is every kernel with
+# -DUSE_SOA, the explicit-stack traversal and include/flx_math.h.
+VARIANTS = {
+    # the reference's kernels as built with Tracer::useDenoiser (src/kernel_impl.hpp:53,346,380,443)
+    "dn_": (["logic_single", "logic_separate", "mk_next_vertex", "mk_sample_bsdf", "postprocess"], ["USE_OPTIX_DENOISER"], [], False),
+    # stackless "bit stack" traversal (src/bvh.cl:10-230; Settings::getUseBitstack, src/clcontext.cpp:147): must find the same hits
+    "bs_": (["ext", "shadow"], ["USE_BITSTACK"], [], False),
+    # array-of-structures path state (no -DUSE_SOA: the macros of src/geom.h:26-37): must compute the same state
+    "aos_": (WF, [], ["USE_SOA"], False),
+    # the C library's sinf / cosf / ... instead of include/flx_math.h (cl_shim.hpp SHIM_LIBM): the independent-math oracle
+    "lm_": (WF, ["SHIM_LIBM"], [], True),
+}
+
 VEC_LITERAL = re.compile(r"\((v?float[234]|int2)\)\(")
 
 
@@ -112,16 +127,28 @@ def build(force=False):
                   "-DGPU", "-DUSE_SOA", "-DAPPLE_SILICON", "-I", SHIM, "-I", INC, "-I", gen]
         jobs = []
         objs = []
-        for name, (tu, defs) in KERNEL_TUS.items():
+
+        def add(name, variant, extra, drop, par):
+            tu, defs = KERNEL_TUS[name]
+            obj = os.path.join(tmp, "%s%s%s.o" % (variant, name, "_par" if par else ""))
+            cmd = [c for c in common if c not in ["-D" + d for d in drop]] + ["-D" + tu] + ["-D" + d for d in defs + extra]
+            if variant:
+                cmd.append("-DREF_VARIANT=" + variant)
+            if par:
+                # the reference builds with -DFLT_FLOAT_ATOMICS (clcontext.cpp:145); needed once work-items run concurrently
+                cmd += ["-DSHIM_PARALLEL", "-DFLT_FLOAT_ATOMICS", "-fopenmp", "-O3", "-march=x86-64-v3"]
+            cmd += ["-c", os.path.join(SHIM, "ref_kernels.cpp"), "-o", obj]
+            jobs.append(cmd)
+            objs.append(obj)
+
+        for name in KERNEL_TUS:
             for par in (False, True):
-                obj = os.path.join(tmp, "%s%s.o" % (name, "_par" if par else ""))
-                cmd = common + ["-D" + tu] + ["-D" + d for d in defs]
-                if par:
-                    # the reference builds with -DFLT_FLOAT_ATOMICS (clcontext.cpp:145); needed once work-items run concurrently
-                    cmd += ["-DSHIM_PARALLEL", "-DFLT_FLOAT_ATOMICS", "-fopenmp", "-O3", "-march=x86-64-v3"]
-                cmd += ["-c", os.path.join(SHIM, "ref_kernels.cpp"), "-o", obj]
-                jobs.append(cmd)
-                objs.append(obj)
+                add(name, "", [], [], par)
+        for variant, (kernels, extra, drop, with_par) in VARIANTS.items():
+            for name in kernels:
+                add(name, variant, extra, drop, False)
+                if with_par:
+                    add(name, variant, extra, drop, True)
         with ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
             list(ex.map(_run, jobs))
         _run(["g++", "-shared", "-fopenmp", "-o", lib] + objs)

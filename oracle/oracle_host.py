@@ -29,7 +29,7 @@ class RefBufs(C.Structure):  # oracle/ref_shim/ref_abi.h
                 ("envW", C.c_int32), ("envH", C.c_int32), ("probTable", C.c_void_p), ("aliasTable", C.c_void_p), ("pdfTable", C.c_void_p),
                 ("materials", C.c_void_p), ("texData", C.c_void_p), ("textures", C.c_void_p), ("params", C.c_void_p),
                 ("currPixelIdx", C.c_void_p), ("numTasks", C.c_uint32), ("firstIteration", C.c_uint32), ("pixelsPreview", C.c_void_p),
-                ("stats", C.c_void_p)]
+                ("stats", C.c_void_p), ("denoiserAlbedoGL", C.c_void_p), ("denoiserNormalGL", C.c_void_p)]
 
 
 QUEUE_FIELDS = ("raygenQueue", "extensionQueue", "shadowQueue", "diffuseQueue", "glossyQueue", "ggxReflQueue", "ggxRefrQueue", "deltaQueue")
@@ -50,8 +50,11 @@ class _CpuContext:
     LIB = None
     PREFIX = None
 
-    def __init__(self, num_tasks, parallel=False, parallel_trace=False):
-        """parallel: every kernel through the OpenMP build (CPU baseline; queue order then depends on thread timing).
+    def __init__(self, num_tasks, parallel=False, parallel_trace=False, variant=""):
+        """variant: one of the extra builds of oracle/build_ref.py -- "dn_" (USE_OPTIX_DENOISER: feature buffers), "bs_" (USE_BITSTACK
+        traversal), "aos_" (no USE_SOA: array-of-structures path state), "lm_" (C-library math instead of include/flx_math.h).  A
+        kernel the variant does not rebuild comes from the base build.
+        parallel: every kernel through the OpenMP build (CPU baseline; queue order then depends on thread timing).
         parallel_trace: only the two traversal kernels through the OpenMP build -- they push to no queue and every work-item
         writes its own path's slots only, so the result is the serial one; what stays serial (reset, raygen, logic, materials)
         is what decides queue order.  This is the deterministic oracle for the full-size parity tests."""
@@ -60,9 +63,12 @@ class _CpuContext:
         self.lib = C.CDLL(self.LIB)
         self.prefix = self.PREFIX + ("par_" if parallel else "")
         self.trace_prefix = self.PREFIX + ("par_" if (parallel or parallel_trace) else "")
+        self.variant = variant
+        self.aos = variant == "aos_"
         self.NUM_TASKS = int(num_tasks)
         n = self.NUM_TASKS
-        self.tasks = np.zeros((64, n), np.uint32)
+        # path state: structure of arrays [slot][path] -- or, in the AoS build, N structs of 64 words (src/geom.h:199-236)
+        self.tasks = np.zeros((n, 64) if self.aos else (64, n), np.uint32)
         self.queues = {q: np.zeros(n, np.uint32) for q in QUEUE_FIELDS}
         self.counters = np.zeros(8, np.uint32)
         self.currPixelIdx = np.zeros(1, np.uint32)
@@ -99,6 +105,8 @@ class _CpuContext:
         self.albedo = np.zeros_like(self.pixels)
         self.normal = np.zeros_like(self.pixels)
         self.preview = np.zeros_like(self.pixels)
+        self.albedo_out = np.zeros_like(self.pixels)
+        self.normal_out = np.zeros_like(self.pixels)
 
     def updateParams(self, params):
         C.memmove(self.params_buf.ctypes.data, C.byref(params), 240)
@@ -123,10 +131,17 @@ class _CpuContext:
         b.numTasks, b.firstIteration = self.NUM_TASKS, first
         b.pixelsPreview = p(self.preview)
         b.stats = p(self.render_stats)
+        b.denoiserAlbedoGL, b.denoiserNormalGL = p(self.albedo_out), p(self.normal_out)
         return b
 
     def _run(self, name, n, first=0):
-        fn = getattr(self.lib, (self.trace_prefix if name in ("ext", "shadow") else self.prefix) + name)
+        base = self.trace_prefix if name in ("ext", "shadow") else self.prefix
+        try:
+            fn = getattr(self.lib, base + self.variant + name)
+        except AttributeError:
+            if self.aos:
+                raise  # every kernel must agree on the path-state layout
+            fn = getattr(self.lib, base + name)
         fn.argtypes = [C.POINTER(RefBufs), C.c_size_t, C.c_size_t]
         fn.restype = None
         b = self._bufs(first)
@@ -220,10 +235,17 @@ class _CpuContext:
         return self.pixels.copy()
 
     def readTasks(self):
-        return self.tasks.copy()
+        return np.ascontiguousarray(self.tasks.T) if self.aos else self.tasks.copy()
 
     def writeTasks(self, slots):
-        self.tasks[...] = slots
+        self.tasks[...] = slots.T if self.aos else slots
+
+    def setDenoiser(self, enabled):
+        assert bool(enabled) == (self.variant == "dn_"), "the feature buffers are a build option of the reference: RefContext(n, variant='dn_')"
+
+    def readDenoiserAOV(self, which, processed=False):
+        src = {("normal", False): self.normal, ("albedo", False): self.albedo, ("normal", True): self.normal_out, ("albedo", True): self.albedo_out}
+        return src[(which, bool(processed))].copy()
 
     def readQueue(self, name, n=None):
         q = self.queues[QUEUE_FIELDS[QUEUE_NAMES.index(name)]]

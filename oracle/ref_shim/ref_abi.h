@@ -30,5 +30,7 @@ typedef struct
     uint32_t firstIteration;
     float *pixelsPreview;   /* W*H float4, output of the post-process kernel (GL PBO in the reference) */
     uint32_t *stats;        /* RenderStats {primaryRays, extensionRays, shadowRays, samples} (geom.h:254-260), microkernel integrator */
+    float *denoiserAlbedoGL; /* W*H float4 each: outputs of the post-process kernel when built with USE_OPTIX_DENOISER */
+    float *denoiserNormalGL;
 } RefBufs;
 #endif

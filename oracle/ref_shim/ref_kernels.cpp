@@ -52,12 +52,20 @@ namespace
 #endif
 } // namespace
 
+// REF_VARIANT (build_ref.py: -DREF_VARIANT=dn_ / bs_ / aos_ / lm_) goes into the exported names, so that the same kernel built
+// with other reference build options (USE_OPTIX_DENOISER, USE_BITSTACK, without USE_SOA) or with the C library's math lives
+// beside the base build in one library: ref_<variant><kernel>, ref_par_<variant><kernel>.
+#ifndef REF_VARIANT
+#define REF_VARIANT
+#endif
+#define REF_CAT3_(a, b, c) a##b##c
+#define REF_CAT3(a, b, c) REF_CAT3_(a, b, c)
 #ifdef SHIM_PARALLEL
 #define REF_LOOP _Pragma("omp parallel for schedule(dynamic, 4096)") for (long long g = (long long)begin; g < (long long)end; ++g)
-#define REF_NAME(n) ref_par_##n
+#define REF_NAME(n) REF_CAT3(ref_par_, REF_VARIANT, n)
 #else
 #define REF_LOOP for (long long g = (long long)begin; g < (long long)end; ++g)
-#define REF_NAME(n) ref_##n
+#define REF_NAME(n) REF_CAT3(ref_, REF_VARIANT, n)
 #endif
 
 #define T(b) ((GPUTaskState *)(b)->tasks)
@@ -80,7 +88,7 @@ extern "C"
     }
 #ifndef SHIM_PARALLEL
     // layout facts the rest of the repo relies on, checked by tests
-    void ref_layout(uint32_t out[8])
+    void REF_NAME(layout)(uint32_t out[8])
     {
         out[0] = sizeof(GPUTaskState); out[1] = sizeof(GPUNode); out[2] = sizeof(Triangle); out[3] = sizeof(Material);
         out[4] = sizeof(RenderParams); out[5] = sizeof(QueueCounters); out[6] = sizeof(TexDescriptor); out[7] = sizeof(Hit);
@@ -131,7 +139,7 @@ extern "C"
 #elif defined(REF_TU_POSTPROCESS)
     void REF_NAME(postprocess)(const RefBufs *b, size_t begin, size_t end)
     {
-        REF_LOOP { g_shim_gid = (size_t)g; process(b->pixels, b->denoiserAlbedo, b->denoiserNormal, b->pixelsPreview, b->denoiserAlbedo, b->denoiserNormal, P(b), b->numTasks); }
+        REF_LOOP { g_shim_gid = (size_t)g; process(b->pixels, b->denoiserAlbedo, b->denoiserNormal, b->pixelsPreview, b->denoiserAlbedoGL, b->denoiserNormalGL, P(b), b->numTasks); }
     }
 #elif defined(REF_TU_MK_RESET)
     void REF_NAME(mk_reset)(const RefBufs *b, size_t begin, size_t end)

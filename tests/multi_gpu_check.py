@@ -28,6 +28,12 @@ def main():
     assert ctx.tilePixels() == fd.tile_pixels(W, H, rank, world, S)
     tr = Tracer(ctx, params)
     tr.start()
+    # every rank runs the same path indices: their random sequences must differ (seed = gid + part * numTasks, k_reset), or the
+    # noise pattern would repeat from stripe to stripe of the gathered image
+    from fluctus_b200 import SLOT
+    seeds = [None] * world
+    dist.all_gather_object(seeds, ctx.readTasks()[SLOT.SEED, :64].tolist())
+    assert len({tuple(s) for s in seeds}) == world, "ranks share random sequences"
     ctx.render(64)
     tile = ctx.readPixels()
     full = np.zeros((W * H, 4), np.float32) if rank == 0 else None
@@ -50,6 +56,36 @@ def main():
         rel = np.abs(m1 - m2) / m2
         assert (rel < 0.03).all(), (m1, m2)
         print("MULTI_GPU_OK world=%d mean radiance tiled %s untiled %s" % (world, m1, m2))
+    # asynchronous gathers every iteration (own stream, double-buffered snapshot) must not disturb the render, and the frame
+    # delivered is the accumulator as of each call
+    ctx.gatherPixels(0)
+    for _ in range(5):
+        ctx.render(1)
+        ctx.gatherPixels(0)
+    tile = ctx.readPixels()
+    full2 = np.zeros((W * H, 4), np.float32) if rank == 0 else None
+    ctx.gatherPixels(0, full2)
+    ref2 = fd.gather_host(tile, W, H, S, root=0)
+    if rank == 0:
+        assert np.array_equal(full2, ref2), "gather after a run of asynchronous gathers differs from the host-side gather"
+    # a new image size with the same communicator: ragged 64x9 first, then 64x16 (the full-image buffer kept its
+    # old, smaller size); ranks that own no rows of the small image sit that one out
+    for (w2, h2) in ((64, 9), (64, 16)):
+        p2 = room_params(scene, w2, h2, max_bounces=3, separate_queues=True)
+        if fd.tile_pixels(w2, h2, rank, world, 8) == 0 or world > 2:
+            continue
+        ctx.setTile(rank, world, 8)
+        ctx.setupPixelStorage(w2, h2)
+        t3 = Tracer(ctx, p2)
+        t3.start()
+        ctx.render(8)
+        tile = ctx.readPixels()
+        fullr = np.zeros((w2 * h2, 4), np.float32) if rank == 0 else None
+        ctx.gatherPixels(0, fullr)
+        refr = fd.gather_host(tile, w2, h2, 8, root=0)
+        if rank == 0:
+            assert np.array_equal(fullr, refr), "gather after resize to %dx%d" % (w2, h2)
+            print("RESIZE_GATHER_OK %dx%d" % (w2, h2))
     ctx.close()
     dist.barrier()
     dist.destroy_process_group()
