@@ -6,8 +6,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 OUT = os.path.join(os.path.dirname(HERE), "libfluctus_b200.so")
-SOURCES = ["flx_api.cu", "flx_scene_io.cpp"]
-DEPS = ["flx_api.cu", "flx_scene_io.cpp", "flx_kernels.cuh", "flx_mk.cuh", "flx_bvh_build.cuh", "flx_bvh_repack.cuh", "flx_trace.cuh", "flx_trace_persistent.cuh", "flx_bsdf.cuh", "flx_device.cuh", os.path.join(ROOT, "include", "fluctus_b200.h"),
+SOURCES = ["flx_api.cu", "flx_scene_io.cpp", "flx_jpeg.cpp"]
+DEPS = ["flx_api.cu", "flx_scene_io.cpp", "flx_jpeg.cpp", "flx_trace_greedy.cuh", "flx_kernels.cuh", "flx_mk.cuh", "flx_bvh_build.cuh", "flx_bvh_repack.cuh", "flx_trace.cuh", "flx_trace_persistent.cuh", "flx_bsdf.cuh", "flx_device.cuh", os.path.join(ROOT, "include", "fluctus_b200.h"),
         os.path.join(ROOT, "include", "flx_math.h"), "build.py"]
 # -fmad=false + IEEE div/sqrt + no ftz: arithmetic is bit-identical to the host oracle (DESIGN.md "Numerics")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false", "-prec-div=true", "-prec-sqrt=true",

@@ -31,6 +31,8 @@
 
 #include "fluctus_b200.h"
 
+bool flx_decode_jpeg(const std::string &path, uint32_t &w, uint32_t &h, std::vector<unsigned char> &rgba, std::string &error); // flx_jpeg.cpp
+
 namespace
 {
 thread_local std::string g_io_error;
@@ -1536,8 +1538,8 @@ try
 }
 FLX_IO_CATCH
 
-// Decode one image file to RGBA8 with the reference's conventions (4 channels, row 0 = bottom row).  PNG only (see decode_png);
-// the buffer belongs to the library until flx_image_free.
+// Decode one image file to RGBA8 with the reference's conventions (4 channels, row 0 = bottom row): PNG (decode_png above) and
+// JPEG (flx_jpeg.cpp), the two formats the reference's scenes use.  The buffer belongs to the library until flx_image_free.
 int flx_image_load(const char *path, uint32_t *width, uint32_t *height, uint8_t **rgba)
 try
 {
@@ -1550,15 +1552,23 @@ try
     std::string lower(path);
     for (char &c : lower)
         c = (char)std::tolower((unsigned char)c);
-    if (!ends_with(lower, ".png"))
-    {
-        g_io_error = std::string(path) + ": only PNG is decoded here (JPEG is lossy and decoder-dependent: pass such textures decoded)";
-        return FLX_E_INVALID;
-    }
     std::vector<unsigned char> pixels;
     uint32_t w = 0, h = 0;
-    if (!decode_png(path, w, h, pixels))
+    if (ends_with(lower, ".png"))
+    {
+        if (!decode_png(path, w, h, pixels))
+            return FLX_E_INVALID;
+    }
+    else if (ends_with(lower, ".jpg") || ends_with(lower, ".jpeg") || ends_with(lower, ".jpe"))
+    {
+        if (!flx_decode_jpeg(path, w, h, pixels, g_io_error))
+            return FLX_E_INVALID;
+    }
+    else
+    {
+        g_io_error = std::string(path) + ": unsupported image format (PNG and JPEG are decoded)";
         return FLX_E_INVALID;
+    }
     uint8_t *out = (uint8_t *)std::malloc(pixels.size());
     if (!out)
     {

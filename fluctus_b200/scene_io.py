@@ -102,8 +102,20 @@ def import_hierarchy(path):
     return nodes, indices
 
 
+def load_model_with_textures(path):
+    """Everything flx_upload_scene needs except the hierarchy, from files only: the model (flx_scene_load), its textures decoded by the
+    library (flx_image_load: PNG and JPEG) and packed like CLContext::packTextures (flx_pack_textures).  Texture names are relative
+    to the model's folder (src/scene.cpp:281-295).  Returns (LoadedModel, tex_desc, tex_data)."""
+    import os
+    model = load_model(path)
+    folder = os.path.dirname(os.path.abspath(str(path)))
+    images = [load_image(os.path.join(folder, name.replace("\\", "/"))) for name in model.texture_names]
+    desc, blob = pack_textures(images)
+    return model, desc, blob
+
+
 def load_image(path):
-    """PNG -> (h, w, 4) uint8, row 0 = bottom row, the reference's in-memory texture form (flx_image_load)."""
+    """PNG or JPEG -> (h, w, 4) uint8, row 0 = bottom row, the reference's in-memory texture form (flx_image_load)."""
     lib = _lib.load()
     w, h, ptr = C.c_uint32(), C.c_uint32(), C.c_void_p()
     if lib.flx_image_load(str(path).encode(), C.byref(w), C.byref(h), C.byref(ptr)) != 0:

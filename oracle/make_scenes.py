@@ -30,6 +30,10 @@ SCENES = {
     "egyptcat": ("obj", "assets/egyptcat/egyptcat.obj"),  # first scene of the reference's own benchmark protocol (tracer.cpp:384-389)
 }
 ENVMAPS = {"night": "assets/env_maps/night.hdr"}
+# Asset FILES that travel as they are (oracle/_ref/assets/, git-ignored like the blobs): the inputs of the "from files only" tests --
+# model + materials + JPEG / PNG textures + environment map through the library's own loaders and decoders, no blob, no Pillow.
+ASSET_DIRS = {"country_kitchen": "assets/country_kitchen", "env_maps": "assets/env_maps"}
+ASSETS_OUT = os.path.join(HERE, "_ref", "assets")
 
 
 def build(names=None, force=False):
@@ -59,6 +63,19 @@ def build(names=None, force=False):
             if getattr(scene, "texture_names", None):
                 np.savez_compressed(side, desc=scene.tex_desc.view(np.uint32).reshape(-1, 3), data=scene.tex_data)
                 made.append(side)
+    import shutil
+    for name, rel in ASSET_DIRS.items():
+        if names and name not in names:
+            continue
+        dst = os.path.join(ASSETS_OUT, name)
+        if force or not os.path.isdir(dst):
+            shutil.rmtree(dst, ignore_errors=True)
+            if name == "env_maps":  # only the map the benchmark configuration uses
+                os.makedirs(dst)
+                shutil.copy(os.path.join(ref, rel, "night.hdr"), dst)
+            else:
+                shutil.copytree(os.path.join(ref, rel), dst)
+        made.append(dst)
     for name, rel in ENVMAPS.items():
         if names and name not in names:
             continue
@@ -73,4 +90,4 @@ def build(names=None, force=False):
 
 if __name__ == "__main__":
     for p in build(sys.argv[1:] and [a for a in sys.argv[1:] if not a.startswith("-")] or None, force="--force" in sys.argv):
-        print(p, os.path.getsize(p))
+        print(p, os.path.getsize(p) if os.path.isfile(p) else "(directory)")

@@ -101,7 +101,7 @@ def check_closed_form(make_ctx, width=40, height=30, iterations=160):
         img = out[name].astype(np.float64)
         assert np.abs(img[outside] / L - 1).max() < 2e-5, "%s: environment pixels are not L" % name
         rel = img[inside] / (ALBEDO * L) - 1
-        assert abs(rel.mean()) < 0.01, "%s sampling is biased on the object: mean relative error %.4f" % (name, rel.mean())
+        assert abs(rel.mean()) < 0.015, "%s sampling is biased on the object: mean relative error %.4f" % (name, rel.mean())
         rms = float(np.sqrt((rel ** 2).mean()))
         assert rms < 0.3 and np.abs(rel).max() < 1.5, "%s: pixels scatter too far around the closed form (rms %.3f, max %.3f)" % (name, rms, np.abs(rel).max())
     return out

@@ -238,3 +238,25 @@ def test_country_kitchen_c3_small():
     params = kitchen_params(scene, W, H)
     with CLContext(W * H) as gpu:
         run_lockstep(gpu, oracle_ctx(W * H), scene, params, iterations=12, env=env, check_every=4)
+
+
+def test_country_kitchen_c3_from_files_only():
+    """C3 with no blob, no reference code and no Pillow on the way in: Country-Kitchen.obj + .mtl through flx_scene_load, its JPEG
+    and PNG textures through flx_image_load + flx_pack_textures, night.hdr through flx_envmap_load, the hierarchy from the GPU
+    builder -- rendered in lockstep with the reference's kernels on the same arrays."""
+    import os
+    from fluctus_b200.scene_io import load_envmap, load_model_with_textures
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "assets")
+    obj, hdr = os.path.join(root, "country_kitchen", "Country-Kitchen.obj"), os.path.join(root, "env_maps", "night.hdr")
+    if not (os.path.exists(obj) and os.path.exists(hdr)):
+        pytest.skip("asset files not under oracle/_ref/assets (oracle/make_scenes.py copies them where /root/reference exists)")
+    model, desc, data = load_model_with_textures(obj)
+    env = load_envmap(hdr)
+    from bench_configs import kitchen_params
+    W, H = 96, 54
+    with CLContext(W * H) as gpu:
+        nodes, idx, ms = gpu.buildBVH(model.tris, 8, "ploc")
+        scene = SceneData(model.tris, idx, nodes, model.materials, desc, data)
+        params = kitchen_params(scene, W, H)
+        tg, tc = run_lockstep(gpu, oracle_ctx(W * H), scene, params, iterations=12, env=env, check_every=4)
+        assert tg.stats["extensionRays"] > 0 and len(model.texture_names) == 11

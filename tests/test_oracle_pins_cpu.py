@@ -59,7 +59,7 @@ def test_single_and_separate_material_queues_compute_the_same_paths():
 
 def test_white_furnace_closed_form_and_estimators_agree():
     from furnace_util import check_closed_form
-    check_closed_form(lambda n: RefContext(n), width=32, height=24, iterations=96)
+    check_closed_form(lambda n: RefContext(n, parallel_trace=True), width=40, height=30, iterations=200)
 
 
 def test_libm_math_oracle_agrees_within_monte_carlo_error():

@@ -428,6 +428,124 @@ def test_png_decoder_matches_an_independent_decoder(tmp_path):
         load_image(bad)
 
 
+def _pillow_rgba(path):
+    from PIL import Image
+    im = Image.open(path)
+    assert im.mode in ("RGB", "L"), im.mode
+    return np.ascontiguousarray(np.asarray(im.convert("RGBA"))[::-1])
+
+
+def test_jpeg_decoder_matches_libjpeg_bit_for_bit(tmp_path):
+    """flx_image_load on JPEG against Pillow (libjpeg-turbo, the IJG decoder family DevIL uses too): IDENTICAL bytes on files that
+    cover every branch of flx_jpeg.cpp -- baseline and progressive, 4:4:4 / 4:2:2 / 4:2:0, grey, qualities 5..100 (the 16-bit-table
+    and clamping corners), optimised Huffman tables, restart intervals, sizes that are not multiples of the MCU, 1x1."""
+    from PIL import Image
+    from fluctus_b200.scene_io import load_image
+    rng = np.random.default_rng(1)
+
+    def picture(h, w, c):
+        yy, xx = np.mgrid[0:h, 0:w]
+        img = np.stack([(np.sin(xx / 7.0 + k) + np.cos(yy / 5.0 * (k + 1))) * 60 + 128 + rng.normal(0, 12, (h, w)) for k in range(c)], -1)
+        return np.clip(img, 0, 255).astype(np.uint8)
+
+    cases = 0
+    for (w, h) in ((1, 1), (7, 5), (16, 16), (17, 33), (250, 123)):
+        for mode in ("RGB", "L"):
+            img = picture(h, w, 3 if mode == "RGB" else 1)
+            im = Image.fromarray(img if mode == "RGB" else img[..., 0], mode)
+            for sub in ((0, 1, 2) if mode == "RGB" else (0,)):
+                for prog in (False, True):
+                    for q, extra in ((5, {}), (50, {}), (50, {"optimize": True}), (50, {"restart_marker_blocks": 3}), (50, {"restart_marker_rows": 1}), (92, {}), (100, {})):
+                        path = tmp_path / "t.jpg"
+                        kw = dict(quality=q, progressive=prog, **extra)
+                        if mode == "RGB":
+                            kw["subsampling"] = sub
+                        try:
+                            im.save(path, "JPEG", **kw)
+                        except (TypeError, OSError, ValueError):
+                            continue  # an encoder option this Pillow does not have
+                        got, want = load_image(path), _pillow_rgba(path)
+                        assert np.array_equal(got, want), "%dx%d %s subsampling %d progressive %s quality %d %r: %d pixels differ" % (
+                            w, h, mode, sub, prog, q, extra, int((got != want).any(axis=2).sum()))
+                        cases += 1
+    assert cases > 200
+
+
+def _kitchen_dir():
+    for root in (os.path.join(os.path.dirname(REF_ASSETS), "assets"), os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "assets")):
+        p = os.path.join(root, "country_kitchen")
+        if os.path.isdir(p):
+            return p
+    pytest.skip("the Country-Kitchen files are neither under /root/reference/assets nor under oracle/_ref/assets (oracle/make_scenes.py)")
+
+
+def test_reference_jpeg_textures_decode_like_libjpeg():
+    """the reference's own JPEGs (11 in Country Kitchen: 8 baseline with restart intervals, 2 progressive, 1 with 4:2:0 chroma,
+    most with an Adobe marker and no JFIF marker) -- identical to Pillow"""
+    from fluctus_b200.scene_io import load_image
+    import glob
+    files = sorted(glob.glob(os.path.join(_kitchen_dir(), "textures", "*.jpg")))
+    assert len(files) == 11
+    for f in files:
+        assert np.array_equal(load_image(f), _pillow_rgba(f)), os.path.basename(f)
+
+
+def test_country_kitchen_from_files_only_equals_the_blob_the_parity_tests_use():
+    """C3 through the library alone -- flx_scene_load (OBJ + MTL), flx_image_load (its JPEG and PNG textures), flx_pack_textures --
+    gives exactly the triangles, materials, texture descriptors and texture bytes of the scene blob (made by the reference's loader
+    code + Pillow) that the GPU parity tests render.  So what those tests pin holds for the files-only path."""
+    from fluctus_b200 import SceneData
+    from fluctus_b200.scene_io import load_model_with_textures
+    blob = SceneData.load_blob(scene_blob("country_kitchen"))
+    model, desc, data = load_model_with_textures(os.path.join(_kitchen_dir(), "Country-Kitchen.obj"))
+    assert model.texture_names == blob.texture_names and len(model.texture_names) == 11  # 9 JPEG + 2 PNG files, used by 17 map_Kd / map_Bump entries
+    assert model.tris.tobytes() == blob.tris.tobytes() and model.materials.tobytes() == blob.materials.tobytes()
+    assert desc.tobytes() == blob.tex_desc.tobytes()
+    assert np.array_equal(data, blob.tex_data)
+
+
+def test_malformed_jpeg_files_are_rejected_or_decoded_never_crashed_on(tmp_path):
+    """truncations and byte flips of a baseline and a progressive file: every outcome is an error or a picture of the announced
+    size (the IJG decoder also carries on over corrupt entropy data); arithmetic-coded / 12-bit / CMYK files are refused by name"""
+    from PIL import Image
+    from fluctus_b200.scene_io import load_image
+    rng = np.random.default_rng(7)
+    img = (rng.uniform(0, 255, (40, 56, 3))).astype(np.uint8)
+    outcomes = {"error": 0, "picture": 0}
+    for prog in (False, True):
+        src = tmp_path / "src.jpg"
+        Image.fromarray(img, "RGB").save(src, "JPEG", quality=80, progressive=prog, subsampling=2)
+        raw = src.read_bytes()
+        mutants = [raw[:k] for k in (0, 1, 2, 3, 10, 100, len(raw) // 2, len(raw) - 2)]
+        for _ in range(150):
+            b = bytearray(raw)
+            for _k in range(int(rng.integers(1, 4))):
+                b[int(rng.integers(2, len(b)))] = int(rng.integers(0, 256))
+            mutants.append(bytes(b))
+        for m in mutants:
+            p = tmp_path / "m.jpg"
+            p.write_bytes(m)
+            try:
+                out = load_image(p)
+                assert out.ndim == 3 and out.shape[2] == 4 and out.size > 0
+                outcomes["picture"] += 1
+            except FluctusError:
+                outcomes["error"] += 1
+    assert outcomes["error"] > 10 and outcomes["picture"] > 10, outcomes
+    cmyk = tmp_path / "cmyk.jpg"
+    Image.fromarray(np.zeros((8, 8, 4), np.uint8), "CMYK").save(cmyk, "JPEG")
+    with pytest.raises(FluctusError, match="three-component"):
+        load_image(cmyk)
+    soft = bytearray((tmp_path / "src.jpg").read_bytes())
+    i = soft.index(b"\xff\xc2")
+    soft[i + 1] = 0xCA  # progressive, arithmetic coding
+    (tmp_path / "arith.jpg").write_bytes(bytes(soft))
+    with pytest.raises(FluctusError, match="arithmetic"):
+        load_image(tmp_path / "arith.jpg")
+    with pytest.raises(FluctusError, match="unsupported image format"):
+        load_image(tmp_path / "picture.bmp")
+
+
 def test_texture_packing_matches_packTextures():
     """flx_pack_textures = CLContext::packTextures (src/clcontext.cpp:570-611); same descriptors and blob as the Python helper the
     scene blobs were made with, and -- where the reference's assets are present -- the egyptcat texture decoded + packed in C
