@@ -304,7 +304,9 @@ def main_ours(args):
             barrier()
             t0 = time.perf_counter()
             ctx.uploadSceneData(host_scene)
+            ta = time.perf_counter()
             ctx.setupPixelStorage(params.width, params.height)
+            tb = time.perf_counter()
             tr = Tracer(ctx, params)
             tr.start()
             t1 = time.perf_counter()
@@ -320,13 +322,15 @@ def main_ours(args):
             rays = tr.stats["extensionRays"] + tr.stats["shadowRays"]
             rays = fd.reduce_scalars([float(rays)])[0]
             dt, setup, loop, read = fd.reduce_scalars([t3 - t0, t1 - t0, t2 - t1, t3 - t2], "max")
-            runs.append(dict(value=rays / dt / 1e6, seconds=dt, setup_ms=setup * 1e3, per_iteration_ms=loop * 1e3 / n_it, readback_ms=read * 1e3))
+            runs.append(dict(value=rays / dt / 1e6, seconds=dt, setup_ms=setup * 1e3, per_iteration_ms=loop * 1e3 / n_it, readback_ms=read * 1e3,
+                             setup_split_ms=[round((ta - t0) * 1e3, 3), round((tb - ta) * 1e3, 3), round((t1 - tb) * 1e3, 3)]))
         med = sorted(runs, key=lambda r: r["value"])[len(runs) // 2]
         d2h = host_image.nbytes if rank == 0 else 0
         e2e = {"value": med["value"], "unit": UNIT, "h2d_bytes_per_step": int(world * (scene.nbytes() + 240) / n_it + 36 * world),
                "d2h_bytes_per_step": int(d2h / n_it + 32 * world), "iterations": n_it, "seconds": round(med["seconds"], 6),
                "setup_ms": round(med["setup_ms"], 3), "per_iteration_ms": round(med["per_iteration_ms"], 4), "readback_ms": round(med["readback_ms"], 3),
-               "runs": [round(r["value"], 1) for r in runs], "host_memory": "page-locked (flx_host_alloc)",
+               "runs": [round(r["value"], 1) for r in runs], "setup_split_ms": {"uploadSceneData, setupPixelStorage, Tracer.start (rank 0, per run)": [r["setup_split_ms"] for r in runs]},
+               "host_memory": "page-locked (flx_host_alloc)",
                "what": "host scene arrays -> uploadSceneData + setupPixelStorage + Tracer.start (setup_ms), per-stage enqueue calls with counter read-back and finishQueue "
                        "every iteration (tracer.cpp:431-470; per_iteration_ms), %s (readback_ms); wall clock, max over ranks, median of %d runs"
                        % ("readPixels" if world == 1 else "NCCL gather of the tiles into the root's host image", len(runs))}
@@ -431,8 +435,10 @@ def main_ours(args):
                                "frac_of_hbm_peak": round(own_ext * ext_rays_per_launch / ext_launch_s / 1e9 / peak, 4) if ext_ms else None,
                                "what": "64 B per inner-node visit + 64 B per triangle test + 112 B attributes + 84 B path state: what the kernel's own loads and stores "
                                        "request (served by L1/L2, not DRAM)"},
-                "issue": {k: prof.get(k) for k in ("threads_per_instruction", "issue_slot_utilization_pct", "l1tex_wavefronts_per_clk_per_sm", "l1_hit_pct", "l2_hit_pct",
-                                                   "registers", "achieved_occupancy_pct", "local_memory_wavefronts", "source", "file") if k in prof},
+                # what bounds the kernel (ncu, committed under profiles/): issue slots and the L1 data pipe, one wavefront per clock per SM at its peak
+                "issue": {k: prof.get(k) for k in ("threads_per_instruction", "issue_slot_utilization_pct", "l1tex_data_pipe_pct", "l1tex_wavefronts_per_clk_per_sm", "l1_hit_pct",
+                                                   "l2_hit_pct", "dram_throughput_pct", "registers", "achieved_occupancy_pct", "local_memory_requests", "duration_us", "source", "file")
+                          if k in prof},
                 "shadow": {"algorithmic_bytes_per_ray": round(a_sh, 1), "per_ray": per_sh, "avg_launch_ms": round(sh_ms / max(sh_n, 1), 4),
                            "achieved": round(a_sh * sh_rays_per_launch / (sh_ms / max(sh_n, 1) * 1e-3) / 1e9, 1) if sh_ms else None,
                            "mrays_per_s": round(sh_rays_per_launch / (sh_ms / max(sh_n, 1)) / 1e3, 1) if sh_ms else None},

@@ -7,10 +7,12 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <queue>
 #include <string>
 #include <type_traits>
@@ -121,6 +123,11 @@ struct flx_ctx
     bool otherTypes = false;     // BSDF types the scene does not contain are not launched; otherTypes: a type none of the lists knows
     bool sceneReady = false;
     size_t sceneBytes = 0;
+    // Device allocations are kept and reused while they are large enough (capacity by owning pointer variable): re-uploading a scene
+    // or re-creating the image at the same size costs no cudaMalloc / cudaFree -- which take tens of microseconds on a quiet box and
+    // have been seen to take hundreds of MILLIseconds on a shared one (gpurun_out/call_r2_07.log: uploadSceneData 75 .. 686 ms).
+    std::map<const void *, size_t> capacity;
+    unsigned char *repackPool = nullptr; // scratch of the device repack (nodes, indices, scans), kept between uploads
     uint64_t sceneHash = 0;      // fingerprint of the uploaded scene (sizes, materials, a sample of nodes and triangles): checkpoints carry it
 
     // environment map
@@ -154,6 +161,7 @@ struct flx_ctx
     flx_RenderParams params;
     bool paramsSet = false;
     float tanHalfFov = 0.0f;
+    int pinholeCamera = 0;    // the thin-lens offset is exactly zero for every sample (lens_offset, flx_kernels.cuh)
 
     // traversal work counters (flx_set_counting): [0..4] extension V,B,T,U,rays  [5..9] shadow V,B,T,U,rays
     unsigned long long *traceCounts = nullptr;
@@ -162,6 +170,7 @@ struct flx_ctx
     // tuning knobs (flx_set_tuning)
     int traceVariant = 1;     // 0: one ray per thread, 1: persistent threads + dynamic fetch, while-while phases (production), 2: 1 + top-of-tree
                               // treelet in shared memory, 3: persistent threads, one majority step per iteration (flx_trace_greedy.cuh; measured equal)
+    int bvhTriCostPercent = 100; // flx_build_bvh: SAH cost of a triangle test relative to a box test, in percent (reference constants: 100)
     int gatherPriority = 0;   // 1: the gather stream gets the render stream's (high) priority instead of the lowest
     int innerBias = 0;        // variant 3: an inner-node step runs when lanes-at-inner + bias >= lanes-at-triangle
     int topNodes = 2047;      // variant 2: treelet nodes staged per CTA (64 B each)
@@ -261,6 +270,7 @@ Frame makeFrame(const flx_ctx *c)
     f.nParts = c->nParts;
     f.stripeRows = c->stripeRows;
     f.tanHalfFov = c->tanHalfFov;
+    f.pinholeCamera = c->pinholeCamera;
     return f;
 }
 
@@ -574,11 +584,24 @@ std::vector<uint32_t> pickTreelet(const flx_Node *nodes, uint32_t nNodes)
     return order;
 }
 
+// dst = a device block of at least `bytes`: the one it already holds when that is large enough, else a fresh one
+template <class T> int reserveDev(flx_ctx *ctx, T *&dst, size_t bytes)
+{
+    size_t &cap = ctx->capacity[static_cast<const void *>(&dst)];
+    if (dst && cap >= bytes)
+        return 0;
+    freeDev(dst);
+    cap = 0;
+    CU(cudaMalloc(&dst, bytes));
+    cap = bytes;
+    return 0;
+}
+
 template <class T> int uploadArray(flx_ctx *ctx, T *&dst, const T *src, size_t count, size_t minCount = 1)
 {
-    freeDev(dst);
     const size_t bytes = std::max(count, minCount) * sizeof(T);
-    CU(cudaMalloc(&dst, bytes));
+    if (int rcReserve = reserveDev(ctx, dst, bytes))
+        return rcReserve;
     // On the context's stream (the work streams are cudaStreamNonBlocking: the legacy default stream does not order against
     // them).  A pinned source (flx_host_alloc) goes by DMA at link speed; a pageable one is staged by the driver before the call
     // returns.  Callers synchronise the stream before they return, so the source is borrowed for the call only.
@@ -593,8 +616,14 @@ template <class T> int uploadArray(flx_ctx *ctx, T *&dst, const T *src, size_t c
 // flx_bvh_repack.cuh driven from the host: nodes / indices go up as they are, the traversal layout is made on the device
 int repackOnDevice(flx_ctx *ctx, const uint32_t *indices, uint32_t nIndices, const flx_Node *nodes, uint32_t nNodes, uint32_t nTris, uint32_t nMaterials)
 {
+    const bool timing = std::getenv("FLX_DEBUG_TIMING") != nullptr;
+    const auto tHost0 = std::chrono::steady_clock::now();
     // sizes and the treelet come from one cheap pass over the host nodes
+    // ONE pass over the host nodes: link ranges, counts, and the depth of the deepest leaf (hierarchyDepth's recurrence inlined: links
+    // only go forward, so a node's depth is known before its children are reached)
     size_t nInner = 0, nLeafTris = 0;
+    std::vector<uint8_t> depth(nNodes, 0);
+    uint32_t deep = 0;
     for (uint32_t i = 0; i < nNodes; i++)
     {
         if (nodes[i].nPrims == 0)
@@ -603,15 +632,21 @@ int repackOnDevice(flx_ctx *ctx, const uint32_t *indices, uint32_t nIndices, con
             if (i + 1 >= nNodes || r >= nNodes || r <= i + 1)
                 return fail(ctx, FLX_E_INVALID, "node %u: child links out of range (left %u, right %u, %u nodes)", i, i + 1, r, nNodes);
             nInner++;
+            const uint32_t d = std::min<uint32_t>(depth[i] + 1u, 255u);
+            depth[i + 1] = depth[r] = (uint8_t)d;
+            deep = std::max(deep, d);
         }
         else
             nLeafTris += nodes[i].nPrims;
     }
     if (nLeafTris > 0x7ffffff0u)
         return fail(ctx, FLX_E_INVALID, "too many leaf references");
-    if (const uint32_t deep = hierarchyDepth(nodes, nNodes); deep > FLX_STACK_DEPTH)
+    if (deep > FLX_STACK_DEPTH)
         return fail(ctx, FLX_E_INVALID, "hierarchy is %u levels deep; the traversal stack holds %d entries (reference: uint stack[64], bvh.cl:240)", deep, FLX_STACK_DEPTH);
     const std::vector<uint32_t> treelet = pickTreelet(nodes, nNodes);
+    if (timing)
+        std::fprintf(stderr, "  flx_upload_scene: %-28s %8.3f ms\n", "host pass over the nodes",
+                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tHost0).count());
 
     // one allocation for all temporaries (cudaMalloc / cudaFree are the expensive part of a small job like this)
     auto align = [](size_t b) { return (b + 255) & ~(size_t)255; };
@@ -620,15 +655,16 @@ int repackOnDevice(flx_ctx *ctx, const uint32_t *indices, uint32_t nIndices, con
     size_t tempBytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tempBytes, (uint32_t *)nullptr, (uint32_t *)nullptr, (int)nNodes, ctx->stream);
     const size_t szScan = align(std::max<size_t>(tempBytes, 16));
-    unsigned char *pool = nullptr;
-    auto cleanup = [&]() { freeDev(pool); };
     int rc = 0;
     auto cu = [&](cudaError_t e, const char *what) {
         if (e != cudaSuccess && rc == 0)
             rc = fail(ctx, (int)e, "flx_upload_scene: %s failed: %s", what, cudaGetErrorString(e));
     };
     cudaStream_t st = ctx->stream;
-    cu(cudaMalloc(&pool, szNodes + szIdx + szTreelet + 5 * szPerNode + szScan + 256), "cudaMalloc");
+    if (int rcPool = reserveDev(ctx, ctx->repackPool, szNodes + szIdx + szTreelet + 5 * szPerNode + szScan + 256))
+        return rcPool;
+    unsigned char *pool = ctx->repackPool;
+    auto cleanup = [&]() {};
     unsigned char *cursor = pool;
     auto take = [&](size_t bytes) { unsigned char *p = cursor; cursor += bytes; return p; };
     flx_Node *dNodes = reinterpret_cast<flx_Node *>(take(szNodes));
@@ -638,11 +674,11 @@ int repackOnDevice(flx_ctx *ctx, const uint32_t *indices, uint32_t nIndices, con
     uint32_t *dScanI = reinterpret_cast<uint32_t *>(take(szPerNode)), *dScanL = reinterpret_cast<uint32_t *>(take(szPerNode));
     void *dTemp = take(szScan);
     uint32_t *dError = reinterpret_cast<uint32_t *>(take(256)); // [0] hierarchy error, [1] first triangle with a bad material + 1
-    freeDev(ctx->tnodes);
-    freeDev(ctx->ttris);
     const size_t nodeBytes = std::max<size_t>(nInner, 1) * 64, triBytes = std::max<size_t>(nLeafTris, 1) * 64;
-    cu(cudaMalloc(&ctx->tnodes, nodeBytes), "cudaMalloc");
-    cu(cudaMalloc(&ctx->ttris, triBytes), "cudaMalloc");
+    if (int rcT = reserveDev(ctx, ctx->tnodes, nodeBytes))
+        return rcT;
+    if (int rcT = reserveDev(ctx, ctx->ttris, triBytes))
+        return rcT;
     if (rc == 0)
     {
         cu(cudaMemcpyAsync(dNodes, nodes, (size_t)nNodes * sizeof(flx_Node), cudaMemcpyHostToDevice, st), "node upload");
@@ -1118,6 +1154,7 @@ void flx_destroy(flx_ctx *c)
     freeDev(c->texData);
     freeDev(c->tnodes);
     freeDev(c->ttris);
+    freeDev(c->repackPool);
     freeDev(c->envRGBA);
     freeDev(c->probTable);
     freeDev(c->pdfTable);
@@ -1260,8 +1297,20 @@ static int uploadSceneImpl(flx_ctx *ctx, const flx_Triangle *tris, uint32_t n_tr
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->sceneReady = false;
     ctx->sceneBytes = 0;
+    auto lap = [&](const char *what) { // FLX_DEBUG_TIMING: where the upload's time goes (synchronises, so only when asked for)
+        static std::chrono::steady_clock::time_point last;
+        if (!timing)
+            return;
+        cudaStreamSynchronize(ctx->stream);
+        const auto t = now();
+        if (what)
+            std::fprintf(stderr, "  flx_upload_scene: %-28s %8.3f ms\n", what, ms(last, t));
+        last = t;
+    };
+    lap(nullptr);
     if ((rc = uploadArray(ctx, ctx->tris, tris, n_tris)))
         return rc;
+    lap("triangles (malloc + copy)");
     if ((rc = uploadArray(ctx, ctx->materials, materials, n_materials)))
         return rc;
     ctx->materialTypes = 0;
@@ -1284,10 +1333,12 @@ static int uploadSceneImpl(flx_ctx *ctx, const flx_Triangle *tris, uint32_t n_tr
     if ((rc = uploadArray(ctx, ctx->texData, tex_data, tex_bytes, 4)))
         return rc;
     ctx->nTris = n_tris;
+    lap("materials + textures");
     if (!ctx->repackOnHost)
     {
         if ((rc = repackOnDevice(ctx, indices, n_indices, nodes, n_nodes, n_tris, n_materials)))
             return rc;
+        lap("hierarchy copy + repack");
         ctx->sceneReady = true;
         if (ctx->l2Persist && (rc = applyL2Persist(ctx)))
             return rc;
@@ -1331,6 +1382,7 @@ try
     memset(&b, 0, sizeof b);
     b.n = n;
     b.maxLeaf = max_leaf;
+    b.triCost = (float)ctx->bvhTriCostPercent / 100.0f;
     flx_Triangle *dTris = nullptr;
     void *sortTemp = nullptr;
     size_t sortBytes = 0;
@@ -1378,6 +1430,7 @@ try
     {
         pb.n = n;
         pb.maxLeaf = max_leaf;
+        pb.triCost = b.triCost;
         pb.keysSorted = b.keysSorted;
         pb.primMin = b.primMin;
         pb.primMax = b.primMax;
@@ -1554,22 +1607,18 @@ static int allocImage(flx_ctx *ctx)
     if (ctx->gatherStream)
         CU(cudaStreamSynchronize(ctx->gatherStream));
     ctx->gatherInFlight = false;
-    freeDev(ctx->imageBlock);
     freeDev(ctx->aovOut);
     ctx->pixels = ctx->denoiserAlbedo = ctx->denoiserNormal = ctx->preview = nullptr;
     ctx->dirtyPixels = nullptr;
-    // the gather buffers are sized for an image and a tiling: a new image or tiling starts from none
-    freeDev(ctx->gatherBuf);
-    freeDev(ctx->fullImage);
-    freeDev(ctx->gatherSnapshot);
-    ctx->gatherBufPixels = ctx->fullImagePixels = ctx->gatherSnapshotPixels = 0;
+    // the gather buffers (flx_gather_pixels) are capacity-checked there, each on its own: they stay
     ctx->snapshotBusy[0] = ctx->snapshotBusy[1] = false;
     ctx->previewStale = true;
     if (ctx->tilePixels == 0)
         return fail(ctx, FLX_E_INVALID, "tile %u of %u owns no rows of a %ux%u image", ctx->part, ctx->nParts, ctx->width, ctx->height);
-    // one allocation, two asynchronous fills (the reference makes three buffers + two GL PBOs, clcontext.cpp:326-384)
+    // one allocation (kept while large enough), two asynchronous fills (the reference makes three buffers + two GL PBOs, clcontext.cpp:326-384)
     const size_t bytes = (size_t)ctx->tilePixels * 4 * sizeof(float);
-    CU(cudaMalloc(&ctx->imageBlock, 4 * bytes + ctx->tilePixels));
+    if (int rcImage = reserveDev(ctx, ctx->imageBlock, 4 * bytes + ctx->tilePixels))
+        return rcImage;
     ctx->pixels = reinterpret_cast<float *>(ctx->imageBlock);
     ctx->denoiserAlbedo = reinterpret_cast<float *>(ctx->imageBlock + bytes);
     ctx->denoiserNormal = reinterpret_cast<float *>(ctx->imageBlock + 2 * bytes);
@@ -1623,6 +1672,15 @@ try
         ctx->previewStale = true; // the display pass maps every pixel differently now
     ctx->params = *p;
     ctx->tanHalfFov = flx_tanf(0.5f * p->camera.fov * 3.14159265358979323846f / 180); // toRad, geom.h:22; wf_raygen.cl:50
+    {
+        // lens_offset (flx_kernels.cuh): scale * (right * rx + up * ry) is +-0 for every disk sample iff the scale is 0 and the basis
+        // is finite; adding +-0 leaves the origin's bits alone iff no component of it is -0.0f
+        auto finite3 = [](const flx_float3 &v) { return std::isfinite(v.x) && std::isfinite(v.y) && std::isfinite(v.z); };
+        auto negZero = [](float x) { return x == 0.0f && std::signbit(x); };
+        const flx_Camera &c = p->camera;
+        ctx->pinholeCamera = (p->worldRadius * c.apertureSize == 0.0f) && std::isfinite(p->worldRadius) && finite3(c.right) && finite3(c.up) && !negZero(c.pos.x) &&
+                             !negZero(c.pos.y) && !negZero(c.pos.z);
+    }
     ctx->paramsSet = true;
     return 0;
 }
@@ -2319,6 +2377,10 @@ try
     case FLX_TUNE_TRACE_VARIANT:
         REQUIRE(value >= 0 && value <= 3, "flx_set_tuning: trace variant must be 0, 1, 2 or 3");
         ctx->traceVariant = value;
+        return 0;
+    case FLX_TUNE_BVH_TRI_COST:
+        REQUIRE(value >= 25 && value <= 1600, "flx_set_tuning: triangle cost must be in 25..1600 percent");
+        ctx->bvhTriCostPercent = value;
         return 0;
     case FLX_TUNE_GATHER_PRIORITY:
         REQUIRE(ctx->gatherStream == nullptr, "flx_set_tuning: the gather stream already exists (set its priority before the first flx_gather_pixels)");

@@ -33,6 +33,7 @@ struct BvhBuild
     const flx_Triangle *tris;
     uint32_t n;
     uint32_t maxLeaf;
+    float triCost;         // SAH cost of a triangle test relative to a box test in the collapse decision (the reference: 1, src/bvh.hpp:72-73)
     unsigned long long *keys, *keysSorted;
     float4 *bmin, *bmax;   // node boxes; node ids: internal i -> i (0 .. n-2), leaf j (sorted position) -> n-1+j
     float4 *primMin, *primMax; // per triangle, by triangle index
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__(FLX_BVH_BLOCK) k_bvh_fit(const BvhBuild b)
         const float4 lo = b.primMin[tri], hi = b.primMax[tri];
         b.bmin[node] = lo;
         b.bmax[node] = hi;
-        b.cost[node] = half_area(lo, hi) * 1.0f;
+        b.cost[node] = half_area(lo, hi) * b.triCost;
         b.size[node] = 1u;
     }
     if (b.n == 1)
@@ -217,7 +218,7 @@ __global__ void __launch_bounds__(FLX_BVH_BLOCK) k_bvh_fit(const BvhBuild b)
         const uint32_t count = r.y - r.x + 1u;
         const volatile float *vcost = b.cost;
         const volatile uint32_t *vsize = b.size;
-        const float leafCost = area * (float)count;                        // parentArea * refs * costTri, sbvh.cpp:129
+        const float leafCost = (area * (float)count) * b.triCost;          // parentArea * refs * costTri, sbvh.cpp:129
         const float innerCost = (area * 2.0f + vcost[ch.x]) + vcost[ch.y]; // nodeSAH + children, sbvh.cpp:115,204
         const bool collapse = count <= b.maxLeaf && leafCost <= innerCost;
         b.bmin[p] = lo;
@@ -301,6 +302,7 @@ __global__ void __launch_bounds__(FLX_BVH_BLOCK) k_bvh_emit(const BvhBuild b)
 struct PlocBuild
 {
     uint32_t n, maxLeaf;
+    float triCost;
     const unsigned long long *keysSorted;
     const float4 *primMin, *primMax;
     float4 *bmin, *bmax;     // per node id (2n - 1)
@@ -328,7 +330,7 @@ __global__ void __launch_bounds__(FLX_BVH_BLOCK) k_ploc_init(const PlocBuild b)
     b.left[j] = -1;
     b.right[j] = -1;
     b.parent[j] = -1;
-    b.cost[j] = half_area(lo, hi) * 1.0f;
+    b.cost[j] = half_area(lo, hi) * b.triCost;
     b.size[j] = 1u;
     b.prims[j] = 1u;
     b.collapsed[j] = 0u;
@@ -424,7 +426,7 @@ __global__ void __launch_bounds__(FLX_BVH_BLOCK) k_ploc_apply(const PlocBuild b,
     const float4 hi = make_float4(fmaxf(lhi.x, rhi.x), fmaxf(lhi.y, rhi.y), fmaxf(lhi.z, rhi.z), 0.0f);
     const float area = half_area(lo, hi);
     const uint32_t count = b.prims[l] + b.prims[r];
-    const float leafCost = area * (float)count;
+    const float leafCost = (area * (float)count) * b.triCost;
     const float innerCost = (area * 2.0f + b.cost[l]) + b.cost[r];
     const bool collapse = count <= b.maxLeaf && leafCost <= innerCost;
     b.bmin[id] = lo;

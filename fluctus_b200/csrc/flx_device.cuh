@@ -52,17 +52,26 @@ struct Tasks
 {
     uint32_t *base;
     uint32_t n;
-    FLX_DEV uint32_t &u(int slot, uint32_t g) const { return base[(size_t)slot * n + g]; }
-    FLX_DEV float f(int slot, uint32_t g) const { return __uint_as_float(base[(size_t)slot * n + g]); }
-    FLX_DEV void setf(int slot, uint32_t g, float v) const { base[(size_t)slot * n + g] = __float_as_uint(v); }
-    FLX_DEV void setu(int slot, uint32_t g, uint32_t v) const { base[(size_t)slot * n + g] = v; }
+    // Address of slot s of path g = (base + g) + s * n.  Written so that the per-path part (base + 4 g, two instructions, shared by
+    // every access of a thread) is one common subexpression and the per-slot part is ONE IMAD.WIDE (n * (4 s) + that pointer): the
+    // straightforward base[(size_t)s * n + g] costs three address instructions per access (IMAD.WIDE + LEA + LEA.HI.X), which made
+    // path-state addressing a quarter of all instructions the fused logic kernel issues (profiles/r2_base_logic_lines.txt).
+    FLX_DEV uint32_t *at(int slot, uint32_t g) const
+    {
+        char *p = reinterpret_cast<char *>(base) + (size_t)g * 4u;
+        return reinterpret_cast<uint32_t *>(p + (size_t)n * (uint32_t)(slot * 4));
+    }
+    FLX_DEV uint32_t &u(int slot, uint32_t g) const { return *at(slot, g); }
+    FLX_DEV float f(int slot, uint32_t g) const { return __uint_as_float(*at(slot, g)); }
+    FLX_DEV void setf(int slot, uint32_t g, float v) const { *at(slot, g) = __float_as_uint(v); }
+    FLX_DEV void setu(int slot, uint32_t g, uint32_t v) const { *at(slot, g) = v; }
     FLX_DEV V3 v(int slot, uint32_t g) const { return V3{f(slot, g), f(slot + 1, g), f(slot + 2, g)}; }
     // streaming flavours (ld/st.global.cs: evict-first): for state touched once by a kernel whose L1 is busy caching the BVH
-    FLX_DEV float f_cs(int slot, uint32_t g) const { return __uint_as_float(__ldcs(base + (size_t)slot * n + g)); }
-    FLX_DEV uint32_t u_cs(int slot, uint32_t g) const { return __ldcs(base + (size_t)slot * n + g); }
+    FLX_DEV float f_cs(int slot, uint32_t g) const { return __uint_as_float(__ldcs(at(slot, g))); }
+    FLX_DEV uint32_t u_cs(int slot, uint32_t g) const { return __ldcs(at(slot, g)); }
     FLX_DEV V3 v_cs(int slot, uint32_t g) const { return V3{f_cs(slot, g), f_cs(slot + 1, g), f_cs(slot + 2, g)}; }
-    FLX_DEV void setf_cs(int slot, uint32_t g, float v) const { __stcs(base + (size_t)slot * n + g, __float_as_uint(v)); }
-    FLX_DEV void setu_cs(int slot, uint32_t g, uint32_t v) const { __stcs(base + (size_t)slot * n + g, v); }
+    FLX_DEV void setf_cs(int slot, uint32_t g, float v) const { __stcs(at(slot, g), __float_as_uint(v)); }
+    FLX_DEV void setu_cs(int slot, uint32_t g, uint32_t v) const { __stcs(at(slot, g), v); }
     FLX_DEV void setv_cs(int slot, uint32_t g, V3 a) const
     {
         setf_cs(slot, g, a.x);

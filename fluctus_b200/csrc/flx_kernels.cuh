@@ -34,7 +34,22 @@ struct Frame
     uint32_t tilePixels; // pixels owned by this context (= width*height when untiled)
     uint32_t part, nParts, stripeRows;
     float tanHalfFov;    // tan(toRad(0.5f * fov)), evaluated once on the host with flx_tanf (wf_raygen.cl:50)
+    int pinholeCamera;   // 1: the thin-lens offset is exactly zero for every sample (aperture 0), decided on the host -- see lens_offset
 };
+
+// Thin lens (wf_raygen.cl:59-63, mk_raygen.cl:49-53; disk sample utils.cl:75-80): origin += (worldRadius * aperture) * (right * rx + up * ry)
+// with (rx, ry) on the unit disk from the two random numbers the caller has already drawn.  With aperture 0 -- the reference's
+// default and every benchmark configuration -- the offset is +-0 for every sample and origin + (+-0) == origin bit for bit,
+// PROVIDED no component of the origin is -0.0f (-0 + +0 = +0): the host checks exactly that (flx_update_params) and sets
+// pinholeCamera, which skips the pinned double-precision cos / sin here.  They are a sixth of the instructions the fused logic
+// kernel issues, executed by the ~5 lanes of a warp that regenerate a path (profiles/r2_base_logic_lines.txt).
+FLX_DEV V3 lens_offset(const Frame &fr, const flx_RenderParams &prm, V3 camRight, V3 camUp, float sqrt_r, float th)
+{
+    if (fr.pinholeCamera)
+        return v3(0.0f);
+    const float rx = sqrt_r * flx_cosf(th), ry = sqrt_r * flx_sinf(th);
+    return (prm.worldRadius * prm.camera.apertureSize) * (camRight * rx + camUp * ry);
+}
 
 enum { Q_RAYGEN = 0, Q_EXT, Q_SHADOW, Q_DIFFUSE, Q_GLOSSY, Q_GGXREFL, Q_GGXREFR, Q_DELTA };
 
@@ -133,8 +148,7 @@ FLX_DEV void raygen_path(const Frame &fr, const flx_RenderParams &prm, uint32_t 
     const V3 fp = camPos + rayDir * prm.camera.focalDist;
     const float sqrt_r = sqrtf(flx_rand(seed));
     const float th = FLX_2PI_F * flx_rand(seed);
-    const float rx = sqrt_r * flx_cosf(th), ry = sqrt_r * flx_sinf(th);
-    rayOrig = rayOrig + (prm.worldRadius * prm.camera.apertureSize) * (camRight * rx + camUp * ry);
+    rayOrig = rayOrig + lens_offset(fr, prm, camRight, camUp, sqrt_r, th);
     rayDir = norm3(fp - rayOrig);
 
     t.setv(FLX_S_ORIG, gid, rayOrig);
@@ -647,36 +661,26 @@ __global__ void __launch_bounds__(FLX_BLOCK, MIN_BLOCKS) k_logic(const __grid_co
         __syncthreads();
         if (threadIdx.x < NQ + (FUSE >= 1 ? 1 : 0))
         {
+            // one thread per queue: per-warp counts -> per-warp offsets (in place), then ONE atomic for the tile's total
             uint32_t total = 0;
 #pragma unroll
             for (int w = 0; w < NW; w++)
-                total += s_cnt[threadIdx.x][w];
+            {
+                const uint32_t c = s_cnt[threadIdx.x][w];
+                s_cnt[threadIdx.x][w] = total;
+                total += c;
+            }
             const int queueId = threadIdx.x == 0 ? Q_SHADOW : (threadIdx.x == NQ ? Q_EXT : Q_DIFFUSE + (int)threadIdx.x - 1);
             s_qbase[threadIdx.x] = total ? atomicAdd(counter_ptr(fr.counters, queueId), total) : 0u;
         }
         __syncthreads();
         const unsigned below = (1u << lane) - 1u;
         if (pushShadow)
-        {
-            uint32_t slot = s_qbase[0] + __popc(shadowMask & below);
-            for (int w = 0; w < warp; w++)
-                slot += s_cnt[0][w];
-            fr.queues[Q_SHADOW][slot] = gid;
-        }
+            fr.queues[Q_SHADOW][s_qbase[0] + s_cnt[0][warp] + __popc(shadowMask & below)] = gid;
         if (q > 0)
-        {
-            uint32_t slot = s_qbase[q] + __popc(myMask & below);
-            for (int w = 0; w < warp; w++)
-                slot += s_cnt[q][w];
-            fr.queues[Q_DIFFUSE + q - 1][slot] = gid;
-        }
+            fr.queues[Q_DIFFUSE + q - 1][s_qbase[q] + s_cnt[q][warp] + __popc(myMask & below)] = gid;
         if (pushExt)
-        {
-            uint32_t slot = s_qbase[NQ] + __popc(extMask & below);
-            for (int w = 0; w < warp; w++)
-                slot += s_cnt[NQ][w];
-            fr.queues[Q_EXT][slot] = gid;
-        }
+            fr.queues[Q_EXT][s_qbase[NQ] + s_cnt[NQ][warp] + __popc(extMask & below)] = gid;
     }
 
     // ---- raygen queue in ascending path order: decoupled look-back over the tile words ----------------------

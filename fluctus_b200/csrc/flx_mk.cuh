@@ -127,8 +127,7 @@ __global__ void __launch_bounds__(FLX_BLOCK) k_mk_raygen(const __grid_constant__
     const V3 fp = camPos + rayDir * prm.camera.focalDist; // depth of field, mk_raygen.cl:49-53
     const float sqrt_r = sqrtf(flx_rand(seed));
     const float th = FLX_2PI_F * flx_rand(seed);
-    const float rx = sqrt_r * flx_cosf(th), ry = sqrt_r * flx_sinf(th);
-    rayOrig = rayOrig + (prm.worldRadius * prm.camera.apertureSize) * (camRight * rx + camUp * ry);
+    rayOrig = rayOrig + lens_offset(fr, prm, camRight, camUp, sqrt_r, th);
     rayDir = norm3(fp - rayOrig);
     t.setv(FLX_S_ORIG, gid, rayOrig);
     t.setv(FLX_S_DIR, gid, rayDir);

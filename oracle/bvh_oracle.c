@@ -44,6 +44,7 @@ static float half_area(f4 lo, f4 hi) { const float dx = hi.x - lo.x, dy = hi.y -
 /* a subtree before emission */
 typedef struct Sub { f4 lo, hi; float cost; uint32_t size, first, last; int leaf; struct Sub *l, *r; } Sub;
 
+extern float g_ploc_tri_cost;
 static Sub *build(const Ctx *c, uint32_t first, uint32_t last)
 {
     Sub *s = (Sub *)calloc(1, sizeof(Sub));
@@ -51,7 +52,7 @@ static Sub *build(const Ctx *c, uint32_t first, uint32_t last)
     if (first == last)
     {
         const uint32_t tri = (uint32_t)(c->keys[first] & 0xffffffffu);
-        s->lo = c->pmin[tri]; s->hi = c->pmax[tri]; s->cost = half_area(s->lo, s->hi) * 1.0f; s->size = 1; s->leaf = 1;
+        s->lo = c->pmin[tri]; s->hi = c->pmax[tri]; s->cost = half_area(s->lo, s->hi) * g_ploc_tri_cost; s->size = 1; s->leaf = 1;
         return s;
     }
     /* split after the last key that shares more leading bits with keys[first] than keys[last] does */
@@ -68,7 +69,7 @@ static Sub *build(const Ctx *c, uint32_t first, uint32_t last)
     s->hi.x = fmaxf(s->l->hi.x, s->r->hi.x); s->hi.y = fmaxf(s->l->hi.y, s->r->hi.y); s->hi.z = fmaxf(s->l->hi.z, s->r->hi.z); s->hi.w = 0.0f;
     const float area = half_area(s->lo, s->hi);
     const uint32_t count = last - first + 1;
-    const float leafCost = area * (float)count;
+    const float leafCost = (area * (float)count) * g_ploc_tri_cost;
     const float innerCost = (area * 2.0f + s->l->cost) + s->r->cost;
     const int collapse = count <= c->maxLeaf && leafCost <= innerCost;
     s->cost = collapse ? leafCost : innerCost;
@@ -137,6 +138,8 @@ int port_build_lbvh(const Triangle *tris, uint32_t n, uint32_t maxLeaf, Node *no
  * that takes the lower partner's place; compaction keeps the order.  Node ids: leaf j (sorted position) -> j, inner nodes
  * n, n+1, ... in order of creation (by round, then by position).  Emission is the general depth-first one. */
 #define PLOC_RADIUS 16
+float g_ploc_tri_cost = 1.0f; /* SAH cost of one triangle test relative to one box test in the collapse decision (FLX_TUNE_BVH_TRI_COST / 100) */
+void port_set_tri_cost(float c) { g_ploc_tri_cost = c; }
 typedef struct { f4 lo, hi; int left, right; float cost; uint32_t size, prims; int collapsed; } PNode;
 
 static void ploc_emit(const PNode *nd, uint32_t id, int32_t parent, Node *out, uint32_t *nOut, uint32_t *indices, uint32_t *nIdx, const uint64_t *keys, uint32_t n, int leafMode)
@@ -177,7 +180,7 @@ int port_build_ploc(const Triangle *tris, uint32_t n, uint32_t maxLeaf, Node *no
     {
         const uint32_t tri = (uint32_t)(keys[j] & 0xffffffffu);
         nd[j].lo = pmin[tri]; nd[j].hi = pmax[tri]; nd[j].left = nd[j].right = -1;
-        nd[j].cost = half_area(nd[j].lo, nd[j].hi) * 1.0f; nd[j].size = 1; nd[j].prims = 1; nd[j].collapsed = 0;
+        nd[j].cost = half_area(nd[j].lo, nd[j].hi) * g_ploc_tri_cost; nd[j].size = 1; nd[j].prims = 1; nd[j].collapsed = 0;
         cid[j] = j;
     }
     uint32_t m = n, nextId = n;
@@ -213,7 +216,7 @@ int port_build_ploc(const Triangle *tris, uint32_t n, uint32_t maxLeaf, Node *no
             o->hi.x = fmaxf(nd[l].hi.x, nd[r].hi.x); o->hi.y = fmaxf(nd[l].hi.y, nd[r].hi.y); o->hi.z = fmaxf(nd[l].hi.z, nd[r].hi.z); o->hi.w = 0.0f;
             const float area = half_area(o->lo, o->hi);
             const uint32_t count = nd[l].prims + nd[r].prims;
-            const float leafCost = area * (float)count;
+            const float leafCost = (area * (float)count) * g_ploc_tri_cost;
             const float innerCost = (area * 2.0f + nd[l].cost) + nd[r].cost;
             const int collapse = count <= maxLeaf && leafCost <= innerCost;
             o->left = (int)l; o->right = (int)r; o->cost = collapse ? leafCost : innerCost;
@@ -229,4 +232,133 @@ int port_build_ploc(const Triangle *tris, uint32_t n, uint32_t maxLeaf, Node *no
     *n_nodes_out = nOut;
     free(pmin); free(pmax); free(keys); free(nd); free(cid); free(next); free(nn);
     return nIdx == n ? 0 : 3;
+}
+
+
+/* ================================================================ reference pre-splitting (FLX_BVH_PLOC_SPLIT)
+ * "Early split clipping" (Ernst & Greiner 2007) in front of the PLOC builder: a triangle whose box is large is handed to the builder
+ * as several REFERENCES, each with the box of the part of the triangle inside one cell of a recursive spatial-median subdivision of
+ * its box -- what the reference's SBVH gets from spatial splits (src/sbvh.cpp:118-142, 240-330): a long or large triangle no longer
+ * forces a large box on every node above it.  The index list then names a triangle once per reference (n_indices > n_tris), as the
+ * reference's SBVH does.
+ *   box of a part = union of the triangle's vertices on that side of the plane and the points where its edges cross the plane,
+ *   intersected with the cell (the SBVH's splitReference does the same, src/sbvh.cpp:268-330); split axis = longest extent of the
+ *   cell, plane = its middle; a cell is split while its half-area exceeds `threshold` and depth < ESC_MAX_DEPTH.
+ * References of one triangle are emitted depth first, lower side first. */
+#define ESC_MAX_DEPTH 6
+typedef struct { f4 lo, hi; int depth; } Cell;
+
+static float axis_of(f4 v, int a) { return a == 0 ? v.x : (a == 1 ? v.y : v.z); }
+static void set_axis(f4 *v, int a, float x) { if (a == 0) v->x = x; else if (a == 1) v->y = x; else v->z = x; }
+static void grow(f4 *lo, f4 *hi, f4 p)
+{
+    lo->x = fminf(lo->x, p.x); lo->y = fminf(lo->y, p.y); lo->z = fminf(lo->z, p.z);
+    hi->x = fmaxf(hi->x, p.x); hi->y = fmaxf(hi->y, p.y); hi->z = fmaxf(hi->z, p.z);
+}
+
+/* splits the part of triangle (a, b, c) inside `cell` at plane axis = pos; returns a bit mask: 1 = lower part exists, 2 = upper */
+static int split_cell(f4 a, f4 b, f4 c, const Cell *cell, int axis, float pos, Cell *lower, Cell *upper)
+{
+    const float BIG = 3.402823466e+38f;
+    f4 llo = {BIG, BIG, BIG, 0.0f}, lhi = {-BIG, -BIG, -BIG, 0.0f}, ulo = llo, uhi = lhi;
+    const f4 v[3] = {a, b, c};
+    for (int e = 0; e < 3; e++)
+    {
+        const f4 v0 = v[e], v1 = v[(e + 1) % 3];
+        const float p0 = axis_of(v0, axis), p1 = axis_of(v1, axis);
+        if (p0 <= pos) grow(&llo, &lhi, v0);
+        if (p0 >= pos) grow(&ulo, &uhi, v0);
+        if ((p0 < pos && p1 > pos) || (p0 > pos && p1 < pos))
+        {
+            const float t = (pos - p0) / (p1 - p0);
+            f4 x;
+            x.x = v0.x + t * (v1.x - v0.x); x.y = v0.y + t * (v1.y - v0.y); x.z = v0.z + t * (v1.z - v0.z); x.w = 0.0f;
+            set_axis(&x, axis, pos);
+            grow(&llo, &lhi, x);
+            grow(&ulo, &uhi, x);
+        }
+    }
+    set_axis(&lhi, axis, fminf(axis_of(lhi, axis), pos));
+    set_axis(&ulo, axis, fmaxf(axis_of(ulo, axis), pos));
+    /* intersect with the cell */
+    llo.x = fmaxf(llo.x, cell->lo.x); llo.y = fmaxf(llo.y, cell->lo.y); llo.z = fmaxf(llo.z, cell->lo.z);
+    lhi.x = fminf(lhi.x, cell->hi.x); lhi.y = fminf(lhi.y, cell->hi.y); lhi.z = fminf(lhi.z, cell->hi.z);
+    ulo.x = fmaxf(ulo.x, cell->lo.x); ulo.y = fmaxf(ulo.y, cell->lo.y); ulo.z = fmaxf(ulo.z, cell->lo.z);
+    uhi.x = fminf(uhi.x, cell->hi.x); uhi.y = fminf(uhi.y, cell->hi.y); uhi.z = fminf(uhi.z, cell->hi.z);
+    int mask = 0;
+    if (llo.x <= lhi.x && llo.y <= lhi.y && llo.z <= lhi.z) { lower->lo = llo; lower->hi = lhi; lower->depth = cell->depth + 1; mask |= 1; }
+    if (ulo.x <= uhi.x && ulo.y <= uhi.y && ulo.z <= uhi.z) { upper->lo = ulo; upper->hi = uhi; upper->depth = cell->depth + 1; mask |= 2; }
+    return mask;
+}
+
+/* the references of one triangle; out may be NULL (count only) */
+static uint32_t esc_triangle(const Triangle *t, float threshold, f4 *rmin, f4 *rmax)
+{
+    Cell stack[2 * ESC_MAX_DEPTH + 2];
+    int sp = 0;
+    uint32_t count = 0;
+    const f4 a = t->v0.p, b = t->v1.p, c = t->v2.p;
+    Cell root;
+    root.lo.x = fminf(fminf(a.x, b.x), c.x); root.lo.y = fminf(fminf(a.y, b.y), c.y); root.lo.z = fminf(fminf(a.z, b.z), c.z); root.lo.w = 0.0f;
+    root.hi.x = fmaxf(fmaxf(a.x, b.x), c.x); root.hi.y = fmaxf(fmaxf(a.y, b.y), c.y); root.hi.z = fmaxf(fmaxf(a.z, b.z), c.z); root.hi.w = 0.0f;
+    root.depth = 0;
+    stack[sp++] = root;
+    while (sp > 0)
+    {
+        const Cell cell = stack[--sp];
+        int done = !(half_area(cell.lo, cell.hi) > threshold) || cell.depth >= ESC_MAX_DEPTH;
+        if (!done)
+        {
+            const float ex = cell.hi.x - cell.lo.x, ey = cell.hi.y - cell.lo.y, ez = cell.hi.z - cell.lo.z;
+            const int axis = (ex >= ey && ex >= ez) ? 0 : (ey >= ez ? 1 : 2);
+            const float pos = (axis_of(cell.lo, axis) + axis_of(cell.hi, axis)) * 0.5f;
+            Cell lower, upper;
+            const int mask = split_cell(a, b, c, &cell, axis, pos, &lower, &upper);
+            if (mask == 3)
+            {
+                stack[sp++] = upper; /* lower side first */
+                stack[sp++] = lower;
+                continue;
+            }
+            done = 1; /* the plane misses the part (rounding): keep the cell as it is */
+        }
+        if (rmin) { rmin[count] = cell.lo; rmax[count] = cell.hi; rmin[count].w = rmax[count].w = 0.0f; }
+        count++;
+    }
+    return count;
+}
+
+/* threshold = alpha * half-area of the scene box (union of the triangle boxes).  Returns 0, or 4 when the references do not fit
+ * indices_capacity (then *n_indices_out = the count needed). */
+int port_build_ploc_split(const Triangle *tris, uint32_t n, uint32_t maxLeaf, float alpha, Node *nodes_out, uint32_t nodes_capacity, uint32_t *n_nodes_out,
+                          uint32_t *indices_out, uint32_t indices_capacity, uint32_t *n_indices_out)
+{
+    if (n == 0) return 1;
+    const float BIG = 3.402823466e+38f;
+    f4 slo = {BIG, BIG, BIG, 0.0f}, shi = {-BIG, -BIG, -BIG, 0.0f};
+    for (uint32_t i = 0; i < n; i++) { grow(&slo, &shi, tris[i].v0.p); grow(&slo, &shi, tris[i].v1.p); grow(&slo, &shi, tris[i].v2.p); }
+    const float threshold = alpha * half_area(slo, shi);
+    uint32_t *base = (uint32_t *)malloc(sizeof(uint32_t) * ((size_t)n + 1));
+    base[0] = 0;
+    for (uint32_t i = 0; i < n; i++) base[i + 1] = base[i] + esc_triangle(&tris[i], threshold, NULL, NULL);
+    const uint32_t m = base[n];
+    *n_indices_out = m;
+    if (m > indices_capacity || 2u * m - 1u > nodes_capacity) { free(base); return 4; }
+    f4 *rmin = (f4 *)malloc(sizeof(f4) * m), *rmax = (f4 *)malloc(sizeof(f4) * m);
+    uint32_t *refTri = (uint32_t *)malloc(sizeof(uint32_t) * m);
+    for (uint32_t i = 0; i < n; i++)
+    {
+        const uint32_t k = esc_triangle(&tris[i], threshold, rmin + base[i], rmax + base[i]);
+        for (uint32_t j = 0; j < k; j++) refTri[base[i] + j] = i;
+    }
+    /* from here on the PLOC builder, over references instead of triangles: a pseudo triangle array would do, but the boxes are
+     * what it reads, so build degenerate "triangles" whose box is the reference's */
+    Triangle *pseudo = (Triangle *)calloc(m, sizeof(Triangle));
+    for (uint32_t r = 0; r < m; r++) { pseudo[r].v0.p = rmin[r]; pseudo[r].v1.p = rmax[r]; pseudo[r].v2.p = rmin[r]; }
+    uint32_t nNodes = 0;
+    const int rc = port_build_ploc(pseudo, m, maxLeaf, nodes_out, &nNodes, indices_out);
+    if (rc == 0) for (uint32_t k = 0; k < m; k++) indices_out[k] = refTri[indices_out[k]];
+    *n_nodes_out = nNodes;
+    free(pseudo); free(base); free(rmin); free(rmax); free(refTri);
+    return rc;
 }

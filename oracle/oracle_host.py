@@ -279,16 +279,18 @@ class PortContext(_CpuContext):
     PREFIX = "port_"
 
 
-def build_ploc(tris, max_leaf=8):
+def build_ploc(tris, max_leaf=8, tri_cost=1.0):
     """CPU restatement of the FLX_BVH_PLOC builder (locally-ordered clustering) -> (nodes, indices)."""
-    return build_lbvh(tris, max_leaf, fn="port_build_ploc")
+    return build_lbvh(tris, max_leaf, fn="port_build_ploc", tri_cost=tri_cost)
 
 
-def build_lbvh(tris, max_leaf=8, fn="port_build_lbvh"):
+def build_lbvh(tris, max_leaf=8, fn="port_build_lbvh", tri_cost=1.0):
     """CPU restatement (oracle/bvh_oracle.c) of the GPU hierarchy builder flx_build_bvh -> (nodes, indices) in the
-    reference's Node[] / index-list format."""
+    reference's Node[] / index-list format.  tri_cost = FLX_TUNE_BVH_TRI_COST / 100."""
     from fluctus_b200.structs import NODE_DTYPE
     lib = C.CDLL(PORT_LIB)
+    lib.port_set_tri_cost.argtypes = [C.c_float]
+    lib.port_set_tri_cost(float(tri_cost))
     n = len(tris)
     nodes = np.zeros(max(2 * n - 1, 1), NODE_DTYPE)
     indices = np.zeros(n, np.uint32)
@@ -296,6 +298,7 @@ def build_lbvh(tris, max_leaf=8, fn="port_build_lbvh"):
     f = getattr(lib, fn)
     f.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p]
     rc = f(tris.ctypes.data, n, int(max_leaf), nodes.ctypes.data, C.byref(n_nodes), indices.ctypes.data)
+    lib.port_set_tri_cost(1.0)
     if rc != 0:
         raise RuntimeError("%s failed (%d)" % (fn, rc))
     return nodes[:n_nodes.value].copy(), indices

@@ -23,11 +23,12 @@ def same_tree(gpu_nodes, gpu_idx, cpu_nodes, cpu_idx, what):
     assert len(bad) == 0, "%s: %d nodes differ, first %d: %r vs %r" % (what, len(bad), bad[0], gpu_nodes[bad[0]], cpu_nodes[bad[0]])
 
 
-def build_both(tris, max_leaf=8, quality="fast"):
+def build_both(tris, max_leaf=8, quality="fast", tri_cost=100):
     from oracle.oracle_host import build_lbvh, build_ploc
     with CLContext(1024) as gpu:
+        gpu.setTuning(bvh_tri_cost=tri_cost)
         nodes, idx, ms = gpu.buildBVH(tris, max_leaf, quality)
-    cn, ci = (build_ploc if quality == "ploc" else build_lbvh)(tris, max_leaf)
+    cn, ci = (build_ploc if quality == "ploc" else build_lbvh)(tris, max_leaf, tri_cost=tri_cost / 100.0)
     return nodes, idx, cn, ci, ms
 
 
@@ -41,6 +42,17 @@ def test_builder_matches_the_cpu_restatement(max_leaf, quality):
         nodes, idx, cn, ci, _ = build_both(scene.tris, max_leaf, quality)
         same_tree(nodes, idx, cn, ci, "%s max_leaf=%d %s" % (name, max_leaf, quality))
         validate_bvh(nodes, idx, scene.tris, max_leaf)
+
+
+@pytest.mark.parametrize("quality", QUALITIES)
+@pytest.mark.parametrize("tri_cost", [150, 200])
+def test_builder_with_a_dearer_triangle_test_matches_the_cpu_restatement(quality, tri_cost):
+    """FLX_TUNE_BVH_TRI_COST: the SAH collapse decision with a triangle test dearer than a box test (smaller leaves)"""
+    scene = make_room_scene(materials="mixed", n_blobs=8)
+    nodes, idx, cn, ci, _ = build_both(scene.tris, 8, quality, tri_cost)
+    same_tree(nodes, idx, cn, ci, "room tri_cost=%d %s" % (tri_cost, quality))
+    base = build_both(scene.tris, 8, quality)[0]
+    assert len(nodes) >= len(base), "a dearer triangle test cannot make leaves larger"
 
 
 @pytest.mark.parametrize("quality", QUALITIES)

@@ -396,3 +396,24 @@ def test_gather_on_its_own_stream_single_rank(tmp_path):
             compare_tasks(a.readTasks(), b.readTasks(), "render with gathers vs without (%dx%d)" % (W, H))
             g_ms, g_n = a.checkTracingPerf()["gather"]
             assert g_n >= 6
+
+
+def test_thin_lens_and_the_pinhole_shortcut():
+    """Depth of field (wf_raygen.cl:59-63, mk_raygen.cl:49-53): with an open aperture the disk sample moves the ray origin; with aperture 0
+    the offset is exactly +-0 and the library skips its cos / sin (lens_offset, flx_kernels.cuh) -- except when a component of the
+    camera position is -0.0f, where origin + (+0) differs from origin in the sign bit and the full arithmetic must run.  All three
+    cases in lockstep with the reference kernels, both integrators."""
+    from parity_util import run_mk_lockstep
+    scene = make_room_scene(materials="mixed", textured=True)
+    W, H, N = 48, 32, 48 * 32
+    for what, pos, aperture in (("open aperture", (0.0, 1.0, 0.95), 0.02), ("pinhole, -0.0 in the camera position", (-0.0, 1.0, 0.95), 0.0), ("pinhole", (0.1, 1.0, 0.95), 0.0)):
+        cam = look_at(pos, (0.0, 0.9, -0.2), fov=70.0, aperture=aperture, focal_dist=1.2)
+        light = dict(pos=(0.0, 1.98, 0.0), N=(0.0, -1.0, 0.0), right=(1.0, 0.0, 0.0), up=(0.0, 0.0, 1.0), size=(0.3, 0.3), E=(60.0, 60.0, 60.0))
+        params = make_params(W, H, cam, scene.world_radius, n_tris=len(scene.tris), light=light, max_bounces=3)
+        with CLContext(N) as gpu:
+            tg, _ = run_lockstep(gpu, oracle_ctx(N), scene, params, iterations=8)
+            orig = gpu.readTasks()[SLOT.ORIG:SLOT.ORIG + 3].view(np.float32)
+        if aperture:
+            assert len(np.unique(orig[0])) > 100, "an open aperture must spread the ray origins"
+        with CLContext(N) as gpu:
+            run_mk_lockstep(gpu, oracle_ctx(N), scene, params, spp=2)
