@@ -7,9 +7,9 @@
 //
 // Camera: there are no saved camera states in the reference tree (data/states is empty), so the camera is placed to frame
 // the scene's bounding box; the light is the reference's "headlamp" (Tracer::updateAreaLight, src/tracer.cpp:820-826:
-// the area light sits just behind the camera and faces along the view direction).  PNG textures are decoded by the library
-// (flx_image_load) and packed like CLContext::packTextures; materials whose texture is in another format (JPEG) fall back to
-// their constants.
+// the area light sits just behind the camera and faces along the view direction).  PNG and JPEG textures are decoded by the
+// library (flx_image_load) and packed like CLContext::packTextures; a material whose texture file is missing or in another
+// format falls back to its constants.
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -49,8 +49,8 @@ int main(int argc, char **argv)
             throw std::runtime_error(flx_io_last_error());
         const uint32_t nTris = flx_scene_num_triangles(scene);
         std::vector<flx_Material> mats(flx_scene_materials(scene), flx_scene_materials(scene) + flx_scene_num_materials(scene));
-        // textures: PNG files are decoded by the library; anything else (JPEG) is left out and the materials that use it fall
-        // back to their constants
+        // textures: PNG and JPEG files are decoded by the library; a texture that cannot be read is left out and the materials
+        // that use it fall back to their constants
         const std::string modelPath = argv[1];
         const std::string folder = modelPath.substr(0, modelPath.find_last_of('/') + 1);
         const uint32_t nTex = flx_scene_num_textures(scene);
@@ -91,7 +91,7 @@ int main(int argc, char **argv)
         for (uint8_t *im : images)
             flx_image_free(im);
         if (nTex)
-            std::fprintf(stderr, "textures: %u of %u decoded (PNG); the others fall back to material constants\n", decoded, nTex);
+            std::fprintf(stderr, "textures: %u of %u decoded%s\n", decoded, nTex, decoded < nTex ? "; the others fall back to material constants" : "");
 
         CLContext clctx(W * H);
         std::vector<flx_Node> nodes(2 * (size_t)nTris);

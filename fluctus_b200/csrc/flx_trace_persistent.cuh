@@ -1,7 +1,7 @@
 // flx_trace_persistent.cuh -- the production traversal kernels: persistent threads with dynamic ray fetch.
 //
 // Why: with one ray per thread (k_extrays/k_shadowrays in flx_kernels.cuh, kept as the simple variant) ncu shows 5.9 of
-// 32 lanes active per issued instruction on Conference (profiles/r1_v1_extrays_raw.csv): incoherent rays differ widely in
+// 32 lanes active per issued instruction on Conference (profiles/old/r1_v1_extrays_raw.csv): incoherent rays differ widely in
 // traversal length, so a warp is held by its longest ray.  Here a warp owns 32 ray SLOTS instead: whenever fewer than
 // `threshold` lanes still hold a ray, the idle lanes take new rays from the queue with one warp-aggregated atomic
 // (persistent-threads scheme after Aila & Laine 2009), and the traversal itself is organised "while-while": all lanes

@@ -152,7 +152,40 @@ class CLContext
     void setTile(uint32_t part, uint32_t nParts, uint32_t stripeRows) { verify(flx_set_tile(ctx, part, nParts, stripeRows), "setTile"); }
     uint32_t tilePixels() const { return flx_tile_pixels(ctx); }
     void commInit(const void *uniqueId128, int rank, int nranks) { verify(flx_comm_init(ctx, uniqueId128, rank, nranks), "commInit"); }
+    // asynchronous like the enqueue* calls (own stream, device-side snapshot of the frame as of this call); complete after
+    // finishQueue(), or on return when a host destination is given
     void gatherPixels(int root, float *fullImageOrNull) { verify(flx_gather_pixels(ctx, root, fullImageOrNull), "gatherPixels"); }
+    void readPixelsInto(float *rgba, size_t numPixels) { verify(flx_read_pixels(ctx, rgba, numPixels), "readPixels"); } // e.g. into hostAlloc()ed memory
+
+    // ---- new: denoiser feature buffers (the reference's Tracer::useDenoiser / -DUSE_OPTIX_DENOISER build, src/kernel_impl.hpp:53)
+    void setDenoiser(bool on) { verify(flx_set_denoiser(ctx, on ? 1 : 0), "setDenoiser"); }
+    std::vector<float> readDenoiserAOV(bool albedo, bool processed)
+    {
+        std::vector<float> rgba((size_t)flx_tile_pixels(ctx) * 4);
+        verify(flx_read_denoiser_aov(ctx, albedo ? 1 : 0, processed ? 1 : 0, rgba.data(), rgba.size() / 4), "readDenoiserAOV");
+        return rgba;
+    }
+
+    // ---- new: hierarchy on the GPU instead of `new SBVH(&tris, ...)` (src/scene.cpp:574-590): the same Node[] / index arrays
+    void buildBVH(const flx_Triangle *tris, uint32_t numTris, std::vector<flx_Node> &nodes, std::vector<uint32_t> &indices, int quality = FLX_BVH_PLOC, uint32_t maxLeaf = 8,
+                  float *buildMs = nullptr)
+    {
+        nodes.resize(numTris ? 2 * (size_t)numTris - 1 : 0);
+        indices.resize(numTris);
+        uint32_t numNodes = 0;
+        verify(flx_build_bvh(ctx, tris, numTris, maxLeaf, quality, nodes.data(), (uint32_t)nodes.size(), &numNodes, indices.data(), buildMs), "buildBVH");
+        nodes.resize(numNodes);
+    }
+
+    // ---- new: page-locked host memory for the arrays handed to uploadSceneData / filled by readPixelsInto (DMA at link speed)
+    static void *hostAlloc(size_t bytes)
+    {
+        void *p = nullptr;
+        if (flx_host_alloc(&p, bytes) != 0)
+            throw std::runtime_error(std::string("hostAlloc: ") + flx_last_error(nullptr));
+        return p;
+    }
+    static void hostFree(void *p) { flx_host_free(p); }
 
     flx_ctx *handle() { return ctx; }
 

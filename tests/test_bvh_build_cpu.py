@@ -129,3 +129,30 @@ def test_builders_on_random_soups(quality):
             nodes, indices = BUILDERS[quality](tris, max_leaf)
             depth, leaves, sah = validate_bvh(nodes, indices, tris, max_leaf)
             assert depth <= 62
+
+
+def test_reference_presplitting_prototype_builds_a_valid_tree_and_is_no_better():
+    """`port_build_ploc_split` (early split clipping in front of PLOC): measured and NOT adopted.  It stays in the oracle
+    as the record of the experiment, so it is kept honest: the tree is structurally valid (duplicated references allowed, every triangle
+    referenced at least once), and on a scene with a few large triangles among many small ones its SAH cost is not below plain PLOC's."""
+    import ctypes as C
+    from fluctus_b200.scene import make_room_scene
+    from fluctus_b200.structs import NODE_DTYPE
+    from oracle.oracle_host import PORT_LIB, build_ploc, port_available
+    from parity_util import validate_bvh
+    if not port_available():
+        pytest.skip("oracle/liboracle.so not built")
+    tris = make_room_scene(materials="mixed", n_blobs=8).tris
+    lib = C.CDLL(PORT_LIB)
+    n, cap = len(tris), 4 * len(tris)
+    nodes, idx = np.zeros(2 * cap, NODE_DTYPE), np.zeros(cap, np.uint32)
+    nn, ni = C.c_uint32(), C.c_uint32()
+    f = lib.port_build_ploc_split
+    f.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_float, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
+    assert f(tris.ctypes.data, n, 8, 1e-2, nodes.ctypes.data, len(nodes), C.byref(nn), idx.ctypes.data, cap, C.byref(ni)) == 0
+    nodes, idx = nodes[:nn.value], idx[:ni.value]
+    assert ni.value > n and set(idx.tolist()) == set(range(n)), "the large triangles must have been split, and none lost"
+    _, _, sah_split = validate_bvh(nodes, idx, tris, unique_refs=False)
+    pn, pi = build_ploc(tris, 8)
+    _, _, sah_plain = validate_bvh(pn, pi, tris)
+    assert sah_split > 0.95 * sah_plain, (sah_split, sah_plain)

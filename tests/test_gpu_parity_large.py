@@ -84,3 +84,31 @@ def test_conference_metric_size_fused_render_matches_oracle():
         compare_pixels(gpu.readPixels(), cpu.readPixels(), "flx_render(3) at 1920x1080, N=2^21", rtol=1e-5)
         st = gpu.getStats()
         assert (st.extensionRays, st.shadowRays, st.primaryRays) == (tc.stats["extensionRays"], tc.stats["shadowRays"], tc.stats["primaryRays"])
+
+
+def test_country_kitchen_c3_320x180_32_iterations():
+    """C3 beyond thumbnail size: 57 600 paths, every BSDF type of the scene in its own queue, 11 textures + the bump map, night.hdr
+    environment lighting with MIS -- 32 iterations (3.5 generations of paths) in lockstep with the oracle."""
+    import os
+    from fluctus_b200 import EnvMapData
+    from conftest import SCENES_DIR
+    scene = SceneData.load_blob(scene_blob("country_kitchen"))
+    envp = os.path.join(SCENES_DIR, "night.env.bin")
+    if not os.path.exists(envp):
+        pytest.skip("env map blob missing")
+    env = EnvMapData.load_blob(envp)
+    from bench_configs import kitchen_params
+    W, H = 320, 180
+    params = kitchen_params(scene, W, H)
+    with CLContext(W * H) as gpu:
+        run_lockstep(gpu, oracle_ctx(W * H), scene, params, iterations=32, env=env, check_every=8)
+
+
+def test_luxball_c4_320x180_40_iterations():
+    """C4 beyond thumbnail size: ideal dielectric + diffuse in separate queues, 16 bounces (a generation of paths lives 17 iterations)."""
+    scene = SceneData.load_blob(scene_blob("luxball"))
+    from bench_configs import luxball_params
+    W, H = 320, 180
+    params = luxball_params(scene, W, H)
+    with CLContext(W * H) as gpu:
+        run_lockstep(gpu, oracle_ctx(W * H), scene, params, iterations=40, check_every=10)
