@@ -171,6 +171,9 @@ struct flx_ctx
     int traceVariant = 1;     // 0: one ray per thread, 1: persistent threads + dynamic fetch, while-while phases (production), 2: 1 + top-of-tree
                               // treelet in shared memory, 3: persistent threads, one majority step per iteration (flx_trace_greedy.cuh; measured equal)
     int bvhTriCostPercent = 100; // flx_build_bvh: SAH cost of a triangle test relative to a box test, in percent (reference constants: 100)
+    int gatherDirect = 0;     // flx_gather_pixels: 1 = receive every stripe straight into its rows of the full image; 0 (default) = rank-major
+                              // buffer + de-interleave.  Measured (C5 on 2 GPUs, profiles/r2_gather_direct_2gpu.txt): NCCL's cost per point-to-point
+                              // operation makes 135 stripe-sized receives take 1.8-2.0 ms against 0.44-0.55 ms for one receive + the pass
     int gatherPriority = 0;   // 1: the gather stream gets the render stream's (high) priority instead of the lowest
     int innerBias = 0;        // variant 3: an inner-node step runs when lanes-at-inner + bias >= lanes-at-triangle
     int topNodes = 2047;      // variant 2: treelet nodes staged per CTA (64 B each)
@@ -2382,6 +2385,9 @@ try
         REQUIRE(value >= 25 && value <= 1600, "flx_set_tuning: triangle cost must be in 25..1600 percent");
         ctx->bvhTriCostPercent = value;
         return 0;
+    case FLX_TUNE_GATHER_DIRECT:
+        ctx->gatherDirect = value != 0;
+        return 0;
     case FLX_TUNE_GATHER_PRIORITY:
         REQUIRE(ctx->gatherStream == nullptr, "flx_set_tuning: the gather stream already exists (set its priority before the first flx_gather_pixels)");
         ctx->gatherPriority = value != 0;
@@ -2921,25 +2927,35 @@ try
         maxTile = std::max(maxTile, tileOf[r]);
     }
     const size_t fullPixels = (size_t)ctx->width * ctx->height;
-    const bool grow = (ctx->rank == root && (ctx->gatherBufPixels < (size_t)maxTile * ctx->nranks || ctx->fullImagePixels < fullPixels)) ||
-                      ctx->gatherSnapshotPixels < ctx->tilePixels;
+    // Two ways to land the tiles in the full image on the root:
+    //   staged (default): one send / recv per rank into a rank-major buffer, then k_deinterleave.
+    //   direct (FLX_TUNE_GATHER_DIRECT = 1): stripe by stripe, sender and root issue one ncclSend / ncclRecv per stripe and the root
+    //     receives each stripe straight into its rows of the full image (a stripe of stripeRows rows is contiguous in both layouts); the
+    //     root's own stripes are one strided device copy.  No gather buffer, no de-interleave pass -- and 3-4x SLOWER: a grouped NCCL
+    //     point-to-point operation costs ~14 us whatever its size, and there is one per stripe (135 at 3840x2160 on 2 GPUs).  Kept,
+    //     bit-identical (tests run both), as the measured reason why the gather stays one transfer per rank.
+    const bool direct = ctx->gatherDirect != 0;
+    const bool isRoot = ctx->rank == root;
+    const bool needSnapshot = !(direct && isRoot); // the root's direct path copies its stripes into the full image instead
+    const bool grow = (isRoot && ((!direct && ctx->gatherBufPixels < (size_t)maxTile * ctx->nranks) || ctx->fullImagePixels < fullPixels)) ||
+                      (needSnapshot && ctx->gatherSnapshotPixels < ctx->tilePixels);
     if (grow && ctx->gatherStream) // a gather still in flight uses the buffers about to be replaced
         CU(cudaStreamSynchronize(ctx->gatherStream));
-    if (ctx->rank == root && ctx->gatherBufPixels < (size_t)maxTile * ctx->nranks)
+    if (isRoot && !direct && ctx->gatherBufPixels < (size_t)maxTile * ctx->nranks)
     {
         freeDev(ctx->gatherBuf);
         ctx->gatherBufPixels = 0;
         CU(cudaMalloc(&ctx->gatherBuf, (size_t)maxTile * ctx->nranks * 16));
         ctx->gatherBufPixels = (size_t)maxTile * ctx->nranks;
     }
-    if (ctx->rank == root && ctx->fullImagePixels < fullPixels)
+    if (isRoot && ctx->fullImagePixels < fullPixels)
     {
         freeDev(ctx->fullImage);
         ctx->fullImagePixels = 0;
         CU(cudaMalloc(&ctx->fullImage, fullPixels * 16));
         ctx->fullImagePixels = fullPixels;
     }
-    if (ctx->gatherSnapshotPixels < ctx->tilePixels)
+    if (needSnapshot && ctx->gatherSnapshotPixels < ctx->tilePixels)
     {
         freeDev(ctx->gatherSnapshot);
         ctx->gatherSnapshotPixels = 0;
@@ -2962,30 +2978,70 @@ try
     // the frame as of now: a snapshot on the render stream (ordered after the last splat, before the next) into the buffer
     // the gather before the previous one used -- so the render stream only ever waits for a gather two frames old
     const int par = ctx->gatherParity;
-    ctx->gatherParity ^= 1;
-    float *snapshot = ctx->gatherSnapshot + (size_t)par * ctx->gatherSnapshotPixels * 4;
-    if (ctx->snapshotBusy[par])
-        CU(cudaStreamWaitEvent(ctx->stream, ctx->evSnapshotFree[par], 0));
-    CU(cudaMemcpyAsync(snapshot, ctx->pixels, (size_t)ctx->tilePixels * 16, cudaMemcpyDeviceToDevice, ctx->stream));
+    const size_t stripeFloats = (size_t)ctx->stripeRows * ctx->width * 4; // one full stripe
+    float *snapshot = nullptr;
+    if (needSnapshot)
+    {
+        ctx->gatherParity ^= 1;
+        snapshot = ctx->gatherSnapshot + (size_t)par * ctx->gatherSnapshotPixels * 4;
+        if (ctx->snapshotBusy[par])
+            CU(cudaStreamWaitEvent(ctx->stream, ctx->evSnapshotFree[par], 0));
+        CU(cudaMemcpyAsync(snapshot, ctx->pixels, (size_t)ctx->tilePixels * 16, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    else
+    {
+        // root, direct: its stripes go from the accumulator into their rows of the full image in one strided copy (local stripe k is
+        // global stripe k * nParts + part; a ragged last stripe is simply fewer bytes).  The full image's other rows belong to the
+        // receives of this and earlier gathers, which are ordered on the gather stream.
+        const uint32_t myRows = localRows(ctx->height, ctx->part, ctx->nParts, ctx->stripeRows);
+        const uint32_t fullStripes = myRows / ctx->stripeRows, tailRows = myRows % ctx->stripeRows;
+        float *dst0 = ctx->fullImage + (size_t)ctx->part * stripeFloats;
+        if (fullStripes)
+            CU(cudaMemcpy2DAsync(dst0, stripeFloats * ctx->nParts * sizeof(float), ctx->pixels, stripeFloats * sizeof(float), stripeFloats * sizeof(float), fullStripes,
+                                 cudaMemcpyDeviceToDevice, ctx->stream));
+        if (tailRows)
+            CU(cudaMemcpyAsync(dst0 + (size_t)fullStripes * ctx->nParts * stripeFloats, ctx->pixels + (size_t)fullStripes * stripeFloats, (size_t)tailRows * ctx->width * 16,
+                               cudaMemcpyDeviceToDevice, ctx->stream));
+    }
     CU(cudaEventRecord(ctx->evSnapshot, ctx->stream));
     CU(cudaStreamWaitEvent(ctx->gatherStream, ctx->evSnapshot, 0));
     ctx->cur = ctx->gatherStream;
     {
-    Timed tm(ctx, FLX_K_GATHER); // NCCL send/recv group + de-interleave, on the gather stream
+    Timed tm(ctx, FLX_K_GATHER); // NCCL send/recv group (+ de-interleave when staged), on the gather stream
     const int ncclFloat = 7; // ncclFloat32
     int r = ctx->nccl.GroupStart();
-    if (r == 0)
-        r = ctx->nccl.Send(snapshot, (size_t)ctx->tilePixels * 4, ncclFloat, root, ctx->comm, ctx->gatherStream);
-    if (r == 0 && ctx->rank == root)
-        for (int src = 0; src < ctx->nranks && r == 0; src++)
-            r = ctx->nccl.Recv(ctx->gatherBuf + (size_t)src * maxTile * 4, (size_t)tileOf[src] * 4, ncclFloat, src, ctx->comm, ctx->gatherStream);
+    if (direct)
+    {
+        // stripe s (global) belongs to rank s % nParts and is local stripe s / nParts there; same order on both sides of each pair
+        const uint32_t nStripes = (ctx->height + ctx->stripeRows - 1) / ctx->stripeRows;
+        for (uint32_t s = 0; s < nStripes && r == 0; s++)
+        {
+            const int owner = (int)(s % ctx->nParts);
+            const uint32_t rows = std::min(ctx->stripeRows, ctx->height - s * ctx->stripeRows);
+            const size_t count = (size_t)rows * ctx->width * 4;
+            if (owner == root)
+                continue;
+            if (ctx->rank == owner)
+                r = ctx->nccl.Send(snapshot + (size_t)(s / ctx->nParts) * stripeFloats, count, ncclFloat, root, ctx->comm, ctx->gatherStream);
+            else if (isRoot)
+                r = ctx->nccl.Recv(ctx->fullImage + (size_t)s * stripeFloats, count, ncclFloat, owner, ctx->comm, ctx->gatherStream);
+        }
+    }
+    else
+    {
+        if (r == 0)
+            r = ctx->nccl.Send(snapshot, (size_t)ctx->tilePixels * 4, ncclFloat, root, ctx->comm, ctx->gatherStream);
+        if (r == 0 && isRoot)
+            for (int src = 0; src < ctx->nranks && r == 0; src++)
+                r = ctx->nccl.Recv(ctx->gatherBuf + (size_t)src * maxTile * 4, (size_t)tileOf[src] * 4, ncclFloat, src, ctx->comm, ctx->gatherStream);
+    }
     const int r2 = ctx->nccl.GroupEnd();
     if (r != 0 || r2 != 0)
     {
         ctx->cur = ctx->stream;
         return fail(ctx, FLX_E_NCCL, "NCCL gather failed: %s", ctx->nccl.GetErrorString(r != 0 ? r : r2));
     }
-    if (ctx->rank == root)
+    if (isRoot && !direct)
         k_deinterleave<<<(unsigned)((fullPixels + 255) / 256), 256, 0, ctx->gatherStream>>>(reinterpret_cast<const float4 *>(ctx->gatherBuf),
                                                                                             reinterpret_cast<float4 *>(ctx->fullImage), ctx->width, ctx->height,
                                                                                             ctx->nParts, ctx->stripeRows, maxTile);
@@ -2994,9 +3050,12 @@ try
     if ((rc = launchCheck(ctx, "k_deinterleave")))
         return rc;
     CU(cudaEventRecord(ctx->evGatherDone, ctx->gatherStream));
-    CU(cudaEventRecord(ctx->evSnapshotFree[par], ctx->gatherStream));
     ctx->gatherInFlight = true;
-    ctx->snapshotBusy[par] = true;
+    if (needSnapshot)
+    {
+        CU(cudaEventRecord(ctx->evSnapshotFree[par], ctx->gatherStream));
+        ctx->snapshotBusy[par] = true;
+    }
     if (ctx->rank == root && full_rgba_host_or_null)
     {
         CU(cudaMemcpyAsync(full_rgba_host_or_null, ctx->fullImage, fullPixels * 16, cudaMemcpyDeviceToHost, ctx->gatherStream));

@@ -22,6 +22,8 @@ def main():
     W, H, N, S = 96, 70, 8192, 4  # 70 rows / stripes of 4: ragged last stripe
     params = room_params(scene, W, H, max_bounces=4, separate_queues=True)
     ctx = CLContext(N, device=local)
+    direct = int(os.environ.get("FLX_GATHER_DIRECT", "0"))  # 0 (default): staged + de-interleave; 1: a send / receive per stripe straight into the full image
+    ctx.setTuning(gather_direct=direct)
     fd.setup_context(ctx, rank, world, S)
     ctx.uploadSceneData(scene)
     ctx.setupPixelStorage(W, H)
@@ -55,7 +57,7 @@ def main():
         m2 = (p2[:, :3].sum(axis=0) / p2[:, 3].sum())
         rel = np.abs(m1 - m2) / m2
         assert (rel < 0.03).all(), (m1, m2)
-        print("MULTI_GPU_OK world=%d mean radiance tiled %s untiled %s" % (world, m1, m2))
+        print("MULTI_GPU_OK world=%d gather_direct=%d mean radiance tiled %s untiled %s" % (world, direct, m1, m2))
     # asynchronous gathers every iteration (own stream, double-buffered snapshot) must not disturb the render, and the frame
     # delivered is the accumulator as of each call
     ctx.gatherPixels(0)

@@ -361,7 +361,8 @@ def test_pinned_host_memory_gives_the_same_bytes():
         compare_pixels(a.readPixels(), out, "pinned vs pageable read-back", rtol=1e-5)
 
 
-def test_gather_on_its_own_stream_single_rank(tmp_path):
+@pytest.mark.parametrize("direct", [1, 0])
+def test_gather_on_its_own_stream_single_rank(tmp_path, direct):
     """flx_gather_pixels with a one-rank communicator (NCCL send/recv to self): the gather runs on the library's gather stream from
     a snapshot, so (1) the frame it delivers is the accumulator AS OF THE CALL even though rendering continues right behind it,
     (2) gathers every iteration do not disturb the render (same path state as without), (3) a resize between gathers gets fresh
@@ -371,6 +372,7 @@ def test_gather_on_its_own_stream_single_rank(tmp_path):
     with CLContext(N) as a, CLContext(N) as b:
         try:
             uid = a.commUniqueId()
+            a.setTuning(gather_direct=direct)
             a.setTile(0, 1, 8)
             a.commInit(uid, 0, 1)
         except FluctusError as e:

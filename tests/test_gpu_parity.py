@@ -184,14 +184,16 @@ def test_traversal_work_counters_match_the_oracle():
         assert [g["shadow"][k] for k in ("nodes", "boxes", "tris")] == list(s)[:3]
 
 
-def test_multi_gpu_tiles_and_nccl_gather():
+@pytest.mark.parametrize("direct", [1, 0])
+def test_multi_gpu_tiles_and_nccl_gather(direct):
     import subprocess, sys, os, torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-                        "--master-port", "29731", os.path.join(root, "tests", "multi_gpu_check.py")], capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0 and "MULTI_GPU_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+                        "--master-port", str(29731 + direct), os.path.join(root, "tests", "multi_gpu_check.py")], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, FLX_GATHER_DIRECT=str(direct)))
+    assert r.returncode == 0 and "MULTI_GPU_OK" in r.stdout and "RESIZE_GATHER_OK 64x16" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
 
 
 def test_cpp_wrapper_headless_driver_matches_golden(tmp_path):

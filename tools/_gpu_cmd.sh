@@ -1,12 +1,10 @@
 #!/bin/bash
 set -x
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -6
-FLX_DEBUG_TIMING=1 timeout 600 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/r2_bench_d.json 2> gpurun_out/r2_bench_d.err; grep -c upload gpurun_out/r2_bench_d.err
-python -c "
-import json
-d=json.load(open('gpurun_out/r2_bench_d.json')); print({k:d[k] for k in ('value','ms_per_step','blocks')}); print(d['e2e']); print(d['roofline']['kernel_share_of_step'], d['cpu_baseline'])"
-timeout 300 python bench.py --impl reference --steps 20 --warmup 5 | python -c "
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_edge_cases.py -x -q -k "multi_gpu or gather" 2>&1 | tail -6
+for t in "gather_direct=0" "gather_direct=1" "gather_direct=1,gather_priority=1"; do
+  echo "== c5 2 gpus $t"
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29621 bench.py --gpus 2 --config c5 --steps 20 --warmup 5 --no-cpu-baseline --no-e2e --min-seconds 0.3 --tune $t 2>/dev/null | grep '^{' | python -c "
 import sys,json
-d=json.loads(sys.stdin.read()); print('reference arm', d['value'], d['cpu_baseline']['cores'])"
-timeout 300 ./examples/flx_render_file oracle/_ref/assets/country_kitchen/Country-Kitchen.obj gpurun_out/r2_kitchen_from_files.png 640 360 32 6 oracle/_ref/assets/env_maps/night.hdr 30 2>&1 | tail -4
+d=json.loads(sys.stdin.read()); g=d['gather']; print(round(d['value'],1), {k:(v['value'],v['ms_per_step'],v['gather_ms_per_call']) for k,v in g.items() if isinstance(v,dict)})"
+done
