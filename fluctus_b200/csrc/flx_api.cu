@@ -116,7 +116,7 @@ struct flx_ctx
     float4 *kdGamma = nullptr;
     flx_TexDescriptor *texDesc = nullptr;
     uint8_t *texData = nullptr;
-    float4 *tnodes = nullptr, *ttris = nullptr;
+    float4 *tnodes = nullptr, *ttris = nullptr, *tattr = nullptr; // traversal layout (flx_trace.cuh): inner nodes, leaf references, per-triangle attributes
     int rootRef = 0;
     uint32_t nTris = 0, nTNodes = 0, nTTris = 0, treeletNodes = 0;
     uint32_t materialTypes = 0;  // OR of the uploaded materials' type bits (Scene::getMaterialTypes, src/scene.cpp:25,299): kernels for
@@ -171,6 +171,8 @@ struct flx_ctx
     int traceVariant = 1;     // 0: one ray per thread, 1: persistent threads + dynamic fetch, while-while phases (production), 2: 1 + top-of-tree
                               // treelet in shared memory, 3: persistent threads, one majority step per iteration (flx_trace_greedy.cuh; measured equal)
     int bvhTriCostPercent = 100; // flx_build_bvh: SAH cost of a triangle test relative to a box test, in percent (reference constants: 100)
+    int shadowLeftFirst = 0;  // any-hit traversal takes the left child first instead of the nearer one (order-free result)
+    int logicTile = 256;      // paths per tile (= threads per CTA) of the logic kernel: 256 or 128
     int gatherDirect = 0;     // flx_gather_pixels: 1 = receive every stripe straight into its rows of the full image; 0 (default) = rank-major
                               // buffer + de-interleave.  Measured (C5 on 2 GPUs, profiles/r2_gather_direct_2gpu.txt): NCCL's cost per point-to-point
                               // operation makes 135 stripe-sized receives take 1.8-2.0 ms against 0.44-0.55 ms for one receive + the pass
@@ -299,8 +301,9 @@ BvhView makeBvh(const flx_ctx *c)
     BvhView b;
     b.nodes = c->tnodes;
     b.tris = c->ttris;
+    b.attr = c->tattr;
     b.rootRef = c->rootRef;
-    b.prefetch = c->prefetchChildren;
+    b.prefetch = c->prefetchChildren | (c->shadowLeftFirst ? 4 : 0);
     return b;
 }
 
@@ -988,6 +991,7 @@ static void preloadKernels()
     PRELOAD(k_repack_flags);
     PRELOAD(k_repack_emit);
     PRELOAD(k_validate_triangles);
+    PRELOAD(k_build_tattr);
 #undef PRELOAD
     cudaGetLastError();
 }
@@ -1080,7 +1084,7 @@ try
     CUB(cudaMemset(c->stats, 0, sizeof(flx_RenderStats64)));
     CUB(cudaMalloc(&c->currPixelIdx, sizeof(uint32_t)));
     CUB(cudaMemset(c->currPixelIdx, 0, sizeof(uint32_t)));
-    c->numScanTiles = (num_tasks + FLX_LOGIC_TILE - 1) / FLX_LOGIC_TILE;
+    c->numScanTiles = (num_tasks + 127) / 128; // enough for the smaller of the two tile sizes of k_logic
     CUB(cudaMalloc(&c->scanTiles, (size_t)c->numScanTiles * sizeof(unsigned long long)));
     CUB(cudaMalloc(&c->scanTicket, sizeof(uint32_t)));
     CUB(cudaMallocHost(&c->pinnedCounters, sizeof(flx_QueueCounters) * flx_ctx::kCounterRing));
@@ -1158,6 +1162,7 @@ void flx_destroy(flx_ctx *c)
     freeDev(c->tnodes);
     freeDev(c->ttris);
     freeDev(c->repackPool);
+    freeDev(c->tattr);
     freeDev(c->envRGBA);
     freeDev(c->probTable);
     freeDev(c->pdfTable);
@@ -1312,6 +1317,12 @@ static int uploadSceneImpl(flx_ctx *ctx, const flx_Triangle *tris, uint32_t n_tr
     };
     lap(nullptr);
     if ((rc = uploadArray(ctx, ctx->tris, tris, n_tris)))
+        return rc;
+    if ((rc = reserveDev(ctx, ctx->tattr, (size_t)n_tris * 64)))
+        return rc;
+    ctx->sceneBytes += (size_t)n_tris * 64;
+    k_build_tattr<<<(n_tris + 255) / 256, 256, 0, ctx->stream>>>(ctx->tris, n_tris, ctx->tattr);
+    if ((rc = launchCheck(ctx, "k_build_tattr")))
         return rc;
     lap("triangles (malloc + copy)");
     if ((rc = uploadArray(ctx, ctx->materials, materials, n_materials)))
@@ -1791,7 +1802,8 @@ static int launchMaterials(flx_ctx *ctx);
 static int launchLogic(flx_ctx *ctx, int first_iteration, bool fused)
 {
     const uint32_t maxId = first_iteration ? std::min(ctx->tilePixels, ctx->numTasks) : ctx->numTasks; // wf_logic.cl:45
-    const uint32_t tiles = (maxId + FLX_LOGIC_TILE - 1) / FLX_LOGIC_TILE;
+    const uint32_t LT = ctx->logicTile == 128 ? 128u : 256u;
+    const uint32_t tiles = (maxId + LT - 1) / LT;
     CU(cudaMemsetAsync(ctx->scanTiles, 0, (size_t)tiles * sizeof(unsigned long long), ctx->stream));
     CU(cudaMemsetAsync(ctx->scanTicket, 0, sizeof(uint32_t), ctx->stream));
     ScanState scan{ctx->scanTiles, ctx->scanTicket};
@@ -1812,13 +1824,21 @@ static int launchLogic(flx_ctx *ctx, int first_iteration, bool fused)
         else                                                                                                                                                   \
             k_logic<false, MB, 2><<<tiles, FLX_BLOCK, 0, ctx->stream>>>(fr, ctx->params, sc, scan, maxId);                                                     \
     } while (0)
-            switch (ctx->fusedMinBlocks)
+            if (LT == 128) // half-size tiles, compiled for twice as many resident CTAs (same register budget as 3 x 256)
             {
-            case 4: FUSEDK(4); break;
-            case 2: FUSEDK(2); break;
-            case 1: FUSEDK(1); break;
-            default: FUSEDK(3); break;
+                if (sep)
+                    k_logic<true, 6, 1, 128><<<tiles, 128, 0, ctx->stream>>>(fr, ctx->params, sc, scan, maxId);
+                else
+                    k_logic<false, 6, 2, 128><<<tiles, 128, 0, ctx->stream>>>(fr, ctx->params, sc, scan, maxId);
             }
+            else
+                switch (ctx->fusedMinBlocks)
+                {
+                case 4: FUSEDK(4); break;
+                case 2: FUSEDK(2); break;
+                case 1: FUSEDK(1); break;
+                default: FUSEDK(3); break;
+                }
 #undef FUSEDK
         }
         markPixelsWritten(ctx);
@@ -1829,6 +1849,14 @@ static int launchLogic(flx_ctx *ctx, int first_iteration, bool fused)
     }
     Timed tm(ctx, FLX_K_LOGIC);
 #define LOGIC(SEP, MB) k_logic<SEP, MB><<<tiles, FLX_BLOCK, 0, ctx->stream>>>(fr, ctx->params, sc, scan, maxId)
+    if (LT == 128)
+    {
+        if (sep)
+            k_logic<true, 6, 0, 128><<<tiles, 128, 0, ctx->stream>>>(fr, ctx->params, sc, scan, maxId);
+        else
+            k_logic<false, 6, 0, 128><<<tiles, 128, 0, ctx->stream>>>(fr, ctx->params, sc, scan, maxId);
+    }
+    else
     switch (ctx->logicMinBlocks)
     {
     case 2: if (sep) LOGIC(true, 2); else LOGIC(false, 2); break;
@@ -2384,6 +2412,13 @@ try
     case FLX_TUNE_BVH_TRI_COST:
         REQUIRE(value >= 25 && value <= 1600, "flx_set_tuning: triangle cost must be in 25..1600 percent");
         ctx->bvhTriCostPercent = value;
+        return 0;
+    case FLX_TUNE_SHADOW_LEFT_FIRST:
+        ctx->shadowLeftFirst = value != 0;
+        return 0;
+    case FLX_TUNE_LOGIC_TILE:
+        REQUIRE(value == 128 || value == 256, "flx_set_tuning: logic tile must be 128 or 256");
+        ctx->logicTile = value;
         return 0;
     case FLX_TUNE_GATHER_DIRECT:
         ctx->gatherDirect = value != 0;

@@ -103,3 +103,18 @@ __global__ void __launch_bounds__(256) k_repack_emit(const RepackView r)
         }
     }
 }
+
+// TAttr (flx_trace.cuh): the shading attributes of every triangle, gathered from the 160-byte records into 64 bytes.  Same values, so the
+// hit record is the same bit for bit; the extension kernel's write-back reads two L1 wavefronts per hit instead of seven.
+__global__ void __launch_bounds__(256) k_build_tattr(const flx_Triangle *tris, uint32_t nTris, float4 *attr)
+{
+    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= nTris)
+        return;
+    const flx_Triangle &T = tris[i];
+    float4 *q = attr + (size_t)i * 4;
+    q[0] = make_float4(T.v0.n.x, T.v0.n.y, T.v0.n.z, T.v1.n.x);
+    q[1] = make_float4(T.v1.n.y, T.v1.n.z, T.v2.n.x, T.v2.n.y);
+    q[2] = make_float4(T.v2.n.z, T.v0.t.x, T.v0.t.y, T.v1.t.x);
+    q[3] = make_float4(T.v1.t.y, T.v2.t.x, T.v2.t.y, __int_as_float(T.matId));
+}

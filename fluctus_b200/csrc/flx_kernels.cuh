@@ -230,14 +230,8 @@ __global__ void __launch_bounds__(FLX_TRACE_BLOCK) k_extrays(const __grid_consta
     int matId = -1, lightHit = 0;
     if (tri >= 0)
     {
-        const float4 *q = reinterpret_cast<const float4 *>(tris160 + tri);
-        const float4 n0 = __ldg(q + 1), t0 = __ldg(q + 2), n1 = __ldg(q + 4), t1 = __ldg(q + 5), n2 = __ldg(q + 7), t2 = __ldg(q + 8);
-        matId = __float_as_int(__ldg(q + 9).x);
         P = o + tbest * d;
-        N = norm3(bary3(ub, vb, v3(n0.x, n0.y, n0.z), v3(n1.x, n1.y, n1.z), v3(n2.x, n2.y, n2.z)));
-        const V3 uv = bary3(ub, vb, v3(t0.x, t0.y, t0.z), v3(t1.x, t1.y, t1.z), v3(t2.x, t2.y, t2.z));
-        tu = uv.x;
-        tv = uv.y;
+        hit_attributes(bvh, tri, ub, vb, N, tu, tv, matId);
     }
     if (prm.sampleImpl && prm.useAreaLight) // wf_extrays.cl:29, intersect.cl:124-155
     {
@@ -375,18 +369,19 @@ __device__ __noinline__ void denoiser_aov_wf(const Frame &fr, const flx_RenderPa
 // materials go through one kernel anyway (the reference's single-queue mode, wavefrontAllMaterials): with per-type queues the
 // point of the separate kernels is that a warp sees ONE BSDF, and folding them into this kernel puts up to five heavy lobes into
 // every warp (Country Kitchen: 0.61 ms for the three kernels, 3.8 ms fully fused) -- so with wfSeparateQueues only level 1 is used.
-template <bool SEPARATE_QUEUES, int MIN_BLOCKS, int FUSE = 0>
-__global__ void __launch_bounds__(FLX_BLOCK, MIN_BLOCKS) k_logic(const __grid_constant__ Frame fr, const __grid_constant__ flx_RenderParams prm, const SceneView sc,
+// LT: paths per tile = threads per CTA (256, or 128: half as many warps to wait for at each of the four barriers)
+template <bool SEPARATE_QUEUES, int MIN_BLOCKS, int FUSE = 0, int LT = FLX_LOGIC_TILE>
+__global__ void __launch_bounds__(LT, MIN_BLOCKS) k_logic(const __grid_constant__ Frame fr, const __grid_constant__ flx_RenderParams prm, const SceneView sc,
                                                      const ScanState scan, const uint32_t maxId)
 {
     __shared__ uint32_t s_tile;
-    __shared__ uint32_t s_warpCount[FLX_BLOCK / 32];
+    __shared__ uint32_t s_warpCount[LT / 32];
     __shared__ uint32_t s_base;
     if (threadIdx.x == 0)
         s_tile = atomicAdd(scan.ticket, 1u); // tiles are numbered in the order blocks start, so look-back never waits on an unscheduled block
     __syncthreads();
     const uint32_t tile = s_tile;
-    const uint32_t gid = tile * FLX_LOGIC_TILE + threadIdx.x;
+    const uint32_t gid = tile * LT + threadIdx.x;
     const bool live = gid < maxId;
     const Tasks &t = fr.tasks;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -480,7 +475,7 @@ __global__ void __launch_bounds__(FLX_BLOCK, MIN_BLOCKS) k_logic(const __grid_co
     __syncthreads();
     uint32_t tileCount = 0, warpBase = 0;
 #pragma unroll
-    for (int w = 0; w < FLX_BLOCK / 32; w++)
+    for (int w = 0; w < LT / 32; w++)
     {
         if (w == warp)
             warpBase = tileCount;
@@ -627,7 +622,7 @@ __global__ void __launch_bounds__(FLX_BLOCK, MIN_BLOCKS) k_logic(const __grid_co
     //      per-warp aggregation the reference's NVIDIA path does (wf_logic.cl:459-519, ptx_asm.cl:83-111).
     {
         constexpr int NQ = SEPARATE_QUEUES ? 6 : 2; // slot 0: shadow, slots 1..: material queues; FUSED: slot NQ = extension queue
-        constexpr int NW = FLX_BLOCK / 32;
+        constexpr int NW = LT / 32;
         __shared__ uint32_t s_cnt[7][NW];
         __shared__ uint32_t s_qbase[7];
         int q = -1; // material queue slot of this path (1-based), -1: none
@@ -741,7 +736,7 @@ __global__ void __launch_bounds__(FLX_BLOCK, MIN_BLOCKS) k_logic(const __grid_co
             t.setu(FLX_S_SEED, gid, seed);
     }
     // the last tile knows the total
-    if (threadIdx.x == 0 && (tile + 1u) * FLX_LOGIC_TILE >= maxId && tile * FLX_LOGIC_TILE < maxId)
+    if (threadIdx.x == 0 && (tile + 1u) * LT >= maxId && tile * LT < maxId)
         atomicAdd(counter_ptr(fr.counters, Q_RAYGEN), s_base + tileCount);
 }
 

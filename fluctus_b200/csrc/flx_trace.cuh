@@ -60,9 +60,39 @@ struct BvhView
 {
     const float4 *nodes; // TNode as 4 x float4
     const float4 *tris;  // TTri as 4 x float4
+    const float4 *attr;  // TAttr as 4 x float4, one per TRIANGLE: what a closest hit needs for its hit record -- the three vertex normals, the
+                         // three texture coordinates and the material index (n0.xyz n1.x | n1.yz n2.xy | n2.z t0.xy t1.x | t1.y t2.xy matId) --
+                         // in 64 bytes = two 256-bit loads instead of seven 128-bit loads scattered over the 160-byte triangle
     int rootRef;
     int prefetch;        // persistent kernels: 0 off, 1 prefetch both children into L1 as soon as their references are known, 2 into L2
 };
+
+struct F8
+{
+    float v[8];
+};
+FLX_DEV F8 ldg256(const void *p) // 32-byte aligned, read-only path: LDG.E.256, new on sm_100
+{
+    F8 r;
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+                 : "l"(p));
+    return r;
+}
+
+// The attributes of a closest hit (bvh.cl:273-278: interpolated, normalised vertex normal; interpolated texture coordinates; material
+// index) from the 64-byte TAttr record of the winning triangle.  The reference interpolates float3 texture coordinates and keeps .xy; z does
+// not reach the result, so it is not stored.
+FLX_DEV void hit_attributes(const BvhView &bvh, int tri, float ub, float vb, V3 &N, float &tu, float &tv, int &matId)
+{
+    const float4 *q = bvh.attr + 4 * (size_t)tri;
+    const F8 a = ldg256(q), b = ldg256(q + 2);
+    N = norm3(bary3(ub, vb, v3(a.v[0], a.v[1], a.v[2]), v3(a.v[3], a.v[4], a.v[5]), v3(a.v[6], a.v[7], b.v[0])));
+    const V3 uv = bary3(ub, vb, v3(b.v[1], b.v[2], 0.0f), v3(b.v[3], b.v[4], 0.0f), v3(b.v[5], b.v[6], 0.0f));
+    tu = uv.x;
+    tv = uv.y;
+    matId = __float_as_int(b.v[7]);
+}
 
 // slab test of one child box (reference: intersectAABB, src/intersect.cl:41-60)
 FLX_DEV bool box_test(float bminx, float bminy, float bminz, float bmaxx, float bmaxy, float bmaxz, V3 o, V3 idir, float tprev, float &tnear)

@@ -99,14 +99,8 @@ __global__ void __launch_bounds__(FLX_TRACE_BLOCK, MIN_BLOCKS) k_trace_greedy(co
                 int matId = -1, lightHit = 0;
                 if (tri >= 0)
                 {
-                    const float4 *q = reinterpret_cast<const float4 *>(tris160 + tri);
-                    const float4 n0 = __ldcs(q + 1), t0 = __ldcs(q + 2), n1 = __ldcs(q + 4), t1 = __ldcs(q + 5), n2 = __ldcs(q + 7), t2 = __ldcs(q + 8);
-                    matId = __float_as_int(__ldcs(q + 9).x);
                     P = o + tbest * d;
-                    N = norm3(bary3(ub, vb, v3(n0.x, n0.y, n0.z), v3(n1.x, n1.y, n1.z), v3(n2.x, n2.y, n2.z)));
-                    const V3 uv = bary3(ub, vb, v3(t0.x, t0.y, t0.z), v3(t1.x, t1.y, t1.z), v3(t2.x, t2.y, t2.z));
-                    tu = uv.x;
-                    tv = uv.y;
+                    hit_attributes(bvh, tri, ub, vb, N, tu, tv, matId);
                 }
                 if (lightTest && light_quad(prm.areaLight, o, d, tbest)) // wf_extrays.cl:29
                 {

@@ -25,18 +25,6 @@
 #include "flx_kernels.cuh"
 #include "flx_mk.cuh"
 
-struct F8
-{
-    float v[8];
-};
-FLX_DEV F8 ldg256(const void *p) // 32-byte aligned, read-only path
-{
-    F8 r;
-    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
-                 : "l"(p));
-    return r;
-}
 FLX_DEV uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // Stage `bytes` (multiple of 16) from global to shared memory with the bulk-copy engine; all threads of the CTA call this.
@@ -147,14 +135,8 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_trace_persistent(const __
                 int matId = -1, lightHit = 0;
                 if (tri >= 0)
                 {
-                    const float4 *q = reinterpret_cast<const float4 *>(tris160 + tri);
-                    const float4 n0 = __ldcs(q + 1), t0 = __ldcs(q + 2), n1 = __ldcs(q + 4), t1 = __ldcs(q + 5), n2 = __ldcs(q + 7), t2 = __ldcs(q + 8);
-                    matId = __float_as_int(__ldcs(q + 9).x);
                     P = o + tbest * d;
-                    N = norm3(bary3(ub, vb, v3(n0.x, n0.y, n0.z), v3(n1.x, n1.y, n1.z), v3(n2.x, n2.y, n2.z)));
-                    const V3 uv = bary3(ub, vb, v3(t0.x, t0.y, t0.z), v3(t1.x, t1.y, t1.z), v3(t2.x, t2.y, t2.z));
-                    tu = uv.x;
-                    tv = uv.y;
+                    hit_attributes(bvh, tri, ub, vb, N, tu, tv, matId);
                 }
                 if (lightTest && light_quad(prm.areaLight, o, d, tbest)) // wf_extrays.cl:29
                 {
@@ -289,11 +271,11 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_trace_persistent(const __
                     q2 = make_float4(h1.v[0], h1.v[1], h1.v[2], h1.v[3]);
                     q3 = make_int4(__float_as_int(h1.v[4]), __float_as_int(h1.v[5]), 0, 0);
                 }
-                if (bvh.prefetch) // both children's records start their way up while the two box tests run
+                if (bvh.prefetch & 3) // both children's records start their way up while the two box tests run
                 {
                     const float4 *c0 = q3.x >= 0 ? bvh.nodes + 4 * (size_t)q3.x : bvh.tris + 4 * (size_t)(~q3.x);
                     const float4 *c1 = q3.y >= 0 ? bvh.nodes + 4 * (size_t)q3.y : bvh.tris + 4 * (size_t)(~q3.y);
-                    if (bvh.prefetch == 1)
+                    if ((bvh.prefetch & 3) == 1)
                     {
                         asm volatile("prefetch.global.L1 [%0];" ::"l"(c0));
                         asm volatile("prefetch.global.L1 [%0];" ::"l"(c1));
@@ -309,7 +291,9 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_trace_persistent(const __
                 const bool rh = box_test(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, o, idir, tbest, rn);
                 if (lh && rh)
                 {
-                    const bool swap = rn < ln; // right child closer -> first (bvh.cl:292); ties keep left first
+                    // right child closer -> first (bvh.cl:292); ties keep left first.  Any-hit rays may visit in any order (the answer
+                    // is order-free): bvh.prefetch bit 2 makes them always take the left child first -- measured, DESIGN.md 4.1
+                    const bool swap = (ANYHIT && (bvh.prefetch & 4)) ? false : rn < ln;
                     FLX_PUSH(swap ? q3.x : q3.y);
                     cur = swap ? q3.y : q3.x;
                 }

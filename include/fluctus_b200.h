@@ -197,6 +197,8 @@ enum { FLX_TUNE_TRACE_VARIANT = 0,      /* 0: one ray per thread; 1 (default): p
                                            step of the majority kind (inner node / one triangle) per iteration (flx_trace_greedy.cuh; measured equal to 1) */
        FLX_TUNE_BVH_TRI_COST = 22,      /* flx_build_bvh: cost of a triangle test relative to a box test in the SAH collapse decision, in percent
                                            (100 = the reference's constants costTri = costBox = 1, src/bvh.hpp:72-73; larger = smaller leaves) */
+       FLX_TUNE_SHADOW_LEFT_FIRST = 25, /* any-hit (shadow) traversal visits the left child first instead of the nearer one; the result is order-free (default 0) */
+       FLX_TUNE_LOGIC_TILE = 24,        /* paths per tile (= threads per CTA) of the logic kernel: 256 (default) or 128 */
        FLX_TUNE_GATHER_DIRECT = 23,     /* flx_gather_pixels: 0 (default) one send / receive per rank into a rank-major buffer + a de-interleave pass; 1 one per
                                            stripe, straight into the rows of the root's full image (measured 3-4x slower: NCCL's per-operation cost); must
                                            be the same on every rank */
