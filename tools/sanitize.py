@@ -64,6 +64,59 @@ def main():
         ctx.render(2)
         tr.iterate()
         assert np.isfinite(ctx.readPixels()).all()
+    # round 2: denoiser feature buffers in both integrators, the gather on its own stream (one-rank communicator) in both
+    # placements, a re-upload into kept allocations, checkpoint save / load, page-locked host buffers, thin lens, 128-path logic tiles
+    import tempfile
+    from fluctus_b200 import FluctusError, look_at, make_params, pinned_empty
+    with CLContext(1500) as ctx:
+        ctx.setDenoiser(True)
+        params = room_params(scene, 40, 24, max_bounces=4, separate_queues=True)
+        for rep in range(2):  # the second round re-uploads into the allocations of the first
+            ctx.uploadSceneData(scene.pinned())
+            ctx.setupPixelStorage(40, 24)
+            tr = Tracer(ctx, params)
+            tr.start()
+            for _ in range(3):
+                tr.iterate()
+            ctx.render(2)
+            out = pinned_empty((40 * 24, 4), np.float32)
+            ctx.readPixels(out)
+            assert np.isfinite(out).all() and np.isfinite(ctx.readDenoiserAOV("normal", True)).all() and np.isfinite(ctx.readDenoiserAOV("albedo")).all()
+            tr.renderSingle(2)
+        ck = os.path.join(tempfile.mkdtemp(), "s.ckpt")
+        tr = Tracer(ctx, params)
+        tr.start()
+        ctx.render(2)
+        ctx.saveCheckpoint(ck)
+        ctx.render(1)
+        ctx.loadCheckpoint(ck)
+        ctx.render(1)
+        ctx.setTuning(logic_tile=128, shadow_left_first=1)
+        cam = look_at((0.0, 1.0, 0.95), (0.0, 0.9, -0.2), fov=70.0, aperture=0.02, focal_dist=1.2)
+        p2 = make_params(40, 24, cam, scene.world_radius, n_tris=len(scene.tris), max_bounces=3)
+        tr = Tracer(ctx, p2)
+        tr.start()
+        ctx.render(3)
+    for direct in (0, 1):
+        with CLContext(1500) as ctx:
+            try:
+                ctx.setTuning(gather_direct=direct)
+                ctx.setTile(0, 1, 4)
+                ctx.commInit(ctx.commUniqueId(), 0, 1)
+            except FluctusError as e:
+                print("gather not exercised: %s" % e)
+                break
+            ctx.uploadSceneData(scene)
+            for (w, h) in ((40, 22), (40, 24)):
+                ctx.setupPixelStorage(w, h)
+                tr = Tracer(ctx, room_params(scene, w, h, max_bounces=3))
+                tr.start()
+                full = np.zeros((w * h, 4), np.float32)
+                for it in range(4):
+                    ctx.render(1)
+                    ctx.gatherPixels(0, full if it % 2 else None)
+                ctx.finishQueue()
+                assert np.isfinite(full).all()
     print("SANITIZE_RUN_OK")
 
 
