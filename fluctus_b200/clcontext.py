@@ -106,14 +106,15 @@ class CLContext:
 
     def buildBVH(self, tris, max_leaf=8, quality="fast"):
         """GPU hierarchy build (flx_build_bvh): what `new SBVH(&tris, ...)` gives the reference (src/scene.cpp:574-590) -- the
-        Node[] / index arrays in the reference's format -- in milliseconds.  quality: "fast" (LBVH) or "ploc" (locally-ordered clustering:
-        better trees, a few ms).  Returns (nodes, indices, device_ms)."""
+        Node[] / index arrays in the reference's format -- in milliseconds.  quality: "fast" (LBVH), "ploc" (locally-ordered clustering:
+        better trees, a few ms) or "ploc_opt" (ploc + the parallel-reinsertion post-pass: trees on a par with the reference's SBVH, tens of
+        ms).  Returns (nodes, indices, device_ms)."""
         from .structs import NODE_DTYPE
         n = len(tris)
         nodes = np.zeros(max(2 * n - 1, 1), NODE_DTYPE)
         indices = np.zeros(n, np.uint32)
         n_nodes, ms = C.c_uint32(), C.c_float()
-        self._check(self._lib.flx_build_bvh(self._h, self._ptr(tris), n, int(max_leaf), {"fast": 0, "ploc": 1}[quality], self._ptr(nodes), len(nodes), C.byref(n_nodes), self._ptr(indices),
+        self._check(self._lib.flx_build_bvh(self._h, self._ptr(tris), n, int(max_leaf), {"fast": 0, "ploc": 1, "ploc_opt": 2}[quality], self._ptr(nodes), len(nodes), C.byref(n_nodes), self._ptr(indices),
                                             C.byref(ms)), "buildBVH")
         return nodes[:n_nodes.value].copy(), indices, ms.value
 
@@ -235,7 +236,7 @@ class CLContext:
         self._check(self._lib.flx_timer_end(self._h, C.byref(ms)), "timerEnd")
         return ms.value
 
-    TUNING = {"trace_variant": 0, "fetch_threshold": 1, "trace_blocks_per_sm": 2, "top_nodes": 3, "inner_min": 4, "logic_min_blocks": 5, "fetch_chunk": 6, "overlap_trace": 7, "postprocess_in_loop": 10, "smem_stack": 11, "max_l1": 12, "fuse_stages": 13, "prefetch_children": 15, "repack_on_host": 16, "overlap_postprocess": 17, "dirty_postprocess": 18, "l2_persist": 19, "fused_min_blocks": 14, "ext_min_blocks": 8, "shadow_min_blocks": 9, "inner_bias": 20, "gather_priority": 21, "bvh_tri_cost": 22, "gather_direct": 23, "logic_tile": 24, "shadow_left_first": 25}
+    TUNING = {"trace_variant": 0, "fetch_threshold": 1, "trace_blocks_per_sm": 2, "top_nodes": 3, "inner_min": 4, "logic_min_blocks": 5, "fetch_chunk": 6, "overlap_trace": 7, "postprocess_in_loop": 10, "smem_stack": 11, "max_l1": 12, "fuse_stages": 13, "prefetch_children": 15, "repack_on_host": 16, "overlap_postprocess": 17, "dirty_postprocess": 18, "l2_persist": 19, "fused_min_blocks": 14, "ext_min_blocks": 8, "shadow_min_blocks": 9, "inner_bias": 20, "gather_priority": 21, "bvh_tri_cost": 22, "gather_direct": 23, "logic_tile": 24, "shadow_left_first": 25, "bvh_reinsert": 26}
 
     def setTuning(self, **kv):
         for k, v in kv.items():

@@ -170,6 +170,7 @@ struct flx_ctx
     // tuning knobs (flx_set_tuning)
     int traceVariant = 1;     // 0: one ray per thread, 1: persistent threads + dynamic fetch, while-while phases (production), 2: 1 + top-of-tree
                               // treelet in shared memory, 3: persistent threads, one majority step per iteration (flx_trace_greedy.cuh; measured equal)
+    int bvhReinsertIterations = 16; // flx_build_bvh, FLX_BVH_PLOC_OPT: iterations of the parallel-reinsertion post-pass
     int bvhTriCostPercent = 100; // flx_build_bvh: SAH cost of a triangle test relative to a box test, in percent (reference constants: 100)
     int shadowLeftFirst = 0;  // any-hit traversal takes the left child first instead of the nearer one (order-free result)
     int logicTile = 256;      // paths per tile (= threads per CTA) of the logic kernel: 256 or 128
@@ -182,7 +183,7 @@ struct flx_ctx
     int fetchThreshold = 16;  // refill when fewer lanes than this still hold a ray
     int extMinBlocks = 9, shadowMinBlocks = 10; // variant 1: resident 128-thread CTAs per SM the kernels are compiled for
     int maxL1 = 0;
-    int smemStack = 0;        // variant 1: first 24 stack levels in shared memory ([level][thread], conflict-free)
+    int smemStack = 0;        // variant 1: first 4 / 8 / 24 stack levels in shared memory ([level][thread], conflict-free); 0 = all in local memory
     int fetchChunk = 32;     // queue entries a warp reserves per atomic
     int repackOnHost = 0;     // flx_upload_scene: build the traversal layout with the host code instead of the device kernels (checker)
     int l2Persist = 0;        // 0 off; 1 / 2: persisting-L2 access window over the TTri / TNode array on the two traversal streams
@@ -786,10 +787,10 @@ __global__ void k_deinterleave(const float4 *gathered, float4 *full, uint32_t wi
 template <bool ANYHIT, class COUNT, int MINB, int SDEPTH> static int launchPersistentV1(flx_ctx *ctx, uint32_t *fetch, unsigned long long *counts)
 {
     auto kern = k_trace_persistent<ANYHIT, COUNT, FLX_TRACE_BLOCK, false, MINB, SDEPTH>;
-    const size_t smem = (size_t)SDEPTH * FLX_TRACE_BLOCK * sizeof(int);
+    const size_t smem = (size_t)(SDEPTH > 0 ? SDEPTH : 0) * FLX_TRACE_BLOCK * sizeof(int);
     if (smem > 48 * 1024)
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (SDEPTH == 0 && ctx->maxL1) // the L1 is what this kernel lives on: ask for the largest L1 carve-out
+    if (SDEPTH <= 0 && ctx->maxL1) // the L1 is what this kernel lives on: ask for the largest L1 carve-out
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1));
     int perSM = ctx->traceBlocksPerSM;
     // the production instantiation (no counters, local-memory stack) asks the occupancy calculator once per context
@@ -839,23 +840,25 @@ template <bool ANYHIT, class COUNT> static int launchPersistentT(flx_ctx *ctx, u
         kern<<<ctx->numSMs, BLOCK, smem, ctx->cur>>>(makeFrame(ctx), ctx->params, makeBvh(ctx), ctx->tris, fetch, ctx->fetchThreshold, ctx->innerMin, ctx->fetchChunk, top, counts, MkView{});
         return 0;
     }
-    // register budget: the kernel is compiled for MINB resident 128-thread CTAs per SM; stack: local or 24 levels in shared memory
+    // register budget: the kernel is compiled for MINB resident 128-thread CTAs per SM; stack: local memory, or its first 4 / 8 / 24
+    // levels in shared memory
     const int mb = ANYHIT ? ctx->shadowMinBlocks : ctx->extMinBlocks;
-    if (ctx->smemStack)
-    {
-        switch (mb)
-        {
-        case 8: return launchPersistentV1<ANYHIT, COUNT, 8, 24>(ctx, fetch, counts);
-        case 9: return launchPersistentV1<ANYHIT, COUNT, 9, 24>(ctx, fetch, counts);
-        default: return launchPersistentV1<ANYHIT, COUNT, 10, 24>(ctx, fetch, counts);
-        }
+#define FLX_BY_MINB(SD)                                                                                                                                        \
+    switch (mb)                                                                                                                                                \
+    {                                                                                                                                                          \
+    case 8: return launchPersistentV1<ANYHIT, COUNT, 8, SD>(ctx, fetch, counts);                                                                               \
+    case 9: return launchPersistentV1<ANYHIT, COUNT, 9, SD>(ctx, fetch, counts);                                                                               \
+    default: return launchPersistentV1<ANYHIT, COUNT, 10, SD>(ctx, fetch, counts);                                                                             \
     }
-    switch (mb)
+    switch (ctx->smemStack)
     {
-    case 8: return launchPersistentV1<ANYHIT, COUNT, 8, 0>(ctx, fetch, counts);
-    case 9: return launchPersistentV1<ANYHIT, COUNT, 9, 0>(ctx, fetch, counts);
-    default: return launchPersistentV1<ANYHIT, COUNT, 10, 0>(ctx, fetch, counts);
+    case -1: FLX_BY_MINB(-1)
+    case 0: FLX_BY_MINB(0)
+    case 4: FLX_BY_MINB(4)
+    case 8: FLX_BY_MINB(8)
+    default: FLX_BY_MINB(24)
     }
+#undef FLX_BY_MINB
 }
 
 template <bool ANYHIT> static int launchPersistent(flx_ctx *ctx)
@@ -1389,7 +1392,9 @@ try
     REQUIRE(tris && nodes_out && n_nodes_out && indices_out, "flx_build_bvh: null array");
     REQUIRE(n_tris > 0 && n_tris < 0x40000000u, "flx_build_bvh: triangle count out of range");
     REQUIRE(max_leaf >= 1 && max_leaf <= 255, "flx_build_bvh: max_leaf must be in 1..255 (nPrims is a byte, src/bvhnode.hpp:58)");
-    REQUIRE(quality == FLX_BVH_FAST || quality == FLX_BVH_PLOC, "flx_build_bvh: quality must be FLX_BVH_FAST or FLX_BVH_PLOC");
+    REQUIRE(quality == FLX_BVH_FAST || quality == FLX_BVH_PLOC || quality == FLX_BVH_PLOC_OPT, "flx_build_bvh: quality must be FLX_BVH_FAST, FLX_BVH_PLOC or FLX_BVH_PLOC_OPT");
+    const bool ploc = quality != FLX_BVH_FAST;
+    const int reinsertIterations = quality == FLX_BVH_PLOC_OPT && n_tris > 2 ? ctx->bvhReinsertIterations : 0;
     CU(cudaSetDevice(ctx->device));
     const uint32_t n = n_tris, total = 2u * n - 1u;
     BvhBuild b;
@@ -1440,7 +1445,9 @@ try
     memset(&pb, 0, sizeof pb);
     void *scanTemp = nullptr;
     size_t scanBytes = 0;
-    if (quality == FLX_BVH_PLOC)
+    ReinsertView ri;
+    memset(&ri, 0, sizeof ri);
+    if (ploc)
     {
         pb.n = n;
         pb.maxLeaf = max_leaf;
@@ -1466,6 +1473,18 @@ try
         BALLOC(pb.scan, n);
         BALLOC(pb.depthMax, 1);
         BALLOC(pb.state, 2);
+        if (reinsertIterations > 0)
+        {
+            BALLOC(ri.alive, total);
+            BALLOC(ri.gain, total);
+            BALLOC(ri.out, total);
+            BALLOC(ri.pivot, total);
+            BALLOC(ri.lock, total);
+            BALLOC(ri.cand, total);
+            BALLOC(ri.win, total);
+            BALLOC(ri.visits, total);
+            BALLOC(ri.moves, 1);
+        }
         cub::DeviceScan::ExclusiveSum(nullptr, scanBytes, pb.flags, pb.scan, (int)n, ctx->stream);
         unsigned char *t = nullptr;
         BALLOC(t, scanBytes);
@@ -1498,7 +1517,7 @@ try
         k_bvh_prims<<<gridN, FLX_BVH_BLOCK, 0, st>>>(b);
         k_bvh_morton<<<gridN, FLX_BVH_BLOCK, 0, st>>>(b);
         cu(cub::DeviceRadixSort::SortKeys(sortTemp, sortBytes, b.keys, b.keysSorted, (int)n, 0, 62, st), "radix sort");
-        if (quality == FLX_BVH_PLOC)
+        if (ploc)
         {
             cu(cudaMemsetAsync(pb.depthMax, 0, sizeof(uint32_t), st), "memset");
             k_ploc_init<<<gridN, FLX_BVH_BLOCK, 0, st>>>(pb);
@@ -1527,6 +1546,27 @@ try
                     rc = fail(ctx, FLX_E_INVALID, "flx_build_bvh: PLOC made no progress (%u clusters after a batch that started with %u)", left, bound);
                 bound = left;
             }
+            if (reinsertIterations > 0 && rc == 0)
+            {
+                // the post-pass of FLX_BVH_PLOC_OPT (flx_bvh_build.cuh, "parallel reinsertion"): nothing comes back to the host in between
+                ri.b = pb;
+                ri.root = (int)(total - 1u); // the last node created
+                ri.total = total;
+                cu(cudaMemsetAsync(ri.moves, 0, sizeof(uint32_t), st), "memset");
+                k_ri_alive<<<gridT, FLX_BVH_BLOCK, 0, st>>>(ri);
+                for (int it = 0; it < reinsertIterations; it++)
+                {
+                    k_ri_search<<<gridT, FLX_BVH_BLOCK, 0, st>>>(ri);
+                    k_ri_lock<<<gridT, FLX_BVH_BLOCK, 0, st>>>(ri);
+                    k_ri_cand<<<gridT, FLX_BVH_BLOCK, 0, st>>>(ri);
+                    k_ri_guard<<<gridT, FLX_BVH_BLOCK, 0, st>>>(ri);
+                    k_ri_apply<<<gridT, FLX_BVH_BLOCK, 0, st>>>(ri);
+                    if (it + 1 < reinsertIterations)
+                        k_ri_refit<false><<<gridT, FLX_BVH_BLOCK, 0, st>>>(ri);
+                    else
+                        k_ri_refit<true><<<gridT, FLX_BVH_BLOCK, 0, st>>>(ri);
+                }
+            }
             k_ploc_emit<<<gridT, FLX_BVH_BLOCK, 0, st>>>(pb);
         }
         else
@@ -1543,14 +1583,14 @@ try
     if (rc == 0)
     {
         // the root: LBVH internal node 0 (or the single leaf, also id 0); PLOC: the last node created
-        const uint32_t rootId = quality == FLX_BVH_PLOC ? total - 1u : 0u;
+        const uint32_t rootId = ploc ? total - 1u : 0u;
         uint32_t depth = 0;
         cu(cudaMemcpyAsync(&nNodes, b.size + rootId, sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "size read-back");
-        if (quality == FLX_BVH_PLOC)
+        if (ploc)
             cu(cudaMemcpyAsync(&depth, pb.depthMax, sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "depth read-back");
         cu(cudaStreamSynchronize(st), "build");
         if (rc == 0 && depth > 62) // the traversal stack holds 64 entries (src/bvh.cl:240); a radix tree cannot get there, this one could
-            rc = fail(ctx, FLX_E_INVALID, "flx_build_bvh: PLOC tree is %u levels deep (limit 62); use FLX_BVH_FAST for this input", depth);
+            rc = fail(ctx, FLX_E_INVALID, "flx_build_bvh: %s tree is %u levels deep (limit 62); use FLX_BVH_FAST for this input", reinsertIterations > 0 ? "optimised PLOC" : "PLOC", depth);
     }
     if (rc == 0 && nNodes > nodes_capacity)
         rc = fail(ctx, FLX_E_INVALID, "flx_build_bvh: %u nodes do not fit the caller's %u", nNodes, nodes_capacity);
@@ -2413,6 +2453,10 @@ try
         REQUIRE(value >= 25 && value <= 1600, "flx_set_tuning: triangle cost must be in 25..1600 percent");
         ctx->bvhTriCostPercent = value;
         return 0;
+    case FLX_TUNE_BVH_REINSERT:
+        REQUIRE(value >= 0 && value <= 64, "flx_set_tuning: reinsertion iterations must be in 0..64");
+        ctx->bvhReinsertIterations = value;
+        return 0;
     case FLX_TUNE_SHADOW_LEFT_FIRST:
         ctx->shadowLeftFirst = value != 0;
         return 0;
@@ -2448,7 +2492,8 @@ try
         ctx->maxL1 = value != 0;
         return 0;
     case FLX_TUNE_SMEM_STACK:
-        ctx->smemStack = value != 0;
+        REQUIRE(value == -1 || value == 0 || value == 1 || value == 4 || value == 8 || value == 24, "flx_set_tuning: smem stack levels must be 0, 4, 8 or 24 (1 = 24), or -1 for local memory + the newest entry in a register");
+        ctx->smemStack = value == 1 ? 24 : value;
         return 0;
     case FLX_TUNE_POSTPROCESS_IN_LOOP:
         ctx->postprocessInLoop = value != 0;

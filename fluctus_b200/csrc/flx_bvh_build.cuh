@@ -507,3 +507,271 @@ __global__ void __launch_bounds__(FLX_BVH_BLOCK) k_ploc_emit(const PlocBuild b)
     }
     b.nodesOut[dfs] = out;
 }
+
+// ================================================================================================ parallel reinsertion
+// FLX_BVH_PLOC_OPT: a post-pass over the finished PLOC tree, after Meister & Bittner, "Parallel reinsertion for bounding volume
+// hierarchy optimization" (2018).  What the reference's SBVH gets from spatial splits -- little overlap between siblings
+// (src/sbvh.cpp:118-142) -- a bottom-up builder can approach by moving subtrees to where they enlarge the fewest boxes: on Conference
+// the PLOC tree makes a ray test both children of a node 50 % more often than the SBVH does, which is where its 10 % traversal deficit
+// came from.  Per iteration, on the tree as it stands:
+//   k_ri_search  every node x (not the root, not a child of the root, not inside a collapsed leaf) looks for the node y next to which it
+//                would sit best: x and its parent p leave (the sibling s takes p's place), p comes back as the parent of (y, x).  Gain =
+//                the half-area inner nodes lose (p itself; the ancestors of p below the lowest common ancestor "pivot" shrink) minus what
+//                they gain (p's new box; the ancestors of y below the pivot grow).  The pivot walks from p to the root; under each pivot
+//                the subtree on the other side is searched depth first, left child first, pruned where even a perfect fit (direct cost =
+//                the area of x) cannot beat the best gain so far.  Read-only, one thread per node;
+//   k_ri_lock    a move with gain > 0 puts (gain bits << 32 | x) on the six nodes whose links it rewrites -- x, p, s, the grandparent, y
+//                and y's parent -- with atomicMax: the largest gain wins a contested node, whatever the order of arrival;
+//   k_ri_cand    a move that holds all six is a candidate;
+//   k_ri_guard   simultaneous moves with disjoint link sets could still close a cycle (x1 goes below x2 while x2 goes below x1, or a longer
+//                chain): that takes, for every move of the chain, another moving node strictly between its pivot and its target -- so a
+//                candidate that finds another candidate's x on its way from y up to the pivot stands back;
+//   k_ri_apply   the remaining moves rewrite their links (disjoint sets: no two write the same node);
+//   k_ri_refit   boxes bottom-up, second arriver proceeds (min / max: exact, order-free).
+// After the last iteration the same bottom-up pass also recomputes SAH cost, subtree size, triangle count and the collapse decision
+// with the builder's formulas, and k_ploc_emit writes the arrays as before.  No float sums across threads, ties broken by node id:
+// oracle/bvh_oracle.c (ploc_reinsert) restates the iterations sequentially and arrives at the same arrays bit for bit.
+#define FLX_RI_STACK 128
+
+struct ReinsertView
+{
+    PlocBuild b;
+    int root;
+    uint32_t total;
+    uint32_t *alive;            // per node id: 0 = inside a collapsed leaf, 1 = inner node of the output tree, 2 = leaf of the output tree
+    float *gain;
+    int *out, *pivot;           // per node id: best target (-1: stay) and the pivot it was found under
+    unsigned long long *lock;
+    uint32_t *cand, *win;
+    uint32_t *visits;           // arrival counters of the bottom-up pass
+    uint32_t *moves;            // moves carried out, all iterations
+};
+
+FLX_DEV bool ri_is_leaf(const PlocBuild &b, int id) { return (uint32_t)id < b.n || b.collapsed[id] != 0u; }
+FLX_DEV void ri_union(float4 alo, float4 ahi, float4 blo, float4 bhi, float4 &lo, float4 &hi)
+{
+    lo = make_float4(fminf(alo.x, blo.x), fminf(alo.y, blo.y), fminf(alo.z, blo.z), 0.0f);
+    hi = make_float4(fmaxf(ahi.x, bhi.x), fmaxf(ahi.y, bhi.y), fmaxf(ahi.z, bhi.z), 0.0f);
+}
+
+__global__ void __launch_bounds__(FLX_BVH_BLOCK) k_ri_alive(const ReinsertView r)
+{
+    const uint32_t id = blockIdx.x * FLX_BVH_BLOCK + threadIdx.x;
+    if (id >= r.total)
+        return;
+    uint32_t alive = 1u;
+    for (int p = r.b.parent[id]; p >= 0; p = r.b.parent[p])
+        if (r.b.collapsed[p])
+        {
+            alive = 0u;
+            break;
+        }
+    r.alive[id] = alive ? (ri_is_leaf(r.b, (int)id) ? 2u : 1u) : 0u;
+}
+
+__global__ void __launch_bounds__(FLX_BVH_BLOCK) k_ri_search(const ReinsertView r)
+{
+    const uint32_t id = blockIdx.x * FLX_BVH_BLOCK + threadIdx.x;
+    if (id >= r.total)
+        return;
+    const PlocBuild &b = r.b;
+    r.lock[id] = 0ull;
+    r.cand[id] = 0u;
+    r.win[id] = 0u;
+    r.visits[id] = 0u;
+    const int x = (int)id;
+    float best = 0.0f;
+    int bestOut = -1, bestPivot = -1;
+    const int p = r.alive[id] ? b.parent[x] : -1;
+    if (x != r.root && p >= 0 && p != r.root)
+    {
+        const float4 xlo = b.bmin[x], xhi = b.bmax[x];
+        const float aX = half_area(xlo, xhi);
+        float dDec = half_area(b.bmin[p], b.bmax[p]);
+        float4 pathLo = xlo, pathHi = xhi; // set when the pivot leaves p
+        int child = x, pivot = p;
+        int stackNode[FLX_RI_STACK];
+        float stackInc[FLX_RI_STACK];
+        while (true)
+        {
+            const int l = b.left[pivot];
+            const int other = l == child ? b.right[pivot] : l;
+            int sp = 0;
+            stackNode[sp] = other;
+            stackInc[sp] = 0.0f;
+            sp++;
+            while (sp > 0)
+            {
+                --sp;
+                const int y = stackNode[sp];
+                const float inc = stackInc[sp];
+                const float4 ylo = b.bmin[y], yhi = b.bmax[y];
+                float4 ulo, uhi;
+                ri_union(ylo, yhi, xlo, xhi, ulo, uhi);
+                const float direct = half_area(ulo, uhi);
+                const float gain = (dDec - inc) - direct;
+                if (gain > best)
+                {
+                    best = gain;
+                    bestOut = y;
+                    bestPivot = pivot;
+                }
+                if (!ri_is_leaf(b, y))
+                {
+                    const float incChild = (inc + direct) - half_area(ylo, yhi);
+                    if (((dDec - incChild) - aX) > best && sp + 2 <= FLX_RI_STACK)
+                    {
+                        stackNode[sp] = b.right[y];
+                        stackInc[sp] = incChild;
+                        sp++;
+                        stackNode[sp] = b.left[y];
+                        stackInc[sp] = incChild;
+                        sp++;
+                    }
+                }
+            }
+            if (pivot == r.root)
+                break;
+            if (pivot == p)
+            {
+                pathLo = b.bmin[other];
+                pathHi = b.bmax[other];
+            }
+            else
+            {
+                ri_union(pathLo, pathHi, b.bmin[other], b.bmax[other], pathLo, pathHi);
+                dDec = dDec + (half_area(b.bmin[pivot], b.bmax[pivot]) - half_area(pathLo, pathHi));
+            }
+            child = pivot;
+            pivot = b.parent[pivot];
+        }
+    }
+    r.gain[id] = best;
+    r.out[id] = bestOut;
+    r.pivot[id] = bestPivot;
+}
+
+// the six nodes whose links the move of x next to y rewrites
+FLX_DEV void ri_link_set(const PlocBuild &b, int x, int y, int (&v)[6])
+{
+    const int p = b.parent[x];
+    v[0] = x;
+    v[1] = p;
+    v[2] = b.left[p] == x ? b.right[p] : b.left[p];
+    v[3] = b.parent[p];
+    v[4] = y;
+    v[5] = b.parent[y];
+}
+FLX_DEV unsigned long long ri_key(float gain, uint32_t x) { return ((unsigned long long)__float_as_uint(gain) << 32) | (unsigned long long)x; }
+
+__global__ void __launch_bounds__(FLX_BVH_BLOCK) k_ri_lock(const ReinsertView r)
+{
+    const uint32_t id = blockIdx.x * FLX_BVH_BLOCK + threadIdx.x;
+    if (id >= r.total || r.out[id] < 0)
+        return;
+    int v[6];
+    ri_link_set(r.b, (int)id, r.out[id], v);
+    const unsigned long long key = ri_key(r.gain[id], id);
+#pragma unroll
+    for (int k = 0; k < 6; k++)
+        atomicMax(r.lock + v[k], key);
+}
+
+__global__ void __launch_bounds__(FLX_BVH_BLOCK) k_ri_cand(const ReinsertView r)
+{
+    const uint32_t id = blockIdx.x * FLX_BVH_BLOCK + threadIdx.x;
+    if (id >= r.total || r.out[id] < 0)
+        return;
+    int v[6];
+    ri_link_set(r.b, (int)id, r.out[id], v);
+    const unsigned long long key = ri_key(r.gain[id], id);
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < 6; k++)
+        ok = ok && r.lock[v[k]] == key;
+    r.cand[id] = ok ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(FLX_BVH_BLOCK) k_ri_guard(const ReinsertView r)
+{
+    const uint32_t id = blockIdx.x * FLX_BVH_BLOCK + threadIdx.x;
+    if (id >= r.total || !r.cand[id])
+        return;
+    bool ok = true;
+    const int pivot = r.pivot[id];
+    for (int v = r.b.parent[r.out[id]]; v != pivot; v = r.b.parent[v])
+        if (r.cand[v])
+            ok = false;
+    r.win[id] = ok ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(FLX_BVH_BLOCK) k_ri_apply(const ReinsertView r)
+{
+    const uint32_t id = blockIdx.x * FLX_BVH_BLOCK + threadIdx.x;
+    if (id >= r.total || !r.win[id])
+        return;
+    const PlocBuild &b = r.b;
+    const int x = (int)id, y = r.out[id];
+    const int p = b.parent[x], s = b.left[p] == x ? b.right[p] : b.left[p], g = b.parent[p];
+    if (b.left[g] == p)
+        b.left[g] = s;
+    else
+        b.right[g] = s;
+    b.parent[s] = g;
+    const int yp = b.parent[y]; // may be g: read after g's link to p has become the link to s
+    if (b.left[yp] == y)
+        b.left[yp] = p;
+    else
+        b.right[yp] = p;
+    b.parent[p] = yp;
+    b.left[p] = y;
+    b.right[p] = x;
+    b.parent[y] = p;
+    atomicAdd(r.moves, 1u);
+}
+
+// bottom-up over the output tree from its leaves (single triangles and collapsed nodes); FULL: also SAH cost, surviving-subtree size,
+// triangle count and the collapse decision, as k_ploc_apply computes them when it creates a node
+template <bool FULL> __global__ void __launch_bounds__(FLX_BVH_BLOCK) k_ri_refit(const ReinsertView r)
+{
+    const uint32_t id = blockIdx.x * FLX_BVH_BLOCK + threadIdx.x;
+    if (id >= r.total)
+        return;
+    const PlocBuild &b = r.b;
+    if (r.alive[id] != 2u) // (not b.collapsed: the FULL pass rewrites it while other threads are still starting)
+        return;
+    int node = (int)id;
+    while (true)
+    {
+        __threadfence();
+        const int p = b.parent[node];
+        if (p < 0)
+            break;
+        if (atomicAdd(r.visits + p, 1u) == 0u)
+            break; // the sibling's thread will do the parent
+        __threadfence();
+        const int l = b.left[p], rr = b.right[p];
+        const volatile float4 *vmin = b.bmin, *vmax = b.bmax;
+        const float4 lmin = make_float4(vmin[l].x, vmin[l].y, vmin[l].z, 0.0f), lmax = make_float4(vmax[l].x, vmax[l].y, vmax[l].z, 0.0f);
+        const float4 rmin = make_float4(vmin[rr].x, vmin[rr].y, vmin[rr].z, 0.0f), rmax = make_float4(vmax[rr].x, vmax[rr].y, vmax[rr].z, 0.0f);
+        float4 lo, hi;
+        ri_union(lmin, lmax, rmin, rmax, lo, hi);
+        b.bmin[p] = lo;
+        b.bmax[p] = hi;
+        if (FULL)
+        {
+            const volatile float *vcost = b.cost;
+            const volatile uint32_t *vsize = b.size, *vprims = b.prims;
+            const float area = half_area(lo, hi);
+            const uint32_t count = vprims[l] + vprims[rr];
+            const float leafCost = (area * (float)count) * b.triCost;
+            const float innerCost = (area * 2.0f + vcost[l]) + vcost[rr];
+            const bool collapse = count <= b.maxLeaf && leafCost <= innerCost;
+            b.cost[p] = collapse ? leafCost : innerCost;
+            b.size[p] = collapse ? 1u : 1u + vsize[l] + vsize[rr];
+            b.prims[p] = count;
+            b.collapsed[p] = collapse ? 1u : 0u;
+        }
+        node = p;
+    }
+}

@@ -95,24 +95,48 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_trace_persistent(const __
     // hits its own bank whatever its depth (a push/pop is ONE wavefront); deeper levels -- beyond any tree the reference's
     // builders make for the shipped scenes -- spill to local memory.  With SDEPTH = 0 the whole stack is local memory, where
     // a push/pop by lanes at different depths touches up to 32 lines of L1, i.e. costs as much as a divergent node fetch.
+    // SDEPTH = -1: the whole stack in local memory, but the most recent entry stays in a register (`topReg`): an entry that is popped
+    // before the next push -- the far child of a node whose near child led straight to a leaf -- never touches memory.
     static_assert(!(TOP && SDEPTH > 0), "the treelet and the stack do not share dynamic shared memory");
-    int lstack[FLX_STACK_DEPTH - SDEPTH];
+    constexpr int SD = SDEPTH > 0 ? SDEPTH : 0;
+    constexpr bool TOPREG = SDEPTH < 0;
+    constexpr int NO_ENTRY = 0x7fffffff; // not a node reference (inner >= 0 and < 2^31 - 1, leaf < 0)
+    int lstack[FLX_STACK_DEPTH - SD];
+    int topReg = NO_ENTRY;
     int *const sstack = reinterpret_cast<int *>(dynSmem) + threadIdx.x;
 #define FLX_PUSH(v)                                                                                                                                            \
     do                                                                                                                                                         \
     {                                                                                                                                                          \
-        if (SDEPTH == 0 || sp >= SDEPTH)                                                                                                                       \
-            lstack[sp - SDEPTH] = (v);                                                                                                                         \
+        if (TOPREG)                                                                                                                                            \
+        {                                                                                                                                                      \
+            if (topReg != NO_ENTRY)                                                                                                                            \
+                lstack[sp++] = topReg;                                                                                                                         \
+            topReg = (v);                                                                                                                                      \
+        }                                                                                                                                                      \
         else                                                                                                                                                   \
-            sstack[sp * BLOCK] = (v);                                                                                                                          \
-        sp++;                                                                                                                                                  \
+        {                                                                                                                                                      \
+            if (SD == 0 || sp >= SD)                                                                                                                           \
+                lstack[sp - SD] = (v);                                                                                                                         \
+            else                                                                                                                                               \
+                sstack[sp * BLOCK] = (v);                                                                                                                      \
+            sp++;                                                                                                                                              \
+        }                                                                                                                                                      \
     } while (0)
 #define FLX_POP(dst)                                                                                                                                           \
     do                                                                                                                                                         \
     {                                                                                                                                                          \
-        --sp;                                                                                                                                                  \
-        (dst) = (SDEPTH == 0 || sp >= SDEPTH) ? lstack[sp - SDEPTH] : sstack[sp * BLOCK];                                                                      \
+        if (TOPREG && topReg != NO_ENTRY)                                                                                                                      \
+        {                                                                                                                                                      \
+            (dst) = topReg;                                                                                                                                    \
+            topReg = NO_ENTRY;                                                                                                                                 \
+        }                                                                                                                                                      \
+        else                                                                                                                                                   \
+        {                                                                                                                                                      \
+            --sp;                                                                                                                                              \
+            (dst) = (SD == 0 || sp >= SD) ? lstack[sp - SD] : sstack[sp * BLOCK];                                                                              \
+        }                                                                                                                                                      \
     } while (0)
+#define FLX_STACK_EMPTY (sp == 0 && (!TOPREG || topReg == NO_ENTRY))
     COUNT cnt;
     unsigned raysDone = 0;
     uint32_t chunkNext = 0, chunkEnd = 0, chunkSize = (uint32_t)fetchChunk; // warp-uniform
@@ -216,6 +240,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_trace_persistent(const __
                     occluded = false;
                     cur = bvh.rootRef;
                     sp = 0;
+                    topReg = NO_ENTRY;
                     active = true;
                     if (quadFirst)
                     {
@@ -301,7 +326,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_trace_persistent(const __
                     cur = q3.x;
                 else if (rh)
                     cur = q3.y;
-                else if (sp > 0)
+                else if (!FLX_STACK_EMPTY)
                     FLX_POP(cur);
                 else
                 {
@@ -352,7 +377,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_trace_persistent(const __
                     ub = umin;
                     vb = vmin;
                 }
-                if ((ANYHIT && occluded) || sp == 0)
+                if ((ANYHIT && occluded) || FLX_STACK_EMPTY)
                 {
                     active = false;
                     pending = true;
@@ -370,4 +395,5 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_trace_persistent(const __
     flush_counts(cnt, countTotals, raysDone);
 #undef FLX_PUSH
 #undef FLX_POP
+#undef FLX_STACK_EMPTY
 }

@@ -116,7 +116,10 @@ int flx_upload_scene(flx_ctx *ctx, const flx_Triangle *tris, uint32_t n_tris, co
  * instead of seconds; the tree is of lower quality than the reference's SBVH (DESIGN.md 4.5 has the measured trade-off).
  * nodes_out must hold nodes_capacity >= 2 * n_tris - 1 records in the worst case; build_ms (may be NULL) = device time. */
 enum { FLX_BVH_FAST = 0, /* LBVH: Morton order + binary radix tree + SAH collapse; a third of a millisecond for 300 k triangles */
-       FLX_BVH_PLOC = 1  /* parallel locally-ordered clustering (radius 16) on the Morton order + SAH collapse: better trees, a few ms */ };
+       FLX_BVH_PLOC = 1, /* parallel locally-ordered clustering (radius 16) on the Morton order + SAH collapse: better trees, a few ms */
+       FLX_BVH_PLOC_OPT = 2 /* FLX_BVH_PLOC + parallel reinsertion (FLX_TUNE_BVH_REINSERT iterations, default 16): subtrees move to where they
+                               enlarge the fewest boxes -- the overlap reduction the reference's SBVH gets from spatial splits (src/sbvh.cpp:118-142);
+                               trees trace within 3 % of / up to 5 % faster than the reference's SBVH; tens of ms */ };
 int flx_build_bvh(flx_ctx *ctx, const flx_Triangle *tris, uint32_t n_tris, uint32_t max_leaf, int quality, flx_Node *nodes_out, uint32_t nodes_capacity,
                   uint32_t *n_nodes_out, uint32_t *indices_out /* n_tris */, float *build_ms);
 
@@ -197,6 +200,7 @@ enum { FLX_TUNE_TRACE_VARIANT = 0,      /* 0: one ray per thread; 1 (default): p
                                            step of the majority kind (inner node / one triangle) per iteration (flx_trace_greedy.cuh; measured equal to 1) */
        FLX_TUNE_BVH_TRI_COST = 22,      /* flx_build_bvh: cost of a triangle test relative to a box test in the SAH collapse decision, in percent
                                            (100 = the reference's constants costTri = costBox = 1, src/bvh.hpp:72-73; larger = smaller leaves) */
+       FLX_TUNE_BVH_REINSERT = 26,      /* flx_build_bvh(FLX_BVH_PLOC_OPT): iterations of the reinsertion post-pass, 0..64 (default 16) */
        FLX_TUNE_SHADOW_LEFT_FIRST = 25, /* any-hit (shadow) traversal visits the left child first instead of the nearer one; the result is order-free (default 0) */
        FLX_TUNE_LOGIC_TILE = 24,        /* paths per tile (= threads per CTA) of the logic kernel: 256 (default) or 128 */
        FLX_TUNE_GATHER_DIRECT = 23,     /* flx_gather_pixels: 0 (default) one send / receive per rank into a rank-major buffer + a de-interleave pass; 1 one per
@@ -212,7 +216,7 @@ enum { FLX_TUNE_TRACE_VARIANT = 0,      /* 0: one ray per thread; 1 (default): p
        FLX_TUNE_EXT_MIN_BLOCKS = 8,     /* variant 1 register budget: extension kernel compiled for 8, 9 (default) or 10 CTAs of 128 per SM */
        FLX_TUNE_SHADOW_MIN_BLOCKS = 9,  /* same for the shadow kernel (default 10) */
        FLX_TUNE_POSTPROCESS_IN_LOOP = 10, /* flx_render: run the display pass every iteration like the reference's loop (default 1) */
-       FLX_TUNE_SMEM_STACK = 11,        /* variant 1: keep the first 24 traversal-stack levels in shared memory (default 0: measured slower, L1 shrinks) */
+       FLX_TUNE_SMEM_STACK = 11,        /* variant 1: keep the first 4 / 8 / 24 (value; 1 = 24) traversal-stack levels in shared memory; 0 = local memory; -1 = local memory + newest entry in a register */
        FLX_TUNE_MAX_L1 = 12,            /* variant 1: request the maximum L1 carve-out for the traversal kernels (default 0: measured 4 % slower) */
        FLX_TUNE_OVERLAP_TRACE = 7,      /* flx_render: run the shadow-ray kernel on a second stream, overlapping the extension kernel's tail (default 1) */
        FLX_TUNE_L2_PERSIST = 19,          /* persisting-L2 access window for the traversal streams: 0 off (default), 1 over the TTri array, 2 over the TNode array;

@@ -167,6 +167,182 @@ static void ploc_emit(const PNode *nd, uint32_t id, int32_t parent, Node *out, u
     ploc_emit(nd, (uint32_t)nd[id].right, (int32_t)ind, out, nOut, indices, nIdx, keys, n, 0);
 }
 
+/* ---------------------------------------------------------------- parallel reinsertion (FLX_BVH_PLOC_OPT)
+ * Post-pass over the finished PLOC tree, after Meister & Bittner, "Parallel reinsertion for bounding volume hierarchy optimization"
+ * (2018): what top-down builders get from spatial splits -- little overlap between siblings -- a bottom-up builder can approach by
+ * moving subtrees to where they enlarge the fewest boxes.  Per iteration, on the tree as it stands (restated here in the order the
+ * GPU kernels of flx_bvh_build.cuh run, so that the result is the same bit for bit):
+ *   search  every node x (not the root, not a child of the root, not inside a collapsed leaf) looks for the node y next to which it
+ *           would sit best: x and its parent p leave (the sibling s takes p's place), p comes back as the parent of (y, x).  The gain
+ *           is the half-area that inner nodes lose (p itself, and the ancestors of p below the lowest common ancestor "pivot", which
+ *           shrink) minus what they gain (the new box of p, and the ancestors of y below the pivot, which grow).  The pivot walks from
+ *           p to the root; under each pivot the subtree on the other side is searched depth first, left child first, pruned where even
+ *           a perfect fit (direct cost = area of x) cannot beat the best gain so far;
+ *   lock    a move with gain > 0 puts (gain bits << 32 | x) on the six nodes whose links it rewrites -- x, p, s, the grandparent g, y and
+ *           y's parent -- with max(): the largest gain wins a contested node; a move that holds all six is a candidate;
+ *   guard   simultaneous moves with disjoint link sets could still close a cycle (x1 goes below x2 while x2 goes below x1, or longer
+ *           chains): that takes, for every move of the chain, another moving node strictly between its pivot and its target -- so a
+ *           candidate with another candidate's x on its way down from the pivot to y stands back;
+ *   apply   the remaining moves are carried out (disjoint link sets: no two write the same node);
+ *   refit   boxes bottom-up.
+ * After the last iteration cost / size / triangle count / collapse decision are recomputed bottom-up with the builder's formulas. */
+static int g_ploc_reinsert = 0;
+void port_set_reinsert(int iterations) { g_ploc_reinsert = iterations; }
+#define RI_STACK 128
+static void box_union(f4 alo, f4 ahi, f4 blo, f4 bhi, f4 *lo, f4 *hi)
+{
+    lo->x = fminf(alo.x, blo.x); lo->y = fminf(alo.y, blo.y); lo->z = fminf(alo.z, blo.z); lo->w = 0.0f;
+    hi->x = fmaxf(ahi.x, bhi.x); hi->y = fmaxf(ahi.y, bhi.y); hi->z = fmaxf(ahi.z, bhi.z); hi->w = 0.0f;
+}
+static int ri_is_leaf(const PNode *nd, uint32_t n, int id) { return (uint32_t)id < n || nd[id].collapsed; }
+
+static void ri_search(const PNode *nd, const int *parent, uint32_t n, int root, int x, float *gainOut, int *outOut, int *pivotOut)
+{
+    const f4 xlo = nd[x].lo, xhi = nd[x].hi;
+    const float aX = half_area(xlo, xhi);
+    const int p = parent[x];
+    float best = 0.0f; int bestOut = -1, bestPivot = -1;
+    float dDec = half_area(nd[p].lo, nd[p].hi);
+    f4 pathLo = xlo, pathHi = xhi; /* set when the pivot leaves p */
+    int child = x, pivot = p;
+    int stackNode[RI_STACK]; float stackInc[RI_STACK];
+    for (;;)
+    {
+        const int other = nd[pivot].left == child ? nd[pivot].right : nd[pivot].left;
+        int sp = 0;
+        stackNode[sp] = other; stackInc[sp] = 0.0f; sp++;
+        while (sp > 0)
+        {
+            --sp;
+            const int y = stackNode[sp]; const float inc = stackInc[sp];
+            f4 ulo, uhi;
+            box_union(nd[y].lo, nd[y].hi, xlo, xhi, &ulo, &uhi);
+            const float direct = half_area(ulo, uhi);
+            const float gain = (dDec - inc) - direct;
+            if (gain > best) { best = gain; bestOut = y; bestPivot = pivot; }
+            if (!ri_is_leaf(nd, n, y))
+            {
+                const float incChild = (inc + direct) - half_area(nd[y].lo, nd[y].hi);
+                if (((dDec - incChild) - aX) > best && sp + 2 <= RI_STACK)
+                {
+                    stackNode[sp] = nd[y].right; stackInc[sp] = incChild; sp++;
+                    stackNode[sp] = nd[y].left; stackInc[sp] = incChild; sp++;
+                }
+            }
+        }
+        if (pivot == root) break;
+        if (pivot == p) { pathLo = nd[other].lo; pathHi = nd[other].hi; }
+        else
+        {
+            box_union(pathLo, pathHi, nd[other].lo, nd[other].hi, &pathLo, &pathHi);
+            dDec = dDec + (half_area(nd[pivot].lo, nd[pivot].hi) - half_area(pathLo, pathHi));
+        }
+        child = pivot; pivot = parent[pivot];
+    }
+    *gainOut = best; *outOut = bestOut; *pivotOut = bestPivot;
+}
+
+/* visits the nodes whose links a move rewrites: x, its parent p, its sibling s, its grandparent g, the target y and y's parent */
+#define RI_FOR_LINKSET(BODY)                                                                                  \
+    do {                                                                                                      \
+        const int p_ = parent[x]; const int s_ = nd[p_].left == x ? nd[p_].right : nd[p_].left;               \
+        int v; v = x; BODY; v = p_; BODY; v = s_; BODY; v = parent[p_]; BODY; v = y; BODY; v = parent[y]; BODY; \
+    } while (0)
+
+static void ri_refit_boxes(PNode *nd, uint32_t n, int id)
+{
+    if (ri_is_leaf(nd, n, id)) return;
+    ri_refit_boxes(nd, n, nd[id].left); ri_refit_boxes(nd, n, nd[id].right);
+    box_union(nd[nd[id].left].lo, nd[nd[id].left].hi, nd[nd[id].right].lo, nd[nd[id].right].hi, &nd[id].lo, &nd[id].hi);
+}
+static void ri_recost(PNode *nd, uint32_t n, uint32_t maxLeaf, int id)
+{
+    if (ri_is_leaf(nd, n, id)) return;
+    const int l = nd[id].left, r = nd[id].right;
+    ri_recost(nd, n, maxLeaf, l); ri_recost(nd, n, maxLeaf, r);
+    PNode *o = &nd[id];
+    box_union(nd[l].lo, nd[l].hi, nd[r].lo, nd[r].hi, &o->lo, &o->hi);
+    const float area = half_area(o->lo, o->hi);
+    const uint32_t count = nd[l].prims + nd[r].prims;
+    const float leafCost = (area * (float)count) * g_ploc_tri_cost;
+    const float innerCost = (area * 2.0f + nd[l].cost) + nd[r].cost;
+    const int collapse = count <= maxLeaf && leafCost <= innerCost;
+    o->cost = collapse ? leafCost : innerCost; o->size = collapse ? 1u : 1u + nd[l].size + nd[r].size; o->prims = count; o->collapsed = collapse;
+}
+static void ri_mark_alive(const PNode *nd, uint32_t n, int id, uint8_t *alive)
+{
+    alive[id] = 1;
+    if (ri_is_leaf(nd, n, id)) return;
+    ri_mark_alive(nd, n, nd[id].left, alive); ri_mark_alive(nd, n, nd[id].right, alive);
+}
+uint32_t g_ploc_reinsert_moves[64]; /* moves carried out per iteration of the last build (diagnostics) */
+static void ploc_reinsert(PNode *nd, uint32_t n, uint32_t total, int root, int iterations)
+{
+    int *parent = (int *)malloc(sizeof(int) * total);
+    uint8_t *alive = (uint8_t *)calloc(total, 1);
+    float *gain = (float *)malloc(sizeof(float) * total);
+    int *out = (int *)malloc(sizeof(int) * total), *piv = (int *)malloc(sizeof(int) * total);
+    uint64_t *lock = (uint64_t *)malloc(sizeof(uint64_t) * total);
+    for (uint32_t i = 0; i < total; i++) parent[i] = -1;
+    ri_mark_alive(nd, n, root, alive);
+    for (uint32_t i = 0; i < total; i++) if (alive[i] && !ri_is_leaf(nd, n, (int)i)) { parent[nd[i].left] = (int)i; parent[nd[i].right] = (int)i; }
+    for (int it = 0; it < iterations; it++)
+    {
+        for (uint32_t i = 0; i < total; i++) { gain[i] = 0.0f; out[i] = -1; lock[i] = 0; }
+        for (uint32_t i = 0; i < total; i++)
+            if (alive[i] && (int)i != root && parent[i] != root)
+                ri_search(nd, parent, n, root, (int)i, &gain[i], &out[i], &piv[i]);
+        for (uint32_t i = 0; i < total; i++)
+            if (out[i] >= 0)
+            {
+                const int x = (int)i, y = out[i];
+                uint32_t bits; memcpy(&bits, &gain[i], 4);
+                const uint64_t key = ((uint64_t)bits << 32) | (uint64_t)i;
+                RI_FOR_LINKSET(if (lock[v] < key) lock[v] = key);
+            }
+        uint32_t moves = 0;
+        uint8_t *cand = (uint8_t *)calloc(total, 1), *win = (uint8_t *)calloc(total, 1);
+        for (uint32_t i = 0; i < total; i++)
+            if (out[i] >= 0)
+            {
+                const int x = (int)i, y = out[i];
+                uint32_t bits; memcpy(&bits, &gain[i], 4);
+                const uint64_t key = ((uint64_t)bits << 32) | (uint64_t)i;
+                int ok = 1;
+                RI_FOR_LINKSET(if (lock[v] != key) ok = 0);
+                cand[i] = (uint8_t)ok;
+            }
+        for (uint32_t i = 0; i < total; i++)
+            if (cand[i])
+            {
+                int ok = 1;
+                for (int v = parent[out[i]]; v != piv[i]; v = parent[v])
+                    if (cand[v]) ok = 0;
+                win[i] = (uint8_t)ok;
+            }
+        free(cand);
+        for (uint32_t i = 0; i < total; i++)
+            if (win[i])
+            {
+                const int x = (int)i, y = out[i];
+                const int p = parent[x], s = nd[p].left == x ? nd[p].right : nd[p].left, g = parent[p];
+                if (nd[g].left == p) nd[g].left = s; else nd[g].right = s;
+                parent[s] = g;
+                const int yp = parent[y];
+                if (nd[yp].left == y) nd[yp].left = p; else nd[yp].right = p;
+                parent[p] = yp;
+                nd[p].left = y; nd[p].right = x;
+                parent[y] = p; parent[x] = p;
+                moves++;
+            }
+        free(win);
+        if (it < 64) g_ploc_reinsert_moves[it] = moves;
+        ri_refit_boxes(nd, n, root);
+        if (moves == 0) break;
+    }
+    free(parent); free(alive); free(gain); free(out); free(piv); free(lock);
+}
+
 int port_build_ploc(const Triangle *tris, uint32_t n, uint32_t maxLeaf, Node *nodes_out, uint32_t *n_nodes_out, uint32_t *indices_out)
 {
     if (n == 0) return 1;
@@ -226,6 +402,11 @@ int port_build_ploc(const Triangle *tris, uint32_t n, uint32_t maxLeaf, Node *no
         if (merged == 0) { free(pmin); free(pmax); free(keys); free(nd); free(cid); free(next); free(nn); return 2; }
         uint32_t *t = cid; cid = next; next = t;
         m = kept; nextId += merged;
+    }
+    if (g_ploc_reinsert > 0 && n > 2)
+    {
+        ploc_reinsert(nd, n, nextId, (int)cid[0], g_ploc_reinsert);
+        ri_recost(nd, n, maxLeaf, (int)cid[0]);
     }
     uint32_t nOut = 0, nIdx = 0;
     ploc_emit(nd, cid[0], -1, nodes_out, &nOut, indices_out, &nIdx, keys, n, 0);

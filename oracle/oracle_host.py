@@ -279,18 +279,21 @@ class PortContext(_CpuContext):
     PREFIX = "port_"
 
 
-def build_ploc(tris, max_leaf=8, tri_cost=1.0):
-    """CPU restatement of the FLX_BVH_PLOC builder (locally-ordered clustering) -> (nodes, indices)."""
-    return build_lbvh(tris, max_leaf, fn="port_build_ploc", tri_cost=tri_cost)
+def build_ploc(tris, max_leaf=8, tri_cost=1.0, reinsert=0):
+    """CPU restatement of the FLX_BVH_PLOC builder (locally-ordered clustering) -> (nodes, indices); reinsert = iterations of
+    the parallel-reinsertion post-pass (FLX_BVH_PLOC_OPT: FLX_TUNE_BVH_REINSERT iterations)."""
+    return build_lbvh(tris, max_leaf, fn="port_build_ploc", tri_cost=tri_cost, reinsert=reinsert)
 
 
-def build_lbvh(tris, max_leaf=8, fn="port_build_lbvh", tri_cost=1.0):
+def build_lbvh(tris, max_leaf=8, fn="port_build_lbvh", tri_cost=1.0, reinsert=0):
     """CPU restatement (oracle/bvh_oracle.c) of the GPU hierarchy builder flx_build_bvh -> (nodes, indices) in the
     reference's Node[] / index-list format.  tri_cost = FLX_TUNE_BVH_TRI_COST / 100."""
     from fluctus_b200.structs import NODE_DTYPE
     lib = C.CDLL(PORT_LIB)
     lib.port_set_tri_cost.argtypes = [C.c_float]
     lib.port_set_tri_cost(float(tri_cost))
+    lib.port_set_reinsert.argtypes = [C.c_int]
+    lib.port_set_reinsert(int(reinsert))
     n = len(tris)
     nodes = np.zeros(max(2 * n - 1, 1), NODE_DTYPE)
     indices = np.zeros(n, np.uint32)

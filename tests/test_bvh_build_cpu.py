@@ -15,7 +15,11 @@ from parity_util import setup_context, validate_bvh
 
 from oracle.oracle_host import PortContext, build_lbvh, build_ploc, port_available
 
-BUILDERS = {"fast": build_lbvh, "ploc": build_ploc}
+def build_ploc_opt(tris, max_leaf=8, tri_cost=1.0):
+    return build_ploc(tris, max_leaf, tri_cost=tri_cost, reinsert=16)
+
+
+BUILDERS = {"fast": build_lbvh, "ploc": build_ploc, "ploc_opt": build_ploc_opt}
 
 pytestmark = pytest.mark.skipif(not port_available(), reason="oracle/liboracle.so not built (python oracle/build_oracle.py)")
 
@@ -33,7 +37,7 @@ def tri_soup(points):
     return t
 
 
-@pytest.mark.parametrize("quality", ["fast", "ploc"])
+@pytest.mark.parametrize("quality", ["fast", "ploc", "ploc_opt"])
 @pytest.mark.parametrize("max_leaf", [1, 4, 8])
 def test_builder_output_honours_the_reference_contract(max_leaf, quality):
     for scene in (make_room_scene(materials="mixed", n_blobs=8), teapot_scene()):
@@ -44,7 +48,7 @@ def test_builder_output_honours_the_reference_contract(max_leaf, quality):
             assert leaves == len(scene.tris)
 
 
-@pytest.mark.parametrize("quality", ["fast", "ploc"])
+@pytest.mark.parametrize("quality", ["fast", "ploc", "ploc_opt"])
 def test_builder_edge_cases(quality):
     build_lbvh = BUILDERS[quality]
     rng = np.random.default_rng(5)
@@ -73,9 +77,11 @@ def test_tree_quality_against_the_reference_sbvh():
         assert mine[2] < bound * ref[2], (name, mine, ref)
         ploc = validate_bvh(*build_ploc(scene.tris), scene.tris)  # locally-ordered clustering: on a par with the reference's SBVH
         assert ploc[2] < ploc_bound * ref[2] and ploc[2] < mine[2], (name, ploc, ref)
+        opt = validate_bvh(*build_ploc(scene.tris, reinsert=16), scene.tris)  # + reinsertion: below the SBVH's cost without duplicating a reference
+        assert opt[2] < ploc[2] and opt[2] < (0.92 if name == "conference" else 1.0) * ref[2] and opt[0] < 62, (name, opt, ploc, ref)
 
 
-@pytest.mark.parametrize("quality", ["fast", "ploc"])
+@pytest.mark.parametrize("quality", ["fast", "ploc", "ploc_opt"])
 def test_rendering_with_the_built_tree_finds_the_same_hits(quality):
     """Primary hits through the built tree and through the reference's SBVH (teapot fixture = reference PLY import + SBVH
     builder): bit-identical distance and triangle for all but grazing rays (shared edges, where which of two abutting
@@ -106,7 +112,7 @@ def test_rendering_with_the_built_tree_finds_the_same_hits(quality):
     assert abs(ma - mb) < 0.02 * abs(ma)
 
 
-@pytest.mark.parametrize("quality", ["fast", "ploc"])
+@pytest.mark.parametrize("quality", ["fast", "ploc", "ploc_opt"])
 def test_builders_on_random_soups(quality):
     """Randomised inputs: uniform, tightly clustered (many triangles per Morton cell), long slivers spanning the scene, exact
     duplicates and sizes around powers of two -- the output contract must hold for all of them."""

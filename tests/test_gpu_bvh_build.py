@@ -23,16 +23,25 @@ def same_tree(gpu_nodes, gpu_idx, cpu_nodes, cpu_idx, what):
     assert len(bad) == 0, "%s: %d nodes differ, first %d: %r vs %r" % (what, len(bad), bad[0], gpu_nodes[bad[0]], cpu_nodes[bad[0]])
 
 
-def build_both(tris, max_leaf=8, quality="fast", tri_cost=100):
+REINSERT_DEFAULT = 16  # FLX_TUNE_BVH_REINSERT default
+
+
+def build_both(tris, max_leaf=8, quality="fast", tri_cost=100, reinsert=None):
     from oracle.oracle_host import build_lbvh, build_ploc
     with CLContext(1024) as gpu:
         gpu.setTuning(bvh_tri_cost=tri_cost)
+        if reinsert is not None:
+            gpu.setTuning(bvh_reinsert=reinsert)
         nodes, idx, ms = gpu.buildBVH(tris, max_leaf, quality)
-    cn, ci = (build_ploc if quality == "ploc" else build_lbvh)(tris, max_leaf, tri_cost=tri_cost / 100.0)
+    if quality == "fast":
+        cn, ci = build_lbvh(tris, max_leaf, tri_cost=tri_cost / 100.0)
+    else:
+        iterations = 0 if quality == "ploc" else (REINSERT_DEFAULT if reinsert is None else reinsert)
+        cn, ci = build_ploc(tris, max_leaf, tri_cost=tri_cost / 100.0, reinsert=iterations)
     return nodes, idx, cn, ci, ms
 
 
-QUALITIES = ["fast", "ploc"]
+QUALITIES = ["fast", "ploc", "ploc_opt"]
 
 
 @pytest.mark.parametrize("quality", QUALITIES)
@@ -67,6 +76,20 @@ def test_builder_edge_cases(quality):
         tris = tri_soup(pts.astype(np.float32))
         nodes, idx, cn, ci, _ = build_both(tris, 4, quality)
         same_tree(nodes, idx, cn, ci, name + " " + quality)
+
+
+@pytest.mark.parametrize("iterations", [1, 2, 5])
+def test_reinsertion_iterations_match_the_cpu_restatement(iterations):
+    """FLX_BVH_PLOC_OPT after 1, 2 and 5 iterations of the reinsertion pass (search, lock, guard, apply, refit): the same arrays as
+    the sequential restatement, and a tree that is valid and no dearer than the plain PLOC one."""
+    scene = SceneData.load_blob(scene_blob("conference"))
+    nodes, idx, cn, ci, _ = build_both(scene.tris, 8, "ploc_opt", reinsert=iterations)
+    same_tree(nodes, idx, cn, ci, "conference, %d reinsertion iterations" % iterations)
+    depth, leaves, sah = validate_bvh(nodes, idx, scene.tris)
+    base = build_both(scene.tris, 8, "ploc")
+    assert sah < validate_bvh(base[0], base[1], scene.tris)[2], "reinsertion must lower the SAH cost on Conference"
+    zero = build_both(scene.tris, 8, "ploc_opt", reinsert=0)
+    same_tree(zero[0], zero[1], base[0], base[1], "0 iterations == FLX_BVH_PLOC")
 
 
 @pytest.mark.parametrize("quality", QUALITIES)

@@ -159,6 +159,29 @@ def test_full_size_invariants_and_kernel_variants_agree():
         compare_pixels(pixels[0], pixels[k], "trace variant 0 vs %d at full size" % k, rtol=1e-5)
 
 
+def test_traversal_stack_placements_agree():
+    """Where the traversal stack lives is invisible in the results: all of it in local memory (0, the default), its first 4 / 8 / 24
+    levels in shared memory, or local memory with the newest entry kept in a register (-1) -- same path state bit for bit after 8
+    iterations of the fused loop on Conference at 1280x720, N = 2^20."""
+    from bench_configs import conference_params
+    scene = SceneData.load_blob(scene_blob("conference"))
+    params = conference_params(scene, 1280, 720)
+    N = 1 << 20
+    base = None
+    for placement in (0, 4, 8, 24, -1):
+        with CLContext(N) as gpu:
+            gpu.setTuning(smem_stack=placement)
+            tr = setup_context(gpu, scene, params)
+            tr.start()
+            tr.render(8)
+            tasks, pix = gpu.readTasks(), gpu.readPixels()
+        if base is None:
+            base = (tasks, pix)
+        else:
+            compare_tasks(base[0], tasks, "stack placement 0 vs %d" % placement)
+            compare_pixels(base[1], pix, "stack placement 0 vs %d" % placement, rtol=1e-5)
+
+
 def test_full_size_is_deterministic_and_matches_fused_loop():
     """Two runs (one per-stage with host round trips, one fused flx_render with the shadow/extension overlap) at full size
     give the same path state bit for bit: no race decides anything that matters."""

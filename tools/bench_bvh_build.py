@@ -21,7 +21,7 @@ def main():
         row = dict(scene=scene_name, triangles=len(ref.tris))
         with CLContext(N) as ctx:
             built = {}
-            for quality, cost in (("fast", 100), ("ploc", 100), ("ploc", 150), ("ploc", 200), ("ploc", 300)):
+            for quality, cost in (("fast", 100), ("ploc", 100), ("ploc_opt", 100), ("ploc_opt", 150), ("ploc_opt", 200), ("ploc", 200)):
                 ctx.setTuning(bvh_tri_cost=cost)
                 ctx.buildBVH(ref.tris, 8, quality)  # warm-up (allocations, cub temp sizing)
                 times = [ctx.buildBVH(ref.tris, 8, quality)[2] for _ in range(5)]
@@ -30,7 +30,7 @@ def main():
                 row["build_ms_" + key] = round(min(times), 3)
                 built[key] = SceneData(ref.tris, idx, nodes, ref.materials, ref.tex_desc, ref.tex_data)
             ctx.setTuning(bvh_tri_cost=100)
-            variants = [("reference_sbvh", ref), ("gpu_lbvh", built["fast"]), ("gpu_ploc", built["ploc"])] + [("gpu_" + k, v) for k, v in built.items() if "_tc" in k]
+            variants = [("reference_sbvh", ref), ("gpu_lbvh", built["fast"]), ("gpu_ploc", built["ploc"]), ("gpu_ploc_opt", built["ploc_opt"])] + [("gpu_" + k, v) for k, v in built.items() if "_tc" in k]
             variants = variants + [("reference_sbvh_again", ref)]  # run-to-run spread of the yardstick itself
             for label, sc in variants:
                 depth, leaves, sah = validate_bvh(sc.nodes, sc.indices, sc.tris, unique_refs=not label.startswith("reference_sbvh"))
@@ -50,8 +50,9 @@ def main():
                                   mrays_per_s=round((st.extensionRays + st.shadowRays) / ms / 1e3, 1))
         row["throughput_ratio_lbvh"] = round(row["gpu_lbvh"]["mrays_per_s"] / row["reference_sbvh"]["mrays_per_s"], 3)
         row["throughput_ratio_ploc"] = round(row["gpu_ploc"]["mrays_per_s"] / row["reference_sbvh"]["mrays_per_s"], 3)
+        row["throughput_ratio_ploc_opt"] = round(row["gpu_ploc_opt"]["mrays_per_s"] / row["reference_sbvh"]["mrays_per_s"], 3)
         for k in list(row):
-            if k.startswith("gpu_ploc_tc"):
+            if k.startswith("gpu_ploc_tc") or k.startswith("gpu_ploc_opt_tc"):
                 row["throughput_ratio_" + k[4:]] = round(row[k]["mrays_per_s"] / row["reference_sbvh"]["mrays_per_s"], 3)
         print(json.dumps(row), flush=True)
 

@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=12)
     ap.add_argument("--iters", type=int, default=2)
     ap.add_argument("--tune", default="")
+    ap.add_argument("--builder", default="", help="fast | ploc: trace through a GPU-built hierarchy instead of the scene file's SBVH")
     a = ap.parse_args()
     from bench_configs import ENV_MAPS, params_for
     from fluctus_b200 import CLContext, EnvMapData, SceneData, Tracer
@@ -31,6 +32,9 @@ def main():
     with CLContext(a.tasks) as ctx:
         if a.tune:
             ctx.setTuning(**{k: int(v) for k, v in (kv.split("=") for kv in a.tune.split(","))})
+        if a.builder:
+            nodes, idx, _ = ctx.buildBVH(scene.tris, 8, a.builder)
+            scene = SceneData(scene.tris, idx, nodes, scene.materials, scene.tex_desc, scene.tex_data)
         ctx.uploadSceneData(scene)
         if a.scene in ENV_MAPS:
             ctx.createEnvMap(EnvMapData.load_blob(os.path.join(ROOT, "oracle", "_ref", "scenes", ENV_MAPS[a.scene] + ".env.bin")))

@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--shadow-blocks", default="10")
     ap.add_argument("--smem-stacks", default="0")
     ap.add_argument("--max-l1", default="1")
+    ap.add_argument("--builder", default="", help="fast | ploc: trace through a GPU-built hierarchy instead of the scene file's SBVH")
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
     from fluctus_b200 import CLContext, EnvMapData, SceneData, Tracer
@@ -37,6 +38,9 @@ def main():
     scene = SceneData.load_blob(os.path.join(ROOT, "oracle", "_ref", "scenes", a.scene + ".bin"))
     params = params_for(a.scene, scene, a.width, a.height)
     ctx = CLContext(a.tasks)
+    if a.builder:
+        nodes, idx, _ = ctx.buildBVH(scene.tris, 8, a.builder)
+        scene = SceneData(scene.tris, idx, nodes, scene.materials, scene.tex_desc, scene.tex_data)
     ctx.uploadSceneData(scene)
     if a.scene in ENV_MAPS:
         ctx.createEnvMap(EnvMapData.load_blob(os.path.join(ROOT, "oracle", "_ref", "scenes", ENV_MAPS[a.scene] + ".env.bin")))
