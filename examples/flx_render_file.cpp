@@ -98,7 +98,7 @@ int main(int argc, char **argv)
         std::vector<uint32_t> indices(nTris);
         uint32_t nNodes = 0;
         float buildMs = 0.0f;
-        if (flx_build_bvh(clctx.handle(), flx_scene_triangles(scene), nTris, 8, FLX_BVH_PLOC, nodes.data(), (uint32_t)nodes.size(), &nNodes, indices.data(), &buildMs) != 0)
+        if (flx_build_bvh(clctx.handle(), flx_scene_triangles(scene), nTris, 8, FLX_BVH_PLOC_OPT, nodes.data(), (uint32_t)nodes.size(), &nNodes, indices.data(), &buildMs) != 0)
             throw std::runtime_error(flx_last_error(clctx.handle()));
 
         SceneArrays s;

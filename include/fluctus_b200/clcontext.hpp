@@ -167,7 +167,7 @@ class CLContext
     }
 
     // ---- new: hierarchy on the GPU instead of `new SBVH(&tris, ...)` (src/scene.cpp:574-590): the same Node[] / index arrays
-    void buildBVH(const flx_Triangle *tris, uint32_t numTris, std::vector<flx_Node> &nodes, std::vector<uint32_t> &indices, int quality = FLX_BVH_PLOC, uint32_t maxLeaf = 8,
+    void buildBVH(const flx_Triangle *tris, uint32_t numTris, std::vector<flx_Node> &nodes, std::vector<uint32_t> &indices, int quality = FLX_BVH_PLOC_OPT, uint32_t maxLeaf = 8,
                   float *buildMs = nullptr)
     {
         nodes.resize(numTris ? 2 * (size_t)numTris - 1 : 0);
