@@ -236,7 +236,7 @@ class CLContext:
         self._check(self._lib.flx_timer_end(self._h, C.byref(ms)), "timerEnd")
         return ms.value
 
-    TUNING = {"trace_variant": 0, "fetch_threshold": 1, "trace_blocks_per_sm": 2, "top_nodes": 3, "inner_min": 4, "logic_min_blocks": 5, "fetch_chunk": 6, "overlap_trace": 7, "postprocess_in_loop": 10, "smem_stack": 11, "max_l1": 12, "fuse_stages": 13, "prefetch_children": 15, "repack_on_host": 16, "overlap_postprocess": 17, "dirty_postprocess": 18, "l2_persist": 19, "fused_min_blocks": 14, "ext_min_blocks": 8, "shadow_min_blocks": 9, "inner_bias": 20, "gather_priority": 21, "bvh_tri_cost": 22, "gather_direct": 23, "logic_tile": 24, "shadow_left_first": 25, "bvh_reinsert": 26}
+    TUNING = {"trace_variant": 0, "fetch_threshold": 1, "trace_blocks_per_sm": 2, "top_nodes": 3, "inner_min": 4, "logic_min_blocks": 5, "fetch_chunk": 6, "overlap_trace": 7, "postprocess_in_loop": 10, "smem_stack": 11, "max_l1": 12, "fuse_stages": 13, "prefetch_children": 15, "repack_on_host": 16, "overlap_postprocess": 17, "dirty_postprocess": 18, "l2_persist": 19, "fused_min_blocks": 14, "ext_min_blocks": 8, "shadow_min_blocks": 9, "inner_bias": 20, "gather_priority": 21, "bvh_tri_cost": 22, "gather_direct": 23, "logic_tile": 24, "shadow_left_first": 25, "bvh_reinsert": 26, "material_mask": 27, "bvh_depth_limit": 28}
 
     def setTuning(self, **kv):
         for k, v in kv.items():

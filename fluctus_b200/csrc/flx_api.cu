@@ -170,6 +170,8 @@ struct flx_ctx
     // tuning knobs (flx_set_tuning)
     int traceVariant = 1;     // 0: one ray per thread, 1: persistent threads + dynamic fetch, while-while phases (production), 2: 1 + top-of-tree
                               // treelet in shared memory, 3: persistent threads, one majority step per iteration (flx_trace_greedy.cuh; measured equal)
+    int useMaterialMask = 1;     // fused logic kernel: compile-time lobe set chosen from materialTypes
+    int bvhDepthLimit = 62;         // deepest PLOC tree flx_build_bvh hands out (tests lower it to reach the fallback)
     int bvhReinsertIterations = 16; // flx_build_bvh, FLX_BVH_PLOC_OPT: iterations of the parallel-reinsertion post-pass
     int bvhTriCostPercent = 100; // flx_build_bvh: SAH cost of a triangle test relative to a box test, in percent (reference constants: 100)
     int shadowLeftFirst = 0;  // any-hit traversal takes the left child first instead of the nearer one (order-free result)
@@ -976,6 +978,7 @@ static void preloadKernels()
     PRELOAD((k_trace_persistent<false, NoCount, FLX_TRACE_BLOCK, false, 9, 0>));
     PRELOAD((k_trace_persistent<true, NoCount, FLX_TRACE_BLOCK, false, 10, 0>));
     PRELOAD((k_logic<false, 3, 2>));
+    PRELOAD((k_logic<false, 3, 2, FLX_LOGIC_TILE, FLX_BXDF_DIFFUSE>));
     PRELOAD((k_logic<true, 3, 1>));
     PRELOAD((k_logic<false, 3, 0>));
     PRELOAD((k_logic<true, 3, 0>));
@@ -1589,8 +1592,15 @@ try
         if (ploc)
             cu(cudaMemcpyAsync(&depth, pb.depthMax, sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "depth read-back");
         cu(cudaStreamSynchronize(st), "build");
-        if (rc == 0 && depth > 62) // the traversal stack holds 64 entries (src/bvh.cl:240); a radix tree cannot get there, this one could
-            rc = fail(ctx, FLX_E_INVALID, "flx_build_bvh: %s tree is %u levels deep (limit 62); use FLX_BVH_FAST for this input", reinsertIterations > 0 ? "optimised PLOC" : "PLOC", depth);
+        // the traversal stack holds 64 entries (src/bvh.cl:240); a radix tree cannot get there, these trees could
+        if (rc == 0 && depth > (uint32_t)ctx->bvhDepthLimit && reinsertIterations > 0)
+        {
+            // reinsertion may deepen a tree (Country Kitchen: 55 -> 56 levels): fall back to the tree it started from
+            release();
+            return flx_build_bvh(ctx, tris, n_tris, max_leaf, FLX_BVH_PLOC, nodes_out, nodes_capacity, n_nodes_out, indices_out, build_ms);
+        }
+        if (rc == 0 && depth > (uint32_t)ctx->bvhDepthLimit)
+            rc = fail(ctx, FLX_E_INVALID, "flx_build_bvh: PLOC tree is %u levels deep (limit %d); use FLX_BVH_FAST for this input", depth, ctx->bvhDepthLimit);
     }
     if (rc == 0 && nNodes > nodes_capacity)
         rc = fail(ctx, FLX_E_INVALID, "flx_build_bvh: %u nodes do not fit the caller's %u", nNodes, nodes_capacity);
@@ -1856,11 +1866,16 @@ static int launchLogic(flx_ctx *ctx, int first_iteration, bool fused)
         // material kernels (a warp of those sees one BSDF, which is the reason the queues exist)
         {
             Timed tm(ctx, FLX_K_LOGIC_FUSED);
+            // the lobes compiled into the material part follow the scene's materials, as the reference's kernel build does
+            // (src/kernel_impl.hpp:261-266); FLX_TUNE_MATERIAL_MASK = 0 forces the all-lobes instantiation
+            const bool diffuseOnly = ctx->useMaterialMask && ctx->materialTypes == (uint32_t)FLX_BXDF_DIFFUSE;
 #define FUSEDK(MB)                                                                                                                                             \
     do                                                                                                                                                         \
     {                                                                                                                                                          \
         if (sep)                                                                                                                                               \
             k_logic<true, MB, 1><<<tiles, FLX_BLOCK, 0, ctx->stream>>>(fr, ctx->params, sc, scan, maxId);                                                      \
+        else if (diffuseOnly)                                                                                                                                  \
+            k_logic<false, MB, 2, FLX_LOGIC_TILE, FLX_BXDF_DIFFUSE><<<tiles, FLX_BLOCK, 0, ctx->stream>>>(fr, ctx->params, sc, scan, maxId);                   \
         else                                                                                                                                                   \
             k_logic<false, MB, 2><<<tiles, FLX_BLOCK, 0, ctx->stream>>>(fr, ctx->params, sc, scan, maxId);                                                     \
     } while (0)
@@ -2452,6 +2467,13 @@ try
     case FLX_TUNE_BVH_TRI_COST:
         REQUIRE(value >= 25 && value <= 1600, "flx_set_tuning: triangle cost must be in 25..1600 percent");
         ctx->bvhTriCostPercent = value;
+        return 0;
+    case FLX_TUNE_BVH_DEPTH_LIMIT:
+        REQUIRE(value >= 1 && value <= 62, "flx_set_tuning: hierarchy depth limit must be in 1..62");
+        ctx->bvhDepthLimit = value;
+        return 0;
+    case FLX_TUNE_MATERIAL_MASK:
+        ctx->useMaterialMask = value != 0;
         return 0;
     case FLX_TUNE_BVH_REINSERT:
         REQUIRE(value >= 0 && value <= 64, "flx_set_tuning: reinsertion iterations must be in 0..64");

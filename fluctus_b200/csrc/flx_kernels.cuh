@@ -370,7 +370,11 @@ __device__ __noinline__ void denoiser_aov_wf(const Frame &fr, const flx_RenderPa
 // point of the separate kernels is that a warp sees ONE BSDF, and folding them into this kernel puts up to five heavy lobes into
 // every warp (Country Kitchen: 0.61 ms for the three kernels, 3.8 ms fully fused) -- so with wfSeparateQueues only level 1 is used.
 // LT: paths per tile = threads per CTA (256, or 128: half as many warps to wait for at each of the four barriers)
-template <bool SEPARATE_QUEUES, int MIN_BLOCKS, int FUSE = 0, int LT = FLX_LOGIC_TILE>
+// MATMASK: the BSDF lobes the fused material part compiles in.  The reference builds its all-materials kernel with only the lobes the
+// scene's materials use ("Only handle material types that exist in scene", src/kernel_impl.hpp:261-266, getBxdfDefines in
+// src/utils.cpp:93-113); here the host picks the instantiation from the uploaded materials' types: all lobes, or diffuse only (Conference).
+#define FLX_ALL_BXDF (FLX_BXDF_DIFFUSE | FLX_BXDF_GLOSSY | FLX_BXDF_GGX_ROUGH_REFLECTION | FLX_BXDF_IDEAL_REFLECTION | FLX_BXDF_GGX_ROUGH_DIELECTRIC | FLX_BXDF_IDEAL_DIELECTRIC | FLX_BXDF_EMISSIVE)
+template <bool SEPARATE_QUEUES, int MIN_BLOCKS, int FUSE = 0, int LT = FLX_LOGIC_TILE, int MATMASK = FLX_ALL_BXDF>
 __global__ void __launch_bounds__(LT, MIN_BLOCKS) k_logic(const __grid_constant__ Frame fr, const __grid_constant__ flx_RenderParams prm, const SceneView sc,
                                                      const ScanState scan, const uint32_t maxId)
 {
@@ -727,10 +731,8 @@ __global__ void __launch_bounds__(LT, MIN_BLOCKS) k_logic(const __grid_constant_
                        matType == FLX_BXDF_IDEAL_REFLECTION || matType == FLX_BXDF_IDEAL_DIELECTRIC;
         if (hasQueue)
         {
-            constexpr int ALL = FLX_BXDF_DIFFUSE | FLX_BXDF_GLOSSY | FLX_BXDF_GGX_ROUGH_REFLECTION | FLX_BXDF_IDEAL_REFLECTION | FLX_BXDF_GGX_ROUGH_DIELECTRIC |
-                                FLX_BXDF_IDEAL_DIELECTRIC | FLX_BXDF_EMISSIVE;
             const V3 L = fHaveL ? fL : t.v(FLX_S_SHADOW_DIR, gid); // no new light sample: whatever an earlier vertex left in the slot
-            material_path<ALL>(t, sc, gid, fS, fMat, fBackface, rayDir, L, T, seed);
+            material_path<MATMASK>(t, sc, gid, fS, fMat, fBackface, rayDir, L, T, seed);
         }
         else
             t.setu(FLX_S_SEED, gid, seed);

@@ -200,6 +200,10 @@ enum { FLX_TUNE_TRACE_VARIANT = 0,      /* 0: one ray per thread; 1 (default): p
                                            step of the majority kind (inner node / one triangle) per iteration (flx_trace_greedy.cuh; measured equal to 1) */
        FLX_TUNE_BVH_TRI_COST = 22,      /* flx_build_bvh: cost of a triangle test relative to a box test in the SAH collapse decision, in percent
                                            (100 = the reference's constants costTri = costBox = 1, src/bvh.hpp:72-73; larger = smaller leaves) */
+       FLX_TUNE_MATERIAL_MASK = 27,     /* fused logic kernel: 1 (default) compile in only the BSDF lobes the uploaded materials use, like the reference's kernel
+                                           build (src/kernel_impl.hpp:261-266); 0 always the all-lobes instantiation */
+       FLX_TUNE_BVH_DEPTH_LIMIT = 28,   /* flx_build_bvh: deepest PLOC tree handed out, 1..62 (default 62: the traversal stack holds 64 entries).  A PLOC_OPT tree
+                                           beyond it falls back to the PLOC tree it started from; a PLOC tree beyond it is an error */
        FLX_TUNE_BVH_REINSERT = 26,      /* flx_build_bvh(FLX_BVH_PLOC_OPT): iterations of the reinsertion post-pass, 0..64 (default 16) */
        FLX_TUNE_SHADOW_LEFT_FIRST = 25, /* any-hit (shadow) traversal visits the left child first instead of the nearer one; the result is order-free (default 0) */
        FLX_TUNE_LOGIC_TILE = 24,        /* paths per tile (= threads per CTA) of the logic kernel: 256 (default) or 128 */

@@ -186,8 +186,9 @@ static void ploc_emit(const PNode *nd, uint32_t id, int32_t parent, Node *out, u
  *   apply   the remaining moves are carried out (disjoint link sets: no two write the same node);
  *   refit   boxes bottom-up.
  * After the last iteration cost / size / triangle count / collapse decision are recomputed bottom-up with the builder's formulas. */
-static int g_ploc_reinsert = 0;
+static int g_ploc_reinsert = 0, g_ploc_depth_limit = 62;
 void port_set_reinsert(int iterations) { g_ploc_reinsert = iterations; }
+void port_set_depth_limit(int levels) { g_ploc_depth_limit = levels; }
 #define RI_STACK 128
 static void box_union(f4 alo, f4 ahi, f4 blo, f4 bhi, f4 *lo, f4 *hi)
 {
@@ -403,7 +404,8 @@ int port_build_ploc(const Triangle *tris, uint32_t n, uint32_t maxLeaf, Node *no
         uint32_t *t = cid; cid = next; next = t;
         m = kept; nextId += merged;
     }
-    if (g_ploc_reinsert > 0 && n > 2)
+    const int reinserted = g_ploc_reinsert > 0 && n > 2;
+    if (reinserted)
     {
         ploc_reinsert(nd, n, nextId, (int)cid[0], g_ploc_reinsert);
         ri_recost(nd, n, maxLeaf, (int)cid[0]);
@@ -412,7 +414,22 @@ int port_build_ploc(const Triangle *tris, uint32_t n, uint32_t maxLeaf, Node *no
     ploc_emit(nd, cid[0], -1, nodes_out, &nOut, indices_out, &nIdx, keys, n, 0);
     *n_nodes_out = nOut;
     free(pmin); free(pmax); free(keys); free(nd); free(cid); free(next); free(nn);
-    return nIdx == n ? 0 : 3;
+    if (nIdx != n) return 3;
+    /* depth of the emitted tree (parents precede children); beyond the limit an optimised tree falls back to the one it started from,
+     * as flx_build_bvh does, and a plain one is an error there (5 here) */
+    uint32_t *depth = (uint32_t *)calloc(nOut, sizeof(uint32_t)), deepest = 0;
+    for (uint32_t i = 1; i < nOut; i++) { depth[i] = depth[nodes_out[i].parent] + 1u; if (depth[i] > deepest) deepest = depth[i]; }
+    free(depth);
+    if (deepest > (uint32_t)g_ploc_depth_limit)
+    {
+        if (!reinserted) return 5;
+        const int keep = g_ploc_reinsert;
+        g_ploc_reinsert = 0;
+        const int rc = port_build_ploc(tris, n, maxLeaf, nodes_out, n_nodes_out, indices_out);
+        g_ploc_reinsert = keep;
+        return rc;
+    }
+    return 0;
 }
 
 

@@ -279,13 +279,13 @@ class PortContext(_CpuContext):
     PREFIX = "port_"
 
 
-def build_ploc(tris, max_leaf=8, tri_cost=1.0, reinsert=0):
+def build_ploc(tris, max_leaf=8, tri_cost=1.0, reinsert=0, depth_limit=62):
     """CPU restatement of the FLX_BVH_PLOC builder (locally-ordered clustering) -> (nodes, indices); reinsert = iterations of
     the parallel-reinsertion post-pass (FLX_BVH_PLOC_OPT: FLX_TUNE_BVH_REINSERT iterations)."""
-    return build_lbvh(tris, max_leaf, fn="port_build_ploc", tri_cost=tri_cost, reinsert=reinsert)
+    return build_lbvh(tris, max_leaf, fn="port_build_ploc", tri_cost=tri_cost, reinsert=reinsert, depth_limit=depth_limit)
 
 
-def build_lbvh(tris, max_leaf=8, fn="port_build_lbvh", tri_cost=1.0, reinsert=0):
+def build_lbvh(tris, max_leaf=8, fn="port_build_lbvh", tri_cost=1.0, reinsert=0, depth_limit=62):
     """CPU restatement (oracle/bvh_oracle.c) of the GPU hierarchy builder flx_build_bvh -> (nodes, indices) in the
     reference's Node[] / index-list format.  tri_cost = FLX_TUNE_BVH_TRI_COST / 100."""
     from fluctus_b200.structs import NODE_DTYPE
@@ -294,6 +294,8 @@ def build_lbvh(tris, max_leaf=8, fn="port_build_lbvh", tri_cost=1.0, reinsert=0)
     lib.port_set_tri_cost(float(tri_cost))
     lib.port_set_reinsert.argtypes = [C.c_int]
     lib.port_set_reinsert(int(reinsert))
+    lib.port_set_depth_limit.argtypes = [C.c_int]
+    lib.port_set_depth_limit(int(depth_limit))
     n = len(tris)
     nodes = np.zeros(max(2 * n - 1, 1), NODE_DTYPE)
     indices = np.zeros(n, np.uint32)
@@ -302,6 +304,8 @@ def build_lbvh(tris, max_leaf=8, fn="port_build_lbvh", tri_cost=1.0, reinsert=0)
     f.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p]
     rc = f(tris.ctypes.data, n, int(max_leaf), nodes.ctypes.data, C.byref(n_nodes), indices.ctypes.data)
     lib.port_set_tri_cost(1.0)
+    lib.port_set_reinsert(0)
+    lib.port_set_depth_limit(62)
     if rc != 0:
         raise RuntimeError("%s failed (%d)" % (fn, rc))
     return nodes[:n_nodes.value].copy(), indices

@@ -162,3 +162,17 @@ def test_reference_presplitting_prototype_builds_a_valid_tree_and_is_no_better()
     pn, pi = build_ploc(tris, 8)
     _, _, sah_plain = validate_bvh(pn, pi, tris)
     assert sah_split > 0.95 * sah_plain, (sah_split, sah_plain)
+
+
+def test_restated_depth_limit_fallback():
+    """oracle/bvh_oracle.c mirrors flx_build_bvh's depth rule: an optimised tree past the limit falls back to the plain PLOC tree, a
+    plain one past it is an error."""
+    scene = SceneData.load_blob(scene_blob("conference"))
+    plain = build_ploc(scene.tris)
+    assert validate_bvh(*plain, scene.tris)[0] == 37
+    opt = build_ploc(scene.tris, reinsert=16)
+    assert validate_bvh(*opt, scene.tris)[0] == 38
+    back = build_ploc(scene.tris, reinsert=16, depth_limit=37)
+    assert np.array_equal(back[0].view(np.uint8), plain[0].view(np.uint8)) and np.array_equal(back[1], plain[1])
+    with pytest.raises(RuntimeError, match="failed \\(5\\)"):
+        build_ploc(scene.tris, depth_limit=36)

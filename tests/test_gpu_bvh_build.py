@@ -92,6 +92,30 @@ def test_reinsertion_iterations_match_the_cpu_restatement(iterations):
     same_tree(zero[0], zero[1], base[0], base[1], "0 iterations == FLX_BVH_PLOC")
 
 
+def test_too_deep_optimised_tree_falls_back_to_the_plain_one():
+    """The traversal stack holds 64 entries, so flx_build_bvh hands out no PLOC tree deeper than 62 levels.  Reinsertion can deepen a
+    tree; past the limit the builder returns the PLOC tree it started from.  Reached here by lowering the limit (FLX_TUNE_BVH_DEPTH_LIMIT):
+    Conference is 37 levels deep after PLOC and 38 after the reinsertion pass."""
+    from fluctus_b200 import FluctusError
+    from oracle.oracle_host import build_ploc
+    scene = SceneData.load_blob(scene_blob("conference"))
+    with CLContext(1024) as gpu:
+        plain = gpu.buildBVH(scene.tris, 8, "ploc")
+        assert validate_bvh(plain[0], plain[1], scene.tris)[0] == 37
+        opt = gpu.buildBVH(scene.tris, 8, "ploc_opt")
+        assert validate_bvh(opt[0], opt[1], scene.tris)[0] == 38
+        gpu.setTuning(bvh_depth_limit=37)
+        back = gpu.buildBVH(scene.tris, 8, "ploc_opt")
+        same_tree(back[0], back[1], plain[0], plain[1], "PLOC_OPT past the depth limit == PLOC")
+        cn, ci = build_ploc(scene.tris, 8, reinsert=REINSERT_DEFAULT, depth_limit=37)
+        same_tree(back[0], back[1], cn, ci, "the restatement falls back the same way")
+        gpu.setTuning(bvh_depth_limit=36)
+        with pytest.raises(FluctusError, match="levels deep"):
+            gpu.buildBVH(scene.tris, 8, "ploc_opt")
+        with pytest.raises(FluctusError, match="levels deep"):
+            gpu.buildBVH(scene.tris, 8, "ploc")
+
+
 @pytest.mark.parametrize("quality", QUALITIES)
 @pytest.mark.parametrize("name", ["conference", "country_kitchen"])
 def test_builder_matches_on_reference_assets(name, quality):
