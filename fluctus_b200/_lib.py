@@ -66,6 +66,7 @@ _SIGNATURES = {
     "flx_comm_unique_id": (C.c_int, [_P]),
     "flx_comm_init": (C.c_int, [_P, _P, C.c_int, C.c_int]),
     "flx_gather_pixels": (C.c_int, [_P, C.c_int, _P]),
+    "flx_read_gathered": (C.c_int, [_P, C.c_int, _P, C.c_size_t]),
     "flx_comm_destroy": (C.c_int, [_P]),
     "flx_device_bytes": (C.c_size_t, [_P]),
     "flx_host_alloc": (C.c_int, [C.POINTER(_P), C.c_size_t]),

@@ -360,3 +360,9 @@ class CLContext:
 
     def gatherPixels(self, root=0, out=None):
         self._check(self._lib.flx_gather_pixels(self._h, int(root), self._ptr(out) if out is not None else None), "gatherPixels")
+
+    def readGathered(self, width, height, preview=False):
+        """Root only, after gatherPixels: the gathered full image -- accumulators, or (preview) the display pass over them."""
+        out = np.empty((int(width) * int(height), 4), np.float32)
+        self._check(self._lib.flx_read_gathered(self._h, 1 if preview else 0, self._ptr(out), len(out)), "readGathered")
+        return out

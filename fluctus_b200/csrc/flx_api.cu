@@ -143,6 +143,9 @@ struct flx_ctx
     uint32_t width = 0, height = 0, tilePixels = 0;
     uint32_t part = 0, nParts = 1, stripeRows = 1;
     float *gatherBuf = nullptr, *fullImage = nullptr; // rank-major gather target and de-interleaved full image (root)
+    float *fullPreview = nullptr;                     // display pass of the full image (root; allocated on first use)
+    size_t fullPreviewPixels = 0;
+    int lastGatherRoot = -1;                          // root of the most recent flx_gather_pixels (-1: none yet)
     size_t gatherBufPixels = 0, fullImagePixels = 0;  // capacities, tracked separately (a resize can grow one and not the other)
     // The gather runs on its own stream from a SNAPSHOT of the accumulator (one device-to-device copy on the render stream, a
     // few microseconds), so the render stream goes on splatting into `pixels` while NCCL moves the snapshot: the collective is
@@ -1177,6 +1180,7 @@ void flx_destroy(flx_ctx *c)
     freeDev(c->aovOut);
     freeDev(c->gatherBuf);
     freeDev(c->fullImage);
+    freeDev(c->fullPreview);
     freeDev(c->gatherSnapshot);
     if (c->evSnapshot)
         cudaEventDestroy(c->evSnapshot);
@@ -2697,11 +2701,17 @@ try
     if (rc)
         return rc;
     REQUIRE(filename != nullptr, "flx_save_image: null file name");
-    REQUIRE(ctx->nParts == 1, "flx_save_image: this context renders a tile; gather the full image first (flx_gather_pixels)");
+    const bool tiled = ctx->nParts != 1;
+    REQUIRE(!tiled || (ctx->comm != nullptr && ctx->lastGatherRoot == ctx->rank),
+            "flx_save_image: this context renders a tile; gather the full image first (flx_gather_pixels) and save it on the root");
     const std::string name(filename);
     const bool hdr = name.size() >= 4 && (name.compare(name.size() - 4, 4, ".hdr") == 0 || name.compare(name.size() - 4, 4, ".HDR") == 0);
-    std::vector<float> host((size_t)ctx->tilePixels * 4);
-    rc = hdr ? flx_read_pixels(ctx, host.data(), ctx->tilePixels) : flx_read_preview(ctx, host.data(), ctx->tilePixels);
+    const size_t count = tiled ? (size_t)ctx->width * ctx->height : (size_t)ctx->tilePixels;
+    std::vector<float> host(count * 4);
+    if (tiled) // the root of the last gather writes the gathered frame: accumulators for .hdr, their display pass otherwise
+        rc = flx_read_gathered(ctx, hdr ? 0 : 1, host.data(), count);
+    else
+        rc = hdr ? flx_read_pixels(ctx, host.data(), ctx->tilePixels) : flx_read_preview(ctx, host.data(), ctx->tilePixels);
     if (rc)
         return rc;
     if (flx_write_image(filename, host.data(), ctx->width, ctx->height) != 0)
@@ -3153,6 +3163,7 @@ try
         return rc;
     CU(cudaEventRecord(ctx->evGatherDone, ctx->gatherStream));
     ctx->gatherInFlight = true;
+    ctx->lastGatherRoot = root;
     if (needSnapshot)
     {
         CU(cudaEventRecord(ctx->evSnapshotFree[par], ctx->gatherStream));
@@ -3163,6 +3174,44 @@ try
         CU(cudaMemcpyAsync(full_rgba_host_or_null, ctx->fullImage, fullPixels * 16, cudaMemcpyDeviceToHost, ctx->gatherStream));
         CU(cudaStreamSynchronize(ctx->gatherStream));
     }
+    return 0;
+}
+FLX_API_CATCH(ctx)
+
+// Root only, after flx_gather_pixels: the gathered full image -- the accumulators (preview = 0), or the display pass over them
+// (preview != 0: mk_postprocess.cl:7-55 with the current exposure / tone-map operator, the same kernel a single-GPU context runs
+// over its own image).  On the gather stream, behind the gather it reads.
+int flx_read_gathered(flx_ctx *ctx, int preview, float *rgba, size_t n_pixels)
+try
+{
+    int rc = checkReady(ctx, false, true);
+    if (rc)
+        return rc;
+    REQUIRE(rgba != nullptr, "flx_read_gathered: null destination");
+    REQUIRE(ctx->comm != nullptr && ctx->lastGatherRoot == ctx->rank && ctx->fullImage, "flx_read_gathered: this context was not the root of a gather (flx_gather_pixels)");
+    const size_t fullPixels = (size_t)ctx->width * ctx->height;
+    REQUIRE(n_pixels <= fullPixels && ctx->fullImagePixels >= fullPixels, "flx_read_gathered: more pixels requested than the gathered image holds");
+    CU(cudaSetDevice(ctx->device));
+    const float *src = ctx->fullImage;
+    if (preview)
+    {
+        if (ctx->fullPreviewPixels < fullPixels)
+        {
+            CU(cudaStreamSynchronize(ctx->gatherStream));
+            freeDev(ctx->fullPreview);
+            ctx->fullPreviewPixels = 0;
+            CU(cudaMalloc(&ctx->fullPreview, fullPixels * 16));
+            ctx->fullPreviewPixels = fullPixels;
+        }
+        k_postprocess<<<streamingGrid((uint32_t)fullPixels), FLX_BLOCK, 0, ctx->gatherStream>>>(reinterpret_cast<const float4 *>(ctx->fullImage), reinterpret_cast<float4 *>(ctx->fullPreview),
+                                                                                              nullptr, 1, (uint32_t)fullPixels, ctx->params.ppParams.exposure,
+                                                                                              ctx->params.ppParams.tmOperator);
+        if ((rc = launchCheck(ctx, "k_postprocess<gathered image>")))
+            return rc;
+        src = ctx->fullPreview;
+    }
+    CU(cudaMemcpyAsync(rgba, src, n_pixels * 16, cudaMemcpyDeviceToHost, ctx->gatherStream));
+    CU(cudaStreamSynchronize(ctx->gatherStream));
     return 0;
 }
 FLX_API_CATCH(ctx)

@@ -815,9 +815,12 @@ __global__ void __launch_bounds__(FLX_BLOCK) k_postprocess(const float4 *__restr
     const float white = uc2_curve(W);
     for (uint32_t i = blockIdx.x * FLX_BLOCK + threadIdx.x; i < nPixels; i += gridDim.x * FLX_BLOCK)
     {
-        if (!all && !dirty[i])
-            continue;
-        dirty[i] = 0;
+        if (dirty) // (null: the full image gathered from all ranks, which has no change marks)
+        {
+            if (!all && !dirty[i])
+                continue;
+            dirty[i] = 0;
+        }
         float4 c = pixels[i];
         if (c.w > 0.0f)
         {

@@ -289,6 +289,10 @@ int flx_comm_init(flx_ctx *ctx, const void *unique_id128, int rank, int nranks);
  * stream order), the transfer runs on the library's gather stream beside whatever is enqueued next, and is complete after
  * flx_finish -- or on return when a host destination is given.  Device time per call: flx_get_kernel_ms(FLX_K_GATHER). */
 int flx_gather_pixels(flx_ctx *ctx, int root, float *full_rgba_host_or_null);
+/* Root only, after flx_gather_pixels: the gathered full image read back -- the accumulators (preview = 0) or the display pass over
+ * them (preview != 0: the post-process kernel of the reference, mk_postprocess.cl:7-55, with the current exposure / tone-map
+ * operator).  flx_save_image on the root of a tiled context writes this frame (.hdr: accumulators, otherwise the display pass). */
+int flx_read_gathered(flx_ctx *ctx, int preview, float *rgba, size_t n_pixels);
 int flx_comm_destroy(flx_ctx *ctx);
 
 /* ---- scene input (host code, no device work).  The reference's Scene::loadModel for OBJ + MTL and ASCII PLY

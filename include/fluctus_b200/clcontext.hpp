@@ -155,6 +155,8 @@ class CLContext
     // asynchronous like the enqueue* calls (own stream, device-side snapshot of the frame as of this call); complete after
     // finishQueue(), or on return when a host destination is given
     void gatherPixels(int root, float *fullImageOrNull) { verify(flx_gather_pixels(ctx, root, fullImageOrNull), "gatherPixels"); }
+    // root, after gatherPixels: the gathered frame -- accumulators, or their display pass (what saveImage writes on a tiled context's root)
+    void readGathered(bool preview, float *rgba, size_t numPixels) { verify(flx_read_gathered(ctx, preview ? 1 : 0, rgba, numPixels), "readGathered"); }
     void readPixelsInto(float *rgba, size_t numPixels) { verify(flx_read_pixels(ctx, rgba, numPixels), "readPixels"); } // e.g. into hostAlloc()ed memory
 
     // ---- new: denoiser feature buffers (the reference's Tracer::useDenoiser / -DUSE_OPTIX_DENOISER build, src/kernel_impl.hpp:53)

@@ -42,8 +42,31 @@ def main():
     ctx.gatherPixels(0, full)
     ctx.finishQueue()
     ref_full = fd.gather_host(tile, W, H, S, root=0)
+    # display pass of the gathered frame on the root (flx_read_gathered / saveImage on a tiled context): the same kernel every rank
+    # runs over its own tile, so gathering the ranks' own previews on the host must give the same bits
+    ctx.enqueuePostprocessKernel()
+    ref_preview = fd.gather_host(ctx.readPreview(), W, H, S, root=0)
+    if rank != 0:
+        try:
+            ctx.readGathered(W, H)
+            raise AssertionError("readGathered must refuse on a rank that was not the gather's root")
+        except Exception as e:
+            assert "root" in str(e), e
     if rank == 0:
         assert np.array_equal(full, ref_full), "NCCL gather + de-interleave differs from the host-side gather"
+        assert np.array_equal(ctx.readGathered(W, H), full), "flx_read_gathered(accumulators) differs from the gathered image"
+        prev = ctx.readGathered(W, H, preview=True)
+        assert np.array_equal(prev, ref_preview), "display pass of the gathered image differs from the ranks' own display passes"
+        import tempfile
+        from PIL import Image
+        with tempfile.TemporaryDirectory() as tmp:
+            ctx.saveImage(os.path.join(tmp, "full.png"))
+            got = np.asarray(Image.open(os.path.join(tmp, "full.png")).convert("RGB"))
+            want = (np.float32(255) * np.clip(prev.reshape(H, W, 4)[..., :3], 0.0, 1.0)).astype(np.uint8)[::-1]
+            assert got.shape == (H, W, 3) and np.array_equal(got, want), "saveImage on the root of a tiled context"
+            ctx.saveImage(os.path.join(tmp, "full.hdr"))
+            assert os.path.getsize(os.path.join(tmp, "full.hdr")) > W * H
+        print("GATHERED_IMAGE_OK")
         assert (full[:, 3] > 0).all(), "some pixels of the full image were never sampled"
         # statistical agreement with an untiled render of the same scene (different seed->pixel map, same estimator)
         solo = CLContext(N * world, device=local)

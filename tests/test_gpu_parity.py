@@ -193,7 +193,7 @@ def test_multi_gpu_tiles_and_nccl_gather(direct):
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                         "--master-port", str(29731 + direct), os.path.join(root, "tests", "multi_gpu_check.py")], capture_output=True, text=True, timeout=600,
                        env=dict(os.environ, FLX_GATHER_DIRECT=str(direct)))
-    assert r.returncode == 0 and "MULTI_GPU_OK" in r.stdout and "RESIZE_GATHER_OK 64x16" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+    assert r.returncode == 0 and "MULTI_GPU_OK" in r.stdout and "GATHERED_IMAGE_OK" in r.stdout and "RESIZE_GATHER_OK 64x16" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
 
 
 def test_cpp_wrapper_headless_driver_matches_golden(tmp_path):
