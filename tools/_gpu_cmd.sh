@@ -1,6 +1,7 @@
 #!/bin/bash
 set -x
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -k "multi or gather or two" 2>&1 | tail -8
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 20 --warmup 5 2>gpurun_out/bench2.err | grep '^{' | tail -1 > gpurun_out/bench_r2_2gpu_now.json; python -c "
-import json; d=json.load(open('gpurun_out/bench_r2_2gpu_now.json')); print({k:d[k] for k in ('value','n_gpus','ms_per_step')}, d['e2e']['value'], d.get('gather'))"
+timeout 300 python tools/sanitize.py 2>&1 | tail -3
+timeout 1500 compute-sanitizer --tool memcheck --print-limit 20 python tools/sanitize.py > gpurun_out/r2_san_memcheck.log 2>&1; tail -4 gpurun_out/r2_san_memcheck.log
+timeout 1500 compute-sanitizer --tool initcheck --print-limit 20 python tools/sanitize.py > gpurun_out/r2_san_initcheck.log 2>&1; tail -4 gpurun_out/r2_san_initcheck.log
+timeout 1500 compute-sanitizer --tool racecheck --print-limit 20 python tools/sanitize.py > gpurun_out/r2_san_racecheck.log 2>&1; tail -4 gpurun_out/r2_san_racecheck.log

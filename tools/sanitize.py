@@ -47,7 +47,7 @@ def main():
                 assert np.isfinite(pix).all()
     # the hierarchy builder, incl. the one- and two-triangle cases and a scene rendered through its tree
     with CLContext(1500) as ctx:
-        for quality in ("fast", "ploc"):
+        for quality in ("fast", "ploc", "ploc_opt"):
             for n in (1, 2, len(scene.tris)):
                 nodes, idx, _ = ctx.buildBVH(scene.tris[:n], 8 if n > 2 else 1, quality)
         from fluctus_b200 import SceneData
