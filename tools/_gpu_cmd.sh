@@ -1,7 +1,4 @@
 #!/bin/bash
 set -x
 mkdir -p gpurun_out
-timeout 300 python tools/sanitize.py 2>&1 | tail -3
-timeout 1500 compute-sanitizer --tool memcheck --print-limit 20 python tools/sanitize.py > gpurun_out/r2_san_memcheck.log 2>&1; tail -4 gpurun_out/r2_san_memcheck.log
-timeout 1500 compute-sanitizer --tool initcheck --print-limit 20 python tools/sanitize.py > gpurun_out/r2_san_initcheck.log 2>&1; tail -4 gpurun_out/r2_san_initcheck.log
-timeout 1500 compute-sanitizer --tool racecheck --print-limit 20 python tools/sanitize.py > gpurun_out/r2_san_racecheck.log 2>&1; tail -4 gpurun_out/r2_san_racecheck.log
+timeout 600 ncu --set full --clock-control none -k regex:'k_trace_persistent' -s 24 -c 2 -f -o gpurun_out/r2_plocopt_prof python tools/prof_step.py --builder ploc_opt 2>&1 | tail -3

@@ -19,9 +19,11 @@ def main():
         ref = SceneData.load_blob(os.path.join(ROOT, "oracle", "_ref", "scenes", scene_name + ".bin"))
         row = dict(scene=scene_name)
         with CLContext(N) as ctx:
-            nodes, idx, _ = ctx.buildBVH(ref.tris, 8, "ploc")
-            ploc = SceneData(ref.tris, idx, nodes, ref.materials, ref.tex_desc, ref.tex_data)
-            for label, sc in (("sbvh", ref), ("ploc", ploc), ("sbvh_again", ref)):
+            built = {}
+            for q in ("ploc", "ploc_opt"):
+                nodes, idx, _ = ctx.buildBVH(ref.tris, 8, q)
+                built[q] = SceneData(ref.tris, idx, nodes, ref.materials, ref.tex_desc, ref.tex_data)
+            for label, sc in (("sbvh", ref), ("ploc", built["ploc"]), ("ploc_opt", built["ploc_opt"]), ("sbvh_again", ref)):
                 params = params_for(scene_name, sc, W, H)
                 ctx.uploadSceneData(sc)
                 if scene_name in ENV_MAPS:
@@ -35,11 +37,13 @@ def main():
                 ms = ctx.renderTimed(100)
                 st = ctx.getStats()
                 out = dict(mrays_per_s=round((st.extensionRays + st.shadowRays) / ms / 1e3, 1), ms_per_iteration=round(ms / 100, 4))
+                ctx.setTuning(overlap_trace=0)  # kernels one after the other: per-kernel times that add up
+                ctx.resetStats()
                 ctx.setProfiling(True)
-                ctx.render(20)
-                ctx.finishQueue()
-                out["kernel_ms"] = {k: round(v[0] / v[1], 4) for k, v in ctx.checkTracingPerf().items() if v[1]}
+                ctx.renderTimed(20)
+                out["kernel_ms_serialised"] = {k: round(v[0] / 20, 4) for k, v in ctx.checkTracingPerf().items() if v[1]}
                 ctx.setProfiling(False)
+                ctx.setTuning(overlap_trace=1)
                 ctx.setCounting(True)
                 ctx.render(5)
                 ctx.finishQueue()
