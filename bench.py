@@ -55,7 +55,7 @@ def parse():
     ap.add_argument("--stripe-rows", type=int, default=8)
     ap.add_argument("--min-seconds", type=float, default=0.5, help="repeat the K-step block until this much device time has been measured")
     ap.add_argument("--max-blocks", type=int, default=400)
-    ap.add_argument("--e2e-runs", type=int, default=3)
+    ap.add_argument("--e2e-runs", type=int, default=5)
     ap.add_argument("--cpu-tasks", type=int, default=1 << 16, help="paths in flight of the CPU sample")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

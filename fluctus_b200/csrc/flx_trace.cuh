@@ -80,13 +80,41 @@ FLX_DEV F8 ldg256(const void *p) // 32-byte aligned, read-only path: LDG.E.256, 
     return r;
 }
 
+// The same load with an L1 eviction-priority hint (SASS: LDG.E.EL / .EF / .NA): 1 = evict last, 2 = evict first, 3 = do not allocate in L1.
+// The traversal lives on L1: inner nodes are revisited by every ray and are asked to stay (FLX_HINT_NODE), leaf triangles and
+// hit attributes are touched once per visit and would only push nodes and stack lines out, so they bypass L1 (FLX_HINT_TRI, FLX_HINT_ATTR).
+// Measured with a run-time switch (profiles/r2_cache_hints.txt): extension kernel -2.0 %, shadow kernel -1.7 % on Conference, -0.7 % / -1.3 %
+// on Country Kitchen, -1.7 % / -0.8 % through a PLOC_OPT tree; hints on the nodes alone or on the attributes alone do nothing.
+#define FLX_HINT_NODE 1
+#define FLX_HINT_TRI 3
+#define FLX_HINT_ATTR 3
+template <int HINT> FLX_DEV F8 ldg256_hint(const void *p)
+{
+    F8 r;
+    if (HINT == 1)
+        asm volatile("ld.global.nc.L1::evict_last.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+                     : "l"(p));
+    else if (HINT == 2)
+        asm volatile("ld.global.nc.L1::evict_first.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+                     : "l"(p));
+    else if (HINT == 3)
+        asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+                     : "l"(p));
+    else
+        r = ldg256(p);
+    return r;
+}
+
 // The attributes of a closest hit (bvh.cl:273-278: interpolated, normalised vertex normal; interpolated texture coordinates; material
 // index) from the 64-byte TAttr record of the winning triangle.  The reference interpolates float3 texture coordinates and keeps .xy; z does
 // not reach the result, so it is not stored.
 FLX_DEV void hit_attributes(const BvhView &bvh, int tri, float ub, float vb, V3 &N, float &tu, float &tv, int &matId)
 {
     const float4 *q = bvh.attr + 4 * (size_t)tri;
-    const F8 a = ldg256(q), b = ldg256(q + 2);
+    const F8 a = ldg256_hint<FLX_HINT_ATTR>(q), b = ldg256_hint<FLX_HINT_ATTR>(q + 2);
     N = norm3(bary3(ub, vb, v3(a.v[0], a.v[1], a.v[2]), v3(a.v[3], a.v[4], a.v[5]), v3(a.v[6], a.v[7], b.v[0])));
     const V3 uv = bary3(ub, vb, v3(b.v[1], b.v[2], 0.0f), v3(b.v[3], b.v[4], 0.0f), v3(b.v[5], b.v[6], 0.0f));
     tu = uv.x;

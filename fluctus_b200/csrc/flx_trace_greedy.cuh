@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(FLX_TRACE_BLOCK, MIN_BLOCKS) k_trace_greedy(co
                 {
                     cnt.inner();
                     const float4 *n = bvh.nodes + 4 * (size_t)cur;
-                    const F8 h0 = ldg256(n), h1 = ldg256(n + 2);
+                    const F8 h0 = ldg256_hint<FLX_HINT_NODE>(n), h1 = ldg256_hint<FLX_HINT_NODE>(n + 2);
                     const int cl = __float_as_int(h1.v[4]), cr = __float_as_int(h1.v[5]);
                     float ln, rn;
                     const bool lh = box_test(h0.v[0], h0.v[1], h0.v[2], h0.v[3], h0.v[4], h0.v[5], o, idir, tbest, ln);
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(FLX_TRACE_BLOCK, MIN_BLOCKS) k_trace_greedy(co
             else if (sT)
             {
                 const float4 *p = bvh.tris + 4 * (size_t)(~cur);
-                const F8 h0 = ldg256(p), h1 = ldg256(p + 2);
+                const F8 h0 = ldg256_hint<FLX_HINT_TRI>(p), h1 = ldg256_hint<FLX_HINT_TRI>(p + 2);
                 const int tag = __float_as_int(h0.v[3]);
                 float tt, uu, vv;
                 cnt.tri();

@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_trace_persistent(const __
                 else
                 {
                     const float4 *n = bvh.nodes + 4 * (size_t)cur;
-                    const F8 h0 = ldg256(n), h1 = ldg256(n + 2);
+                    const F8 h0 = ldg256_hint<FLX_HINT_NODE>(n), h1 = ldg256_hint<FLX_HINT_NODE>(n + 2);
                     q0 = make_float4(h0.v[0], h0.v[1], h0.v[2], h0.v[3]);
                     q1 = make_float4(h0.v[4], h0.v[5], h0.v[6], h0.v[7]);
                     q2 = make_float4(h1.v[0], h1.v[1], h1.v[2], h1.v[3]);
@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_trace_persistent(const __
                 int imin = -1;
                 while (true)
                 {
-                    const F8 h0 = ldg256(p), h1 = ldg256(p + 2);
+                    const F8 h0 = ldg256_hint<FLX_HINT_TRI>(p), h1 = ldg256_hint<FLX_HINT_TRI>(p + 2);
                     const int tag = __float_as_int(h0.v[3]);
                     float tt, uu, vv;
                     cnt.tri();
