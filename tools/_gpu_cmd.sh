@@ -1,8 +1,5 @@
 #!/bin/bash
 set -x
 mkdir -p gpurun_out
-C="--variants 1 --thresholds 16 --ext-blocks 9 --shadow-blocks 10 --max-l1 0 --iters 40 --smem-stacks 0"
-timeout 900 python tools/tune_trace.py $C --overlaps 0 --hot-nodes 0,512,1024,2048,4096,8192,1,0 2>/dev/null | python -c "
-import sys,json
-for l in sys.stdin:
-    r=json.loads(l); print('hot',r['hot_nodes'],'ms/iter %.4f Mrays %.1f ext %.4f shadow %.4f'%(r['ms_per_iter'],r['mrays'],r['ext_ms'],r['shadow_ms']))"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_trace_persistent|k_logic' -s 36 -c 3 -f -o gpurun_out/r2_final_prof python tools/prof_step.py 2>&1 | tail -3
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches.csv python tools/prof_step.py --warmup 12 --iters 2 2>&1 | tail -2
