@@ -276,62 +276,73 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_trace_persistent(const __
                     break; // few stragglers and some lane has a leaf to intersect: switch phase (never with nothing to do)
                 if (!atInner)
                     continue;
-                cnt.inner();
-                float4 q0, q1, q2;
-                int4 q3;
-                if (TOP && cur < topCount)
+                // Several node steps per vote: a lane that is still at an inner node after its step takes the next one without asking the
+                // warp again (lanes that reached a leaf meanwhile just wait: the result cannot change, only who idles when).  The two votes
+                // of the loop header were 9 % of all issued instructions at 32 lanes; measured (Conference, kernels alone): closest hit
+                // 0.702 -> 0.670 ms with 2 steps (0.681 with 3), any hit 0.345 -> 0.333 with 2, 0.329 with 3.
+                constexpr int INNER_STEPS = ANYHIT ? 3 : 2;
+#pragma unroll
+                for (int rep = 0; rep < INNER_STEPS; rep++)
                 {
-                    const float4 *n = topNodes + 4 * cur;
-                    q0 = n[0];
-                    q1 = n[1];
-                    q2 = n[2];
-                    q3 = *reinterpret_cast<const int4 *>(n + 3);
-                }
-                else
-                {
-                    const float4 *n = bvh.nodes + 4 * (size_t)cur;
-                    const F8 h0 = ldg256_hint<FLX_HINT_NODE>(n), h1 = ldg256_hint<FLX_HINT_NODE>(n + 2);
-                    q0 = make_float4(h0.v[0], h0.v[1], h0.v[2], h0.v[3]);
-                    q1 = make_float4(h0.v[4], h0.v[5], h0.v[6], h0.v[7]);
-                    q2 = make_float4(h1.v[0], h1.v[1], h1.v[2], h1.v[3]);
-                    q3 = make_int4(__float_as_int(h1.v[4]), __float_as_int(h1.v[5]), 0, 0);
-                }
-                if (bvh.prefetch & 3) // both children's records start their way up while the two box tests run
-                {
-                    const float4 *c0 = q3.x >= 0 ? bvh.nodes + 4 * (size_t)q3.x : bvh.tris + 4 * (size_t)(~q3.x);
-                    const float4 *c1 = q3.y >= 0 ? bvh.nodes + 4 * (size_t)q3.y : bvh.tris + 4 * (size_t)(~q3.y);
-                    if ((bvh.prefetch & 3) == 1)
+                    if (rep > 0 && !(active && cur >= 0))
+                        break;
+                    cnt.inner();
+                    float4 q0, q1, q2;
+                    int4 q3;
+                    if (TOP && cur < topCount)
                     {
-                        asm volatile("prefetch.global.L1 [%0];" ::"l"(c0));
-                        asm volatile("prefetch.global.L1 [%0];" ::"l"(c1));
+                        const float4 *n = topNodes + 4 * cur;
+                        q0 = n[0];
+                        q1 = n[1];
+                        q2 = n[2];
+                        q3 = *reinterpret_cast<const int4 *>(n + 3);
                     }
                     else
                     {
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(c0));
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(c1));
+                        const float4 *n = bvh.nodes + 4 * (size_t)cur;
+                        const F8 h0 = ldg256_hint<FLX_HINT_NODE>(n), h1 = ldg256_hint<FLX_HINT_NODE>(n + 2);
+                        q0 = make_float4(h0.v[0], h0.v[1], h0.v[2], h0.v[3]);
+                        q1 = make_float4(h0.v[4], h0.v[5], h0.v[6], h0.v[7]);
+                        q2 = make_float4(h1.v[0], h1.v[1], h1.v[2], h1.v[3]);
+                        q3 = make_int4(__float_as_int(h1.v[4]), __float_as_int(h1.v[5]), 0, 0);
                     }
-                }
-                float ln, rn;
-                const bool lh = box_test(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, o, idir, tbest, ln);
-                const bool rh = box_test(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, o, idir, tbest, rn);
-                if (lh && rh)
-                {
-                    // right child closer -> first (bvh.cl:292); ties keep left first.  Any-hit rays may visit in any order (the answer
-                    // is order-free): bvh.prefetch bit 2 makes them always take the left child first -- measured, DESIGN.md 4.1
-                    const bool swap = (ANYHIT && (bvh.prefetch & 4)) ? false : rn < ln;
-                    FLX_PUSH(swap ? q3.x : q3.y);
-                    cur = swap ? q3.y : q3.x;
-                }
-                else if (lh)
-                    cur = q3.x;
-                else if (rh)
-                    cur = q3.y;
-                else if (!FLX_STACK_EMPTY)
-                    FLX_POP(cur);
-                else
-                {
-                    active = false;
-                    pending = true;
+                    if (bvh.prefetch & 3) // both children's records start their way up while the two box tests run
+                    {
+                        const float4 *c0 = q3.x >= 0 ? bvh.nodes + 4 * (size_t)q3.x : bvh.tris + 4 * (size_t)(~q3.x);
+                        const float4 *c1 = q3.y >= 0 ? bvh.nodes + 4 * (size_t)q3.y : bvh.tris + 4 * (size_t)(~q3.y);
+                        if ((bvh.prefetch & 3) == 1)
+                        {
+                            asm volatile("prefetch.global.L1 [%0];" ::"l"(c0));
+                            asm volatile("prefetch.global.L1 [%0];" ::"l"(c1));
+                        }
+                        else
+                        {
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(c0));
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(c1));
+                        }
+                    }
+                    float ln, rn;
+                    const bool lh = box_test(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, o, idir, tbest, ln);
+                    const bool rh = box_test(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, o, idir, tbest, rn);
+                    if (lh && rh)
+                    {
+                        // right child closer -> first (bvh.cl:292); ties keep left first.  Any-hit rays may visit in any order (the answer
+                        // is order-free): bvh.prefetch bit 2 makes them always take the left child first -- measured, DESIGN.md 4.1
+                        const bool swap = (ANYHIT && (bvh.prefetch & 4)) ? false : rn < ln;
+                        FLX_PUSH(swap ? q3.x : q3.y);
+                        cur = swap ? q3.y : q3.x;
+                    }
+                    else if (lh)
+                        cur = q3.x;
+                    else if (rh)
+                        cur = q3.y;
+                    else if (!FLX_STACK_EMPTY)
+                        FLX_POP(cur);
+                    else
+                    {
+                        active = false;
+                        pending = true;
+                    }
                 }
             }
             // (2) one leaf
