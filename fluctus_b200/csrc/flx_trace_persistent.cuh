@@ -85,11 +85,14 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_trace_persistent(const __
     const Tasks &t = fr.tasks;
     const bool lightTest = ANYHIT ? (prm.useAreaLight != 0) : (prm.sampleImpl && prm.useAreaLight);
 
-    bool active = false, pending = false, exhausted = false; // pending: ray finished, result not yet written
+    // A lane's state is its node reference: an inner node (0 <= cur < TR_DONE), a leaf (cur < 0), TR_DONE = ray finished and its result not
+    // yet written, TR_IDLE = no ray.  (Separate flags cost a dozen byte-permute instructions per node step: the compiler packs bools.)
+    constexpr int TR_IDLE = 0x7fffffff, TR_DONE = 0x7ffffffe;
+    bool exhausted = false;
     uint32_t gid = 0;
     V3 o = v3(0.0f), d = v3(0.0f), idir = v3(0.0f);
     float tbest = 0.0f, ub = 0.0f, vb = 0.0f;
-    int tri = -1, cur = 0, sp = 0;
+    int tri = -1, cur = TR_IDLE, sp = 0;
     bool occluded = false;
     // Traversal stack: the first SDEPTH levels live in shared memory, laid out [level][thread] so that every lane always
     // hits its own bank whatever its depth (a push/pop is ONE wavefront); deeper levels -- beyond any tree the reference's
@@ -144,9 +147,9 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_trace_persistent(const __
     while (true)
     {
         // ---- write back finished rays (all lanes that finished since the last round do this together)
-        if (pending)
+        if (cur == TR_DONE)
         {
-            pending = false;
+            cur = TR_IDLE;
             raysDone++;
             if (ANYHIT && MODE == TRACE_MK_NEE)
                 mk.scratch.setu_cs(MK_X_BLOCKED0 + (int)(gid & 1u), gid >> 1, occluded ? 1u : 0u);
@@ -185,7 +188,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_trace_persistent(const __
         // ---- idle lanes take the next rays of the queue.  A warp reserves the queue in chunks (one atomic per chunk, not
         //      per refill: every warp of the grid hits the same counter word and same-address atomics serialise in L2)
         //      and hands the chunk out locally; chunks shrink to 32 near the end of the queue to keep the tail balanced.
-        const bool need = !active && !exhausted;
+        const bool need = cur == TR_IDLE && !exhausted;
         const unsigned needMask = __ballot_sync(FULL, need);
         if (needMask)
         {
@@ -241,15 +244,13 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_trace_persistent(const __
                     cur = bvh.rootRef;
                     sp = 0;
                     topReg = NO_ENTRY;
-                    active = true;
                     if (quadFirst)
                     {
                         float tl = tbest;
                         if (light_quad(prm.areaLight, o, d, tl))
                         {
                             occluded = true;
-                            active = false;
-                            pending = true;
+                            cur = TR_DONE;
                         }
                     }
                 }
@@ -258,7 +259,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_trace_persistent(const __
             }
         }
         const bool drain = __any_sync(FULL, exhausted); // nothing left to fetch: run the remaining rays to the end
-        if (__ballot_sync(FULL, active || pending) == 0u && (MODE != TRACE_MK_NEXT || drain))
+        if (__ballot_sync(FULL, cur != TR_IDLE) == 0u && (MODE != TRACE_MK_NEXT || drain))
             break; // queue drained and every lane idle (TRACE_MK_NEXT: a round may draw only paths in other phases)
 
         // ---- traverse until too few lanes hold a ray
@@ -268,11 +269,11 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_trace_persistent(const __
             //     (innerMin = 1: until every lane has reached a leaf or finished its ray)
             while (true)
             {
-                const bool atInner = active && cur >= 0;
+                const bool atInner = (unsigned)cur < (unsigned)TR_DONE;
                 const unsigned innerMask = __ballot_sync(FULL, atInner);
                 if (innerMask == 0u)
                     break;
-                if (__popc(innerMask) < innerMin && __ballot_sync(FULL, active && cur < 0) != 0u)
+                if (__popc(innerMask) < innerMin && __ballot_sync(FULL, cur < 0) != 0u)
                     break; // few stragglers and some lane has a leaf to intersect: switch phase (never with nothing to do)
                 if (!atInner)
                     continue;
@@ -284,7 +285,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_trace_persistent(const __
 #pragma unroll
                 for (int rep = 0; rep < INNER_STEPS; rep++)
                 {
-                    if (rep > 0 && !(active && cur >= 0))
+                    if (rep > 0 && !((unsigned)cur < (unsigned)TR_DONE))
                         break;
                     cnt.inner();
                     float4 q0, q1, q2;
@@ -340,13 +341,12 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_trace_persistent(const __
                         FLX_POP(cur);
                     else
                     {
-                        active = false;
-                        pending = true;
+                        cur = TR_DONE;
                     }
                 }
             }
             // (2) one leaf
-            if (active && cur < 0)
+            if (cur < 0)
             {
                 cnt.leaf();
                 const float4 *p = bvh.tris + 4 * (size_t)(~cur);
@@ -390,13 +390,12 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_trace_persistent(const __
                 }
                 if ((ANYHIT && occluded) || FLX_STACK_EMPTY)
                 {
-                    active = false;
-                    pending = true;
+                    cur = TR_DONE;
                 }
                 else
                     FLX_POP(cur);
             }
-            const unsigned still = __ballot_sync(FULL, active);
+            const unsigned still = __ballot_sync(FULL, (unsigned)(cur - TR_DONE) > 1u); // lanes with a ray under way
             if (still == 0u)
                 break;
             if (!drain && __popc(still) < threshold)
