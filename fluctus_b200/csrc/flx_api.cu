@@ -177,7 +177,6 @@ struct flx_ctx
     int bvhDepthLimit = 62;         // deepest PLOC tree flx_build_bvh hands out (tests lower it to reach the fallback)
     int bvhReinsertIterations = 16; // flx_build_bvh, FLX_BVH_PLOC_OPT: iterations of the parallel-reinsertion post-pass
     int bvhTriCostPercent = 100; // flx_build_bvh: SAH cost of a triangle test relative to a box test, in percent (reference constants: 100)
-    int shadowLeftFirst = 0;  // any-hit traversal takes the left child first instead of the nearer one (order-free result)
     int logicTile = 256;      // paths per tile (= threads per CTA) of the logic kernel: 256 or 128
     int gatherDirect = 0;     // flx_gather_pixels: 1 = receive every stripe straight into its rows of the full image; 0 (default) = rank-major
                               // buffer + de-interleave.  Measured (C5 on 2 GPUs, profiles/r2_gather_direct_2gpu.txt): NCCL's cost per point-to-point
@@ -192,7 +191,6 @@ struct flx_ctx
     int fetchChunk = 32;     // queue entries a warp reserves per atomic
     int repackOnHost = 0;     // flx_upload_scene: build the traversal layout with the host code instead of the device kernels (checker)
     int l2Persist = 0;        // 0 off; 1 / 2: persisting-L2 access window over the TTri / TNode array on the two traversal streams
-    int prefetchChildren = 0; // persistent kernels: prefetch both children of an inner node (1: L1, 2: L2) while its box tests run
     int logicMinBlocks = 3;   // resident 256-thread CTAs per SM the logic kernel is compiled for (register budget)
     int fuseStages = 1;       // flx_render: logic + raygen + materials as one kernel
     int fusedMinBlocks = 3;   // register budget of that kernel (1..4 resident CTAs of 256 per SM; 3 measured best)
@@ -309,7 +307,6 @@ BvhView makeBvh(const flx_ctx *c)
     b.tris = c->ttris;
     b.attr = c->tattr;
     b.rootRef = c->rootRef;
-    b.prefetch = c->prefetchChildren | (c->shadowLeftFirst ? 4 : 0);
     return b;
 }
 
@@ -2484,7 +2481,9 @@ try
         ctx->bvhReinsertIterations = value;
         return 0;
     case FLX_TUNE_SHADOW_LEFT_FIRST:
-        ctx->shadowLeftFirst = value != 0;
+    case FLX_TUNE_PREFETCH_CHILDREN:
+        // measured slower in rounds 1 / 2 (profiles/r2_knob_sweep.txt) and removed from the traversal loop, where even a skipped branch costs
+        REQUIRE(value == 0, "flx_set_tuning: this experiment was measured, rejected and removed (DESIGN.md 4.1); only 0 is accepted");
         return 0;
     case FLX_TUNE_LOGIC_TILE:
         REQUIRE(value == 128 || value == 256, "flx_set_tuning: logic tile must be 128 or 256");
@@ -2549,10 +2548,6 @@ try
         return applyL2Persist(ctx);
     case FLX_TUNE_REPACK_ON_HOST:
         ctx->repackOnHost = value != 0;
-        return 0;
-    case FLX_TUNE_PREFETCH_CHILDREN:
-        REQUIRE(value >= 0 && value <= 2, "flx_set_tuning: prefetch mode must be 0, 1 or 2");
-        ctx->prefetchChildren = value;
         return 0;
     case FLX_TUNE_FUSE_STAGES:
         ctx->fuseStages = value != 0;

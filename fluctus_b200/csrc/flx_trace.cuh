@@ -64,7 +64,6 @@ struct BvhView
                          // three texture coordinates and the material index (n0.xyz n1.x | n1.yz n2.xy | n2.z t0.xy t1.x | t1.y t2.xy matId) --
                          // in 64 bytes = two 256-bit loads instead of seven 128-bit loads scattered over the 160-byte triangle
     int rootRef;
-    int prefetch;        // persistent kernels: 0 off, 1 prefetch both children into L1 as soon as their references are known, 2 into L2
 };
 
 struct F8

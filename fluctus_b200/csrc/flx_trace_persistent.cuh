@@ -307,29 +307,15 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_trace_persistent(const __
                         q2 = make_float4(h1.v[0], h1.v[1], h1.v[2], h1.v[3]);
                         q3 = make_int4(__float_as_int(h1.v[4]), __float_as_int(h1.v[5]), 0, 0);
                     }
-                    if (bvh.prefetch & 3) // both children's records start their way up while the two box tests run
-                    {
-                        const float4 *c0 = q3.x >= 0 ? bvh.nodes + 4 * (size_t)q3.x : bvh.tris + 4 * (size_t)(~q3.x);
-                        const float4 *c1 = q3.y >= 0 ? bvh.nodes + 4 * (size_t)q3.y : bvh.tris + 4 * (size_t)(~q3.y);
-                        if ((bvh.prefetch & 3) == 1)
-                        {
-                            asm volatile("prefetch.global.L1 [%0];" ::"l"(c0));
-                            asm volatile("prefetch.global.L1 [%0];" ::"l"(c1));
-                        }
-                        else
-                        {
-                            asm volatile("prefetch.global.L2 [%0];" ::"l"(c0));
-                            asm volatile("prefetch.global.L2 [%0];" ::"l"(c1));
-                        }
-                    }
                     float ln, rn;
                     const bool lh = box_test(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, o, idir, tbest, ln);
                     const bool rh = box_test(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, o, idir, tbest, rn);
                     if (lh && rh)
                     {
-                        // right child closer -> first (bvh.cl:292); ties keep left first.  Any-hit rays may visit in any order (the answer
-                        // is order-free): bvh.prefetch bit 2 makes them always take the left child first -- measured, DESIGN.md 4.1
-                        const bool swap = (ANYHIT && (bvh.prefetch & 4)) ? false : rn < ln;
+                        // right child closer -> first (bvh.cl:292); ties keep left first.  (Any-hit rays could visit in any order; always
+                        // taking the left child first was measured slower, 0.344 -> 0.364 ms: near-first finds occluders sooner.  So was
+                        // prefetching both children while the box tests run.  Both knobs are gone from this loop: profiles/r2_knob_sweep.txt.)
+                        const bool swap = rn < ln;
                         FLX_PUSH(swap ? q3.x : q3.y);
                         cur = swap ? q3.y : q3.x;
                     }

@@ -205,7 +205,7 @@ enum { FLX_TUNE_TRACE_VARIANT = 0,      /* 0: one ray per thread; 1 (default): p
        FLX_TUNE_BVH_DEPTH_LIMIT = 28,   /* flx_build_bvh: deepest PLOC tree handed out, 1..62 (default 62: the traversal stack holds 64 entries).  A PLOC_OPT tree
                                            beyond it falls back to the PLOC tree it started from; a PLOC tree beyond it is an error */
        FLX_TUNE_BVH_REINSERT = 26,      /* flx_build_bvh(FLX_BVH_PLOC_OPT): iterations of the reinsertion post-pass, 0..64 (default 16) */
-       FLX_TUNE_SHADOW_LEFT_FIRST = 25, /* any-hit (shadow) traversal visits the left child first instead of the nearer one; the result is order-free (default 0) */
+       FLX_TUNE_SHADOW_LEFT_FIRST = 25, /* (removed: any-hit traversal taking the left child first was measured slower; only 0 is accepted) */
        FLX_TUNE_LOGIC_TILE = 24,        /* paths per tile (= threads per CTA) of the logic kernel: 256 (default) or 128 */
        FLX_TUNE_GATHER_DIRECT = 23,     /* flx_gather_pixels: 0 (default) one send / receive per rank into a rank-major buffer + a de-interleave pass; 1 one per
                                            stripe, straight into the rows of the root's full image (measured 3-4x slower: NCCL's per-operation cost); must
@@ -229,7 +229,7 @@ enum { FLX_TUNE_TRACE_VARIANT = 0,      /* 0: one ray per thread; 1 (default): p
        FLX_TUNE_OVERLAP_POSTPROCESS = 17, /* display pass beside the traversal stages on a third stream: 0 never, 1 (default) in the per-stage ABI
                                              (flx_enqueue_postprocess starts from the accumulator's last writer), 2 also inside flx_render */
        FLX_TUNE_REPACK_ON_HOST = 16,    /* flx_upload_scene: make the traversal layout with the host code instead of the device kernels (default 0) */
-       FLX_TUNE_PREFETCH_CHILDREN = 15, /* persistent traversal: prefetch both children of an inner node while its box tests run (0 off, 1 L1, 2 L2) */
+       FLX_TUNE_PREFETCH_CHILDREN = 15, /* (removed: prefetching both children of an inner node was measured slower; only 0 is accepted) */
        FLX_TUNE_FUSE_STAGES = 13,       /* flx_render: logic + raygen + materials as ONE kernel over the path state (default 1) */
        FLX_TUNE_FUSED_MIN_BLOCKS = 14,  /* register budget of that kernel: compiled for 1..4 resident CTAs of 256 per SM (default 3) */
        FLX_TUNE_INNER_MIN = 4           /* leave the inner-node phase when fewer lanes than this are still at inner nodes (default 8) */ };

@@ -91,7 +91,7 @@ def main():
         ctx.render(1)
         ctx.loadCheckpoint(ck)
         ctx.render(1)
-        ctx.setTuning(logic_tile=128, shadow_left_first=1)
+        ctx.setTuning(logic_tile=128)
         cam = look_at((0.0, 1.0, 0.95), (0.0, 0.9, -0.2), fov=70.0, aperture=0.02, focal_dist=1.2)
         p2 = make_params(40, 24, cam, scene.world_radius, n_tris=len(scene.tris), max_bounces=3)
         tr = Tracer(ctx, p2)
