@@ -6,7 +6,7 @@ import os
 from .structs import QueueCounters, RenderParams, RenderStats64
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfluctus_b200.so")
+LIB_PATH = os.environ.get("FLX_LIB_PATH") or os.path.join(_HERE, "libfluctus_b200.so")  # FLX_LIB_PATH: an experiment build (csrc/build.py)
 
 _P = C.c_void_p
 _SIGNATURES = {

@@ -80,13 +80,20 @@ FLX_DEV F8 ldg256(const void *p) // 32-byte aligned, read-only path: LDG.E.256, 
 }
 
 // The same load with an L1 eviction-priority hint (SASS: LDG.E.EL / .EF / .NA): 1 = evict last, 2 = evict first, 3 = do not allocate in L1.
-// The traversal lives on L1: inner nodes are revisited by every ray and are asked to stay (FLX_HINT_NODE), leaf triangles and
-// hit attributes are touched once per visit and would only push nodes and stack lines out, so they bypass L1 (FLX_HINT_TRI, FLX_HINT_ATTR).
-// Measured with a run-time switch (profiles/r2_cache_hints.txt): extension kernel -2.0 %, shadow kernel -1.7 % on Conference, -0.7 % / -1.3 %
-// on Country Kitchen, -1.7 % / -0.8 % through a PLOC_OPT tree; hints on the nodes alone or on the attributes alone do nothing.
+// The traversal lives on L1: inner nodes are revisited by every ray and are asked to stay (FLX_HINT_NODE = evict last); leaf
+// triangles are touched once per visit and would push nodes and stack lines out, so they are the first to go (FLX_HINT_TRI = evict first);
+// hit attributes are read once per ray and bypass L1 (FLX_HINT_ATTR = no allocation).  Measured (profiles/r2_cache_hints.txt): with the
+// triangles evict-first Conference 2984 -> 3018, Country Kitchen 3018 -> 3025, Luxball 3638 -> 3634 Mrays/s.  Triangles WITHOUT allocation are
+// another 0.8 % on Conference but cost 15 % on Luxball (3090 Mrays/s), whose coherent rays re-read a leaf's triangles from L1 -- not taken.
+#ifndef FLX_HINT_NODE
 #define FLX_HINT_NODE 1
-#define FLX_HINT_TRI 3
+#endif
+#ifndef FLX_HINT_TRI
+#define FLX_HINT_TRI 2
+#endif
+#ifndef FLX_HINT_ATTR
 #define FLX_HINT_ATTR 3
+#endif
 template <int HINT> FLX_DEV F8 ldg256_hint(const void *p)
 {
     F8 r;
