@@ -59,6 +59,8 @@ struct Tasks
     FLX_DEV uint32_t *at(int slot, uint32_t g) const
     {
         char *p = reinterpret_cast<char *>(base) + (size_t)g * 4u;
+        asm("" : "+l"(p)); // opaque to the optimiser: otherwise it re-associates to (n * 4s + 4g) + base = IMAD.WIDE + IADD3 + IADD3.X per access
+        __builtin_assume(__isGlobal(p)); // (the empty asm hides where the pointer came from; without this the accesses become generic LD / ST)
         return reinterpret_cast<uint32_t *>(p + (size_t)n * (uint32_t)(slot * 4));
     }
     FLX_DEV uint32_t &u(int slot, uint32_t g) const { return *at(slot, g); }
