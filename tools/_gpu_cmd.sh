@@ -1,17 +1,9 @@
 #!/bin/bash
-set -x
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-timeout 600 python bench.py --gpus 1 --steps 20 --warmup 5 2>/dev/null | grep '^{' | tail -1 > gpurun_out/bench_r2_now.json; python -c "
-import json; d=json.load(open('gpurun_out/bench_r2_now.json')); print({k:d[k] for k in ('value','ms_per_step')}, d['e2e']['value'], d['e2e']['runs'], d['roofline']['avg_launch_ms'], d['roofline']['frac'])"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_trace_persistent|k_logic' -s 36 -c 3 -f -o gpurun_out/r2_final_prof python tools/prof_step.py 2>&1 | tail -2
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches.csv python tools/prof_step.py --warmup 12 --iters 2 2>&1 | tail -1
-timeout 300 python tools/run_configs.py > gpurun_out/r2_configs_single_gpu.jsonl 2>/dev/null; python -c "
+timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus 8 --steps 20 --warmup 5 2>gpurun_out/bench8.err | grep '^{' | tail -1 > gpurun_out/bench_r2_8gpu_now.json
+timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29542 bench.py --gpus 8 --steps 20 --warmup 5 --config c5 2>gpurun_out/bench8c5.err | grep '^{' | tail -1 > gpurun_out/bench_r2_c5_8gpu_now.json
+python -c "
 import json
-for l in open('gpurun_out/r2_configs_single_gpu.jsonl'):
-    r=json.loads(l); print(r['config'], r['mrays_per_s'], r['ms_per_iteration'])"
-timeout 300 python tools/bench_mk.py > gpurun_out/r2_mk_integrator.jsonl 2>/dev/null; python -c "
-import json
-for l in open('gpurun_out/r2_mk_integrator.jsonl'):
-    r=json.loads(l); print(r.get('integrator'), r['scene'], r['mrays_per_s'])"
-timeout 300 python __graft_entry__.py --smoke 2>&1 | tail -2
+for f in ('gpurun_out/bench_r2_8gpu_now.json','gpurun_out/bench_r2_c5_8gpu_now.json'):
+    d=json.load(open(f)); print(f, {k:d[k] for k in ('value','n_gpus','ms_per_step')}, 'e2e', d['e2e']['value'], {k:(v['value'],v['gather_ms_per_call']) for k,v in d['gather'].items() if isinstance(v,dict)})"
+tail -2 gpurun_out/bench8.err
