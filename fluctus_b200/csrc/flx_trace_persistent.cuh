@@ -281,11 +281,13 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_trace_persistent(const __
                 // warp again (lanes that reached a leaf meanwhile just wait: the result cannot change, only who idles when).  The two votes
                 // of the loop header were 9 % of all issued instructions at 32 lanes; measured (Conference, kernels alone): closest hit
                 // 0.702 -> 0.670 ms with 2 steps (0.681 with 3), any hit 0.345 -> 0.333 with 2, 0.329 with 3.
-#ifdef FLX_INNER_STEPS
-                constexpr int INNER_STEPS = FLX_INNER_STEPS;
-#else
-                constexpr int INNER_STEPS = ANYHIT ? 3 : 2;
+#ifndef FLX_INNER_STEPS_CLOSEST
+#define FLX_INNER_STEPS_CLOSEST 2
 #endif
+#ifndef FLX_INNER_STEPS_ANY
+#define FLX_INNER_STEPS_ANY 3
+#endif
+                constexpr int INNER_STEPS = ANYHIT ? FLX_INNER_STEPS_ANY : FLX_INNER_STEPS_CLOSEST;
 #pragma unroll
                 for (int rep = 0; rep < INNER_STEPS; rep++)
                 {
