@@ -980,6 +980,7 @@ static void preloadKernels()
     PRELOAD((k_logic<false, 3, 2>));
     PRELOAD((k_logic<false, 3, 2, FLX_LOGIC_TILE, FLX_BXDF_DIFFUSE>));
     PRELOAD((k_logic<true, 3, 1>));
+    PRELOAD((k_logic<true, 3, 2, FLX_LOGIC_TILE, FLX_CHEAP_BXDF>));
     PRELOAD((k_logic<false, 3, 0>));
     PRELOAD((k_logic<true, 3, 0>));
     constexpr int ALL = FLX_BXDF_DIFFUSE | FLX_BXDF_GLOSSY | FLX_BXDF_GGX_ROUGH_REFLECTION | FLX_BXDF_IDEAL_REFLECTION | FLX_BXDF_GGX_ROUGH_DIELECTRIC |
@@ -1861,6 +1862,7 @@ static int launchLogic(flx_ctx *ctx, int first_iteration, bool fused)
     const Frame fr = makeFrame(ctx);
     const SceneView sc = makeScene(ctx);
     const bool sep = ctx->params.wfSeparateQueues != 0;
+    bool sepCheap = false;
     if (fused)
     {
         // single material queue: logic + raygen + materials in one kernel; per-type queues: logic + raygen here, then the per-type
@@ -1870,10 +1872,16 @@ static int launchLogic(flx_ctx *ctx, int first_iteration, bool fused)
             // the lobes compiled into the material part follow the scene's materials, as the reference's kernel build does
             // (src/kernel_impl.hpp:261-266); FLX_TUNE_MATERIAL_MASK = 0 forces the all-lobes instantiation
             const bool diffuseOnly = ctx->useMaterialMask && ctx->materialTypes == (uint32_t)FLX_BXDF_DIFFUSE;
+            // per-type queues exist so that a warp of the material kernels sees ONE heavy BSDF; when every lobe the scene uses is a cheap one
+            // (diffuse, the two ideal ones -- Luxball) there is nothing to keep apart, and the material part is fused here as well: the
+            // queues are still filled, only nobody needs to read them (same state, queues and counters; the material kernels are skipped)
+            sepCheap = sep && ctx->useMaterialMask && ctx->materialTypes != 0u && (ctx->materialTypes & ~(uint32_t)FLX_CHEAP_BXDF) == 0u && LT == 256;
 #define FUSEDK(MB)                                                                                                                                             \
     do                                                                                                                                                         \
     {                                                                                                                                                          \
-        if (sep)                                                                                                                                               \
+        if (sepCheap)                                                                                                                                          \
+            k_logic<true, MB, 2, FLX_LOGIC_TILE, FLX_CHEAP_BXDF><<<tiles, FLX_BLOCK, 0, ctx->stream>>>(fr, ctx->params, sc, scan, maxId);                      \
+        else if (sep)                                                                                                                                          \
             k_logic<true, MB, 1><<<tiles, FLX_BLOCK, 0, ctx->stream>>>(fr, ctx->params, sc, scan, maxId);                                                      \
         else if (diffuseOnly)                                                                                                                                  \
             k_logic<false, MB, 2, FLX_LOGIC_TILE, FLX_BXDF_DIFFUSE><<<tiles, FLX_BLOCK, 0, ctx->stream>>>(fr, ctx->params, sc, scan, maxId);                   \
@@ -1899,7 +1907,7 @@ static int launchLogic(flx_ctx *ctx, int first_iteration, bool fused)
         }
         markPixelsWritten(ctx);
         int rc = launchCheck(ctx, "k_logic<fused>");
-        if (rc == 0 && sep)
+        if (rc == 0 && sep && !sepCheap)
             rc = launchMaterials(ctx);
         return rc;
     }

@@ -374,6 +374,7 @@ __device__ __noinline__ void denoiser_aov_wf(const Frame &fr, const flx_RenderPa
 // scene's materials use ("Only handle material types that exist in scene", src/kernel_impl.hpp:261-266, getBxdfDefines in
 // src/utils.cpp:93-113); here the host picks the instantiation from the uploaded materials' types: all lobes, or diffuse only (Conference).
 #define FLX_ALL_BXDF (FLX_BXDF_DIFFUSE | FLX_BXDF_GLOSSY | FLX_BXDF_GGX_ROUGH_REFLECTION | FLX_BXDF_IDEAL_REFLECTION | FLX_BXDF_GGX_ROUGH_DIELECTRIC | FLX_BXDF_IDEAL_DIELECTRIC | FLX_BXDF_EMISSIVE)
+#define FLX_CHEAP_BXDF (FLX_BXDF_DIFFUSE | FLX_BXDF_IDEAL_REFLECTION | FLX_BXDF_IDEAL_DIELECTRIC) // lobes without GGX / glossy machinery
 template <bool SEPARATE_QUEUES, int MIN_BLOCKS, int FUSE = 0, int LT = FLX_LOGIC_TILE, int MATMASK = FLX_ALL_BXDF>
 __global__ void __launch_bounds__(LT, MIN_BLOCKS) k_logic(const __grid_constant__ Frame fr, const __grid_constant__ flx_RenderParams prm, const SceneView sc,
                                                      const ScanState scan, const uint32_t maxId)

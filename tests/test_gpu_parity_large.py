@@ -112,3 +112,35 @@ def test_luxball_c4_320x180_40_iterations():
     params = luxball_params(scene, W, H)
     with CLContext(W * H) as gpu:
         run_lockstep(gpu, oracle_ctx(W * H), scene, params, iterations=40, check_every=10)
+
+
+def test_luxball_c4_fused_render_matches_oracle():
+    """C4 through flx_render: Luxball's materials use only the cheap lobes (diffuse, ideal dielectric), so although the configuration has
+    per-type material queues the material part is fused into the logic kernel (flx_api.cu, `sepCheap`) and the material kernels are skipped.
+    State, queue counters and accumulator after 24 iterations == the oracle's, which runs the reference's separate kernels."""
+    from parity_util import compare_pixels, compare_tasks, setup_context
+    scene = SceneData.load_blob(scene_blob("luxball"))
+    from bench_configs import luxball_params
+    W, H = 320, 180
+    params = luxball_params(scene, W, H)
+    assert params.wfSeparateQueues
+    cpu = oracle_ctx(W * H)
+    with CLContext(W * H) as gpu:
+        tg, tc = setup_context(gpu, scene, params), setup_context(cpu, scene, params)
+        tg.start()
+        tc.start()
+        gpu.resetStats()
+        tg.render(24)
+        for _ in range(24):
+            tc.iterate()
+        compare_tasks(gpu.readTasks(), cpu.readTasks(), "flx_render(24) on Luxball, per-type queues, fused material part")
+        compare_pixels(gpu.readPixels(), cpu.readPixels(), "flx_render(24) on Luxball", rtol=1e-5)
+        st = gpu.getStats()
+        assert (st.extensionRays, st.shadowRays, st.primaryRays) == (tc.stats["extensionRays"], tc.stats["shadowRays"], tc.stats["primaryRays"])
+        # and the same frame with the fusion switched off (separate material kernels)
+        with CLContext(W * H) as plain:
+            plain.setTuning(material_mask=0)
+            tp = setup_context(plain, scene, params)
+            tp.start()
+            tp.render(24)
+            compare_tasks(gpu.readTasks(), plain.readTasks(), "fused material part vs separate material kernels")
