@@ -654,7 +654,8 @@ __global__ void __launch_bounds__(LT, MIN_BLOCKS) k_logic(const __grid_constant_
                 myMask = m;
         }
         // FUSED: every path that was regenerated or sent through its material is an extension ray of this iteration
-        const bool pushExt = FUSE >= 1 && live && (terminate || (FUSE == 2 && q > 0));
+        // (fused material part with per-type queues: only the lobes compiled in are done here, the others stay with their queue's kernel)
+        const bool pushExt = FUSE >= 1 && live && (terminate || (FUSE == 2 && q > 0 && (!SEPARATE_QUEUES || (matType & MATMASK) != 0)));
         const unsigned extMask = FUSE >= 1 ? __ballot_sync(0xffffffffu, pushExt) : 0u;
         if (FUSE >= 1 && lane == 0)
             s_cnt[NQ][warp] = __popc(extMask);
@@ -730,7 +731,7 @@ __global__ void __launch_bounds__(LT, MIN_BLOCKS) k_logic(const __grid_constant_
         if (SEPARATE_QUEUES) // a type without a queue is dropped, as in the reference (wf_logic.cl:362-364)
             hasQueue = matType == FLX_BXDF_DIFFUSE || matType == FLX_BXDF_GLOSSY || matType == FLX_BXDF_GGX_ROUGH_REFLECTION || matType == FLX_BXDF_GGX_ROUGH_DIELECTRIC ||
                        matType == FLX_BXDF_IDEAL_REFLECTION || matType == FLX_BXDF_IDEAL_DIELECTRIC;
-        if (hasQueue)
+        if (hasQueue && (!SEPARATE_QUEUES || (matType & MATMASK) != 0))
         {
             const V3 L = fHaveL ? fL : t.v(FLX_S_SHADOW_DIR, gid); // no new light sample: whatever an earlier vertex left in the slot
             material_path<MATMASK>(t, sc, gid, fS, fMat, fBackface, rayDir, L, T, seed);

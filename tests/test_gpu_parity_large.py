@@ -144,3 +144,35 @@ def test_luxball_c4_fused_render_matches_oracle():
             tp.start()
             tp.render(24)
             compare_tasks(gpu.readTasks(), plain.readTasks(), "fused material part vs separate material kernels")
+
+
+def test_country_kitchen_c3_fused_render_matches_oracle():
+    """C3 through flx_render (the loop bench.py times) with per-type queues: fused logic + raygen kernel, then the five material kernels;
+    the state after 16 iterations == the oracle's.  (Fusing the cheap lobes' material part into the logic kernel as on Luxball was built,
+    passed this test, and was measured slower on this scene -- flx_api.cu, `sepCheap`.)"""
+    import os
+    from fluctus_b200 import EnvMapData
+    from conftest import SCENES_DIR
+    from parity_util import compare_pixels, compare_tasks, setup_context
+    scene = SceneData.load_blob(scene_blob("country_kitchen"))
+    envp = os.path.join(SCENES_DIR, "night.env.bin")
+    if not os.path.exists(envp):
+        pytest.skip("env map blob missing")
+    env = EnvMapData.load_blob(envp)
+    from bench_configs import kitchen_params
+    W, H = 320, 180
+    params = kitchen_params(scene, W, H)
+    assert params.wfSeparateQueues
+    cpu = oracle_ctx(W * H)
+    with CLContext(W * H) as gpu:
+        tg, tc = setup_context(gpu, scene, params, env=env), setup_context(cpu, scene, params, env=env)
+        tg.start()
+        tc.start()
+        gpu.resetStats()
+        tg.render(16)
+        for _ in range(16):
+            tc.iterate()
+        compare_tasks(gpu.readTasks(), cpu.readTasks(), "flx_render(16) on Country Kitchen")
+        compare_pixels(gpu.readPixels(), cpu.readPixels(), "flx_render(16) on Country Kitchen", rtol=1e-5)
+        st = gpu.getStats()
+        assert (st.extensionRays, st.shadowRays, st.primaryRays) == (tc.stats["extensionRays"], tc.stats["shadowRays"], tc.stats["primaryRays"])
