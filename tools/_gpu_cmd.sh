@@ -1,7 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-timeout 300 python tools/run_configs.py > gpurun_out/r2_configs_single_gpu.jsonl 2>/dev/null; python -c "
-import json
-for l in open('gpurun_out/r2_configs_single_gpu.jsonl'):
-    r=json.loads(l); print(r['config'], r['mrays_per_s'], r['ms_per_iteration'])"
+timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -k "multi or gather or two" 2>&1 | tail -3
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 20 --warmup 5 2>gpurun_out/bench2.err | grep '^{' | tail -1 > gpurun_out/bench_r2_2gpu_now.json; python -c "
+import json; d=json.load(open('gpurun_out/bench_r2_2gpu_now.json')); print({k:d[k] for k in ('value','n_gpus','ms_per_step')}, d['e2e']['value'], {k:(v['value'],v['gather_ms_per_call']) for k,v in d['gather'].items() if isinstance(v,dict)})"
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29534 bench.py --gpus 2 --steps 2 --warmup 1 --impl reference 2>/dev/null | grep '^{' | tail -1 | cut -c1-300
