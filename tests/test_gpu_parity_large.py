@@ -51,7 +51,7 @@ def test_conference_c2_1280x720_65536_paths():
 
 
 def test_conference_metric_size_lockstep():
-    """The metric row itself: 1920x1080, N = 2^21 paths in flight, prologue + 3 iterations in lockstep with the oracle --
+    """The metric row itself: 1920x1080, N = 2^21 paths in flight, prologue + 6 iterations in lockstep with the oracle --
     2 M-entry extension queue, ~1.4 M-entry shadow queue, 8192 logic tiles.  Complete path state bit for bit, queue
     membership, raygen order, counters, accumulator."""
     scene = SceneData.load_blob(scene_blob("conference"))
@@ -59,8 +59,8 @@ def test_conference_metric_size_lockstep():
     W, H, N = 1920, 1080, 1 << 21
     params = conference_params(scene, W, H)
     with CLContext(N) as gpu:
-        tg, tc = run_lockstep(gpu, oracle_ctx(N), scene, params, iterations=3)
-        assert tg.stats == tc.stats and tg.stats["extensionRays"] == 3 * N
+        tg, tc = run_lockstep(gpu, oracle_ctx(N), scene, params, iterations=6, check_every=2)
+        assert tg.stats == tc.stats and tg.stats["extensionRays"] == 6 * N
 
 
 def test_conference_metric_size_fused_render_matches_oracle():

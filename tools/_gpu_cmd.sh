@@ -1,6 +1,24 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -k "multi or gather or two" 2>&1 | tail -3
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 20 --warmup 5 2>gpurun_out/bench2.err | grep '^{' | tail -1 > gpurun_out/bench_r2_2gpu_now.json; python -c "
-import json; d=json.load(open('gpurun_out/bench_r2_2gpu_now.json')); print({k:d[k] for k in ('value','n_gpus','ms_per_step')}, d['e2e']['value'], {k:(v['value'],v['gather_ms_per_call']) for k,v in d['gather'].items() if isinstance(v,dict)})"
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29534 bench.py --gpus 2 --steps 2 --warmup 1 --impl reference 2>/dev/null | grep '^{' | tail -1 | cut -c1-300
+cd tests
+timeout 1200 python - <<'PY' 2>&1 | tail -5
+import sys, time
+sys.path.insert(0, '..'); sys.path.insert(0, '.')
+from fluctus_b200 import CLContext, SceneData
+from conftest import scene_blob
+from parity_util import run_lockstep
+from oracle.oracle_host import RefContext
+from bench_configs import conference_params, kitchen_params, luxball_params
+t = time.time()
+scene = SceneData.load_blob(scene_blob("conference"))
+W, H, N = 1920, 1080, 1 << 21
+with CLContext(N) as gpu:
+    tg, tc = run_lockstep(gpu, RefContext(N, parallel_trace=True), scene, conference_params(scene, W, H), iterations=12, check_every=4)
+    print("metric size, 12 iterations in lockstep with the oracle: OK", tg.stats, "%.0f s" % (time.time() - t))
+t = time.time()
+scene = SceneData.load_blob(scene_blob("luxball"))
+N = 1 << 19
+with CLContext(N) as gpu:
+    tg, tc = run_lockstep(gpu, RefContext(N, parallel_trace=True), scene, luxball_params(scene, 1280, 720), iterations=24, check_every=8)
+    print("luxball 1280x720, 2^19 paths, 24 iterations in lockstep: OK", tg.stats, "%.0f s" % (time.time() - t))
+PY
