@@ -200,6 +200,7 @@ struct flx_ctx
     int maxDynSmem = 48 * 1024;
     int occExt[3] = {0, 0, 0}, occShadow[3] = {0, 0, 0}; // resident CTAs per SM of the persistent kernels (min-blocks 8, 9, 10), asked once
     uint32_t *fetchCounters = nullptr; // [0] extension, [1] shadow, [2] microkernel nextVertex, [3] microkernel light samples
+    bool fetchClean[2] = {false, false}; // [0] / [1] were zeroed on the device by the previous iteration's k_end_iteration (flx_render)
 
     // microkernel integrator (flx_mk.cuh), allocated on first use
     uint32_t *mkScratch = nullptr;  // MK_X_SLOTS x numTasks
@@ -315,6 +316,7 @@ IterationState makeIter(const flx_ctx *c)
     IterationState it;
     it.counters = c->counters;
     it.snapshot = c->snapshot;
+    it.fetch = nullptr;
     it.stats = c->stats;
     it.currPixelIdx = c->currPixelIdx;
     it.tilePixels = c->tilePixels;
@@ -866,7 +868,10 @@ template <bool ANYHIT, class COUNT> static int launchPersistentT(flx_ctx *ctx, u
 template <bool ANYHIT> static int launchPersistent(flx_ctx *ctx)
 {
     uint32_t *fetch = ctx->fetchCounters + (ANYHIT ? 1 : 0);
-    CU(cudaMemsetAsync(fetch, 0, sizeof(uint32_t), ctx->cur));
+    if (ctx->fetchClean[ANYHIT ? 1 : 0]) // flx_render: the previous iteration's last kernel left it at zero (one memset node less per launch)
+        ctx->fetchClean[ANYHIT ? 1 : 0] = false;
+    else
+        CU(cudaMemsetAsync(fetch, 0, sizeof(uint32_t), ctx->cur));
     Timed tm(ctx, ANYHIT ? FLX_K_SHADOWRAYS : FLX_K_EXTRAYS);
     int rc = ctx->counting ? launchPersistentT<ANYHIT, RayCount>(ctx, fetch, ctx->traceCounts + (ANYHIT ? 5 : 0)) : launchPersistentT<ANYHIT, NoCount>(ctx, fetch, nullptr);
     if (rc)
@@ -992,7 +997,6 @@ static void preloadKernels()
     PRELOAD(k_material<FLX_BXDF_GGX_ROUGH_DIELECTRIC>);
     PRELOAD((k_material<FLX_BXDF_IDEAL_REFLECTION | FLX_BXDF_IDEAL_DIELECTRIC>));
     PRELOAD(k_postprocess);
-    PRELOAD(k_snapshot_counters);
     PRELOAD(k_end_iteration);
     PRELOAD(k_repack_scatter_treelet);
     PRELOAD(k_repack_flags);
@@ -2393,7 +2397,8 @@ try
                 return rc;
             CU(cudaEventRecord(ctx->evPostJoin, ctx->stream3));
         }
-        k_snapshot_counters<<<1, 32, 0, ctx->stream>>>(it);
+        // (no counter snapshot here: nothing between this point and k_end_iteration changes the queue counters -- the traversal stages only
+        //  read them -- so the end-of-iteration kernel reads them in place)
         // extension then shadow rays: the second call overlaps the first on a second stream (see flx_enqueue_shadowrays)
         if ((rc = flx_enqueue_extrays(ctx)))
             return rc;
@@ -2401,7 +2406,11 @@ try
             return rc;
         {
             Timed tm(ctx, FLX_K_END_ITERATION);
-            k_end_iteration<<<1, 32, 0, ctx->stream>>>(it);
+            IterationState itEnd = it;
+            itEnd.snapshot = it.counters;
+            itEnd.fetch = ctx->fetchCounters;
+            k_end_iteration<<<1, 32, 0, ctx->stream>>>(itEnd);
+            ctx->fetchClean[0] = ctx->fetchClean[1] = true;
         }
         if ((rc = launchCheck(ctx, "k_end_iteration")))
             return rc;

@@ -851,17 +851,12 @@ __global__ void __launch_bounds__(FLX_BLOCK) k_postprocess(const float4 *__restr
 struct IterationState
 {
     flx_QueueCounters *counters;
-    flx_QueueCounters *snapshot; // counters as they were after the material stage (enqueueGetCounters point)
+    flx_QueueCounters *snapshot; // counters as they were after the material stage (enqueueGetCounters point); may be `counters` itself
+    uint32_t *fetch;             // the two traversal kernels' queue-fetch counters, zeroed here for the next iteration (null: leave them)
     flx_RenderStats64 *stats;
     uint32_t *currPixelIdx;
     uint32_t tilePixels;
 };
-// single thread: snapshot = counters (tracer.cpp:436)
-__global__ void k_snapshot_counters(const IterationState it)
-{
-    if (threadIdx.x == 0 && blockIdx.x == 0)
-        *it.snapshot = *it.counters;
-}
 // single thread: stats += snapshot (tracer.cpp:455-462), pixelIdx advance (clcontext.cpp:891-895), clear (877-883)
 __global__ void k_end_iteration(const IterationState it)
 {
@@ -876,4 +871,6 @@ __global__ void k_end_iteration(const IterationState it)
     *it.currPixelIdx = (uint32_t)(((uint64_t)*it.currPixelIdx + c.raygenQueue) % it.tilePixels);
     flx_QueueCounters z = {0, 0, 0, 0, 0, 0, 0, 0};
     *it.counters = z;
+    if (it.fetch)
+        it.fetch[0] = it.fetch[1] = 0u;
 }
