@@ -200,6 +200,8 @@ struct flx_ctx
     int maxDynSmem = 48 * 1024;
     int occExt[3] = {0, 0, 0}, occShadow[3] = {0, 0, 0}; // resident CTAs per SM of the persistent kernels (min-blocks 8, 9, 10), asked once
     uint32_t *fetchCounters = nullptr; // [0] extension, [1] shadow, [2] microkernel nextVertex, [3] microkernel light samples
+    bool scanClean = false;        // the logic kernel's scan state was zeroed on the device by k_end_iteration (flx_render)
+    uint32_t lastLogicTiles = 0;   // tiles the most recent logic launch used (= status words it left non-zero)
     bool fetchClean[2] = {false, false}; // [0] / [1] were zeroed on the device by the previous iteration's k_end_iteration (flx_render)
 
     // microkernel integrator (flx_mk.cuh), allocated on first use
@@ -317,6 +319,9 @@ IterationState makeIter(const flx_ctx *c)
     it.counters = c->counters;
     it.snapshot = c->snapshot;
     it.fetch = nullptr;
+    it.scanTiles = nullptr;
+    it.nScanTiles = 0;
+    it.scanTicket = nullptr;
     it.stats = c->stats;
     it.currPixelIdx = c->currPixelIdx;
     it.tilePixels = c->tilePixels;
@@ -1860,8 +1865,15 @@ static int launchLogic(flx_ctx *ctx, int first_iteration, bool fused)
     const uint32_t maxId = first_iteration ? std::min(ctx->tilePixels, ctx->numTasks) : ctx->numTasks; // wf_logic.cl:45
     const uint32_t LT = ctx->logicTile == 128 ? 128u : 256u;
     const uint32_t tiles = (maxId + LT - 1) / LT;
-    CU(cudaMemsetAsync(ctx->scanTiles, 0, (size_t)tiles * sizeof(unsigned long long), ctx->stream));
-    CU(cudaMemsetAsync(ctx->scanTicket, 0, sizeof(uint32_t), ctx->stream));
+    // flx_render: the previous iteration's last kernel has zeroed every status word the previous logic launch touched, which covers this launch
+    // unless it uses more tiles (first iteration -> steady state, another tile size)
+    if (!ctx->scanClean || tiles > ctx->lastLogicTiles)
+    {
+        CU(cudaMemsetAsync(ctx->scanTiles, 0, (size_t)std::max(tiles, ctx->lastLogicTiles) * sizeof(unsigned long long), ctx->stream));
+        CU(cudaMemsetAsync(ctx->scanTicket, 0, sizeof(uint32_t), ctx->stream));
+    }
+    ctx->scanClean = false;
+    ctx->lastLogicTiles = tiles;
     ScanState scan{ctx->scanTiles, ctx->scanTicket};
     const Frame fr = makeFrame(ctx);
     const SceneView sc = makeScene(ctx);
@@ -2409,8 +2421,12 @@ try
             IterationState itEnd = it;
             itEnd.snapshot = it.counters;
             itEnd.fetch = ctx->fetchCounters;
-            k_end_iteration<<<1, 32, 0, ctx->stream>>>(itEnd);
+            itEnd.scanTiles = ctx->scanTiles;
+            itEnd.nScanTiles = ctx->lastLogicTiles;
+            itEnd.scanTicket = ctx->scanTicket;
+            k_end_iteration<<<1, 256, 0, ctx->stream>>>(itEnd);
             ctx->fetchClean[0] = ctx->fetchClean[1] = true;
+            ctx->scanClean = true;
         }
         if ((rc = launchCheck(ctx, "k_end_iteration")))
             return rc;

@@ -853,6 +853,9 @@ struct IterationState
     flx_QueueCounters *counters;
     flx_QueueCounters *snapshot; // counters as they were after the material stage (enqueueGetCounters point); may be `counters` itself
     uint32_t *fetch;             // the two traversal kernels' queue-fetch counters, zeroed here for the next iteration (null: leave them)
+    unsigned long long *scanTiles; // the logic kernel's tile status words to zero (nScanTiles of them; 0: leave them) and its ticket
+    uint32_t nScanTiles;
+    uint32_t *scanTicket;
     flx_RenderStats64 *stats;
     uint32_t *currPixelIdx;
     uint32_t tilePixels;
@@ -860,8 +863,14 @@ struct IterationState
 // single thread: stats += snapshot (tracer.cpp:455-462), pixelIdx advance (clcontext.cpp:891-895), clear (877-883)
 __global__ void k_end_iteration(const IterationState it)
 {
+    // the logic kernel's scan state (one status word per tile + the tile ticket) back to zero for the next iteration: these words and the
+    // fetch counters below were three memset nodes in front of the next iteration's kernels
+    for (uint32_t i = threadIdx.x; i < it.nScanTiles; i += blockDim.x)
+        it.scanTiles[i] = 0ull;
     if (threadIdx.x != 0 || blockIdx.x != 0)
         return;
+    if (it.scanTicket)
+        *it.scanTicket = 0u;
     const flx_QueueCounters c = *it.snapshot;
     it.stats->extensionRays += c.extensionQueue;
     it.stats->shadowRays += c.shadowQueue;
