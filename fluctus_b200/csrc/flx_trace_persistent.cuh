@@ -14,7 +14,11 @@
 //
 // Memory path (what the ncu capture of the first persistent version showed: the L1TEX tag stage, one wavefront per
 // lane per load instruction for divergent 16-byte loads, was the limiter at ~1.1 wavefronts/clk/SM):
-//   * nodes and triangles are fetched with 256-bit loads (LDG.E.256, new on sm_100): 2 wavefronts per record, not 4 / 3;
+//   * nodes and triangles are fetched with 256-bit loads (LDG.E.256, new on sm_100): 2 wavefronts per record, not 4 / 3, with L1
+//     eviction hints (inner nodes evict-last, leaf triangles evict-first, hit attributes without allocation: flx_trace.cuh);
+//   * the instruction stream (round 2, once the loads were no longer the only limiter): a lane's state IS its node reference (inner
+//     node / leaf / TR_DONE / TR_IDLE) instead of flags the compiler packs and unpacks, and a lane takes 2 (closest hit) or 3 (any hit)
+//     node steps per warp vote -- 10 % fewer issued instructions per launch, same results;
 //   * TOP variant: the hottest part of the tree -- a treelet grown from the root by always expanding the node with the
 //     largest box area, which repack_bvh lays out FIRST in the node array -- is staged once per CTA into shared memory
 //     by the bulk-copy engine (cp.async.bulk + mbarrier, SASS UBLKCP) and read with LDS.128.  On Conference a 2047-node
